@@ -1,0 +1,126 @@
+"""In-tree build of the native core (``bagua_b200/_C.so``) for sm_100a.
+
+The reference builds its Rust/C++ core for every ``sm_XX`` nvcc knows
+(rust/bagua-core/bagua-core-internal/build.rs:16-35).  This project targets exactly one
+architecture: ``-gencode arch=compute_100a,code=sm_100a``.  Sources are compiled with plain
+``nvcc``/``g++`` (no torch headers → seconds per file) and linked into one shared object that lives
+next to the python package, so it travels with the source tree.
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import shutil
+import subprocess
+import sys
+import sysconfig
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+CSRC = PKG_DIR / "csrc"
+OBJ_DIR = PKG_DIR / "csrc" / "build"
+TARGET = PKG_DIR / "_C.so"
+
+CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+NVCC = os.environ.get("NVCC", str(Path(CUDA_HOME) / "bin" / "nvcc"))
+CXX = os.environ.get("CXX", "g++")
+
+GENCODE = ["-gencode", "arch=compute_100a,code=sm_100a"]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-Wall", "-Wno-unused-function"]
+
+
+def _includes() -> list[str]:
+    import pybind11
+
+    incs = [str(CSRC), str(Path(CUDA_HOME) / "include"), pybind11.get_include(), sysconfig.get_paths()["include"]]
+    cutlass = cutlass_include()
+    if cutlass:
+        incs.append(cutlass)
+    return incs
+
+
+def cutlass_include() -> str | None:
+    """CUTLASS/CuTe header tree vendored in site-packages (used only as a header library)."""
+    for sp in sys.path:
+        cand = Path(sp) / "flashinfer" / "data" / "cutlass" / "include"
+        if (cand / "cute").is_dir():
+            return str(cand)
+    return None
+
+
+def _sources() -> list[Path]:
+    return sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cpp")))
+
+
+def _deps_stamp() -> str:
+    h = hashlib.sha1()
+    for p in sorted(list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh"))):
+        h.update(p.name.encode())
+        h.update(p.read_bytes())
+    h.update(" ".join(GENCODE + NVCC_FLAGS + CXX_FLAGS).encode())
+    return h.hexdigest()
+
+
+def _compile_one(src: Path, stamp: str, verbose: bool) -> tuple[Path, bool]:
+    obj = OBJ_DIR / (src.name + ".o")
+    meta = OBJ_DIR / (src.name + ".json")
+    key = hashlib.sha1(src.read_bytes()).hexdigest() + stamp
+    if obj.exists() and meta.exists():
+        try:
+            if json.loads(meta.read_text()).get("key") == key:
+                return obj, False
+        except Exception:
+            pass
+    incs = [f"-I{i}" for i in _includes()]
+    if src.suffix == ".cu":
+        cmd = [NVCC, *GENCODE, *NVCC_FLAGS, *incs, "-c", str(src), "-o", str(obj)]
+        if os.environ.get("BAGUA_PTXAS_VERBOSE"):
+            cmd[1:1] = ["-Xptxas", "-v"]
+    else:
+        cmd = [CXX, *CXX_FLAGS, *incs, "-c", str(src), "-o", str(obj)]
+    if verbose:
+        print("[bagua_b200 build]", " ".join(cmd), flush=True)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"compilation of {src.name} failed:\n{res.stdout}\n{res.stderr}")
+    if verbose and res.stderr.strip():
+        print(res.stderr, flush=True)
+    meta.write_text(json.dumps({"key": key}))
+    return obj, True
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile every source under csrc/ for sm_100a and link ``bagua_b200/_C.so`` (incremental)."""
+    if not Path(NVCC).exists():
+        raise RuntimeError(f"nvcc not found at {NVCC}; set CUDA_HOME")
+    OBJ_DIR.mkdir(parents=True, exist_ok=True)
+    if force:
+        shutil.rmtree(OBJ_DIR)
+        OBJ_DIR.mkdir(parents=True)
+    stamp = _deps_stamp()
+    srcs = _sources()
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        results = list(ex.map(lambda s: _compile_one(s, stamp, verbose), srcs))
+    objs = [str(o) for o, _ in results]
+    changed = any(c for _, c in results)
+    if changed or not TARGET.exists():
+        cmd = [NVCC, *GENCODE, "-shared", "-o", str(TARGET), *objs, "-lcuda" if os.environ.get("BAGUA_LINK_LIBCUDA") else "", "-ldl", "-lpthread"]
+        cmd = [c for c in cmd if c]
+        if verbose:
+            print("[bagua_b200 build]", " ".join(cmd), flush=True)
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    return TARGET
+
+
+def is_built() -> bool:
+    return TARGET.exists()
+
+
+if __name__ == "__main__":
+    path = build(force="--force" in sys.argv, verbose=True)
+    print(f"built {path}")

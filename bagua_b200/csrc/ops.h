@@ -1,0 +1,214 @@
+// PeerComm (per-group NVSwitch communicator state) and the native comm ops a bucket can run.
+//
+// Reference counterparts: BaguaSingleCommunicator (communicators/mod.rs:26-73, 474-489) and the six comm ops
+// (comm_ops/*.rs). Here a "communicator" is nothing but symmetric signal pads + an abort/timeout flag: the
+// collectives themselves are kernels (peer_kernels.cu, bytegrad_kernels.cu) that load/store peer memory.
+#pragma once
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "scheduler.h"
+
+namespace bagua {
+
+class PeerComm {
+public:
+    // flag_ptrs[p] = address (mapped in this process) of rank p's signal pad, ≥ kMaxCommBlocks*kMaxPeers*4 bytes, zeroed.
+    PeerComm(int rank, int world, int device, const std::vector<uint64_t>& flag_ptrs, double timeout_s);
+    ~PeerComm();
+    PeerComm(const PeerComm&) = delete;
+    const PeerCtx& ctx() const { return ctx_; }
+    int rank() const { return ctx_.rank; }
+    int world() const { return ctx_.world; }
+    int device() const { return device_; }
+    void abort();            // make every spinning kernel of this comm give up (ncclCommAbort analogue)
+    void reset_abort();
+    bool aborted() const;
+    int error_code();        // synchronising read of the device error word (0 ok, 1 timeout, 2 aborted, 3 grid timeout)
+    void clear_error();
+    void set_timeout(double seconds);
+    static size_t signal_pad_bytes() { return static_cast<size_t>(kMaxCommBlocks) * kMaxPeers * sizeof(uint32_t); }
+
+private:
+    PeerCtx ctx_{};
+    int device_;
+    int* abort_host_ = nullptr;
+};
+
+struct SymmBuf {
+    PeerBuf buf{};
+    size_t bytes = 0;
+    SymmBuf() = default;
+    SymmBuf(const std::vector<uint64_t>& ptrs, uint64_t mc, size_t nbytes);
+    bool has_multicast() const { return buf.mc != nullptr; }
+};
+
+struct LaunchCfg {
+    int nblocks = 32;
+    int nthreads = 512;
+};
+
+// Per-instance scratch of a quantised op (device allocations + host counters).
+class QuantScratch {
+public:
+    QuantScratch(int device, size_t reduced_elems);
+    ~QuantScratch();
+    QuantScratch(const QuantScratch&) = delete;
+    const ByteGradScratch& get() const { return s_; }
+
+private:
+    ByteGradScratch s_{};
+    unsigned long long host_state_[2] = {0, 0};
+    int device_;
+};
+
+class AllReduceOp final : public CommOp {
+public:
+    AllReduceOp(std::shared_ptr<PeerComm> comm, SymmBuf src, SymmBuf dst, size_t src_off, size_t dst_off, size_t bytes,
+                int dtype, float scale, int variant, LaunchCfg cfg)
+        : comm_(std::move(comm)), src_(src), dst_(dst), src_off_(src_off), dst_off_(dst_off), bytes_(bytes), dtype_(dtype),
+          scale_(scale), variant_(variant), cfg_(cfg) {}
+    const char* kind() const override { return variant_ == AR_MULTIMEM ? "allreduce_multimem" : "allreduce_twoshot"; }
+    void run(Bucket&, StreamHandle stream, int device) override;
+    void set_variant(int v, LaunchCfg cfg) { variant_ = v, cfg_ = cfg; }
+
+private:
+    std::shared_ptr<PeerComm> comm_;
+    SymmBuf src_, dst_;
+    size_t src_off_, dst_off_, bytes_;
+    int dtype_;
+    float scale_;
+    int variant_;
+    LaunchCfg cfg_;
+};
+
+class AllReduceOneShotOp final : public CommOp {
+public:
+    AllReduceOneShotOp(std::shared_ptr<PeerComm> comm, SymmBuf staging, size_t slot_bytes, uint64_t in, uint64_t out, size_t bytes,
+                       int dtype, float scale, LaunchCfg cfg)
+        : comm_(std::move(comm)), staging_(staging), slot_bytes_(slot_bytes), in_(in), out_(out), bytes_(bytes), dtype_(dtype),
+          scale_(scale), cfg_(cfg) {}
+    const char* kind() const override { return "allreduce_oneshot"; }
+    void run(Bucket&, StreamHandle stream, int device) override;
+
+private:
+    std::shared_ptr<PeerComm> comm_;
+    SymmBuf staging_;
+    size_t slot_bytes_;
+    uint64_t in_, out_;
+    size_t bytes_;
+    int dtype_;
+    float scale_;
+    LaunchCfg cfg_;
+};
+
+// reduce-scatter(grads) → SGD on the owned shard → all-gather(weights), one kernel per bucket.
+class AllReduceSgdOp final : public CommOp {
+public:
+    AllReduceSgdOp(std::shared_ptr<PeerComm> comm, SymmBuf grads, SymmBuf weights, size_t g_off, size_t w_off, size_t bytes, int dtype,
+                   uint64_t master, uint64_t momentum, float scale, bool zero_grads, bool use_multimem, LaunchCfg cfg)
+        : comm_(std::move(comm)), grads_(grads), weights_(weights), g_off_(g_off), w_off_(w_off), bytes_(bytes), dtype_(dtype),
+          master_(master), momentum_(momentum), scale_(scale), zero_grads_(zero_grads), use_mc_(use_multimem), cfg_(cfg) {}
+    const char* kind() const override { return "allreduce_sgd"; }
+    void run(Bucket&, StreamHandle stream, int device) override;
+    void set_hyper(float lr, float momentum, float dampening, float weight_decay, bool nesterov) {
+        std::lock_guard<std::mutex> lk(mu_);
+        hp_.lr = lr, hp_.momentum = momentum, hp_.dampening = dampening, hp_.weight_decay = weight_decay, hp_.nesterov = nesterov;
+    }
+    void set_grad_scale(float s) {
+        std::lock_guard<std::mutex> lk(mu_);
+        scale_ = s;
+    }
+    uint64_t steps() const { return steps_; }
+    void set_steps(uint64_t s) { steps_ = s; }
+
+private:
+    std::shared_ptr<PeerComm> comm_;
+    SymmBuf grads_, weights_;
+    size_t g_off_, w_off_, bytes_;
+    int dtype_;
+    uint64_t master_, momentum_;
+    float scale_;
+    bool zero_grads_, use_mc_;
+    LaunchCfg cfg_;
+    SgdParams hp_{0.01f, 0.f, 0.f, 0.f, 0, 1};
+    uint64_t steps_ = 0;
+    std::mutex mu_;
+};
+
+// Decentralized SGD, shift_one pairing (peer formula: comm_ops/decentralized_full_precision_synchronous.rs:81-85).
+class PeerAverageOp final : public CommOp {
+public:
+    PeerAverageOp(std::shared_ptr<PeerComm> comm, SymmBuf weights, size_t off, uint64_t out, size_t bytes, int dtype, LaunchCfg cfg)
+        : comm_(std::move(comm)), weights_(weights), off_(off), out_(out), bytes_(bytes), dtype_(dtype), cfg_(cfg) {}
+    const char* kind() const override { return "peer_average_shift_one"; }
+    void run(Bucket&, StreamHandle stream, int device) override;
+    static int shift_one_peer(int rank, int nranks, int64_t step);
+    int64_t step() const { return step_; }
+
+private:
+    std::shared_ptr<PeerComm> comm_;
+    SymmBuf weights_;
+    size_t off_;
+    uint64_t out_;
+    size_t bytes_;
+    int dtype_;
+    LaunchCfg cfg_;
+    int64_t step_ = 0;
+};
+
+class ByteGradOp final : public CommOp {
+public:
+    ByteGradOp(std::shared_ptr<PeerComm> comm, uint64_t data, size_t numel, int dtype, SymmBuf inbox, size_t inbox_off, SymmBuf outbox,
+               size_t outbox_off, bool average, LaunchCfg cfg);
+    const char* kind() const override { return "bytegrad_fused"; }
+    void run(Bucket&, StreamHandle stream, int device) override;
+    static size_t box_bytes(size_t numel, int nranks) { return static_cast<size_t>(nranks) * minmax_uint8_chunk_bytes(numel / nranks); }
+
+private:
+    std::shared_ptr<PeerComm> comm_;
+    uint64_t data_;
+    size_t numel_;
+    int dtype_;
+    SymmBuf inbox_, outbox_;
+    size_t inbox_off_, outbox_off_;
+    bool average_;
+    LaunchCfg cfg_;
+    std::unique_ptr<QuantScratch> scratch_;
+};
+
+class LowPrecRingOp final : public CommOp {
+public:
+    LowPrecRingOp(std::shared_ptr<PeerComm> comm, uint64_t x, uint64_t w, uint64_t l, uint64_t r, size_t numel, int dtype, SymmBuf box,
+                  size_t box_off, LaunchCfg cfg);
+    const char* kind() const override { return "low_precision_ring_fused"; }
+    void run(Bucket&, StreamHandle stream, int device) override;
+    static size_t box_bytes(size_t numel) { return 6 * minmax_uint8_chunk_bytes(numel); }
+
+private:
+    std::shared_ptr<PeerComm> comm_;
+    uint64_t x_, w_, l_, r_;
+    size_t numel_;
+    int dtype_;
+    SymmBuf box_;
+    size_t box_off_;
+    LaunchCfg cfg_;
+    std::unique_ptr<QuantScratch> scratch_;
+};
+
+// Plain device-to-device copy on the comm stream (snapshots / copy-back).
+class CopyOp final : public CommOp {
+public:
+    CopyOp(uint64_t dst, uint64_t src, size_t bytes) : dst_(dst), src_(src), bytes_(bytes) {}
+    const char* kind() const override { return "copy"; }
+    void run(Bucket&, StreamHandle stream, int device) override;
+
+private:
+    uint64_t dst_, src_;
+    size_t bytes_;
+};
+
+}  // namespace bagua

@@ -1,0 +1,368 @@
+// Fused collective kernels over NVLink 5 / NVSwitch symmetric memory (sm_100a).
+//
+// These replace the reference's "kernel + separate NCCL call" sequences
+// (rust/bagua-core/bagua-core-internal/src/comm_ops/*.rs, communicators/mod.rs:1121-1153): the reduction,
+// the averaging scale, the dtype handling, the optimizer update and the data movement to/from the peers
+// happen in ONE kernel that issues peer (P2P) or NVLS multicast loads/stores itself.
+#include "kernels.h"
+#include "peer.cuh"
+
+namespace bagua {
+using namespace dev;
+
+// ---------------------------------------------------------------------------------------------------------
+// allreduce, two-shot over peer pointers: rank r reduces slice r (reading it from every peer) and writes the
+// result into slice r of every peer. src and dst may alias (in-place): slice r is only ever read and written
+// by rank r between the two barriers.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, int P>
+__global__ void __launch_bounds__(512) allreduce_twoshot_kernel(PeerCtx ctx, PeerBuf src, PeerBuf dst, size_t src_off,
+                                                                size_t dst_off, size_t total_vecs, float scale) {
+    const uint32_t e0 = load_epoch(ctx);
+    bool ok = peer_barrier(ctx, e0 + 1);
+    if (ok) {
+        const size_t vpr = (total_vecs + P - 1) / P;
+        const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+        const size_t base = static_cast<size_t>(ctx.rank) * vpr;
+        for (size_t j = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < vpr; j += stride) {
+            const size_t v = base + j;
+            if (v >= total_vecs) break;
+            float acc[Vec16<T>::N];
+            uint4 raw[P];
+#pragma unroll
+            for (int i = 0; i < P; ++i) {
+                const int p = (ctx.rank + i) % P;  // start at self, rotate so peers' links are hit evenly
+                raw[i] = ld_peer16(src.ptr[p] + src_off + v * 16);
+            }
+            Vec16<T>::unpack(raw[0], acc);
+#pragma unroll
+            for (int i = 1; i < P; ++i) {
+                float f[Vec16<T>::N];
+                Vec16<T>::unpack(raw[i], f);
+#pragma unroll
+                for (int k = 0; k < Vec16<T>::N; ++k) acc[k] += f[k];
+            }
+#pragma unroll
+            for (int k = 0; k < Vec16<T>::N; ++k) acc[k] *= scale;
+            const uint4 out = Vec16<T>::pack(acc);
+#pragma unroll
+            for (int i = 0; i < P; ++i) {
+                const int p = (ctx.rank + i) % P;
+                st_peer16(dst.ptr[p] + dst_off + v * 16, out);
+            }
+        }
+        peer_barrier(ctx, e0 + 2);
+    }
+    store_epoch(ctx, e0 + 2);
+}
+
+// Same schedule through the switch: one multimem.ld_reduce returns the sum over all GPUs (reduced inside
+// NVSwitch), one multimem.st lands the result on all GPUs.
+template <typename T>
+__global__ void __launch_bounds__(512) allreduce_multimem_kernel(PeerCtx ctx, PeerBuf src, PeerBuf dst, size_t src_off,
+                                                                 size_t dst_off, size_t total_vecs, float scale) {
+    const uint32_t e0 = load_epoch(ctx);
+    bool ok = peer_barrier(ctx, e0 + 1);
+    if (ok) {
+        const int P = ctx.world;
+        const size_t vpr = (total_vecs + P - 1) / P;
+        const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+        const size_t base = static_cast<size_t>(ctx.rank) * vpr;
+        for (size_t j = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < vpr; j += stride) {
+            const size_t v = base + j;
+            if (v >= total_vecs) break;
+            uint4 red = multimem_ld_reduce_add<T>(src.mc + src_off + v * 16);
+            if (scale != 1.0f) {
+                float f[Vec16<T>::N];
+                Vec16<T>::unpack(red, f);
+#pragma unroll
+                for (int k = 0; k < Vec16<T>::N; ++k) f[k] *= scale;
+                red = Vec16<T>::pack(f);
+            }
+            multimem_st16(dst.mc + dst_off + v * 16, red);
+        }
+        peer_barrier(ctx, e0 + 2);
+    }
+    store_epoch(ctx, e0 + 2);
+}
+
+// One-shot, push flavour, for latency-bound messages: every rank stores its message into slot [parity][rank]
+// of every peer's staging area, ONE barrier, then reduces the P slots it received locally. The staging area is
+// double-buffered by epoch parity, so no second barrier is needed (a rank can only be two calls ahead of a peer
+// after that peer has left the call in between).
+template <typename T, int P>
+__global__ void __launch_bounds__(512) allreduce_oneshot_kernel(PeerCtx ctx, PeerBuf staging, size_t slot_bytes,
+                                                                const char* in, char* out, size_t total_vecs, float scale) {
+    const uint32_t e0 = load_epoch(ctx);
+    const size_t parity = (e0 & 1u);
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    for (size_t v = tid; v < total_vecs; v += stride) {
+        const uint4 mine = ld_stream16(in + v * 16);
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+            const int p = (ctx.rank + i) % P;
+            st_peer16(staging.ptr[p] + (parity * P + ctx.rank) * slot_bytes + v * 16, mine);
+        }
+    }
+    bool ok = peer_barrier(ctx, e0 + 1);
+    if (ok) {
+        const char* mystage = staging.ptr[ctx.rank] + parity * P * slot_bytes;
+        for (size_t v = tid; v < total_vecs; v += stride) {
+            float acc[Vec16<T>::N];
+            Vec16<T>::unpack(ld_peer16(mystage + v * 16), acc);
+#pragma unroll
+            for (int p = 1; p < P; ++p) {
+                float f[Vec16<T>::N];
+                Vec16<T>::unpack(ld_peer16(mystage + p * slot_bytes + v * 16), f);
+#pragma unroll
+                for (int k = 0; k < Vec16<T>::N; ++k) acc[k] += f[k];
+            }
+#pragma unroll
+            for (int k = 0; k < Vec16<T>::N; ++k) acc[k] *= scale;
+            st_stream16(out + v * 16, Vec16<T>::pack(acc));
+        }
+    }
+    store_epoch(ctx, e0 + 1);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Gradient reduce-scatter  →  SGD(momentum) on the owned 1/P slice  →  all-gather of the updated WEIGHTS,
+// in one kernel. Each rank keeps fp32 master weights and momentum only for its own slice (optimizer state is
+// sharded P ways), the gradient bucket is zeroed for the next iteration on the way out, and the optimizer step
+// overlaps the rest of backward because it runs inside the bucket's communication kernel.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, int P, bool USE_MC>
+__global__ void __launch_bounds__(512)
+    allreduce_sgd_kernel(PeerCtx ctx, PeerBuf grads, PeerBuf weights, size_t g_off, size_t w_off, size_t total_vecs,
+                         float* master, float* momentum_buf, SgdParams hp, float scale, int zero_grads) {
+    const uint32_t e0 = load_epoch(ctx);
+    bool ok = peer_barrier(ctx, e0 + 1);
+    constexpr int N = Vec16<T>::N;
+    const size_t vpr = (total_vecs + P - 1) / P;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (ok) {
+        const size_t base = static_cast<size_t>(ctx.rank) * vpr;
+        for (size_t j = tid; j < vpr; j += stride) {
+            const size_t v = base + j;
+            if (v >= total_vecs) break;
+            float g[N];
+            if (USE_MC) {
+                Vec16<T>::unpack(multimem_ld_reduce_add<T>(grads.mc + g_off + v * 16), g);
+            } else {
+                uint4 raw[P];
+#pragma unroll
+                for (int i = 0; i < P; ++i) raw[i] = ld_peer16(grads.ptr[(ctx.rank + i) % P] + g_off + v * 16);
+                Vec16<T>::unpack(raw[0], g);
+#pragma unroll
+                for (int i = 1; i < P; ++i) {
+                    float f[N];
+                    Vec16<T>::unpack(raw[i], f);
+#pragma unroll
+                    for (int k = 0; k < N; ++k) g[k] += f[k];
+                }
+            }
+            // optimizer state of the owned slice: index j*N within the shard
+            float w[N], m[N];
+            float4* mp = reinterpret_cast<float4*>(master + j * N);
+            float4* mo = reinterpret_cast<float4*>(momentum_buf + j * N);
+#pragma unroll
+            for (int q = 0; q < N / 4; ++q) {
+                float4 a = mp[q];
+                w[4 * q] = a.x, w[4 * q + 1] = a.y, w[4 * q + 2] = a.z, w[4 * q + 3] = a.w;
+                if (hp.momentum != 0.f) {
+                    float4 b = mo[q];
+                    m[4 * q] = b.x, m[4 * q + 1] = b.y, m[4 * q + 2] = b.z, m[4 * q + 3] = b.w;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                float d = g[k] * scale + hp.weight_decay * w[k];
+                if (hp.momentum != 0.f) {
+                    m[k] = hp.first_step ? d : hp.momentum * m[k] + (1.f - hp.dampening) * d;
+                    d = hp.nesterov ? d + hp.momentum * m[k] : m[k];
+                }
+                w[k] -= hp.lr * d;
+            }
+#pragma unroll
+            for (int q = 0; q < N / 4; ++q) {
+                mp[q] = make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+                if (hp.momentum != 0.f) mo[q] = make_float4(m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
+            }
+            const uint4 out = Vec16<T>::pack(w);
+            if (USE_MC) {
+                multimem_st16(weights.mc + w_off + v * 16, out);
+            } else {
+#pragma unroll
+                for (int i = 0; i < P; ++i) st_peer16(weights.ptr[(ctx.rank + i) % P] + w_off + v * 16, out);
+            }
+        }
+        ok = peer_barrier(ctx, e0 + 2);
+    }
+    if (ok && zero_grads) {
+        // Block b of every peer has finished reading column-range b of all my slices: safe to clear them.
+        char* mine = grads.ptr[ctx.rank] + g_off;
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        for (size_t j = tid; j < vpr; j += stride) {
+#pragma unroll
+            for (int s = 0; s < P; ++s) {
+                const size_t v = static_cast<size_t>(s) * vpr + j;
+                if (v < total_vecs) st_stream16(mine + v * 16, z);
+            }
+        }
+    }
+    store_epoch(ctx, e0 + 2);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Decentralized SGD, shift_one: out = (mine + peer's weights) / 2, the peer's bucket being read straight over
+// NVLink (replaces grouped send/recv + average kernel, comm_ops/decentralized_full_precision_synchronous.rs:81-92).
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(512)
+    peer_average_kernel(PeerCtx ctx, PeerBuf weights, size_t off, int peer, char* out, size_t total_vecs) {
+    const uint32_t e0 = load_epoch(ctx);
+    bool ok = peer_barrier(ctx, e0 + 1);
+    if (ok) {
+        const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+        const char* mine = weights.ptr[ctx.rank] + off;
+        const char* theirs = weights.ptr[peer] + off;
+        for (size_t v = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < total_vecs; v += stride) {
+            float a[Vec16<T>::N], b[Vec16<T>::N];
+            const uint4 rb = ld_peer16(theirs + v * 16);
+            Vec16<T>::unpack(ld_stream16(mine + v * 16), a);
+            Vec16<T>::unpack(rb, b);
+#pragma unroll
+            for (int k = 0; k < Vec16<T>::N; ++k) a[k] = (a[k] + b[k]) * 0.5f;
+            st_stream16(out + v * 16, Vec16<T>::pack(a));
+        }
+        // nobody may overwrite its weights (copy-back / optimizer step) before every reader is done
+        peer_barrier(ctx, e0 + 2);
+    }
+    store_epoch(ctx, e0 + 2);
+}
+
+// A bare cross-GPU barrier (1 CTA) — used for arena hand-over and by tests.
+__global__ void peer_barrier_kernel(PeerCtx ctx) {
+    const uint32_t e0 = load_epoch(ctx);
+    peer_barrier(ctx, e0 + 1);
+    store_epoch(ctx, e0 + 1);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+template <typename F>
+void dispatch_world(int world, F&& f) {
+    switch (world) {
+        case 1: f(std::integral_constant<int, 1>{}); break;
+        case 2: f(std::integral_constant<int, 2>{}); break;
+        case 3: f(std::integral_constant<int, 3>{}); break;
+        case 4: f(std::integral_constant<int, 4>{}); break;
+        case 5: f(std::integral_constant<int, 5>{}); break;
+        case 6: f(std::integral_constant<int, 6>{}); break;
+        case 7: f(std::integral_constant<int, 7>{}); break;
+        case 8: f(std::integral_constant<int, 8>{}); break;
+        default: throw std::runtime_error("bagua: peer kernels support 1..8 ranks, got " + std::to_string(world));
+    }
+}
+template <typename F>
+void dispatch_float(int dtype, F&& f) {
+    switch (dtype) {
+        case F32: f(float{}); break;
+        case F16: f(__half{}); break;
+        case BF16: f(__nv_bfloat16{}); break;
+        default: throw std::runtime_error("bagua: peer reduction kernels need f32/f16/bf16, got dtype code " + std::to_string(dtype));
+    }
+}
+void check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw std::runtime_error(std::string("bagua: launch of ") + what + " failed: " + cudaGetErrorString(e));
+}
+void check_blocks(int nblocks) {
+    if (nblocks < 1 || nblocks > kMaxCommBlocks) throw std::runtime_error("bagua: peer kernel grid must be 1.." + std::to_string(kMaxCommBlocks));
+}
+}  // namespace
+
+void launch_allreduce(const PeerCtx& ctx, const PeerBuf& src, const PeerBuf& dst, size_t src_off, size_t dst_off,
+                      size_t bytes, int dtype, float scale, int variant, int nblocks, int nthreads, cudaStream_t stream) {
+    if (bytes % 16 || src_off % 16 || dst_off % 16) throw std::runtime_error("bagua: allreduce needs 16-byte aligned size/offsets");
+    check_blocks(nblocks);
+    const size_t vecs = bytes / 16;
+    if (vecs == 0) return;
+    dispatch_float(dtype, [&](auto tag) {
+        using T = decltype(tag);
+        if (variant == AR_MULTIMEM) {
+            if (!src.mc || !dst.mc) throw std::runtime_error("bagua: multimem allreduce requested but no multicast mapping");
+            allreduce_multimem_kernel<T><<<nblocks, nthreads, 0, stream>>>(ctx, src, dst, src_off, dst_off, vecs, scale);
+        } else {
+            dispatch_world(ctx.world, [&](auto pw) {
+                constexpr int P = decltype(pw)::value;
+                allreduce_twoshot_kernel<T, P><<<nblocks, nthreads, 0, stream>>>(ctx, src, dst, src_off, dst_off, vecs, scale);
+            });
+        }
+    });
+    check_launch("allreduce");
+}
+
+void launch_allreduce_oneshot(const PeerCtx& ctx, const PeerBuf& staging, size_t slot_bytes, const void* in, void* out,
+                              size_t bytes, int dtype, float scale, int nblocks, int nthreads, cudaStream_t stream) {
+    if (bytes % 16) throw std::runtime_error("bagua: one-shot allreduce needs a 16-byte multiple");
+    if (bytes > slot_bytes) throw std::runtime_error("bagua: one-shot allreduce message larger than its staging slot");
+    check_blocks(nblocks);
+    const size_t vecs = bytes / 16;
+    if (vecs == 0) return;
+    dispatch_float(dtype, [&](auto tag) {
+        using T = decltype(tag);
+        dispatch_world(ctx.world, [&](auto pw) {
+            constexpr int P = decltype(pw)::value;
+            allreduce_oneshot_kernel<T, P><<<nblocks, nthreads, 0, stream>>>(
+                ctx, staging, slot_bytes, static_cast<const char*>(in), static_cast<char*>(out), vecs, scale);
+        });
+    });
+    check_launch("allreduce_oneshot");
+}
+
+void launch_allreduce_sgd(const PeerCtx& ctx, const PeerBuf& grads, const PeerBuf& weights, size_t g_off, size_t w_off,
+                          size_t bytes, int dtype, float* master, float* momentum, const SgdParams& hp, float scale,
+                          bool zero_grads, bool use_multimem, int nblocks, int nthreads, cudaStream_t stream) {
+    if (bytes % 16 || g_off % 16 || w_off % 16) throw std::runtime_error("bagua: allreduce_sgd needs 16-byte aligned size/offsets");
+    check_blocks(nblocks);
+    const size_t vecs = bytes / 16;
+    if (vecs == 0) return;
+    dispatch_float(dtype, [&](auto tag) {
+        using T = decltype(tag);
+        dispatch_world(ctx.world, [&](auto pw) {
+            constexpr int P = decltype(pw)::value;
+            if (use_multimem)
+                allreduce_sgd_kernel<T, P, true><<<nblocks, nthreads, 0, stream>>>(ctx, grads, weights, g_off, w_off, vecs, master,
+                                                                                 momentum, hp, scale, zero_grads ? 1 : 0);
+            else
+                allreduce_sgd_kernel<T, P, false><<<nblocks, nthreads, 0, stream>>>(ctx, grads, weights, g_off, w_off, vecs, master,
+                                                                                  momentum, hp, scale, zero_grads ? 1 : 0);
+        });
+    });
+    check_launch("allreduce_sgd");
+}
+
+void launch_peer_average(const PeerCtx& ctx, const PeerBuf& weights, size_t off, int peer, void* out, size_t bytes, int dtype,
+                         int nblocks, int nthreads, cudaStream_t stream) {
+    if (bytes % 16 || off % 16) throw std::runtime_error("bagua: peer_average needs 16-byte aligned size/offset");
+    if (peer < 0 || peer >= ctx.world) throw std::runtime_error("bagua: peer_average peer rank out of range");
+    check_blocks(nblocks);
+    const size_t vecs = bytes / 16;
+    dispatch_float(dtype, [&](auto tag) {
+        using T = decltype(tag);
+        peer_average_kernel<T><<<nblocks, nthreads, 0, stream>>>(ctx, weights, off, peer, static_cast<char*>(out), vecs);
+    });
+    check_launch("peer_average");
+}
+
+void launch_peer_barrier(const PeerCtx& ctx, cudaStream_t stream) {
+    peer_barrier_kernel<<<1, 32, 0, stream>>>(ctx);
+    check_launch("peer_barrier");
+}
+
+}  // namespace bagua
