@@ -1,0 +1,860 @@
+"""Process groups, communicators and the blocking collective API.
+
+Capability parity with ``bagua/torch_api/communication.py`` of the reference (init_process_group :446-548,
+new_group :206-273, from_torch_group :279-309, the 20 blocking collectives :573-1401, ReduceOp :64-75).
+
+B200-first design:
+
+* one process per GPU; ``torch.distributed`` (NCCL on GPUs, gloo on CPU) is the *plumbing*: rendezvous, object
+  exchange, the cold user-facing primitives and the fallback for every op.  The reference is GPU/NCCL only
+  (communication.py:540-546, :585); the gloo path lets the whole engine run and be tested without a GPU.
+* the *hot* paths (bucket allreduce, ByteGrad, decentralized averaging, MoE dispatch) do not go through this
+  file at all: they are sm_100a kernels over NVSwitch symmetric memory owned by :class:`PeerEngine`
+  (``bagua_b200/parallel/symm.py``), reached through ``BaguaProcessGroup.peer_engine()``.
+* a communicator is (torch ProcessGroup, comm stream); blocking collectives keep the reference's stream
+  protocol: current stream → event → comm stream runs the op → host waits for the comm stream.
+"""
+from __future__ import annotations
+
+import io
+import logging
+import os
+import pickle
+import threading
+import weakref
+from enum import IntEnum
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import env
+
+__all__ = [
+    "ReduceOp",
+    "BaguaProcessGroup",
+    "Communicator",
+    "init_process_group",
+    "is_initialized",
+    "new_group",
+    "from_torch_group",
+    "send",
+    "recv",
+    "broadcast",
+    "broadcast_coalesced",
+    "broadcast_object",
+    "reduce",
+    "reduce_inplace",
+    "allreduce",
+    "allreduce_inplace",
+    "allreduce_coalesced_inplace",
+    "allgather",
+    "allgather_inplace",
+    "gather",
+    "gather_inplace",
+    "scatter",
+    "scatter_inplace",
+    "reduce_scatter",
+    "reduce_scatter_inplace",
+    "alltoall",
+    "alltoall_inplace",
+    "alltoall_v",
+    "alltoall_v_inplace",
+    "barrier",
+]
+
+logger = logging.getLogger(__name__)
+
+
+class ReduceOp(IntEnum):
+    """Reduction operations; numbering identical to the reference (communication.py:64-75)."""
+
+    SUM = 0
+    PRODUCT = 1
+    MIN = 2
+    MAX = 3
+    BOR = 7
+    BAND = 8
+    BXOR = 9
+    AVG = 10
+
+
+_TORCH_OP = {
+    ReduceOp.SUM: dist.ReduceOp.SUM,
+    ReduceOp.PRODUCT: dist.ReduceOp.PRODUCT,
+    ReduceOp.MIN: dist.ReduceOp.MIN,
+    ReduceOp.MAX: dist.ReduceOp.MAX,
+    ReduceOp.BOR: dist.ReduceOp.BOR,
+    ReduceOp.BAND: dist.ReduceOp.BAND,
+    ReduceOp.BXOR: dist.ReduceOp.BXOR,
+}
+
+
+def _use_cuda() -> bool:
+    return torch.cuda.is_available() and os.environ.get("BAGUA_FORCE_CPU", "0") != "1"
+
+
+def _device_index() -> int:
+    return torch.cuda.current_device() if _use_cuda() else -1
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# communicator
+# ---------------------------------------------------------------------------------------------------------------
+class Communicator:
+    """A (torch ProcessGroup, comm stream) pair with the collective methods of the reference's
+    ``BaguaSingleCommunicatorPy`` (rust/bagua-core/bagua-core-py/src/lib.rs:43-236)."""
+
+    def __init__(self, pg: Optional[dist.ProcessGroup], ranks: Sequence[int], stream, scope: str = "global", owner=None):
+        self.pg = pg
+        self.ranks = list(ranks)
+        self.cuda_stream = stream
+        self.scope = scope
+        self._aborted = False
+        self._owner = weakref.ref(owner) if owner is not None else None
+        self._global_rank = dist.get_rank() if dist.is_initialized() else 0
+
+    # -- identity ------------------------------------------------------------------------------------------
+    def rank(self) -> int:
+        return self.ranks.index(self._global_rank) if self._global_rank in self.ranks else -1
+
+    def nranks(self) -> int:
+        return len(self.ranks)
+
+    def device_id(self) -> int:
+        return _device_index()
+
+    def abort(self):
+        """Unblock in-flight peer kernels of this group (ncclCommAbort analogue, reference mod.rs:474-489)."""
+        self._aborted = True
+        owner = self._owner() if self._owner else None
+        if owner is not None and owner._peer_engine is not None:
+            owner._peer_engine.comm.abort()
+
+    def check_abort(self) -> bool:
+        return self._aborted
+
+    def _global(self, group_rank: int) -> int:
+        return self.ranks[group_rank]
+
+    # -- helpers -------------------------------------------------------------------------------------------
+    def _reduce_op(self, op):
+        op = ReduceOp(int(op))
+        if op == ReduceOp.AVG:
+            return None
+        return _TORCH_OP[op]
+
+    def _finish_avg(self, tensor: torch.Tensor, op):
+        if ReduceOp(int(op)) == ReduceOp.AVG:
+            # AVG divides by the communicator size, not the world size
+            if tensor.is_floating_point():
+                tensor.div_(self.nranks())
+            else:
+                tensor.copy_(torch.div(tensor, self.nranks(), rounding_mode="floor"))
+
+    # -- collectives (all in group-rank space like the reference) --------------------------------------------
+    def send(self, tensor, dst: int):
+        dist.send(tensor, self._global(dst), group=self.pg)
+
+    def recv(self, tensor, src: int):
+        dist.recv(tensor, self._global(src), group=self.pg)
+
+    def broadcast(self, tensor, src: int = 0):
+        dist.broadcast(tensor, self._global(src), group=self.pg)
+
+    def reduce(self, send_tensor, recv_tensor, dst: int, op=ReduceOp.SUM):
+        buf = send_tensor.clone()
+        self.reduce_inplace(buf, dst, op)
+        if self.rank() == dst:
+            recv_tensor.copy_(buf)
+
+    def reduce_inplace(self, tensor, dst: int, op=ReduceOp.SUM):
+        top = self._reduce_op(op)
+        dist.reduce(tensor, self._global(dst), op=top if top is not None else dist.ReduceOp.SUM, group=self.pg)
+        if self.rank() == dst:
+            self._finish_avg(tensor, op)
+
+    def allreduce(self, send_tensor, recv_tensor, op=ReduceOp.SUM):
+        if recv_tensor.data_ptr() != send_tensor.data_ptr():
+            recv_tensor.copy_(send_tensor)
+        self.allreduce_inplace(recv_tensor, op)
+
+    def allreduce_inplace(self, tensor, op=ReduceOp.SUM):
+        top = self._reduce_op(op)
+        dist.all_reduce(tensor, op=top if top is not None else dist.ReduceOp.SUM, group=self.pg)
+        self._finish_avg(tensor, op)
+
+    def allgather(self, send_tensor, recv_tensor):
+        n = self.nranks()
+        assert recv_tensor.numel() == send_tensor.numel() * n, "allgather: recv must hold nranks * send elements"
+        dist.all_gather_into_tensor(recv_tensor.view(-1), send_tensor.contiguous().view(-1), group=self.pg) if _supports_into_tensor(
+            self.pg, send_tensor
+        ) else _allgather_list(self, send_tensor, recv_tensor)
+
+    def allgather_inplace(self, tensor):
+        n = self.nranks()
+        assert tensor.numel() % n == 0, "allgather_inplace: tensor size must be divisible by nranks"
+        chunk = tensor.view(-1).chunk(n)[self.rank()].clone()
+        self.allgather(chunk, tensor)
+
+    def gather(self, send_tensor, recv_tensor, dst: int):
+        n = self.nranks()
+        if self.rank() == dst:
+            outs = list(recv_tensor.view(-1).chunk(n))
+            tmp = [torch.empty_like(send_tensor.view(-1)) for _ in range(n)]
+            dist.gather(send_tensor.contiguous().view(-1), tmp, dst=self._global(dst), group=self.pg)
+            for o, t in zip(outs, tmp):
+                o.copy_(t)
+        else:
+            dist.gather(send_tensor.contiguous().view(-1), None, dst=self._global(dst), group=self.pg)
+
+    def gather_inplace(self, tensor, count: int, dst: int):
+        chunk = tensor.view(-1)[self.rank() * count : (self.rank() + 1) * count].clone() if self.rank() == dst else tensor.view(-1)[:count].clone()
+        if self.rank() == dst:
+            self.gather(chunk, tensor.view(-1)[: count * self.nranks()], dst)
+        else:
+            self.gather(chunk, tensor, dst)
+
+    def scatter(self, send_tensor, recv_tensor, src: int):
+        n = self.nranks()
+        if self.rank() == src:
+            ins = [c.contiguous() for c in send_tensor.view(-1).chunk(n)]
+            dist.scatter(recv_tensor.view(-1), ins, src=self._global(src), group=self.pg)
+        else:
+            dist.scatter(recv_tensor.view(-1), None, src=self._global(src), group=self.pg)
+
+    def scatter_inplace(self, tensor, count: int, src: int):
+        out = torch.empty(count, dtype=tensor.dtype, device=tensor.device)
+        self.scatter(tensor.view(-1)[: count * self.nranks()] if self.rank() == src else tensor, out, src)
+        tensor.view(-1)[:count].copy_(out)
+
+    def reduce_scatter(self, send_tensor, recv_tensor, op=ReduceOp.SUM):
+        n = self.nranks()
+        assert send_tensor.numel() == recv_tensor.numel() * n, "reduce_scatter: send must hold nranks * recv elements"
+        top = self._reduce_op(op)
+        top = top if top is not None else dist.ReduceOp.SUM
+        try:
+            dist.reduce_scatter_tensor(recv_tensor.view(-1), send_tensor.contiguous().view(-1), op=top, group=self.pg)
+        except (RuntimeError, NotImplementedError):
+            # gloo has no reduce_scatter: allreduce a copy and keep the own slice
+            buf = send_tensor.clone().view(-1)
+            dist.all_reduce(buf, op=top, group=self.pg)
+            recv_tensor.view(-1).copy_(buf.chunk(n)[self.rank()])
+        self._finish_avg(recv_tensor, op)
+
+    def reduce_scatter_inplace(self, tensor, op=ReduceOp.SUM):
+        n = self.nranks()
+        out = torch.empty(tensor.numel() // n, dtype=tensor.dtype, device=tensor.device)
+        self.reduce_scatter(tensor, out, op)
+        tensor.view(-1)[: out.numel()].copy_(out)
+
+    def alltoall(self, send_tensor, recv_tensor):
+        try:
+            dist.all_to_all_single(recv_tensor.view(-1), send_tensor.contiguous().view(-1), group=self.pg)
+        except (RuntimeError, NotImplementedError):
+            _alltoall_p2p(self, send_tensor, recv_tensor)
+
+    def alltoall_inplace(self, tensor):
+        self.alltoall(tensor.clone(), tensor)
+
+    def alltoall_v(self, send_tensor, send_counts, send_displs, recv_tensor, recv_counts, recv_displs):
+        n = self.nranks()
+        sends = [send_tensor.view(-1)[send_displs[i] : send_displs[i] + send_counts[i]].contiguous() for i in range(n)]
+        recvs = [torch.empty(recv_counts[i], dtype=recv_tensor.dtype, device=recv_tensor.device) for i in range(n)]
+        try:
+            dist.all_to_all(recvs, sends, group=self.pg)
+        except (RuntimeError, NotImplementedError):
+            _alltoall_list_p2p(self, sends, recvs)
+        flat = recv_tensor.view(-1)
+        for i in range(n):
+            flat[recv_displs[i] : recv_displs[i] + recv_counts[i]].copy_(recvs[i])
+
+    def alltoall_v_inplace(self, tensor, counts, displs):
+        self.alltoall_v(tensor.clone(), counts, displs, tensor, counts, displs)
+
+    def barrier(self):
+        # the reference's barrier is a 1-element allreduce (communication.py:1396-1398)
+        t = torch.zeros(1, device="cuda" if _use_cuda() else "cpu")
+        dist.all_reduce(t, group=self.pg)
+
+
+def _supports_into_tensor(pg, tensor) -> bool:
+    return True
+
+
+def _allgather_list(comm: Communicator, send_tensor, recv_tensor):
+    outs = [torch.empty_like(send_tensor.view(-1)) for _ in range(comm.nranks())]
+    dist.all_gather(outs, send_tensor.contiguous().view(-1), group=comm.pg)
+    for o, c in zip(outs, recv_tensor.view(-1).chunk(comm.nranks())):
+        c.copy_(o)
+
+
+def _alltoall_list_p2p(comm: Communicator, sends: List[torch.Tensor], recvs: List[torch.Tensor]):
+    me = comm.rank()
+    recvs[me].copy_(sends[me])
+    reqs = []
+    for p in range(comm.nranks()):
+        if p == me:
+            continue
+        reqs.append(dist.isend(sends[p], comm._global(p), group=comm.pg))
+        reqs.append(dist.irecv(recvs[p], comm._global(p), group=comm.pg))
+    for r in reqs:
+        r.wait()
+
+
+def _alltoall_p2p(comm: Communicator, send_tensor, recv_tensor):
+    n = comm.nranks()
+    sends = [c.contiguous() for c in send_tensor.view(-1).chunk(n)]
+    recvs = [torch.empty_like(s) for s in sends]
+    _alltoall_list_p2p(comm, sends, recvs)
+    for c, r in zip(recv_tensor.view(-1).chunk(n), recvs):
+        c.copy_(r)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# process groups
+# ---------------------------------------------------------------------------------------------------------------
+class BaguaProcessGroup:
+    """A set of ranks + the comm stream their collectives run on (reference communication.py:108-148).
+
+    Communicators are created lazily: ``global`` (all ranks of the group), ``intra`` (ranks of the group on this
+    node) and ``inter`` (ranks of the group with this process's local rank, one per node)."""
+
+    def __init__(self, ranks: Sequence[int], stream, group_name: str, torch_pg: Optional[dist.ProcessGroup] = None):
+        self.ranks = list(ranks)
+        self.stream = stream
+        self.group_name = group_name
+        self._torch_pg = torch_pg
+        self._comms: Dict[str, Communicator] = {}
+        self._peer_engine = None
+        self._peer_engine_failed = False
+        self._lock = threading.Lock()
+        mapping = _get_rank_mappings()
+        node_of = {r: mapping[r][0] for r in self.ranks if r in mapping}
+        local_of = {r: mapping[r][1] for r in self.ranks if r in mapping}
+        me = dist.get_rank() if dist.is_initialized() else 0
+        self.intra_ranks = [r for r in self.ranks if node_of.get(r) == node_of.get(me, env.get_node_rank())] or [me]
+        self.inter_ranks = [r for r in self.ranks if local_of.get(r) == local_of.get(me, env.get_local_rank())] or [me]
+        self.nnodes = len(set(node_of.values())) if node_of else 1
+
+    # torch ProcessGroup accessors ----------------------------------------------------------------------------
+    def _pg_for(self, scope: str) -> Optional[dist.ProcessGroup]:
+        if scope == "global":
+            return self._torch_pg
+        ranks = self.intra_ranks if scope == "intra" else self.inter_ranks
+        if ranks == self.ranks:
+            return self._torch_pg
+        key = (scope, tuple(ranks))
+        pg = _subgroup_cache.get(key)
+        if pg is None:
+            pg = dist.new_group(ranks=ranks, use_local_synchronization=True)
+            _subgroup_cache[key] = pg
+        return pg
+
+    def _get(self, scope: str) -> Communicator:
+        with self._lock:
+            c = self._comms.get(scope)
+            if c is None:
+                ranks = {"global": self.ranks, "intra": self.intra_ranks, "inter": self.inter_ranks}[scope]
+                c = Communicator(self._pg_for(scope), ranks, self.stream, scope, owner=self)
+                self._comms[scope] = c
+            return c
+
+    def get_global_communicator(self) -> Communicator:
+        return self._get("global")
+
+    def get_inter_node_communicator(self) -> Communicator:
+        return self._get("inter")
+
+    def get_intra_node_communicator(self) -> Communicator:
+        return self._get("intra")
+
+    @property
+    def torch_group(self) -> Optional[dist.ProcessGroup]:
+        return self._torch_pg
+
+    def rank(self) -> int:
+        return self.get_global_communicator().rank()
+
+    def size(self) -> int:
+        return len(self.ranks)
+
+    # NVSwitch symmetric-memory engine ---------------------------------------------------------------------------
+    def peer_engine(self):
+        """The :class:`~bagua_b200.parallel.symm.PeerEngine` of this group, or ``None`` when the group cannot use
+        peer kernels (CPU, multi-node, > 8 ranks, BAGUA_ALLREDUCE_VARIANT=nccl, or symmetric memory unavailable)."""
+        if self._peer_engine is not None or self._peer_engine_failed:
+            return self._peer_engine
+        from .parallel import symm
+
+        with self._lock:
+            if self._peer_engine is None and not self._peer_engine_failed:
+                try:
+                    self._peer_engine = symm.PeerEngine.create(self)
+                except Exception as e:  # noqa: BLE001
+                    logger.warning("bagua_b200: peer (NVSwitch) engine unavailable for group %s: %s", self.group_name, e)
+                    self._peer_engine = None
+                if self._peer_engine is None:
+                    self._peer_engine_failed = True
+        return self._peer_engine
+
+
+_subgroup_cache: Dict[tuple, dist.ProcessGroup] = {}
+_default_pg: Optional[BaguaProcessGroup] = None
+_group_count = 0
+_rank_mappings: Optional[Dict[int, tuple]] = None
+_pg_map: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+_autotune_server = None
+_autotune_service_port = None
+_backends: Dict[str, object] = {}
+
+
+def _get_rank_mappings() -> Dict[int, tuple]:
+    """global rank → (node_rank, local_rank), gathered once (reference communication.py:151-163)."""
+    global _rank_mappings
+    if _rank_mappings is not None:
+        return _rank_mappings
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        _rank_mappings = {0: (env.get_node_rank(), env.get_local_rank())}
+        return _rank_mappings
+    objs: List[object] = [None] * dist.get_world_size()
+    dist.all_gather_object(objs, (env.get_node_rank(), env.get_local_rank()))
+    _rank_mappings = {r: tuple(o) for r, o in enumerate(objs)}
+    return _rank_mappings
+
+
+def is_initialized() -> bool:
+    """Whether :func:`init_process_group` has been called."""
+    return _default_pg is not None
+
+
+def _get_default_group() -> BaguaProcessGroup:
+    if _default_pg is None:
+        raise RuntimeError("Default process group has not been initialized, please make sure to call init_process_group.")
+    return _default_pg
+
+
+def _rank_not_in_group(group: Optional[BaguaProcessGroup]) -> bool:
+    if group is None:
+        return False
+    return dist.get_rank() not in group.ranks
+
+
+def _make_stream(priority_high: bool = True):
+    if not _use_cuda():
+        return None
+    return torch.cuda.Stream(priority=-1 if priority_high else 0)
+
+
+def new_group(ranks: Optional[Sequence[int]] = None, stream=None) -> BaguaProcessGroup:
+    """Create a new process group over ``ranks`` (default: all) whose collectives run on ``stream``.
+
+    Must be entered by all processes of the job, in the same order (reference communication.py:206-273)."""
+    global _group_count
+    if not dist.is_initialized():
+        raise RuntimeError("torch.distributed is not initialized; call bagua_b200.init_process_group() first")
+    world = dist.get_world_size()
+    if ranks is None:
+        ranks = list(range(world))
+    ranks = sorted(int(r) for r in ranks)
+    if len(ranks) == 0 or len(ranks) > world or any(r < 0 or r >= world for r in ranks):
+        raise ValueError(f"invalid ranks {ranks} for a world of {world}")
+    group_name = str(_group_count)
+    _group_count += 1
+    torch_pg = dist.new_group(ranks=ranks) if len(ranks) != world or _group_count > 1 else dist.group.WORLD
+    if stream is None:
+        stream = _make_stream()
+    pg = BaguaProcessGroup(ranks, stream, group_name, torch_pg)
+    return pg
+
+
+def from_torch_group(group: dist.ProcessGroup, stream=None) -> BaguaProcessGroup:
+    """Wrap an existing ``torch.distributed`` group (reference communication.py:279-309)."""
+    global _group_count
+    cached = _pg_map.get(group)
+    if cached is not None and (stream is None or cached.stream is stream):
+        return cached
+    ranks = sorted(dist.get_process_group_ranks(group))
+    group_name = f"torch{_group_count}"
+    _group_count += 1
+    pg = BaguaProcessGroup(ranks, stream if stream is not None else _make_stream(), group_name, group)
+    try:
+        _pg_map[group] = pg
+    except TypeError:
+        pass
+    return pg
+
+
+def _patch_torch_process_group():
+    """``ProcessGroup.bagua_patch / bagua_pg / bagua_get_*_communicator`` (reference communication.py:78-105)."""
+
+    def bagua_patch(self, stream=None):
+        from_torch_group(self, stream)
+        return self
+
+    def bagua_pg(self):
+        return from_torch_group(self)
+
+    dist.ProcessGroup.bagua_patch = bagua_patch
+    dist.ProcessGroup.bagua_pg = property(bagua_pg)
+    dist.ProcessGroup.bagua_get_global_communicator = lambda self: from_torch_group(self).get_global_communicator()
+    dist.ProcessGroup.bagua_get_inter_node_communicator = lambda self: from_torch_group(self).get_inter_node_communicator()
+    dist.ProcessGroup.bagua_get_intra_node_communicator = lambda self: from_torch_group(self).get_intra_node_communicator()
+
+
+def get_backend(model_name: str):
+    """One native scheduler (worker thread + ordered bucket list) per module name
+    (reference communication.py:377-381), so several models can train in one process."""
+    from .core import native
+
+    be = _backends.get(model_name)
+    if be is None:
+        pg = _get_default_group()
+        dev = _device_index()
+        stream = pg.stream.cuda_stream if (dev >= 0 and pg.stream is not None) else 0
+        be = native().Backend(100, dev, stream, env.get_comm_timeout_s())
+        _backends[model_name] = be
+    return be
+
+
+def _shutdown_backends():
+    for be in list(_backends.values()):
+        try:
+            be.shutdown()
+        except Exception:  # noqa: BLE001
+            pass
+    _backends.clear()
+
+
+def get_autotune_service_port() -> Optional[int]:
+    return _autotune_service_port
+
+
+def _start_autotune_server(world_size: int):
+    """Rank 0 hosts the autotune HTTP service in a daemon process (reference communication.py:384-443)."""
+    global _autotune_server, _autotune_service_port
+    from .service.autotune_service import start_autotune_server_process
+
+    store = dist.distributed_c10d._get_default_store()
+    if dist.get_rank() == 0:
+        port = env.get_bagua_service_port()
+        if port <= 0:
+            port = env.find_free_network_port()
+        _autotune_server = start_autotune_server_process(port, world_size)
+        store.set("bagua_autotune_service_port", str(port))
+    _autotune_service_port = int(store.get("bagua_autotune_service_port"))
+    os.environ.setdefault("AUTO_TUNE_SERVER_ADDR", f"{env.get_master_addr()}:{_autotune_service_port}")
+    from .service.autotune_service import AutotuneClient
+
+    client = AutotuneClient(env.get_master_addr(), _autotune_service_port)
+    import time
+
+    deadline = time.time() + max(30, env.get_autotune_server_wait_time())
+    while time.time() < deadline:
+        if client.health_check():
+            return
+        time.sleep(0.2)
+    raise RuntimeError("autotune service did not come up in time")
+
+
+def init_process_group(store=None, rank: int = -1, world_size: int = -1, local_world_size: int = -1):
+    """Initialise the default process group (reference communication.py:446-548).
+
+    ``store is None`` → ``env://`` rendezvous (``MASTER_ADDR``/``MASTER_PORT``/``RANK``/``WORLD_SIZE``); otherwise the
+    given c10d store with explicit ``rank``/``world_size``/``local_world_size``.  Backend is NCCL when a GPU is
+    visible and gloo otherwise."""
+    global _default_pg, _rank_mappings
+    if _default_pg is not None:
+        raise RuntimeError("trying to initialize the default process group twice!")
+    if store is not None:
+        assert rank >= 0 and world_size > 0 and local_world_size > 0, "rank, world_size and local_world_size are required with a store"
+        os.environ["RANK"] = str(rank)
+        os.environ["WORLD_SIZE"] = str(world_size)
+        os.environ["LOCAL_WORLD_SIZE"] = str(local_world_size)
+        os.environ.setdefault("LOCAL_RANK", str(rank % local_world_size))
+    backend = "nccl" if _use_cuda() else "gloo"
+    if not dist.is_initialized():
+        kwargs = {}
+        if backend == "nccl":
+            kwargs["device_id"] = torch.device("cuda", torch.cuda.current_device())
+        if store is not None:
+            dist.init_process_group(backend=backend, store=store, rank=rank, world_size=world_size, **kwargs)
+        else:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29500")
+            dist.init_process_group(backend=backend, init_method="env://", rank=env.get_rank(), world_size=env.get_world_size(), **kwargs)
+    _rank_mappings = None
+    _patch_torch_process_group()
+    _default_pg = new_group(stream=_make_stream())
+    if env.get_autotune_level() > 0:
+        _start_autotune_server(dist.get_world_size())
+    import atexit
+
+    atexit.register(_shutdown_backends)
+    return _default_pg
+
+
+def _reset_for_tests():
+    """Tear down module state (used by the test-suite between in-process scenarios)."""
+    global _default_pg, _group_count, _rank_mappings
+    _shutdown_backends()
+    _default_pg = None
+    _group_count = 0
+    _rank_mappings = None
+    _subgroup_cache.clear()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# blocking collective API (module level, reference communication.py:573-1401)
+# ---------------------------------------------------------------------------------------------------------------
+def _comm(comm: Optional[Communicator]) -> Communicator:
+    return comm if comm is not None else _get_default_group().get_global_communicator()
+
+
+def _check(comm: Communicator, *tensors):
+    if _use_cuda():
+        for t in tensors:
+            assert t.device.type == "cuda", "input tensors must be CUDA tensors when a GPU backend is active"
+
+
+class _on_comm_stream:
+    """current stream → event → comm stream runs the body → host waits for the comm stream."""
+
+    def __init__(self, comm: Communicator):
+        self.comm = comm
+        self.ctx = None
+
+    def __enter__(self):
+        s = self.comm.cuda_stream
+        if s is not None and _use_cuda():
+            ev = torch.cuda.current_stream().record_event()
+            s.wait_event(ev)
+            self.ctx = torch.cuda.stream(s)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+            self.comm.cuda_stream.synchronize()
+        return False
+
+
+def send(tensor: torch.Tensor, dst: int, comm: Optional[Communicator] = None):
+    """Send ``tensor`` to group-rank ``dst`` (blocking)."""
+    c = _comm(comm)
+    _check(c, tensor)
+    with _on_comm_stream(c):
+        c.send(tensor, dst)
+
+
+def recv(tensor: torch.Tensor, src: int, comm: Optional[Communicator] = None):
+    """Receive into ``tensor`` from group-rank ``src`` (blocking)."""
+    c = _comm(comm)
+    _check(c, tensor)
+    with _on_comm_stream(c):
+        c.recv(tensor, src)
+
+
+def broadcast(tensor: torch.Tensor, src: int = 0, comm: Optional[Communicator] = None):
+    """Broadcast ``tensor`` from group-rank ``src`` to every rank of the communicator."""
+    c = _comm(comm)
+    _check(c, tensor)
+    with _on_comm_stream(c):
+        c.broadcast(tensor, src)
+
+
+def broadcast_coalesced(tensors: Sequence[torch.Tensor], src: int = 0, comm: Optional[Communicator] = None):
+    """Broadcast a list of tensors as one flat message per dtype."""
+    c = _comm(comm)
+    _check(c, *tensors)
+    with _on_comm_stream(c):
+        by_dtype: Dict[torch.dtype, List[torch.Tensor]] = {}
+        for t in tensors:
+            by_dtype.setdefault(t.dtype, []).append(t)
+        for group in by_dtype.values():
+            flat = torch.cat([t.reshape(-1) for t in group])
+            c.broadcast(flat, src)
+            off = 0
+            for t in group:
+                t.copy_(flat[off : off + t.numel()].view_as(t))
+                off += t.numel()
+
+
+def broadcast_object(obj: object, src: int = 0, comm: Optional[Communicator] = None) -> object:
+    """Broadcast a picklable python object; returns it on every rank (reference communication.py:683-741)."""
+    c = _comm(comm)
+    dev = "cuda" if _use_cuda() else "cpu"
+    if c.rank() == src:
+        buf = io.BytesIO()
+        pickle.dump(obj, buf)
+        data = bytearray(buf.getvalue())
+        length = torch.tensor([len(data)], dtype=torch.int64, device=dev)
+        payload = torch.tensor(list(data), dtype=torch.uint8, device=dev) if len(data) else torch.empty(0, dtype=torch.uint8, device=dev)
+        broadcast(length, src, c)
+        broadcast(payload, src, c)
+        return obj
+    length = torch.zeros(1, dtype=torch.int64, device=dev)
+    broadcast(length, src, c)
+    payload = torch.empty(int(length.item()), dtype=torch.uint8, device=dev)
+    broadcast(payload, src, c)
+    return pickle.loads(bytes(payload.cpu().tolist()))
+
+
+def reduce(send_tensor, recv_tensor, dst: int, op: ReduceOp = ReduceOp.SUM, comm: Optional[Communicator] = None):
+    """Reduce ``send_tensor`` across ranks into ``recv_tensor`` on group-rank ``dst``."""
+    c = _comm(comm)
+    _check(c, send_tensor, recv_tensor)
+    with _on_comm_stream(c):
+        c.reduce(send_tensor, recv_tensor, dst, op)
+
+
+def reduce_inplace(tensor, dst: int, op: ReduceOp = ReduceOp.SUM, comm: Optional[Communicator] = None):
+    c = _comm(comm)
+    _check(c, tensor)
+    with _on_comm_stream(c):
+        c.reduce_inplace(tensor, dst, op)
+
+
+def _peer_allreduce(c: Communicator, tensor: torch.Tensor, op) -> bool:
+    """Route eligible allreduces through the NVSwitch kernels; returns False when NCCL/gloo must do it."""
+    if not _use_cuda() or ReduceOp(int(op)) not in (ReduceOp.SUM, ReduceOp.AVG):
+        return False
+    if tensor.dtype not in (torch.float32, torch.float16, torch.bfloat16) or not tensor.is_contiguous():
+        return False
+    owner = c._owner() if c._owner else None
+    if owner is None or c.scope != "global":
+        return False
+    eng = owner.peer_engine()
+    if eng is None:
+        return False
+    return eng.allreduce_tensor(tensor, average=ReduceOp(int(op)) == ReduceOp.AVG)
+
+
+def allreduce(send_tensor, recv_tensor, op: ReduceOp = ReduceOp.SUM, comm: Optional[Communicator] = None):
+    """All-reduce ``send_tensor`` into ``recv_tensor`` (same shape) on every rank."""
+    c = _comm(comm)
+    _check(c, send_tensor, recv_tensor)
+    assert send_tensor.numel() == recv_tensor.numel(), "send and recv tensors must have the same size"
+    with _on_comm_stream(c):
+        if recv_tensor.data_ptr() != send_tensor.data_ptr():
+            recv_tensor.copy_(send_tensor)
+        if not _peer_allreduce(c, recv_tensor, op):
+            c.allreduce_inplace(recv_tensor, op)
+
+
+def allreduce_inplace(tensor, op: ReduceOp = ReduceOp.SUM, comm: Optional[Communicator] = None):
+    c = _comm(comm)
+    _check(c, tensor)
+    with _on_comm_stream(c):
+        if not _peer_allreduce(c, tensor, op):
+            c.allreduce_inplace(tensor, op)
+
+
+def allreduce_coalesced_inplace(tensors: Sequence[torch.Tensor], op: ReduceOp = ReduceOp.SUM, comm: Optional[Communicator] = None):
+    """All-reduce a list of tensors as flat messages (one per dtype)."""
+    c = _comm(comm)
+    _check(c, *tensors)
+    with _on_comm_stream(c):
+        by_dtype: Dict[torch.dtype, List[torch.Tensor]] = {}
+        for t in tensors:
+            by_dtype.setdefault(t.dtype, []).append(t)
+        for group in by_dtype.values():
+            flat = torch.cat([t.reshape(-1) for t in group])
+            if not _peer_allreduce(c, flat, op):
+                c.allreduce_inplace(flat, op)
+            off = 0
+            for t in group:
+                t.copy_(flat[off : off + t.numel()].view_as(t))
+                off += t.numel()
+
+
+def allgather(send_tensor, recv_tensor, comm: Optional[Communicator] = None):
+    c = _comm(comm)
+    _check(c, send_tensor, recv_tensor)
+    with _on_comm_stream(c):
+        c.allgather(send_tensor, recv_tensor)
+
+
+def allgather_inplace(tensor, comm: Optional[Communicator] = None):
+    c = _comm(comm)
+    _check(c, tensor)
+    with _on_comm_stream(c):
+        c.allgather_inplace(tensor)
+
+
+def gather(send_tensor, recv_tensor, dst: int, comm: Optional[Communicator] = None):
+    c = _comm(comm)
+    _check(c, send_tensor, recv_tensor)
+    with _on_comm_stream(c):
+        c.gather(send_tensor, recv_tensor, dst)
+
+
+def gather_inplace(tensor, count: int, dst: int, comm: Optional[Communicator] = None):
+    c = _comm(comm)
+    _check(c, tensor)
+    with _on_comm_stream(c):
+        c.gather_inplace(tensor, count, dst)
+
+
+def scatter(send_tensor, recv_tensor, src: int, comm: Optional[Communicator] = None):
+    c = _comm(comm)
+    _check(c, send_tensor, recv_tensor)
+    with _on_comm_stream(c):
+        c.scatter(send_tensor, recv_tensor, src)
+
+
+def scatter_inplace(tensor, count: int, src: int, comm: Optional[Communicator] = None):
+    c = _comm(comm)
+    _check(c, tensor)
+    with _on_comm_stream(c):
+        c.scatter_inplace(tensor, count, src)
+
+
+def reduce_scatter(send_tensor, recv_tensor, op: ReduceOp = ReduceOp.SUM, comm: Optional[Communicator] = None):
+    c = _comm(comm)
+    _check(c, send_tensor, recv_tensor)
+    with _on_comm_stream(c):
+        c.reduce_scatter(send_tensor, recv_tensor, op)
+
+
+def reduce_scatter_inplace(tensor, op: ReduceOp = ReduceOp.SUM, comm: Optional[Communicator] = None):
+    c = _comm(comm)
+    _check(c, tensor)
+    with _on_comm_stream(c):
+        c.reduce_scatter_inplace(tensor, op)
+
+
+def alltoall(send_tensor, recv_tensor, comm: Optional[Communicator] = None):
+    c = _comm(comm)
+    _check(c, send_tensor, recv_tensor)
+    with _on_comm_stream(c):
+        c.alltoall(send_tensor, recv_tensor)
+
+
+def alltoall_inplace(tensor, comm: Optional[Communicator] = None):
+    c = _comm(comm)
+    _check(c, tensor)
+    with _on_comm_stream(c):
+        c.alltoall_inplace(tensor)
+
+
+def alltoall_v(send_tensor, send_counts, send_displs, recv_tensor, recv_counts, recv_displs, comm: Optional[Communicator] = None):
+    c = _comm(comm)
+    _check(c, send_tensor, recv_tensor)
+    with _on_comm_stream(c):
+        c.alltoall_v(send_tensor, send_counts, send_displs, recv_tensor, recv_counts, recv_displs)
+
+
+def alltoall_v_inplace(tensor, counts, displs, comm: Optional[Communicator] = None):
+    c = _comm(comm)
+    _check(c, tensor)
+    with _on_comm_stream(c):
+        c.alltoall_v_inplace(tensor, counts, displs)
+
+
+def barrier(comm: Optional[Communicator] = None):
+    """Block until every rank of the communicator has entered the barrier."""
+    c = _comm(comm)
+    with _on_comm_stream(c):
+        c.barrier()

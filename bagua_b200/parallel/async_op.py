@@ -1,0 +1,103 @@
+"""The asynchronous model-average bucket op (comm op 5 of SURVEY §2.5; reference
+rust/bagua-core/bagua-core-internal/src/comm_ops/decentralized_full_precision_asynchronous.rs:30-180).
+
+One averaging round, executed on the scheduler's worker thread:
+
+1. all ranks agree whether anybody asked to stop (MIN-allreduce of a flag on the background group);
+2. snapshot the weights; 3. sum the snapshots over all ranks — on NVSwitch one out-of-place two-shot / multimem kernel
+   from the symmetric ``snap`` buffer into the symmetric ``red`` buffer, on the background group's own stream;
+4. under the weight lock apply ``w += red/P − snap`` (one kernel, on the compute stream so it is ordered with the
+   optimizer step exactly like the reference).
+"""
+from __future__ import annotations
+
+import threading
+
+import torch
+import torch.distributed as dist
+
+from ..core import dtype_code, native
+
+
+class AsyncModelAverageOp:
+    def __init__(self, bucket, group):
+        self.bucket = bucket
+        self.group = group
+        self.lock = threading.Lock()
+        self._abort = False
+        self._running = True
+        flat = bucket.backend_tensor
+        assert flat is not None, "Async algorithm supports `do_flatten=True` only"
+        self.flat = flat
+        self.snap = bucket.new_companion(init_from_bucket=False, symmetric=True, group=group)
+        self.red = bucket.new_companion(init_from_bucket=False, symmetric=True, group=group)
+        self._native = None
+        eng = bucket._engine(group)
+        s_snap, s_red = getattr(self.snap, "_bagua_symm_slice", None), getattr(self.red, "_bagua_symm_slice", None)
+        if eng is not None and s_snap is not None and s_red is not None and flat.dtype in (torch.float32, torch.float16, torch.bfloat16):
+            nbytes = flat.numel() * flat.element_size()
+            if nbytes % 16 == 0:
+                op, _ = eng.make_allreduce_op(s_snap, s_red, nbytes, flat.dtype, False, "auto")
+                self._native = (eng, op)
+        dev = flat.device
+        self._flag = torch.ones(1, dtype=torch.int32, device=dev)
+
+    # -- mutex protocol (trainer holds it from forward-pre to post-backward) ---------------------------------------
+    def lock_weight(self):
+        self.lock.acquire()
+
+    def unlock_weight(self):
+        if self.lock.locked():
+            self.lock.release()
+
+    def abort(self):
+        self._abort = True
+
+    def reset(self):
+        self._abort = False
+        self._running = True
+
+    def get_status(self) -> bool:
+        return self._running
+
+    # -- one round ---------------------------------------------------------------------------------------------------
+    def run(self, _bucket_name: str):
+        pg = self.group
+        n = pg.size()
+        cuda = self.flat.is_cuda
+        with torch.no_grad():
+            self._flag.fill_(0 if self._abort else 1)
+            if n > 1:
+                if cuda:
+                    with torch.cuda.stream(pg.stream):
+                        dist.all_reduce(self._flag, op=dist.ReduceOp.MIN, group=pg.torch_group)
+                else:
+                    dist.all_reduce(self._flag, op=dist.ReduceOp.MIN, group=pg.torch_group)
+            if int(self._flag.item()) == 0:
+                self._running = False
+                return
+            if cuda:
+                main = torch.cuda.current_stream()
+                self.snap.copy_(self.flat)  # on the compute stream, like the reference (…asynchronous.rs:124)
+                ev = main.record_event()
+                pg.stream.wait_event(ev)
+                if self._native is not None:
+                    eng, op = self._native
+                    native().run_op(op, pg.stream.cuda_stream, self.flat.device.index)
+                else:
+                    with torch.cuda.stream(pg.stream):
+                        self.red.copy_(self.snap)
+                        if n > 1:
+                            dist.all_reduce(self.red, group=pg.torch_group)
+                pg.stream.synchronize()
+                with self.lock:
+                    native().async_apply(self.flat.data_ptr(), self.red.data_ptr(), self.snap.data_ptr(), self.flat.numel(), dtype_code(self.flat.dtype),
+                                         1.0 / n, main.cuda_stream)
+                    main.synchronize()
+            else:
+                self.snap.copy_(self.flat)
+                self.red.copy_(self.snap)
+                if n > 1:
+                    dist.all_reduce(self.red, group=pg.torch_group)
+                with self.lock:
+                    self.flat.add_(self.red / n - self.snap)

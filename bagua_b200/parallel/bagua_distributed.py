@@ -1,0 +1,437 @@
+"""The data-parallel engine behind ``module.with_bagua(...)`` and the DDP-compatible wrapper.
+
+Capability parity with ``bagua/torch_api/data_parallel/bagua_distributed.py`` (hooks :93-148, param build :155-212,
+state broadcast :229-323, autotune :325-391, hook registration :417-481, bucket reset :483-496).
+
+B200-first changes of the hot path:
+
+* one forward-pre hook and one *post-accumulate-grad* hook per parameter whose closure is built once per
+  (re)initialisation — the reference rebuilds the algorithm's hook closure for every gradient of every iteration
+  (bagua_distributed.py:431);
+* a gradient is handed to the native scheduler with its producing stream; the scheduler records ONE event per bucket;
+* the end of backward does not block the host: the compute stream is made to wait (on the device) for the last bucket's
+  completion event, so ``optimizer.step()`` launches while collectives are still in flight;
+* all buckets of a model live in one contiguous arena of NVSwitch symmetric memory, so (a) each bucket op is a single
+  fused kernel with no staging copy and (b) the fused optimizer updates the whole model with one launch.
+"""
+from __future__ import annotations
+
+import collections
+import io
+import logging
+import pickle
+import time
+from types import MethodType
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .. import communication as comm_mod
+from .. import env
+from ..bucket import BaguaBucket, BucketArena, bucket_arena
+from ..core import native, to_bagua_datatype
+from ..define import BaguaHyperparameter, TensorDeclaration
+from ..utils import StatisticalAverage
+
+logger = logging.getLogger(__name__)
+
+__all__ = ["BaguaDistributedDataParallel"]
+
+
+def _is_moe_param(param: torch.Tensor) -> bool:
+    return bool(getattr(param, "expert", False))
+
+
+class _States:
+    """Bookkeeping object stored on the wrapped module (so a second ``with_bagua`` can undo the first)."""
+
+
+class BaguaDistributedDataParallel:
+    def __init__(
+        self,
+        module: torch.nn.Module,
+        optimizers: List[torch.optim.Optimizer],
+        algorithm,
+        process_group,
+        bagua_module_name: Optional[str] = None,
+        gradient_as_bucket_view: bool = True,
+        find_unused_parameters: bool = False,
+    ) -> None:
+        self.module = module
+        self.bagua_module_name = bagua_module_name
+        self.bagua_optimizers = optimizers
+        self.process_group = process_group
+        self.bagua_algorithm = algorithm.reify(process_group)
+        self.gradient_as_bucket_view = gradient_as_bucket_view
+        self.find_unused_parameters = find_unused_parameters
+        self.parameters_to_ignore: List[str] = []
+        for attr in ("_bagua_params_and_buffers_to_ignore", "_ddp_params_and_buffers_to_ignore"):
+            if hasattr(module, attr):
+                self.parameters_to_ignore.extend(getattr(module, attr))
+
+        self.bagua_train_step_counter = 0
+        self.bagua_buckets: List[BaguaBucket] = []
+        self._bagua_autotune_last_report_time = time.time()
+        self._bagua_autotune_completed = False
+        self._is_post_backward_callback_queued = False
+        self.require_backward_grad_sync = True
+        self.autograd_graph_params: Dict[str, torch.nn.Parameter] = {}
+        self.params_in_use = set()
+        self._arena = None
+
+        if hasattr(module, "_bagua_states"):
+            self._reset_algorithm_state()
+        module._bagua_states = _States()
+        module._bagua_states._bagua_autograd_hooks = []
+        module._bagua_states._bagua_framework_hooks = []
+
+        self._bagua_backend = comm_mod.get_backend(self.bagua_module_name)
+        self._bagua_hyperparameters = BaguaHyperparameter()
+        self._speed_metrics_switch_on = env.get_autotune_level() >= 1
+        self._speed_metrics = StatisticalAverage()
+        self._on_cuda = any(p.is_cuda for p in module.parameters())
+        self._bagua_autotune_client = None
+        if env.get_autotune_level() >= 1:
+            from ..service.autotune_service import AutotuneClient
+
+            port = comm_mod.get_autotune_service_port()
+            assert port is not None, "autotune level > 0 but the autotune service was not started by init_process_group"
+            self._bagua_autotune_client = AutotuneClient(env.get_master_addr(), port)
+            self._bagua_backend.set_record_spans(True)
+
+        ddp = self
+
+        def forward_pre_hook(mod, inputs):
+            ddp.autograd_graph_params.clear()
+            if mod.training:
+                ddp.bagua_train_step_counter += 1
+                if ddp.bagua_algorithm.need_reset():
+                    ddp._bagua_init_algorithm()
+                ddp._fwd_pre_hook(inputs)
+                ddp._record_speed_metrics_event()
+                if ddp._bagua_autotune_client is not None and not ddp._bagua_autotune_completed:
+                    ddp._bagua_autotune_step()
+            ddp._is_post_backward_callback_queued = False
+
+        module._bagua_states._bagua_framework_hooks.append(module.register_forward_pre_hook(forward_pre_hook))
+        self._bagua_init_algorithm()
+
+    # ---------------------------------------------------------------------------------------------------------
+    # parameters
+    # ---------------------------------------------------------------------------------------------------------
+    def bagua_build_params(self) -> List[Tuple[str, torch.nn.Parameter]]:
+        """``(name, parameter)`` for every parameter that requires grad, is not ignored, is not a MoE expert parameter
+        (experts are not data-parallel), deduplicated; sparse-gradient modules are rejected (reference :155-212)."""
+        out: List[Tuple[str, torch.nn.Parameter]] = []
+        seen = set()
+        for module_name, sub in self.module.named_modules():
+            if isinstance(sub, (torch.nn.Embedding, torch.nn.EmbeddingBag)) and sub.sparse:
+                raise NotImplementedError("sparse gradient not supported yet")
+            for pname, p in sub.named_parameters(recurse=False):
+                full = f"{module_name}.{pname}" if module_name else pname
+                if not p.requires_grad or full in self.parameters_to_ignore or _is_moe_param(p):
+                    continue
+                if self.find_unused_parameters and self.autograd_graph_params and full not in self.autograd_graph_params:
+                    continue
+                if id(p) in seen:
+                    continue
+                seen.add(id(p))
+                out.append((full, p))
+        return out
+
+    # ---------------------------------------------------------------------------------------------------------
+    # state broadcast
+    # ---------------------------------------------------------------------------------------------------------
+    def _bagua_broadcast_parameters(self):
+        """Rank 0's parameters and optimizer state become everybody's (coalesced: one message per dtype)."""
+        comm = self.process_group.get_global_communicator()
+        if comm.nranks() == 1:
+            return
+        tensors = [p.data for _, p in self.bagua_build_params()]
+        if tensors:
+            comm_mod.broadcast_coalesced(tensors, src=0, comm=comm)
+        for opt in self.bagua_optimizers:
+            self._bagua_broadcast_optimizer_state(opt)
+
+    def _bagua_broadcast_optimizer_state(self, optimizer):
+        if isinstance(optimizer, torch.optim.LBFGS):
+            raise ValueError("cannot broadcast torch.optim.LBFGS state")
+        comm = self.process_group.get_global_communicator()
+        sd = optimizer.state_dict()
+        if len(sd["state"]) == 0:
+            return
+        state_tensors, scalars = [], collections.OrderedDict()
+        for gi, group in enumerate(sd["param_groups"]):
+            for k in sorted(group.keys()):
+                if k != "params":
+                    scalars[f"group{gi}.{k}"] = group[k]
+            for pid in sorted(group["params"]):
+                st = sd["state"].get(pid)
+                if st is None:
+                    continue
+                for k in sorted(st.keys(), key=str):
+                    v = st[k]
+                    if isinstance(v, torch.Tensor):
+                        state_tensors.append(v)
+                    else:
+                        scalars[f"state{pid}.{k}"] = v
+        on_dev = [t for t in state_tensors if t.device.type == ("cuda" if self._on_cuda else "cpu")]
+        off_dev = [t for t in state_tensors if t not in on_dev]
+        if on_dev:
+            comm_mod.broadcast_coalesced(on_dev, src=0, comm=comm)
+        for t in off_dev:  # e.g. CPU "step" tensors of GPU optimizers
+            dev = "cuda" if self._on_cuda else "cpu"
+            tmp = t.to(dev)
+            comm_mod.broadcast(tmp, src=0, comm=comm)
+            t.copy_(tmp.to(t.device))
+        scalars = comm_mod.broadcast_object(scalars, src=0, comm=comm)
+        for gi, group in enumerate(optimizer.param_groups):
+            for k in list(group.keys()):
+                key = f"group{gi}.{k}"
+                if k != "params" and key in scalars:
+                    group[k] = scalars[key]
+        pid_to_param = {}
+        idx = 0
+        for group in optimizer.param_groups:
+            for p in group["params"]:
+                pid_to_param[idx] = p
+                idx += 1
+        for key, v in scalars.items():
+            if key.startswith("state"):
+                pid_s, name = key[len("state"):].split(".", 1)
+                p = pid_to_param.get(int(pid_s))
+                if p is not None and p in optimizer.state:
+                    optimizer.state[p][name] = v
+
+    # ---------------------------------------------------------------------------------------------------------
+    # autotune / bucketing
+    # ---------------------------------------------------------------------------------------------------------
+    def _tensor_declarations(self) -> List[TensorDeclaration]:
+        return [
+            TensorDeclaration(name=t.bagua_tensor_name, num_elements=t.bagua_getter_closure().numel(), dtype=to_bagua_datatype(t.bagua_getter_closure().dtype))
+            for t in self._bagua_tensors
+        ]
+
+    def _bagua_autotune_register_tensors(self):
+        if self._bagua_autotune_client is None:
+            return
+        rsp = self._bagua_autotune_client.register_tensors(model_name=self.bagua_module_name, tensor_list=self._tensor_declarations())
+        assert rsp.status_code == 200, f"Unexpected rsp={rsp}"
+
+    def _bagua_autotune_get_buckets(self) -> List[List[torch.Tensor]]:
+        if self._bagua_autotune_client is None:
+            from ..service.autotune_task_manager import split_bucket_by_bucket_size
+
+            size = self._bagua_hyperparameters.bucket_size or env.get_default_bucket_size()
+            self._bagua_hyperparameters.bucket_size = size
+            decl = split_bucket_by_bucket_size(self._tensor_declarations(), size)
+            self._bagua_hyperparameters.buckets = decl
+            return [[self._bagua_tensor_map[td["name"]] for td in b] for b in decl]
+        self._flush_ready_spans()
+        rsp = self._bagua_autotune_client.ask_hyperparameters(model_name=self.bagua_module_name, rank=env.get_rank(), train_iter=self.bagua_train_step_counter)
+        assert rsp.status_code == 200, f"Unexpected rsp={rsp}"
+        body = rsp.json()
+        self._bagua_hyperparameters.update(body["recommended_hyperparameters"])
+        self._bagua_autotune_completed = body["is_autotune_completed"]
+        return [[self._bagua_tensor_map[td["name"]] for td in b] for b in body["recommended_hyperparameters"]["buckets"]]
+
+    def _flush_ready_spans(self):
+        """Tensor-ready order recorded by the native scheduler → autotune service (the reference streams OpenTelemetry
+        spans from Rust, bagua-opentelemetry/src/exporter/agent.rs:31-43)."""
+        if self._bagua_autotune_client is None:
+            return
+        spans = self._bagua_backend.pop_ready_spans()
+        if not spans:
+            return
+        last_iter = spans[-1][2]
+        payload = [
+            {"trace_id": int(it), "action": "tensor_ready", "tensor_name": name, "start_time": int(t), "end_time": int(t)}
+            for name, t, it in spans
+            if it == last_iter
+        ]
+        try:
+            self._bagua_autotune_client.report_tensor_execution_order(payload)
+        except Exception as e:  # noqa: BLE001
+            logger.debug("report_tensor_execution_order failed: %s", e)
+
+    def _bagua_autotune_step(self):
+        CYCLE_STEP = 100
+        if self.bagua_train_step_counter != 0 and self.bagua_train_step_counter % CYCLE_STEP == 0:
+            since = time.time() - self._bagua_autotune_last_report_time
+            speed = self._speed_metrics.get(since)
+            rsp = self._bagua_autotune_client.report_metrics(
+                model_name=self.bagua_module_name,
+                rank=env.get_rank(),
+                train_iter=self.bagua_train_step_counter,
+                hyperparameters=self._bagua_hyperparameters.dict(),
+                speed=speed,
+            )
+            assert rsp.status_code == 200, f"Unexpected rsp={rsp}"
+            self._reset_buckets()
+            self._bagua_autotune_last_report_time = time.time()
+
+    def _record_speed_metrics_event(self):
+        if not self._speed_metrics_switch_on:
+            return
+        if self._on_cuda:
+            pair = getattr(self, "_last_event_pair", None)
+            if pair is not None:
+                start, stop = pair
+                try:
+                    elapsed = start.elapsed_time(stop) / 1000.0
+                    gb = sum(b.bytes() for b in self.bagua_buckets) / 1024.0 ** 3
+                    if elapsed > 0:
+                        self._speed_metrics.record(gb / elapsed)
+                except RuntimeError as err:
+                    logger.debug("ignore cuda err=%s", err)
+            start_event = torch.cuda.Event(enable_timing=True)
+            self._speed_metrics_end_event = torch.cuda.Event(enable_timing=True)
+            torch.cuda.current_stream().record_event(start_event)
+            self._last_event_pair = (start_event, self._speed_metrics_end_event)
+        else:
+            now = time.time()
+            t0, t1 = getattr(self, "_last_time_pair", (None, None))
+            if t0 is not None and t1 is not None and t1 > t0:
+                gb = sum(b.bytes() for b in self.bagua_buckets) / 1024.0 ** 3
+                self._speed_metrics.record(gb / (t1 - t0))
+            self._last_time_pair = (now, None)
+
+    # ---------------------------------------------------------------------------------------------------------
+    # (re)initialisation
+    # ---------------------------------------------------------------------------------------------------------
+    def _bagua_init_algorithm(self):
+        self._bagua_cleanup_algorithm()
+        self._bagua_broadcast_parameters()
+        self._bagua_tensors = self.bagua_algorithm.init_tensors(self)
+        self._bagua_tensor_map = {t.bagua_tensor_name: t for t in self._bagua_tensors}
+        self._bagua_autotune_register_tensors()
+        self._reset_buckets()
+        self._register_autograd_hooks()
+        self._register_optimizer_hooks()
+
+    def _bagua_cleanup_algorithm(self):
+        # let in-flight work of the previous program drain before its buffers are recycled
+        try:
+            self._bagua_backend.wait_pending_comm_ops(self._consumer_stream(), not self._on_cuda)
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _consumer_stream(self) -> int:
+        return torch.cuda.current_stream().cuda_stream if self._on_cuda else 0
+
+    def _reset_buckets(self):
+        raw = self._bagua_autotune_get_buckets()
+        old = self.bagua_buckets
+        for b in old:
+            b.clear_ops()
+        old_arena = self._arena
+        self._arena = None
+        if self.gradient_as_bucket_view and raw:
+            sizes = [sum(t.bagua_getter_closure().numel() * t.bagua_getter_closure().element_size() for t in b) for b in raw]
+            dev = raw[0][0].bagua_getter_closure().device
+            self._arena = BucketArena(self.process_group, dev, BucketArena.required_bytes(sizes))
+        with bucket_arena(self._arena):
+            self.bagua_buckets = self.bagua_algorithm.tensors_to_buckets(raw, self.gradient_as_bucket_view)
+        for bucket in self.bagua_buckets:
+            self.bagua_algorithm.init_operations(self, bucket)
+        self._bagua_backend.register_ordered_buckets([b.backend_bucket for b in self.bagua_buckets])
+        for b in old:
+            b.release()
+        if old_arena is not None:
+            old_arena.free()
+        self.params_in_use = set(name for name, _ in self.bagua_build_params())
+        self._fwd_pre_hook = self.bagua_algorithm.init_forward_pre_hook(self)
+        self._backward_hook = self.bagua_algorithm.init_backward_hook(self)
+        self._post_backward_hook = self.bagua_algorithm.init_post_backward_hook(self)
+
+    def _delay_allreduce(self):
+        for name, p in self.bagua_build_params():
+            self._backward_hook(name, p)
+        self._post_backward_hook()
+
+    # ---------------------------------------------------------------------------------------------------------
+    # hooks
+    # ---------------------------------------------------------------------------------------------------------
+    def _cleanup_autograd_hooks(self):
+        st = self.module._bagua_states
+        for h in st._bagua_autograd_hooks:
+            h.remove()
+        st._bagua_autograd_hooks.clear()
+
+    def _register_autograd_hooks(self):
+        self._cleanup_autograd_hooks()
+        st = self.module._bagua_states
+        ddp = self
+
+        def queue_post_backward():
+            if not ddp._is_post_backward_callback_queued:
+                torch.autograd.Variable._execution_engine.queue_callback(ddp._real_post_backward_hook)
+                ddp._is_post_backward_callback_queued = True
+
+        def factory(name: str):
+            def hook(param):
+                if not ddp.require_backward_grad_sync:
+                    return
+                if ddp.find_unused_parameters:
+                    ddp.autograd_graph_params[name] = param
+                ddp._backward_hook(name, param)
+                queue_post_backward()
+
+            return hook
+
+        for name, p in self.module.named_parameters():
+            if p.requires_grad:
+                st._bagua_autograd_hooks.append(p.register_post_accumulate_grad_hook(factory(name)))
+
+    def _real_post_backward_hook(self):
+        self._post_backward_hook()
+        if self._speed_metrics_switch_on:
+            if self._on_cuda:
+                torch.cuda.current_stream().record_event(self._speed_metrics_end_event)
+            else:
+                t0, _ = getattr(self, "_last_time_pair", (None, None))
+                self._last_time_pair = (t0, time.time())
+        if self.find_unused_parameters and set(self.autograd_graph_params.keys()) != self.params_in_use:
+            self._reset_buckets()
+            self._delay_allreduce()
+
+    def _register_optimizer_hooks(self):
+        hook = self.bagua_algorithm.init_post_optimizer_step_hook(self)
+        bucketed = set()
+        for t in getattr(self, "_bagua_tensors", []):
+            bucketed.add(id(t))
+        for optimizer in self.bagua_optimizers:
+            if not hasattr(optimizer, "_bagua_original_step"):
+                optimizer._bagua_original_step = optimizer.step
+            if not hasattr(optimizer, "_bagua_original_zero_grad"):
+                optimizer._bagua_original_zero_grad = optimizer.zero_grad
+
+            def new_step(self_opt, *args, **kwargs):
+                result = self_opt._bagua_original_step(*args, **kwargs)
+                hook(self_opt)
+                return result
+
+            def new_zero_grad(self_opt, set_to_none: bool = False):
+                # gradients are views into the bucket arena: they must stay allocated
+                return self_opt._bagua_original_zero_grad(set_to_none=False)
+
+            optimizer.step = MethodType(new_step, optimizer)
+            optimizer._bagua_post_step_hook = hook  # fuse_step() triggers it too
+            optimizer.zero_grad = MethodType(new_zero_grad, optimizer)
+
+    def _reset_algorithm_state(self):
+        st = self.module._bagua_states
+        for h in getattr(st, "_bagua_framework_hooks", []):
+            h.remove()
+        if hasattr(st, "_bagua_autograd_hooks"):
+            self._cleanup_autograd_hooks()
+
+    # used by the default algorithm hooks ------------------------------------------------------------------------
+    def mark_tensor_ready(self, tensor: torch.Tensor):
+        """Fast ready mark: the scheduler records one event on the current stream when the tensor's bucket completes."""
+        self._bagua_backend.mark_ready_on_stream(tensor._bagua_backend_tensor, self._consumer_stream())
+
+    def wait_pending_comm_ops(self) -> int:
+        """Order the current stream after every scheduled bucket (device-side wait on GPU, host wait on CPU)."""
+        return self._bagua_backend.wait_pending_comm_ops(self._consumer_stream(), not self._on_cuda)

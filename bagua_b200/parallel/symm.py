@@ -1,0 +1,249 @@
+"""NVSwitch symmetric-memory engine: the per-group state behind every fused collective kernel.
+
+There is no counterpart in the reference — its communicators are NCCL handles
+(rust/bagua-core/bagua-core-internal/src/communicators/mod.rs:26-73).  On an HGX B200 every GPU reaches every
+peer at full NVLink 5 bandwidth through NVSwitch, so a group's "communicator" here is:
+
+* symmetric device memory: identical allocations on every rank, each mapped into every peer's address space
+  (+ an NVLS multicast alias when the fabric offers it).  Allocation/handle exchange is bootstrapped with
+  ``torch.distributed._symmetric_memory`` (CUDA VMM + fd passing); the kernels are ours.
+* a signal pad (epoch flags) in that memory + an abort flag → ``_C.PeerComm``.
+* a slab allocator handing out slices for bucket storage, peer replicas and quantised in/out boxes.
+"""
+from __future__ import annotations
+
+import logging
+import os
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from .. import env
+from ..core import dtype_code, native
+
+logger = logging.getLogger(__name__)
+
+_ALIGN = 1024                       # slice alignment (bytes); ≥ 16 B vectors, keeps TMA/128 B lines happy
+_SLAB_BYTES = 256 * 1024 ** 2       # symmetric memory is requested in slabs of this size (or larger on demand)
+ONE_SHOT_SLOT = 512 * 1024          # staging slot per (parity, rank) of the one-shot allreduce
+
+
+def _round_up(x: int, a: int) -> int:
+    return (x + a - 1) // a * a
+
+
+class _Slab:
+    def __init__(self, engine: "PeerEngine", nbytes: int):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.nbytes = nbytes
+        self.tensor = symm_mem.empty(nbytes, dtype=torch.uint8, device=engine.device)
+        self.tensor.zero_()
+        self.handle = symm_mem.rendezvous(self.tensor, engine.torch_pg)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        mc = 0
+        if engine.use_multicast:
+            try:
+                mc = int(self.handle.multicast_ptr or 0)
+            except Exception:  # noqa: BLE001
+                mc = 0
+        self.ptrs = ptrs
+        self.mc = mc
+        self.buf = native().SymmBuf(ptrs, mc, nbytes)
+        self.free_list: List[List[int]] = [[0, nbytes]]  # [offset, size], kept sorted and coalesced
+
+    def alloc(self, nbytes: int) -> Optional[int]:
+        for i, (off, size) in enumerate(self.free_list):
+            if size >= nbytes:
+                if size == nbytes:
+                    self.free_list.pop(i)
+                else:
+                    self.free_list[i] = [off + nbytes, size - nbytes]
+                return off
+        return None
+
+    def free(self, off: int, nbytes: int):
+        self.free_list.append([off, nbytes])
+        self.free_list.sort()
+        merged: List[List[int]] = []
+        for o, s in self.free_list:
+            if merged and merged[-1][0] + merged[-1][1] == o:
+                merged[-1][1] += s
+            else:
+                merged.append([o, s])
+        self.free_list = merged
+
+
+@dataclass
+class SymmSlice:
+    """``nbytes`` of symmetric memory: ``tensor`` is this rank's view; ``buf``/``offset`` address the same bytes on peers."""
+
+    slab: _Slab
+    offset: int
+    nbytes: int
+    tensor: torch.Tensor
+
+    @property
+    def buf(self):
+        return self.slab.buf
+
+    @property
+    def has_multicast(self) -> bool:
+        return self.slab.mc != 0
+
+    def view(self, dtype: torch.dtype, numel: Optional[int] = None) -> torch.Tensor:
+        t = self.tensor.view(dtype)
+        return t if numel is None else t[:numel]
+
+    def free(self):
+        if self.slab is not None:
+            self.slab.free(self.offset, self.nbytes)
+            self.slab = None
+
+
+class PeerEngine:
+    """Owns the symmetric memory, signal pads and kernel-variant policy of one process group."""
+
+    @classmethod
+    def create(cls, group) -> Optional["PeerEngine"]:
+        if not torch.cuda.is_available() or os.environ.get("BAGUA_FORCE_CPU", "0") == "1":
+            return None
+        if env.get_allreduce_variant() == "nccl":
+            return None
+        n = len(group.ranks)
+        if n < 2 or n > native().MAX_PEERS or group.nnodes != 1:
+            return None
+        if dist.get_rank() not in group.ranks:
+            return None
+        return cls(group)
+
+    def __init__(self, group):
+        C = native()
+        self.group = group
+        self.torch_pg = group.torch_group
+        self.world = len(group.ranks)
+        self.rank = group.ranks.index(dist.get_rank())
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.use_multicast = os.environ.get("BAGUA_DISABLE_MULTICAST", "0") != "1"
+        self._slabs: List[_Slab] = []
+        # signal pads first: their own tiny symmetric allocation, zeroed before anybody can signal
+        pad = self._new_slab(_round_up(C.signal_pad_bytes(), 4096), track=False)
+        self._pad_slab = pad
+        self.comm = C.PeerComm(self.rank, self.world, self.device.index, pad.ptrs, env.get_peer_kernel_timeout_s())
+        torch.cuda.synchronize()
+        dist.barrier(group=self.torch_pg)
+        self.has_multicast = pad.mc != 0
+        self._staging: Optional[SymmSlice] = None
+        self._workspace: Optional[SymmSlice] = None
+        self.sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
+        logger.info("bagua_b200 PeerEngine: group %s rank %d/%d multicast=%s", group.group_name, self.rank, self.world, self.has_multicast)
+
+    # -- allocation ------------------------------------------------------------------------------------------------
+    def _new_slab(self, nbytes: int, track: bool = True) -> _Slab:
+        slab = _Slab(self, nbytes)
+        if track:
+            self._slabs.append(slab)
+        return slab
+
+    def alloc(self, nbytes: int) -> SymmSlice:
+        """Collective: every rank of the group must request the same sizes in the same order."""
+        nbytes = _round_up(max(int(nbytes), 1), _ALIGN)
+        for slab in self._slabs:
+            off = slab.alloc(nbytes)
+            if off is not None:
+                return SymmSlice(slab, off, nbytes, slab.tensor[off : off + nbytes])
+        slab = self._new_slab(max(_SLAB_BYTES, _round_up(nbytes, 2 * 1024 ** 2)))
+        off = slab.alloc(nbytes)
+        return SymmSlice(slab, off, nbytes, slab.tensor[off : off + nbytes])
+
+    # -- policy ------------------------------------------------------------------------------------------------------
+    def choose_variant(self, nbytes: int, requested: str = "auto") -> str:
+        v = requested if requested not in (None, "", "auto") else env.get_allreduce_variant()
+        if v in ("one_shot", "two_shot"):
+            return v
+        if v == "multimem":
+            return "multimem" if self.has_multicast else "two_shot"
+        if nbytes <= ONE_SHOT_SLOT // 2:
+            return "one_shot"
+        return "multimem" if self.has_multicast else "two_shot"
+
+    def launch_cfg(self, variant: str, nbytes: int, blocks: int = 0):
+        C = native()
+        env_blocks = int(os.environ.get("BAGUA_COMM_BLOCKS", "0"))
+        if blocks <= 0:
+            blocks = env_blocks
+        if blocks <= 0:
+            vecs = max(nbytes // 16, 1)
+            if variant == "one_shot":
+                blocks = max(1, min(8, vecs // 512))
+            elif variant == "multimem":
+                blocks = max(1, min(16, vecs // (self.world * 512)))
+            else:
+                blocks = max(1, min(32, vecs // (self.world * 512)))
+        return C.LaunchCfg(int(min(blocks, C.MAX_COMM_BLOCKS)), 512)
+
+    def staging(self) -> SymmSlice:
+        if self._staging is None:
+            self._staging = self.alloc(2 * self.world * ONE_SHOT_SLOT)
+        return self._staging
+
+    # -- op factories ----------------------------------------------------------------------------------------------
+    def make_allreduce_op(self, src: SymmSlice, dst: SymmSlice, nbytes: int, dtype: torch.dtype, average: bool, variant: str = "auto",
+                          src_off: int = 0, dst_off: int = 0, blocks: int = 0):
+        """Native op reducing ``nbytes`` at ``src``(+off) over all ranks into ``dst``(+off) on all ranks."""
+        C = native()
+        v = self.choose_variant(nbytes, variant)
+        scale = 1.0 / self.world if average else 1.0
+        nbytes16 = _round_up(nbytes, 16)
+        if v == "one_shot" and nbytes16 <= ONE_SHOT_SLOT:
+            st = self.staging()
+            return C.AllReduceOneShotOp(self.comm, st.buf, ONE_SHOT_SLOT, src.tensor.data_ptr() + src_off, dst.tensor.data_ptr() + dst_off,
+                                        nbytes16, dtype_code(dtype), scale, self.launch_cfg("one_shot", nbytes16, blocks)), "one_shot"
+        if v == "one_shot":
+            v = "multimem" if self.has_multicast else "two_shot"
+        if v == "multimem" and not (src.has_multicast and dst.has_multicast):
+            v = "two_shot"
+        code = C.AR_MULTIMEM if v == "multimem" else C.AR_TWO_SHOT
+        op = C.AllReduceOp(self.comm, src.buf, dst.buf, src.offset + src_off, dst.offset + dst_off, nbytes16, dtype_code(dtype), scale, code,
+                           self.launch_cfg(v, nbytes16, blocks))
+        return op, v
+
+    # -- blocking-API fast path --------------------------------------------------------------------------------------
+    def allreduce_tensor(self, tensor: torch.Tensor, average: bool) -> bool:
+        """All-reduce an arbitrary contiguous CUDA tensor on the *current* stream through the peer kernels."""
+        C = native()
+        nbytes = tensor.numel() * tensor.element_size()
+        if nbytes == 0:
+            return True
+        stream = torch.cuda.current_stream().cuda_stream
+        scale = 1.0 / self.world if average else 1.0
+        if nbytes % 16 == 0 and tensor.data_ptr() % 16 == 0 and nbytes <= ONE_SHOT_SLOT:
+            st = self.staging()
+            op = C.AllReduceOneShotOp(self.comm, st.buf, ONE_SHOT_SLOT, tensor.data_ptr(), tensor.data_ptr(), nbytes, dtype_code(tensor.dtype),
+                                      scale, self.launch_cfg("one_shot", nbytes))
+            C.run_op(op, stream, self.device.index)
+            return True
+        padded = _round_up(nbytes, 16 * self.world)
+        if self._workspace is None or self._workspace.nbytes < padded:
+            # collective growth: every rank sees the same message sizes
+            self._workspace = self.alloc(max(padded, 64 * 1024 ** 2))
+        ws = self._workspace
+        flat = ws.tensor[:nbytes].view(tensor.dtype)
+        flat.copy_(tensor.reshape(-1))
+        if padded > nbytes:
+            ws.tensor[nbytes:padded].zero_()
+        op, _ = self.make_allreduce_op(ws, ws, padded, tensor.dtype, average, "auto")
+        C.run_op(op, stream, self.device.index)
+        tensor.reshape(-1).copy_(flat)
+        return True
+
+    def barrier(self, stream: Optional[torch.cuda.Stream] = None):
+        s = (stream or torch.cuda.current_stream()).cuda_stream
+        self.comm.barrier(s)
+
+    def check_error(self):
+        code = self.comm.error_code()
+        if code:
+            raise RuntimeError({1: "peer kernel timed out waiting for another rank", 2: "peer kernel aborted", 3: "grid barrier timed out"}.get(code, f"peer kernel error {code}"))
