@@ -352,6 +352,9 @@ class BaguaBucket:
                 return self
             self.append_python_op(lambda _name: quant.bytegrad_allreduce_fallback(self, pg, average), group=group)
             return self
+        if n == 1:
+            self.allreduce_variant = "none(world=1)"
+            return self  # nothing to reduce; the scheduler still orders the bucket (events only)
         if eng is not None and self._slice is not None and self.backend_tensor.dtype in (torch.float32, torch.float16, torch.bfloat16):
             nbytes = self.backend_tensor.numel() * self.backend_tensor.element_size()
             v = "two_shot" if (scattergather and variant == "auto") else variant

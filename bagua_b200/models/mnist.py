@@ -1,0 +1,22 @@
+"""The small CNN of the reference's MNIST example (examples/mnist/main.py:15-45): conv32-conv64-fc128-fc10."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class MnistNet(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.conv1 = nn.Conv2d(1, 32, 3, 1)
+        self.conv2 = nn.Conv2d(32, 64, 3, 1)
+        self.dropout1 = nn.Dropout(0.25)
+        self.dropout2 = nn.Dropout(0.5)
+        self.fc1 = nn.Linear(9216, 128)
+        self.fc2 = nn.Linear(128, 10)
+
+    def forward(self, x):
+        x = F.relu(self.conv1(x))
+        x = F.max_pool2d(F.relu(self.conv2(x)), 2)
+        x = torch.flatten(self.dropout1(x), 1)
+        x = self.dropout2(F.relu(self.fc1(x)))
+        return F.log_softmax(self.fc2(x), dim=1)

@@ -1,0 +1,64 @@
+"""Spawn-N-local-processes harness (same idea as the reference's tests/internal/multi_process.py:9-53): fabricate the
+launcher environment, run ``fn(rank, world, *args)`` in every process, collect the returned (picklable) results."""
+from __future__ import annotations
+
+import os
+import socket
+import traceback
+from contextlib import closing
+
+import torch.multiprocessing as mp
+
+
+def free_port() -> int:
+    with closing(socket.socket(socket.AF_INET, socket.SOCK_STREAM)) as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _entry(rank, world, port, fn, args, use_cuda, extra_env, queue):
+    try:
+        os.environ.update(
+            RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), LOCAL_WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+            MASTER_PORT=str(port), BAGUA_PEER_TIMEOUT_S="20", BAGUA_COMM_TIMEOUT_S="120",
+        )
+        os.environ.update(extra_env or {})
+        if not use_cuda:
+            os.environ["BAGUA_FORCE_CPU"] = "1"
+            os.environ["CUDA_VISIBLE_DEVICES"] = ""
+        else:
+            import torch
+
+            torch.cuda.set_device(rank)
+        out = fn(rank, world, *args)
+        queue.put((rank, "ok", out))
+    except Exception:  # noqa: BLE001
+        queue.put((rank, "error", traceback.format_exc()))
+
+
+def run_distributed(fn, world: int = 2, args=(), use_cuda: bool = False, timeout: float = 240.0, extra_env=None):
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=_entry, args=(r, world, port, fn, args, use_cuda, extra_env, queue)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = {}
+    errors = []
+    try:
+        for _ in range(world):
+            rank, status, payload = queue.get(timeout=timeout)
+            if status == "ok":
+                results[rank] = payload
+            else:
+                errors.append(f"rank {rank}:\n{payload}")
+    except Exception as e:  # queue.Empty → timeout
+        errors.append(f"timeout waiting for workers: {e!r}")
+    for p in procs:
+        p.join(timeout=20)
+        if p.is_alive():
+            p.kill()
+            errors.append(f"process {p.pid} had to be killed")
+    if errors:
+        raise AssertionError("\n".join(errors))
+    return [results[r] for r in range(world)]

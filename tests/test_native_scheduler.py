@@ -1,0 +1,130 @@
+"""C++ CommScheduler semantics (reference behaviours: lib.rs:270-337): strict in-order scheduling, duplicate detection,
+python ops on the worker thread, waitable completion, watchdog."""
+import threading
+import time
+
+import pytest
+
+from bagua_b200.core import native
+
+
+def make(names, base=0x1000):
+    C = native()
+    return [C.Tensor(n, base + 64 * i, 4, 0, -1) for i, n in enumerate(names)]
+
+
+def test_in_order_scheduling_and_python_ops():
+    C = native()
+    be = C.Backend(10, -1, 0, 30.0)
+    order = []
+    t0, t1 = make(["a", "b"]), make(["c"], base=0x2000)
+    b0, b1 = C.Bucket("b0", t0), C.Bucket("b1", t1)
+    b0.append_python_op(lambda name: order.append(name))
+    b1.append_python_op(lambda name: order.append(name))
+    be.register_ordered_buckets([b0, b1])
+    # bucket 1 becomes ready first but must wait behind bucket 0
+    be.mark_communication_ready(t1[0], 0)
+    time.sleep(0.05)
+    assert order == []
+    be.mark_communication_ready(t0[0], 0)
+    be.mark_communication_ready(t0[1], 0)
+    assert be.wait_pending_comm_ops(0, True) == 2
+    assert order == ["b0", "b1"]
+    # a second iteration works (flags are reset, buckets rotate)
+    for t in t0 + t1:
+        be.mark_communication_ready(t, 0)
+    assert be.wait_pending_comm_ops(0, True) == 2
+    assert order == ["b0", "b1", "b0", "b1"]
+    assert be.scheduled_total() == 4
+    be.shutdown()
+
+
+def test_duplicate_detection():
+    C = native()
+    be = C.Backend(10, -1, 0, 30.0)
+    a = C.Tensor("x", 0x1000, 4, 0, -1)
+    b = C.Tensor("x", 0x2000, 4, 0, -1)
+    with pytest.raises(ValueError):
+        be.register_ordered_buckets([C.Bucket("b0", [a]), C.Bucket("b1", [b])])
+    c = C.Tensor("y", 0x1000, 4, 0, -1)
+    with pytest.raises(ValueError):
+        be.register_ordered_buckets([C.Bucket("b0", [a]), C.Bucket("b1", [c])])
+    with pytest.raises(ValueError):
+        C.Bucket("mixed", [a, C.Tensor("z", 0x3000, 4, 1, -1)])  # mixed dtypes
+    be.shutdown()
+
+
+def test_padding_tensor_is_always_ready_and_contiguity():
+    C = native()
+    be = C.Backend(10, -1, 0, 30.0)
+    t = C.Tensor("w", 0x1000, 4, 0, -1)
+    pad = C.Tensor("pad", 0x1010, 4, 0, -1)
+    b = C.Bucket("b", [t, pad])
+    assert b.contiguous() and b.flat_ptr() == 0x1000 and b.bytes() == 32
+    b.mark_padding(1)
+    hits = []
+    b.append_python_op(lambda n: hits.append(n))
+    be.register_ordered_buckets([b])
+    be.mark_communication_ready(t, 0)
+    assert be.wait_pending_comm_ops(0, True) == 1 and hits == ["b"]
+    be.shutdown()
+
+
+def test_python_op_error_is_reported():
+    C = native()
+    be = C.Backend(10, -1, 0, 30.0)
+    (t,) = make(["e"])
+    b = C.Bucket("b", [t])
+
+    def boom(_):
+        raise RuntimeError("boom")
+
+    b.append_python_op(boom)
+    be.register_ordered_buckets([b])
+    be.mark_communication_ready(t, 0)
+    with pytest.raises(RuntimeError, match="boom"):
+        be.wait_pending_comm_ops(0, True)
+    be.shutdown()
+
+
+def test_watchdog_reports_stuck_op():
+    C = native()
+    be = C.Backend(10, -1, 0, 0.5)
+    be.set_watchdog_fatal(False)
+    (t,) = make(["s"])
+    b = C.Bucket("b", [t])
+    release = threading.Event()
+    b.append_python_op(lambda _: release.wait(5))
+    be.register_ordered_buckets([b])
+    be.mark_communication_ready(t, 0)
+    with pytest.raises(RuntimeError, match="watchdog"):
+        be.wait_pending_comm_ops(0, True)
+    release.set()
+    time.sleep(0.1)
+    assert "watchdog" in be.watchdog_error()
+    be.shutdown()
+
+
+def test_ready_spans_are_recorded():
+    C = native()
+    be = C.Backend(10, -1, 0, 30.0)
+    be.set_record_spans(True)
+    ts = make(["p", "q"])
+    b = C.Bucket("b", ts)
+    be.register_ordered_buckets([b])
+    be.mark_communication_ready(ts[1], 0)
+    be.mark_communication_ready(ts[0], 0)
+    be.wait_pending_comm_ops(0, True)
+    spans = be.pop_ready_spans()
+    assert [s[0] for s in spans] == ["q", "p"]
+    be.shutdown()
+
+
+def test_shift_one_peer_formula():
+    # reference: decentralized_full_precision_synchronous.rs:81-85 (and tests/torch_api/test_decentralized.py:251-259)
+    C = native()
+    for n in (2, 4, 8):
+        for step in range(6):
+            peers = [C.PeerAverageOp.shift_one_peer(r, n, step) for r in range(n)]
+            for r, p in enumerate(peers):
+                assert peers[p] == r and p != r  # a perfect matching

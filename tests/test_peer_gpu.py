@@ -1,0 +1,155 @@
+"""Multi-GPU tests of the NVSwitch peer kernels (≥ 2 GPUs): every fused collective against torch.distributed / the
+python oracles, then the algorithms end to end."""
+import pytest
+import torch
+
+from tests.mp_utils import run_distributed
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+
+
+def _ngpu():
+    return min(torch.cuda.device_count(), 8)
+
+
+def _allreduce_worker(rank, world):
+    import torch.distributed as dist
+
+    import bagua_b200 as bagua
+    from bagua_b200.core import native
+
+    bagua.init_process_group()
+    pg = bagua.communication._get_default_group()
+    eng = pg.peer_engine()
+    assert eng is not None, "peer engine must be available on a single NVSwitch node"
+    dev = torch.device("cuda", rank)
+    C = native()
+    results = {"multicast": eng.has_multicast}
+    stream = torch.cuda.current_stream().cuda_stream
+    for dtype in (torch.float32, torch.bfloat16, torch.float16):
+        for numel in (4096, 1 << 20, (1 << 22) + 4096):
+            nbytes = numel * torch.empty(0, dtype=dtype).element_size()
+            sl = eng.alloc(nbytes)
+            for variant in ["one_shot", "two_shot"] + (["multimem"] if eng.has_multicast else []):
+                torch.manual_seed(100 + rank)
+                x = torch.randn(numel, device=dev).to(dtype)
+                t = sl.view(dtype, numel)
+                t.copy_(x)
+                ref = x.float().clone()
+                dist.all_reduce(ref)
+                ref /= world
+                op, chosen = eng.make_allreduce_op(sl, sl, nbytes, dtype, True, variant)
+                torch.cuda.synchronize()
+                dist.barrier()
+                C.run_op(op, stream, rank)
+                torch.cuda.synchronize()
+                tol = 1e-5 if dtype == torch.float32 else 2e-2
+                err = (t.float() - ref).abs().max().item()
+                assert err <= tol * max(1.0, ref.abs().max().item()), f"{dtype} {numel} {variant}->{chosen}: err {err}"
+            sl.free()
+    # blocking API fast path on an arbitrary tensor
+    y = torch.full((12345,), float(rank + 1), device=dev)
+    bagua.allreduce_inplace(y, op=bagua.ReduceOp.AVG)
+    assert torch.allclose(y, torch.full_like(y, (world + 1) / 2))
+    assert eng.comm.error_code() == 0
+    return results
+
+
+def test_peer_allreduce_variants():
+    run_distributed(_allreduce_worker, world=_ngpu(), use_cuda=True)
+
+
+def _bytegrad_worker(rank, world):
+    import torch.distributed as dist
+
+    import bagua_b200 as bagua
+    from bagua_b200.core import dtype_code, native
+    from bagua_b200.ops import quant
+
+    bagua.init_process_group()
+    pg = bagua.communication._get_default_group()
+    eng = pg.peer_engine()
+    C = native()
+    dev = torch.device("cuda", rank)
+    for dtype in (torch.float32, torch.bfloat16):
+        numel = 32 * world * 257
+        torch.manual_seed(7 + rank)
+        x = torch.randn(numel, device=dev).to(dtype)
+        # oracle: the reference pipeline on torch.distributed
+        class FakeBucket:
+            def __init__(self, t):
+                self.t = t
+
+            def _flat_or_gather(self):
+                return self.t, None
+
+        ref = x.clone()
+        quant.bytegrad_allreduce_fallback(FakeBucket(ref), pg, True)
+        data = x.clone()
+        box = C.ByteGradOp.box_bytes(numel, world)
+        inbox, outbox = eng.alloc(box), eng.alloc(box)
+        op = C.ByteGradOp(eng.comm, data.data_ptr(), numel, dtype_code(dtype), inbox.buf, inbox.offset, outbox.buf, outbox.offset, True, C.LaunchCfg(2 * world, 256))
+        torch.cuda.synchronize()
+        dist.barrier()
+        for _ in range(2):  # run twice: exercises the parity double-buffering
+            data.copy_(x)
+            C.run_op(op, torch.cuda.current_stream().cuda_stream, rank)
+        torch.cuda.synchronize()
+        step = (x.float().max() - x.float().min()).item() / 255
+        assert (data.float() - ref.float()).abs().max().item() <= 2.5 * step
+        assert eng.comm.error_code() == 0
+    return True
+
+
+def test_bytegrad_fused_matches_pipeline():
+    run_distributed(_bytegrad_worker, world=_ngpu(), use_cuda=True)
+
+
+def _algorithms_worker(rank, world, name):
+    import torch.distributed as dist
+    import torch.nn as nn
+
+    import bagua_b200 as bagua
+    from bagua_b200.parallel.algorithms import Algorithm, q_adam
+
+    bagua.init_process_group()
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(rank)
+    model = nn.Sequential(nn.Linear(32, 64), nn.ReLU(), nn.Linear(64, 16)).to(dev)
+    if name == "qadam":
+        opt = q_adam.QAdamOptimizer(model.parameters(), lr=1e-3, warmup_steps=3)
+        algo = q_adam.QAdamAlgorithm(opt)
+    else:
+        opt = torch.optim.SGD(model.parameters(), lr=0.05)
+        kw = {"sync_interval_ms": 20} if name == "async" else {}
+        if name == "decentralized_shift_one":
+            algo = Algorithm.init("decentralized", peer_selection_mode="shift_one")
+        else:
+            algo = Algorithm.init(name, **kw)
+    model = model.with_bagua([opt], algo)
+    for it in range(8):
+        x = torch.randn(8, 32, device=dev)
+        opt.zero_grad()
+        model(x).square().mean().backward()
+        opt.step()
+    if name == "async":
+        model.bagua_algorithm.abort(model)
+    torch.cuda.synchronize()
+    flat = torch.cat([p.data.view(-1) for p in model.parameters()])
+    assert torch.isfinite(flat).all()
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    spread = max((g - gathered[0]).abs().max().item() for g in gathered)
+    eng = bagua.communication._get_default_group().peer_engine()
+    assert eng.comm.error_code() == 0
+    return spread
+
+
+@pytest.mark.parametrize("name", ["gradient_allreduce", "bytegrad", "decentralized", "decentralized_shift_one", "low_precision_decentralized", "qadam", "async"])
+def test_algorithms_on_peer_kernels(name):
+    world = _ngpu() if _ngpu() % 2 == 0 else _ngpu() - 1
+    spreads = run_distributed(_algorithms_worker, world=world, args=(name,), use_cuda=True)
+    if name == "gradient_allreduce":
+        assert max(spreads) < 1e-6  # replicas stay bit-close
+    elif name in ("bytegrad", "qadam"):
+        assert max(spreads) < 1e-2
