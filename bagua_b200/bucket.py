@@ -17,6 +17,7 @@ import torch.distributed as dist
 from . import communication as comm_mod
 from .core import dtype_code, native
 from .ops import quant
+from .tensor import dense_strides
 from .utils import check_contiguous
 
 __all__ = ["BaguaBucket", "BucketArena", "bucket_arena"]
@@ -222,15 +223,14 @@ class BaguaBucket:
                 return
             else:
                 flat = torch.zeros(total, dtype=effs[0].dtype, device=effs[0].device)
-            off = 0
-            for e in effs:
-                flat[off : off + e.numel()].copy_(e.reshape(-1))
-                off += e.numel()
             storage = flat.untyped_storage()
             off = flat.storage_offset()
-            for t in self._all_tensors:
+            for t, e in zip(self._all_tensors, effs):
+                # copy in *memory* order (dense permutations such as channels_last keep their strides)
+                dst = torch.empty(0, dtype=e.dtype, device=e.device).set_(storage, off, e.shape, dense_strides(e))
+                dst.copy_(e)
                 t.bagua_set_storage(storage, off)
-                off += t.bagua_getter_closure().numel()
+                off += e.numel()
         self.backend_tensor = flat
         assert self.check_flatten(), "flatten failed: effective tensors are not contiguous"
 

@@ -14,6 +14,7 @@ from typing import Dict, List, Optional
 import torch
 
 from ..core import dtype_code, native
+from ..tensor import dense_strides
 
 __all__ = ["FusedSGD", "FusedAdam", "flat_sgd_", "flat_adam_", "multi_tensor_plan"]
 
@@ -99,8 +100,9 @@ class _Segment:
         self.param_flat = torch.zeros(self.numel, dtype=pdtype, device=dev)
         with torch.no_grad():
             for p, off in zip(self.params, self.offsets):
-                self.param_flat[off : off + p.numel()].copy_(p.data.reshape(-1))
-                p.data = self.param_flat[off : off + p.numel()].view(p.shape)
+                dst = torch.as_strided(self.param_flat, p.shape, p.stride(), off)
+                dst.copy_(p.data)
+                p.data = dst
         self.master = None
         if master_weights and pdtype in (torch.float16, torch.bfloat16):
             self.master = self.param_flat.float()
@@ -124,7 +126,7 @@ class _Segment:
 
     def view_of(self, flat: torch.Tensor, idx: int) -> torch.Tensor:
         p, off = self.params[idx], self.offsets[idx]
-        return flat[off : off + p.numel()].view(p.shape)
+        return torch.as_strided(flat, p.shape, p.stride(), off)
 
 
 def _can_flatten(group_params: List[torch.nn.Parameter], all_params: List[torch.nn.Parameter]) -> bool:
@@ -135,7 +137,10 @@ def _can_flatten(group_params: List[torch.nn.Parameter], all_params: List[torch.
         return False
     mine = set(id(p) for p in group_params)
     for p in group_params:
-        if p.grad is None or p.grad.dtype != g0.dtype or p.dtype != group_params[0].dtype or not p.grad.is_contiguous() or not p.is_contiguous():
+        if p.grad is None or p.grad.dtype != g0.dtype or p.dtype != group_params[0].dtype:
+            return False
+        # flat index i must address the same logical element in grad and param: identical dense layouts
+        if p.grad.stride() != p.stride() or dense_strides(p) != p.stride():
             return False
         if p.grad.untyped_storage().data_ptr() != g0.untyped_storage().data_ptr():
             return False

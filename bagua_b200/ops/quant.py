@@ -32,11 +32,16 @@ def compressed_size(numel: int, n_chunks: int) -> int:
 
 
 # ---- torch implementation (oracle / CPU) --------------------------------------------------------------------
+def _scale(mn: torch.Tensor, mx: torch.Tensor) -> torch.Tensor:
+    # a true fp32 division like the kernel's 255/(max-min+eps) — `255.0 / tensor` would be reciprocal()*255 (two roundings)
+    return torch.div(torch.full_like(mx, LEVELS), (mx - mn) + torch.full_like(mx, EPS))
+
+
 def torch_compress_chunk(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """Returns (minmax[2] in x.dtype, uint8 levels) for one chunk."""
     xf = x.float()
     mn, mx = xf.min(), xf.max()
-    scale = LEVELS / (mx - mn + EPS)
+    scale = _scale(mn, mx)
     upper = torch.round(mx * scale)
     lower = upper - LEVELS
     level = torch.minimum(torch.round(xf * scale), upper)
@@ -45,7 +50,7 @@ def torch_compress_chunk(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 
 def torch_decompress_chunk(minmax: torch.Tensor, q: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     mn, mx = minmax[0].float(), minmax[1].float()
-    scale = LEVELS / (mx - mn + EPS)
+    scale = _scale(mn, mx)
     upper = torch.round(mx * scale)
     lower = upper - LEVELS
     return ((q.float() + lower) / scale).to(dtype)

@@ -176,8 +176,9 @@ class BaguaDistributedDataParallel:
                         state_tensors.append(v)
                     else:
                         scalars[f"state{pid}.{k}"] = v
-        on_dev = [t for t in state_tensors if t.device.type == ("cuda" if self._on_cuda else "cpu")]
-        off_dev = [t for t in state_tensors if t not in on_dev]
+        want = "cuda" if self._on_cuda else "cpu"
+        on_dev = [t for t in state_tensors if t.device.type == want]
+        off_dev = [t for t in state_tensors if t.device.type != want]
         if on_dev:
             comm_mod.broadcast_coalesced(on_dev, src=0, comm=comm)
         for t in off_dev:  # e.g. CPU "step" tensors of GPU optimizers

@@ -13,7 +13,24 @@ import torch
 
 from .core import dtype_code, native
 
-__all__ = ["BaguaTensor"]
+__all__ = ["BaguaTensor", "dense_strides"]
+
+
+def dense_strides(t: torch.Tensor):
+    """Strides to use when ``t`` is re-homed into a flat buffer: its own strides when it is a dense permutation
+    (contiguous, channels_last, ...) so the memory order — and the autograd gradient-layout contract — is preserved;
+    plain contiguous strides otherwise."""
+    if t.numel() == 0 or t.is_contiguous():
+        return t.stride()
+    order = sorted(range(t.dim()), key=lambda d: (t.stride(d), t.size(d)))
+    expect = 1
+    for d in order:
+        if t.size(d) == 1:
+            continue
+        if t.stride(d) != expect:
+            return torch.empty(t.shape).stride()
+        expect *= t.size(d)
+    return t.stride()
 
 
 def _device_id(t: torch.Tensor) -> int:
@@ -116,12 +133,13 @@ class BaguaTensor:
     def bagua_set_storage(self, storage, storage_offset: int = 0):
         """Re-point the effective tensor at ``storage[storage_offset:]`` keeping shape (reference tensor.py:239-263)."""
         eff = self.bagua_getter_closure()
+        strides = dense_strides(eff)
         with torch.no_grad():
             if getattr(self, "_bagua_setter_closure", None) is not None:
-                new = torch.empty(0, dtype=eff.dtype, device=eff.device).set_(storage, storage_offset, eff.shape, eff.stride() if eff.is_contiguous() else None)
+                new = torch.empty(0, dtype=eff.dtype, device=eff.device).set_(storage, storage_offset, eff.shape, strides)
                 self.bagua_setter_closure(new)
             else:
-                eff.set_(storage, storage_offset, eff.shape)
+                eff.set_(storage, storage_offset, eff.shape, strides)
                 self._bagua_refresh_backend_tensor()
 
 

@@ -16,6 +16,32 @@ def free_port() -> int:
         return s.getsockname()[1]
 
 
+def _portable(obj):
+    """Tensors travel by value (numpy) so the parent never depends on a child's shared-memory handles."""
+    import torch
+
+    if isinstance(obj, torch.Tensor):
+        t = obj.detach().cpu()
+        return ("__tensor__", t.float().numpy() if t.dtype in (torch.bfloat16, torch.float16) else t.numpy(), str(t.dtype))
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_portable(o) for o in obj)
+    if isinstance(obj, dict):
+        return {k: _portable(v) for k, v in obj.items()}
+    return obj
+
+
+def _restore(obj):
+    import torch
+
+    if isinstance(obj, tuple) and len(obj) == 3 and obj[0] == "__tensor__":
+        return torch.from_numpy(obj[1]).to(getattr(torch, obj[2].split(".")[1]))
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_restore(o) for o in obj)
+    if isinstance(obj, dict):
+        return {k: _restore(v) for k, v in obj.items()}
+    return obj
+
+
 def _entry(rank, world, port, fn, args, use_cuda, extra_env, queue):
     try:
         os.environ.update(
@@ -31,7 +57,7 @@ def _entry(rank, world, port, fn, args, use_cuda, extra_env, queue):
 
             torch.cuda.set_device(rank)
         out = fn(rank, world, *args)
-        queue.put((rank, "ok", out))
+        queue.put((rank, "ok", _portable(out)))
     except Exception:  # noqa: BLE001
         queue.put((rank, "error", traceback.format_exc()))
 
@@ -49,7 +75,7 @@ def run_distributed(fn, world: int = 2, args=(), use_cuda: bool = False, timeout
         for _ in range(world):
             rank, status, payload = queue.get(timeout=timeout)
             if status == "ok":
-                results[rank] = payload
+                results[rank] = _restore(payload)
             else:
                 errors.append(f"rank {rank}:\n{payload}")
     except Exception as e:  # queue.Empty → timeout
