@@ -28,17 +28,24 @@ def is_fused_optimizer(optimizer: torch.optim.Optimizer) -> bool:
     return hasattr(optimizer, "_bagua_fused_optimizer")
 
 
-def _flatten_tensors_(tensors: List[torch.Tensor]):
-    """Re-point ``tensors`` (same dtype/device) into one fresh contiguous storage, in order."""
+def _flatten_params_(params: List[torch.nn.Parameter], what: str):
+    """Re-point the weights (``what='data'``) or gradients (``what='grad'``) of ``params`` into one fresh contiguous
+    storage, in order, keeping each tensor's (dense) strides."""
+    from ...tensor import dense_strides
+
+    tensors = [p.data if what == "data" else p.grad for p in params]
     total = sum(t.numel() for t in tensors)
     flat = torch.zeros(total, dtype=tensors[0].dtype, device=tensors[0].device)
     off = 0
     with torch.no_grad():
-        for t in tensors:
-            n = t.numel()
-            flat[off : off + n].copy_(t.reshape(-1))
-            t.set_(flat.untyped_storage(), flat.storage_offset() + off, t.shape)
-            off += n
+        for p, t in zip(params, tensors):
+            view = torch.as_strided(flat, t.shape, dense_strides(t), off)
+            view.copy_(t)
+            if what == "data":
+                p.data = view
+            else:
+                p.grad = view
+            off += t.numel()
     return flat
 
 
@@ -60,9 +67,9 @@ def flatten_params_and_grads_(optimizer: torch.optim.Optimizer):
                 params = sorted(params, key=lambda p: p.grad.data_ptr())
             weight_comm = any(getattr(p, "_bagua_bucket", None) is not None and getattr(p, "_bagua_getter_closure", None) is None for p in params)
             if not weight_comm and not check_contiguous([p.data for p in params]):
-                _flatten_tensors_([p.data for p in params])
+                _flatten_params_(params, "data")
             if not bucketed and not check_contiguous([p.grad for p in params]):
-                _flatten_tensors_([p.grad for p in params])
+                _flatten_params_(params, "grad")
 
 
 def calculate_mutual_groups(tensors_list: List[List[torch.Tensor]]) -> List[List[int]]:

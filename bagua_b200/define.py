@@ -38,6 +38,13 @@ def get_tensor_declaration_bytes(td: TensorDeclaration) -> int:
     return td["num_elements"] * _DTYPE_BYTES[dtype]
 
 
+def _as_declaration(td) -> TensorDeclaration:
+    d = dict(td)
+    if not isinstance(d.get("dtype"), TensorDtype):
+        d["dtype"] = TensorDtype(d["dtype"])
+    return TensorDeclaration(**d)
+
+
 class BaguaCoreTelemetrySpan(BaseModel):
     trace_id: int
     action: str
@@ -63,7 +70,7 @@ class BaguaHyperparameter(BaseModel):
                 self.__dict__[key] = value
         for key, value in param_dict.items():
             if key in tmp and key == "buckets":
-                self.buckets = [[TensorDeclaration(**td) if isinstance(td, dict) else td for td in b] for b in value]
+                self.buckets = [[_as_declaration(td) for td in b] for b in value]
         return self
 
     # pydantic v1 spelling used by the reference's call sites

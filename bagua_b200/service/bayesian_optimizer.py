@@ -106,7 +106,11 @@ class BayesianOptimizer:
         yn = (y - mu) / sd
         kernel = ConstantKernel(1.0, (1e-2, 1e2)) * Matern(length_scale=0.3, length_scale_bounds=(1e-2, 1e1), nu=2.5) + WhiteKernel(1e-3, (1e-6, 1e0))
         gp = GaussianProcessRegressor(kernel=kernel, normalize_y=False, n_restarts_optimizer=1, random_state=self._rng.randint(1 << 30))
-        gp.fit(X, yn)
+        import warnings
+
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            gp.fit(X, yn)
         cand = self._rng.rand(512, len(self.names))
         # snap candidates to the decodable lattice so integer/bool dims are evaluated where they will be sampled
         cand = np.asarray([self._encode(self._decode(c)) for c in cand])

