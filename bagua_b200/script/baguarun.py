@@ -1,0 +1,68 @@
+r"""``baguarun``: start the launcher on several hosts over ssh (reference: bagua/script/baguarun.py:1-227, parallel-ssh based).
+
+    baguarun --host_list host1,host2 --ssh_port 22 --nproc_per_node 8 [-x ENV_NAME ...] train.py --arg ...
+
+Every host runs ``python -m bagua_b200.distributed.launch --nnodes N --node_rank i --master_addr host1 ...``; output is
+streamed with a ``[host]`` prefix; the exit status is the first non-zero one."""
+from __future__ import annotations
+
+import argparse
+import os
+import shlex
+import subprocess
+import sys
+import threading
+from typing import List
+
+
+def parse_args(argv=None):
+    p = argparse.ArgumentParser(description="launch a bagua_b200 job on several hosts over ssh")
+    p.add_argument("--host_list", type=str, default=os.environ.get("BAGUA_NODE_DOMAIN_NAMES", ""), help="comma separated hosts (first = master)")
+    p.add_argument("--ssh_port", type=int, default=int(os.environ.get("BAGUA_SSH_PORT", 22)))
+    p.add_argument("--nproc_per_node", type=int, default=1)
+    p.add_argument("--master_port", type=int, default=29500)
+    p.add_argument("-x", dest="export_env", action="append", default=[], help="environment variable to forward to every host")
+    p.add_argument("--dry_run", action="store_true", help="print the per-host commands instead of running them")
+    p.add_argument("launch_args", nargs=argparse.REMAINDER, help="[launcher flags] script [script args]")
+    return p.parse_args(argv)
+
+
+def build_commands(args) -> List[List[str]]:
+    hosts = [h.strip() for h in args.host_list.split(",") if h.strip()]
+    if not hosts:
+        raise SystemExit("baguarun: --host_list (or BAGUA_NODE_DOMAIN_NAMES) is required")
+    exports = " ".join(f"{k}={shlex.quote(os.environ[k])}" for k in args.export_env if k in os.environ)
+    cmds = []
+    for i, host in enumerate(hosts):
+        remote = (f"cd {shlex.quote(os.getcwd())} && {exports} {shlex.quote(sys.executable)} -m bagua_b200.distributed.launch "
+                  f"--nnodes={len(hosts)} --node_rank={i} --nproc_per_node={args.nproc_per_node} --master_addr={hosts[0]} --master_port={args.master_port} "
+                  + " ".join(shlex.quote(a) for a in args.launch_args))
+        cmds.append(["ssh", "-o", "StrictHostKeyChecking=no", "-p", str(args.ssh_port), host, remote])
+    return cmds
+
+
+def main(argv=None) -> int:
+    args = parse_args(argv)
+    cmds = build_commands(args)
+    if args.dry_run:
+        for c in cmds:
+            print(" ".join(shlex.quote(x) for x in c))
+        return 0
+    procs = [subprocess.Popen(c, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for c in cmds]
+
+    def pump(p, host):
+        for line in p.stdout:
+            sys.stdout.write(f"[{host}] {line}")
+
+    threads = [threading.Thread(target=pump, args=(p, c[-2]), daemon=True) for p, c in zip(procs, cmds)]
+    for t in threads:
+        t.start()
+    rc = 0
+    for p in procs:
+        r = p.wait()
+        rc = rc or r
+    return rc
+
+
+if __name__ == "__main__":
+    sys.exit(main())
