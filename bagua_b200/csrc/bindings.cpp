@@ -239,6 +239,20 @@ PYBIND11_MODULE(_C, m) {
     m.def("qadam_momentum", [](uint64_t m1, uint64_t grad, int gdt, size_t n, float beta1, uint64_t stream) {
         launch_qadam_momentum(reinterpret_cast<float*>(m1), reinterpret_cast<const void*>(grad), gdt, n, beta1, S(stream));
     });
+    m.def("moe_scatter",
+          [](std::shared_ptr<PeerComm> comm, SymmBuf dst, size_t dst_off, uint64_t rows, uint64_t eidx, uint64_t sidx, uint64_t scale, int n_tok, int K,
+             int M, int E_local, int C, int dtype, int nblocks, uint64_t stream) {
+              launch_moe_scatter(comm->ctx(), dst.buf, dst_off, reinterpret_cast<const void*>(rows), reinterpret_cast<const int64_t*>(eidx),
+                                 reinterpret_cast<const int64_t*>(sidx), reinterpret_cast<const float*>(scale), n_tok, K, M, E_local, C, dtype, nblocks,
+                                 S(stream));
+          });
+    m.def("moe_gather",
+          [](std::shared_ptr<PeerComm> comm, SymmBuf src, size_t src_off, uint64_t out, uint64_t eidx, uint64_t sidx, uint64_t weights, uint64_t picked,
+             int n_tok, int K, int M, int E_local, int C, int dtype, int nblocks, uint64_t stream) {
+              launch_moe_gather(comm->ctx(), src.buf, src_off, reinterpret_cast<void*>(out), reinterpret_cast<const int64_t*>(eidx),
+                                reinterpret_cast<const int64_t*>(sidx), reinterpret_cast<const float*>(weights), reinterpret_cast<void*>(picked), n_tok, K, M,
+                                E_local, C, dtype, nblocks, S(stream));
+          });
     m.def("minmax_uint8_compress",
           [](uint64_t in, size_t numel, int dtype, int n_chunks, int target_chunk, uint64_t out, uint64_t scratch, uint64_t stream) {
               launch_minmax_uint8_compress(reinterpret_cast<const void*>(in), numel, dtype, n_chunks, target_chunk,

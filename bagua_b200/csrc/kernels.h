@@ -45,6 +45,16 @@ void launch_peer_average(const PeerCtx& ctx, const PeerBuf& weights, size_t off,
                          int nblocks, int nthreads, cudaStream_t stream);
 void launch_peer_barrier(const PeerCtx& ctx, cudaStream_t stream);
 
+// ---- MoE expert-parallel token exchange (moe_kernels.cu) ------------------------------------------------
+// Symmetric row buffers have layout [world(src rank), E_local, C, M]. scatter: rows_in[s] → owner's slot (optionally scaled
+// per (s,k)); gather: out[s] = Σ_k w[s,k]·owner_row, optionally saving the fetched rows in picked[S,K,M].
+void launch_moe_scatter(const PeerCtx& ctx, const PeerBuf& dst, size_t dst_off, const void* rows_in, const int64_t* expert_idx,
+                        const int64_t* slot_idx, const float* scale, int S, int K, int M, int E_local, int C, int dtype, int nblocks,
+                        cudaStream_t stream);
+void launch_moe_gather(const PeerCtx& ctx, const PeerBuf& src, size_t src_off, void* out, const int64_t* expert_idx, const int64_t* slot_idx,
+                       const float* weights, void* picked, int S, int K, int M, int E_local, int C, int dtype, int nblocks,
+                       cudaStream_t stream);
+
 // ---- quantised (MinMaxUInt8) collectives (bytegrad_kernels.cu) ------------------------------------------
 // Wire format per chunk (same as the reference, kernels/bagua_kernels.cu:456-501): [min:T][max:T][pad → 32 B][u8 payload, padded → 32 B]
 inline size_t align32(size_t x) { return (x + 31) / 32 * 32; }

@@ -1,9 +1,140 @@
-"""NVSwitch path of MoE dispatch/combine (kernels in csrc/moe_kernels.cu).  Filled in by the peer-kernel milestone;
-until the kernels are registered ``get_context`` reports that the fused path is unavailable."""
+"""NVSwitch path of MoE dispatch/combine: autograd functions over the peer scatter/gather kernels (csrc/moe_kernels.cu).
+
+Forward and backward each need one *scatter* (rows pushed into the owner GPU's capacity slots) and one *gather* (rows pulled
+from the owners, weighted and summed):
+
+=================  =============================================  ==========================================
+                   forward                                        backward
+=================  =============================================  ==========================================
+dispatch           scatter(tokens)                                gather(grad_dispatched, w=1)
+combine            gather(expert_out, w) (+ keeps fetched rows)   scatter(grad_out · w)  and  grad_w = <grad_out, fetched rows>
+=================  =============================================  ==========================================
+
+Two symmetric buffers per (group, shape) are shared by all MoE layers: results are copied out right away (a 16 MiB copy
+is ~5 µs of HBM time) so the buffers can be recycled by the next layer.  The kernels run on the *current* (compute)
+stream with the group's own signal pads, in the same order on every rank.
+"""
 from __future__ import annotations
 
-_contexts = {}
+import os
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from ..core import dtype_code, native
+
+_contexts: Dict[int, Optional["MoEPeerContext"]] = {}
 
 
-def get_context(group, world: int):
-    return None
+class MoEPeerContext:
+    def __init__(self, engine):
+        self.engine = engine
+        self.comm = engine.comm
+        self.world = engine.world
+        self.rank = engine.rank
+        self._buffers: Dict[int, tuple] = {}
+        self.blocks = int(os.environ.get("BAGUA_MOE_BLOCKS", "64"))
+
+    def _buf(self, nbytes: int, which: int):
+        pair = self._buffers.get(nbytes)
+        if pair is None:
+            pair = (self.engine.alloc(nbytes), self.engine.alloc(nbytes))  # collective: identical call sequence on all ranks
+            self._buffers[nbytes] = pair
+        return pair[which]
+
+    # -- raw kernels ------------------------------------------------------------------------------------------------------
+    def scatter(self, rows: torch.Tensor, expert_idx, slot_idx, scale: Optional[torch.Tensor], E_local: int, C: int) -> torch.Tensor:
+        """rows[S, M] → local view [world, E_local, C, M] of what every rank sent to my experts."""
+        S, M = rows.shape
+        K = expert_idx.shape[1]
+        nbytes = self.world * E_local * C * M * rows.element_size()
+        buf = self._buf(nbytes, 0)
+        rows = rows.contiguous()
+        native().moe_scatter(self.comm, buf.buf, buf.offset, rows.data_ptr(), expert_idx.data_ptr(), slot_idx.data_ptr(),
+                             scale.data_ptr() if scale is not None else 0, S, K, M, E_local, C, dtype_code(rows.dtype), self.blocks,
+                             torch.cuda.current_stream().cuda_stream)
+        return buf.view(rows.dtype, self.world * E_local * C * M).view(self.world, E_local, C, M).clone()
+
+    def gather(self, owner_rows: torch.Tensor, expert_idx, slot_idx, weights: Optional[torch.Tensor], S: int, keep_rows: bool,
+               E_local: int, C: int) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        """owner_rows [world, E_local, C, M] (what my experts produced for every source rank) → out[S, M] on the source ranks."""
+        M = owner_rows.shape[-1]
+        K = expert_idx.shape[1]
+        nbytes = owner_rows.numel() * owner_rows.element_size()
+        buf = self._buf(nbytes, 1)
+        buf.view(owner_rows.dtype, owner_rows.numel()).copy_(owner_rows.reshape(-1))
+        out = torch.empty(S, M, dtype=owner_rows.dtype, device=owner_rows.device)
+        picked = torch.empty(S, K, M, dtype=owner_rows.dtype, device=owner_rows.device) if keep_rows else None
+        native().moe_gather(self.comm, buf.buf, buf.offset, out.data_ptr(), expert_idx.data_ptr(), slot_idx.data_ptr(),
+                            weights.data_ptr() if weights is not None else 0, picked.data_ptr() if picked is not None else 0, S, K, M, E_local, C,
+                            dtype_code(owner_rows.dtype), self.blocks, torch.cuda.current_stream().cuda_stream)
+        return out, picked
+
+    # -- autograd ------------------------------------------------------------------------------------------------------
+    def dispatch(self, tokens, expert_idx, slot_idx, num_experts: int, capacity: int, num_local_experts: int):
+        return _Dispatch.apply(tokens, expert_idx.contiguous(), slot_idx.contiguous(), self, num_local_experts, capacity)
+
+    def combine(self, expert_out, expert_idx, slot_idx, weights, num_experts: int, capacity: int, num_local_experts: int):
+        return _Combine.apply(expert_out, weights, expert_idx.contiguous(), slot_idx.contiguous(), self, num_local_experts, capacity)
+
+
+class _Dispatch(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tokens, expert_idx, slot_idx, pctx: MoEPeerContext, E_local: int, C: int):
+        ctx.pctx, ctx.E_local, ctx.C, ctx.S = pctx, E_local, C, tokens.shape[0]
+        ctx.save_for_backward(expert_idx, slot_idx)
+        return pctx.scatter(tokens, expert_idx, slot_idx, None, E_local, C)
+
+    @staticmethod
+    def backward(ctx, grad_dispatched):
+        expert_idx, slot_idx = ctx.saved_tensors
+        g, _ = ctx.pctx.gather(grad_dispatched.contiguous(), expert_idx, slot_idx, None, ctx.S, False, ctx.E_local, ctx.C)
+        return g, None, None, None, None, None
+
+
+class _Combine(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, expert_out, weights, expert_idx, slot_idx, pctx: MoEPeerContext, E_local: int, C: int):
+        S = expert_idx.shape[0]
+        w32 = weights.float().contiguous()
+        out, picked = pctx.gather(expert_out.contiguous(), expert_idx, slot_idx, w32, S, True, E_local, C)
+        ctx.pctx, ctx.E_local, ctx.C = pctx, E_local, C
+        ctx.wdtype = weights.dtype
+        ctx.save_for_backward(expert_idx, slot_idx, w32, picked)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        expert_idx, slot_idx, w32, picked = ctx.saved_tensors
+        grad_out = grad_out.contiguous()
+        valid = (slot_idx >= 0).to(torch.float32)
+        grad_w = (picked.float() * grad_out.float().unsqueeze(1)).sum(-1) * valid
+        grad_rows = ctx.pctx.scatter(grad_out, expert_idx, slot_idx, (w32 * valid).contiguous(), ctx.E_local, ctx.C)
+        return grad_rows, grad_w.to(ctx.wdtype), None, None, None, None, None
+
+
+def get_context(group, world: int) -> Optional[MoEPeerContext]:
+    """The MoE peer context of a torch process group (``None`` → use all_to_all_single)."""
+    if os.environ.get("BAGUA_MOE_PEER", "1") != "1" or not dist.is_initialized():
+        return None
+    key = id(group) if group is not None else 0
+    if key in _contexts:
+        return _contexts[key]
+    ctx = None
+    try:
+        from .. import communication as comm_mod
+
+        torch_group = group if group is not None else dist.group.WORLD
+        # a dedicated BaguaProcessGroup → dedicated signal pads: these kernels run on the compute stream and must not share
+        # epochs with the bucket kernels on the comm stream
+        ranks = sorted(dist.get_process_group_ranks(torch_group))
+        pg = comm_mod.BaguaProcessGroup(ranks, None, f"moe{key}", torch_group)
+        eng = pg.peer_engine()
+        if eng is not None:
+            ctx = MoEPeerContext(eng)
+            ctx._pg = pg
+    except Exception:  # noqa: BLE001
+        ctx = None
+    _contexts[key] = ctx
+    return ctx

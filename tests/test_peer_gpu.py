@@ -153,3 +153,50 @@ def test_algorithms_on_peer_kernels(name):
         assert max(spreads) < 1e-6  # replicas stay bit-close
     elif name in ("bytegrad", "qadam"):
         assert max(spreads) < 1e-2
+
+
+def _moe_worker(rank, world):
+    import torch.distributed as dist
+
+    import bagua_b200 as bagua
+    from bagua_b200.ops import moe as moe_ops
+    from bagua_b200.ops import moe_peer
+    from bagua_b200.parallel.moe.sharded_moe import top2gating_indices
+
+    bagua.init_process_group()
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(5 + rank)
+    S, M, E_local = 256, 128, 2
+    E = E_local * world
+    for dtype in (torch.float32, torch.bfloat16):
+        logits = torch.randn(S, E, device=dev)
+        g = top2gating_indices(logits, 1.0)
+        C = g.capacity
+        tokens = torch.randn(S, M, device=dev).to(dtype)
+        expert_w = torch.randn(M, M, device=dev).to(dtype) * 0.1
+        outs = []
+        for peer in (True, False):
+            os_env = "1" if peer else "0"
+            import os
+
+            os.environ["BAGUA_MOE_PEER"] = os_env
+            moe_peer._contexts.clear()
+            t = tokens.clone().requires_grad_(True)
+            w = g.weights.to(dtype).clone().requires_grad_(True)
+            ew = expert_w.clone().requires_grad_(True)
+            disp = moe_ops.dispatch(t, g.expert_idx, g.slot_idx, E, C, dist.group.WORLD, world, E_local)
+            assert disp.shape == (world, E_local, C, M)
+            eo = disp @ ew
+            out = moe_ops.combine(eo, g.expert_idx, g.slot_idx, w, E, C, dist.group.WORLD, world, E_local)
+            out.float().pow(2).sum().backward()
+            outs.append((out.detach().float(), t.grad.float(), w.grad.float(), ew.grad.float()))
+            if peer:
+                assert moe_peer.get_context(dist.group.WORLD, world) is not None, "peer MoE path must be active"
+        tol = 1e-4 if dtype == torch.float32 else 6e-2
+        for a, b in zip(*outs):
+            torch.testing.assert_close(a, b, rtol=tol, atol=tol * max(1.0, b.abs().max().item()))
+    return True
+
+
+def test_moe_peer_dispatch_combine_matches_all_to_all():
+    run_distributed(_moe_worker, world=_ngpu(), use_cuda=True)
