@@ -239,6 +239,11 @@ PYBIND11_MODULE(_C, m) {
     m.def("qadam_momentum", [](uint64_t m1, uint64_t grad, int gdt, size_t n, float beta1, uint64_t stream) {
         launch_qadam_momentum(reinterpret_cast<float*>(m1), reinterpret_cast<const void*>(grad), gdt, n, beta1, S(stream));
     });
+    m.def("grouped_gemm_supported", &grouped_gemm_supported);
+    m.def("grouped_gemm_tn", [](uint64_t A, uint64_t B, uint64_t C, uint64_t bias, int G, int M, int N, int K, int act, uint64_t stream) {
+        launch_grouped_gemm_tn(reinterpret_cast<const void*>(A), reinterpret_cast<const void*>(B), reinterpret_cast<void*>(C),
+                               reinterpret_cast<const float*>(bias), G, M, N, K, act, S(stream));
+    });
     m.def("moe_scatter",
           [](std::shared_ptr<PeerComm> comm, SymmBuf dst, size_t dst_off, uint64_t rows, uint64_t eidx, uint64_t sidx, uint64_t scale, int n_tok, int K,
              int M, int E_local, int C, int dtype, int nblocks, uint64_t stream) {

@@ -1,0 +1,252 @@
+// Grouped bf16 GEMM on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), hand-written for sm_100a.
+//
+//   C[g] = act( A[g] · B[g]^T + bias[g] ),   A: [G, M, K]  B: [G, N, K]  (both K-contiguous),  C: [G, M, N]  bf16, fp32 accumulate
+//
+// This is the MoE expert FFN (the one GEMM-shaped hot op of the framework; the reference runs a python loop of cuBLAS
+// linears, bagua/torch_api/model_parallel/moe/experts.py:31-41). One CTA computes one 128x128 output tile:
+//   warp 0      : TMA producer  — cp.async.bulk.tensor (128B-swizzled 128x64 tiles of A and B) into a 4-stage smem ring
+//   warp 1      : MMA issuer    — one elected thread issues tcgen05.mma (M128 N128 K16, kind::f16) per 32-byte K slice,
+//                                  accumulating in TMEM; tcgen05.commit releases smem stages / signals the epilogue
+//   warps 2..5  : epilogue      — tcgen05.ld the fp32 accumulator (32 lanes x 32 columns per instruction), + bias, GELU,
+//                                  convert to bf16, 64-byte stores
+// Synchronisation is mbarrier-only (full/empty per stage + one "accumulator ready"). All waits are bounded: a wedged
+// pipeline traps instead of hanging the GPU.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <stdexcept>
+#include <string>
+
+#include "kernels.h"
+
+namespace bagua {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 4;
+constexpr int UMMA_K = 16;
+constexpr int kGemmThreads = 192;
+constexpr uint32_t kStageBytesA = BM * BK * 2, kStageBytesB = BN * BK * 2;
+constexpr uint32_t kTmemCols = 128;  // one 128x128 fp32 accumulator
+
+struct __align__(1024) GemmSmem {
+    uint8_t a[STAGES][kStageBytesA];
+    uint8_t b[STAGES][kStageBytesB];
+    uint64_t full[STAGES];
+    uint64_t empty[STAGES];
+    uint64_t acc_ready;
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) __trap();  // seconds of waiting: the pipeline is wedged — fail loudly, never hang
+    }
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+
+// K-major operand tile in smem with the 128-byte swizzle written by TMA: rows of 128 B, 8-row atoms of 1024 B.
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64))
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// cute::UMMA::InstrDescriptor for kind::f16: D=F32 [4,6)=1, A=BF16 [7,10)=1, B=BF16 [10,13)=1, K-major A/B, N>>3 [17,23), M>>4 [24,29)
+__device__ __forceinline__ constexpr uint32_t make_instr_desc() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float gelu_tanh(float x) {
+    const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+    const float u = k0 * (x + k1 * x * x * x);
+    return 0.5f * x * (1.f + tanhf(u));
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+    grouped_gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, __nv_bfloat16* __restrict__ C,
+                           const float* __restrict__ bias, int M, int N, int K, int act) {
+    extern __shared__ uint8_t smem_raw[];
+    GemmSmem& sm = *reinterpret_cast<GemmSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM, g = blockIdx.z;
+    const int num_kb = K / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_b)) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], 1);
+        }
+        mbar_init(&sm.acc_ready, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // whole warp: TMEM allocation (the same warp frees it)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = sm.tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer =====
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t parity = ((kb / STAGES) & 1) ^ 1;
+                mbar_wait(&sm.empty[s], parity);  // fresh barrier: waiting on parity 1 passes immediately
+                mbar_expect_tx(&sm.full[s], kStageBytesA + kStageBytesB);
+                tma_load_3d(sm.a[s], &tm_a, &sm.full[s], kb * BK, m0, g);
+                tma_load_3d(sm.b[s], &tm_b, &sm.full[s], kb * BK, n0, g);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ===== MMA issuer =====
+            const uint32_t idesc = make_instr_desc();
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&sm.full[s], (kb / STAGES) & 1);
+                tcgen05_fence_after();
+                const uint64_t da = make_smem_desc(smem_u32(sm.a[s])), db = make_smem_desc(smem_u32(sm.b[s]));
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    // advance 32 bytes (16 bf16) along K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+                    umma_bf16(tmem_base, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                tcgen05_commit(&sm.empty[s]);  // arrives when the MMAs above have finished reading this stage
+            }
+            tcgen05_commit(&sm.acc_ready);
+        }
+    } else {  // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        mbar_wait(&sm.acc_ready, 0);
+        tcgen05_fence_after();
+        __nv_bfloat16* crow = C + (static_cast<size_t>(g) * M + (m0 + row)) * N + n0;
+        const float* brow = bias ? bias + static_cast<size_t>(g) * N + n0 : nullptr;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c), r);
+            uint32_t packed[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float v0 = __uint_as_float(r[2 * j]), v1 = __uint_as_float(r[2 * j + 1]);
+                if (brow) v0 += __ldg(brow + c + 2 * j), v1 += __ldg(brow + c + 2 * j + 1);
+                if (act == 1) v0 = gelu_tanh(v0), v1 = gelu_tanh(v1);
+                __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+                packed[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(crow + c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) throw std::runtime_error("bagua: cuTensorMapEncodeTiled is not available from the driver");
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// [G, rows, K] bf16, K contiguous → box (BK x box_rows x 1), 128-byte swizzle
+CUtensorMap make_map(const void* ptr, int G, int rows, int K, int box_rows) {
+    CUtensorMap m;
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(G)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(K) * 2, static_cast<cuuint64_t>(rows) * K * 2};
+    cuuint32_t box[3] = {BK, static_cast<cuuint32_t>(box_rows), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw std::runtime_error("bagua: cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
+    return m;
+}
+
+}  // namespace
+
+bool grouped_gemm_supported(int M, int N, int K) { return M > 0 && N > 0 && K > 0 && M % BM == 0 && N % BN == 0 && K % BK == 0; }
+
+void launch_grouped_gemm_tn(const void* A, const void* B, void* C, const float* bias, int G, int M, int N, int K, int act, cudaStream_t stream) {
+    if (!grouped_gemm_supported(M, N, K)) throw std::runtime_error("bagua: grouped_gemm_tn needs M%128==0, N%128==0, K%64==0");
+    if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) & 15u)
+        throw std::runtime_error("bagua: grouped_gemm_tn needs 16-byte aligned operands");
+    const CUtensorMap ta = make_map(A, G, M, K, BM), tb = make_map(B, G, N, K, BN);
+    const size_t smem = sizeof(GemmSmem) + 1024;
+    static bool configured = false;
+    if (!configured) {
+        BAGUA_CUDA_CHECK(cudaFuncSetAttribute(grouped_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        configured = true;
+    }
+    dim3 grid(N / BN, M / BM, G);
+    grouped_gemm_tn_kernel<<<grid, kGemmThreads, smem, stream>>>(ta, tb, static_cast<__nv_bfloat16*>(C), bias, M, N, K, act);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw std::runtime_error(std::string("bagua: launch of grouped_gemm_tn failed: ") + cudaGetErrorString(e));
+}
+
+}  // namespace bagua

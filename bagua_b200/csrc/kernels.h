@@ -45,6 +45,11 @@ void launch_peer_average(const PeerCtx& ctx, const PeerBuf& weights, size_t off,
                          int nblocks, int nthreads, cudaStream_t stream);
 void launch_peer_barrier(const PeerCtx& ctx, cudaStream_t stream);
 
+// ---- tcgen05 grouped GEMM (gemm_tcgen05.cu) ----------------------------------------------------------------------
+// C[g] = act(A[g]·B[g]^T + bias[g]); A [G,M,K], B [G,N,K], C [G,M,N] bf16 (K-contiguous operands), bias fp32 [G,N] or null; act: 0 none, 1 GELU(tanh)
+bool grouped_gemm_supported(int M, int N, int K);
+void launch_grouped_gemm_tn(const void* A, const void* B, void* C, const float* bias, int G, int M, int N, int K, int act, cudaStream_t stream);
+
 // ---- MoE expert-parallel token exchange (moe_kernels.cu) ------------------------------------------------
 // Symmetric row buffers have layout [world(src rank), E_local, C, M]. scatter: rows_in[s] → owner's slot (optionally scaled
 // per (s,k)); gather: out[s] = Σ_k w[s,k]·owner_row, optionally saving the fetched rows in picked[S,K,M].
