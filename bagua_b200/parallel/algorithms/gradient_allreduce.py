@@ -40,3 +40,117 @@ class GradientAllReduceAlgorithm(Algorithm):
 
     def reify(self, process_group) -> GradientAllReduceAlgorithmImpl:
         return GradientAllReduceAlgorithmImpl(process_group, hierarchical=self.hierarchical, average=self.average, variant=self.variant)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Gradient allreduce with the optimizer folded into the communication kernel
+# ---------------------------------------------------------------------------------------------------------------
+class ShardedFusedSGD(object):
+    """Marker mix-in: see :func:`make_sharded_fused_sgd`."""
+
+
+def make_sharded_fused_sgd(params, lr=1e-3, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False):
+    """SGD whose update runs *inside* each bucket's NVSwitch kernel (``allreduce_sgd_kernel``): reduce-scatter of the
+    gradients → SGD(momentum) on this rank's 1/N shard with fp32 master weights → all-gather of the updated weights, one
+    launch per bucket, overlapped with the rest of backward.  Optimizer state is sharded N ways (ZeRO-1-like) and the
+    gradient bucket is cleared on the way out.  Use together with ``FusedGradientAllReduceAlgorithm``; with one process (or
+    without a peer engine) it behaves like :class:`bagua_b200.ops.optim.FusedSGD`."""
+    from ...ops.optim import FusedSGD
+
+    class _ShardedFusedSGD(FusedSGD, ShardedFusedSGD):
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            self._comm_ops = []   # AllReduceSgdOp per bucket once the algorithm has taken over
+
+        def _sync_hyper(self):
+            g = self.param_groups[0]
+            for op in self._comm_ops:
+                op.set_hyper(float(g["lr"]), float(g["momentum"]), float(g["dampening"]), float(g["weight_decay"]), bool(g["nesterov"]))
+
+        def step(self, closure=None):
+            if not self._comm_ops:
+                return super().step(closure)
+            # the update already happened in the bucket kernels of this iteration; publish hyper-parameters for the next
+            self._sync_hyper()
+            self._grads_zeroed = True
+            self.kernel_launches += len(self._comm_ops)
+            return None
+
+    return _ShardedFusedSGD(params, lr=lr, momentum=momentum, dampening=dampening, weight_decay=weight_decay, nesterov=nesterov,
+                            master_weights=True, zero_grad_in_step=True)
+
+
+class FusedGradientAllReduceAlgorithmImpl(GradientAllReduceAlgorithmImpl):
+    def __init__(self, process_group, optimizer, average: bool = True):
+        super().__init__(process_group, hierarchical=False, average=average)
+        self.optimizer = optimizer
+        self._weight_slices = []
+
+    def tensors_to_buckets(self, tensors, do_flatten):
+        from ...bucket import BaguaBucket
+
+        assert do_flatten, "the fused optimizer needs flattened buckets"
+        es = tensors[0][0].bagua_getter_closure().element_size()
+        return [BaguaBucket(b, flatten=True, name=str(i), alignment=max(1, 16 // es), group=self.process_group) for i, b in enumerate(tensors)]
+
+    def init_operations(self, bagua_ddp, bucket):
+        import torch
+
+        from ...core import dtype_code, native
+        from ...tensor import dense_strides
+
+        bucket.clear_ops()
+        eng = bucket._engine(self.process_group)
+        opt = self.optimizer
+        if eng is None or bucket._slice is None or not isinstance(opt, ShardedFusedSGD):
+            return super().init_operations(bagua_ddp, bucket)
+        assert len(opt.param_groups) == 1, "the in-kernel optimizer supports a single parameter group"
+        C = native()
+        flat = bucket.backend_tensor
+        n, rank = self.process_group.size(), self.process_group.rank()
+        nbytes = flat.numel() * flat.element_size()
+        assert nbytes % 16 == 0
+        # weights mirror the gradient bucket layout inside their own symmetric slice (peers write them in the kernel)
+        wslice = eng.alloc(nbytes)
+        bucket._companion_slices.append(wslice)
+        wflat = wslice.view(flat.dtype, flat.numel())
+        wflat.zero_()
+        base = flat.data_ptr()
+        with torch.no_grad():
+            for t in bucket.tensors:
+                g = t.bagua_getter_closure()
+                assert t.dtype == flat.dtype, "weights and gradients must share a dtype for the fused kernel"
+                off = (g.data_ptr() - base) // flat.element_size()
+                view = torch.as_strided(wflat, t.shape, dense_strides(t), off)
+                view.copy_(t.data)
+                t.data = view
+        vecs = nbytes // 16
+        vpr = (vecs + n - 1) // n
+        per = 16 // flat.element_size()
+        lo, hi = rank * vpr * per, min((rank + 1) * vpr * per, flat.numel())
+        master = torch.zeros(vpr * per, dtype=torch.float32, device=flat.device)
+        if hi > lo:
+            master[: hi - lo].copy_(wflat[lo:hi].float())
+        momentum = torch.zeros(vpr * per, dtype=torch.float32, device=flat.device)
+        bucket._fused_state = (master, momentum)
+        use_mc = bool(wslice.has_multicast and bucket._slice.has_multicast and eng.choose_variant(nbytes) == "multimem")
+        op = C.AllReduceSgdOp(eng.comm, bucket._slice.buf, wslice.buf, bucket._slice.offset, wslice.offset, nbytes, dtype_code(flat.dtype),
+                              master.data_ptr(), momentum.data_ptr(), (1.0 / n) if self.average else 1.0, True, use_mc,
+                              eng.launch_cfg("multimem" if use_mc else "two_shot", nbytes))
+        bucket.backend_bucket.append_op(op)
+        bucket._ops_keepalive.append(op)
+        bucket.allreduce_variant = "fused_sgd_multimem" if use_mc else "fused_sgd_two_shot"
+        opt._comm_ops.append(op)
+        opt._sync_hyper()
+
+
+class FusedGradientAllReduceAlgorithm(Algorithm):
+    """Gradient allreduce whose buckets also apply the SGD update (see :func:`make_sharded_fused_sgd`)."""
+
+    def __init__(self, optimizer, average: bool = True):
+        self.optimizer = optimizer
+        self.average = average
+
+    def reify(self, process_group):
+        self.optimizer._comm_ops = []
+        return FusedGradientAllReduceAlgorithmImpl(process_group, self.optimizer, average=self.average)

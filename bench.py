@@ -139,9 +139,15 @@ def main():
 
     bs = args.batch_size
     model = get_model(args.model).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
-    optimizer = FusedSGD(model.parameters(), lr=0.01 * world, momentum=args.momentum, master_weights=True, zero_grad_in_step=True)
-    algo_kwargs = {}
-    model = model.with_bagua([optimizer], Algorithm.init(args.algorithm, **algo_kwargs))
+    if args.fused_shard:
+        from bagua_b200.parallel.algorithms.gradient_allreduce import FusedGradientAllReduceAlgorithm, make_sharded_fused_sgd
+
+        optimizer = make_sharded_fused_sgd(model.parameters(), lr=0.01 * world, momentum=args.momentum)
+        algorithm = FusedGradientAllReduceAlgorithm(optimizer)
+    else:
+        optimizer = FusedSGD(model.parameters(), lr=0.01 * world, momentum=args.momentum, master_weights=True, zero_grad_in_step=True)
+        algorithm = Algorithm.init(args.algorithm)
+    model = model.with_bagua([optimizer], algorithm)
 
     # synthetic ImageNet batch (reference: fixed random data + target, synthetic_benchmark.py)
     x_dev = torch.randn(bs, 3, 224, 224, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
@@ -197,7 +203,7 @@ def main():
         sampler.start()
     ms = timed(lambda i: train_step(x_dev, y_dev), args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    native_comm_ops = sum(1 for b in model.bagua_buckets if getattr(b, "allreduce_variant", "") in ("one_shot", "two_shot", "multimem"))
+    native_comm_ops = sum(1 for b in model.bagua_buckets if getattr(b, "allreduce_variant", "") in ("one_shot", "two_shot", "multimem", "fused_sgd_two_shot", "fused_sgd_multimem"))
     comm_launches = (model.bagua_ddp._bagua_backend.scheduled_total() - sched0) if native_comm_ops else 0
     gpu_launches = (optimizer.kernel_launches - launches0) + comm_launches
     value = bs * world * args.steps / (ms / 1e3)
@@ -234,7 +240,7 @@ def main():
                 "image": "3x224x224",
                 "parallelism": f"dp{world}",
                 "algorithm": args.algorithm,
-                "optimizer": f"FusedSGD(momentum={args.momentum}, fp32 master weights)",
+                "optimizer": ("SGD fused into the bucket allreduce kernel (sharded fp32 master weights)" if args.fused_shard else f"FusedSGD(momentum={args.momentum}, fp32 master weights)"),
                 "allreduce_variants": variants,
                 "buckets": len(model.bagua_buckets),
                 "l2_policy": "working set (276 MB bf16 weights + activations) far exceeds the 126 MB L2; no explicit flush",

@@ -1,0 +1,83 @@
+"""Synthetic throughput benchmark for every algorithm (reference: examples/benchmark/synthetic_benchmark.py).
+
+    python -m bagua_b200.distributed.launch --nproc_per_node=8 examples/benchmark/synthetic_benchmark.py --model vgg16 --algorithm gradient_allreduce
+
+Prints Horovod-style ``Img/sec per GPU`` / ``Total img/sec`` lines; timing is device-side (CUDA events, max over ranks)."""
+import argparse
+
+import torch
+import torch.nn.functional as F
+
+import bagua_b200 as bagua
+from bagua_b200.models import get_model
+from bagua_b200.parallel.algorithms import Algorithm, q_adam
+
+p = argparse.ArgumentParser()
+p.add_argument("--model", default="resnet50")
+p.add_argument("--batch-size", type=int, default=32)
+p.add_argument("--num-warmup-batches", type=int, default=10)
+p.add_argument("--num-batches-per-iter", type=int, default=10)
+p.add_argument("--num-iters", type=int, default=10)
+p.add_argument("--algorithm", default="gradient_allreduce", help="gradient_allreduce, bytegrad, decentralized, low_precision_decentralized, qadam, async")
+p.add_argument("--fuse-optimizer", action="store_true")
+p.add_argument("--bf16", action="store_true")
+p.add_argument("--async-sync-interval", type=int, default=500)
+p.add_argument("--async-warmup-steps", type=int, default=100)
+args = p.parse_args()
+
+torch.cuda.set_device(bagua.get_local_rank())
+bagua.init_process_group()
+dev = torch.device("cuda", bagua.get_local_rank())
+torch.backends.cudnn.benchmark = True
+model = get_model(args.model).to(dev)
+if args.bf16:
+    model = model.to(torch.bfloat16).to(memory_format=torch.channels_last)
+if args.algorithm == "qadam":
+    optimizer = q_adam.QAdamOptimizer(model.parameters(), lr=0.01 * bagua.get_world_size(), warmup_steps=100)
+    algorithm = q_adam.QAdamAlgorithm(optimizer)
+else:
+    optimizer = torch.optim.SGD(model.parameters(), lr=0.01 * bagua.get_world_size())
+    kw = dict(sync_interval_ms=args.async_sync_interval, warmup_steps=args.async_warmup_steps) if args.algorithm == "async" else {}
+    algorithm = Algorithm.init(args.algorithm, **kw)
+model = model.with_bagua([optimizer], algorithm)
+if args.fuse_optimizer:
+    optimizer = bagua.contrib.fuse_optimizer(optimizer)
+
+data = torch.randn(args.batch_size, 3, 224, 224, device=dev)
+if args.bf16:
+    data = data.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+target = torch.randint(0, 1000, (args.batch_size,), device=dev)
+
+
+def step():
+    optimizer.zero_grad()
+    loss = F.cross_entropy(model(data).float(), target)
+    loss.backward()
+    optimizer.fuse_step() if args.fuse_optimizer else optimizer.step()
+
+
+for _ in range(args.num_warmup_batches):
+    step()
+speeds = []
+for i in range(args.num_iters):
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(args.num_batches_per_iter):
+        step()
+    e.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([s.elapsed_time(e)], device=dev)
+    bagua.allreduce_inplace(ms, op=bagua.ReduceOp.MAX)
+    speeds.append(args.batch_size * args.num_batches_per_iter / (ms.item() / 1e3))
+    if bagua.get_rank() == 0:
+        print(f"Iter #{i}: {speeds[-1]:.1f} img/sec per GPU")
+if args.algorithm == "async":
+    model.bagua_algorithm.abort(model)
+if bagua.get_rank() == 0:
+    import statistics
+
+    m, c = statistics.mean(speeds), 1.96 * statistics.pstdev(speeds)
+    n = bagua.get_world_size()
+    print(f"Img/sec per GPU: {m:.1f} +-{c:.1f}")
+    print(f"Total img/sec on {n} GPU(s): {n * m:.1f} +-{n * c:.1f}")
