@@ -155,8 +155,6 @@ def main():
     n_host = 4
     x_host = [torch.randn(bs, 3, 224, 224).pin_memory() for _ in range(n_host)]
     y_host = [torch.randint(0, 1000, (bs,)).pin_memory() for _ in range(n_host)]
-    x_stage = torch.empty(bs, 3, 224, 224, device=dev)
-    y_stage = torch.empty(bs, dtype=torch.long, device=dev)
 
     def train_step(x, y):
         optimizer.zero_grad()
@@ -166,25 +164,41 @@ def main():
         optimizer.step()
         return loss
 
-    def e2e_step(i):
-        x_stage.copy_(x_host[i % n_host], non_blocking=True)
-        y_stage.copy_(y_host[i % n_host], non_blocking=True)
-        x = x_stage.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        loss = train_step(x, y_stage)
-        return loss.item()  # device→host read of the step's result
+    from bagua_b200.utils.data import DevicePrefetcher, LossReader
+
+    def to_model_format(x, y):
+        return x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last), y
+
+    def host_batches(n):
+        for i in range(n):
+            yield x_host[i % n_host], y_host[i % n_host]
+
+    loss_reader = LossReader(dev)
+
+    def e2e_loop(steps):
+        """The loop a user writes: pinned host batches → DevicePrefetcher (H2D of batch i+1 overlaps step i) → train step →
+        asynchronous D2H read of every step's loss."""
+        last = None
+        for x, y in DevicePrefetcher(host_batches(steps), dev, to_model_format):
+            loss = train_step(x, y)
+            last = loss_reader.push(loss)
+        return loss_reader.flush()
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, whole_loop=False):
         sync_all()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.nvtx.range_push("timed")
         start.record()
-        for i in range(steps):
-            fn(i)
+        if whole_loop:
+            fn(steps)
+        else:
+            for i in range(steps):
+                fn(i)
         end.record()
         torch.cuda.nvtx.range_pop()
         torch.cuda.synchronize()
@@ -210,9 +224,8 @@ def main():
 
     e2e = None
     if not args.no_e2e:
-        for i in range(3):
-            e2e_step(i)
-        ms_e2e = timed(e2e_step, args.steps)
+        e2e_loop(3)
+        ms_e2e = timed(e2e_loop, args.steps, whole_loop=True)
         h2d = x_host[0].numel() * x_host[0].element_size() + y_host[0].numel() * y_host[0].element_size()
         e2e = {"value": bs * world * args.steps / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                "ms_per_step": ms_e2e / args.steps}

@@ -289,3 +289,33 @@ def test_ddp_wrapper_no_sync_and_state_broadcast():
     assert torch.equal(r0[0], r1[0]) and torch.equal(r0[1], r1[1])  # params and Adam state broadcast from rank 0
     assert not torch.equal(r0[2], r1[2])                             # no_sync kept gradients local
     torch.testing.assert_close(r0[3], r1[3])                          # after the sync step both hold the average
+
+
+# ---- fused allreduce+SGD algorithm: CPU/gloo fallback (plain allreduce + FusedSGD torch path) -------------------------
+def _fused_fallback_worker(rank, world):
+    import torch.distributed as dist
+
+    import bagua_b200 as bagua
+    from bagua_b200.parallel.algorithms.gradient_allreduce import FusedGradientAllReduceAlgorithm, make_sharded_fused_sgd
+
+    bagua.init_process_group()
+    torch.manual_seed(3)
+    model = _net()
+    oracle = copy.deepcopy(model)
+    opt = make_sharded_fused_sgd(model.parameters(), lr=0.05, momentum=0.9)
+    oopt = torch.optim.SGD(oracle.parameters(), lr=0.05, momentum=0.9)
+    model = model.with_bagua([opt], FusedGradientAllReduceAlgorithm(opt))
+
+    def avg(_it):
+        for p in oracle.parameters():
+            dist.all_reduce(p.grad)
+            p.grad /= world
+
+    _train(model, opt, rank, 4)
+    _train(oracle, oopt, rank, 4, post=avg)
+    return _flat(model), _flat(oracle)
+
+
+def test_fused_allreduce_sgd_cpu_fallback():
+    for mine, oracle in run_distributed(_fused_fallback_worker, world=2):
+        torch.testing.assert_close(mine, oracle, rtol=1e-5, atol=1e-6)
