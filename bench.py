@@ -36,6 +36,7 @@ def parse():
     p.add_argument("--algorithm", default="gradient_allreduce")
     p.add_argument("--momentum", type=float, default=0.0)
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--profile", default="", help="write a torch.profiler kernel table of 3 steps to this file (not a benchmark run)")
     p.add_argument("--fused-shard", action="store_true", help="fold the SGD update into the allreduce kernel (sharded optimizer state)")
     return p.parse_args()
 
@@ -210,6 +211,18 @@ def main():
 
     for i in range(max(args.warmup, 3)):
         train_step(x_dev, y_dev)
+    if args.profile:
+        from torch.profiler import ProfilerActivity, profile
+
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for _ in range(3):
+                train_step(x_dev, y_dev)
+            torch.cuda.synchronize()
+        if rank == 0:
+            with open(args.profile, "w") as f:
+                f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
+        return 0
     launches0 = optimizer.kernel_launches
     sched0 = model.bagua_ddp._bagua_backend.scheduled_total()
     sampler = ClockSampler(local_rank)

@@ -10,10 +10,20 @@ from contextlib import closing
 import torch.multiprocessing as mp
 
 
+_used_ports = set()
+
+
 def free_port() -> int:
-    with closing(socket.socket(socket.AF_INET, socket.SOCK_STREAM)) as s:
-        s.bind(("127.0.0.1", 0))
-        return s.getsockname()[1]
+    """A port nobody listens on right now and that this test session has not handed out before (TIME_WAIT / reuse races
+    between consecutive spawns showed up as EADDRINUSE on the GPU box)."""
+    for _ in range(64):
+        with closing(socket.socket(socket.AF_INET, socket.SOCK_STREAM)) as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        if port not in _used_ports and port > 20000:
+            _used_ports.add(port)
+            return port
+    raise RuntimeError("no free port")
 
 
 def _portable(obj):
