@@ -168,8 +168,8 @@ PYBIND11_MODULE(_C, m) {
              py::arg("variant"), py::arg("cfg"))
         .def("set_variant", &AllReduceOp::set_variant);
     py::class_<AllReduceOneShotOp, CommOp, std::shared_ptr<AllReduceOneShotOp>>(m, "AllReduceOneShotOp")
-        .def(py::init<std::shared_ptr<PeerComm>, SymmBuf, size_t, uint64_t, uint64_t, size_t, int, float, LaunchCfg>(), py::arg("comm"),
-             py::arg("staging"), py::arg("slot_bytes"), py::arg("in_ptr"), py::arg("out_ptr"), py::arg("bytes"), py::arg("dtype"),
+        .def(py::init<std::shared_ptr<PeerComm>, SymmBuf, size_t, size_t, uint64_t, uint64_t, size_t, int, float, LaunchCfg>(), py::arg("comm"),
+             py::arg("staging"), py::arg("staging_off"), py::arg("slot_bytes"), py::arg("in_ptr"), py::arg("out_ptr"), py::arg("bytes"), py::arg("dtype"),
              py::arg("scale"), py::arg("cfg"));
     py::class_<AllReduceSgdOp, CommOp, std::shared_ptr<AllReduceSgdOp>>(m, "AllReduceSgdOp")
         .def(py::init<std::shared_ptr<PeerComm>, SymmBuf, SymmBuf, size_t, size_t, size_t, int, uint64_t, uint64_t, float, bool, bool,
@@ -239,6 +239,22 @@ PYBIND11_MODULE(_C, m) {
     m.def("qadam_momentum", [](uint64_t m1, uint64_t grad, int gdt, size_t n, float beta1, uint64_t stream) {
         launch_qadam_momentum(reinterpret_cast<float*>(m1), reinterpret_cast<const void*>(grad), gdt, n, beta1, S(stream));
     });
+    m.def("bias_relu_nhwc_fwd", [](uint64_t y, uint64_t bias, size_t rows, int C, int dtype, uint64_t stream) {
+        launch_bias_relu_nhwc_fwd(reinterpret_cast<void*>(y), reinterpret_cast<const void*>(bias), rows, C, dtype, S(stream));
+    });
+    m.def("bias_relu_nhwc_bwd", [](uint64_t g, uint64_t y, uint64_t gout, uint64_t bias_grad, size_t rows, int C, int dtype, uint64_t stream) {
+        launch_bias_relu_nhwc_bwd(reinterpret_cast<const void*>(g), reinterpret_cast<const void*>(y), reinterpret_cast<void*>(gout),
+                                  reinterpret_cast<float*>(bias_grad), rows, C, dtype, S(stream));
+    });
+    m.def("bias_relu_pool_nhwc_fwd", [](uint64_t x, uint64_t bias, uint64_t out, uint64_t idx, int N, int H, int W, int C, int dtype, uint64_t stream) {
+        launch_bias_relu_pool_nhwc_fwd(reinterpret_cast<const void*>(x), reinterpret_cast<const void*>(bias), reinterpret_cast<void*>(out),
+                                       reinterpret_cast<uint8_t*>(idx), N, H, W, C, dtype, S(stream));
+    });
+    m.def("bias_relu_pool_nhwc_bwd",
+          [](uint64_t g, uint64_t out, uint64_t idx, uint64_t gin, uint64_t bias_grad, int N, int H, int W, int C, int dtype, uint64_t stream) {
+              launch_bias_relu_pool_nhwc_bwd(reinterpret_cast<const void*>(g), reinterpret_cast<const void*>(out), reinterpret_cast<const uint8_t*>(idx),
+                                             reinterpret_cast<void*>(gin), reinterpret_cast<float*>(bias_grad), N, H, W, C, dtype, S(stream));
+          });
     m.def("grouped_gemm_supported", &grouped_gemm_supported);
     m.def("grouped_gemm_tn", [](uint64_t A, uint64_t B, uint64_t C, uint64_t bias, int G, int M, int N, int K, int act, uint64_t stream) {
         launch_grouped_gemm_tn(reinterpret_cast<const void*>(A), reinterpret_cast<const void*>(B), reinterpret_cast<void*>(C),

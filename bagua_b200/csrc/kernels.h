@@ -36,7 +36,7 @@ struct AdamParams {
 // ---- peer kernels (peer_kernels.cu) ------------------------------------------------------------------------
 void launch_allreduce(const PeerCtx& ctx, const PeerBuf& src, const PeerBuf& dst, size_t src_off, size_t dst_off, size_t bytes,
                       int dtype, float scale, int variant, int nblocks, int nthreads, cudaStream_t stream);
-void launch_allreduce_oneshot(const PeerCtx& ctx, const PeerBuf& staging, size_t slot_bytes, const void* in, void* out,
+void launch_allreduce_oneshot(const PeerCtx& ctx, const PeerBuf& staging, size_t staging_off, size_t slot_bytes, const void* in, void* out,
                               size_t bytes, int dtype, float scale, int nblocks, int nthreads, cudaStream_t stream);
 void launch_allreduce_sgd(const PeerCtx& ctx, const PeerBuf& grads, const PeerBuf& weights, size_t g_off, size_t w_off,
                           size_t bytes, int dtype, float* master, float* momentum, const SgdParams& hp, float scale,
@@ -44,6 +44,14 @@ void launch_allreduce_sgd(const PeerCtx& ctx, const PeerBuf& grads, const PeerBu
 void launch_peer_average(const PeerCtx& ctx, const PeerBuf& weights, size_t off, int peer, void* out, size_t bytes, int dtype,
                          int nblocks, int nthreads, cudaStream_t stream);
 void launch_peer_barrier(const PeerCtx& ctx, cudaStream_t stream);
+
+// ---- fused NHWC conv-block epilogues (nhwc_fused.cu); tensors are [N,H,W,C] f16/bf16, rows = N*H*W --------------------
+void launch_bias_relu_nhwc_fwd(void* y, const void* bias, size_t rows, int C, int dtype, cudaStream_t stream);
+void launch_bias_relu_nhwc_bwd(const void* g, const void* y, void* gout, float* bias_grad, size_t rows, int C, int dtype, cudaStream_t stream);
+void launch_bias_relu_pool_nhwc_fwd(const void* x, const void* bias, void* out, uint8_t* idx, int N, int H, int W, int C, int dtype,
+                                    cudaStream_t stream);
+void launch_bias_relu_pool_nhwc_bwd(const void* g, const void* out, const uint8_t* idx, void* gin, float* bias_grad, int N, int H, int W, int C,
+                                    int dtype, cudaStream_t stream);
 
 // ---- tcgen05 grouped GEMM (gemm_tcgen05.cu) ----------------------------------------------------------------------
 // C[g] = act(A[g]·B[g]^T + bias[g]); A [G,M,K], B [G,N,K], C [G,M,N] bf16 (K-contiguous operands), bias fp32 [G,N] or null; act: 0 none, 1 GELU(tanh)

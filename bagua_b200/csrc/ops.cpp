@@ -99,7 +99,7 @@ void AllReduceOp::run(Bucket&, StreamHandle stream, int) {
 }
 
 void AllReduceOneShotOp::run(Bucket&, StreamHandle stream, int) {
-    launch_allreduce_oneshot(comm_->ctx(), staging_.buf, slot_bytes_, reinterpret_cast<const void*>(in_), reinterpret_cast<void*>(out_),
+    launch_allreduce_oneshot(comm_->ctx(), staging_.buf, staging_off_, slot_bytes_, reinterpret_cast<const void*>(in_), reinterpret_cast<void*>(out_),
                              bytes_, dtype_, scale_, cfg_.nblocks, cfg_.nthreads, S(stream));
 }
 

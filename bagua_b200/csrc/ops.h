@@ -87,9 +87,9 @@ private:
 
 class AllReduceOneShotOp final : public CommOp {
 public:
-    AllReduceOneShotOp(std::shared_ptr<PeerComm> comm, SymmBuf staging, size_t slot_bytes, uint64_t in, uint64_t out, size_t bytes,
-                       int dtype, float scale, LaunchCfg cfg)
-        : comm_(std::move(comm)), staging_(staging), slot_bytes_(slot_bytes), in_(in), out_(out), bytes_(bytes), dtype_(dtype),
+    AllReduceOneShotOp(std::shared_ptr<PeerComm> comm, SymmBuf staging, size_t staging_off, size_t slot_bytes, uint64_t in, uint64_t out,
+                       size_t bytes, int dtype, float scale, LaunchCfg cfg)
+        : comm_(std::move(comm)), staging_(staging), staging_off_(staging_off), slot_bytes_(slot_bytes), in_(in), out_(out), bytes_(bytes), dtype_(dtype),
           scale_(scale), cfg_(cfg) {}
     const char* kind() const override { return "allreduce_oneshot"; }
     void run(Bucket&, StreamHandle stream, int device) override;
@@ -97,6 +97,7 @@ public:
 private:
     std::shared_ptr<PeerComm> comm_;
     SymmBuf staging_;
+    size_t staging_off_;
     size_t slot_bytes_;
     uint64_t in_, out_;
     size_t bytes_;

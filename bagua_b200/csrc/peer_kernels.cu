@@ -91,8 +91,9 @@ __global__ void __launch_bounds__(512) allreduce_multimem_kernel(PeerCtx ctx, Pe
 // double-buffered by epoch parity, so no second barrier is needed (a rank can only be two calls ahead of a peer
 // after that peer has left the call in between).
 template <typename T, int P>
-__global__ void __launch_bounds__(512) allreduce_oneshot_kernel(PeerCtx ctx, PeerBuf staging, size_t slot_bytes,
-                                                                const char* in, char* out, size_t total_vecs, float scale) {
+__global__ void __launch_bounds__(512) allreduce_oneshot_kernel(PeerCtx ctx, PeerBuf staging, size_t staging_off,
+                                                                size_t slot_bytes, const char* in, char* out, size_t total_vecs,
+                                                                float scale) {
     const uint32_t e0 = load_epoch(ctx);
     const size_t parity = (e0 & 1u);
     const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -102,12 +103,12 @@ __global__ void __launch_bounds__(512) allreduce_oneshot_kernel(PeerCtx ctx, Pee
 #pragma unroll
         for (int i = 0; i < P; ++i) {
             const int p = (ctx.rank + i) % P;
-            st_peer16(staging.ptr[p] + (parity * P + ctx.rank) * slot_bytes + v * 16, mine);
+            st_peer16(staging.ptr[p] + staging_off + (parity * P + ctx.rank) * slot_bytes + v * 16, mine);
         }
     }
     bool ok = peer_barrier(ctx, e0 + 1);
     if (ok) {
-        const char* mystage = staging.ptr[ctx.rank] + parity * P * slot_bytes;
+        const char* mystage = staging.ptr[ctx.rank] + staging_off + parity * P * slot_bytes;
         for (size_t v = tid; v < total_vecs; v += stride) {
             float acc[Vec16<T>::N];
             Vec16<T>::unpack(ld_peer16(mystage + v * 16), acc);
@@ -307,7 +308,7 @@ void launch_allreduce(const PeerCtx& ctx, const PeerBuf& src, const PeerBuf& dst
     check_launch("allreduce");
 }
 
-void launch_allreduce_oneshot(const PeerCtx& ctx, const PeerBuf& staging, size_t slot_bytes, const void* in, void* out,
+void launch_allreduce_oneshot(const PeerCtx& ctx, const PeerBuf& staging, size_t staging_off, size_t slot_bytes, const void* in, void* out,
                               size_t bytes, int dtype, float scale, int nblocks, int nthreads, cudaStream_t stream) {
     if (bytes % 16) throw std::runtime_error("bagua: one-shot allreduce needs a 16-byte multiple");
     if (bytes > slot_bytes) throw std::runtime_error("bagua: one-shot allreduce message larger than its staging slot");
@@ -319,7 +320,7 @@ void launch_allreduce_oneshot(const PeerCtx& ctx, const PeerBuf& staging, size_t
         dispatch_world(ctx.world, [&](auto pw) {
             constexpr int P = decltype(pw)::value;
             allreduce_oneshot_kernel<T, P><<<nblocks, nthreads, 0, stream>>>(
-                ctx, staging, slot_bytes, static_cast<const char*>(in), static_cast<char*>(out), vecs, scale);
+                ctx, staging, staging_off, slot_bytes, static_cast<const char*>(in), static_cast<char*>(out), vecs, scale);
         });
     });
     check_launch("allreduce_oneshot");

@@ -8,6 +8,7 @@ _CFG_D = [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 51
 class VGG(nn.Module):
     def __init__(self, cfg=_CFG_D, num_classes: int = 1000, dropout: float = 0.5):
         super().__init__()
+        self.fuse_epilogues = True  # use the fused NHWC conv-block epilogues on CUDA f16/bf16 channels_last inputs
         layers, c_in = [], 3
         for v in cfg:
             if v == "M":
@@ -30,8 +31,30 @@ class VGG(nn.Module):
                 nn.init.normal_(m.weight, 0, 0.01)
                 nn.init.zeros_(m.bias)
 
+    def _features_fused(self, x):
+        """conv → (bias+ReLU[+maxpool]) blocks through the fused NHWC epilogue kernels; module structure / state_dict stay
+        the standard ``features.N`` Sequential."""
+        from ..ops.nhwc import conv_bias_relu
+
+        mods = list(self.features)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, nn.Conv2d) and i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU):
+                pool = i + 2 < len(mods) and isinstance(mods[i + 2], nn.MaxPool2d) and mods[i + 2].kernel_size == 2 and mods[i + 2].stride == 2
+                if x.is_contiguous(memory_format=torch.channels_last) and m.out_channels % 8 == 0:
+                    x = conv_bias_relu(x, m, pool)
+                    i += 3 if pool else 2
+                    continue
+            x = m(x)
+            i += 1
+        return x
+
     def forward(self, x):
-        x = self.features(x)
+        if self.fuse_epilogues and x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and x.dim() == 4:
+            x = self._features_fused(x.contiguous(memory_format=torch.channels_last))
+        else:
+            x = self.features(x)
         x = self.avgpool(x)
         x = torch.flatten(x, 1)
         return self.classifier(x)

@@ -199,7 +199,7 @@ class PeerEngine:
         nbytes16 = _round_up(nbytes, 16)
         if v == "one_shot" and nbytes16 <= ONE_SHOT_SLOT:
             st = self.staging()
-            return C.AllReduceOneShotOp(self.comm, st.buf, ONE_SHOT_SLOT, src.tensor.data_ptr() + src_off, dst.tensor.data_ptr() + dst_off,
+            return C.AllReduceOneShotOp(self.comm, st.buf, st.offset, ONE_SHOT_SLOT, src.tensor.data_ptr() + src_off, dst.tensor.data_ptr() + dst_off,
                                         nbytes16, dtype_code(dtype), scale, self.launch_cfg("one_shot", nbytes16, blocks)), "one_shot"
         if v == "one_shot":
             v = "multimem" if self.has_multicast else "two_shot"
@@ -221,7 +221,7 @@ class PeerEngine:
         scale = 1.0 / self.world if average else 1.0
         if nbytes % 16 == 0 and tensor.data_ptr() % 16 == 0 and nbytes <= ONE_SHOT_SLOT:
             st = self.staging()
-            op = C.AllReduceOneShotOp(self.comm, st.buf, ONE_SHOT_SLOT, tensor.data_ptr(), tensor.data_ptr(), nbytes, dtype_code(tensor.dtype),
+            op = C.AllReduceOneShotOp(self.comm, st.buf, st.offset, ONE_SHOT_SLOT, tensor.data_ptr(), tensor.data_ptr(), nbytes, dtype_code(tensor.dtype),
                                       scale, self.launch_cfg("one_shot", nbytes))
             C.run_op(op, stream, self.device.index)
             return True

@@ -183,3 +183,49 @@ def test_tcgen05_grouped_gemm_matches_fp32_reference(dev, G, M, N, K):
     (torch.bmm(x2, w2.transpose(1, 2)) + b2.unsqueeze(1)).backward(gy.float())
     for got, want in ((x.grad, x2.grad), (w.grad, w2.grad), (bb.grad, b2.grad)):
         torch.testing.assert_close(got.float(), want, rtol=3e-2, atol=3e-2 * want.abs().max().item())
+
+
+@pytest.mark.parametrize("C,H", [(64, 16), (128, 12), (512, 8)])
+def test_fused_nhwc_conv_epilogues_match_torch(dev, C, H):
+    from bagua_b200.ops.nhwc import bias_relu, bias_relu_maxpool2
+
+    torch.manual_seed(6)
+    for pool in (False, True):
+        x = torch.randn(4, C, H, H, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        b = torch.randn(C, device=dev).to(torch.bfloat16)
+        gy = None
+        outs = []
+        for fused in (True, False):
+            xi = x.clone().requires_grad_(True)
+            bi = b.clone().requires_grad_(True)
+            if fused:
+                y0 = xi * 1.0  # non-leaf input (the conv output in real use); in-place epilogue is allowed on it
+                out = bias_relu_maxpool2(y0, bi) if pool else bias_relu(y0, bi)
+            else:
+                out = torch.nn.functional.relu(xi.float() + bi.float().view(1, -1, 1, 1))
+                out = torch.nn.functional.max_pool2d(out, 2, 2) if pool else out
+            if gy is None:
+                gy = torch.randn_like(out.float())
+            out.backward(gy.to(out.dtype))
+            outs.append((out.detach().float(), xi.grad.float(), bi.grad.float()))
+        (o1, gx1, gb1), (o2, gx2, gb2) = outs
+        torch.testing.assert_close(o1, o2, rtol=1e-2, atol=1e-2)
+        torch.testing.assert_close(gx1, gx2, rtol=1e-2, atol=1e-2)
+        torch.testing.assert_close(gb1, gb2, rtol=2e-2, atol=2e-2 * max(1.0, gb2.abs().max().item()))
+
+
+def test_vgg16_fused_path_matches_module_path(dev):
+    from bagua_b200.models import vgg16
+
+    torch.manual_seed(8)
+    m = vgg16(num_classes=10).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last).eval()
+    x = torch.randn(2, 3, 64, 64, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    res = []
+    for fuse in (True, False):
+        m.fuse_epilogues = fuse
+        m.zero_grad()
+        out = m(x)
+        out.float().sum().backward()
+        res.append((out.detach().float(), m.features[0].bias.grad.float().clone(), m.features[28].weight.grad.float().clone()))
+    for a, b in zip(*res):
+        torch.testing.assert_close(a, b, rtol=5e-2, atol=5e-2 * max(1.0, b.abs().max().item()))
