@@ -18,37 +18,45 @@ using namespace dev;
 template <typename T, int P>
 __global__ void __launch_bounds__(512) allreduce_twoshot_kernel(PeerCtx ctx, PeerBuf src, PeerBuf dst, size_t src_off,
                                                                 size_t dst_off, size_t total_vecs, float scale) {
+    // U vectors per thread per iteration keep U*P independent 16-byte peer loads in flight (NVLink latency is ~2 us:
+    // bandwidth = bytes in flight / latency, measured 7.5 GB/s per CTA without unrolling)
+    constexpr int U = P <= 2 ? 8 : (P <= 4 ? 4 : 2);
     const uint32_t e0 = load_epoch(ctx);
     bool ok = peer_barrier(ctx, e0 + 1);
     if (ok) {
         const size_t vpr = (total_vecs + P - 1) / P;
         const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
         const size_t base = static_cast<size_t>(ctx.rank) * vpr;
-        for (size_t j = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < vpr; j += stride) {
-            const size_t v = base + j;
-            if (v >= total_vecs) break;
-            float acc[Vec16<T>::N];
-            uint4 raw[P];
+        const size_t limit = (base + vpr < total_vecs ? base + vpr : total_vecs);  // exclusive end of my slice
+        for (size_t j0 = base + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; j0 < limit; j0 += stride * U) {
+            uint4 raw[U][P];
 #pragma unroll
-            for (int i = 0; i < P; ++i) {
-                const int p = (ctx.rank + i) % P;  // start at self, rotate so peers' links are hit evenly
-                raw[i] = ld_peer16(src.ptr[p] + src_off + v * 16);
-            }
-            Vec16<T>::unpack(raw[0], acc);
+            for (int u = 0; u < U; ++u) {
+                const size_t v = j0 + u * stride;
+                if (v < limit) {
 #pragma unroll
-            for (int i = 1; i < P; ++i) {
-                float f[Vec16<T>::N];
-                Vec16<T>::unpack(raw[i], f);
-#pragma unroll
-                for (int k = 0; k < Vec16<T>::N; ++k) acc[k] += f[k];
+                    for (int i = 0; i < P; ++i) raw[u][i] = ld_peer16(src.ptr[(ctx.rank + i) % P] + src_off + v * 16);  // rotate: links hit evenly
+                }
             }
 #pragma unroll
-            for (int k = 0; k < Vec16<T>::N; ++k) acc[k] *= scale;
-            const uint4 out = Vec16<T>::pack(acc);
+            for (int u = 0; u < U; ++u) {
+                const size_t v = j0 + u * stride;
+                if (v < limit) {
+                    float acc[Vec16<T>::N];
+                    Vec16<T>::unpack(raw[u][0], acc);
 #pragma unroll
-            for (int i = 0; i < P; ++i) {
-                const int p = (ctx.rank + i) % P;
-                st_peer16(dst.ptr[p] + dst_off + v * 16, out);
+                    for (int i = 1; i < P; ++i) {
+                        float f[Vec16<T>::N];
+                        Vec16<T>::unpack(raw[u][i], f);
+#pragma unroll
+                        for (int k = 0; k < Vec16<T>::N; ++k) acc[k] += f[k];
+                    }
+#pragma unroll
+                    for (int k = 0; k < Vec16<T>::N; ++k) acc[k] *= scale;
+                    const uint4 out = Vec16<T>::pack(acc);
+#pragma unroll
+                    for (int i = 0; i < P; ++i) st_peer16(dst.ptr[(ctx.rank + i) % P] + dst_off + v * 16, out);
+                }
             }
         }
         peer_barrier(ctx, e0 + 2);
@@ -61,6 +69,7 @@ __global__ void __launch_bounds__(512) allreduce_twoshot_kernel(PeerCtx ctx, Pee
 template <typename T>
 __global__ void __launch_bounds__(512) allreduce_multimem_kernel(PeerCtx ctx, PeerBuf src, PeerBuf dst, size_t src_off,
                                                                  size_t dst_off, size_t total_vecs, float scale) {
+    constexpr int U = 8;  // independent in-switch reductions in flight per thread
     const uint32_t e0 = load_epoch(ctx);
     bool ok = peer_barrier(ctx, e0 + 1);
     if (ok) {
@@ -68,18 +77,28 @@ __global__ void __launch_bounds__(512) allreduce_multimem_kernel(PeerCtx ctx, Pe
         const size_t vpr = (total_vecs + P - 1) / P;
         const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
         const size_t base = static_cast<size_t>(ctx.rank) * vpr;
-        for (size_t j = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < vpr; j += stride) {
-            const size_t v = base + j;
-            if (v >= total_vecs) break;
-            uint4 red = multimem_ld_reduce_add<T>(src.mc + src_off + v * 16);
-            if (scale != 1.0f) {
-                float f[Vec16<T>::N];
-                Vec16<T>::unpack(red, f);
+        const size_t limit = (base + vpr < total_vecs ? base + vpr : total_vecs);
+        for (size_t j0 = base + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; j0 < limit; j0 += stride * U) {
+            uint4 red[U];
 #pragma unroll
-                for (int k = 0; k < Vec16<T>::N; ++k) f[k] *= scale;
-                red = Vec16<T>::pack(f);
+            for (int u = 0; u < U; ++u) {
+                const size_t v = j0 + u * stride;
+                if (v < limit) red[u] = multimem_ld_reduce_add<T>(src.mc + src_off + v * 16);
             }
-            multimem_st16(dst.mc + dst_off + v * 16, red);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const size_t v = j0 + u * stride;
+                if (v < limit) {
+                    if (scale != 1.0f) {
+                        float f[Vec16<T>::N];
+                        Vec16<T>::unpack(red[u], f);
+#pragma unroll
+                        for (int k = 0; k < Vec16<T>::N; ++k) f[k] *= scale;
+                        red[u] = Vec16<T>::pack(f);
+                    }
+                    multimem_st16(dst.mc + dst_off + v * 16, red[u]);
+                }
+            }
         }
         peer_barrier(ctx, e0 + 2);
     }
@@ -144,59 +163,73 @@ __global__ void __launch_bounds__(512)
     const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
     const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (ok) {
+        constexpr int U = USE_MC ? 4 : (P <= 2 ? 4 : (P <= 4 ? 2 : 1));  // vectors in flight per thread (register budget: U*P*4)
         const size_t base = static_cast<size_t>(ctx.rank) * vpr;
-        for (size_t j = tid; j < vpr; j += stride) {
-            const size_t v = base + j;
-            if (v >= total_vecs) break;
-            float g[N];
-            if (USE_MC) {
-                Vec16<T>::unpack(multimem_ld_reduce_add<T>(grads.mc + g_off + v * 16), g);
-            } else {
-                uint4 raw[P];
+        const size_t limit = (base + vpr < total_vecs ? base + vpr : total_vecs);
+        for (size_t j0 = base + tid; j0 < limit; j0 += stride * U) {
+            uint4 raw[U][USE_MC ? 1 : P];
 #pragma unroll
-                for (int i = 0; i < P; ++i) raw[i] = ld_peer16(grads.ptr[(ctx.rank + i) % P] + g_off + v * 16);
-                Vec16<T>::unpack(raw[0], g);
+            for (int u = 0; u < U; ++u) {
+                const size_t v = j0 + u * stride;
+                if (v < limit) {
+                    if (USE_MC) {
+                        raw[u][0] = multimem_ld_reduce_add<T>(grads.mc + g_off + v * 16);
+                    } else {
 #pragma unroll
-                for (int i = 1; i < P; ++i) {
-                    float f[N];
-                    Vec16<T>::unpack(raw[i], f);
-#pragma unroll
-                    for (int k = 0; k < N; ++k) g[k] += f[k];
-                }
-            }
-            // optimizer state of the owned slice: index j*N within the shard
-            float w[N], m[N];
-            float4* mp = reinterpret_cast<float4*>(master + j * N);
-            float4* mo = reinterpret_cast<float4*>(momentum_buf + j * N);
-#pragma unroll
-            for (int q = 0; q < N / 4; ++q) {
-                float4 a = mp[q];
-                w[4 * q] = a.x, w[4 * q + 1] = a.y, w[4 * q + 2] = a.z, w[4 * q + 3] = a.w;
-                if (hp.momentum != 0.f) {
-                    float4 b = mo[q];
-                    m[4 * q] = b.x, m[4 * q + 1] = b.y, m[4 * q + 2] = b.z, m[4 * q + 3] = b.w;
+                        for (int i = 0; i < (USE_MC ? 1 : P); ++i) raw[u][i] = ld_peer16(grads.ptr[(ctx.rank + i) % P] + g_off + v * 16);
+                    }
                 }
             }
 #pragma unroll
-            for (int k = 0; k < N; ++k) {
-                float d = g[k] * scale + hp.weight_decay * w[k];
-                if (hp.momentum != 0.f) {
-                    m[k] = hp.first_step ? d : hp.momentum * m[k] + (1.f - hp.dampening) * d;
-                    d = hp.nesterov ? d + hp.momentum * m[k] : m[k];
+            for (int u = 0; u < U; ++u) {
+                const size_t v = j0 + u * stride;
+                if (v >= limit) continue;
+                const size_t j = v - base;
+                float g[N];
+                Vec16<T>::unpack(raw[u][0], g);
+                if (!USE_MC) {
+#pragma unroll
+                    for (int i = 1; i < (USE_MC ? 1 : P); ++i) {
+                        float f[N];
+                        Vec16<T>::unpack(raw[u][i], f);
+#pragma unroll
+                        for (int k = 0; k < N; ++k) g[k] += f[k];
+                    }
                 }
-                w[k] -= hp.lr * d;
-            }
+                // optimizer state of the owned slice: index j*N within the shard
+                float w[N], m[N];
+                float4* mp = reinterpret_cast<float4*>(master + j * N);
+                float4* mo = reinterpret_cast<float4*>(momentum_buf + j * N);
 #pragma unroll
-            for (int q = 0; q < N / 4; ++q) {
-                mp[q] = make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-                if (hp.momentum != 0.f) mo[q] = make_float4(m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
-            }
-            const uint4 out = Vec16<T>::pack(w);
-            if (USE_MC) {
-                multimem_st16(weights.mc + w_off + v * 16, out);
-            } else {
+                for (int q = 0; q < N / 4; ++q) {
+                    float4 a = mp[q];
+                    w[4 * q] = a.x, w[4 * q + 1] = a.y, w[4 * q + 2] = a.z, w[4 * q + 3] = a.w;
+                    if (hp.momentum != 0.f) {
+                        float4 bb = mo[q];
+                        m[4 * q] = bb.x, m[4 * q + 1] = bb.y, m[4 * q + 2] = bb.z, m[4 * q + 3] = bb.w;
+                    }
+                }
 #pragma unroll
-                for (int i = 0; i < P; ++i) st_peer16(weights.ptr[(ctx.rank + i) % P] + w_off + v * 16, out);
+                for (int k = 0; k < N; ++k) {
+                    float d = g[k] * scale + hp.weight_decay * w[k];
+                    if (hp.momentum != 0.f) {
+                        m[k] = hp.first_step ? d : hp.momentum * m[k] + (1.f - hp.dampening) * d;
+                        d = hp.nesterov ? d + hp.momentum * m[k] : m[k];
+                    }
+                    w[k] -= hp.lr * d;
+                }
+#pragma unroll
+                for (int q = 0; q < N / 4; ++q) {
+                    mp[q] = make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+                    if (hp.momentum != 0.f) mo[q] = make_float4(m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
+                }
+                const uint4 out = Vec16<T>::pack(w);
+                if (USE_MC) {
+                    multimem_st16(weights.mc + w_off + v * 16, out);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < P; ++i) st_peer16(weights.ptr[(ctx.rank + i) % P] + w_off + v * 16, out);
+                }
             }
         }
         ok = peer_barrier(ctx, e0 + 2);
