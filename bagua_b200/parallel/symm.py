@@ -167,6 +167,10 @@ class PeerEngine:
             return "multimem" if self.has_multicast else "two_shot"
         if nbytes <= ONE_SHOT_SLOT // 2:
             return "one_shot"
+        # measured (profiles/allreduce_n*.json): with 2 ranks the peer-load two-shot kernel beats the in-switch reduction
+        # (654 vs 402 GB/s at 256 MiB); from 4 ranks on multimem moves ~N/2 x fewer bytes over each GPU's links
+        if self.world <= 2:
+            return "two_shot"
         return "multimem" if self.has_multicast else "two_shot"
 
     def launch_cfg(self, variant: str, nbytes: int, blocks: int = 0):
@@ -179,9 +183,9 @@ class PeerEngine:
             if variant == "one_shot":
                 blocks = max(1, min(8, vecs // 512))
             elif variant == "multimem":
-                blocks = max(1, min(16, vecs // (self.world * 512)))
+                blocks = max(1, min(16, vecs // (self.world * 2048)))
             else:
-                blocks = max(1, min(32, vecs // (self.world * 512)))
+                blocks = max(1, min(32, vecs // (self.world * 2048)))
         return C.LaunchCfg(int(min(blocks, C.MAX_COMM_BLOCKS)), 512)
 
     def staging(self) -> SymmSlice:
