@@ -183,7 +183,7 @@ class PeerEngine:
             if variant == "one_shot":
                 blocks = max(1, min(8, vecs // 512))
             elif variant == "multimem":
-                blocks = max(1, min(16, vecs // (self.world * 2048)))
+                blocks = max(1, min(8, vecs // (self.world * 2048)))  # 8 CTAs saturate NVLS (profiles/allreduce_n8.json)
             else:
                 blocks = max(1, min(32, vecs // (self.world * 2048)))
         return C.LaunchCfg(int(min(blocks, C.MAX_COMM_BLOCKS)), 512)

@@ -37,7 +37,9 @@ def parse():
     p.add_argument("--momentum", type=float, default=0.0)
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--profile", default="", help="write a torch.profiler kernel table of 3 steps to this file (not a benchmark run)")
-    p.add_argument("--fused-shard", action="store_true", help="fold the SGD update into the allreduce kernel (sharded optimizer state)")
+    p.add_argument("--fused-shard", dest="fused_shard", action="store_true", default=None,
+                   help="fold the SGD update into the allreduce kernel (sharded optimizer state); default: on for N > 1")
+    p.add_argument("--no-fused-shard", dest="fused_shard", action="store_false")
     return p.parse_args()
 
 
@@ -138,6 +140,8 @@ def main():
     torch.backends.cudnn.benchmark = True
     torch.manual_seed(1234 + rank)
 
+    if args.fused_shard is None:
+        args.fused_shard = world > 1 and args.algorithm == "gradient_allreduce"
     bs = args.batch_size
     model = get_model(args.model).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
     if args.fused_shard:
