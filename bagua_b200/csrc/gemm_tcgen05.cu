@@ -24,18 +24,30 @@ namespace bagua {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 4;
+constexpr int BM = 128, BK = 64;
 constexpr int UMMA_K = 16;
 constexpr int kGemmThreads = 192;
-constexpr uint32_t kStageBytesA = BM * BK * 2, kStageBytesB = BN * BK * 2;
-constexpr uint32_t kTmemCols = 128;  // one 128x128 fp32 accumulator
+constexpr uint32_t kStageBytesA = BM * BK * 2;
 
+// Persistent kernel, tile BM x BN with BN in {128, 256}. BN = 256 keeps the tensor pipe fed from shared memory: one
+// M128 N256 K16 MMA takes 128 cycles and reads 4 KB of A + 8 KB of B = 96 B/cycle (the smem port moves 128 B/cycle; at
+// N128 it would be exactly 128 B/cycle, i.e. smem-bound). Two accumulators of BN columns each double-buffer TMEM so
+// the epilogue of tile i overlaps the MMAs of tile i+1.
+template <int BN>
+struct GemmCfg {
+    static constexpr int STAGES = BN == 256 ? 4 : 6;
+    static constexpr uint32_t kStageBytesB = BN * BK * 2;
+    static constexpr uint32_t kTmemCols = 2 * BN;  // 256 or 512 (power of two)
+};
+
+template <int BN>
 struct __align__(1024) GemmSmem {
-    uint8_t a[STAGES][kStageBytesA];
-    uint8_t b[STAGES][kStageBytesB];
-    uint64_t full[STAGES];
-    uint64_t empty[STAGES];
-    uint64_t acc_ready;
+    uint8_t a[GemmCfg<BN>::STAGES][kStageBytesA];
+    uint8_t b[GemmCfg<BN>::STAGES][GemmCfg<BN>::kStageBytesB];
+    uint64_t full[GemmCfg<BN>::STAGES];
+    uint64_t empty[GemmCfg<BN>::STAGES];
+    uint64_t acc_full[2];
+    uint64_t acc_empty[2];
     uint32_t tmem_base;
 };
 
@@ -46,6 +58,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -82,6 +97,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 // cute::UMMA::InstrDescriptor for kind::f16: D=F32 [4,6)=1, A=BF16 [7,10)=1, B=BF16 [10,13)=1, K-major A/B, N>>3 [17,23), M>>4 [24,29)
+template <int BN>
 __device__ __forceinline__ constexpr uint32_t make_instr_desc() {
     return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
 }
@@ -111,13 +127,28 @@ __device__ __forceinline__ float gelu_tanh(float x) {
     return 0.5f * x * (1.f + tanhf(u));
 }
 
+// tile id → (group, m block, n block): consecutive ids (= concurrently running CTAs) share the B tile and walk along M
+struct TileCoord {
+    int g, m0, n0;
+};
+__device__ __forceinline__ TileCoord tile_coord(int tile, int tiles_m, int tiles_n, int BN) {
+    TileCoord c;
+    c.m0 = (tile % tiles_m) * BM;
+    const int r = tile / tiles_m;
+    c.n0 = (r % tiles_n) * BN;
+    c.g = r / tiles_n;
+    return c;
+}
+
+template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     grouped_gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, __nv_bfloat16* __restrict__ C,
-                           const float* __restrict__ bias, int M, int N, int K, int act) {
+                           const float* __restrict__ bias, int M, int N, int K, int num_tiles, int tiles_m, int tiles_n, int act) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
-    GemmSmem& sm = *reinterpret_cast<GemmSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    GemmSmem<BN>& sm = *reinterpret_cast<GemmSmem<BN>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM, g = blockIdx.z;
     const int num_kb = K / BK;
 
     if (warp == 0 && lane == 0) {
@@ -127,11 +158,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             mbar_init(&sm.full[s], 1);
             mbar_init(&sm.empty[s], 1);
         }
-        mbar_init(&sm.acc_ready, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&sm.acc_full[i], 1);
+            mbar_init(&sm.acc_empty[i], 4);  // one arrival per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // whole warp: TMEM allocation (the same warp frees it)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(Cfg::kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tcgen05_fence_before();
@@ -141,62 +175,80 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 
     if (warp == 0) {
         if (lane == 0) {  // ===== TMA producer =====
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t parity = ((kb / STAGES) & 1) ^ 1;
-                mbar_wait(&sm.empty[s], parity);  // fresh barrier: waiting on parity 1 passes immediately
-                mbar_expect_tx(&sm.full[s], kStageBytesA + kStageBytesB);
-                tma_load_3d(sm.a[s], &tm_a, &sm.full[s], kb * BK, m0, g);
-                tma_load_3d(sm.b[s], &tm_b, &sm.full[s], kb * BK, n0, g);
+            uint32_t it = 0;  // running stage counter across tiles
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const TileCoord tc = tile_coord(tile, tiles_m, tiles_n, BN);
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&sm.empty[s], ((it / STAGES) & 1) ^ 1);  // fresh barrier: waiting on parity 1 passes immediately
+                    mbar_expect_tx(&sm.full[s], kStageBytesA + Cfg::kStageBytesB);
+                    tma_load_3d(sm.a[s], &tm_a, &sm.full[s], kb * BK, tc.m0, tc.g);
+                    tma_load_3d(sm.b[s], &tm_b, &sm.full[s], kb * BK, tc.n0, tc.g);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {  // ===== MMA issuer =====
-            const uint32_t idesc = make_instr_desc();
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                mbar_wait(&sm.full[s], (kb / STAGES) & 1);
+            constexpr uint32_t idesc = make_instr_desc<BN>();
+            uint32_t it = 0, local = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+                const uint32_t acc = local & 1;
+                mbar_wait(&sm.acc_empty[acc], ((local >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
                 tcgen05_fence_after();
-                const uint64_t da = make_smem_desc(smem_u32(sm.a[s])), db = make_smem_desc(smem_u32(sm.b[s]));
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&sm.full[s], (it / STAGES) & 1);
+                    tcgen05_fence_after();
+                    const uint64_t da = make_smem_desc(smem_u32(sm.a[s])), db = make_smem_desc(smem_u32(sm.b[s]));
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                    // advance 32 bytes (16 bf16) along K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-                    umma_bf16(tmem_base, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // advance 32 bytes (16 bf16) along K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+                        umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    tcgen05_commit(&sm.empty[s]);  // arrives when the MMAs above have finished reading this stage
                 }
-                tcgen05_commit(&sm.empty[s]);  // arrives when the MMAs above have finished reading this stage
+                tcgen05_commit(&sm.acc_full[acc]);
             }
-            tcgen05_commit(&sm.acc_ready);
         }
     } else {  // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        mbar_wait(&sm.acc_ready, 0);
-        tcgen05_fence_after();
-        __nv_bfloat16* crow = C + (static_cast<size_t>(g) * M + (m0 + row)) * N + n0;
-        const float* brow = bias ? bias + static_cast<size_t>(g) * N + n0 : nullptr;
+        uint32_t local = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+            const TileCoord tc = tile_coord(tile, tiles_m, tiles_n, BN);
+            const uint32_t acc = local & 1;
+            mbar_wait(&sm.acc_full[acc], (local >> 1) & 1);
+            tcgen05_fence_after();
+            __nv_bfloat16* crow = C + (static_cast<size_t>(tc.g) * M + (tc.m0 + row)) * N + tc.n0;
+            const float* brow = bias ? bias + static_cast<size_t>(tc.g) * N + tc.n0 : nullptr;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c), r);
-            uint32_t packed[16];
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + static_cast<uint32_t>(c), r);
+                uint32_t packed[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float v0 = __uint_as_float(r[2 * j]), v1 = __uint_as_float(r[2 * j + 1]);
-                if (brow) v0 += __ldg(brow + c + 2 * j), v1 += __ldg(brow + c + 2 * j + 1);
-                if (act == 1) v0 = gelu_tanh(v0), v1 = gelu_tanh(v1);
-                __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-                packed[j] = *reinterpret_cast<uint32_t*>(&h);
+                for (int j = 0; j < 16; ++j) {
+                    float v0 = __uint_as_float(r[2 * j]), v1 = __uint_as_float(r[2 * j + 1]);
+                    if (brow) v0 += __ldg(brow + c + 2 * j), v1 += __ldg(brow + c + 2 * j + 1);
+                    if (act == 1) v0 = gelu_tanh(v0), v1 = gelu_tanh(v1);
+                    __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+                    packed[j] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(crow + c);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
             }
-            uint4* dst = reinterpret_cast<uint4*>(crow + c);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.acc_empty[acc]);  // this warp no longer reads the accumulator
         }
     }
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
     }
 }
 
@@ -220,7 +272,7 @@ CUtensorMap make_map(const void* ptr, int G, int rows, int K, int box_rows) {
     CUtensorMap m;
     cuuint64_t dims[3] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(G)};
     cuuint64_t strides[2] = {static_cast<cuuint64_t>(K) * 2, static_cast<cuuint64_t>(rows) * K * 2};
-    cuuint32_t box[3] = {BK, static_cast<cuuint32_t>(box_rows), 1};
+    cuuint32_t box[3] = {BK, static_cast<cuuint32_t>(box_rows), 1};  // ≤ 256 rows per box
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -230,21 +282,37 @@ CUtensorMap make_map(const void* ptr, int G, int rows, int K, int box_rows) {
 
 }  // namespace
 
-bool grouped_gemm_supported(int M, int N, int K) { return M > 0 && N > 0 && K > 0 && M % BM == 0 && N % BN == 0 && K % BK == 0; }
+bool grouped_gemm_supported(int M, int N, int K) { return M > 0 && N > 0 && K > 0 && M % BM == 0 && N % 128 == 0 && K % BK == 0; }
+
+namespace {
+template <int BN>
+void launch_bn(const void* A, const void* B, void* C, const float* bias, int G, int M, int N, int K, int act, cudaStream_t stream) {
+    const CUtensorMap ta = make_map(A, G, M, K, BM), tb = make_map(B, G, N, K, BN);
+    const size_t smem = sizeof(GemmSmem<BN>) + 1024;
+    static bool configured = false;
+    static int num_sms = 0;
+    if (!configured) {
+        BAGUA_CUDA_CHECK(cudaFuncSetAttribute(grouped_gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        int dev = 0;
+        BAGUA_CUDA_CHECK(cudaGetDevice(&dev));
+        BAGUA_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        configured = true;
+    }
+    const int tiles_m = M / BM, tiles_n = N / BN;
+    const int num_tiles = tiles_m * tiles_n * G;
+    const int grid = num_tiles < num_sms ? num_tiles : num_sms;  // persistent: one CTA per SM
+    grouped_gemm_tn_kernel<BN><<<grid, kGemmThreads, smem, stream>>>(ta, tb, static_cast<__nv_bfloat16*>(C), bias, M, N, K, num_tiles, tiles_m, tiles_n, act);
+}
+}  // namespace
 
 void launch_grouped_gemm_tn(const void* A, const void* B, void* C, const float* bias, int G, int M, int N, int K, int act, cudaStream_t stream) {
     if (!grouped_gemm_supported(M, N, K)) throw std::runtime_error("bagua: grouped_gemm_tn needs M%128==0, N%128==0, K%64==0");
     if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) & 15u)
         throw std::runtime_error("bagua: grouped_gemm_tn needs 16-byte aligned operands");
-    const CUtensorMap ta = make_map(A, G, M, K, BM), tb = make_map(B, G, N, K, BN);
-    const size_t smem = sizeof(GemmSmem) + 1024;
-    static bool configured = false;
-    if (!configured) {
-        BAGUA_CUDA_CHECK(cudaFuncSetAttribute(grouped_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        configured = true;
-    }
-    dim3 grid(N / BN, M / BM, G);
-    grouped_gemm_tn_kernel<<<grid, kGemmThreads, smem, stream>>>(ta, tb, static_cast<__nv_bfloat16*>(C), bias, M, N, K, act);
+    if (N % 256 == 0)
+        launch_bn<256>(A, B, C, bias, G, M, N, K, act, stream);
+    else
+        launch_bn<128>(A, B, C, bias, G, M, N, K, act, stream);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw std::runtime_error(std::string("bagua: launch of grouped_gemm_tn failed: ") + cudaGetErrorString(e));
 }
