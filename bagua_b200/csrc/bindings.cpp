@@ -56,6 +56,7 @@ PYBIND11_MODULE(_C, m) {
         cudaRuntimeGetVersion(&rt);
         return std::string("bagua_b200 native core; target sm_100a; cuda runtime ") + std::to_string(rt);
     });
+    m.def("launch_count", &launch_count);
     m.def("signal_pad_bytes", &PeerComm::signal_pad_bytes);
     m.def("minmax_uint8_chunk_bytes", &minmax_uint8_chunk_bytes);
     m.def("dtype_size", &dtype_size);

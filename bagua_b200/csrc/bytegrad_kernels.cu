@@ -387,6 +387,7 @@ void dispatch_float(int dtype, F&& f) {
 void check(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw std::runtime_error(std::string("bagua: launch of ") + what + " failed: " + cudaGetErrorString(e));
+    count_launch();
 }
 }  // namespace
 

@@ -53,6 +53,10 @@ struct PeerBuf {
     char* mc;  // multicast (NVLS) address of the same pages or nullptr
 };
 
+// Number of kernels this library has launched in the current process (benchmarks report it as `gpu_launches`).
+uint64_t launch_count();
+void count_launch(int n = 1);
+
 #define BAGUA_CUDA_CHECK(expr)                                                                         \
     do {                                                                                               \
         cudaError_t _e = (expr);                                                                       \

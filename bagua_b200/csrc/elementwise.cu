@@ -22,6 +22,7 @@ inline int grid_for(size_t work_items, int per_thread = 4, int max_blocks = 148 
 void check(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw std::runtime_error(std::string("bagua: launch of ") + what + " failed: " + cudaGetErrorString(e));
+    count_launch();
 }
 template <typename F>
 void dispatch_float(int dtype, F&& f) {
@@ -109,6 +110,7 @@ void launch_minmax_uint8_compress(const void* in, size_t numel, int dtype, int n
         chunk_quantize_kernel<T><<<grid, kThreads, 0, stream>>>(static_cast<const T*>(in), chunk, chunk_bytes, first, mm, out);
     });
     check("minmax_uint8_compress");
+    count_launch(2);  // init + min/max + quantise = 3 launches
 }
 
 void launch_minmax_uint8_decompress(const uint8_t* in, size_t numel, int dtype, int n_chunks, void* out, cudaStream_t stream) {

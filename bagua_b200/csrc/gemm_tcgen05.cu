@@ -315,6 +315,7 @@ void launch_grouped_gemm_tn(const void* A, const void* B, void* C, const float* 
         launch_bn<128>(A, B, C, bias, G, M, N, K, act, stream);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw std::runtime_error(std::string("bagua: launch of grouped_gemm_tn failed: ") + cudaGetErrorString(e));
+    count_launch();
 }
 
 }  // namespace bagua

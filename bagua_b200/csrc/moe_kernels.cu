@@ -124,6 +124,7 @@ void dispatch_float(int dtype, F&& f) {
 void check(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw std::runtime_error(std::string("bagua: launch of ") + what + " failed: " + cudaGetErrorString(e));
+    count_launch();
 }
 void check_shape(int M, int dtype, int nblocks) {
     if ((static_cast<size_t>(M) * dtype_size(dtype)) % 16) throw std::runtime_error("bagua: MoE rows must be a multiple of 16 bytes");

@@ -22,6 +22,7 @@ constexpr int kVec = 8;  // elements per thread per iteration
 void check(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw std::runtime_error(std::string("bagua: launch of ") + what + " failed: " + cudaGetErrorString(e));
+    count_launch();
 }
 
 template <typename T>

@@ -175,6 +175,7 @@ void dispatch_half(int dtype, F&& f) {
 void check(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw std::runtime_error(std::string("bagua: launch of ") + what + " failed: " + cudaGetErrorString(e));
+    count_launch();
 }
 void check_c(int C) {
     if (C % 8 || C > 2048) throw std::runtime_error("bagua: NHWC fused epilogues need C % 8 == 0 and C <= 2048");

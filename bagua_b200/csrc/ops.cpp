@@ -4,7 +4,13 @@
 
 #include <cstring>
 
+#include <atomic>
+
 namespace bagua {
+
+static std::atomic<uint64_t> g_launches{0};
+uint64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
+void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
 
 namespace {
 inline cudaStream_t S(StreamHandle s) { return reinterpret_cast<cudaStream_t>(s); }

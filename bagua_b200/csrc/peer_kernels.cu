@@ -314,6 +314,7 @@ void dispatch_float(int dtype, F&& f) {
 void check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw std::runtime_error(std::string("bagua: launch of ") + what + " failed: " + cudaGetErrorString(e));
+    count_launch();
 }
 void check_blocks(int nblocks) {
     if (nblocks < 1 || nblocks > kMaxCommBlocks) throw std::runtime_error("bagua: peer kernel grid must be 1.." + std::to_string(kMaxCommBlocks));

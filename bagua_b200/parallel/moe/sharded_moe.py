@@ -152,9 +152,20 @@ class TopKGate(torch.nn.Module):
         self.min_capacity = min_capacity
         self.noisy_gate_policy = noisy_gate_policy
 
+    def _apply(self, fn, *args, **kwargs):
+        # The gate is always fp32 (reference sharded_moe.py:271-273 re-casts it inside forward). Doing it here instead keeps
+        # ``model.to(torch.bfloat16)`` from ever producing a bf16 gate, so the parameter (and its bucketed gradient) is never
+        # re-created after ``with_bagua`` has registered it.
+        super()._apply(fn, *args, **kwargs)
+        if self.wg.weight.is_floating_point() and self.wg.weight.dtype != torch.float32:
+            self.wg.weight.data = self.wg.weight.data.float()
+            if self.wg.weight.grad is not None:
+                self.wg.weight.grad = self.wg.weight.grad.float()
+        return self
+
     def route(self, input: Tensor, used_token: Optional[Tensor] = None) -> GateOutput:
         if self.wg.weight.dtype != torch.float32:
-            self.wg = self.wg.float()
+            raise RuntimeError("the MoE gate must stay fp32; do not cast `gate.wg` after wrapping the model with with_bagua")
         x = input.float()
         if self.noisy_gate_policy == "Jitter" and self.training:
             x = multiplicative_jitter(x, device=input.device)

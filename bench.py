@@ -72,7 +72,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:  # noqa: BLE001
             self.proc = None
@@ -111,6 +111,12 @@ def main():
     args = parse()
     if args.impl == "reference":
         return reference_arm(args)
+
+    # Only the final JSON line may reach stdout: libraries (e.g. NCCL's "NCCL version ..." banner) print there too, so fd 1
+    # is pointed at stderr for the duration of the run and restored just before the result is printed.
+    sys.stdout.flush()
+    saved_stdout_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -213,6 +219,9 @@ def main():
             dist.barrier()
         return float(ms.item())
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # started before the warm-up so that the (short) timed region is covered by several samples
     for i in range(max(args.warmup, 3)):
         train_step(x_dev, y_dev)
     if args.profile:
@@ -227,16 +236,14 @@ def main():
             with open(args.profile, "w") as f:
                 f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
         return 0
-    launches0 = optimizer.kernel_launches
-    sched0 = model.bagua_ddp._bagua_backend.scheduled_total()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    from bagua_b200.core import native
+
+    torch.cuda.synchronize()
+    launches0 = native().launch_count()  # every kernel of this library counts itself (csrc/common.h: count_launch)
     ms = timed(lambda i: train_step(x_dev, y_dev), args.steps)
+    model.bagua_ddp._bagua_backend.wait_pending_comm_ops(torch.cuda.current_stream().cuda_stream, False)
+    gpu_launches = native().launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    native_comm_ops = sum(1 for b in model.bagua_buckets if getattr(b, "allreduce_variant", "") in ("one_shot", "two_shot", "multimem", "fused_sgd_two_shot", "fused_sgd_multimem"))
-    comm_launches = (model.bagua_ddp._bagua_backend.scheduled_total() - sched0) if native_comm_ops else 0
-    gpu_launches = (optimizer.kernel_launches - launches0) + comm_launches
     value = bs * world * args.steps / (ms / 1e3)
 
     e2e = None
@@ -280,7 +287,10 @@ def main():
             "e2e": e2e,
             "gpu_launches": int(gpu_launches),
         }
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.dup2(saved_stdout_fd, 1)
+        print(json.dumps(out), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier()
     return 0
