@@ -1,0 +1,128 @@
+"""Drop-in for the reference's native python module ``bagua_core`` (rust/bagua-core/bagua-core-py/src/lib.rs:540-568;
+shim package bagua_core/__init__.py): the same class names on top of the C++ core of this repository
+(``bagua_b200._C``).  Tensors are described by raw pointers here, so ``BaguaTensorPy`` takes a torch tensor and extracts
+them once; communicators are the (torch ProcessGroup, stream) pairs of ``bagua_b200.communication``."""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from bagua_b200.core import dtype_code, native
+
+__all__ = ["BaguaCommBackendPy", "BaguaTensorPy", "BaguaBucketPy", "BaguaSingleCommunicatorPy", "show_version", "install_deps"]
+
+
+def show_version() -> str:
+    v = native().show_version()
+    print(v)
+    return v
+
+
+def install_deps():
+    """The reference downloads an NCCL tarball here (bagua_core/bagua_install_deps.py); nothing to install: the native core
+    is built in-tree from source (``python -m bagua_b200._build``)."""
+    return None
+
+
+class BaguaTensorPy:
+    def __init__(self, name: str, torch_tensor: torch.Tensor):
+        self.torch_tensor = torch_tensor
+        self.inner = native().Tensor(name, torch_tensor.data_ptr(), torch_tensor.numel(), dtype_code(torch_tensor.dtype),
+                                     torch_tensor.device.index if torch_tensor.is_cuda else -1)
+
+    def name(self) -> str:
+        return self.inner.name()
+
+    def data_ptr(self) -> int:
+        return self.inner.data_ptr()
+
+    def device_id(self) -> int:
+        return self.inner.device_id()
+
+    def num_elements(self) -> int:
+        return self.inner.num_elements()
+
+    def num_elements_allocated(self) -> int:
+        return self.inner.num_elements()
+
+    def dtype(self) -> str:
+        return {0: "f32", 1: "f16", 2: "u8", 3: "i64", 4: "bf16"}[self.inner.dtype()]
+
+    def compress(self, method: str, n_chunks: int, target_chunk: int = -1) -> "BaguaTensorPy":
+        from bagua_b200.ops import quant
+
+        assert method == "MinMaxUInt8"
+        return BaguaTensorPy(self.name() + "_compressed", quant.compress(self.torch_tensor.contiguous().view(-1), n_chunks, target_chunk))
+
+    def decompress_from(self, method: str, n_chunks: int, compressed: "BaguaTensorPy"):
+        from bagua_b200.ops import quant
+
+        assert method == "MinMaxUInt8"
+        quant.decompress(compressed.torch_tensor, self.torch_tensor.view(-1), n_chunks)
+
+    def to_numpy_f32(self):
+        return self.torch_tensor.detach().float().cpu().numpy()
+
+    def to_numpy_u8(self):
+        return self.torch_tensor.detach().to(torch.uint8).cpu().numpy()
+
+
+class BaguaBucketPy:
+    def __init__(self, name: str, tensors: List[BaguaTensorPy]):
+        self._tensors = tensors
+        self.inner = native().Bucket(name, [t.inner for t in tensors])
+
+    def tensors(self) -> List[BaguaTensorPy]:
+        return self._tensors
+
+    def append_python_op(self, op):
+        self.inner.append_python_op(op, "python")
+
+    def print_ops(self):
+        print(self.inner.print_ops())
+
+    def clear_ops(self):
+        self.inner.clear_ops()
+
+    def ready_for_comm(self) -> bool:
+        return self.inner.ready_for_comm()
+
+    def reset_comm_ready(self):
+        self.inner.reset_comm_ready()
+
+
+class BaguaCommBackendPy:
+    def __init__(self, schedule_channel_cap: int, device_id: int, comm_stream: int = 0):
+        self.inner = native().Backend(schedule_channel_cap, device_id, comm_stream, 300.0)
+
+    def register_ordered_buckets(self, buckets: List[BaguaBucketPy]):
+        self.inner.register_ordered_buckets([b.inner for b in buckets])
+
+    def mark_communication_ready(self, tensor: BaguaTensorPy, ready_cuda_event_ptr: int = 0):
+        self.inner.mark_communication_ready(tensor.inner, ready_cuda_event_ptr)
+
+    def wait_pending_comm_ops(self) -> int:
+        return self.inner.wait_pending_comm_ops(0, True)
+
+
+class BaguaSingleCommunicatorPy:
+    """(rank, nranks, device, stream) communicator with the reference's collective method names, backed by
+    ``bagua_b200.communication.Communicator`` over the default torch process group."""
+
+    def __init__(self, rank: int, nranks: int, device_id: int, stream_ptr: int = 0, nccl_unique_id_str: Optional[str] = None):
+        from bagua_b200 import communication as comm_mod
+
+        self._comm = comm_mod._get_default_group().get_global_communicator()
+        assert self._comm.nranks() == nranks and self._comm.rank() == rank, "communicator shape must match the default process group"
+        self._device_id = device_id
+
+    @staticmethod
+    def generate_nccl_unique_id_str() -> str:
+        return "bagua_b200-symmetric-memory"  # no NCCL id is exchanged: groups rendezvous through torch.distributed
+
+    def __getattr__(self, name):
+        return getattr(self._comm, name)
+
+    def device_id(self) -> int:
+        return self._device_id

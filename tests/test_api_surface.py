@@ -1,0 +1,132 @@
+"""Public API surface parity: names importable through ``bagua.torch_api`` / ``bagua_core`` exactly as
+user code of the reference expects, tensor/bucket patch methods, multiple models in one process."""
+import copy
+
+import pytest
+import torch
+
+from tests.mp_utils import run_distributed
+
+
+def test_reference_import_paths_resolve():
+    import bagua.torch_api as bagua
+    from bagua.bagua_define import BaguaHyperparameter, TensorDeclaration, TensorDtype, get_tensor_declaration_bytes  # noqa: F401
+    from bagua.service import AutotuneClient, AutotuneService  # noqa: F401
+    from bagua.service.autotune_task_manager import AutotuneTaskManager  # noqa: F401
+    from bagua.service.bayesian_optimizer import BayesianOptimizer, BoolParam, FloatParam, IntParam  # noqa: F401
+    from bagua.torch_api.algorithms import Algorithm, GlobalAlgorithmRegistry, async_model_average, bytegrad, decentralized, gradient_allreduce, q_adam  # noqa: F401
+    from bagua.torch_api.bucket import BaguaBucket  # noqa: F401
+    from bagua.torch_api.checkpoint import load_checkpoint, save_checkpoint  # noqa: F401
+    from bagua.torch_api.communication import ReduceOp, _get_default_group, _rank_not_in_group, from_torch_group, init_process_group, is_initialized, new_group  # noqa: F401
+    from bagua.torch_api.contrib import CachedDataset, CacheLoader, LoadBalancingDistributedBatchSampler, LoadBalancingDistributedSampler, fuse_optimizer  # noqa: F401
+    from bagua.torch_api.contrib.sync_batchnorm import SyncBatchNorm  # noqa: F401
+    from bagua.torch_api.contrib.utils.redis_store import RedisStore  # noqa: F401
+    from bagua.torch_api.contrib.utils.store import ClusterStore, Store  # noqa: F401
+    from bagua.torch_api.data_parallel import DistributedDataParallel  # noqa: F401
+    from bagua.torch_api.data_parallel.functional import all_reduce  # noqa: F401
+    from bagua.torch_api.model_parallel.moe import MoE  # noqa: F401
+    from bagua.torch_api.moe import is_moe_param  # noqa: F401
+    from bagua.torch_api.utils import StatisticalAverage  # noqa: F401
+
+    for name in ["init_process_group", "get_rank", "get_world_size", "get_local_rank", "get_local_size", "send", "recv", "broadcast", "broadcast_coalesced",
+                 "broadcast_object", "reduce", "reduce_inplace", "allreduce", "allreduce_inplace", "allreduce_coalesced_inplace", "allgather",
+                 "allgather_inplace", "gather", "gather_inplace", "scatter", "scatter_inplace", "reduce_scatter", "reduce_scatter_inplace", "alltoall",
+                 "alltoall_inplace", "alltoall_v", "alltoall_v_inplace", "barrier", "ReduceOp", "BaguaModule", "DistributedDataParallel"]:
+        assert hasattr(bagua, name), name
+    assert [int(ReduceOp.SUM), int(ReduceOp.PRODUCT), int(ReduceOp.MIN), int(ReduceOp.MAX), int(ReduceOp.BOR), int(ReduceOp.BAND), int(ReduceOp.BXOR),
+            int(ReduceOp.AVG)] == [0, 1, 2, 3, 7, 8, 9, 10]
+    assert set(GlobalAlgorithmRegistry.available_algorithms()) == {"gradient_allreduce", "bytegrad", "decentralized", "low_precision_decentralized", "qadam", "async"}
+    assert isinstance(Algorithm.init("gradient_allreduce", hierarchical=True), gradient_allreduce.GradientAllReduceAlgorithm)
+    for m in ("with_bagua", "bagua_module_name", "bagua_algorithm", "bagua_optimizers", "bagua_buckets"):
+        assert hasattr(torch.nn.Module, m)
+    for m in ("is_bagua_tensor", "ensure_bagua_tensor", "to_bagua_tensor", "bagua_getter_closure", "bagua_setter_closure", "bagua_backend_tensor",
+              "bagua_ensure_grad", "bagua_mark_communication_ready", "bagua_mark_communication_ready_without_synchronization", "bagua_set_storage"):
+        assert hasattr(torch.Tensor, m), m
+
+
+def test_bagua_core_shim():
+    import bagua_core as B
+
+    assert "bagua_b200" in B.show_version()
+    t = torch.arange(8, dtype=torch.float32)
+    bt = B.BaguaTensorPy("t", t)
+    assert bt.num_elements() == 8 and bt.dtype() == "f32" and bt.data_ptr() == t.data_ptr() and bt.device_id() == -1
+    bucket = B.BaguaBucketPy("b", [bt])
+    be = B.BaguaCommBackendPy(10, -1)
+    hits = []
+    bucket.append_python_op(lambda name: hits.append(name))
+    be.register_ordered_buckets([bucket])
+    be.mark_communication_ready(bt, 0)
+    assert be.wait_pending_comm_ops() == 1 and hits == ["b"]
+    c = bt.compress("MinMaxUInt8", 1)
+    out = B.BaguaTensorPy("o", torch.zeros(8))
+    out.decompress_from("MinMaxUInt8", 1, c)
+    assert torch.allclose(out.torch_tensor, t, atol=7 / 255)
+    assert list(c.to_numpy_u8()[32:40]) == [0, 36, 73, 109, 146, 182, 219, 255]
+
+
+def _tensor_bucket_worker(rank, world):
+    import bagua_b200 as bagua
+    from bagua_b200.bucket import BaguaBucket
+
+    bagua.init_process_group()
+    p1, p2 = torch.nn.Parameter(torch.randn(3, 5)), torch.nn.Parameter(torch.randn(7))
+    for p in (p1, p2):
+        p.bagua_ensure_grad()
+    t1 = p1.ensure_bagua_tensor("p1", "m", getter_closure=lambda p: p.grad, setter_closure=lambda p, t: setattr(p, "grad", t))
+    t2 = p2.ensure_bagua_tensor("p2", "m", getter_closure=lambda p: p.grad, setter_closure=lambda p, t: setattr(p, "grad", t))
+    assert t1.is_bagua_tensor() and t1.bagua_tensor_name == "p1" and t1.bagua_getter_closure() is p1.grad
+    with pytest.raises(AssertionError):
+        p1.ensure_bagua_tensor("other", "m")
+    p1.grad.fill_(1.0)
+    p2.grad.fill_(2.0)
+    b = BaguaBucket([t1, t2], "b0", flatten=True, alignment=8)
+    assert b.check_flatten() and b.padding_tensor is not None and b.padding_tensor.numel() == 2 and b.numel() == 24 and b.bytes() == 22 * 4
+    assert torch.equal(b.backend_tensor[:15], torch.ones(15)) and torch.equal(b.backend_tensor[15:22], torch.full((7,), 2.0))
+    assert p1.grad.data_ptr() == b.backend_tensor.data_ptr() and p1.bagua_backend_tensor().data_ptr() == p1.grad.data_ptr()
+    p1.grad.add_(rank)  # writes go through the flat storage
+    ran = []
+    b.append_python_op(lambda name: ran.append(name)).append_centralized_synchronous_op(average=True)
+    be = bagua.communication.get_backend("m")
+    be.register_ordered_buckets([b.backend_bucket])
+    t1.bagua_mark_communication_ready()
+    t2.bagua_mark_communication_ready_without_synchronization()
+    be.wait_pending_comm_ops(0, True)
+    assert ran == ["b0"] and torch.allclose(p1.grad, torch.full((3, 5), 1.0 + (world - 1) / 2)) and torch.equal(p2.grad, torch.full((7,), 2.0))
+    b.clear_ops()
+    assert b.backend_bucket.num_ops() == 0
+    return True
+
+
+def test_tensor_and_bucket_api():
+    assert all(run_distributed(_tensor_bucket_worker, world=2))
+
+
+def _multi_models_worker(rank, world):
+    """Two models with different algorithms in one process (reference: tests/torch_api/test_multi_models.py) —
+    one native scheduler per module name."""
+    import torch.nn.functional as F
+
+    import bagua_b200 as bagua
+    from bagua_b200.parallel.algorithms import bytegrad, gradient_allreduce
+
+    bagua.init_process_group()
+    torch.manual_seed(rank)
+    nets = [torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 2)) for _ in range(2)]
+    opts = [torch.optim.SGD(n.parameters(), lr=0.1) for n in nets]
+    nets[0] = nets[0].with_bagua([opts[0]], gradient_allreduce.GradientAllReduceAlgorithm())
+    nets[1] = nets[1].with_bagua([opts[1]], bytegrad.ByteGradAlgorithm())
+    assert nets[0].bagua_module_name != nets[1].bagua_module_name
+    for it in range(4):
+        for n, o in zip(nets, opts):
+            x = torch.randn(4, 8)
+            o.zero_grad()
+            F.mse_loss(n(x), torch.zeros(4, 2)).backward()
+            o.step()
+    return [torch.cat([p.detach().reshape(-1) for p in n.parameters()]) for n in nets]
+
+
+def test_multiple_models_in_one_process():
+    r0, r1 = run_distributed(_multi_models_worker, world=2)
+    assert torch.equal(r0[0], r1[0])
+    assert torch.allclose(r0[1], r1[1], atol=1e-2)
