@@ -133,7 +133,8 @@ class FusedGradientAllReduceAlgorithmImpl(GradientAllReduceAlgorithmImpl):
             master[: hi - lo].copy_(wflat[lo:hi].float())
         momentum = torch.zeros(vpr * per, dtype=torch.float32, device=flat.device)
         bucket._fused_state = (master, momentum)
-        use_mc = bool(wslice.has_multicast and bucket._slice.has_multicast and eng.choose_variant(nbytes) == "multimem")
+        # NVLS whenever the fabric offers it (the variant validated on 2 and 8 GPUs); peer ld/st two-shot otherwise
+        use_mc = bool(wslice.has_multicast and bucket._slice.has_multicast and eng.has_multicast)
         op = C.AllReduceSgdOp(eng.comm, bucket._slice.buf, wslice.buf, bucket._slice.offset, wslice.offset, nbytes, dtype_code(flat.dtype),
                               master.data_ptr(), momentum.data_ptr(), (1.0 / n) if self.average else 1.0, True, use_mc,
                               eng.launch_cfg("multimem" if use_mc else "two_shot", nbytes))
