@@ -137,7 +137,9 @@ class FusedGradientAllReduceAlgorithmImpl(GradientAllReduceAlgorithmImpl):
         use_mc = bool(wslice.has_multicast and bucket._slice.has_multicast and eng.has_multicast)
         op = C.AllReduceSgdOp(eng.comm, bucket._slice.buf, wslice.buf, bucket._slice.offset, wslice.offset, nbytes, dtype_code(flat.dtype),
                               master.data_ptr(), momentum.data_ptr(), (1.0 / n) if self.average else 1.0, True, use_mc,
-                              eng.launch_cfg("multimem" if use_mc else "two_shot", nbytes))
+                              # 16 CTAs: the configuration measured at 56 994 img/s on 8 GPUs (profiles/bench8_fused.json); the kernel also
+                              # streams the fp32 optimizer shard, so it wants more CTAs than the bare multimem allreduce (8)
+                              eng.launch_cfg("multimem" if use_mc else "two_shot", nbytes, blocks=16 if use_mc else 32))
         bucket.backend_bucket.append_op(op)
         bucket._ops_keepalive.append(op)
         bucket.allreduce_variant = "fused_sgd_multimem" if use_mc else "fused_sgd_two_shot"
