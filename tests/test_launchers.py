@@ -1,0 +1,76 @@
+"""Launchers: flag → environment mapping, static launcher failure propagation, elastic restart-all semantics
+(reference: bagua/distributed/launch.py:157-179,283-300; run.py + torch elastic)."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ENV = dict(os.environ, PYTHONPATH=REPO + os.pathsep + os.environ.get("PYTHONPATH", ""), CUDA_VISIBLE_DEVICES="", BAGUA_FORCE_CPU="1")
+
+
+def _port():
+    from tests.mp_utils import free_port
+
+    return free_port()
+
+
+def test_set_bagua_env_and_parser():
+    from bagua_b200.distributed import launch
+
+    args = launch.parse_args(["--nproc_per_node", "4", "--autotune_level", "1", "--default_bucket_size", "123", "--bagua_service_port", "4242",
+                              "--master_addr", "10.0.0.1", "--report_metrics", "train.py", "--lr", "0.1"])
+    env = {}
+    launch.set_bagua_env(args, env)
+    assert env["BAGUA_DEFAULT_BUCKET_SIZE"] == "123" and env["BAGUA_AUTOTUNE"] == "1" and env["BAGUA_SERVICE_PORT"] == "4242"
+    assert env["AUTO_TUNE_SERVER_ADDR"] == "10.0.0.1:4242" and env["BAGUA_REPORT_METRICS"] == "1"
+    assert args.training_script == "train.py" and args.training_script_args == ["--lr", "0.1"]
+    from bagua_b200.distributed import run
+
+    a = run.parse_args(["--standalone", "--nproc_per_node", "2", "--autotune_level", "0", "x.py"])
+    assert a.standalone and a.autotune_level == 0
+
+
+def test_static_launcher_propagates_failure(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent("""
+        import os, sys, time
+        if os.environ["RANK"] == "1":
+            sys.exit(3)
+        time.sleep(30)
+    """))
+    r = subprocess.run([sys.executable, "-m", "bagua_b200.distributed.launch", "--nproc_per_node=2", f"--master_port={_port()}", str(script)], env=ENV,
+                       capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0  # the surviving worker was terminated long before its 30 s sleep ended
+
+
+def test_elastic_launcher_restarts_all_workers(tmp_path):
+    marker = tmp_path / "attempts"
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys
+        sys.path.insert(0, {REPO!r})
+        import torch, bagua_b200 as bagua
+        bagua.init_process_group()
+        restart = int(os.environ.get("TORCHELASTIC_RESTART_COUNT", "0"))
+        with open({str(marker)!r} + f".{{bagua.get_rank()}}.{{restart}}", "w") as f:
+            f.write("x")
+        t = torch.ones(1)
+        bagua.allreduce_inplace(t)
+        assert t.item() == bagua.get_world_size()
+        if restart == 0 and bagua.get_rank() == 1:
+            sys.exit(7)   # first attempt: one worker dies → torch elastic restarts the whole gang
+        print("DONE", bagua.get_rank(), restart, flush=True)
+    """))
+    r = subprocess.run([sys.executable, "-m", "bagua_b200.distributed.run", "--nnodes=1", "--nproc_per_node=2", "--max_restarts=2", "--rdzv_backend=c10d",
+                        f"--rdzv_endpoint=127.0.0.1:{_port()}", "--rdzv_id=elastic_test", "--monitor_interval=1", str(script)], env=ENV, capture_output=True,
+                       text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
+    files = sorted(os.listdir(tmp_path))
+    # both ranks ran the failed first attempt and one restarted attempt (restart-all semantics)
+    for rank in (0, 1):
+        attempts = sorted(int(f.split(".")[2]) for f in files if f.startswith(f"attempts.{rank}."))
+        assert attempts[0] == 0 and len(attempts) == 2 and attempts[1] > 0, files
+    assert "DONE 0" in r.stdout and "DONE 1" in r.stdout
