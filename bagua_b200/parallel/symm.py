@@ -139,6 +139,9 @@ class PeerEngine:
         self._workspace: Optional[SymmSlice] = None
         self.sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
         logger.info("bagua_b200 PeerEngine: group %s rank %d/%d multicast=%s", group.group_name, self.rank, self.world, self.has_multicast)
+        self.variant_table = None
+        if os.environ.get("BAGUA_PEER_CALIBRATE", "0") == "1":
+            self.calibrate()
 
     # -- allocation ------------------------------------------------------------------------------------------------
     def _new_slab(self, nbytes: int, track: bool = True) -> _Slab:
@@ -159,12 +162,63 @@ class PeerEngine:
         return SymmSlice(slab, off, nbytes, slab.tensor[off : off + nbytes])
 
     # -- policy ------------------------------------------------------------------------------------------------------
+    def calibrate(self, sizes=(64 * 1024, 1024 ** 2, 16 * 1024 ** 2, 128 * 1024 ** 2), iters: int = 10, dtype: torch.dtype = torch.bfloat16):
+        """Measure every allreduce variant (and a few CTA counts) at a handful of message sizes on THIS fabric and keep, per
+        size class, the fastest one — "variant per message size from measured bus bandwidth".  Collective; times are
+        CUDA-event durations reduced with MAX over ranks, so every rank derives the identical table.  Enabled with
+        ``BAGUA_PEER_CALIBRATE=1`` (or called explicitly); the table is also handed to the autotune service as the prior."""
+        C = native()
+        stream = torch.cuda.current_stream()
+        table = []
+        for nbytes in sizes:
+            sl = self.alloc(nbytes)
+            sl.view(dtype).normal_()
+            best = None
+            cands = ([("one_shot", b) for b in (4, 8)] if nbytes <= ONE_SHOT_SLOT else []) + [("two_shot", b) for b in (8, 16, 32)]
+            if self.has_multicast:
+                cands += [("multimem", b) for b in (8, 16)]
+            for variant, blocks in cands:
+                op, chosen = self.make_allreduce_op(sl, sl, nbytes, dtype, True, variant, blocks=blocks)
+                for _ in range(2):
+                    C.run_op(op, stream.cuda_stream, self.device.index)
+                stream.synchronize()
+                dist.barrier(group=self.torch_pg)
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record(stream)
+                for _ in range(iters):
+                    C.run_op(op, stream.cuda_stream, self.device.index)
+                e.record(stream)
+                stream.synchronize()
+                t = torch.tensor([s.elapsed_time(e) / iters], device=self.device)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.torch_pg)
+                ms = float(t.item())
+                busbw = nbytes / ms / 1e6 * 2 * (self.world - 1) / self.world
+                if best is None or ms < best["ms"]:
+                    best = {"bytes": nbytes, "variant": chosen, "blocks": blocks, "ms": ms, "busbw_GBs": busbw}
+            sl.free()
+            table.append(best)
+        self.variant_table = table
+        logger.info("bagua_b200 allreduce calibration: %s", table)
+        return table
+
+    def _from_table(self, nbytes: int):
+        table = getattr(self, "variant_table", None)
+        if not table:
+            return None
+        # nearest calibrated size on a log scale
+        import math
+
+        return min(table, key=lambda r: abs(math.log2(max(nbytes, 1)) - math.log2(r["bytes"])))
+
     def choose_variant(self, nbytes: int, requested: str = "auto") -> str:
         v = requested if requested not in (None, "", "auto") else env.get_allreduce_variant()
         if v in ("one_shot", "two_shot"):
             return v
         if v == "multimem":
             return "multimem" if self.has_multicast else "two_shot"
+        row = self._from_table(nbytes)
+        if row is not None and not (row["variant"] == "one_shot" and nbytes > ONE_SHOT_SLOT):
+            return row["variant"]
         if nbytes <= ONE_SHOT_SLOT // 2:
             return "one_shot"
         # measured (profiles/allreduce_n*.json): with 2 ranks the peer-load two-shot kernel beats the in-switch reduction
@@ -178,6 +232,10 @@ class PeerEngine:
         env_blocks = int(os.environ.get("BAGUA_COMM_BLOCKS", "0"))
         if blocks <= 0:
             blocks = env_blocks
+        if blocks <= 0:
+            row = self._from_table(nbytes)
+            if row is not None and row["variant"] == variant:
+                blocks = row["blocks"]
         if blocks <= 0:
             vecs = max(nbytes // 16, 1)
             if variant == "one_shot":
