@@ -582,7 +582,9 @@ def init_process_group(store=None, rank: int = -1, world_size: int = -1, local_w
         else:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             os.environ.setdefault("MASTER_PORT", "29500")
-            dist.init_process_group(backend=backend, init_method="env://", rank=env.get_rank(), world_size=env.get_world_size(), **kwargs)
+            # rank / world size come from the environment: passing them explicitly makes torch rewrite the env:// URL, which
+            # breaks re-rendezvous of restarted gangs under the elastic launcher (stale store keys → connect refused)
+            dist.init_process_group(backend=backend, **kwargs)
     _rank_mappings = None
     _patch_torch_process_group()
     _default_pg = new_group(stream=_make_stream())
