@@ -187,9 +187,10 @@ class Communicator:
     def allgather(self, send_tensor, recv_tensor):
         n = self.nranks()
         assert recv_tensor.numel() == send_tensor.numel() * n, "allgather: recv must hold nranks * send elements"
-        dist.all_gather_into_tensor(recv_tensor.view(-1), send_tensor.contiguous().view(-1), group=self.pg) if _supports_into_tensor(
-            self.pg, send_tensor
-        ) else _allgather_list(self, send_tensor, recv_tensor)
+        try:
+            dist.all_gather_into_tensor(recv_tensor.view(-1), send_tensor.contiguous().view(-1), group=self.pg)
+        except (RuntimeError, NotImplementedError):  # backends without the flat variant
+            _allgather_list(self, send_tensor, recv_tensor)
 
     def allgather_inplace(self, tensor):
         n = self.nranks()
@@ -276,10 +277,6 @@ class Communicator:
         # the reference's barrier is a 1-element allreduce (communication.py:1396-1398)
         t = torch.zeros(1, device="cuda" if _use_cuda() else "cpu")
         dist.all_reduce(t, group=self.pg)
-
-
-def _supports_into_tensor(pg, tensor) -> bool:
-    return True
 
 
 def _allgather_list(comm: Communicator, send_tensor, recv_tensor):

@@ -6,7 +6,7 @@ element ``r`` of every chunk, so all replicas process similarly expensive sample
 from __future__ import annotations
 
 import math
-from typing import Callable, Iterator, List, Optional
+from typing import Callable, Iterator, Optional
 
 import numpy as np
 import torch

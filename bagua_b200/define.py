@@ -4,7 +4,7 @@
 from __future__ import annotations
 
 import enum
-from typing import List, Optional
+from typing import List
 
 try:  # python ≥ 3.8
     from typing import TypedDict

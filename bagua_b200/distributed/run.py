@@ -12,7 +12,6 @@ semantics are torch elastic's: when a worker fails or membership changes, *all* 
 from __future__ import annotations
 
 import os
-import sys
 from argparse import ArgumentParser
 
 from .launch import add_bagua_arguments, set_bagua_env

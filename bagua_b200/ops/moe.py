@@ -8,8 +8,6 @@ Paths: (1) NVSwitch peer kernels (``csrc/moe_kernels.cu``): rows are stored/load
 The reference does dense one-hot einsums + ``all_to_all_single`` (sharded_moe.py:352-374)."""
 from __future__ import annotations
 
-from typing import Optional
-
 import torch
 import torch.distributed as dist
 

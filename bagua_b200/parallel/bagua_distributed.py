@@ -17,20 +17,17 @@ B200-first changes of the hot path:
 from __future__ import annotations
 
 import collections
-import io
 import logging
-import pickle
 import time
 from types import MethodType
 from typing import Dict, List, Optional, Tuple
 
 import torch
-import torch.distributed as dist
 
 from .. import communication as comm_mod
 from .. import env
 from ..bucket import BaguaBucket, BucketArena, bucket_arena
-from ..core import native, to_bagua_datatype
+from ..core import to_bagua_datatype
 from ..define import BaguaHyperparameter, TensorDeclaration
 from ..utils import StatisticalAverage
 

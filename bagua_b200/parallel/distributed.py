@@ -2,7 +2,7 @@
 from __future__ import annotations
 
 import itertools
-from typing import List, Optional
+from typing import List
 
 import torch
 

@@ -4,8 +4,6 @@ model for a few iterations under the launcher and prints Horovod-style ``Img/sec
 from __future__ import annotations
 
 import argparse
-import os
-import sys
 import time
 
 

@@ -19,7 +19,6 @@ import os
 import statistics
 import subprocess
 import sys
-import time
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 PUBLISHED_PER_GPU = 126.5  # VGG16 img/s per GPU, Bagua + Bagua-Net, 32x V100 (rust/bagua-net/README.md:52-67)
