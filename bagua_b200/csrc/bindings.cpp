@@ -237,6 +237,13 @@ PYBIND11_MODULE(_C, m) {
                                reinterpret_cast<const int32_t*>(b2t), reinterpret_cast<const int32_t*>(b2c), n_tensors, n_blocks, chunk};
               launch_multi_tensor_adam(d, dtype, make_adam(lr, b1, b2, eps, wd, step, adamw), grad_scale, S(stream));
           });
+    m.def("multi_tensor_adam_mp",
+          [](uint64_t ptrs, uint64_t sizes, uint64_t b2t, uint64_t b2c, int n_tensors, int n_blocks, int chunk, int dtype, float lr, float b1,
+             float b2, float eps, float wd, int step, bool adamw, float grad_scale, uint64_t stream) {
+              TensorListDesc d{reinterpret_cast<const uint64_t*>(ptrs), reinterpret_cast<const int64_t*>(sizes),
+                               reinterpret_cast<const int32_t*>(b2t), reinterpret_cast<const int32_t*>(b2c), n_tensors, n_blocks, chunk};
+              launch_multi_tensor_adam_mp(d, dtype, make_adam(lr, b1, b2, eps, wd, step, adamw), grad_scale, S(stream));
+          });
     m.def("qadam_momentum", [](uint64_t m1, uint64_t grad, int gdt, size_t n, float beta1, uint64_t stream) {
         launch_qadam_momentum(reinterpret_cast<float*>(m1), reinterpret_cast<const void*>(grad), gdt, n, beta1, S(stream));
     });

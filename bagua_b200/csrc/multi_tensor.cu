@@ -273,6 +273,38 @@ __global__ void __launch_bounds__(kThreads) multi_tensor_adam_kernel(TensorListD
     }
 }
 
+// Mixed precision: lists = [param(T), grad(T), exp_avg(f32), exp_avg_sq(f32), master(f32)] — low-precision parameters with fp32
+// moments and fp32 master weights (the update happens on the master copy; the parameter receives the rounded result).
+template <typename T>
+__global__ void __launch_bounds__(kThreads) multi_tensor_adam_mp_kernel(TensorListDesc d, AdamParams hp, float grad_scale) {
+    const int t = d.block_to_tensor[blockIdx.x];
+    const size_t off = static_cast<size_t>(d.block_to_chunk[blockIdx.x]) * d.chunk;
+    const size_t n = static_cast<size_t>(d.sizes[t]);
+    const size_t len = (n - off) < static_cast<size_t>(d.chunk) ? (n - off) : static_cast<size_t>(d.chunk);
+    T* p = reinterpret_cast<T*>(d.ptrs[t]) + off;
+    const T* g = reinterpret_cast<const T*>(d.ptrs[d.n_tensors + t]) + off;
+    float* m1 = reinterpret_cast<float*>(d.ptrs[2 * d.n_tensors + t]) + off;
+    float* m2 = reinterpret_cast<float*>(d.ptrs[3 * d.n_tensors + t]) + off;
+    float* mw = reinterpret_cast<float*>(d.ptrs[4 * d.n_tensors + t]) + off;
+    for (size_t i = threadIdx.x; i < len; i += blockDim.x) {
+        float w = mw[i], a = m1[i], b = m2[i];
+        adam_update(w, to_f32<T>(g[i]), a, b, hp, grad_scale);
+        mw[i] = w;
+        m1[i] = a;
+        m2[i] = b;
+        p[i] = from_f32<T>(w);
+    }
+}
+
+void launch_multi_tensor_adam_mp(const TensorListDesc& d, int dtype, const AdamParams& hp, float grad_scale, cudaStream_t stream) {
+    if (d.n_blocks <= 0) return;
+    dispatch_float(dtype, [&](auto tag) {
+        using T = decltype(tag);
+        multi_tensor_adam_mp_kernel<T><<<d.n_blocks, kThreads, 0, stream>>>(d, hp, grad_scale);
+    });
+    check("multi_tensor_adam_mp");
+}
+
 void launch_multi_tensor_sgd(const TensorListDesc& d, int dtype, bool has_momentum, const SgdParams& hp, float grad_scale,
                              cudaStream_t stream) {
     if (d.n_blocks <= 0) return;

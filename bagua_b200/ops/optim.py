@@ -335,21 +335,31 @@ class FusedAdam(_FusedBase):
             for p in params:
                 by_dtype.setdefault(p.dtype, []).append(p)
             for dt, ps in by_dtype.items():
+                # low-precision parameters keep fp32 moments and fp32 master weights (mixed-precision kernel)
+                mixed = self.master_weights and dt in (torch.float16, torch.bfloat16)
                 for p in ps:
                     st = self.state[p]
                     if "exp_avg" not in st:
-                        st["exp_avg"], st["exp_avg_sq"], st["step"] = torch.zeros_like(p.data), torch.zeros_like(p.data), 0
+                        sdt = torch.float32 if mixed else p.dtype
+                        st["exp_avg"] = torch.zeros_like(p.data, dtype=sdt, memory_format=torch.contiguous_format)
+                        st["exp_avg_sq"] = torch.zeros_like(p.data, dtype=sdt, memory_format=torch.contiguous_format)
+                        st["step"] = 0
+                        if mixed:
+                            st["master"] = p.data.detach().float().contiguous()
                     st["step"] += 1
                 step = self.state[ps[0]]["step"]
                 lists = [[p.data for p in ps], [p.grad for p in ps], [self.state[p]["exp_avg"] for p in ps], [self.state[p]["exp_avg_sq"] for p in ps]]
+                if mixed:
+                    lists.append([self.state[p]["master"] for p in ps])
                 key = (gi, dt)
                 plan = self._multi.get(key)
                 sig = tuple(t.data_ptr() for lst in lists for t in lst)
                 if plan is None or plan.signature != sig:
                     plan = _MultiPlan(lists)
                     self._multi[key] = plan
-                C.multi_tensor_adam(*plan.args(), dtype_code(dt), float(lr), float(betas[0]), float(betas[1]), float(eps), float(wd), int(step),
-                                    bool(adamw), float(self.grad_scale), _stream())
+                fn = C.multi_tensor_adam_mp if mixed else C.multi_tensor_adam
+                fn(*plan.args(), dtype_code(dt), float(lr), float(betas[0]), float(betas[1]), float(eps), float(wd), int(step), bool(adamw),
+                   float(self.grad_scale), _stream())
                 self.kernel_launches += 1
         self._grads_zeroed = self.zero_grad_in_step and all(s is not None for s in self._segments.values()) and len(self._segments) == len(self.param_groups)
         return loss
