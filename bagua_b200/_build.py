@@ -117,6 +117,25 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return TARGET
 
 
+NET_DIR = CSRC / "net"
+NET_TARGET = PKG_DIR / "libnccl-net-bagua.so"
+
+
+def build_net_plugin(force: bool = False, verbose: bool = False) -> Path:
+    """Build the NCCL network plugin (multi-stream TCP transport, host code only) as ``libnccl-net-bagua.so``."""
+    srcs = sorted(NET_DIR.glob("*.cpp"))
+    deps = srcs + sorted(NET_DIR.glob("*.h"))
+    if not force and NET_TARGET.exists() and all(NET_TARGET.stat().st_mtime >= d.stat().st_mtime for d in deps):
+        return NET_TARGET
+    cmd = [CXX, "-O2", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-Wall", "-shared", f"-I{NET_DIR}", *map(str, srcs), "-o", str(NET_TARGET), "-lpthread"]
+    if verbose:
+        print("[bagua_b200 build]", " ".join(cmd), flush=True)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"net plugin build failed:\n{res.stdout}\n{res.stderr}")
+    return NET_TARGET
+
+
 def is_built() -> bool:
     return TARGET.exists()
 
@@ -124,3 +143,4 @@ def is_built() -> bool:
 if __name__ == "__main__":
     path = build(force="--force" in sys.argv, verbose=True)
     print(f"built {path}")
+    print(f"built {build_net_plugin(force='--force' in sys.argv, verbose=True)}")

@@ -34,7 +34,7 @@ def add_bagua_arguments(parser: ArgumentParser):
     parser.add_argument("--autotune_warmup_time", type=float, default=30.0)
     parser.add_argument("--default_bucket_size", type=int, default=10 * 1024 ** 2, help="bucket size in bytes before autotune")
     parser.add_argument("--enable_bagua_net", action="store_true", default=False,
-                        help="kept for CLI parity: inside one NVSwitch domain traffic never touches a NIC plugin; multi-node jobs use NCCL's own transport")
+                        help="load the multi-stream TCP NCCL network plugin (libnccl-net-bagua.so) in the workers; only inter-node traffic uses it")
     parser.add_argument("--host_list", type=str, default="", help="(baguarun) comma separated host list")
     parser.add_argument("--ssh_port", type=int, default=22, help="(baguarun) ssh port")
 
@@ -67,6 +67,10 @@ def set_bagua_env(args, env: dict):
     env["BAGUA_AUTOTUNE_WARMUP_TIME_S"] = str(args.autotune_warmup_time)
     if args.autotune_level > 0:
         env["AUTO_TUNE_SERVER_ADDR"] = f"{args.master_addr}:{args.bagua_service_port}"
+    if getattr(args, "enable_bagua_net", False):
+        from ..net import enable as enable_net_plugin
+
+        enable_net_plugin(env)  # NCCL_NET_PLUGIN=bagua + LD_LIBRARY_PATH (reference launch.py:102-107 does the same for libnccl-net.so)
 
 
 def _worker_cmd(args, local_rank: int) -> List[str]:

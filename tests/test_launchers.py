@@ -26,7 +26,10 @@ def test_set_bagua_env_and_parser():
     launch.set_bagua_env(args, env)
     assert env["BAGUA_DEFAULT_BUCKET_SIZE"] == "123" and env["BAGUA_AUTOTUNE"] == "1" and env["BAGUA_SERVICE_PORT"] == "4242"
     assert env["AUTO_TUNE_SERVER_ADDR"] == "10.0.0.1:4242" and env["BAGUA_REPORT_METRICS"] == "1"
-    assert args.training_script == "train.py" and args.training_script_args == ["--lr", "0.1"]
+    assert args.training_script == "train.py" and args.training_script_args == ["--lr", "0.1"] and "NCCL_NET_PLUGIN" not in env
+    args = launch.parse_args(["--enable_bagua_net", "train.py"])
+    launch.set_bagua_env(args, env)
+    assert env["NCCL_NET_PLUGIN"] == "bagua" and os.path.exists(os.path.join(env["LD_LIBRARY_PATH"].split(":")[0], "libnccl-net-bagua.so"))
     from bagua_b200.distributed import run
 
     a = run.parse_args(["--standalone", "--nproc_per_node", "2", "--autotune_level", "0", "x.py"])
