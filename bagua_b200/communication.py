@@ -468,6 +468,8 @@ def new_group(ranks: Optional[Sequence[int]] = None, stream=None) -> BaguaProces
 def from_torch_group(group: dist.ProcessGroup, stream=None) -> BaguaProcessGroup:
     """Wrap an existing ``torch.distributed`` group (reference communication.py:279-309)."""
     global _group_count
+    if not isinstance(group, dist.ProcessGroup):  # torch hands non-members the GroupMember.NON_GROUP_MEMBER sentinel
+        raise ValueError("from_torch_group: this rank is not a member of the given torch.distributed group")
     cached = _pg_map.get(group)
     if cached is not None and (stream is None or cached.stream is stream):
         return cached

@@ -168,6 +168,7 @@ class AsyncModelAverageAlgorithmImpl(AlgorithmImpl):
         """Stop the background averaging on every rank (call after training / before evaluation)."""
         bagua_ddp = _unwrap_ddp(bagua_ddp)
         if self.status in (_AsyncInternalState.SCHEDULED, _AsyncInternalState.STARTED):
+            self._unlock_model(bagua_ddp)  # a forward without backward must not keep the averaging round (and this abort) waiting
             comm_mod.barrier(comm=self.process_group.get_global_communicator())
             if hasattr(bagua_ddp.bagua_buckets[0], "_async_op"):
                 bagua_ddp.bagua_buckets[0]._async_op.abort()

@@ -26,6 +26,7 @@ class AsyncModelAverageOp:
         self.lock = threading.Lock()
         self._abort = False
         self._running = True
+        self._trainer_holds = False
         flat = bucket.backend_tensor
         assert flat is not None, "Async algorithm supports `do_flatten=True` only"
         self.flat = flat
@@ -43,11 +44,18 @@ class AsyncModelAverageOp:
         self._flag = torch.ones(1, dtype=torch.int32, device=dev)
 
     # -- mutex protocol (trainer holds it from forward-pre to post-backward) ---------------------------------------
+    # Only the training thread calls lock_weight / unlock_weight; the comm worker takes ``self.lock`` around the apply.
+    # A forward that is never followed by a backward (evaluation in train mode) leaves the trainer holding the lock;
+    # the next forward must not dead-lock on it, hence the ownership flag instead of a bare acquire.
     def lock_weight(self):
+        if self._trainer_holds:
+            return
         self.lock.acquire()
+        self._trainer_holds = True
 
     def unlock_weight(self):
-        if self.lock.locked():
+        if self._trainer_holds:
+            self._trainer_holds = False
             self.lock.release()
 
     def abort(self):

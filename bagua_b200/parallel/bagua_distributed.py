@@ -29,6 +29,7 @@ from .. import env
 from ..bucket import BaguaBucket, BucketArena, bucket_arena
 from ..core import to_bagua_datatype
 from ..define import BaguaHyperparameter, TensorDeclaration
+from ..tensor import dense_strides
 from ..utils import StatisticalAverage
 
 logger = logging.getLogger(__name__)
@@ -348,6 +349,27 @@ class BaguaDistributedDataParallel:
             self._backward_hook(name, p)
         self._post_backward_hook()
 
+    def _rebuild_for_used_parameters(self):
+        """``find_unused_parameters``: the parameters that took part in this backward differ from the bucketed set, so
+        exactly those are registered again and re-bucketed (the reference re-buckets at the same point,
+        bagua_distributed.py:440-446).  Tensors that drop out get private storage first — the arena they lived in is
+        recycled by ``_reset_buckets``."""
+        old = list(getattr(self, "_bagua_tensors", []))
+        self._bagua_tensors = self.bagua_algorithm.init_tensors(self)
+        keep = set(id(t) for t in self._bagua_tensors)
+        for t in old:
+            if id(t) in keep:
+                continue
+            eff = t.bagua_getter_closure()
+            if eff is None:
+                continue
+            private = torch.empty_strided(eff.shape, dense_strides(eff), dtype=eff.dtype, device=eff.device)
+            private.copy_(eff)
+            t.bagua_set_storage(private.untyped_storage(), 0)
+        self._bagua_tensor_map = {t.bagua_tensor_name: t for t in self._bagua_tensors}
+        self._bagua_autotune_register_tensors()
+        self._reset_buckets()
+
     # ---------------------------------------------------------------------------------------------------------
     # hooks
     # ---------------------------------------------------------------------------------------------------------
@@ -373,6 +395,9 @@ class BaguaDistributedDataParallel:
                     return
                 if ddp.find_unused_parameters:
                     ddp.autograd_graph_params[name] = param
+                    if name not in ddp.params_in_use:  # not bucketed right now: picked up by the post-backward rebuild
+                        queue_post_backward()
+                        return
                 ddp._backward_hook(name, param)
                 queue_post_backward()
 
@@ -391,7 +416,7 @@ class BaguaDistributedDataParallel:
                 t0, _ = getattr(self, "_last_time_pair", (None, None))
                 self._last_time_pair = (t0, time.time())
         if self.find_unused_parameters and set(self.autograd_graph_params.keys()) != self.params_in_use:
-            self._reset_buckets()
+            self._rebuild_for_used_parameters()
             self._delay_allreduce()
 
     def _register_optimizer_hooks(self):

@@ -1,0 +1,228 @@
+"""More of the reference's test scenarios on CPU/gloo: QAdam warm-up math (tests/torch_api/test_qadam.py),
+find_unused_parameters (tests/torch_api/data_parallel/test_bagua_ddp.py), async abort/resume/abort
+(tests/torch_api/test_async_model_average.py:77-86), optimizer-state broadcast for several optimizers
+(tests/torch_api/test_broadcast_state.py), sub-group training (tests/torch_api/test_decentralized.py:406-422),
+process-group bookkeeping (tests/torch_api/test_process_group.py)."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from tests.mp_utils import run_distributed
+
+
+def test_qadam_optimizer_equals_adam_during_warmup():
+    from bagua_b200.parallel.algorithms.q_adam import QAdamOptimizer
+
+    torch.manual_seed(0)
+    a = nn.Sequential(nn.Linear(10, 16), nn.Tanh(), nn.Linear(16, 3))
+    b = nn.Sequential(nn.Linear(10, 16), nn.Tanh(), nn.Linear(16, 3))
+    b.load_state_dict(a.state_dict())
+    oa = QAdamOptimizer(a.parameters(), lr=1e-2, warmup_steps=50, weight_decay=0.01)
+    ob = torch.optim.Adam(b.parameters(), lr=1e-2, weight_decay=0.01)
+    for it in range(20):
+        x = torch.randn(8, 10, generator=torch.Generator().manual_seed(it))
+        for m, o in ((a, oa), (b, ob)):
+            o.zero_grad()
+            m(x).pow(2).mean().backward()
+            o.step()
+    for p, q in zip(a.parameters(), b.parameters()):
+        torch.testing.assert_close(p, q, rtol=1e-5, atol=1e-6)
+
+
+class _Branchy(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.trunk = nn.Linear(8, 8)
+        self.a = nn.Linear(8, 4)
+        self.b = nn.Linear(8, 4)      # only used when use_b
+        self.never = nn.Linear(8, 4)  # never used
+
+    def forward(self, x, use_b=False):
+        h = torch.relu(self.trunk(x))
+        return self.a(h) + (self.b(h) if use_b else 0)
+
+
+def _unused_worker(rank, world):
+    import torch.distributed as dist
+
+    import bagua_b200 as bagua
+    from bagua_b200.parallel.algorithms import gradient_allreduce
+    from bagua_b200.parallel.data_parallel import DistributedDataParallel
+
+    bagua.init_process_group()
+    torch.manual_seed(3)
+    model = _Branchy()
+    ref = _Branchy()
+    ref.load_state_dict(model.state_dict())
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.1)
+    ddp = DistributedDataParallel(model, optimizers=[opt], algorithm=gradient_allreduce.GradientAllReduceAlgorithm(), find_unused_parameters=True)
+    for it in range(6):
+        use_b = it >= 3                                       # the set of parameters in the graph changes mid-training
+        x = torch.randn(4, 8, generator=torch.Generator().manual_seed(10 * it + rank))
+        opt.zero_grad()
+        ddp(x, use_b=use_b).pow(2).mean().backward()
+        opt.step()
+        ropt.zero_grad()
+        ref(x, use_b=use_b).pow(2).mean().backward()
+        for p in ref.parameters():
+            if p.grad is not None:
+                dist.all_reduce(p.grad)
+                p.grad /= world
+        ropt.step()
+    mine = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    want = torch.cat([p.detach().reshape(-1) for p in ref.parameters()])
+    return mine, want
+
+
+def test_find_unused_parameters_rebuckets_and_matches_manual_averaging():
+    res = run_distributed(_unused_worker, world=2)
+    for mine, want in res:
+        torch.testing.assert_close(mine, want, rtol=1e-5, atol=1e-6)
+    assert torch.equal(res[0][0], res[1][0])
+
+
+def _async_worker(rank, world):
+    import bagua_b200 as bagua
+    from bagua_b200.parallel.algorithms import async_model_average
+
+    bagua.init_process_group()
+    torch.manual_seed(rank)
+    model = nn.Sequential(nn.Linear(6, 12), nn.ReLU(), nn.Linear(12, 2))
+    opt = torch.optim.SGD(model.parameters(), lr=0.05)
+    algo = async_model_average.AsyncModelAverageAlgorithm(sync_interval_ms=5, warmup_steps=2)
+    model = model.with_bagua([opt], algo)
+    impl = model.bagua_algorithm
+
+    def epoch(n, seed):
+        for it in range(n):
+            x = torch.randn(4, 6, generator=torch.Generator().manual_seed(seed + it + 100 * rank))
+            opt.zero_grad()
+            model(x).pow(2).mean().backward()
+            opt.step()
+
+    for cycle in range(3):                                   # train / abort / (evaluate) / resume, repeatedly
+        epoch(8, 1000 * cycle)
+        impl.abort(model)
+        impl.abort(model)                                     # a second abort is a no-op, not a hang
+        with torch.no_grad():
+            model(torch.zeros(1, 6))
+        impl.resume(model)
+        impl.resume(model)
+    epoch(5, 9999)
+    impl.abort(model)
+    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    return flat, bool(torch.isfinite(flat).all())
+
+
+def test_async_model_average_repeated_abort_resume():
+    res = run_distributed(_async_worker, world=2, timeout=240)
+    assert all(ok for _, ok in res)
+    # the replicas have been averaged many times: they must be close (not bit-equal — the algorithm is asynchronous)
+    assert (res[0][0] - res[1][0]).abs().max() < 0.5
+
+
+def _broadcast_state_worker(rank, world):
+    import bagua_b200 as bagua
+    from bagua_b200.parallel.algorithms import gradient_allreduce
+
+    bagua.init_process_group()
+    out = {}
+    for name, make in [
+        ("sgd_momentum", lambda ps: torch.optim.SGD(ps, lr=0.1 * (rank + 1), momentum=0.9)),
+        ("adam", lambda ps: torch.optim.Adam(ps, lr=1e-3 * (rank + 1))),
+        ("adamw", lambda ps: torch.optim.AdamW(ps, lr=1e-3 * (rank + 1), weight_decay=0.1 * (rank + 1))),
+        ("rmsprop", lambda ps: torch.optim.RMSprop(ps, lr=1e-3 * (rank + 1), momentum=0.5)),
+        ("adagrad", lambda ps: torch.optim.Adagrad(ps, lr=1e-2 * (rank + 1))),
+    ]:
+        torch.manual_seed(100 + rank)
+        model = nn.Sequential(nn.Linear(5, 7), nn.ReLU(), nn.Linear(7, 3))
+        opt = make(model.parameters())
+        # give every rank a different, non-empty optimizer state before wrapping
+        for it in range(2):
+            opt.zero_grad()
+            model(torch.randn(3, 5)).sum().backward()
+            opt.step()
+        model = model.with_bagua([opt], gradient_allreduce.GradientAllReduceAlgorithm())
+        state = []
+        for g in opt.param_groups:
+            state.append(torch.tensor([float(v) for k, v in sorted(g.items()) if isinstance(v, (int, float)) and not isinstance(v, bool)]))
+            for p in g["params"]:
+                for k, v in sorted(opt.state[p].items()):
+                    if torch.is_tensor(v):
+                        state.append(v.detach().reshape(-1).float())
+        out[name] = (torch.cat([p.detach().reshape(-1) for p in model.parameters()]), torch.cat(state))
+    return out
+
+
+def test_parameters_and_optimizer_state_are_broadcast_for_several_optimizers():
+    res = run_distributed(_broadcast_state_worker, world=2, timeout=240)
+    for name in res[0]:
+        torch.testing.assert_close(res[0][name][0], res[1][name][0], rtol=0, atol=0, msg=name)
+        torch.testing.assert_close(res[0][name][1], res[1][name][1], rtol=0, atol=0, msg=name)
+
+
+def _subgroup_worker(rank, world):
+    import torch.distributed as dist
+
+    import bagua_b200 as bagua
+    from bagua_b200.parallel.algorithms import decentralized, gradient_allreduce
+
+    bagua.init_process_group()
+    group = bagua.new_group(ranks=[0, 1])                     # every rank calls new_group; rank 2 is not a member
+    tg = dist.new_group(ranks=[0, 1])
+    if rank == 2:
+        try:
+            bagua.from_torch_group(tg)
+            raise AssertionError("non-member must be rejected")
+        except ValueError:
+            return None
+    assert bagua.from_torch_group(tg).ranks == [0, 1]
+    torch.manual_seed(rank)
+    outs = []
+    for algo in (gradient_allreduce.GradientAllReduceAlgorithm(), decentralized.DecentralizedAlgorithm(hierarchical=False)):
+        model = nn.Sequential(nn.Linear(4, 4), nn.ReLU(), nn.Linear(4, 2))
+        opt = torch.optim.SGD(model.parameters(), lr=0.1)
+        model = model.with_bagua([opt], algo, process_group=group)
+        for it in range(4):
+            x = torch.randn(4, 4, generator=torch.Generator().manual_seed(it + 7 * rank))
+            opt.zero_grad()
+            model(x).pow(2).mean().backward()
+            opt.step()
+        outs.append(torch.cat([p.detach().reshape(-1) for p in model.parameters()]))
+    return outs
+
+
+def test_training_on_a_sub_group_leaves_outsiders_alone():
+    res = run_distributed(_subgroup_worker, world=3, timeout=240)
+    assert res[2] is None
+    torch.testing.assert_close(res[0][0], res[1][0], rtol=0, atol=0)          # gradient allreduce: bit-identical replicas
+    assert (res[0][1] - res[1][1]).abs().max() < 0.2                          # decentralized: weights pulled together
+
+
+def _pg_worker(rank, world):
+    import gc
+
+    import torch.distributed as dist
+
+    import bagua_b200 as bagua
+    from bagua_b200 import communication as comm
+
+    bagua.init_process_group()
+    g = bagua.new_group(ranks=[0, 1])
+    t = torch.full((4,), float(rank + 1))
+    bagua.allreduce_inplace(t, comm=g.get_global_communicator())
+    tg = dist.new_group(ranks=[0, 1])
+    before = len(comm._torch_to_bagua_pg) if hasattr(comm, "_torch_to_bagua_pg") else None
+    bg = bagua.from_torch_group(tg)
+    same = bagua.from_torch_group(tg) is bg                                    # cached per torch group
+    name = bg.group_name
+    del bg
+    gc.collect()
+    return t, same, name, before
+
+
+def test_process_group_bookkeeping():
+    res = run_distributed(_pg_worker, world=2)
+    for t, same, name, _ in res:
+        assert torch.equal(t, torch.full((4,), 3.0)) and same and isinstance(name, str)
