@@ -166,3 +166,18 @@ def test_stores_and_cache():
         for i in range(20):
             assert cached[i][1] == i % 13
     assert ds.loads == 20 and len(cached) == 20
+
+
+def test_lightning_strategy_is_lazy_and_builds_algorithms():
+    from bagua_b200.contrib import lightning as bl
+    from bagua_b200.parallel.algorithms import bytegrad, gradient_allreduce
+
+    if not bl.lightning_available():
+        with pytest.raises(ImportError):
+            bl.BaguaStrategy(algorithm="gradient_allreduce")
+    assert isinstance(bl._build_algorithm("gradient_allreduce", [], {}), gradient_allreduce.GradientAllReduceAlgorithm)
+    assert isinstance(bl._build_algorithm("bytegrad", [], {"average": False}), bytegrad.ByteGradAlgorithm)
+    with pytest.raises(ValueError):
+        bl._build_algorithm("qadam", [torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=0.1)], {})
+    custom = gradient_allreduce.GradientAllReduceAlgorithm()
+    assert bl._build_algorithm(custom, [], {}) is custom
