@@ -341,11 +341,12 @@ class FusedAdam(_FusedBase):
                     st = self.state[p]
                     if "exp_avg" not in st:
                         sdt = torch.float32 if mixed else p.dtype
-                        st["exp_avg"] = torch.zeros_like(p.data, dtype=sdt, memory_format=torch.contiguous_format)
-                        st["exp_avg_sq"] = torch.zeros_like(p.data, dtype=sdt, memory_format=torch.contiguous_format)
+                        # preserve_format: state shares the parameter's memory order (the kernel walks raw memory)
+                        st["exp_avg"] = torch.zeros_like(p.data, dtype=sdt)
+                        st["exp_avg_sq"] = torch.zeros_like(p.data, dtype=sdt)
                         st["step"] = 0
                         if mixed:
-                            st["master"] = p.data.detach().float().contiguous()
+                            st["master"] = torch.empty_like(p.data, dtype=torch.float32).copy_(p.data)
                     st["step"] += 1
                 step = self.state[ps[0]]["step"]
                 lists = [[p.data for p in ps], [p.grad for p in ps], [self.state[p]["exp_avg"] for p in ps], [self.state[p]["exp_avg_sq"] for p in ps]]
