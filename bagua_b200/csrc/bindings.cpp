@@ -268,6 +268,12 @@ PYBIND11_MODULE(_C, m) {
         launch_grouped_gemm_tn(reinterpret_cast<const void*>(A), reinterpret_cast<const void*>(B), reinterpret_cast<void*>(C),
                                reinterpret_cast<const float*>(bias), G, M, N, K, act, S(stream));
     });
+    m.def("grouped_gemm_tn_push",
+          [](uint64_t A, uint64_t B, uint64_t bias, int G, int N, int K, int act, std::shared_ptr<PeerComm> comm, SymmBuf out, size_t out_off, int cap,
+             uint64_t stream) {
+              launch_grouped_gemm_tn_push(reinterpret_cast<const void*>(A), reinterpret_cast<const void*>(B), reinterpret_cast<const float*>(bias), G, N, K,
+                                          act, comm->ctx(), out.buf, out_off, cap, S(stream));
+          });
     m.def("moe_scatter",
           [](std::shared_ptr<PeerComm> comm, SymmBuf dst, size_t dst_off, uint64_t rows, uint64_t eidx, uint64_t sidx, uint64_t scale, int n_tok, int K,
              int M, int E_local, int C, int dtype, int nblocks, uint64_t stream) {
@@ -277,11 +283,14 @@ PYBIND11_MODULE(_C, m) {
           });
     m.def("moe_gather",
           [](std::shared_ptr<PeerComm> comm, SymmBuf src, size_t src_off, uint64_t out, uint64_t eidx, uint64_t sidx, uint64_t weights, uint64_t picked,
-             int n_tok, int K, int M, int E_local, int C, int dtype, int nblocks, uint64_t stream) {
+             int n_tok, int K, int M, int E_local, int C, int dtype, int nblocks, uint64_t stream, bool local_layout) {
               launch_moe_gather(comm->ctx(), src.buf, src_off, reinterpret_cast<void*>(out), reinterpret_cast<const int64_t*>(eidx),
                                 reinterpret_cast<const int64_t*>(sidx), reinterpret_cast<const float*>(weights), reinterpret_cast<void*>(picked), n_tok, K, M,
-                                E_local, C, dtype, nblocks, S(stream));
-          });
+                                E_local, C, dtype, nblocks, S(stream), local_layout);
+          },
+          py::arg("comm"), py::arg("src"), py::arg("src_off"), py::arg("out"), py::arg("eidx"), py::arg("sidx"), py::arg("weights"), py::arg("picked"),
+          py::arg("n_tok"), py::arg("K"), py::arg("M"), py::arg("E_local"), py::arg("C"), py::arg("dtype"), py::arg("nblocks"), py::arg("stream"),
+          py::arg("local_layout") = false);
     m.def("minmax_uint8_compress",
           [](uint64_t in, size_t numel, int dtype, int n_chunks, int target_chunk, uint64_t out, uint64_t scratch, uint64_t stream) {
               launch_minmax_uint8_compress(reinterpret_cast<const void*>(in), numel, dtype, n_chunks, target_chunk,

@@ -3,13 +3,17 @@
 //   C[g] = act( A[g] · B[g]^T + bias[g] ),   A: [G, M, K]  B: [G, N, K]  (both K-contiguous),  C: [G, M, N]  bf16, fp32 accumulate
 //
 // This is the MoE expert FFN (the one GEMM-shaped hot op of the framework; the reference runs a python loop of cuBLAS
-// linears, bagua/torch_api/model_parallel/moe/experts.py:31-41). One CTA computes one 128x128 output tile:
-//   warp 0      : TMA producer  — cp.async.bulk.tensor (128B-swizzled 128x64 tiles of A and B) into a 4-stage smem ring
-//   warp 1      : MMA issuer    — one elected thread issues tcgen05.mma (M128 N128 K16, kind::f16) per 32-byte K slice,
-//                                  accumulating in TMEM; tcgen05.commit releases smem stages / signals the epilogue
+// linears, bagua/torch_api/model_parallel/moe/experts.py:31-41). Persistent kernel, one CTA per SM walking 128 x BN
+// output tiles (BN = 256, or 128 when N is not a multiple of 256):
+//   warp 0      : TMA producer  — cp.async.bulk.tensor (128B-swizzled 128x64 / BNx64 tiles of A and B) into a 4/6-stage smem ring
+//   warp 1      : MMA issuer    — one elected thread issues tcgen05.mma (M128 N{128,256} K16, kind::f16) per 32-byte K slice,
+//                                  accumulating in one of TWO TMEM accumulators; tcgen05.commit releases smem stages and
+//                                  signals the epilogue, which drains accumulator i while the MMAs fill accumulator i^1
 //   warps 2..5  : epilogue      — tcgen05.ld the fp32 accumulator (32 lanes x 32 columns per instruction), + bias, GELU,
-//                                  convert to bf16, 64-byte stores
-// Synchronisation is mbarrier-only (full/empty per stage + one "accumulator ready"). All waits are bounded: a wedged
+//                                  convert to bf16, 64-byte stores — to local memory, or (PEER variant) straight into the
+//                                  symmetric buffer of the GPU that owns the token (the MoE "combine" all-to-all happens in
+//                                  the epilogue, tile by tile, overlapped with the MMAs of the next tile)
+// Synchronisation is mbarrier-only (full/empty per stage + accumulator full/empty). All waits are bounded: a wedged
 // pipeline traps instead of hanging the GPU.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -140,10 +144,22 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, int tiles_m, int tiles
     return c;
 }
 
-template <int BN>
+// PEER variant: where the epilogue stores go. Rows of A are ordered [source rank][capacity slot]; the tile of rows
+// [m0, m0+128) of expert g belongs to source rank m0 / cap and lands in THAT rank's buffer, laid out
+// [owner rank][expert][slot][N] so the receiver finds "what expert e on rank r produced for my slot c".
+struct GemmPeerOut {
+    char* ptr[kMaxPeers];
+    size_t off;
+    int rank;    // this (owner) rank
+    int cap;     // capacity slots per (source rank, expert); multiple of BM
+    int groups;  // local experts
+};
+
+template <int BN, bool PEER>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     grouped_gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, __nv_bfloat16* __restrict__ C,
-                           const float* __restrict__ bias, int M, int N, int K, int num_tiles, int tiles_m, int tiles_n, int act) {
+                           const float* __restrict__ bias, int M, int N, int K, int num_tiles, int tiles_m, int tiles_n, int act,
+                           const GemmPeerOut peer) {
     using Cfg = GemmCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -220,7 +236,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             const uint32_t acc = local & 1;
             mbar_wait(&sm.acc_full[acc], (local >> 1) & 1);
             tcgen05_fence_after();
-            __nv_bfloat16* crow = C + (static_cast<size_t>(tc.g) * M + (tc.m0 + row)) * N + tc.n0;
+            __nv_bfloat16* crow;
+            if constexpr (PEER) {
+                const int src = tc.m0 / peer.cap, c0 = tc.m0 - src * peer.cap;
+                crow = reinterpret_cast<__nv_bfloat16*>(peer.ptr[src] + peer.off) +
+                       ((static_cast<size_t>(peer.rank) * peer.groups + tc.g) * peer.cap + (c0 + row)) * N + tc.n0;
+            } else {
+                crow = C + (static_cast<size_t>(tc.g) * M + (tc.m0 + row)) * N + tc.n0;
+            }
             const float* brow = bias ? bias + static_cast<size_t>(tc.g) * N + tc.n0 : nullptr;
 #pragma unroll 1
             for (int c = 0; c < BN; c += 32) {
@@ -285,14 +308,15 @@ CUtensorMap make_map(const void* ptr, int G, int rows, int K, int box_rows) {
 bool grouped_gemm_supported(int M, int N, int K) { return M > 0 && N > 0 && K > 0 && M % BM == 0 && N % 128 == 0 && K % BK == 0; }
 
 namespace {
-template <int BN>
-void launch_bn(const void* A, const void* B, void* C, const float* bias, int G, int M, int N, int K, int act, cudaStream_t stream) {
+template <int BN, bool PEER>
+void launch_bn(const void* A, const void* B, void* C, const float* bias, int G, int M, int N, int K, int act, const GemmPeerOut& peer,
+               cudaStream_t stream) {
     const CUtensorMap ta = make_map(A, G, M, K, BM), tb = make_map(B, G, N, K, BN);
     const size_t smem = sizeof(GemmSmem<BN>) + 1024;
     static bool configured = false;
     static int num_sms = 0;
     if (!configured) {
-        BAGUA_CUDA_CHECK(cudaFuncSetAttribute(grouped_gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        BAGUA_CUDA_CHECK(cudaFuncSetAttribute(grouped_gemm_tn_kernel<BN, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         int dev = 0;
         BAGUA_CUDA_CHECK(cudaGetDevice(&dev));
         BAGUA_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -301,7 +325,8 @@ void launch_bn(const void* A, const void* B, void* C, const float* bias, int G, 
     const int tiles_m = M / BM, tiles_n = N / BN;
     const int num_tiles = tiles_m * tiles_n * G;
     const int grid = num_tiles < num_sms ? num_tiles : num_sms;  // persistent: one CTA per SM
-    grouped_gemm_tn_kernel<BN><<<grid, kGemmThreads, smem, stream>>>(ta, tb, static_cast<__nv_bfloat16*>(C), bias, M, N, K, num_tiles, tiles_m, tiles_n, act);
+    grouped_gemm_tn_kernel<BN, PEER><<<grid, kGemmThreads, smem, stream>>>(ta, tb, static_cast<__nv_bfloat16*>(C), bias, M, N, K, num_tiles, tiles_m,
+                                                                            tiles_n, act, peer);
 }
 }  // namespace
 
@@ -309,12 +334,38 @@ void launch_grouped_gemm_tn(const void* A, const void* B, void* C, const float* 
     if (!grouped_gemm_supported(M, N, K)) throw std::runtime_error("bagua: grouped_gemm_tn needs M%128==0, N%128==0, K%64==0");
     if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) & 15u)
         throw std::runtime_error("bagua: grouped_gemm_tn needs 16-byte aligned operands");
+    const GemmPeerOut none{};
     if (N % 256 == 0)
-        launch_bn<256>(A, B, C, bias, G, M, N, K, act, stream);
+        launch_bn<256, false>(A, B, C, bias, G, M, N, K, act, none, stream);
     else
-        launch_bn<128>(A, B, C, bias, G, M, N, K, act, stream);
+        launch_bn<128, false>(A, B, C, bias, G, M, N, K, act, none, stream);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw std::runtime_error(std::string("bagua: launch of grouped_gemm_tn failed: ") + cudaGetErrorString(e));
+    count_launch();
+}
+
+// GEMM whose epilogue IS the MoE combine all-to-all: A [G, world*cap, K] (rows ordered [source rank][slot]), B [G, N, K];
+// the 128-row tiles of source rank s are stored into rank s's symmetric buffer at [this rank][g][slot][N].
+// No cross-GPU synchronisation inside: the consumer kernel (moe_gather, local layout) starts with the peer barrier that
+// makes the pushes of every owner visible, and ends with the one that lets the owners reuse the buffer.
+void launch_grouped_gemm_tn_push(const void* A, const void* B, const float* bias, int G, int N, int K, int act, const PeerCtx& ctx, const PeerBuf& out,
+                                 size_t out_off, int cap, cudaStream_t stream) {
+    const int M = ctx.world * cap;
+    if (!grouped_gemm_supported(M, N, K) || cap % BM != 0) throw std::runtime_error("bagua: grouped_gemm_tn_push needs cap%128==0, N%128==0, K%64==0");
+    if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | out_off) & 15u)
+        throw std::runtime_error("bagua: grouped_gemm_tn_push needs 16-byte aligned operands");
+    GemmPeerOut peer{};
+    for (int p = 0; p < ctx.world; ++p) peer.ptr[p] = out.ptr[p];
+    peer.off = out_off;
+    peer.rank = ctx.rank;
+    peer.cap = cap;
+    peer.groups = G;
+    if (N % 256 == 0)
+        launch_bn<256, true>(A, B, nullptr, bias, G, M, N, K, act, peer, stream);
+    else
+        launch_bn<128, true>(A, B, nullptr, bias, G, M, N, K, act, peer, stream);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw std::runtime_error(std::string("bagua: launch of grouped_gemm_tn_push failed: ") + cudaGetErrorString(e));
     count_launch();
 }
 

@@ -57,6 +57,10 @@ void launch_bias_relu_pool_nhwc_bwd(const void* g, const void* out, const uint8_
 // C[g] = act(A[g]·B[g]^T + bias[g]); A [G,M,K], B [G,N,K], C [G,M,N] bf16 (K-contiguous operands), bias fp32 [G,N] or null; act: 0 none, 1 GELU(tanh)
 bool grouped_gemm_supported(int M, int N, int K);
 void launch_grouped_gemm_tn(const void* A, const void* B, void* C, const float* bias, int G, int M, int N, int K, int act, cudaStream_t stream);
+// Same GEMM with the MoE combine all-to-all as its epilogue: A [G, world*cap, K] with rows ordered [source rank][slot]; the
+// tile rows of source rank s are stored into `out` ON RANK s at [this rank][g][slot][N] (peer stores over NVLink).
+void launch_grouped_gemm_tn_push(const void* A, const void* B, const float* bias, int G, int N, int K, int act, const PeerCtx& ctx, const PeerBuf& out,
+                                 size_t out_off, int cap, cudaStream_t stream);
 
 // ---- MoE expert-parallel token exchange (moe_kernels.cu) ------------------------------------------------
 // Symmetric row buffers have layout [world(src rank), E_local, C, M]. scatter: rows_in[s] → owner's slot (optionally scaled
@@ -66,7 +70,7 @@ void launch_moe_scatter(const PeerCtx& ctx, const PeerBuf& dst, size_t dst_off, 
                         cudaStream_t stream);
 void launch_moe_gather(const PeerCtx& ctx, const PeerBuf& src, size_t src_off, void* out, const int64_t* expert_idx, const int64_t* slot_idx,
                        const float* weights, void* picked, int S, int K, int M, int E_local, int C, int dtype, int nblocks,
-                       cudaStream_t stream);
+                       cudaStream_t stream, bool local_layout = false);  // local_layout: rows were pushed into MY buffer at [owner][e][slot]
 
 // ---- quantised (MinMaxUInt8) collectives (bytegrad_kernels.cu) ------------------------------------------
 // Wire format per chunk (same as the reference, kernels/bagua_kernels.cu:456-501): [min:T][max:T][pad → 32 B][u8 payload, padded → 32 B]

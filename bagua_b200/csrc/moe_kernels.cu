@@ -70,7 +70,7 @@ template <typename T>
 __global__ void __launch_bounds__(kMoeThreads)
     moe_gather_kernel(PeerCtx ctx, PeerBuf src, size_t src_off, T* __restrict__ out, const int64_t* __restrict__ expert_idx,
                       const int64_t* __restrict__ slot_idx, const float* __restrict__ weights, T* __restrict__ picked, int S, int K, int M,
-                      int E_local, int C) {
+                      int E_local, int C, int local_layout) {
     const uint32_t e0 = load_epoch(ctx);
     bool ok = peer_barrier(ctx, e0 + 1);  // every owner's rows are complete (stream order before its kernel) and visible
     const size_t row_bytes = static_cast<size_t>(M) * sizeof(T);
@@ -93,8 +93,12 @@ __global__ void __launch_bounds__(kMoeThreads)
                         const int64_t e = expert_idx[item];
                         const int owner = static_cast<int>(e / E_local);
                         const int el = static_cast<int>(e % E_local);
-                        const size_t srow = (static_cast<size_t>(ctx.rank) * E_local + el) * C + static_cast<size_t>(slot);
-                        raw = ld_peer16(src.ptr[owner] + src_off + srow * row_bytes + v * 16);
+                        // pull layout: the row sits on its owner at [my rank][expert][slot];
+                        // local layout (the owner's GEMM epilogue pushed it here): my buffer at [owner][expert][slot]
+                        const int from = local_layout ? ctx.rank : owner;
+                        const int major = local_layout ? owner : ctx.rank;
+                        const size_t srow = (static_cast<size_t>(major) * E_local + el) * C + static_cast<size_t>(slot);
+                        raw = ld_peer16(src.ptr[from] + src_off + srow * row_bytes + v * 16);
                         const float w = weights ? weights[item] : 1.0f;
                         float f[Vec16<T>::N];
                         Vec16<T>::unpack(raw, f);
@@ -149,12 +153,12 @@ void launch_moe_scatter(const PeerCtx& ctx, const PeerBuf& dst, size_t dst_off, 
 
 void launch_moe_gather(const PeerCtx& ctx, const PeerBuf& src, size_t src_off, void* out, const int64_t* expert_idx, const int64_t* slot_idx,
                        const float* weights, void* picked, int S, int K, int M, int E_local, int C, int dtype, int nblocks,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, bool local_layout) {
     check_shape(M, dtype, nblocks);
     dispatch_float(dtype, [&](auto tag) {
         using T = decltype(tag);
         moe_gather_kernel<T><<<nblocks, kMoeThreads, 0, stream>>>(ctx, src, src_off, static_cast<T*>(out), expert_idx, slot_idx, weights,
-                                                                 static_cast<T*>(picked), S, K, M, E_local, C);
+                                                                 static_cast<T*>(picked), S, K, M, E_local, C, local_layout ? 1 : 0);
     });
     check("moe_gather");
 }

@@ -71,6 +71,32 @@ class MoEPeerContext:
                             dtype_code(owner_rows.dtype), self.blocks, torch.cuda.current_stream().cuda_stream)
         return out, picked
 
+    def linear_push_gather(self, x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], expert_idx, slot_idx, weights: torch.Tensor, S: int,
+                           C: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``combine(linear(x))`` with the all-to-all inside the GEMM: x [E_local, world*C, K] (rows ordered [source rank][slot]),
+        w [E_local, N, K].  The tcgen05 GEMM's epilogue stores every 128-row tile straight into the symmetric buffer of the
+        rank the tokens came from; the local-layout gather (which opens with the peer barrier) then forms
+        out[s] = Σ_k weights[s,k] · row.  Returns (out [S, N], picked [S, k, N])."""
+        E_local, _, Kdim = x.shape
+        N = w.shape[1]
+        K = expert_idx.shape[1]
+        nbytes = self.world * E_local * C * N * x.element_size()
+        buf = self._buf(nbytes, 1)
+        bias32 = bias.float().contiguous() if bias is not None else None
+        stream = torch.cuda.current_stream().cuda_stream
+        native().grouped_gemm_tn_push(x.data_ptr(), w.data_ptr(), bias32.data_ptr() if bias32 is not None else 0, E_local, N, Kdim, 0, self.comm, buf.buf,
+                                      buf.offset, C, stream)
+        out = torch.empty(S, N, dtype=x.dtype, device=x.device)
+        picked = torch.empty(S, K, N, dtype=x.dtype, device=x.device)
+        native().moe_gather(self.comm, buf.buf, buf.offset, out.data_ptr(), expert_idx.data_ptr(), slot_idx.data_ptr(), weights.data_ptr(),
+                            picked.data_ptr(), S, K, N, E_local, C, dtype_code(x.dtype), self.blocks, stream, True)
+        return out, picked
+
+    def fused_combine_supported(self, x: torch.Tensor, N: int, C: int) -> bool:
+        Kdim = x.shape[-1]
+        return (x.is_cuda and x.dtype == torch.bfloat16 and C % 128 == 0 and native().grouped_gemm_supported(self.world * C, N, Kdim)
+                and os.environ.get("BAGUA_MOE_FUSED_COMBINE", "0") == "1")
+
     # -- autograd ------------------------------------------------------------------------------------------------------
     def dispatch(self, tokens, expert_idx, slot_idx, num_experts: int, capacity: int, num_local_experts: int):
         return _Dispatch.apply(tokens, expert_idx.contiguous(), slot_idx.contiguous(), self, num_local_experts, capacity)
@@ -112,6 +138,50 @@ class _Combine(torch.autograd.Function):
         grad_w = (picked.float() * grad_out.float().unsqueeze(1)).sum(-1) * valid
         grad_rows = ctx.pctx.scatter(grad_out, expert_idx, slot_idx, (w32 * valid).contiguous(), ctx.E_local, ctx.C)
         return grad_rows, grad_w.to(ctx.wdtype), None, None, None, None, None
+
+
+class _LinearCombine(torch.autograd.Function):
+    """``combine(grouped_linear(x, w, b))`` with the combine all-to-all fused into the GEMM epilogue (forward).  Backward is
+    the mirror image built from the existing pieces: scatter(grad_out · weight) to the owners, then the two backward GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, weights, expert_idx, slot_idx, pctx: "MoEPeerContext", C: int):
+        S = expert_idx.shape[0]
+        x, w = x.contiguous(), w.contiguous()
+        w32 = weights.float().contiguous()
+        out, picked = pctx.linear_push_gather(x, w, bias, expert_idx, slot_idx, w32, S, C)
+        ctx.pctx, ctx.C, ctx.wdtype, ctx.has_bias = pctx, C, weights.dtype, bias is not None
+        ctx.save_for_backward(x, w, expert_idx, slot_idx, w32, picked)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        from .gemm import grouped_gemm_tn, tcgen05_supported
+
+        x, w, expert_idx, slot_idx, w32, picked = ctx.saved_tensors
+        E_local, rows, Kdim = x.shape
+        N = w.shape[1]
+        grad_out = grad_out.contiguous()
+        valid = (slot_idx >= 0).to(torch.float32)
+        grad_w = (picked.float() * grad_out.float().unsqueeze(1)).sum(-1) * valid
+        gy = ctx.pctx.scatter(grad_out, expert_idx, slot_idx, (w32 * valid).contiguous(), E_local, ctx.C)      # [world, E_local, C, N]
+        gy = gy.permute(1, 0, 2, 3).reshape(E_local, rows, N)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = grouped_gemm_tn(gy, w.transpose(1, 2).contiguous()) if tcgen05_supported(gy, rows, Kdim, N) else torch.bmm(gy, w)
+        if ctx.needs_input_grad[1]:
+            if tcgen05_supported(gy, N, Kdim, rows):
+                gw = grouped_gemm_tn(gy.transpose(1, 2).contiguous(), x.transpose(1, 2).contiguous())
+            else:
+                gw = torch.bmm(gy.transpose(1, 2), x)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = gy.float().sum(dim=1).to(gy.dtype)
+        return gx, gw, gb, grad_w.to(ctx.wdtype), None, None, None, None
+
+
+def linear_combine(x, w, bias, weights, expert_idx, slot_idx, pctx: "MoEPeerContext", capacity: int):
+    """See :class:`_LinearCombine`."""
+    return _LinearCombine.apply(x, w, bias, weights, expert_idx.contiguous(), slot_idx.contiguous(), pctx, capacity)
 
 
 def get_context(group, world: int) -> Optional[MoEPeerContext]:

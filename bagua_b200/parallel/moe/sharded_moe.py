@@ -204,6 +204,10 @@ class MOELayer(torch.nn.Module):
         # [E_total, C, M] rows land on the rank owning the expert: [world(src), E_local, C, M]
         dispatched = moe_ops.dispatch(tokens, g.expert_idx, g.slot_idx, g.num_experts, g.capacity, self.group, self.world_size,
                                       self.num_local_experts)
+        fused = self.experts.fused_combine_context(dispatched, self.group, self.world_size) if hasattr(self.experts, "fused_combine_context") else None
+        if fused is not None:
+            combined = self.experts.forward_combine(dispatched, g.weights.to(x.dtype), g.expert_idx, g.slot_idx, fused)
+            return combined.reshape(x.shape)
         expert_out = self.experts(dispatched)
         combined = moe_ops.combine(expert_out, g.expert_idx, g.slot_idx, g.weights.to(x.dtype), g.num_experts, g.capacity, self.group,
                                    self.world_size, self.num_local_experts)

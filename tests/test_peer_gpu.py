@@ -200,3 +200,53 @@ def _moe_worker(rank, world):
 
 def test_moe_peer_dispatch_combine_matches_all_to_all():
     run_distributed(_moe_worker, world=_ngpu(), use_cuda=True)
+
+
+def _fused_combine_worker(rank, world):
+    """fc2 GEMM with the combine all-to-all in its epilogue vs the two-step path (grouped GEMM, then pull-combine)."""
+    import os
+
+    import torch.distributed as dist
+
+    import bagua_b200 as bagua
+    from bagua_b200.models.gpt2_moe import ExpertMLP
+    from bagua_b200.ops import moe as moe_ops
+    from bagua_b200.ops import moe_peer
+    from bagua_b200.parallel.moe.experts import Experts
+    from bagua_b200.parallel.moe.sharded_moe import top2gating_indices
+
+    bagua.init_process_group()
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(11 + rank)
+    S, M, E_local = 512, 256, 2
+    E = E_local * world
+    logits = torch.randn(S, E, device=dev)
+    g = top2gating_indices(logits, 1.0)
+    C = ((g.capacity + 127) // 128) * 128      # the 128-row GEMM tiles need a capacity that is a multiple of 128
+    slot_idx = g.slot_idx
+    experts = Experts(ExpertMLP(M), E_local).to(dev).to(torch.bfloat16)
+    tokens = (torch.randn(S, M, device=dev) * 0.5).to(torch.bfloat16)
+    res = []
+    for fused in (True, False):
+        os.environ["BAGUA_MOE_FUSED_COMBINE"] = "1" if fused else "0"
+        experts.zero_grad(set_to_none=True)
+        t = tokens.clone().requires_grad_(True)
+        w = g.weights.to(torch.bfloat16).clone().requires_grad_(True)
+        disp = moe_ops.dispatch(t, g.expert_idx, slot_idx, E, C, dist.group.WORLD, world, E_local)
+        pctx = experts.fused_combine_context(disp, dist.group.WORLD, world)
+        assert (pctx is not None) == fused
+        if fused:
+            out = experts.forward_combine(disp, w, g.expert_idx, slot_idx, pctx)
+        else:
+            out = moe_ops.combine(experts(disp), g.expert_idx, slot_idx, w, E, C, dist.group.WORLD, world, E_local)
+        out.float().pow(2).sum().backward()
+        res.append([out.detach().float(), t.grad.float(), w.grad.float()] + [p.grad.float() for p in experts.parameters()])
+    for a, b in zip(*res):
+        torch.testing.assert_close(a, b, rtol=5e-2, atol=5e-2 * max(1.0, b.abs().max().item()))
+    assert moe_peer.get_context(dist.group.WORLD, world).comm.error_code() == 0
+    return True
+
+
+@pytest.mark.skipif(__import__("os").environ.get("BAGUA_EXPERIMENTAL") != "1", reason="fused GEMM+combine kernel is opt-in until validated on hardware")
+def test_moe_fused_gemm_combine_matches_two_step():
+    run_distributed(_fused_combine_worker, world=_ngpu(), use_cuda=True)
