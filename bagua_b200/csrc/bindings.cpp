@@ -181,6 +181,16 @@ PYBIND11_MODULE(_C, m) {
         .def("set_grad_scale", &AllReduceSgdOp::set_grad_scale)
         .def("steps", &AllReduceSgdOp::steps)
         .def("set_steps", &AllReduceSgdOp::set_steps);
+    py::class_<AllReduceAdamOp, CommOp, std::shared_ptr<AllReduceAdamOp>>(m, "AllReduceAdamOp")
+        .def(py::init<std::shared_ptr<PeerComm>, SymmBuf, SymmBuf, size_t, size_t, size_t, int, uint64_t, uint64_t, uint64_t, float, bool, bool,
+                      LaunchCfg>(),
+             py::arg("comm"), py::arg("grads"), py::arg("weights"), py::arg("g_off"), py::arg("w_off"), py::arg("bytes"), py::arg("dtype"),
+             py::arg("master_ptr"), py::arg("exp_avg_ptr"), py::arg("exp_avg_sq_ptr"), py::arg("scale"), py::arg("zero_grads"), py::arg("use_multimem"),
+             py::arg("cfg"))
+        .def("set_hyper", &AllReduceAdamOp::set_hyper)
+        .def("set_grad_scale", &AllReduceAdamOp::set_grad_scale)
+        .def("steps", &AllReduceAdamOp::steps)
+        .def("set_steps", &AllReduceAdamOp::set_steps);
     py::class_<PeerAverageOp, CommOp, std::shared_ptr<PeerAverageOp>>(m, "PeerAverageOp")
         .def(py::init<std::shared_ptr<PeerComm>, SymmBuf, size_t, uint64_t, size_t, int, LaunchCfg>(), py::arg("comm"), py::arg("weights"),
              py::arg("off"), py::arg("out_ptr"), py::arg("bytes"), py::arg("dtype"), py::arg("cfg"))

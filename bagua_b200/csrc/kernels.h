@@ -41,6 +41,10 @@ void launch_allreduce_oneshot(const PeerCtx& ctx, const PeerBuf& staging, size_t
 void launch_allreduce_sgd(const PeerCtx& ctx, const PeerBuf& grads, const PeerBuf& weights, size_t g_off, size_t w_off,
                           size_t bytes, int dtype, float* master, float* momentum, const SgdParams& hp, float scale,
                           bool zero_grads, bool use_multimem, int nblocks, int nthreads, cudaStream_t stream);
+// Adam / AdamW variant (fp32 master + both moments sharded world ways); hp carries the bias corrections of THIS step.
+void launch_allreduce_adam(const PeerCtx& ctx, const PeerBuf& grads, const PeerBuf& weights, size_t g_off, size_t w_off, size_t bytes, int dtype,
+                           float* master, float* exp_avg, float* exp_avg_sq, const AdamParams& hp, float scale, bool zero_grads, bool use_multimem,
+                           int nblocks, int nthreads, cudaStream_t stream);
 void launch_peer_average(const PeerCtx& ctx, const PeerBuf& weights, size_t off, int peer, void* out, size_t bytes, int dtype,
                          int nblocks, int nthreads, cudaStream_t stream);
 void launch_peer_barrier(const PeerCtx& ctx, cudaStream_t stream);

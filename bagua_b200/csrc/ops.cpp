@@ -1,5 +1,7 @@
 #include "ops.h"
 
+#include <cmath>
+
 #include <cuda_runtime.h>
 
 #include <cstring>
@@ -120,6 +122,23 @@ void AllReduceSgdOp::run(Bucket&, StreamHandle stream, int) {
     hp.first_step = steps_ == 0 ? 1 : 0;
     launch_allreduce_sgd(comm_->ctx(), grads_.buf, weights_.buf, g_off_, w_off_, bytes_, dtype_, reinterpret_cast<float*>(master_),
                          reinterpret_cast<float*>(momentum_), hp, scale, zero_grads_, use_mc_, cfg_.nblocks, cfg_.nthreads, S(stream));
+    steps_++;
+}
+
+void AllReduceAdamOp::run(Bucket&, StreamHandle stream, int) {
+    AdamParams hp{};
+    float scale;
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        hp.lr = lr_, hp.beta1 = b1_, hp.beta2 = b2_, hp.eps = eps_, hp.weight_decay = wd_, hp.adamw = adamw_ ? 1 : 0;
+        scale = scale_;
+    }
+    const double t = static_cast<double>(steps_ + 1);
+    hp.bias_correction1 = static_cast<float>(1.0 - std::pow(static_cast<double>(hp.beta1), t));
+    hp.bias_correction2 = static_cast<float>(1.0 - std::pow(static_cast<double>(hp.beta2), t));
+    launch_allreduce_adam(comm_->ctx(), grads_.buf, weights_.buf, g_off_, w_off_, bytes_, dtype_, reinterpret_cast<float*>(master_),
+                          reinterpret_cast<float*>(m1_), reinterpret_cast<float*>(m2_), hp, scale, zero_grads_, use_mc_, cfg_.nblocks, cfg_.nthreads,
+                          S(stream));
     steps_++;
 }
 

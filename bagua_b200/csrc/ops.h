@@ -140,6 +140,41 @@ private:
     std::mutex mu_;
 };
 
+// The Adam / AdamW flavour of the fused bucket op; the step counter (bias correction) advances with every launch.
+class AllReduceAdamOp final : public CommOp {
+public:
+    AllReduceAdamOp(std::shared_ptr<PeerComm> comm, SymmBuf grads, SymmBuf weights, size_t g_off, size_t w_off, size_t bytes, int dtype,
+                    uint64_t master, uint64_t exp_avg, uint64_t exp_avg_sq, float scale, bool zero_grads, bool use_multimem, LaunchCfg cfg)
+        : comm_(std::move(comm)), grads_(grads), weights_(weights), g_off_(g_off), w_off_(w_off), bytes_(bytes), dtype_(dtype),
+          master_(master), m1_(exp_avg), m2_(exp_avg_sq), scale_(scale), zero_grads_(zero_grads), use_mc_(use_multimem), cfg_(cfg) {}
+    const char* kind() const override { return "allreduce_adam"; }
+    void run(Bucket&, StreamHandle stream, int device) override;
+    void set_hyper(float lr, float beta1, float beta2, float eps, float weight_decay, bool adamw) {
+        std::lock_guard<std::mutex> lk(mu_);
+        lr_ = lr, b1_ = beta1, b2_ = beta2, eps_ = eps, wd_ = weight_decay, adamw_ = adamw;
+    }
+    void set_grad_scale(float s) {
+        std::lock_guard<std::mutex> lk(mu_);
+        scale_ = s;
+    }
+    uint64_t steps() const { return steps_; }
+    void set_steps(uint64_t s) { steps_ = s; }
+
+private:
+    std::shared_ptr<PeerComm> comm_;
+    SymmBuf grads_, weights_;
+    size_t g_off_, w_off_, bytes_;
+    int dtype_;
+    uint64_t master_, m1_, m2_;
+    float scale_;
+    bool zero_grads_, use_mc_;
+    LaunchCfg cfg_;
+    float lr_ = 1e-3f, b1_ = 0.9f, b2_ = 0.999f, eps_ = 1e-8f, wd_ = 0.f;
+    bool adamw_ = false;
+    uint64_t steps_ = 0;
+    std::mutex mu_;
+};
+
 // Decentralized SGD, shift_one pairing (peer formula: comm_ops/decentralized_full_precision_synchronous.rs:81-85).
 class PeerAverageOp final : public CommOp {
 public:

@@ -250,6 +250,105 @@ __global__ void __launch_bounds__(512)
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// The same reduce-scatter → optimizer → all-gather kernel with Adam / AdamW on the owned shard (fp32 master weights and
+// both moments sharded P ways). Update rule identical to flat_adam_kernel (multi_tensor.cu) / torch.optim.Adam[W].
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, int P, bool USE_MC>
+__global__ void __launch_bounds__(512)
+    allreduce_adam_kernel(PeerCtx ctx, PeerBuf grads, PeerBuf weights, size_t g_off, size_t w_off, size_t total_vecs, float* master,
+                          float* exp_avg, float* exp_avg_sq, AdamParams hp, float scale, int zero_grads) {
+    const uint32_t e0 = load_epoch(ctx);
+    bool ok = peer_barrier(ctx, e0 + 1);
+    constexpr int N = Vec16<T>::N;
+    const size_t vpr = (total_vecs + P - 1) / P;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (ok) {
+        constexpr int U = USE_MC ? 4 : (P <= 2 ? 4 : (P <= 4 ? 2 : 1));
+        const size_t base = static_cast<size_t>(ctx.rank) * vpr;
+        const size_t limit = (base + vpr < total_vecs ? base + vpr : total_vecs);
+        const float inv_bc1 = 1.f / hp.bias_correction1, inv_sqrt_bc2 = rsqrtf(hp.bias_correction2);
+        for (size_t j0 = base + tid; j0 < limit; j0 += stride * U) {
+            uint4 raw[U][USE_MC ? 1 : P];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const size_t v = j0 + u * stride;
+                if (v < limit) {
+                    if (USE_MC) {
+                        raw[u][0] = multimem_ld_reduce_add<T>(grads.mc + g_off + v * 16);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < (USE_MC ? 1 : P); ++i) raw[u][i] = ld_peer16(grads.ptr[(ctx.rank + i) % P] + g_off + v * 16);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const size_t v = j0 + u * stride;
+                if (v >= limit) continue;
+                const size_t j = v - base;
+                float g[N];
+                Vec16<T>::unpack(raw[u][0], g);
+                if (!USE_MC) {
+#pragma unroll
+                    for (int i = 1; i < (USE_MC ? 1 : P); ++i) {
+                        float f[N];
+                        Vec16<T>::unpack(raw[u][i], f);
+#pragma unroll
+                        for (int k = 0; k < N; ++k) g[k] += f[k];
+                    }
+                }
+                float4* wp = reinterpret_cast<float4*>(master + j * N);
+                float4* ap = reinterpret_cast<float4*>(exp_avg + j * N);
+                float4* bp = reinterpret_cast<float4*>(exp_avg_sq + j * N);
+                float w[N];
+#pragma unroll
+                for (int q = 0; q < N / 4; ++q) {
+                    float4 ww = wp[q], aa = ap[q], bb = bp[q];
+                    float wv[4] = {ww.x, ww.y, ww.z, ww.w}, av[4] = {aa.x, aa.y, aa.z, aa.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float gg = g[4 * q + k] * scale;
+                        if (hp.adamw)
+                            wv[k] *= (1.f - hp.lr * hp.weight_decay);
+                        else
+                            gg += hp.weight_decay * wv[k];
+                        av[k] = hp.beta1 * av[k] + (1.f - hp.beta1) * gg;
+                        bv[k] = hp.beta2 * bv[k] + (1.f - hp.beta2) * gg * gg;
+                        const float denom = sqrtf(bv[k]) * inv_sqrt_bc2 + hp.eps;
+                        wv[k] -= (hp.lr * inv_bc1) * (av[k] / denom);
+                        w[4 * q + k] = wv[k];
+                    }
+                    wp[q] = make_float4(wv[0], wv[1], wv[2], wv[3]);
+                    ap[q] = make_float4(av[0], av[1], av[2], av[3]);
+                    bp[q] = make_float4(bv[0], bv[1], bv[2], bv[3]);
+                }
+                const uint4 out = Vec16<T>::pack(w);
+                if (USE_MC) {
+                    multimem_st16(weights.mc + w_off + v * 16, out);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < P; ++i) st_peer16(weights.ptr[(ctx.rank + i) % P] + w_off + v * 16, out);
+                }
+            }
+        }
+        ok = peer_barrier(ctx, e0 + 2);
+    }
+    if (ok && zero_grads) {
+        char* mine = grads.ptr[ctx.rank] + g_off;
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        for (size_t j = tid; j < vpr; j += stride) {
+#pragma unroll
+            for (int s = 0; s < P; ++s) {
+                const size_t v = static_cast<size_t>(s) * vpr + j;
+                if (v < total_vecs) st_stream16(mine + v * 16, z);
+            }
+        }
+    }
+    store_epoch(ctx, e0 + 2);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Decentralized SGD, shift_one: out = (mine + peer's weights) / 2, the peer's bucket being read straight over
 // NVLink (replaces grouped send/recv + average kernel, comm_ops/decentralized_full_precision_synchronous.rs:81-92).
 // ---------------------------------------------------------------------------------------------------------
@@ -380,6 +479,29 @@ void launch_allreduce_sgd(const PeerCtx& ctx, const PeerBuf& grads, const PeerBu
         });
     });
     check_launch("allreduce_sgd");
+}
+
+void launch_allreduce_adam(const PeerCtx& ctx, const PeerBuf& grads, const PeerBuf& weights, size_t g_off, size_t w_off, size_t bytes, int dtype,
+                           float* master, float* exp_avg, float* exp_avg_sq, const AdamParams& hp, float scale, bool zero_grads, bool use_multimem,
+                           int nblocks, int nthreads, cudaStream_t stream) {
+    if (bytes % 16 || g_off % 16 || w_off % 16) throw std::runtime_error("bagua: allreduce_adam needs 16-byte aligned size/offsets");
+    if (hp.amsgrad) throw std::runtime_error("bagua: allreduce_adam does not implement amsgrad");
+    check_blocks(nblocks);
+    const size_t vecs = bytes / 16;
+    if (vecs == 0) return;
+    dispatch_float(dtype, [&](auto tag) {
+        using T = decltype(tag);
+        dispatch_world(ctx.world, [&](auto pw) {
+            constexpr int P = decltype(pw)::value;
+            if (use_multimem)
+                allreduce_adam_kernel<T, P, true><<<nblocks, nthreads, 0, stream>>>(ctx, grads, weights, g_off, w_off, vecs, master, exp_avg,
+                                                                                  exp_avg_sq, hp, scale, zero_grads ? 1 : 0);
+            else
+                allreduce_adam_kernel<T, P, false><<<nblocks, nthreads, 0, stream>>>(ctx, grads, weights, g_off, w_off, vecs, master, exp_avg,
+                                                                                   exp_avg_sq, hp, scale, zero_grads ? 1 : 0);
+        });
+    });
+    check_launch("allreduce_adam");
 }
 
 void launch_peer_average(const PeerCtx& ctx, const PeerBuf& weights, size_t off, int peer, void* out, size_t bytes, int dtype,

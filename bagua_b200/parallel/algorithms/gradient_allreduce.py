@@ -80,6 +80,38 @@ def make_sharded_fused_sgd(params, lr=1e-3, momentum=0.0, dampening=0.0, weight_
                             master_weights=True, zero_grad_in_step=True)
 
 
+class ShardedFusedAdam(object):
+    """Marker mix-in: see :func:`make_sharded_fused_adam`."""
+
+
+def make_sharded_fused_adam(params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, adamw=False):
+    """Adam / AdamW counterpart of :func:`make_sharded_fused_sgd`: the update of this rank's 1/N shard (fp32 master weights
+    and both moments) runs inside each bucket's reduce-scatter → all-gather kernel (``allreduce_adam_kernel``).  With one
+    process (or without a peer engine) it behaves like :class:`bagua_b200.ops.optim.FusedAdam`."""
+    from ...ops.optim import FusedAdam
+
+    class _ShardedFusedAdam(FusedAdam, ShardedFusedAdam):
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            self._comm_ops = []
+
+        def _sync_hyper(self):
+            g = self.param_groups[0]
+            for op in self._comm_ops:
+                op.set_hyper(float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), bool(g["adamw"]))
+
+        def step(self, closure=None):
+            if not self._comm_ops:
+                return super().step(closure)
+            self._sync_hyper()
+            self._grads_zeroed = True
+            self.kernel_launches += len(self._comm_ops)
+            return None
+
+    return _ShardedFusedAdam(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, adamw=adamw, master_weights=True,
+                             zero_grad_in_step=True)
+
+
 class FusedGradientAllReduceAlgorithmImpl(GradientAllReduceAlgorithmImpl):
     def __init__(self, process_group, optimizer, average: bool = True):
         super().__init__(process_group, hierarchical=False, average=average)
@@ -102,7 +134,8 @@ class FusedGradientAllReduceAlgorithmImpl(GradientAllReduceAlgorithmImpl):
         bucket.clear_ops()
         eng = bucket._engine(self.process_group)
         opt = self.optimizer
-        if eng is None or bucket._slice is None or not isinstance(opt, ShardedFusedSGD):
+        is_adam = isinstance(opt, ShardedFusedAdam)
+        if eng is None or bucket._slice is None or not (isinstance(opt, ShardedFusedSGD) or is_adam):
             return super().init_operations(bagua_ddp, bucket)
         assert len(opt.param_groups) == 1, "the in-kernel optimizer supports a single parameter group"
         C = native()
@@ -132,23 +165,31 @@ class FusedGradientAllReduceAlgorithmImpl(GradientAllReduceAlgorithmImpl):
         if hi > lo:
             master[: hi - lo].copy_(wflat[lo:hi].float())
         momentum = torch.zeros(vpr * per, dtype=torch.float32, device=flat.device)
-        bucket._fused_state = (master, momentum)
         # NVLS whenever the fabric offers it (the variant validated on 2 and 8 GPUs); peer ld/st two-shot otherwise
         use_mc = bool(wslice.has_multicast and bucket._slice.has_multicast and eng.has_multicast)
-        op = C.AllReduceSgdOp(eng.comm, bucket._slice.buf, wslice.buf, bucket._slice.offset, wslice.offset, nbytes, dtype_code(flat.dtype),
-                              master.data_ptr(), momentum.data_ptr(), (1.0 / n) if self.average else 1.0, True, use_mc,
-                              # 16 CTAs: the configuration measured at 56 994 img/s on 8 GPUs (profiles/bench8_fused.json); the kernel also
-                              # streams the fp32 optimizer shard, so it wants more CTAs than the bare multimem allreduce (8)
-                              eng.launch_cfg("multimem" if use_mc else "two_shot", nbytes, blocks=16 if use_mc else 32))
+        # 16 CTAs: the configuration measured at 56 994 img/s on 8 GPUs (profiles/bench8_fused.json); the kernel also streams
+        # the fp32 optimizer shard, so it wants more CTAs than the bare multimem allreduce (8)
+        cfg = eng.launch_cfg("multimem" if use_mc else "two_shot", nbytes, blocks=16 if use_mc else 32)
+        scale = (1.0 / n) if self.average else 1.0
+        if is_adam:
+            second = torch.zeros(vpr * per, dtype=torch.float32, device=flat.device)
+            bucket._fused_state = (master, momentum, second)
+            op = C.AllReduceAdamOp(eng.comm, bucket._slice.buf, wslice.buf, bucket._slice.offset, wslice.offset, nbytes, dtype_code(flat.dtype),
+                                   master.data_ptr(), momentum.data_ptr(), second.data_ptr(), scale, True, use_mc, cfg)
+        else:
+            bucket._fused_state = (master, momentum)
+            op = C.AllReduceSgdOp(eng.comm, bucket._slice.buf, wslice.buf, bucket._slice.offset, wslice.offset, nbytes, dtype_code(flat.dtype),
+                                  master.data_ptr(), momentum.data_ptr(), scale, True, use_mc, cfg)
         bucket.backend_bucket.append_op(op)
         bucket._ops_keepalive.append(op)
-        bucket.allreduce_variant = "fused_sgd_multimem" if use_mc else "fused_sgd_two_shot"
+        bucket.allreduce_variant = ("fused_adam_" if is_adam else "fused_sgd_") + ("multimem" if use_mc else "two_shot")
         opt._comm_ops.append(op)
         opt._sync_hyper()
 
 
 class FusedGradientAllReduceAlgorithm(Algorithm):
-    """Gradient allreduce whose buckets also apply the SGD update (see :func:`make_sharded_fused_sgd`)."""
+    """Gradient allreduce whose buckets also apply the optimizer update (see :func:`make_sharded_fused_sgd` /
+    :func:`make_sharded_fused_adam`)."""
 
     def __init__(self, optimizer, average: bool = True):
         self.optimizer = optimizer

@@ -292,18 +292,22 @@ def test_ddp_wrapper_no_sync_and_state_broadcast():
 
 
 # ---- fused allreduce+SGD algorithm: CPU/gloo fallback (plain allreduce + FusedSGD torch path) -------------------------
-def _fused_fallback_worker(rank, world):
+def _fused_fallback_worker(rank, world, kind="sgd"):
     import torch.distributed as dist
 
     import bagua_b200 as bagua
-    from bagua_b200.parallel.algorithms.gradient_allreduce import FusedGradientAllReduceAlgorithm, make_sharded_fused_sgd
+    from bagua_b200.parallel.algorithms.gradient_allreduce import FusedGradientAllReduceAlgorithm, make_sharded_fused_adam, make_sharded_fused_sgd
 
     bagua.init_process_group()
     torch.manual_seed(3)
     model = _net()
     oracle = copy.deepcopy(model)
-    opt = make_sharded_fused_sgd(model.parameters(), lr=0.05, momentum=0.9)
-    oopt = torch.optim.SGD(oracle.parameters(), lr=0.05, momentum=0.9)
+    if kind == "sgd":
+        opt = make_sharded_fused_sgd(model.parameters(), lr=0.05, momentum=0.9)
+        oopt = torch.optim.SGD(oracle.parameters(), lr=0.05, momentum=0.9)
+    else:
+        opt = make_sharded_fused_adam(model.parameters(), lr=1e-2, weight_decay=0.01, adamw=True)
+        oopt = torch.optim.AdamW(oracle.parameters(), lr=1e-2, weight_decay=0.01)
     model = model.with_bagua([opt], FusedGradientAllReduceAlgorithm(opt))
 
     def avg(_it):
@@ -316,6 +320,7 @@ def _fused_fallback_worker(rank, world):
     return _flat(model), _flat(oracle)
 
 
-def test_fused_allreduce_sgd_cpu_fallback():
-    for mine, oracle in run_distributed(_fused_fallback_worker, world=2):
+@pytest.mark.parametrize("kind", ["sgd", "adam"])
+def test_fused_allreduce_sgd_cpu_fallback(kind):
+    for mine, oracle in run_distributed(_fused_fallback_worker, world=2, args=(kind,)):
         torch.testing.assert_close(mine, oracle, rtol=1e-5, atol=1e-6)

@@ -250,3 +250,46 @@ def _fused_combine_worker(rank, world):
 @pytest.mark.skipif(__import__("os").environ.get("BAGUA_EXPERIMENTAL") != "1", reason="fused GEMM+combine kernel is opt-in until validated on hardware")
 def test_moe_fused_gemm_combine_matches_two_step():
     run_distributed(_fused_combine_worker, world=_ngpu(), use_cuda=True)
+
+
+def _fused_adam_worker(rank, world):
+    """reduce-scatter → AdamW on the shard → all-gather in one kernel per bucket vs torch.optim.AdamW on averaged gradients."""
+    import copy
+
+    import torch.distributed as dist
+
+    import bagua_b200 as bagua
+    from bagua_b200.parallel.algorithms.gradient_allreduce import FusedGradientAllReduceAlgorithm, make_sharded_fused_adam
+
+    bagua.init_process_group()
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(7)
+    model = torch.nn.Sequential(torch.nn.Linear(256, 512), torch.nn.GELU(), torch.nn.Linear(512, 512), torch.nn.GELU(), torch.nn.Linear(512, 64)).to(dev)
+    oracle = copy.deepcopy(model)
+    opt = make_sharded_fused_adam(model.parameters(), lr=1e-3, weight_decay=0.01, adamw=True)
+    oopt = torch.optim.AdamW(oracle.parameters(), lr=1e-3, weight_decay=0.01)
+    model = model.with_bagua([opt], FusedGradientAllReduceAlgorithm(opt))
+    assert all(b.allreduce_variant.startswith("fused_adam") for b in model.bagua_buckets)
+    for it in range(5):
+        x = torch.randn(32, 256, device=dev, generator=torch.Generator(device=dev).manual_seed(100 * it + rank))
+        opt.zero_grad()
+        model(x).pow(2).mean().backward()
+        opt.step()
+        oopt.zero_grad()
+        oracle(x).pow(2).mean().backward()
+        for p in oracle.parameters():
+            dist.all_reduce(p.grad)
+            p.grad /= world
+        oopt.step()
+    torch.cuda.synchronize()
+    mine = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    want = torch.cat([p.detach().reshape(-1) for p in oracle.parameters()])
+    torch.testing.assert_close(mine, want, rtol=1e-4, atol=1e-5)
+    return mine
+
+
+@pytest.mark.skipif(__import__("os").environ.get("BAGUA_EXPERIMENTAL") != "1", reason="fused allreduce+Adam kernel is opt-in until validated on hardware")
+def test_fused_allreduce_adam_matches_adamw():
+    res = run_distributed(_fused_adam_worker, world=_ngpu(), use_cuda=True)
+    for r in res[1:]:
+        assert torch.equal(res[0], r)
