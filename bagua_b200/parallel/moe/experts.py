@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import copy
+import os
 
 import torch
 
@@ -75,7 +76,7 @@ class Experts(torch.nn.Module):
 
     def forward(self, inputs: torch.Tensor) -> torch.Tensor:
         """``inputs``: ``[world, num_local_experts, capacity, model]``; expert ``i`` processes ``inputs[:, i]``."""
-        if inputs.is_cuda and inputs.dtype == torch.bfloat16 and self._grouped_mlp():
+        if inputs.is_cuda and inputs.dtype == torch.bfloat16 and self._grouped_mlp() and os.environ.get("BAGUA_DISABLE_GROUPED_GEMM") != "1":
             return self._forward_grouped(inputs)
         outs = []
         for chunk, expert in zip(inputs.chunk(self.num_local_experts, dim=1), self.bagua_experts):

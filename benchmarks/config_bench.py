@@ -24,7 +24,12 @@ p.add_argument("--warmup", type=int, default=5)
 p.add_argument("--batch-size", type=int, default=0)
 p.add_argument("--tiny", action="store_true", help="shrunken models for CPU smoke tests")
 p.add_argument("--cpu", action="store_true")
+p.add_argument("--arm", choices=["peer", "nccl"], default="peer", help="nccl = same schedule on NCCL collectives / cuBLAS experts only (baseline arm)")
 args = p.parse_args()
+if args.arm == "nccl":
+    os.environ["BAGUA_ALLREDUCE_VARIANT"] = "nccl"
+    os.environ["BAGUA_MOE_PEER"] = "0"
+    os.environ["BAGUA_DISABLE_GROUPED_GEMM"] = "1"
 
 import bagua_b200 as bagua  # noqa: E402
 from bagua_b200 import models  # noqa: E402
@@ -137,7 +142,7 @@ if cfg == "resnet50_async":
 finite = bool(torch.isfinite(loss.detach().float()).item())
 if rank == 0:
     print(json.dumps({
-        "config": cfg, "n_gpus": world, "value": per_step * world * args.steps / (ms.item() / 1e3), "unit": unit, "ms_per_step": ms.item() / args.steps,
+        "config": cfg, "arm": args.arm, "moe_fused_combine": os.environ.get("BAGUA_MOE_FUSED_COMBINE", "0"), "n_gpus": world, "value": per_step * world * args.steps / (ms.item() / 1e3), "unit": unit, "ms_per_step": ms.item() / args.steps,
         "per_gpu_batch": bs, "dtype": str(dtype), "loss_finite": finite,
         "arm": "nccl-only" if os.environ.get("BAGUA_ALLREDUCE_VARIANT") == "nccl" else "peer-kernels",
         "moe_peer": os.environ.get("BAGUA_MOE_PEER", "1"),

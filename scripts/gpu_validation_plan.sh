@@ -1,0 +1,38 @@
+#!/usr/bin/env bash
+# The GPU work that is queued behind the CPU-only development of round 1, in the order it should be spent
+# (each block is one gpurun call; budgets in GPU-minutes = wall minutes x GPUs).
+#
+#   1 GPU  (~12 min):  gpurun --timeout 900  -- 'bash scripts/gpu_validation_plan.sh one'
+#   2 GPUs (~2x10 min): gpurun --gpus 2 --timeout 900 -- 'bash scripts/gpu_validation_plan.sh two'
+#   8 GPUs (~8x6 min):  gpurun --gpus 8 --timeout 600 -- 'bash scripts/gpu_validation_plan.sh eight'
+set -uo pipefail
+mkdir -p gpurun_out
+case "${1:-one}" in
+one)
+  timeout 600 python -m pytest tests -m "gpu and not multigpu" -x -q > gpurun_out/pytest_gpu_1.log 2>&1; echo "pytest1 exit=$?" | tee gpurun_out/plan_one.txt
+  timeout 600 bash scripts/ncu_profile.sh; echo "ncu exit=$?" | tee -a gpurun_out/plan_one.txt
+  timeout 120 python bench.py --steps 30 --warmup 5 > gpurun_out/bench1.json 2> gpurun_out/bench1.err; echo "bench exit=$?" | tee -a gpurun_out/plan_one.txt
+  ;;
+two)
+  # opt-in kernels written without hardware access in round 1: fused GEMM+combine, fused allreduce+Adam, mixed-precision Adam
+  BAGUA_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_peer_gpu.py -x -q -k "fused" > gpurun_out/pytest_experimental_2.log 2>&1
+  echo "experimental exit=$?" | tee gpurun_out/plan_two.txt
+  timeout 400 python -m pytest tests/test_peer_gpu.py -x -q > gpurun_out/pytest_peer_2.log 2>&1; echo "peer exit=$?" | tee -a gpurun_out/plan_two.txt
+  for fused in 0 1; do
+    BAGUA_MOE_FUSED_COMBINE=$fused timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $((29610 + fused)) \
+      benchmarks/config_bench.py --config gpt2_moe --steps 10 --warmup 3 >> gpurun_out/config_bench_n2.jsonl 2>> gpurun_out/config_bench_n2.err
+    echo "gpt2_moe fused=$fused exit=$?" | tee -a gpurun_out/plan_two.txt
+  done
+  ;;
+eight)
+  port=29700
+  for cfg in gpt2_moe bert_bytegrad resnet50_decentralized; do
+    for arm in peer nccl; do
+      port=$((port + 1))
+      timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port $port \
+        benchmarks/config_bench.py --config $cfg --arm $arm --steps 10 --warmup 3 >> gpurun_out/config_bench_n8.jsonl 2>> gpurun_out/config_bench_n8.err
+      echo "$cfg $arm exit=$?" | tee -a gpurun_out/plan_eight.txt
+    done
+  done
+  ;;
+esac
