@@ -19,6 +19,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
@@ -275,6 +276,191 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
 }
 
+// =====================================================================================================================
+// 2-CTA variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256 tile. CTA r holds rows
+// [m0 + 128 r, +128) of A and rows [n0 + 128 r, +128) of B in its shared memory; ONE thread of the leader CTA issues
+// tcgen05.mma.cta_group::2 (M256 N256 K16) which reads A from "its own" SM and both halves of B from both SMs, so each
+// SM stages only half of B per K block (32 KB per stage instead of 48 KB → 6 stages) and the tensor pipes of both SMs are
+// driven by a single instruction stream. Accumulators: 128 lanes x 256 columns in each CTA's TMEM, double buffered.
+//   full[s]      (leader's)  : 2 arrivals (leader's arrive.expect_tx + peer's remote arrive) + bytes of all four TMA loads
+//   empty[s]     (both CTAs) : multicast tcgen05.commit from the leader's MMA thread
+//   acc_full[a]  (both CTAs) : multicast tcgen05.commit
+//   acc_empty[a] (leader's)  : 8 arrivals, one per epilogue warp of the pair (the peer's arrive remotely)
+// Opt-in (BAGUA_GEMM_2CTA=1): written without hardware access, numerics test gated by BAGUA_EXPERIMENTAL=1.
+// =====================================================================================================================
+constexpr int BN2 = 256;
+constexpr int kStages2 = 6;
+constexpr uint32_t kStageBytesB2 = (BN2 / 2) * BK * 2;
+
+struct __align__(1024) GemmSmem2 {
+    uint8_t a[kStages2][kStageBytesA];
+    uint8_t b[kStages2][kStageBytesB2];
+    uint64_t full[kStages2];
+    uint64_t empty[kStages2];
+    uint64_t acc_full[2];
+    uint64_t acc_empty[2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared::cta pointer of this CTA) as seen in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
+    uint32_t out;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(smem_u32(p)), "r"(rank));
+    return out;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_2sm(uint64_t* bar) {
+    const uint16_t mask = 0b11;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+    grouped_gemm_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, __nv_bfloat16* __restrict__ C,
+                                const float* __restrict__ bias, int M, int N, int K, int num_tiles, int tiles_m, int tiles_n, int act) {
+    extern __shared__ uint8_t smem_raw[];
+    GemmSmem2& sm = *reinterpret_cast<GemmSmem2*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb = K / BK;
+    const uint32_t cta = cluster_ctarank();
+    const bool leader = cta == 0;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    constexpr int TM = 2 * BM;  // rows per cluster tile
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_b)) : "memory");
+        for (int s = 0; s < kStages2; ++s) {
+            mbar_init(&sm.full[s], 2);
+            mbar_init(&sm.empty[s], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&sm.acc_full[i], 1);
+            mbar_init(&sm.acc_empty[i], 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // the same warp of both CTAs allocates (and later frees) the pair's TMEM columns
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(2 * BN2) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();  // barrier inits and TMEM base visible to both CTAs
+    tcgen05_fence_after();
+    const uint32_t tmem_base = sm.tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer (both CTAs: own half of A, own half of B; bytes are credited to the leader's barrier) =====
+            uint32_t it = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                const int m0 = (tile % tiles_m) * TM;
+                const int r = tile / tiles_m;
+                const int n0 = (r % tiles_n) * BN2, g = r / tiles_n;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % kStages2;
+                    mbar_wait(&sm.empty[s], ((it / kStages2) & 1) ^ 1);
+                    const uint32_t lead_full = mapa_u32(&sm.full[s], 0);
+                    if (leader)
+                        mbar_expect_tx(&sm.full[s], 2 * (kStageBytesA + kStageBytesB2));
+                    else
+                        mbar_arrive_cluster(lead_full);
+                    tma_load_3d_2sm(sm.a[s], &tm_a, lead_full, kb * BK, m0 + static_cast<int>(cta) * BM, g);
+                    tma_load_3d_2sm(sm.b[s], &tm_b, lead_full, kb * BK, n0 + static_cast<int>(cta) * (BN2 / 2), g);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {  // ===== MMA issuer: one thread for both SMs =====
+            // instruction descriptor as in the 1-CTA kernel with M = 256
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN2 >> 3) << 17) | (static_cast<uint32_t>(TM >> 4) << 24);
+            uint32_t it = 0, local = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
+                const uint32_t acc = local & 1;
+                mbar_wait(&sm.acc_empty[acc], ((local >> 1) & 1) ^ 1);  // all 8 epilogue warps of the pair have drained it
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN2;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % kStages2;
+                    mbar_wait(&sm.full[s], (it / kStages2) & 1);
+                    tcgen05_fence_after();
+                    const uint64_t da = make_smem_desc(smem_u32(sm.a[s])), db = make_smem_desc(smem_u32(sm.b[s]));
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_bf16_2sm(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                    tcgen05_commit_2sm(&sm.empty[s]);  // frees stage s in BOTH CTAs
+                }
+                tcgen05_commit_2sm(&sm.acc_full[acc]);  // wakes the epilogue warps of BOTH CTAs
+            }
+        }
+    } else {  // ===== epilogue warps 2..5 of each CTA: its own 128 rows =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        uint32_t local = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
+            const int m0 = (tile % tiles_m) * TM + static_cast<int>(cta) * BM;
+            const int r = tile / tiles_m;
+            const int n0 = (r % tiles_n) * BN2, g = r / tiles_n;
+            const uint32_t acc = local & 1;
+            mbar_wait(&sm.acc_full[acc], (local >> 1) & 1);
+            tcgen05_fence_after();
+            __nv_bfloat16* crow = C + (static_cast<size_t>(g) * M + (m0 + row)) * N + n0;
+            const float* brow = bias ? bias + static_cast<size_t>(g) * N + n0 : nullptr;
+#pragma unroll 1
+            for (int c = 0; c < BN2; c += 32) {
+                uint32_t rr[32];
+                tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN2 + static_cast<uint32_t>(c), rr);
+                uint32_t packed[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float v0 = __uint_as_float(rr[2 * j]), v1 = __uint_as_float(rr[2 * j + 1]);
+                    if (brow) v0 += __ldg(brow + c + 2 * j), v1 += __ldg(brow + c + 2 * j + 1);
+                    if (act == 1) v0 = gelu_tanh(v0), v1 = gelu_tanh(v1);
+                    __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+                    packed[j] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(crow + c);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(&sm.acc_empty[acc], 0));  // the MMA thread waits on the LEADER's barrier
+        }
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();  // neither CTA may free TMEM / exit while its partner still reads operands or accumulators
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN2) : "memory");
+    }
+}
+
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
@@ -330,12 +516,43 @@ void launch_bn(const void* A, const void* B, void* C, const float* bias, int G, 
 }
 }  // namespace
 
+namespace {
+bool use_2cta(int M, int N) {
+    static const bool enabled = [] {
+        const char* v = getenv("BAGUA_GEMM_2CTA");
+        return v && v[0] == '1';
+    }();
+    return enabled && M % 256 == 0 && N % 256 == 0;
+}
+
+void launch_2cta(const void* A, const void* B, void* C, const float* bias, int G, int M, int N, int K, int act, cudaStream_t stream) {
+    const CUtensorMap ta = make_map(A, G, M, K, BM), tb = make_map(B, G, N, K, BN2 / 2);
+    const size_t smem = sizeof(GemmSmem2) + 1024;
+    static bool configured = false;
+    static int num_sms = 0;
+    if (!configured) {
+        BAGUA_CUDA_CHECK(cudaFuncSetAttribute(grouped_gemm_tn_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        int dev = 0;
+        BAGUA_CUDA_CHECK(cudaGetDevice(&dev));
+        BAGUA_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        configured = true;
+    }
+    const int tiles_m = M / (2 * BM), tiles_n = N / BN2;
+    const int num_tiles = tiles_m * tiles_n * G;
+    const int clusters = num_tiles < num_sms / 2 ? num_tiles : num_sms / 2;  // persistent: one CTA pair per TPC
+    grouped_gemm_tn_2cta_kernel<<<2 * clusters, kGemmThreads, smem, stream>>>(ta, tb, static_cast<__nv_bfloat16*>(C), bias, M, N, K, num_tiles, tiles_m,
+                                                                              tiles_n, act);
+}
+}  // namespace
+
 void launch_grouped_gemm_tn(const void* A, const void* B, void* C, const float* bias, int G, int M, int N, int K, int act, cudaStream_t stream) {
     if (!grouped_gemm_supported(M, N, K)) throw std::runtime_error("bagua: grouped_gemm_tn needs M%128==0, N%128==0, K%64==0");
     if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) & 15u)
         throw std::runtime_error("bagua: grouped_gemm_tn needs 16-byte aligned operands");
     const GemmPeerOut none{};
-    if (N % 256 == 0)
+    if (use_2cta(M, N))
+        launch_2cta(A, B, C, bias, G, M, N, K, act, stream);
+    else if (N % 256 == 0)
         launch_bn<256, false>(A, B, C, bias, G, M, N, K, act, none, stream);
     else
         launch_bn<128, false>(A, B, C, bias, G, M, N, K, act, none, stream);

@@ -30,3 +30,31 @@ def test_fused_adam_mixed_precision_multi_tensor(dev):
         assert opt.state[p]["exp_avg"].dtype == torch.float32 and "master" in opt.state[p]
         torch.testing.assert_close(opt.state[p]["master"], r.data, rtol=1e-4, atol=1e-5)   # fp32 trajectory is preserved
         torch.testing.assert_close(p.data.float(), r.data, rtol=0, atol=8e-3)              # parameter = rounded master
+
+
+@pytest.mark.skipif(__import__("os").environ.get("BAGUA_EXPERIMENTAL") != "1", reason="2-CTA tcgen05 GEMM is opt-in until validated on hardware")
+def test_tcgen05_2cta_gemm_matches_fp32_reference():
+    """cta_group::2 variant (BAGUA_GEMM_2CTA=1 is read once per process → separate interpreter, bounded by a timeout)."""
+    import os
+    import subprocess
+    import sys
+
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from bagua_b200.ops.gemm import grouped_gemm_tn
+torch.manual_seed(0)
+for G, M, N, K in [(1, 256, 256, 64), (1, 512, 512, 1024), (2, 1024, 512, 512), (1, 8192, 4096, 1024)]:
+    a = (torch.randn(G, M, K, device="cuda") * 0.5).bfloat16()
+    b = (torch.randn(G, N, K, device="cuda") * 0.5).bfloat16()
+    bias = torch.randn(G, N, device="cuda")
+    out = grouped_gemm_tn(a, b, bias).float()
+    ref = torch.bmm(a.float(), b.float().transpose(1, 2)) + bias.unsqueeze(1)
+    err = (out - ref).abs().max().item()
+    assert err <= 2e-2 * max(1.0, ref.abs().max().item()), (G, M, N, K, err)
+torch.cuda.synchronize()
+print("2CTA_OK")
+''' % repo
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, BAGUA_GEMM_2CTA="1"), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "2CTA_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
