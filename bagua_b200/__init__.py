@@ -47,6 +47,7 @@ from .parallel import algorithms  # noqa: F401
 from .parallel import data_parallel  # noqa: F401
 from .parallel.data_parallel import DistributedDataParallel  # noqa: F401
 from . import contrib  # noqa: F401
+from . import ops  # noqa: F401
 from . import checkpoint  # noqa: F401
 from .parallel import moe  # noqa: F401
 
