@@ -123,6 +123,19 @@ PYBIND11_MODULE(_C, m) {
         .def("set_watchdog_fatal", &Backend::set_watchdog_fatal)
         .def("watchdog_error", &Backend::watchdog_error)
         .def("set_record_spans", &Backend::set_record_spans)
+        .def("set_profile", &Backend::set_profile)
+        .def("bucket_stats",
+             [](Backend& b, bool reset) {
+                 py::list out;
+                 for (auto& s : b.bucket_stats(reset)) {
+                     py::dict d;
+                     d["name"] = s.name, d["ops"] = s.ops, d["bytes"] = s.bytes, d["count"] = s.count, d["total_ms"] = s.total_ms, d["max_ms"] = s.max_ms,
+                     d["queue_ms"] = s.queue_ms;
+                     out.append(d);
+                 }
+                 return out;
+             },
+             py::arg("reset") = false)
         .def("pop_ready_spans",
              [](Backend& b) {
                  py::list out;

@@ -93,6 +93,14 @@ void Backend::shutdown() {
         std::lock_guard<std::mutex> lk(pool_mu_);
         for (auto e : event_pool_) cudaEventDestroy(E(e));
         event_pool_.clear();
+        std::lock_guard<std::mutex> plk(prof_mu_);
+        for (auto e : timing_pool_) cudaEventDestroy(E(e));
+        timing_pool_.clear();
+        for (auto& smp : prof_pending_) {
+            if (smp.start) cudaEventDestroy(E(smp.start));
+            if (smp.stop) cudaEventDestroy(E(smp.stop));
+        }
+        prof_pending_.clear();
     }
 }
 
@@ -110,6 +118,59 @@ EventHandle Backend::acquire_event() {
     return reinterpret_cast<EventHandle>(e);
 }
 
+EventHandle Backend::acquire_timing_event() {
+    {
+        std::lock_guard<std::mutex> lk(prof_mu_);
+        if (!timing_pool_.empty()) {
+            auto e = timing_pool_.back();
+            timing_pool_.pop_back();
+            return e;
+        }
+    }
+    cudaEvent_t e;
+    BAGUA_CUDA_CHECK(cudaEventCreate(&e));
+    return reinterpret_cast<EventHandle>(e);
+}
+
+std::vector<BucketStat> Backend::bucket_stats(bool reset) {
+    std::lock_guard<std::mutex> lk(prof_mu_);
+    while (!prof_pending_.empty()) {
+        ProfSample& smp = prof_pending_.front();
+        double ms = smp.host_ms;
+        if (smp.stop) {
+            if (cudaEventQuery(E(smp.stop)) != cudaSuccess) {
+                (void)cudaGetLastError();  // cudaErrorNotReady is expected: the kernels of this bucket are still running
+                break;
+            }
+            float f = 0.f;
+            if (cudaEventElapsedTime(&f, E(smp.start), E(smp.stop)) != cudaSuccess) {
+                (void)cudaGetLastError();
+                f = 0.f;
+            }
+            ms = f;
+            timing_pool_.push_back(smp.start);
+            timing_pool_.push_back(smp.stop);
+        }
+        auto it = prof_stats_.find(smp.name);
+        if (it != prof_stats_.end()) {
+            BucketStat& st = it->second;
+            st.count++;
+            st.total_ms += ms;
+            st.queue_ms += smp.queue_ms;
+            if (ms > st.max_ms) st.max_ms = ms;
+        }
+        prof_pending_.pop_front();
+    }
+    std::vector<BucketStat> out;
+    for (auto& n : prof_order_) {
+        auto it = prof_stats_.find(n);
+        if (it != prof_stats_.end()) out.push_back(it->second);
+    }
+    if (reset)
+        for (auto& kv : prof_stats_) kv.second.count = 0, kv.second.total_ms = kv.second.max_ms = kv.second.queue_ms = 0.0;
+    return out;
+}
+
 void Backend::release_event(EventHandle e) {
     if (!e) return;
     std::lock_guard<std::mutex> lk(pool_mu_);
@@ -117,6 +178,19 @@ void Backend::release_event(EventHandle e) {
 }
 
 void Backend::register_ordered_buckets(std::vector<std::shared_ptr<Bucket>> buckets) {
+    {
+        std::lock_guard<std::mutex> plk(prof_mu_);
+        prof_stats_.clear();
+        prof_order_.clear();
+        for (auto& b : buckets) {
+            BucketStat st;
+            st.name = b->name();
+            st.ops = b->describe_ops();
+            st.bytes = b->bytes();
+            prof_stats_[st.name] = st;
+            prof_order_.push_back(st.name);
+        }
+    }
     // Same sanity checks as the reference (lib.rs:282-292): tensor names and storage must be unique.
     std::set<std::string> names;
     std::set<uint64_t> ptrs;
@@ -248,6 +322,19 @@ void Backend::worker_loop() {
                 }
                 for (auto e : tk->wait_events) BAGUA_CUDA_CHECK(cudaStreamWaitEvent(S(stream_), E(e), 0));
             }
+            const bool prof = profile_.load(std::memory_order_relaxed);
+            ProfSample smp;
+            std::chrono::steady_clock::time_point t_issue;
+            if (prof) {
+                t_issue = std::chrono::steady_clock::now();
+                smp.name = tk->bucket->name();
+                smp.queue_ms = std::chrono::duration<double, std::milli>(t_issue - tk->t_sched).count();
+                if (device_ >= 0) {
+                    smp.start = acquire_timing_event();
+                    smp.stop = acquire_timing_event();
+                    BAGUA_CUDA_CHECK(cudaEventRecord(E(smp.start), S(stream_)));
+                }
+            }
             nvtxRangePushA(tk->bucket->name().c_str());
             for (auto& op : tk->bucket->ops()) {
                 nvtxRangePushA(op->kind());
@@ -255,6 +342,14 @@ void Backend::worker_loop() {
                 nvtxRangePop();
             }
             nvtxRangePop();
+            if (prof) {
+                if (device_ >= 0)
+                    BAGUA_CUDA_CHECK(cudaEventRecord(E(smp.stop), S(stream_)));
+                else
+                    smp.host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_issue).count();
+                std::lock_guard<std::mutex> plk(prof_mu_);
+                prof_pending_.push_back(std::move(smp));
+            }
             if (device_ >= 0) {
                 tk->done_event = acquire_event();
                 BAGUA_CUDA_CHECK(cudaEventRecord(E(tk->done_event), S(stream_)));

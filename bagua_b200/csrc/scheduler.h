@@ -125,6 +125,20 @@ private:
     std::vector<EventHandle> user_events_;
 };
 
+// Per-bucket communication statistics (opt-in, Backend::set_profile): device time of the bucket's op list measured with
+// a pair of timing events on the comm stream (host time on the CPU backend), plus the host-side queueing delay between
+// "last tensor marked" and "ops issued". The reference has no equivalent (its speed metric is one number per iteration,
+// data_parallel/bagua_distributed.py:113-131); these feed the per-bucket GB/s report and the autotuner.
+struct BucketStat {
+    std::string name;
+    std::string ops;
+    size_t bytes = 0;
+    uint64_t count = 0;
+    double total_ms = 0.0;
+    double max_ms = 0.0;
+    double queue_ms = 0.0;  // sum of (issue time − schedule time) on the host
+};
+
 struct ReadySpan {
     std::string tensor_name;
     int64_t t_ns;     // steady clock, ns
@@ -153,6 +167,9 @@ public:
     std::string watchdog_error();
     std::vector<ReadySpan> pop_ready_spans();
     void set_record_spans(bool on) { record_spans_ = on; }
+    void set_profile(bool on) { profile_ = on; }
+    // Folds every finished measurement into the table and returns it (non-blocking: kernels still running stay pending).
+    std::vector<BucketStat> bucket_stats(bool reset = false);
     uint64_t scheduled_total() const { return scheduled_total_.load(); }
     int device_id() const { return device_; }
     StreamHandle comm_stream() const { return stream_; }
@@ -184,6 +201,19 @@ private:
     double timeout_s_;
     std::atomic<bool> watchdog_fatal_{true};
     std::atomic<bool> record_spans_{false};
+    std::atomic<bool> profile_{false};
+    struct ProfSample {
+        std::string name;
+        EventHandle start = nullptr, stop = nullptr;  // GPU backend
+        double host_ms = -1.0;                        // CPU backend
+        double queue_ms = 0.0;
+    };
+    std::mutex prof_mu_;
+    std::deque<ProfSample> prof_pending_;
+    std::vector<EventHandle> timing_pool_;
+    std::unordered_map<std::string, BucketStat> prof_stats_;
+    std::vector<std::string> prof_order_;
+    EventHandle acquire_timing_event();
 
     std::mutex mu_;
     std::condition_variable cv_worker_;   // queue not empty / stop

@@ -344,6 +344,31 @@ class BaguaDistributedDataParallel:
         self._backward_hook = self.bagua_algorithm.init_backward_hook(self)
         self._post_backward_hook = self.bagua_algorithm.init_post_backward_hook(self)
 
+    # ---------------------------------------------------------------------------------------------------------
+    # per-bucket communication profile
+    # ---------------------------------------------------------------------------------------------------------
+    def comm_profile(self, enable: bool = True):
+        """Start / stop measuring every bucket's communication program (timing events on the comm stream, see
+        ``Backend::set_profile``).  Costs two event records per bucket launch; off by default."""
+        self._bagua_backend.set_profile(bool(enable))
+        if enable:
+            self._bagua_backend.bucket_stats(True)
+
+    def comm_report(self, reset: bool = False) -> List[dict]:
+        """Per bucket: launches, mean / max device time of its op list, achieved GB/s over the bucket bytes (algorithmic
+        bandwidth), mean host-side queueing delay and the kernel variant in use."""
+        variants = {b.name: getattr(b, "allreduce_variant", None) for b in self.bagua_buckets}
+        out = []
+        for st in self._bagua_backend.bucket_stats(reset):
+            n = max(int(st["count"]), 1)
+            mean_ms = st["total_ms"] / n
+            out.append({
+                "bucket": st["name"], "ops": st["ops"], "variant": variants.get(st["name"]), "bytes": int(st["bytes"]), "launches": int(st["count"]),
+                "mean_ms": mean_ms, "max_ms": st["max_ms"], "queue_ms": st["queue_ms"] / n,
+                "algbw_GBps": (st["bytes"] / 1e9) / (mean_ms / 1e3) if st["count"] and mean_ms > 0 else 0.0,
+            })
+        return out
+
     def _delay_allreduce(self):
         for name, p in self.bagua_build_params():
             self._backward_hook(name, p)

@@ -24,6 +24,7 @@ p.add_argument("--warmup", type=int, default=5)
 p.add_argument("--batch-size", type=int, default=0)
 p.add_argument("--tiny", action="store_true", help="shrunken models for CPU smoke tests")
 p.add_argument("--cpu", action="store_true")
+p.add_argument("--comm-report", action="store_true", help="per-bucket device time / GB/s of the communication programs (adds 2 event records per bucket)")
 p.add_argument("--arm", choices=["peer", "nccl"], default="peer", help="nccl = same schedule on NCCL collectives / cuBLAS experts only (baseline arm)")
 args = p.parse_args()
 if args.arm == "nccl":
@@ -120,6 +121,8 @@ def sync():
 for _ in range(max(args.warmup, 3)):
     loss = step()
 sync()
+if args.comm_report:
+    model.bagua_ddp.comm_profile(True)
 if cuda:
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
@@ -140,6 +143,11 @@ if world > 1:
 if cfg == "resnet50_async":
     model.bagua_algorithm.abort(model)
 finite = bool(torch.isfinite(loss.detach().float()).item())
+if args.comm_report and rank == 0:
+    if cuda:
+        torch.cuda.synchronize()
+    for r in model.bagua_ddp.comm_report():
+        print("[comm]", json.dumps(r), file=sys.stderr)
 if rank == 0:
     print(json.dumps({
         "config": cfg, "arm": args.arm, "moe_fused_combine": os.environ.get("BAGUA_MOE_FUSED_COMBINE", "0"), "n_gpus": world, "value": per_step * world * args.steps / (ms.item() / 1e3), "unit": unit, "ms_per_step": ms.item() / args.steps,

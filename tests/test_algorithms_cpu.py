@@ -58,9 +58,12 @@ def _grad_allreduce_worker(rank, world):
             dist.all_reduce(p.grad)
             p.grad /= world
 
+    model.bagua_ddp.comm_profile(True)
     _train(model, opt, rank, 6)
     _train(oracle, oopt, rank, 6, post=avg)
     assert len(model.bagua_buckets) >= 1 and all(b.check_flatten() for b in model.bagua_buckets)
+    report = model.bagua_ddp.comm_report()
+    assert len(report) == len(model.bagua_buckets) and all(r["launches"] == 6 and r["mean_ms"] > 0 and r["bytes"] > 0 for r in report), report
     return _flat(model), _flat(oracle)
 
 

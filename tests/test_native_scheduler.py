@@ -128,3 +128,33 @@ def test_shift_one_peer_formula():
             peers = [C.PeerAverageOp.shift_one_peer(r, n, step) for r in range(n)]
             for r, p in enumerate(peers):
                 assert peers[p] == r and p != r  # a perfect matching
+
+
+def test_bucket_profile_measures_op_time_and_queueing():
+    """Backend::set_profile on the CPU backend: host time of each bucket's op list, launch counts, table reset on re-registration."""
+    import time
+
+    C = native()
+    backend = C.Backend(8, -1, 0, 60.0)
+    t1 = C.Tensor("a", 1000, 16, 0, -1)
+    t2 = C.Tensor("b", 2000, 32, 0, -1)
+    b1, b2 = C.Bucket("slow", [t1]), C.Bucket("fast", [t2])
+    b1.append_python_op(lambda name: time.sleep(0.03))
+    b2.append_python_op(lambda name: None)
+    backend.register_ordered_buckets([b1, b2])
+    backend.set_profile(True)
+    for _ in range(3):
+        backend.mark_communication_ready(t1, 0)
+        backend.mark_communication_ready(t2, 0)
+        backend.wait_pending_comm_ops(0, True)
+    stats = {s["name"]: s for s in backend.bucket_stats()}
+    assert stats["slow"]["count"] == 3 and stats["fast"]["count"] == 3
+    assert stats["slow"]["total_ms"] >= 80 and stats["slow"]["max_ms"] >= 25 and stats["fast"]["total_ms"] < 30
+    assert stats["slow"]["bytes"] == 64 and stats["fast"]["bytes"] == 128 and "python" in stats["slow"]["ops"]
+    assert backend.bucket_stats(True)[0]["count"] == 3 and backend.bucket_stats()[0]["count"] == 0   # reset
+    backend.set_profile(False)
+    backend.mark_communication_ready(t1, 0)
+    backend.mark_communication_ready(t2, 0)
+    backend.wait_pending_comm_ops(0, True)
+    assert all(s["count"] == 0 for s in backend.bucket_stats())
+    backend.shutdown()
