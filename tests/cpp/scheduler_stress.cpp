@@ -16,6 +16,7 @@ int main() {
     Backend be(4, -1, nullptr, 30.0);
     be.set_watchdog_fatal(false);
     be.set_record_spans(true);
+    be.set_profile(true);  // per-bucket statistics are read concurrently with the worker below
     std::vector<std::shared_ptr<Bucket>> buckets;
     std::vector<std::shared_ptr<Tensor>> tensors;
     std::vector<int> order;
@@ -48,8 +49,10 @@ int main() {
                 for (int i : idx) be.mark_communication_ready(tensors[i], nullptr);
             });
         }
+        std::thread reader([&] { (void)be.bucket_stats(false); });
         for (auto& t : producers) t.join();
         size_t n = be.wait_pending_comm_ops(nullptr, true);
+        reader.join();
         if (n != kBuckets) {
             std::fprintf(stderr, "iteration %d: waited for %zu buckets, expected %d\n", it, n, kBuckets);
             ++failures;
@@ -60,6 +63,12 @@ int main() {
     }
     auto spans = be.pop_ready_spans();
     if (spans.empty()) ++failures;
+    uint64_t launches = 0;
+    for (auto& st : be.bucket_stats(false)) launches += st.count;
+    if (launches != static_cast<uint64_t>(kIters) * kBuckets) {
+        std::fprintf(stderr, "profile counted %llu launches, expected %d\n", static_cast<unsigned long long>(launches), kIters * kBuckets);
+        ++failures;
+    }
     be.shutdown();
     std::printf("scheduler stress: %d iterations, %zu ops, %d failures\n", kIters, order.size(), failures);
     return failures == 0 ? 0 : 1;
