@@ -65,6 +65,9 @@ class BucketArena:
 
     def __init__(self, group, device: torch.device, capacity_bytes: int):
         eng = group.peer_engine() if device.type == "cuda" else None
+        if eng is None and device.type == "cuda" and getattr(group, "nnodes", 1) > 1:
+            hier = group.hier_engine()  # multi-node: the arena lives in the NODE's symmetric memory (intra-node kernels)
+            eng = hier[0] if hier is not None else None
         capacity_bytes = max(int(capacity_bytes), _ARENA_ALIGN)
         self.engine = eng
         if eng is not None:
@@ -362,6 +365,35 @@ class BaguaBucket:
             self.backend_bucket.append_op(op)
             self._ops_keepalive.append(op)
             self.allreduce_variant = chosen
+            return self
+
+        hier = pg.hier_engine() if (eng is None and self._slice is not None and pg.nnodes > 1) else None
+        flat_t = self.backend_tensor
+        if hier is not None and flat_t is not None and flat_t.dtype in (torch.float32, torch.float16, torch.bfloat16) and (flat_t.numel() * flat_t.element_size()) % 16 == 0:
+            # several NVSwitch nodes: NVLink reduce-scatter kernel → inter-node all-reduce of my 1/L slice on my rail → NVLink all-gather kernel
+            ieng, rail_pg, L, nodes = hier
+            C = native()
+            es = flat_t.element_size()
+            nbytes = flat_t.numel() * es
+            vecs = nbytes // 16
+            vpr = (vecs + L - 1) // L
+            lo, hi = ieng.rank * vpr * 16, min((ieng.rank + 1) * vpr * 16, nbytes)
+            shard = flat_t.view(-1)[lo // es: max(lo, hi) // es]
+            use_mc = bool(self._slice.has_multicast and ieng.has_multicast)
+            cfg = ieng.launch_cfg("multimem" if use_mc else "two_shot", nbytes)
+            rs = C.ReduceScatterOp(ieng.comm, self._slice.buf, self._slice.offset, nbytes, dtype_code(flat_t.dtype), (1.0 / (L * nodes)) if average else 1.0,
+                                   use_mc, cfg)
+            ag = C.AllGatherOp(ieng.comm, self._slice.buf, self._slice.offset, nbytes, dtype_code(flat_t.dtype), use_mc, cfg)
+
+            def inter_node(_name: str):
+                if shard.numel():
+                    dist.all_reduce(shard, group=rail_pg)
+
+            self.backend_bucket.append_op(rs)
+            self.append_python_op(inter_node, group=group)
+            self.backend_bucket.append_op(ag)
+            self._ops_keepalive += [rs, ag]
+            self.allreduce_variant = "hier:rs_" + ("multimem" if use_mc else "peer") + "+rail_allreduce+ag"
             return self
 
         def fallback(_name: str):

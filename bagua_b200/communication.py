@@ -331,8 +331,18 @@ class BaguaProcessGroup:
         local_of = {r: mapping[r][1] for r in self.ranks if r in mapping}
         me = dist.get_rank() if dist.is_initialized() else 0
         self.intra_ranks = [r for r in self.ranks if node_of.get(r) == node_of.get(me, env.get_node_rank())] or [me]
-        self.inter_ranks = [r for r in self.ranks if local_of.get(r) == local_of.get(me, env.get_local_rank())] or [me]
+        # "rail" peers: the group members holding the same position inside their node (== same local rank when the group
+        # takes the same local ranks on every node; still connects the nodes when it does not)
+        by_node: Dict[object, List[int]] = {}
+        for r in self.ranks:
+            by_node.setdefault(node_of.get(r), []).append(r)
+        pos = {r: sorted(members).index(r) for members in by_node.values() for r in members}
+        self.inter_ranks = [r for r in self.ranks if pos.get(r) == pos.get(me, 0)] if me in pos else [me]
         self.nnodes = len(set(node_of.values())) if node_of else 1
+        self._node_sizes = sorted(len(m) for m in by_node.values())
+        self._local_of = local_of
+        self._hier = None
+        self._hier_failed = False
 
     # torch ProcessGroup accessors ----------------------------------------------------------------------------
     def _pg_for(self, scope: str) -> Optional[dist.ProcessGroup]:
@@ -396,6 +406,35 @@ class BaguaProcessGroup:
         return self._peer_engine
 
 
+def _hier_engine(self):
+    """Multi-node counterpart of :meth:`peer_engine`: ``(intra-node PeerEngine, rail torch group, ranks per node, nodes)`` for
+    a CUDA group that spans several NVSwitch nodes with the same number (2…8) of ranks on each; ``None`` otherwise.
+    Collective over the group on first use.  The hierarchical all-reduce built on it: reduce-scatter kernel inside the node →
+    all-reduce of this rank's 1/L slice with its rail peers (NCCL; every NIC rail carries 1/L of the bucket) → all-gather kernel."""
+    if self._hier is not None or self._hier_failed:
+        return self._hier
+    from .core import native
+
+    with self._lock:
+        if self._hier is None and not self._hier_failed:
+            try:
+                ok = (_use_cuda() and env.get_allreduce_variant() != "nccl" and self.nnodes > 1 and len(set(self._node_sizes)) == 1
+                      and 2 <= self._node_sizes[0] <= native().MAX_PEERS and dist.get_rank() in self.ranks)
+                if ok:
+                    intra_pg = BaguaProcessGroup(self.intra_ranks, self.stream, self.group_name + ".intra", self._pg_for("intra"))
+                    eng = intra_pg.peer_engine()
+                    rail = self._pg_for("inter")
+                    if eng is not None:
+                        self._hier = (eng, rail, self._node_sizes[0], self.nnodes)
+                        self._hier_intra_pg = intra_pg
+            except Exception as e:  # noqa: BLE001
+                logger.warning("bagua_b200: hierarchical peer engine unavailable for group %s: %s", self.group_name, e)
+            if self._hier is None:
+                self._hier_failed = True
+    return self._hier
+
+
+BaguaProcessGroup.hier_engine = _hier_engine
 _subgroup_cache: Dict[tuple, dist.ProcessGroup] = {}
 _default_pg: Optional[BaguaProcessGroup] = None
 _group_count = 0

@@ -194,6 +194,12 @@ PYBIND11_MODULE(_C, m) {
         .def("set_grad_scale", &AllReduceSgdOp::set_grad_scale)
         .def("steps", &AllReduceSgdOp::steps)
         .def("set_steps", &AllReduceSgdOp::set_steps);
+    py::class_<ReduceScatterOp, CommOp, std::shared_ptr<ReduceScatterOp>>(m, "ReduceScatterOp")
+        .def(py::init<std::shared_ptr<PeerComm>, SymmBuf, size_t, size_t, int, float, bool, LaunchCfg>(), py::arg("comm"), py::arg("buf"), py::arg("off"),
+             py::arg("bytes"), py::arg("dtype"), py::arg("scale"), py::arg("use_multimem"), py::arg("cfg"));
+    py::class_<AllGatherOp, CommOp, std::shared_ptr<AllGatherOp>>(m, "AllGatherOp")
+        .def(py::init<std::shared_ptr<PeerComm>, SymmBuf, size_t, size_t, int, bool, LaunchCfg>(), py::arg("comm"), py::arg("buf"), py::arg("off"),
+             py::arg("bytes"), py::arg("dtype"), py::arg("use_multimem"), py::arg("cfg"));
     py::class_<AllReduceAdamOp, CommOp, std::shared_ptr<AllReduceAdamOp>>(m, "AllReduceAdamOp")
         .def(py::init<std::shared_ptr<PeerComm>, SymmBuf, SymmBuf, size_t, size_t, size_t, int, uint64_t, uint64_t, uint64_t, float, bool, bool,
                       LaunchCfg>(),

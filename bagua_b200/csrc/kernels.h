@@ -41,6 +41,12 @@ void launch_allreduce_oneshot(const PeerCtx& ctx, const PeerBuf& staging, size_t
 void launch_allreduce_sgd(const PeerCtx& ctx, const PeerBuf& grads, const PeerBuf& weights, size_t g_off, size_t w_off,
                           size_t bytes, int dtype, float* master, float* momentum, const SgdParams& hp, float scale,
                           bool zero_grads, bool use_multimem, int nblocks, int nthreads, cudaStream_t stream);
+// Halves of the two-shot schedule (hierarchical all-reduce): in-place reduce of slice `rank` over the group (scaled), and
+// publication of slice `rank` to every peer. Slices are ceil(vecs / world) 16-byte vectors.
+void launch_reduce_scatter(const PeerCtx& ctx, const PeerBuf& buf, size_t off, size_t bytes, int dtype, float scale, bool use_multimem, int nblocks,
+                           int nthreads, cudaStream_t stream);
+void launch_all_gather(const PeerCtx& ctx, const PeerBuf& buf, size_t off, size_t bytes, int dtype, bool use_multimem, int nblocks, int nthreads,
+                       cudaStream_t stream);
 // Adam / AdamW variant (fp32 master + both moments sharded world ways); hp carries the bias corrections of THIS step.
 void launch_allreduce_adam(const PeerCtx& ctx, const PeerBuf& grads, const PeerBuf& weights, size_t g_off, size_t w_off, size_t bytes, int dtype,
                            float* master, float* exp_avg, float* exp_avg_sq, const AdamParams& hp, float scale, bool zero_grads, bool use_multimem,

@@ -125,6 +125,14 @@ void AllReduceSgdOp::run(Bucket&, StreamHandle stream, int) {
     steps_++;
 }
 
+void ReduceScatterOp::run(Bucket&, StreamHandle stream, int) {
+    launch_reduce_scatter(comm_->ctx(), buf_.buf, off_, bytes_, dtype_, scale_, use_mc_, cfg_.nblocks, cfg_.nthreads, S(stream));
+}
+
+void AllGatherOp::run(Bucket&, StreamHandle stream, int) {
+    launch_all_gather(comm_->ctx(), buf_.buf, off_, bytes_, dtype_, use_mc_, cfg_.nblocks, cfg_.nthreads, S(stream));
+}
+
 void AllReduceAdamOp::run(Bucket&, StreamHandle stream, int) {
     AdamParams hp{};
     float scale;

@@ -140,6 +140,41 @@ private:
     std::mutex mu_;
 };
 
+// Intra-node halves of a hierarchical all-reduce (see reduce_scatter_kernel): ReduceScatterOp, then a callback op that
+// all-reduces slice `rank` between nodes, then AllGatherOp.
+class ReduceScatterOp final : public CommOp {
+public:
+    ReduceScatterOp(std::shared_ptr<PeerComm> comm, SymmBuf buf, size_t off, size_t bytes, int dtype, float scale, bool use_multimem, LaunchCfg cfg)
+        : comm_(std::move(comm)), buf_(buf), off_(off), bytes_(bytes), dtype_(dtype), scale_(scale), use_mc_(use_multimem), cfg_(cfg) {}
+    const char* kind() const override { return "reduce_scatter"; }
+    void run(Bucket&, StreamHandle stream, int device) override;
+
+private:
+    std::shared_ptr<PeerComm> comm_;
+    SymmBuf buf_;
+    size_t off_, bytes_;
+    int dtype_;
+    float scale_;
+    bool use_mc_;
+    LaunchCfg cfg_;
+};
+
+class AllGatherOp final : public CommOp {
+public:
+    AllGatherOp(std::shared_ptr<PeerComm> comm, SymmBuf buf, size_t off, size_t bytes, int dtype, bool use_multimem, LaunchCfg cfg)
+        : comm_(std::move(comm)), buf_(buf), off_(off), bytes_(bytes), dtype_(dtype), use_mc_(use_multimem), cfg_(cfg) {}
+    const char* kind() const override { return "all_gather"; }
+    void run(Bucket&, StreamHandle stream, int device) override;
+
+private:
+    std::shared_ptr<PeerComm> comm_;
+    SymmBuf buf_;
+    size_t off_, bytes_;
+    int dtype_;
+    bool use_mc_;
+    LaunchCfg cfg_;
+};
+
 // The Adam / AdamW flavour of the fused bucket op; the step counter (bias correction) advances with every launch.
 class AllReduceAdamOp final : public CommOp {
 public:

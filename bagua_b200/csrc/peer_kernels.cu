@@ -105,6 +105,99 @@ __global__ void __launch_bounds__(512) allreduce_multimem_kernel(PeerCtx ctx, Pe
     store_epoch(ctx, e0 + 2);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The two halves of the two-shot schedule as separate kernels, for hierarchical (multi-node) all-reduce:
+//   reduce_scatter: rank r reduces slice r over the node's GPUs IN PLACE (its own buffer, slice r)   [intra-node, NVLink]
+//   … the caller all-reduces slice r between nodes (NCCL / net plugin, 1/L of the bucket per GPU, all rails busy) …
+//   all_gather:     rank r publishes slice r into every peer's buffer                                [intra-node, NVLink]
+// Slice r of rank r's buffer is read and written by rank r only, so in-place is safe; the closing barrier of the
+// first kernel ("everybody finished reading my other slices") is what allows the second one to overwrite them.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, int P, bool USE_MC>
+__global__ void __launch_bounds__(512) reduce_scatter_kernel(PeerCtx ctx, PeerBuf buf, size_t off, size_t total_vecs, float scale) {
+    constexpr int U = USE_MC ? 8 : (P <= 2 ? 8 : (P <= 4 ? 4 : 2));
+    const uint32_t e0 = load_epoch(ctx);
+    bool ok = peer_barrier(ctx, e0 + 1);
+    if (ok) {
+        const size_t vpr = (total_vecs + P - 1) / P;
+        const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+        const size_t base = static_cast<size_t>(ctx.rank) * vpr;
+        const size_t limit = (base + vpr < total_vecs ? base + vpr : total_vecs);
+        char* mine = buf.ptr[ctx.rank] + off;
+        for (size_t j0 = base + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; j0 < limit; j0 += stride * U) {
+            uint4 raw[U][USE_MC ? 1 : P];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const size_t v = j0 + u * stride;
+                if (v < limit) {
+                    if (USE_MC) {
+                        raw[u][0] = multimem_ld_reduce_add<T>(buf.mc + off + v * 16);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < (USE_MC ? 1 : P); ++i) raw[u][i] = ld_peer16(buf.ptr[(ctx.rank + i) % P] + off + v * 16);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const size_t v = j0 + u * stride;
+                if (v >= limit) continue;
+                float acc[Vec16<T>::N];
+                Vec16<T>::unpack(raw[u][0], acc);
+                if (!USE_MC) {
+#pragma unroll
+                    for (int i = 1; i < (USE_MC ? 1 : P); ++i) {
+                        float f[Vec16<T>::N];
+                        Vec16<T>::unpack(raw[u][i], f);
+#pragma unroll
+                        for (int k = 0; k < Vec16<T>::N; ++k) acc[k] += f[k];
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < Vec16<T>::N; ++k) acc[k] *= scale;
+                st_stream16(mine + v * 16, Vec16<T>::pack(acc));
+            }
+        }
+        peer_barrier(ctx, e0 + 2);
+    }
+    store_epoch(ctx, e0 + 2);
+}
+
+template <typename T, int P, bool USE_MC>
+__global__ void __launch_bounds__(512) all_gather_kernel(PeerCtx ctx, PeerBuf buf, size_t off, size_t total_vecs) {
+    constexpr int U = 4;
+    const uint32_t e0 = load_epoch(ctx);
+    bool ok = peer_barrier(ctx, e0 + 1);  // nobody is still reading the slices that are about to be overwritten
+    if (ok) {
+        const size_t vpr = (total_vecs + P - 1) / P;
+        const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+        const size_t base = static_cast<size_t>(ctx.rank) * vpr;
+        const size_t limit = (base + vpr < total_vecs ? base + vpr : total_vecs);
+        const char* mine = buf.ptr[ctx.rank] + off;
+        for (size_t j0 = base + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; j0 < limit; j0 += stride * U) {
+            uint4 raw[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const size_t v = j0 + u * stride;
+                if (v < limit) raw[u] = ld_stream16(mine + v * 16);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const size_t v = j0 + u * stride;
+                if (v >= limit) continue;
+                if (USE_MC) {
+                    multimem_st16(buf.mc + off + v * 16, raw[u]);
+                } else {
+#pragma unroll
+                    for (int i = 1; i < P; ++i) st_peer16(buf.ptr[(ctx.rank + i) % P] + off + v * 16, raw[u]);  // my own copy is already in place
+                }
+            }
+        }
+        peer_barrier(ctx, e0 + 2);  // every slice has landed everywhere
+    }
+    store_epoch(ctx, e0 + 2);
+}
+
 // One-shot, push flavour, for latency-bound messages: every rank stores its message into slot [parity][rank]
 // of every peer's staging area, ONE barrier, then reduces the P slots it received locally. The staging area is
 // double-buffered by epoch parity, so no second barrier is needed (a rank can only be two calls ahead of a peer
@@ -479,6 +572,44 @@ void launch_allreduce_sgd(const PeerCtx& ctx, const PeerBuf& grads, const PeerBu
         });
     });
     check_launch("allreduce_sgd");
+}
+
+void launch_reduce_scatter(const PeerCtx& ctx, const PeerBuf& buf, size_t off, size_t bytes, int dtype, float scale, bool use_multimem, int nblocks,
+                           int nthreads, cudaStream_t stream) {
+    if (bytes % 16 || off % 16) throw std::runtime_error("bagua: reduce_scatter needs 16-byte aligned size/offset");
+    check_blocks(nblocks);
+    const size_t vecs = bytes / 16;
+    if (vecs == 0) return;
+    dispatch_float(dtype, [&](auto tag) {
+        using T = decltype(tag);
+        dispatch_world(ctx.world, [&](auto pw) {
+            constexpr int P = decltype(pw)::value;
+            if (use_multimem)
+                reduce_scatter_kernel<T, P, true><<<nblocks, nthreads, 0, stream>>>(ctx, buf, off, vecs, scale);
+            else
+                reduce_scatter_kernel<T, P, false><<<nblocks, nthreads, 0, stream>>>(ctx, buf, off, vecs, scale);
+        });
+    });
+    check_launch("reduce_scatter");
+}
+
+void launch_all_gather(const PeerCtx& ctx, const PeerBuf& buf, size_t off, size_t bytes, int dtype, bool use_multimem, int nblocks, int nthreads,
+                       cudaStream_t stream) {
+    if (bytes % 16 || off % 16) throw std::runtime_error("bagua: all_gather needs 16-byte aligned size/offset");
+    check_blocks(nblocks);
+    const size_t vecs = bytes / 16;
+    if (vecs == 0) return;
+    dispatch_float(dtype, [&](auto tag) {
+        using T = decltype(tag);
+        dispatch_world(ctx.world, [&](auto pw) {
+            constexpr int P = decltype(pw)::value;
+            if (use_multimem)
+                all_gather_kernel<T, P, true><<<nblocks, nthreads, 0, stream>>>(ctx, buf, off, vecs);
+            else
+                all_gather_kernel<T, P, false><<<nblocks, nthreads, 0, stream>>>(ctx, buf, off, vecs);
+        });
+    });
+    check_launch("all_gather");
 }
 
 void launch_allreduce_adam(const PeerCtx& ctx, const PeerBuf& grads, const PeerBuf& weights, size_t g_off, size_t w_off, size_t bytes, int dtype,

@@ -139,3 +139,35 @@ def test_init_twice_raises_and_uninitialised_default_group():
     assert not bagua.is_initialized()
     with pytest.raises(RuntimeError):
         bagua.communication._get_default_group()
+
+
+def _virtual_nodes_worker(rank, world):
+    """4 processes pretending to be 2 nodes x 2 ranks: intra / rail groups and the hierarchical all-reduce legs."""
+    import os
+
+    os.environ["NODE_RANK"] = str(rank // 2)
+    os.environ["LOCAL_RANK"] = str(rank % 2)
+    os.environ["LOCAL_WORLD_SIZE"] = "2"
+    import torch
+
+    import bagua_b200 as bagua
+    from bagua_b200.bucket import _torch_allreduce
+
+    bagua.init_process_group()
+    pg = bagua.communication._get_default_group()
+    assert pg.nnodes == 2 and pg.intra_ranks == [2 * (rank // 2), 2 * (rank // 2) + 1] and pg.inter_ranks == [rank % 2, rank % 2 + 2]
+    assert pg.peer_engine() is None and pg.hier_engine() is None           # CPU: no peer kernels, torch legs instead
+    t = torch.full((10,), float(rank + 1))
+    _torch_allreduce(t, pg, True, True)                                    # intra reduce → inter all-reduce → intra broadcast
+    sub = bagua.new_group(ranks=[0, 3])                                    # one rank per node, different local ranks: rails must still connect them
+    if rank in (0, 3):
+        assert sub.nnodes == 2 and sub.intra_ranks == [rank] and sub.inter_ranks == [0, 3]
+        u = torch.full((4,), float(rank + 1))
+        _torch_allreduce(u, sub, True, True)
+        assert torch.allclose(u, torch.full((4,), 2.5))
+    return t
+
+
+def test_virtual_multi_node_groups_and_hierarchical_allreduce():
+    for t in run_distributed(_virtual_nodes_worker, world=4):
+        assert torch.allclose(t, torch.full((10,), 2.5))

@@ -293,3 +293,55 @@ def test_fused_allreduce_adam_matches_adamw():
     res = run_distributed(_fused_adam_worker, world=_ngpu(), use_cuda=True)
     for r in res[1:]:
         assert torch.equal(res[0], r)
+
+
+def _hier_worker(rank, world):
+    """One box pretending to be 2 nodes of world/2 GPUs: NVLink reduce-scatter kernel → NCCL all-reduce on the rail → NVLink
+    all-gather kernel must equal a flat all-reduce."""
+    import os
+
+    L = world // 2
+    os.environ["NODE_RANK"] = str(rank // L)
+    os.environ["LOCAL_WORLD_SIZE"] = str(L)
+    import copy
+
+    import torch.distributed as dist
+
+    import bagua_b200 as bagua
+    from bagua_b200.parallel.algorithms import gradient_allreduce
+
+    bagua.init_process_group()
+    pg = bagua.communication._get_default_group()
+    assert pg.nnodes == 2 and pg.peer_engine() is None and pg.hier_engine() is not None
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(3)
+    model = torch.nn.Sequential(torch.nn.Linear(128, 256), torch.nn.ReLU(), torch.nn.Linear(256, 64)).to(dev)
+    oracle = copy.deepcopy(model)
+    opt = torch.optim.SGD(model.parameters(), lr=0.05)
+    oopt = torch.optim.SGD(oracle.parameters(), lr=0.05)
+    model = model.with_bagua([opt], gradient_allreduce.GradientAllReduceAlgorithm(hierarchical=True))
+    assert all(b.allreduce_variant.startswith("hier:") for b in model.bagua_buckets), [b.allreduce_variant for b in model.bagua_buckets]
+    for it in range(4):
+        x = torch.randn(16, 128, device=dev, generator=torch.Generator(device=dev).manual_seed(10 * it + rank))
+        for m, o, manual in ((model, opt, False), (oracle, oopt, True)):
+            o.zero_grad()
+            m(x).pow(2).mean().backward()
+            if manual:
+                for p in oracle.parameters():
+                    dist.all_reduce(p.grad)
+                    p.grad /= world
+            o.step()
+    torch.cuda.synchronize()
+    mine = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    want = torch.cat([p.detach().reshape(-1) for p in oracle.parameters()])
+    torch.testing.assert_close(mine, want, rtol=1e-5, atol=1e-6)
+    return mine
+
+
+@pytest.mark.skipif(__import__("os").environ.get("BAGUA_EXPERIMENTAL") != "1" or torch.cuda.device_count() < 4,
+                    reason="hierarchical (virtual multi-node) path: opt-in until validated on hardware; needs >= 4 GPUs")
+def test_hierarchical_allreduce_on_virtual_nodes():
+    n = 4 if _ngpu() < 8 else 8
+    res = run_distributed(_hier_worker, world=n, use_cuda=True)
+    for r in res[1:]:
+        assert torch.equal(res[0], r)
