@@ -27,6 +27,8 @@ two)
   done
   ;;
 eight)
+  BAGUA_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_peer_gpu.py -x -q -k "hierarchical or fused" > gpurun_out/pytest_experimental_8.log 2>&1
+  echo "experimental(8) exit=$?" | tee gpurun_out/plan_eight.txt
   port=29700
   for cfg in gpt2_moe bert_bytegrad resnet50_decentralized; do
     for arm in peer nccl; do
