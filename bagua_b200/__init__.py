@@ -6,6 +6,15 @@ from __future__ import annotations
 
 __version__ = "0.1.0"
 
+import logging as _logging
+import os as _os
+
+# LOG_LEVEL (TRACE|DEBUG|INFO|WARN|ERROR) drives both the native core's stderr log (csrc/log.h) and this package's loggers
+_lvl = {"TRACE": 5, "DEBUG": _logging.DEBUG, "INFO": _logging.INFO, "WARN": _logging.WARNING, "WARNING": _logging.WARNING,
+        "ERROR": _logging.ERROR}.get(_os.environ.get("LOG_LEVEL", "").upper())
+if _lvl is not None:
+    _logging.getLogger(__name__).setLevel(_lvl)
+
 from . import env  # noqa: F401
 from .env import get_rank, get_world_size, get_local_rank, get_local_size, get_node_rank  # noqa: F401
 from . import tensor as _tensor_patch  # noqa: F401  (installs torch.Tensor.*bagua* methods)

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include "kernels.h"
+#include "log.h"
 #include "ops.h"
 #include "scheduler.h"
 
@@ -46,6 +47,8 @@ AdamParams make_adam(float lr, float b1, float b2, float eps, float wd, int step
 
 PYBIND11_MODULE(_C, m) {
     m.doc() = "bagua_b200 native core (sm_100a)";
+    m.def("log_level", [] { return std::string(bagua::log::name(bagua::log::threshold())); });
+    m.def("set_log_level", [](const std::string& lvl) { bagua::log::threshold() = bagua::log::parse_level(lvl.c_str()); });
     m.attr("MAX_PEERS") = kMaxPeers;
     m.attr("MAX_COMM_BLOCKS") = kMaxCommBlocks;
     m.attr("AR_ONE_SHOT") = static_cast<int>(AR_ONE_SHOT);

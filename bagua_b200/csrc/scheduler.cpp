@@ -1,4 +1,5 @@
 #include "scheduler.h"
+#include "log.h"
 
 #include <cuda_runtime.h>
 #include <nvtx3/nvToolsExt.h>
@@ -70,6 +71,7 @@ void Bucket::reset_comm_ready() {
 
 Backend::Backend(size_t channel_cap, int device_id, StreamHandle comm_stream, double watchdog_timeout_s)
     : cap_(std::max<size_t>(channel_cap, 1)), device_(device_id), stream_(comm_stream), timeout_s_(watchdog_timeout_s) {
+    BAGUA_LOG(INFO, "comm backend created: device %d, channel capacity %zu, watchdog %.0f s", device_, cap_, timeout_s_);
     worker_ = std::thread([this] { worker_loop(); });
     watchdog_ = std::thread([this] { watchdog_loop(); });
 }
@@ -293,6 +295,7 @@ void Backend::schedule_locked(std::unique_lock<std::mutex>& lk) {
         b->user_events_.clear();
         b->producer_stream_set_ = false;
         tk->t_sched = std::chrono::steady_clock::now();
+        BAGUA_LOG(DEBUG, "bucket %s ready: scheduled (%zu in queue, %zu wait events)", b->name().c_str(), queue_.size() + 1, tk->wait_events.size());
         queue_.push_back(tk);
         not_waited_.push_back(tk);
         scheduled_total_++;
@@ -338,6 +341,7 @@ void Backend::worker_loop() {
             nvtxRangePushA(tk->bucket->name().c_str());
             for (auto& op : tk->bucket->ops()) {
                 nvtxRangePushA(op->kind());
+                BAGUA_LOG(TRACE, "bucket %s: issuing op %s", tk->bucket->name().c_str(), op->kind());
                 op->run(*tk->bucket, stream_, device_);
                 nvtxRangePop();
             }
@@ -357,6 +361,7 @@ void Backend::worker_loop() {
         } catch (const std::exception& ex) {
             tk->failed = true;
             tk->error = ex.what();
+            BAGUA_LOG(ERROR, "communication of %s failed: %s", tk->bucket->describe_ops().c_str(), ex.what());
         } catch (...) {
             tk->failed = true;
             tk->error = "unknown error in comm op";

@@ -158,3 +158,13 @@ def test_bucket_profile_measures_op_time_and_queueing():
     backend.wait_pending_comm_ops(0, True)
     assert all(s["count"] == 0 for s in backend.bucket_stats())
     backend.shutdown()
+
+
+def test_log_level_is_settable():
+    C = native()
+    before = C.log_level()
+    C.set_log_level("debug")
+    assert C.log_level() == "DEBUG"
+    C.set_log_level("nonsense")
+    assert C.log_level() == "WARN"
+    C.set_log_level(before)
