@@ -345,3 +345,52 @@ def test_hierarchical_allreduce_on_virtual_nodes():
     res = run_distributed(_hier_worker, world=n, use_cuda=True)
     for r in res[1:]:
         assert torch.equal(res[0], r)
+
+
+def _abort_worker(rank, world):
+    """Fault injection (reference tests/comm/test_communicator.py:48-70): an all-reduce nobody else joins must be unblocked by
+    ``abort()``, and a second one by the in-kernel timeout — the GPU is never left spinning."""
+    import time
+
+    import torch.distributed as dist
+
+    import bagua_b200 as bagua
+    from bagua_b200.core import native
+
+    bagua.init_process_group()
+    pg = bagua.communication._get_default_group()
+    eng = pg.peer_engine()
+    C = native()
+    nbytes = 1 << 20
+    sl = eng.alloc(nbytes)
+    op, _ = eng.make_allreduce_op(sl, sl, nbytes, torch.float32, True, "two_shot")
+    dist.barrier()
+    out = {}
+    if rank == 0:
+        stream = torch.cuda.current_stream()
+        C.run_op(op, stream.cuda_stream, rank)
+        time.sleep(1.0)
+        out["spinning"] = not stream.query()
+        t0 = time.time()
+        pg.get_global_communicator().abort()
+        torch.cuda.synchronize()
+        out["abort_latency_s"] = time.time() - t0
+        out["code_after_abort"] = eng.comm.error_code()
+        eng.comm.reset_abort()
+        eng.comm.clear_error()
+        eng.comm.set_timeout(2.0)
+        t0 = time.time()
+        C.run_op(op, stream.cuda_stream, rank)
+        torch.cuda.synchronize()
+        out["timeout_latency_s"] = time.time() - t0
+        out["code_after_timeout"] = eng.comm.error_code()
+    dist.barrier()
+    return out
+
+
+@pytest.mark.skipif(__import__("os").environ.get("BAGUA_EXPERIMENTAL") != "1", reason="fault-injection test: opt-in until validated on hardware")
+def test_abort_and_timeout_unblock_a_lonely_allreduce():
+    res = run_distributed(_abort_worker, world=2, use_cuda=True)
+    r0 = res[0]
+    assert r0["spinning"] and r0["abort_latency_s"] < 1.0 and r0["code_after_abort"] == 2
+    assert 1.5 < r0["timeout_latency_s"] < 6.0 and r0["code_after_timeout"] in (1, 3)
