@@ -394,3 +394,39 @@ def test_abort_and_timeout_unblock_a_lonely_allreduce():
     r0 = res[0]
     assert r0["spinning"] and r0["abort_latency_s"] < 1.0 and r0["code_after_abort"] == 2
     assert 1.5 < r0["timeout_latency_s"] < 6.0 and r0["code_after_timeout"] in (1, 3)
+
+
+def _syncbn_worker(rank, world):
+    """CUDA path of contrib.SyncBatchNorm (ATen batch_norm_* kernels + packed all-gather / all-reduce) vs torch.nn.SyncBatchNorm
+    (reference tests/contrib/test_sync_bn.py:66-227)."""
+    import torch.distributed as dist
+
+    import bagua_b200 as bagua
+    from bagua_b200.contrib.sync_batchnorm import SyncBatchNorm
+
+    bagua.init_process_group()
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(20 + rank)
+    mine = SyncBatchNorm(16).to(dev)
+    ref = torch.nn.SyncBatchNorm(16).to(dev)
+    with torch.no_grad():
+        w, b = torch.rand(16, device=dev) + 0.5, torch.randn(16, device=dev)
+        dist.broadcast(w, 0)
+        dist.broadcast(b, 0)
+        for m in (mine, ref):
+            m.weight.copy_(w)
+            m.bias.copy_(b)
+    outs = []
+    for m in (mine, ref):
+        x = torch.randn(4 + rank, 16, 5, 7, device=dev, generator=torch.Generator(device=dev).manual_seed(rank)).requires_grad_(True)
+        y = m(x)
+        (y * torch.arange(y.numel(), device=dev).view_as(y).float().cos()).sum().backward()
+        outs.append((y.detach(), x.grad, m.weight.grad, m.bias.grad, m.running_mean.clone(), m.running_var.clone()))
+    for a, b_ in zip(*outs):
+        torch.testing.assert_close(a, b_, rtol=1e-4, atol=1e-4)
+    return True
+
+
+@pytest.mark.skipif(__import__("os").environ.get("BAGUA_EXPERIMENTAL") != "1", reason="SyncBatchNorm CUDA path: opt-in until validated on hardware")
+def test_sync_batchnorm_cuda_matches_torch():
+    run_distributed(_syncbn_worker, world=min(_ngpu(), 4), use_cuda=True)
