@@ -43,7 +43,12 @@ _ALIASES = {
     "checkpoint.checkpointing": "bagua_b200.checkpoint.checkpointing",
     "model_parallel": "bagua_b200.parallel",
     "model_parallel.moe": "bagua_b200.parallel.moe",
+    "model_parallel.moe.layer": "bagua_b200.parallel.moe.layer",
+    "model_parallel.moe.sharded_moe": "bagua_b200.parallel.moe.sharded_moe",
+    "model_parallel.moe.experts": "bagua_b200.parallel.moe.experts",
+    "model_parallel.moe.utils": "bagua_b200.parallel.moe.utils",
     "moe": "bagua_b200.parallel.moe",
+    "ops": "bagua_b200.ops",
 }
 for _k, _v in _ALIASES.items():
     _m = _importlib.import_module(_v)

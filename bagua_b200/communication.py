@@ -343,6 +343,7 @@ class BaguaProcessGroup:
         self._local_of = local_of
         self._hier = None
         self._hier_failed = False
+        _named_groups[group_name] = self
 
     # torch ProcessGroup accessors ----------------------------------------------------------------------------
     def _pg_for(self, scope: str) -> Optional[dist.ProcessGroup]:
@@ -443,6 +444,7 @@ _pg_map: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
 _autotune_server = None
 _autotune_service_port = None
 _backends: Dict[str, object] = {}
+_named_groups: "weakref.WeakValueDictionary" = weakref.WeakValueDictionary()
 
 
 def _get_rank_mappings() -> Dict[int, tuple]:
@@ -593,6 +595,44 @@ def _start_autotune_server(world_size: int):
             return
         time.sleep(0.2)
     raise RuntimeError("autotune service did not come up in time")
+
+
+def start_autotune_server(service_port: int = -1):
+    """Start the autotune service on this process (reference communication.py:384-412; rank 0 calls it from
+    :func:`init_process_group` when ``BAGUA_AUTOTUNE > 0``).  Returns the server process."""
+    from .service.autotune_service import start_autotune_server_process
+
+    port = service_port if service_port and service_port > 0 else env.find_free_network_port()
+    return start_autotune_server_process(port, dist.get_world_size() if dist.is_initialized() else env.get_world_size())
+
+
+def get_hyperparameters_service_client():
+    """REST client of the running autotune service (reference communication.py:355-361)."""
+    from .service.autotune_service import AutotuneClient
+
+    port = _autotune_service_port if _autotune_service_port else env.get_bagua_service_port()
+    return AutotuneClient(env.get_master_addr(), port)
+
+
+class CommMember(object):
+    """Sentinels of the reference API (communication.py:567-570)."""
+
+    WORLD = None  # "use the default group's global communicator"
+    NON_COMM_MEMBER = object()
+
+
+def get_communicator(group_name: str, comm_name: str):
+    """The ``global`` / ``inter`` / ``intra`` communicator of a named group, or ``CommMember.NON_COMM_MEMBER`` when this rank
+    is not part of it (reference communication.py:313-352)."""
+    pg = _named_groups.get(group_name)
+    if pg is None:
+        raise KeyError(f"unknown process group {group_name!r}")
+    if comm_name not in ("global", "inter", "intra"):
+        raise ValueError("comm_name should be one of ['global', 'inter', 'intra']")
+    ranks = {"global": pg.ranks, "inter": pg.inter_ranks, "intra": pg.intra_ranks}[comm_name]
+    if dist.get_rank() not in ranks:
+        return CommMember.NON_COMM_MEMBER
+    return pg._get(comm_name)
 
 
 def init_process_group(store=None, rank: int = -1, world_size: int = -1, local_world_size: int = -1):

@@ -131,3 +131,17 @@ def _get_host_ip() -> str:
         return "127.0.0.1"
     finally:
         s.close()
+
+
+def get_host_ip() -> str:
+    """This host's outward-facing address (cached) — reference redis_store.py:216-223."""
+    global _host_ip
+    if _host_ip is None:
+        _host_ip = _get_host_ip()
+    return _host_ip
+
+
+def create_redis_client(host: str, port: int):
+    """A ``redis.Redis`` client; a server on this host is reached through loopback (reference redis_store.py:194-196)."""
+    redis = _redis()
+    return redis.Redis(port=port) if host in (get_host_ip(), "127.0.0.1", "localhost") else redis.Redis(host=host, port=port)

@@ -29,7 +29,18 @@ def to_bagua_process_group(process_group=None):
     raise Exception(f"unexpect input {type(process_group)}")
 
 
-class DistributedDataParallel_V1_9_0(torch.nn.Module):
+class DistributedDataParallel_V1_9_0_Interface(torch.nn.Module):
+    r"""The subset of PyTorch 1.9 DDP's interface that wrappers implement (reference distributed.py:19-60): ``forward``,
+    ``no_sync``, ``scatter`` / ``to_kwargs`` / ``gather`` are inherited or overridden by the concrete class."""
+
+    def no_sync(self):
+        raise NotImplementedError
+
+    def forward(self, *inputs, **kwargs):
+        raise NotImplementedError
+
+
+class DistributedDataParallel_V1_9_0(DistributedDataParallel_V1_9_0_Interface):
     r"""DDP-compatible module wrapper; the engine is ``self.inner``."""
 
     def __init__(

@@ -6,7 +6,20 @@ import torch
 from ... import communication as comm_mod
 from ...communication import ReduceOp
 
-__all__ = ["all_reduce"]
+__all__ = ["all_reduce", "torch_reduce_op_to_bagua"]
+
+
+def torch_reduce_op_to_bagua(op) -> ReduceOp:
+    """``torch.distributed.ReduceOp`` → :class:`bagua_b200.ReduceOp` (reference functional.py:22-28, extended beyond SUM/MAX)."""
+    import torch.distributed as dist
+
+    table = {dist.ReduceOp.SUM: ReduceOp.SUM, dist.ReduceOp.MAX: ReduceOp.MAX, dist.ReduceOp.MIN: ReduceOp.MIN, dist.ReduceOp.PRODUCT: ReduceOp.PRODUCT}
+    if hasattr(dist.ReduceOp, "AVG"):
+        table[dist.ReduceOp.AVG] = ReduceOp.AVG
+    for k, v in table.items():
+        if op == k:
+            return v
+    raise ValueError(f"Unexpect input={op}")
 
 
 class _AllReduce(torch.autograd.Function):

@@ -233,6 +233,27 @@ def start_autotune_server_process(port: int, world_size: int, **kwargs) -> multi
     return p
 
 
+NpEncoder = _Encoder  # name used by the reference (autotune_service.py:21-32)
+
+
+def reset_error_retry(request_func, max_retries: int = 3, delay_s: float = 1.0):
+    """Decorator: repeat a request when the connection is reset by the peer (reference autotune_service.py:306-322)."""
+    import functools
+
+    @functools.wraps(request_func)
+    def wrapper(*args, **kwargs):
+        for attempt in range(max_retries + 1):
+            try:
+                return request_func(*args, **kwargs)
+            except (ConnectionResetError, requests.exceptions.ConnectionError) as e:
+                if attempt == max_retries:
+                    raise
+                logging.warning("request failed (attempt %d): %s", attempt, e)
+                time.sleep(delay_s)
+
+    return wrapper
+
+
 class AutotuneClient:
     """REST client with keep-alive and retries (reference autotune_service.py:306-435)."""
 

@@ -153,3 +153,25 @@ class StatisticalAverage:
 
     def __str__(self) -> str:
         return str({"last_update_time": self.last_update_time, "records": self.records, "record_tail": self.record_tail})
+
+
+def apply_flattened_call(bucket: List[torch.Tensor], call, extra_args=None):
+    """Run ``call`` once on the concatenation of ``bucket`` and scatter the result back (``dist.all_reduce`` results are
+    averaged) — reference utils.py:16-28."""
+    import torch.distributed as dist
+
+    coalesced = flatten(bucket)
+    call(coalesced, *(extra_args or ()))
+    if call is dist.all_reduce:
+        coalesced /= dist.get_world_size()
+    for buf, synced in zip(bucket, unflatten(coalesced, bucket)):
+        buf.copy_(synced)
+
+
+def apply_flattened_call_all(tensors: List[torch.Tensor], call):
+    """:func:`apply_flattened_call` per tensor type (dtype + device) — reference utils.py:41-48."""
+    groups = OrderedDict()
+    for t in tensors:
+        groups.setdefault(t.type(), []).append(t)
+    for group in groups.values():
+        apply_flattened_call(group, call)
