@@ -98,3 +98,24 @@ def run_distributed(fn, world: int = 2, args=(), use_cuda: bool = False, timeout
     if errors:
         raise AssertionError("\n".join(errors))
     return [results[r] for r in range(world)]
+
+
+def run_in_session(cmd, timeout: float, **popen_kw):
+    """``subprocess.run`` for launcher commands: the command gets its own session and the whole process group is killed on
+    timeout (and swept after a normal exit), so a hung worker can never outlive the test."""
+    import signal
+    import subprocess
+
+    proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True, **popen_kw)
+    try:
+        out, err = proc.communicate(timeout=timeout)
+        return subprocess.CompletedProcess(cmd, proc.returncode, out, err)
+    except subprocess.TimeoutExpired:
+        os.killpg(proc.pid, signal.SIGKILL)
+        out, err = proc.communicate()
+        raise subprocess.TimeoutExpired(cmd, timeout, output=out, stderr=err)
+    finally:
+        try:
+            os.killpg(proc.pid, signal.SIGKILL)
+        except (ProcessLookupError, PermissionError):
+            pass

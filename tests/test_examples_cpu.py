@@ -1,7 +1,6 @@
 """The shipped examples as acceptance workloads: each runs for a few steps on CPU/gloo with two
 processes under the static launcher, exactly as a user would start it."""
 import os
-import subprocess
 import sys
 
 import pytest
@@ -24,9 +23,9 @@ CASES = {
 
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_example_runs_under_the_static_launcher(name, tmp_path):
-    from tests.mp_utils import free_port
+    from tests.mp_utils import free_port, run_in_session
 
     argv = [a.replace("{tmp}", str(tmp_path)) for a in CASES[name]]
     cmd = [sys.executable, "-m", "bagua_b200.distributed.launch", "--nproc_per_node=2", f"--master_port={free_port()}", os.path.join(REPO, argv[0]), *argv[1:]]
-    r = subprocess.run(cmd, env=ENV, cwd=str(tmp_path), capture_output=True, text=True, timeout=240)
+    r = run_in_session(cmd, 240, env=ENV, cwd=str(tmp_path))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]

@@ -1,6 +1,7 @@
 """Launchers: flag → environment mapping, static launcher failure propagation, elastic restart-all semantics
 (reference: bagua/distributed/launch.py:157-179,283-300; run.py + torch elastic)."""
 import os
+import signal
 import subprocess
 import sys
 import textwrap
@@ -44,8 +45,9 @@ def test_static_launcher_propagates_failure(tmp_path):
             sys.exit(3)
         time.sleep(30)
     """))
-    r = subprocess.run([sys.executable, "-m", "bagua_b200.distributed.launch", "--nproc_per_node=2", f"--master_port={_port()}", str(script)], env=ENV,
-                       capture_output=True, text=True, timeout=60)
+    from tests.mp_utils import run_in_session
+
+    r = run_in_session([sys.executable, "-m", "bagua_b200.distributed.launch", "--nproc_per_node=2", f"--master_port={_port()}", str(script)], 60, env=ENV)
     assert r.returncode != 0  # the surviving worker was terminated long before its 30 s sleep ended
 
 
@@ -75,13 +77,23 @@ def test_elastic_launcher_restarts_all_workers(tmp_path):
         for f in os.listdir(tmp_path):
             if f.startswith("attempts."):
                 os.remove(tmp_path / f)
+        # own session: when an attempt hangs, the launcher AND its workers are killed as one process group (no orphans)
+        proc = subprocess.Popen([sys.executable, "-m", "bagua_b200.distributed.run", "--nnodes=1", "--nproc_per_node=2", "--max_restarts=2",
+                                 "--rdzv_backend=c10d", f"--rdzv_endpoint=127.0.0.1:{_port()}", f"--rdzv_id=elastic_test{attempt}", "--monitor_interval=1",
+                                 str(script)], env=ENV, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)
         try:
-            r = subprocess.run([sys.executable, "-m", "bagua_b200.distributed.run", "--nnodes=1", "--nproc_per_node=2", "--max_restarts=2",
-                                "--rdzv_backend=c10d", f"--rdzv_endpoint=127.0.0.1:{_port()}", f"--rdzv_id=elastic_test{attempt}", "--monitor_interval=1",
-                                str(script)], env=ENV, capture_output=True, text=True, timeout=45)
+            out, err = proc.communicate(timeout=45)
+            r = subprocess.CompletedProcess(proc.args, proc.returncode, out, err)
         except subprocess.TimeoutExpired:
+            os.killpg(proc.pid, signal.SIGKILL)
+            proc.communicate()
             r = None
             continue
+        finally:
+            try:
+                os.killpg(proc.pid, signal.SIGKILL)  # stragglers of a finished attempt, if any
+            except ProcessLookupError:
+                pass
         if r.returncode == 0:
             break
     if r is None or r.returncode != 0:
