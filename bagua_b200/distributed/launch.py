@@ -73,6 +73,17 @@ def set_bagua_env(args, env: dict):
         enable_net_plugin(env)  # NCCL_NET_PLUGIN=bagua + LD_LIBRARY_PATH (reference launch.py:102-107 does the same for libnccl-net.so)
 
 
+def _die_with_parent():
+    """``preexec_fn`` of the workers (Linux): if the launcher is killed outright (SIGKILL, OOM), the kernel sends SIGTERM to the
+    worker — no orphaned ranks spinning in a collective.  The reference's launcher leaves them behind in that case."""
+    try:
+        import ctypes
+
+        ctypes.CDLL("libc.so.6", use_errno=True).prctl(1, int(signal.SIGTERM))  # PR_SET_PDEATHSIG
+    except Exception:  # noqa: BLE001 - best effort, e.g. non-glibc systems
+        pass
+
+
 def _worker_cmd(args, local_rank: int) -> List[str]:
     cmd: List[str] = []
     if not args.no_python:
@@ -114,7 +125,7 @@ def main(argv=None) -> int:
             prefix = os.path.join(args.logdir, f"node_{args.node_rank}_local_rank_{local_rank}")
             out, err = open(prefix + "_stdout", "w"), open(prefix + "_stderr", "w")
             files += [out, err]
-        procs.append(subprocess.Popen(_worker_cmd(args, local_rank), env=env, stdout=out, stderr=err))
+        procs.append(subprocess.Popen(_worker_cmd(args, local_rank), env=env, stdout=out, stderr=err, preexec_fn=_die_with_parent))
 
     def forward(signum, _frame):
         for p in procs:

@@ -104,3 +104,33 @@ def test_elastic_launcher_restarts_all_workers(tmp_path):
         attempts = sorted(int(f.split(".")[2]) for f in files if f.startswith(f"attempts.{rank}."))
         assert attempts[0] == 0 and len(attempts) >= 2 and attempts[-1] > 0, files
     assert "DONE 0" in r.stdout and "DONE 1" in r.stdout
+
+
+def test_workers_die_when_the_launcher_is_killed(tmp_path):
+    """SIGKILL the static launcher: its workers must not survive it (PR_SET_PDEATHSIG)."""
+    import signal
+    import time
+
+    script = tmp_path / "sleepy.py"
+    script.write_text("import os, time\nopen(os.environ['PIDFILE'] + os.environ['RANK'], 'w').write(str(os.getpid()))\ntime.sleep(120)\n")
+    env = dict(ENV, PIDFILE=str(tmp_path / "pid"))
+    proc = subprocess.Popen([sys.executable, "-m", "bagua_b200.distributed.launch", "--nproc_per_node=2", f"--master_port={_port()}", str(script)], env=env,
+                            start_new_session=True)
+    try:
+        deadline = time.time() + 60
+        while time.time() < deadline and not all(os.path.exists(str(tmp_path / f"pid{r}")) for r in (0, 1)):
+            time.sleep(0.1)
+        pids = [int(open(str(tmp_path / f"pid{r}")).read()) for r in (0, 1)]
+        os.kill(proc.pid, signal.SIGKILL)
+        proc.wait()
+        deadline = time.time() + 20
+        alive = pids
+        while time.time() < deadline and alive:
+            alive = [p for p in alive if os.path.exists(f"/proc/{p}") and "zombie" not in open(f"/proc/{p}/status").read().lower()]
+            time.sleep(0.2)
+        assert not alive, f"workers {alive} outlived the launcher"
+    finally:
+        try:
+            os.killpg(proc.pid, signal.SIGKILL)
+        except ProcessLookupError:
+            pass
