@@ -55,7 +55,8 @@ def reference_arm(args):
             why = f"reference python package present but its native module bagua_core is missing: {e!r}"
     if why is None:
         why = "reference arm runner not wired: baseline/_ref unexpectedly importable — rerun after inspecting it"
-    print(json.dumps({"impl": "reference", "unavailable": why}))
+    if int(os.environ.get("RANK", "0")) == 0:  # under torchrun every rank gets here: one line, from rank 0
+        print(json.dumps({"impl": "reference", "unavailable": why}))
     return 0
 
 
