@@ -89,6 +89,7 @@ class BaguaDistributedDataParallel:
         self._speed_metrics_switch_on = env.get_autotune_level() >= 1
         self._speed_metrics = StatisticalAverage()
         self._on_cuda = any(p.is_cuda for p in module.parameters())
+        self._stream_cache = 0
         self._bagua_autotune_client = None
         if env.get_autotune_level() >= 1:
             from ..service.autotune_service import AutotuneClient
@@ -101,6 +102,7 @@ class BaguaDistributedDataParallel:
         ddp = self
 
         def forward_pre_hook(mod, inputs):
+            ddp._stream_cache = ddp._consumer_stream()  # backward runs on the forward's stream: one lookup per step, not per parameter
             ddp.autograd_graph_params.clear()
             if mod.training:
                 ddp.bagua_train_step_counter += 1
@@ -428,9 +430,33 @@ class BaguaDistributedDataParallel:
 
             return hook
 
+        # Fast path for algorithms that keep the default "mark the gradient ready" hook (gradient all-reduce, ByteGrad, the fused
+        # optimizer variants): one flat closure per parameter — pointer check, one call into the scheduler with the stream
+        # cached at forward-pre — instead of four Python frames. ~400 parameters fire per BERT-large backward, on the thread
+        # that also launches the backward kernels.
+        from .algorithms.base import AlgorithmImpl
+
+        default_hook = type(self.bagua_algorithm).init_backward_hook is AlgorithmImpl.init_backward_hook and not self.find_unused_parameters
+        comm_names = getattr(self.bagua_algorithm, "_communication_tensor_names", set())
+        mark = self._bagua_backend.mark_ready_on_stream
+
+        def fast_factory(name: str, param):
+            def hook(p):
+                if not ddp.require_backward_grad_sync:
+                    return
+                bt = p._bagua_backend_tensor
+                if bt.data_ptr() != p.grad.data_ptr():
+                    raise AssertionError("bagua backend tensor data_ptr should match parameter grad")
+                mark(bt, ddp._stream_cache)
+                if not ddp._is_post_backward_callback_queued:
+                    queue_post_backward()
+
+            return hook
+
         for name, p in self.module.named_parameters():
             if p.requires_grad:
-                st._bagua_autograd_hooks.append(p.register_post_accumulate_grad_hook(factory(name)))
+                fast = default_hook and name in comm_names and hasattr(p, "_bagua_backend_tensor")
+                st._bagua_autograd_hooks.append(p.register_post_accumulate_grad_hook(fast_factory(name, p) if fast else factory(name)))
 
     def _real_post_backward_hook(self):
         self._post_backward_hook()
