@@ -12,6 +12,7 @@ import shlex
 import subprocess
 import sys
 import threading
+import time
 from typing import List
 
 
@@ -57,10 +58,24 @@ def main(argv=None) -> int:
     threads = [threading.Thread(target=pump, args=(p, c[-2]), daemon=True) for p, c in zip(procs, cmds)]
     for t in threads:
         t.start()
+    # first failure wins: a host that dies would leave the others blocked in rendezvous / collectives forever, so they are
+    # terminated (their launchers forward the signal to the workers)
     rc = 0
-    for p in procs:
-        r = p.wait()
-        rc = rc or r
+    pending = list(procs)
+    while pending:
+        for p in list(pending):
+            r = p.poll()
+            if r is None:
+                continue
+            pending.remove(p)
+            if r != 0 and rc == 0:
+                rc = r
+                for q in pending:
+                    q.terminate()
+        if pending:
+            time.sleep(0.2)
+    for t in threads:
+        t.join(timeout=2)
     return rc
 
 

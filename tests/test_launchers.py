@@ -134,3 +134,44 @@ def test_workers_die_when_the_launcher_is_killed(tmp_path):
             os.killpg(proc.pid, signal.SIGKILL)
         except ProcessLookupError:
             pass
+
+
+def _fake_ssh(tmp_path):
+    """An ``ssh`` that ignores the host and runs the remote command line locally: enough to drive baguarun end to end."""
+    d = tmp_path / "bin"
+    d.mkdir()
+    ssh = d / "ssh"
+    ssh.write_text('#!/bin/bash\n# usage: ssh [-o opt] [-p port] host command\nexec bash -c "${@: -1}"\n')
+    ssh.chmod(0o755)
+    return str(d)
+
+
+def test_baguarun_starts_one_launcher_per_host_and_propagates_failure(tmp_path):
+    from tests.mp_utils import run_in_session
+
+    env = dict(ENV, PATH=_fake_ssh(tmp_path) + os.pathsep + os.environ["PATH"], BAGUA_TEST_MARK="forwarded")
+    ok = tmp_path / "ok.py"
+    ok.write_text(textwrap.dedent(f"""
+        import os, sys
+        sys.path.insert(0, {REPO!r})
+        import torch, bagua_b200 as bagua
+        bagua.init_process_group()
+        t = torch.ones(1) * (bagua.get_rank() + 1)
+        bagua.allreduce_inplace(t)
+        assert t.item() == 3 and bagua.get_world_size() == 2 and os.environ["BAGUA_TEST_MARK"] == "forwarded"
+        print("NODE", bagua.get_node_rank(), "OK", flush=True)
+    """))
+    port = _port()
+    r = run_in_session([sys.executable, "-m", "bagua_b200.script.baguarun", "--host_list", "127.0.0.1,localhost", "--nproc_per_node", "1", "--master_port", str(port),
+                        "-x", "BAGUA_TEST_MARK", "-x", "PYTHONPATH", "-x", "BAGUA_FORCE_CPU", "-x", "CUDA_VISIBLE_DEVICES", str(ok)], 120, env=env, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "[127.0.0.1] NODE 0 OK" in r.stdout and "[localhost] NODE 1 OK" in r.stdout
+    bad = tmp_path / "bad.py"
+    bad.write_text("import os, sys, time\nif os.environ['NODE_RANK'] == '1':\n    sys.exit(5)\ntime.sleep(60)\n")
+    r = run_in_session([sys.executable, "-m", "bagua_b200.script.baguarun", "--host_list", "127.0.0.1,localhost", "--nproc_per_node", "1", "--master_port", str(_port()),
+                        "-x", "PYTHONPATH", str(bad)], 40, env=env, cwd=str(tmp_path))
+    assert r.returncode != 0      # host 1 failed → host 0's 60 s sleep was cut short
+    d = subprocess.run([sys.executable, "-m", "bagua_b200.script.baguarun", "--host_list", "a,b,c", "--nproc_per_node", "8", "--dry_run", "train.py", "--lr", "1"],
+                       env=env, capture_output=True, text=True)
+    lines = d.stdout.strip().splitlines()
+    assert len(lines) == 3 and "--nnodes=3" in lines[2] and "--node_rank=2" in lines[2] and "--master_addr=a" in lines[2] and lines[2].rstrip("'").endswith("train.py --lr 1")
