@@ -14,22 +14,29 @@ import sys
 from .bayesian_optimizer import BayesianOptimizer, IntParam
 
 
-def sysperf(host_list: str, nproc_per_node: int, ssh_port: int, env: dict, model: str = "vgg16") -> float:
+def sysperf(host_list: str, nproc_per_node: int, ssh_port: int, env: dict, model: str = "vgg16", extra_args=(), master_port: int = 0) -> float:
+    """One measurement: total img/s printed by ``bagua_sys_perf`` under ``env`` (0.0 when the run failed)."""
     full_env = dict(os.environ)
     full_env.update({k: str(v) for k, v in env.items()})
     if host_list:
         cmd = [sys.executable, "-m", "bagua_b200.script.baguarun", "--host_list", host_list, "--ssh_port", str(ssh_port), "--nproc_per_node", str(nproc_per_node)]
         for k in env:
             cmd += ["-x", k]
-        cmd += ["-m", "bagua_b200.script.bagua_sys_perf", "--model", model]
+        if master_port:
+            cmd += ["--master_port", str(master_port)]
+        cmd += ["-m", "bagua_b200.script.bagua_sys_perf", "--model", model, *extra_args]
     else:
-        cmd = [sys.executable, "-m", "bagua_b200.distributed.launch", f"--nproc_per_node={nproc_per_node}", "-m", "bagua_b200.script.bagua_sys_perf", "--model", model]
+        cmd = [sys.executable, "-m", "bagua_b200.distributed.launch", f"--nproc_per_node={nproc_per_node}"]
+        if master_port:
+            cmd.append(f"--master_port={master_port}")
+        cmd += ["-m", "bagua_b200.script.bagua_sys_perf", "--model", model, *extra_args]
     out = subprocess.run(cmd, env=full_env, capture_output=True, text=True).stdout
     m = re.search(r"Total img/sec on (\d+) (\S+)\(s\): (\d*\.\d+|\d+)", out)
     return float(m.group(3)) if m else 0.0
 
 
-def autotune_system_hyperparameters(host_list: str, nproc_per_node: int, ssh_port: int, max_samples: int = 100, model: str = "vgg16"):
+def autotune_system_hyperparameters(host_list: str, nproc_per_node: int, ssh_port: int, max_samples: int = 100, model: str = "vgg16", extra_args=(),
+                                    port_fn=None):
     optim = BayesianOptimizer(
         {
             "NCCL_MIN_NCHANNELS": IntParam(0, (0, 12)),
@@ -46,7 +53,7 @@ def autotune_system_hyperparameters(host_list: str, nproc_per_node: int, ssh_por
         env = {k: v for k, v in param.items() if k != "nccl_buffsize_2p" and v > 0}
         if param["nccl_buffsize_2p"] > 0:
             env["NCCL_BUFFSIZE"] = 2 ** param["nccl_buffsize_2p"]
-        score = sysperf(host_list, nproc_per_node, ssh_port, env, model)
+        score = sysperf(host_list, nproc_per_node, ssh_port, env, model, extra_args, port_fn() if port_fn else 0)
         if score > best[1]:
             best = (env, score)
         optim.tell(param, score)
