@@ -13,6 +13,7 @@ one)
   timeout 600 bash scripts/ncu_profile.sh; echo "ncu exit=$?" | tee -a gpurun_out/plan_one.txt
   BAGUA_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_zz_new_kernels_gpu.py -x -q > gpurun_out/pytest_new_kernels.log 2>&1; echo "new kernels exit=$?" | tee -a gpurun_out/plan_one.txt
   BAGUA_GEMM_2CTA=1 timeout 200 python benchmarks/gemm_bench.py --out gpurun_out/gemm_bench_2cta.json > gpurun_out/gemm_bench_2cta.log 2>&1; echo "gemm 2cta exit=$?" | tee -a gpurun_out/plan_one.txt
+  timeout 120 python benchmarks/torch_ddp_baseline.py --steps 30 --warmup 5 > gpurun_out/torch_ddp_n1.json 2> gpurun_out/torch_ddp_n1.err; echo "torch ddp baseline exit=$?" | tee -a gpurun_out/plan_one.txt
   timeout 120 python bench.py --steps 30 --warmup 5 > gpurun_out/bench1.json 2> gpurun_out/bench1.err; echo "bench exit=$?" | tee -a gpurun_out/plan_one.txt
   ;;
 two)
@@ -29,6 +30,8 @@ two)
 eight)
   BAGUA_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_peer_gpu.py -x -q -k "hierarchical or fused" > gpurun_out/pytest_experimental_8.log 2>&1
   echo "experimental(8) exit=$?" | tee gpurun_out/plan_eight.txt
+  timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29690 benchmarks/torch_ddp_baseline.py \
+    --steps 30 --warmup 5 > gpurun_out/torch_ddp_n8.json 2> gpurun_out/torch_ddp_n8.err; echo "torch ddp baseline(8) exit=$?" | tee -a gpurun_out/plan_eight.txt
   port=29700
   for cfg in gpt2_moe bert_bytegrad resnet50_decentralized; do
     for arm in peer nccl; do
