@@ -18,7 +18,7 @@ import torch.distributed as dist
 import torch.nn.functional as F
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from bagua_b200.models import get_model  # noqa: E402  (architecture only; fuse_epilogues=False → plain torch modules)
+from bagua_b200.models import get_model  # noqa: E402  (architecture only; the fused epilogues are switched off below)
 
 p = argparse.ArgumentParser()
 p.add_argument("--steps", type=int, default=30)
@@ -36,8 +36,10 @@ if world > 1:
     dist.init_process_group("nccl")
 torch.backends.cudnn.benchmark = True
 torch.manual_seed(1234 + rank)
-kw = {"fuse_epilogues": False} if args.model == "vgg16" else {}
-model = get_model(args.model, **kw).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
+model = get_model(args.model)
+if hasattr(model, "fuse_epilogues"):
+    model.fuse_epilogues = False  # stock eager Conv2d → ReLU → MaxPool2d modules, no bagua_b200 kernels on this arm
+model = model.to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
 if world > 1:
     model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], bucket_cap_mb=args.bucket_cap_mb, gradient_as_bucket_view=True)
 opt = torch.optim.SGD(model.parameters(), lr=0.01 * world, momentum=args.momentum)
