@@ -226,3 +226,42 @@ def test_process_group_bookkeeping():
     res = run_distributed(_pg_worker, world=2)
     for t, same, name, _ in res:
         assert torch.equal(t, torch.full((4,), 3.0)) and same and isinstance(name, str)
+
+
+def _fused_combo_worker(rank, world, name):
+    """fuse_optimizer together with an algorithm must train exactly like the unfused optimizer with the same algorithm; it
+    fuses when the optimizer owns the flat layout (bagua do_flatten=False) and silently stays unfused when the bucket arena
+    re-flattens the gradients in its own order (reference tests/contrib/test_fused_optimizer.py:317-437: 102 vs 0 fused steps)."""
+    import bagua_b200 as bagua
+    from bagua_b200.contrib import fuse_optimizer
+    from bagua_b200.parallel.algorithms import Algorithm
+
+    bagua.init_process_group()
+    outs, counts = [], []
+    for fused, bagua_flatten in ((False, True), (True, False), (True, True)):
+        torch.manual_seed(5)
+        model = nn.Sequential(nn.Linear(12, 24), nn.ReLU(), nn.Linear(24, 24), nn.ReLU(), nn.Linear(24, 4))
+        opt = torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9)
+        if fused:
+            opt = fuse_optimizer(opt, do_flatten=True)          # first fuse the optimizer, then wrap the module
+        model = model.with_bagua([opt], Algorithm.init(name), do_flatten=bagua_flatten)
+        for it in range(5):
+            x = torch.randn(8, 12, generator=torch.Generator().manual_seed(100 * it + rank))
+            opt.zero_grad()
+            model(x).pow(2).mean().backward()
+            opt.fuse_step() if fused else opt.step()
+        outs.append(torch.cat([p.detach().reshape(-1) for p in model.parameters()]))
+        counts.append(getattr(opt, "_bagua_fused_count", None))
+    return outs, counts
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("name", ["gradient_allreduce", "bytegrad", "decentralized"])
+def test_fuse_optimizer_combined_with_algorithms(name):
+    res = run_distributed(_fused_combo_worker, world=2, args=(name,), timeout=240)
+    for (plain, fused_optflat, fused_bothflat), counts in res:
+        torch.testing.assert_close(plain, fused_optflat, rtol=1e-6, atol=1e-7)
+        torch.testing.assert_close(plain, fused_bothflat, rtol=1e-6, atol=1e-7)
+        assert counts[1] >= 1, counts      # optimizer-owned flat layout → the steps were fused
