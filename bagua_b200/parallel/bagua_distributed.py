@@ -55,8 +55,10 @@ class BaguaDistributedDataParallel:
         bagua_module_name: Optional[str] = None,
         gradient_as_bucket_view: bool = True,
         find_unused_parameters: bool = False,
+        broadcast_buffers: bool = True,
     ) -> None:
         self.module = module
+        self.broadcast_buffers = broadcast_buffers
         self.bagua_module_name = bagua_module_name
         self.bagua_optimizers = optimizers
         self.process_group = process_group
@@ -149,6 +151,19 @@ class BaguaDistributedDataParallel:
         if comm.nranks() == 1:
             return
         tensors = [p.data for _, p in self.bagua_build_params()]
+        # The reference stops here (trainable, non-ignored parameters only, bagua_distributed.py:314-321). Replicas must
+        # also agree on what is NOT trained: frozen parameters and buffers (BatchNorm statistics, position tables) are
+        # synchronised like torch DDP does at construction; ignored names and MoE expert parameters stay rank-local.
+        seen = set(t.data_ptr() for t in tensors)
+        for name, p in self.module.named_parameters():
+            if not p.requires_grad and name not in self.parameters_to_ignore and not _is_moe_param(p) and p.data_ptr() not in seen:
+                seen.add(p.data_ptr())
+                tensors.append(p.data)
+        if self.broadcast_buffers:
+            for name, b in self.module.named_buffers():
+                if name not in self.parameters_to_ignore and b.numel() > 0 and b.data_ptr() not in seen:
+                    seen.add(b.data_ptr())
+                    tensors.append(b.data)
         if tensors:
             comm_mod.broadcast_coalesced(tensors, src=0, comm=comm)
         for opt in self.bagua_optimizers:

@@ -265,3 +265,73 @@ def test_fuse_optimizer_combined_with_algorithms(name):
         torch.testing.assert_close(plain, fused_optflat, rtol=1e-6, atol=1e-7)
         torch.testing.assert_close(plain, fused_bothflat, rtol=1e-6, atol=1e-7)
         assert counts[1] >= 1, counts      # optimizer-owned flat layout → the steps were fused
+
+
+class _Tied(nn.Module):
+    """Tied weights, a frozen layer, an ignored layer and a BatchNorm with buffers — the DDP corner cases of the reference's
+    lifted PyTorch suite (tests/torch_api/data_parallel/test_c10d_common.py)."""
+
+    def __init__(self):
+        super().__init__()
+        self.emb = nn.Linear(6, 6, bias=False)
+        self.frozen = nn.Linear(6, 6)
+        self.local_only = nn.Linear(6, 6)
+        self.bn = nn.BatchNorm1d(6)
+        self.out = nn.Linear(6, 6, bias=False)
+        self.out.weight = self.emb.weight           # shared parameter: must be registered once
+        for p in self.frozen.parameters():
+            p.requires_grad_(False)
+        self._bagua_params_and_buffers_to_ignore = ["local_only.weight", "local_only.bias"]
+
+    def forward(self, x):
+        return self.out(self.bn(self.local_only(self.frozen(self.emb(x)))))
+
+
+def _ddp_corner_worker(rank, world):
+    import torch.distributed as dist
+
+    import bagua_b200 as bagua
+    from bagua_b200.parallel.algorithms import gradient_allreduce
+
+    bagua.init_process_group()
+    torch.manual_seed(100 + rank)                    # different init (and BN buffers) per rank
+    model = _Tied()
+    with torch.no_grad():
+        model.bn.running_mean.fill_(float(rank + 1))
+    ref = _Tied()
+    ref.load_state_dict(model.state_dict())
+    for t in list(ref.parameters()) + list(ref.buffers()):
+        if t.dtype.is_floating_point:
+            dist.broadcast(t.data, 0)                # what with_bagua is expected to do ... except for the ignored layer
+    with torch.no_grad():
+        ref.local_only.load_state_dict(model.local_only.state_dict())
+    opt = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr=0.1)
+    ropt = torch.optim.SGD([p for p in ref.parameters() if p.requires_grad], lr=0.1)
+    model = model.with_bagua([opt], gradient_allreduce.GradientAllReduceAlgorithm())
+    names = sorted(t.bagua_tensor_name for b in model.bagua_buckets for t in b.tensors if not t.bagua_tensor_name.startswith("bagua_padding"))
+    for it in range(3):
+        x = torch.randn(8, 6, generator=torch.Generator().manual_seed(50 * it + rank))
+        for m, o, manual in ((model, opt, False), (ref, ropt, True)):
+            o.zero_grad()
+            m(x).pow(2).mean().backward()
+            if manual:
+                for n, p in ref.named_parameters():
+                    if p.grad is not None and not n.startswith("local_only"):
+                        dist.all_reduce(p.grad)
+                        p.grad /= world
+            o.step()
+    mine = {n: p.detach().clone() for n, p in model.named_parameters()}
+    want = {n: p.detach().clone() for n, p in ref.named_parameters()}
+    return names, mine, want, model.bn.running_mean.clone()
+
+
+def test_ddp_corner_cases_shared_frozen_ignored_parameters_and_buffers():
+    res = run_distributed(_ddp_corner_worker, world=2, timeout=240)
+    for names, mine, want, _ in res:
+        assert names == ["bn.bias", "bn.weight", "emb.weight"], names   # tied weight once; frozen + ignored layers not registered
+        for n in mine:
+            torch.testing.assert_close(mine[n], want[n], rtol=1e-5, atol=1e-6, msg=n)
+    # ignored parameters stay rank-local, everything else is identical on both ranks
+    assert not torch.equal(res[0][1]["local_only.weight"], res[1][1]["local_only.weight"])
+    for n in ("emb.weight", "bn.weight", "frozen.weight"):
+        assert torch.equal(res[0][1][n], res[1][1][n]), n
