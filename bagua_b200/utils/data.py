@@ -49,29 +49,36 @@ class DevicePrefetcher:
 
 
 class LossReader:
-    """Device→host read of every step's loss without stalling the launch queue: each step copies its loss into a pinned
-    slot asynchronously; ``push`` returns the value of the *previous* step (already on the host), ``flush`` the last one."""
+    """Device→host read of every step's loss without draining the launch queue: each step copies its loss into a pinned
+    slot asynchronously; ``push`` returns the value of the step ``lag`` steps back (already on the host, or nearly so),
+    ``flush`` reads whatever is still outstanding and returns the last value.  With ``lag=1`` the host may run at most one
+    step ahead of the GPU — any hiccup on the launching thread then idles the device; ``lag=2`` keeps two steps queued."""
 
-    def __init__(self, device: torch.device, slots: int = 4):
+    def __init__(self, device: torch.device, slots: int = 8, lag: int = 2):
+        assert 1 <= lag < slots
         self.buf = torch.zeros(slots, dtype=torch.float32).pin_memory()
         self.events = [torch.cuda.Event() for _ in range(slots)]
-        self.n = 0
+        self.n = 0          # losses pushed
+        self.read = 0       # losses already read on the host
         self.slots = slots
+        self.lag = lag
+        self.last: Optional[float] = None
+
+    def _read_until(self, count: int):
+        while self.read < count:
+            j = self.read % self.slots
+            self.events[j].synchronize()
+            self.last = float(self.buf[j])
+            self.read += 1
 
     def push(self, loss: torch.Tensor) -> Optional[float]:
         i = self.n % self.slots
         self.buf[i : i + 1].copy_(loss.detach().float().reshape(1), non_blocking=True)
         self.events[i].record()
         self.n += 1
-        if self.n < 2:
-            return None
-        j = (self.n - 2) % self.slots
-        self.events[j].synchronize()
-        return float(self.buf[j])
+        self._read_until(self.n - self.lag)
+        return self.last
 
     def flush(self) -> Optional[float]:
-        if self.n == 0:
-            return None
-        j = (self.n - 1) % self.slots
-        self.events[j].synchronize()
-        return float(self.buf[j])
+        self._read_until(self.n)
+        return self.last

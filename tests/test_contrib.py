@@ -181,3 +181,27 @@ def test_lightning_strategy_is_lazy_and_builds_algorithms():
         bl._build_algorithm("qadam", [torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=0.1)], {})
     custom = gradient_allreduce.GradientAllReduceAlgorithm()
     assert bl._build_algorithm(custom, [], {}) is custom
+
+
+def test_loss_reader_lags_but_reads_every_loss(monkeypatch):
+    """LossReader bookkeeping (the CUDA event / pinned-memory parts are stubbed): every pushed loss is read exactly once, in
+    order, ``lag`` steps late; ``flush`` drains the rest."""
+    from bagua_b200.utils import data as d
+
+    class FakeEvent:
+        def record(self):
+            pass
+
+        def synchronize(self):
+            pass
+
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    r = d.LossReader(torch.device("cpu"), slots=8, lag=2)
+    outs = [r.push(torch.tensor(float(i))) for i in range(20)]
+    assert outs[:4] == [None, None, 0.0, 1.0] and outs[-1] == 17.0
+    assert r.flush() == 19.0 and r.read == r.n == 20
+    r = d.LossReader(torch.device("cpu"), slots=4, lag=1)
+    assert [r.push(torch.tensor(float(i))) for i in range(6)] == [None, 0.0, 1.0, 2.0, 3.0, 4.0] and r.flush() == 5.0
+    with pytest.raises(AssertionError):
+        d.LossReader(torch.device("cpu"), slots=2, lag=2)
