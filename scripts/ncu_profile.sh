@@ -1,7 +1,9 @@
 #!/usr/bin/env bash
 # ncu captures of the top kernels (run under gpurun on ONE GPU; never wrap a multi-rank command in ncu).
 #   gpurun --timeout 900 -- 'bash scripts/ncu_profile.sh'
-# Reports land in gpurun_out/*.ncu-rep; read them offline with
+# Reports land in gpurun_out/*.ncu-rep; summarise them offline (no GPU needed) into the tracked profiles/ directory with
+#   python scripts/ncu_summary.py gpurun_out/ncu_*.ncu-rep --launches gpurun_out/launches_step.csv > profiles/ncu_summary.md
+# or read single metrics with
 #   ncu -i gpurun_out/<name>.ncu-rep --page raw --csv | grep -E 'dram__bytes_(read|write).sum|gpu__dram_throughput|sm__pipe_tensor_cycles_active|launch__registers_per_thread'
 set -euo pipefail
 mkdir -p gpurun_out
