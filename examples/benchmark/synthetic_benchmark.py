@@ -4,13 +4,16 @@
 
 Prints Horovod-style ``Img/sec per GPU`` / ``Total img/sec`` lines; timing is device-side (CUDA events, max over ranks)."""
 import argparse
+import os
+import sys
 
 import torch
 import torch.nn.functional as F
 
-import bagua_b200 as bagua
-from bagua_b200.models import get_model
-from bagua_b200.parallel.algorithms import Algorithm, q_adam
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import bagua_b200 as bagua  # noqa: E402
+from bagua_b200.models import get_model  # noqa: E402
+from bagua_b200.parallel.algorithms import Algorithm, q_adam  # noqa: E402
 
 p = argparse.ArgumentParser()
 p.add_argument("--model", default="resnet50")
@@ -23,12 +26,22 @@ p.add_argument("--fuse-optimizer", action="store_true")
 p.add_argument("--bf16", action="store_true")
 p.add_argument("--async-sync-interval", type=int, default=500)
 p.add_argument("--async-warmup-steps", type=int, default=100)
+p.add_argument("--deterministic", action="store_true", help="fixed seeds + deterministic kernels; prints the final loss (the reference's CI "
+               "compares it against a recorded value, .buildkite/scripts/benchmark_master.sh:84)")
+p.add_argument("--image-size", type=int, default=224)
+p.add_argument("--cpu", action="store_true", help="gloo + CPU tensors (smoke tests)")
 args = p.parse_args()
 
-torch.cuda.set_device(bagua.get_local_rank())
+cuda = torch.cuda.is_available() and not args.cpu
+if cuda:
+    torch.cuda.set_device(bagua.get_local_rank())
 bagua.init_process_group()
-dev = torch.device("cuda", bagua.get_local_rank())
-torch.backends.cudnn.benchmark = True
+dev = torch.device("cuda", bagua.get_local_rank()) if cuda else torch.device("cpu")
+if args.deterministic:
+    torch.manual_seed(42)
+    torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = True, False
+else:
+    torch.backends.cudnn.benchmark = True
 model = get_model(args.model).to(dev)
 if args.bf16:
     model = model.to(torch.bfloat16).to(memory_format=torch.channels_last)
@@ -43,10 +56,12 @@ model = model.with_bagua([optimizer], algorithm)
 if args.fuse_optimizer:
     optimizer = bagua.contrib.fuse_optimizer(optimizer)
 
-data = torch.randn(args.batch_size, 3, 224, 224, device=dev)
+shape = (args.batch_size, 1, 28, 28) if args.model == "mnist" else (args.batch_size, 3, args.image_size, args.image_size)
+num_classes = 10 if args.model == "mnist" else 1000
+data = torch.randn(*shape, device=dev)
 if args.bf16:
     data = data.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-target = torch.randint(0, 1000, (args.batch_size,), device=dev)
+target = torch.randint(0, num_classes, (args.batch_size,), device=dev)
 
 
 def step():
@@ -54,22 +69,37 @@ def step():
     loss = F.cross_entropy(model(data).float(), target)
     loss.backward()
     optimizer.fuse_step() if args.fuse_optimizer else optimizer.step()
+    return loss
+
+
+def timed(n):
+    """Device-timed on GPUs (CUDA events, max over ranks); wall clock on the CPU smoke path."""
+    if cuda:
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+    else:
+        import time
+
+        t0 = time.perf_counter()
+    for _ in range(n):
+        loss = step()
+    if cuda:
+        e.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+    else:
+        ms = torch.tensor([(time.perf_counter() - t0) * 1e3])
+    bagua.allreduce_inplace(ms, op=bagua.ReduceOp.MAX)
+    return ms.item(), loss
 
 
 for _ in range(args.num_warmup_batches):
     step()
 speeds = []
 for i in range(args.num_iters):
-    torch.cuda.synchronize()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    for _ in range(args.num_batches_per_iter):
-        step()
-    e.record()
-    torch.cuda.synchronize()
-    ms = torch.tensor([s.elapsed_time(e)], device=dev)
-    bagua.allreduce_inplace(ms, op=bagua.ReduceOp.MAX)
-    speeds.append(args.batch_size * args.num_batches_per_iter / (ms.item() / 1e3))
+    ms, loss = timed(args.num_batches_per_iter)
+    speeds.append(args.batch_size * args.num_batches_per_iter / (ms / 1e3))
     if bagua.get_rank() == 0:
         print(f"Iter #{i}: {speeds[-1]:.1f} img/sec per GPU")
 if args.algorithm == "async":
@@ -81,3 +111,5 @@ if bagua.get_rank() == 0:
     n = bagua.get_world_size()
     print(f"Img/sec per GPU: {m:.1f} +-{c:.1f}")
     print(f"Total img/sec on {n} GPU(s): {n * m:.1f} +-{n * c:.1f}")
+    if args.deterministic:
+        print(f"Final loss: {loss.item():.6f}")

@@ -16,6 +16,8 @@ CASES = {
     "elastic": ["examples/elastic_training/main.py", "--cpu", "--steps", "5", "--ckpt", "{tmp}/ckpt.pt"],
     "imagenet": ["examples/imagenet/main.py", "--cpu", "--synthetic", "--epochs", "1", "--steps-per-epoch", "2", "--batch-size", "2", "--num-classes", "10",
                  "--image-size", "32", "--print-freq", "1"],
+    "synthetic_benchmark": ["examples/benchmark/synthetic_benchmark.py", "--cpu", "--model", "mnist", "--deterministic", "--num-warmup-batches", "1",
+                            "--num-batches-per-iter", "2", "--num-iters", "2", "--batch-size", "4", "--algorithm", "low_precision_decentralized"],
     "squad": ["examples/squad/main.py", "--cpu", "--tiny", "--epochs", "1", "--num-synthetic", "48", "--batch-size", "4", "--max-seq-length", "64",
               "--print-freq", "2", "--algorithm", "decentralized"],
 }
