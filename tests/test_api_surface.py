@@ -135,6 +135,7 @@ def test_multiple_models_in_one_process():
 # names of the reference that are implementation details of ITS design (NCCL unique-id plumbing, Flask glue, the internals of
 # its alias-based fused optimizer) and have no counterpart by construction
 _NOT_APPLICABLE = {
+    "bagua.torch_api.contrib.cache_loader": {"BatchFetcher"},   # internal helper of the reference's loader; ours is _WriteBehind
     "bagua.torch_api.communication": {"BaguaProcessGroupPatch", "run_flask_app", "broadcast_nccl_unique_id", "comm"},
     "bagua.torch_api.contrib.fuse.optimizer": {"flatten_tensors_with_closure", "flatten_params_and_states", "group_tensors", "infer_state_tensors",
                                                "make_optimizer_instance", "fuse_step", "do_fuse", "check_optimizer", "sync_param_group_scalars",

@@ -160,6 +160,32 @@ def test_stores_and_cache():
         for k in range(10):
             assert loader.get(k, lambda key: calls.append(key) or key * 2) == k * 2
     assert len(calls) == 10
+    st = loader.stats()
+    assert st["hits"] == 10 and st["misses"] == 10 and st["queued"] == 2        # 8 entries went out as two msets, 2 still queued
+    assert loader.num_keys() == 10 and loader.stats()["queued"] == 0             # num_keys flushes first
+
+    class _Flaky:                                                               # store whose writes fail once: nothing may be lost
+        def __init__(self):
+            self.data, self.fail = {}, True
+
+        def get(self, k):
+            return self.data.get(k)
+
+        def mset(self, m):
+            if self.fail:
+                self.fail = False
+                raise ConnectionError("down")
+            self.data.update(m)
+
+        def num_keys(self):
+            return len(self.data)
+
+    flaky = CacheLoader(backend="memory", dataset_name="f", writer_buffer_size=1)
+    flaky.store = flaky._pending.store = _Flaky()
+    assert flaky.get("x", lambda k: 7) == 7 and flaky.stats()["failed_flushes"] == 1 and flaky.get("x", lambda k: 8) == 7
+    with flaky:
+        assert flaky.get("y", lambda k: 9) == 9
+    assert flaky.num_keys() == 2
     ds = _DS(20)
     cached = CachedDataset(ds, backend="tcp", dataset_name="ds", writer_buffer_size=5)
     for _ in range(3):
