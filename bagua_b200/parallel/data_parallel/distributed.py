@@ -1,10 +1,15 @@
 """``DistributedDataParallel(module, ...)`` with the constructor of ``torch.nn.parallel.DistributedDataParallel`` plus
-``optimizers=`` and ``algorithm=`` (reference: bagua/torch_api/data_parallel/distributed.py:93-360)."""
+``optimizers=`` and ``algorithm=`` (capability of the reference's bagua/torch_api/data_parallel/distributed.py:93-360).
+
+The torch-DDP compatible options travel as one ``_DDPOptions`` record: it knows which combinations this engine implements
+(``engine_supported``), which ones are handed to upstream DDP (``torch_kwargs``), and validates the module once.
+"""
 from __future__ import annotations
 
 import warnings
 from contextlib import contextmanager
-from typing import List, Optional, Union
+from dataclasses import dataclass
+from typing import Any, List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
@@ -29,9 +34,46 @@ def to_bagua_process_group(process_group=None):
     raise Exception(f"unexpect input {type(process_group)}")
 
 
+@dataclass
+class _DDPOptions:
+    """The keyword arguments of torch DDP (v1.9 signature) that the wrapper accepts."""
+
+    device_ids: Optional[Sequence[Any]] = None
+    output_device: Any = None
+    dim: int = 0
+    broadcast_buffers: bool = True
+    process_group: Any = None
+    bucket_cap_mb: int = 25
+    find_unused_parameters: bool = False
+    check_reduction: bool = False
+    gradient_as_bucket_view: bool = True
+
+    def engine_supported(self) -> bool:
+        """One device per process, batch dimension 0, buffers synchronised: what the bagua engine implements."""
+        return self.device_ids is None and self.output_device is None and self.dim == 0 and self.broadcast_buffers is True and not self.check_reduction
+
+    def torch_kwargs(self) -> dict:
+        pg = self.process_group
+        if pg is not None and not isinstance(pg, dist.ProcessGroup):
+            pg = pg.torch_group
+        return dict(device_ids=self.device_ids, output_device=self.output_device, dim=self.dim, broadcast_buffers=self.broadcast_buffers, process_group=pg,
+                    bucket_cap_mb=self.bucket_cap_mb, find_unused_parameters=self.find_unused_parameters, gradient_as_bucket_view=self.gradient_as_bucket_view)
+
+    @staticmethod
+    def check_module(module: torch.nn.Module, device_ids) -> str:
+        params = list(module.parameters())
+        if not any(p.requires_grad for p in params):
+            raise AssertionError("DistributedDataParallel is not needed when a module doesn't have any parameter that requires a gradient.")
+        if device_ids is not None and len(device_ids) > 1:
+            raise ValueError("device_ids can only be None or contain a single element.")
+        kinds = {p.device.type for p in params}
+        if len(kinds) != 1:
+            raise ValueError(f"DistributedDataParallel's input module must be on the same type of devices, but input module parameters locate in {kinds}.")
+        return kinds.pop()
+
+
 class DistributedDataParallel_V1_9_0_Interface(torch.nn.Module):
-    r"""The subset of PyTorch 1.9 DDP's interface that wrappers implement (reference distributed.py:19-60): ``forward``,
-    ``no_sync``, ``scatter`` / ``to_kwargs`` / ``gather`` are inherited or overridden by the concrete class."""
+    r"""What a PyTorch-1.9-style DDP wrapper offers: ``forward`` and ``no_sync`` (overridden by the concrete class)."""
 
     def no_sync(self):
         raise NotImplementedError
@@ -43,59 +85,24 @@ class DistributedDataParallel_V1_9_0_Interface(torch.nn.Module):
 class DistributedDataParallel_V1_9_0(DistributedDataParallel_V1_9_0_Interface):
     r"""DDP-compatible module wrapper; the engine is ``self.inner``."""
 
-    def __init__(
-        self,
-        module,
-        device_ids=None,
-        output_device=None,
-        dim=0,
-        broadcast_buffers=True,
-        process_group=None,
-        bucket_cap_mb=25,
-        find_unused_parameters=False,
-        check_reduction=False,
-        gradient_as_bucket_view=True,
-        optimizers: List[torch.optim.Optimizer] = [],
-        algorithm=None,
-    ) -> None:
+    def __init__(self, module, device_ids=None, output_device=None, dim=0, broadcast_buffers=True, process_group=None, bucket_cap_mb=25,
+                 find_unused_parameters=False, check_reduction=False, gradient_as_bucket_view=True, optimizers: Sequence[torch.optim.Optimizer] = (),
+                 algorithm=None) -> None:
         super().__init__()
-        assert any(p.requires_grad for p in module.parameters()), (
-            "DistributedDataParallel is not needed when a module doesn't have any parameter that requires a gradient."
-        )
-        if device_ids is not None and len(device_ids) > 1:
-            raise ValueError("device_ids can only be None or contain a single element.")
-        self.is_multi_device_module = len({p.device for p in module.parameters()}) > 1
-        distinct = {p.device.type for p in module.parameters()}
-        if len(distinct) != 1:
-            raise ValueError(f"DistributedDataParallel's input module must be on the same type of devices, but input module parameters locate in {distinct}.")
-        self.device_type = list(distinct)[0]
-        self.static_graph = False
-        self.dim = dim
-        self.module = module
-        self.device = next(module.parameters()).device
-        assert broadcast_buffers is True, "Not yet supported"
-        self.broadcast_buffers = broadcast_buffers
-        self.find_unused_parameters = find_unused_parameters
+        self.device_type = _DDPOptions.check_module(module, device_ids)
+        if broadcast_buffers is not True:
+            raise AssertionError("broadcast_buffers=False is not supported by the bagua engine")
+        params = list(module.parameters())
+        self.is_multi_device_module = len({p.device for p in params}) > 1
+        self.device = params[0].device
+        self.module, self.dim, self.static_graph = module, dim, False
+        self.broadcast_buffers, self.find_unused_parameters = broadcast_buffers, find_unused_parameters
         if not hasattr(module, "_bagua_module_name"):
-            module._bagua_module_name = f"{self.__class__.__name__}_{next(_name_counter)}"
+            module._bagua_module_name = f"{type(self).__name__}_{next(_name_counter)}"
         self.inner = BaguaDistributedDataParallel(
-            self.module,
-            list(optimizers),
-            algorithm if algorithm is not None else GradientAllReduceAlgorithm(),
-            process_group=to_bagua_process_group(process_group),
-            gradient_as_bucket_view=gradient_as_bucket_view,
-            find_unused_parameters=find_unused_parameters,
-            bagua_module_name=module.bagua_module_name,
-        )
-
-    @property
-    def require_backward_grad_sync(self):
-        """Gradient synchronisation switch, see :meth:`no_sync`."""
-        return self.inner.require_backward_grad_sync
-
-    @property
-    def parameters_to_ignore(self):
-        return self.inner.parameters_to_ignore
+            module, list(optimizers), algorithm if algorithm is not None else GradientAllReduceAlgorithm(),
+            process_group=to_bagua_process_group(process_group), gradient_as_bucket_view=gradient_as_bucket_view,
+            find_unused_parameters=find_unused_parameters, bagua_module_name=module.bagua_module_name, broadcast_buffers=broadcast_buffers)
 
     def forward(self, *inputs, **kwargs):
         return self.module(*inputs, **kwargs)
@@ -104,76 +111,37 @@ class DistributedDataParallel_V1_9_0(DistributedDataParallel_V1_9_0_Interface):
     def no_sync(self):
         r"""Disable gradient synchronisation inside the context; gradients accumulate locally in the bucket views and are
         communicated by the first backward after leaving it."""
-        old = self.require_backward_grad_sync
+        previous = self.inner.require_backward_grad_sync
         self.inner.require_backward_grad_sync = False
         try:
             yield
         finally:
-            self.inner.require_backward_grad_sync = old
+            self.inner.require_backward_grad_sync = previous
 
-    @property
-    def bagua_algorithm(self):
-        return self.inner.bagua_algorithm
-
-    @property
-    def bagua_optimizers(self):
-        return self.inner.bagua_optimizers
-
-    @property
-    def bagua_buckets(self):
-        return self.inner.bagua_buckets
+    # engine state surfaced on the wrapper
+    require_backward_grad_sync = property(lambda self: self.inner.require_backward_grad_sync, doc="Gradient synchronisation switch, see :meth:`no_sync`.")
+    parameters_to_ignore = property(lambda self: self.inner.parameters_to_ignore)
+    bagua_algorithm = property(lambda self: self.inner.bagua_algorithm)
+    bagua_optimizers = property(lambda self: self.inner.bagua_optimizers)
+    bagua_buckets = property(lambda self: self.inner.bagua_buckets)
 
 
-def DistributedDataParallel(
-    module: torch.nn.Module,
-    device_ids: Optional[List[Union[int, torch.device]]] = None,
-    output_device: Union[int, torch.device, None] = None,
-    dim: int = 0,
-    broadcast_buffers: bool = True,
-    process_group=None,
-    bucket_cap_mb: int = 25,
-    find_unused_parameters: bool = False,
-    check_reduction: bool = False,
-    gradient_as_bucket_view: bool = True,
-    optimizers: List[torch.optim.Optimizer] = [],
-    algorithm=None,
-):
-    r"""PyTorch-DDP-compatible constructor plus ``optimizers`` and ``algorithm``.  Unsupported DDP arguments fall back to
-    upstream ``torch.nn.parallel.DistributedDataParallel`` with a warning (reference distributed.py:319-346).
+def DistributedDataParallel(module: torch.nn.Module, device_ids=None, output_device=None, dim: int = 0, broadcast_buffers: bool = True, process_group=None,
+                            bucket_cap_mb: int = 25, find_unused_parameters: bool = False, check_reduction: bool = False,
+                            gradient_as_bucket_view: bool = True, optimizers: List[torch.optim.Optimizer] = [], algorithm=None):
+    r"""PyTorch-DDP-compatible constructor plus ``optimizers`` and ``algorithm``.  Option combinations the engine does not
+    implement fall back to upstream ``torch.nn.parallel.DistributedDataParallel`` with a warning.
 
     Example::
 
         >>> bagua_b200.init_process_group()
         >>> net = bagua_b200.data_parallel.DistributedDataParallel(model, optimizers=[opt], algorithm=ByteGradAlgorithm())
     """
-    supported = [device_ids is None, output_device is None, dim == 0, broadcast_buffers is True, check_reduction is False]
-    if not all(supported):
-        warnings.warn(
-            "Some parameters passed into BaguaDistributedDataParallel have not been supported yet. "
-            "Falling back to upstream PyTorch DistributedDataParallel."
-        )
-        return TorchDistributedDataParallel(
-            module,
-            device_ids=device_ids,
-            output_device=output_device,
-            dim=dim,
-            broadcast_buffers=broadcast_buffers,
-            process_group=process_group if isinstance(process_group, dist.ProcessGroup) or process_group is None else process_group.torch_group,
-            bucket_cap_mb=bucket_cap_mb,
-            find_unused_parameters=find_unused_parameters,
-            gradient_as_bucket_view=gradient_as_bucket_view,
-        )
-    return DistributedDataParallel_V1_9_0(
-        module,
-        device_ids=device_ids,
-        output_device=output_device,
-        dim=dim,
-        broadcast_buffers=broadcast_buffers,
-        process_group=process_group,
-        bucket_cap_mb=bucket_cap_mb,
-        find_unused_parameters=find_unused_parameters,
-        check_reduction=check_reduction,
-        gradient_as_bucket_view=gradient_as_bucket_view,
-        optimizers=optimizers,
-        algorithm=algorithm,
-    )
+    opts = _DDPOptions(device_ids, output_device, dim, broadcast_buffers, process_group, bucket_cap_mb, find_unused_parameters, check_reduction,
+                       gradient_as_bucket_view)
+    if not opts.engine_supported():
+        warnings.warn("Some parameters passed into BaguaDistributedDataParallel have not been supported yet. "
+                      "Falling back to upstream PyTorch DistributedDataParallel.")
+        return TorchDistributedDataParallel(module, **opts.torch_kwargs())
+    return DistributedDataParallel_V1_9_0(module, process_group=process_group, bucket_cap_mb=bucket_cap_mb, find_unused_parameters=find_unused_parameters,
+                                          gradient_as_bucket_view=gradient_as_bucket_view, optimizers=optimizers, algorithm=algorithm)
