@@ -100,22 +100,65 @@ def run_distributed(fn, world: int = 2, args=(), use_cuda: bool = False, timeout
     return [results[r] for r in range(world)]
 
 
-def run_in_session(cmd, timeout: float, **popen_kw):
-    """``subprocess.run`` for launcher commands: the command gets its own session and the whole process group is killed on
-    timeout (and swept after a normal exit), so a hung worker can never outlive the test."""
-    import signal
-    import subprocess
-
-    proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True, **popen_kw)
-    try:
-        out, err = proc.communicate(timeout=timeout)
-        return subprocess.CompletedProcess(cmd, proc.returncode, out, err)
-    except subprocess.TimeoutExpired:
-        os.killpg(proc.pid, signal.SIGKILL)
-        out, err = proc.communicate()
-        raise subprocess.TimeoutExpired(cmd, timeout, output=out, stderr=err)
-    finally:
+def _descendants(pid: int):
+    """Every live process whose ancestor chain contains ``pid`` (torch elastic puts its workers into their own sessions, so a
+    process-group kill alone does not reach them)."""
+    children = {}
+    for entry in os.listdir("/proc"):
+        if not entry.isdigit():
+            continue
         try:
-            os.killpg(proc.pid, signal.SIGKILL)
+            with open(f"/proc/{entry}/stat") as f:
+                fields = f.read().rsplit(")", 1)[1].split()
+            children.setdefault(int(fields[1]), []).append(int(entry))
+        except (OSError, IndexError, ValueError):
+            continue
+    out, stack = [], [pid]
+    while stack:
+        for c in children.get(stack.pop(), []):
+            out.append(c)
+            stack.append(c)
+    return out
+
+
+def kill_tree(pid: int):
+    import signal
+
+    victims = _descendants(pid)
+    for target in [pid] + victims:
+        try:
+            os.kill(target, signal.SIGKILL)
         except (ProcessLookupError, PermissionError):
             pass
+    try:
+        os.killpg(pid, signal.SIGKILL)
+    except (ProcessLookupError, PermissionError):
+        pass
+
+
+def run_in_session(cmd, timeout: float, **popen_kw):
+    """``subprocess.run`` for launcher commands: the command gets its own session and its whole process tree is killed on
+    timeout (and swept after a normal exit), so a hung worker can never outlive the test.  Output goes through temporary
+    files, not pipes: an orphan that keeps a pipe open must not be able to block the test either."""
+    import subprocess
+    import tempfile
+
+    with tempfile.TemporaryFile("w+") as out, tempfile.TemporaryFile("w+") as err:
+        proc = subprocess.Popen(cmd, stdout=out, stderr=err, text=True, start_new_session=True, **popen_kw)
+        timed_out = False
+        try:
+            proc.wait(timeout=timeout)
+        except subprocess.TimeoutExpired:
+            timed_out = True
+        finally:
+            kill_tree(proc.pid)
+            try:
+                proc.wait(timeout=10)
+            except subprocess.TimeoutExpired:
+                pass
+        out.seek(0)
+        err.seek(0)
+        stdout, stderr = out.read(), err.read()
+    if timed_out:
+        raise subprocess.TimeoutExpired(cmd, timeout, output=stdout, stderr=stderr)
+    return subprocess.CompletedProcess(cmd, proc.returncode, stdout, stderr)

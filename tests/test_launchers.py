@@ -77,23 +77,15 @@ def test_elastic_launcher_restarts_all_workers(tmp_path):
         for f in os.listdir(tmp_path):
             if f.startswith("attempts."):
                 os.remove(tmp_path / f)
-        # own session: when an attempt hangs, the launcher AND its workers are killed as one process group (no orphans)
-        proc = subprocess.Popen([sys.executable, "-m", "bagua_b200.distributed.run", "--nnodes=1", "--nproc_per_node=2", "--max_restarts=2",
-                                 "--rdzv_backend=c10d", f"--rdzv_endpoint=127.0.0.1:{_port()}", f"--rdzv_id=elastic_test{attempt}", "--monitor_interval=1",
-                                 str(script)], env=ENV, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)
+        from tests.mp_utils import run_in_session
+
         try:
-            out, err = proc.communicate(timeout=45)
-            r = subprocess.CompletedProcess(proc.args, proc.returncode, out, err)
-        except subprocess.TimeoutExpired:
-            os.killpg(proc.pid, signal.SIGKILL)
-            proc.communicate()
+            r = run_in_session([sys.executable, "-m", "bagua_b200.distributed.run", "--nnodes=1", "--nproc_per_node=2", "--max_restarts=2",
+                                "--rdzv_backend=c10d", f"--rdzv_endpoint=127.0.0.1:{_port()}", f"--rdzv_id=elastic_test{attempt}", "--monitor_interval=1",
+                                str(script)], 45, env=ENV)
+        except subprocess.TimeoutExpired:   # the whole process tree of the attempt has been killed
             r = None
             continue
-        finally:
-            try:
-                os.killpg(proc.pid, signal.SIGKILL)  # stragglers of a finished attempt, if any
-            except ProcessLookupError:
-                pass
         if r.returncode == 0:
             break
     if r is None or r.returncode != 0:
