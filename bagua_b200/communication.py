@@ -849,11 +849,24 @@ def allreduce_coalesced_inplace(tensors: Sequence[torch.Tensor], op: ReduceOp = 
                 off += t.numel()
 
 
+def _peer_engine_for(c: Communicator):
+    """The NVSwitch engine behind a global communicator when the opt-in peer collectives are enabled
+    (``BAGUA_PEER_COLLECTIVES=1``: all-gather / reduce-scatter through the peer kernels instead of NCCL)."""
+    if not _use_cuda() or os.environ.get("BAGUA_PEER_COLLECTIVES", "0") != "1":
+        return None
+    owner = c._owner() if c._owner else None
+    if owner is None or c.scope != "global":
+        return None
+    return owner.peer_engine()
+
+
 def allgather(send_tensor, recv_tensor, comm: Optional[Communicator] = None):
     c = _comm(comm)
     _check(c, send_tensor, recv_tensor)
     with _on_comm_stream(c):
-        c.allgather(send_tensor, recv_tensor)
+        eng = _peer_engine_for(c)
+        if eng is None or not eng.allgather_tensor(send_tensor, recv_tensor):
+            c.allgather(send_tensor, recv_tensor)
 
 
 def allgather_inplace(tensor, comm: Optional[Communicator] = None):
@@ -895,7 +908,9 @@ def reduce_scatter(send_tensor, recv_tensor, op: ReduceOp = ReduceOp.SUM, comm: 
     c = _comm(comm)
     _check(c, send_tensor, recv_tensor)
     with _on_comm_stream(c):
-        c.reduce_scatter(send_tensor, recv_tensor, op)
+        eng = _peer_engine_for(c) if ReduceOp(int(op)) in (ReduceOp.SUM, ReduceOp.AVG) else None
+        if eng is None or not eng.reduce_scatter_tensor(send_tensor, recv_tensor, ReduceOp(int(op)) == ReduceOp.AVG):
+            c.reduce_scatter(send_tensor, recv_tensor, op)
 
 
 def reduce_scatter_inplace(tensor, op: ReduceOp = ReduceOp.SUM, comm: Optional[Communicator] = None):

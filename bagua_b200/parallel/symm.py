@@ -288,10 +288,7 @@ class PeerEngine:
             C.run_op(op, stream, self.device.index)
             return True
         padded = _round_up(nbytes, 16 * self.world)
-        if self._workspace is None or self._workspace.nbytes < padded:
-            # collective growth: every rank sees the same message sizes
-            self._workspace = self.alloc(max(padded, 64 * 1024 ** 2))
-        ws = self._workspace
+        ws = self._ensure_workspace(padded)
         flat = ws.tensor[:nbytes].view(tensor.dtype)
         flat.copy_(tensor.reshape(-1))
         if padded > nbytes:
@@ -299,6 +296,45 @@ class PeerEngine:
         op, _ = self.make_allreduce_op(ws, ws, padded, tensor.dtype, average, "auto")
         C.run_op(op, stream, self.device.index)
         tensor.reshape(-1).copy_(flat)
+        return True
+
+    def _ensure_workspace(self, nbytes: int) -> "SymmSlice":
+        if self._workspace is None or self._workspace.nbytes < nbytes:
+            self._workspace = self.alloc(max(nbytes, 64 * 1024 ** 2))  # collective growth: every rank sees the same message sizes
+        return self._workspace
+
+    def allgather_tensor(self, send: torch.Tensor, recv: torch.Tensor) -> bool:
+        """``recv`` = concatenation of every rank's ``send`` (any dtype, moved as 16-byte vectors): own chunk → symmetric
+        workspace → ``all_gather_kernel`` (peer stores / multimem.st) → ``recv``.  False when the shape is not eligible."""
+        C = native()
+        sb = send.numel() * send.element_size()
+        if sb == 0 or sb % 16 or recv.numel() * recv.element_size() != sb * self.world or not (send.is_contiguous() and recv.is_contiguous()):
+            return False
+        total = sb * self.world
+        ws = self._ensure_workspace(total)
+        ws.tensor[self.rank * sb: (self.rank + 1) * sb].copy_(send.reshape(-1).view(torch.uint8))
+        use_mc = bool(ws.has_multicast and self.has_multicast)
+        op = C.AllGatherOp(self.comm, ws.buf, ws.offset, total, dtype_code(torch.float32), use_mc, self.launch_cfg("multimem" if use_mc else "two_shot", total))
+        C.run_op(op, torch.cuda.current_stream().cuda_stream, self.device.index)
+        recv.reshape(-1).view(torch.uint8).copy_(ws.tensor[:total])
+        return True
+
+    def reduce_scatter_tensor(self, send: torch.Tensor, recv: torch.Tensor, average: bool) -> bool:
+        """``recv`` = sum (or mean) over ranks of chunk ``rank`` of ``send``: ``send`` → symmetric workspace →
+        ``reduce_scatter_kernel`` (peer loads / multimem.ld_reduce) → ``recv``."""
+        C = native()
+        rb = recv.numel() * recv.element_size()
+        if (rb == 0 or rb % 16 or send.numel() != recv.numel() * self.world or send.dtype != recv.dtype
+                or send.dtype not in (torch.float32, torch.float16, torch.bfloat16) or not (send.is_contiguous() and recv.is_contiguous())):
+            return False
+        total = rb * self.world
+        ws = self._ensure_workspace(total)
+        ws.tensor[:total].view(send.dtype).copy_(send.reshape(-1))
+        use_mc = bool(ws.has_multicast and self.has_multicast)
+        op = C.ReduceScatterOp(self.comm, ws.buf, ws.offset, total, dtype_code(send.dtype), (1.0 / self.world) if average else 1.0, use_mc,
+                               self.launch_cfg("multimem" if use_mc else "two_shot", total))
+        C.run_op(op, torch.cuda.current_stream().cuda_stream, self.device.index)
+        recv.reshape(-1).copy_(ws.tensor[self.rank * rb: (self.rank + 1) * rb].view(recv.dtype))
         return True
 
     def barrier(self, stream: Optional[torch.cuda.Stream] = None):

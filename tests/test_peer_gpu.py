@@ -430,3 +430,44 @@ def _syncbn_worker(rank, world):
 @pytest.mark.skipif(__import__("os").environ.get("BAGUA_EXPERIMENTAL") != "1", reason="SyncBatchNorm CUDA path: opt-in until validated on hardware")
 def test_sync_batchnorm_cuda_matches_torch():
     run_distributed(_syncbn_worker, world=min(_ngpu(), 4), use_cuda=True)
+
+
+def _peer_collectives_worker(rank, world):
+    """Opt-in peer-kernel all-gather / reduce-scatter (``BAGUA_PEER_COLLECTIVES=1``) against torch.distributed."""
+    import os
+
+    import torch.distributed as dist
+
+    os.environ["BAGUA_PEER_COLLECTIVES"] = "1"
+    import bagua_b200 as bagua
+
+    bagua.init_process_group()
+    dev = torch.device("cuda", rank)
+    for dtype in (torch.float32, torch.bfloat16, torch.int64):
+        for n in (8, 4096, 1 << 20):
+            g = torch.Generator(device=dev).manual_seed(1000 * rank + n)
+            send = (torch.randn(n, device=dev, generator=g) * 100).to(dtype)
+            got = torch.empty(n * world, dtype=dtype, device=dev)
+            want = torch.empty_like(got)
+            bagua.allgather(send, got)
+            dist.all_gather_into_tensor(want, send)
+            assert torch.equal(got, want), (dtype, n)
+    for dtype in (torch.float32, torch.bfloat16):
+        for n in (8, 4096, 1 << 18):
+            g = torch.Generator(device=dev).manual_seed(7 * rank + n)
+            send = torch.randn(n * world, device=dev, generator=g).to(dtype)
+            got = torch.empty(n, dtype=dtype, device=dev)
+            want = torch.empty(n, dtype=torch.float32, device=dev)
+            bagua.reduce_scatter(send, got, op=bagua.ReduceOp.AVG)
+            dist.reduce_scatter_tensor(want, send.float())
+            want /= world
+            tol = 1e-5 if dtype == torch.float32 else 2e-2
+            torch.testing.assert_close(got.float(), want, rtol=tol, atol=tol * max(1.0, want.abs().max().item()))
+    torch.cuda.synchronize()
+    assert bagua.communication._get_default_group().peer_engine().comm.error_code() == 0
+    return True
+
+
+@pytest.mark.skipif(__import__("os").environ.get("BAGUA_EXPERIMENTAL") != "1", reason="peer all-gather / reduce-scatter: opt-in until validated on hardware")
+def test_peer_allgather_and_reduce_scatter_match_torch():
+    run_distributed(_peer_collectives_worker, world=_ngpu(), use_cuda=True)
