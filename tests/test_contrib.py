@@ -231,3 +231,62 @@ def test_loss_reader_lags_but_reads_every_loss(monkeypatch):
     assert [r.push(torch.tensor(float(i))) for i in range(6)] == [None, 0.0, 1.0, 2.0, 3.0, 4.0] and r.flush() == 5.0
     with pytest.raises(AssertionError):
         d.LossReader(torch.device("cpu"), slots=2, lag=2)
+
+
+def test_redis_store_logic_with_a_fake_redis_module(monkeypatch):
+    """RedisStore / CacheLoader(backend="redis") against an in-memory stand-in of the ``redis`` package: key sharding over several
+    servers, mset/mget routing, bootstrap-free construction from an explicit host list (reference tests/contrib/test_store.py
+    spawns real redis-server processes, which this image does not have)."""
+    import sys
+    import types
+
+    servers = {}
+
+    class FakeRedis:
+        def __init__(self, host="127.0.0.1", port=6379):
+            self.db = servers.setdefault((host, port), {})
+
+        def ping(self):
+            return True
+
+        def set(self, k, v):
+            self.db[k] = v if isinstance(v, bytes) else str(v).encode()
+
+        def get(self, k):
+            return self.db.get(k)
+
+        def mset(self, m):
+            for k, v in m.items():
+                self.set(k, v)
+
+        def mget(self, ks):
+            return [self.db.get(k) for k in ks]
+
+        def dbsize(self):
+            return len(self.db)
+
+        def flushdb(self):
+            self.db.clear()
+
+        def shutdown(self, nosave=True):
+            pass
+
+    monkeypatch.setitem(sys.modules, "redis", types.SimpleNamespace(Redis=FakeRedis))
+    from bagua_b200.contrib.utils.redis_store import RedisStore
+
+    hosts = [{"host": "10.0.0.1", "port": 7000}, {"host": "10.0.0.2", "port": 7000}, {"host": "10.0.0.3", "port": 7001}]
+    store = RedisStore(hosts=hosts, cluster_mode=True)
+    data = {f"key{i}": f"value{i}".encode() for i in range(200)}
+    store.mset(data)
+    assert store.num_keys() == 200 and store.status()
+    assert store.mget(list(data)[:50]) == list(data.values())[:50]
+    assert store.get("key7") == b"value7" and store.get("missing") is None
+    sizes = sorted(len(db) for db in servers.values())
+    assert len(servers) == 3 and sizes[0] > 30                      # keys are spread over all three servers, none starved
+    store.set("solo", b"x")
+    assert sum("solo" in db for db in servers.values()) == 1        # each key lives on exactly one shard
+    loader = CacheLoader(backend="redis", dataset_name="r", writer_buffer_size=3, hosts=hosts, cluster_mode=True)
+    assert [loader.get(i, lambda k: k * 3) for i in range(7)] == [i * 3 for i in range(7)]
+    assert loader.num_keys() == 208 and [loader.get(i, lambda k: -1) for i in range(7)] == [i * 3 for i in range(7)]
+    store.clear()
+    assert store.num_keys() == 0
