@@ -171,3 +171,31 @@ def _virtual_nodes_worker(rank, world):
 def test_virtual_multi_node_groups_and_hierarchical_allreduce():
     for t in run_distributed(_virtual_nodes_worker, world=4):
         assert torch.allclose(t, torch.full((10,), 2.5))
+
+
+def _explicit_store_worker(rank, world):
+    """``init_process_group(store=..., rank=..., world_size=..., local_world_size=...)``: no env:// rendezvous involved."""
+    import datetime
+    import os
+
+    import torch
+    import torch.distributed as dist
+
+    import bagua_b200 as bagua
+
+    port = int(os.environ["MASTER_PORT"])
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE"):   # nothing may be read from the launcher environment
+        os.environ.pop(k, None)
+    store = dist.TCPStore("127.0.0.1", port, world, is_master=(rank == 0), timeout=datetime.timedelta(seconds=60))
+    bagua.init_process_group(store=store, rank=rank, world_size=world, local_world_size=world)
+    assert bagua.get_rank() == rank and bagua.get_world_size() == world and bagua.get_local_size() == world
+    t = torch.full((3,), float(rank))
+    bagua.allreduce_inplace(t, op=bagua.ReduceOp.SUM)
+    objs = bagua.broadcast_object({"from": rank}, src=1)
+    return t, objs
+
+
+def test_init_process_group_with_an_explicit_store():
+    res = run_distributed(_explicit_store_worker, world=2)
+    for t, obj in res:
+        assert torch.equal(t, torch.full((3,), 1.0)) and obj == {"from": 1}
