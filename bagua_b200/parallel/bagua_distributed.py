@@ -88,7 +88,9 @@ class BaguaDistributedDataParallel:
 
         self._bagua_backend = comm_mod.get_backend(self.bagua_module_name)
         self._bagua_hyperparameters = BaguaHyperparameter()
-        self._speed_metrics_switch_on = env.get_autotune_level() >= 1
+        self._report_metrics = env.is_report_metrics_switch_on()   # BAGUA_REPORT_METRICS / --report_metrics
+        self._report_every = 100
+        self._speed_metrics_switch_on = env.get_autotune_level() >= 1 or self._report_metrics
         self._speed_metrics = StatisticalAverage()
         self._on_cuda = any(p.is_cuda for p in module.parameters())
         self._stream_cache = 0
@@ -114,6 +116,8 @@ class BaguaDistributedDataParallel:
                 ddp._record_speed_metrics_event()
                 if ddp._bagua_autotune_client is not None and not ddp._bagua_autotune_completed:
                     ddp._bagua_autotune_step()
+                if ddp._report_metrics:
+                    ddp._log_metrics()
             ddp._is_post_backward_callback_queued = False
 
         module._bagua_states._bagua_framework_hooks.append(module.register_forward_pre_hook(forward_pre_hook))
@@ -364,6 +368,20 @@ class BaguaDistributedDataParallel:
     # ---------------------------------------------------------------------------------------------------------
     # per-bucket communication profile
     # ---------------------------------------------------------------------------------------------------------
+    def _log_metrics(self):
+        """``BAGUA_REPORT_METRICS=1``: every ``_report_every`` training steps rank 0 logs the smoothed communication speed and
+        the per-bucket profile (the reference defines the switch, env.py:88-92, but nothing consumes it)."""
+        step = self.bagua_train_step_counter
+        if step == 1:
+            self.comm_profile(True)
+        if step % self._report_every or env.get_rank() != 0:
+            return
+        rows = self.comm_report(reset=True)
+        speed = self._speed_metrics.get(30.0)
+        logger.warning("[bagua metrics] module=%s step=%d comm_speed=%.3f GiB/s buckets=%s", self.bagua_module_name, step, speed,
+                       [{k: (round(v, 3) if isinstance(v, float) else v) for k, v in r.items() if k in ("bucket", "variant", "bytes", "launches", "mean_ms", "algbw_GBps")}
+                        for r in rows])
+
     def comm_profile(self, enable: bool = True):
         """Start / stop measuring every bucket's communication program (timing events on the comm stream, see
         ``Backend::set_profile``).  Costs two event records per bucket launch; off by default."""

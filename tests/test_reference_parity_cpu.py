@@ -335,3 +335,35 @@ def test_ddp_corner_cases_shared_frozen_ignored_parameters_and_buffers():
     assert not torch.equal(res[0][1]["local_only.weight"], res[1][1]["local_only.weight"])
     for n in ("emb.weight", "bn.weight", "frozen.weight"):
         assert torch.equal(res[0][1][n], res[1][1][n]), n
+
+
+def test_report_metrics_switch_logs_per_bucket_profile(tmp_path):
+    """``BAGUA_REPORT_METRICS=1`` (launcher flag ``--report_metrics``) has a consumer here: periodic per-bucket communication report."""
+    import os
+    import subprocess
+    import sys
+    import textwrap
+
+    from tests.mp_utils import free_port
+
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "m.py"
+    script.write_text(textwrap.dedent(f"""
+        import sys
+        sys.path.insert(0, {repo!r})
+        import torch, bagua_b200 as bagua
+        from bagua_b200.parallel.algorithms import gradient_allreduce
+        bagua.init_process_group()
+        m = torch.nn.Linear(8, 8)
+        opt = torch.optim.SGD(m.parameters(), lr=0.1)
+        m = m.with_bagua([opt], gradient_allreduce.GradientAllReduceAlgorithm())
+        m.bagua_ddp._report_every = 4
+        for i in range(9):
+            opt.zero_grad(); m(torch.randn(2, 8)).sum().backward(); opt.step()
+    """))
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(free_port()), BAGUA_FORCE_CPU="1",
+               CUDA_VISIBLE_DEVICES="", BAGUA_REPORT_METRICS="1")
+    r = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in (r.stdout + r.stderr).splitlines() if "[bagua metrics]" in ln]
+    assert len(lines) == 2 and "step=4" in lines[0] and "step=8" in lines[1] and "'launches': 4" in lines[1], lines
