@@ -92,8 +92,26 @@ def _compile_one(src: Path, stamp: str, verbose: bool) -> tuple[Path, bool]:
     return obj, True
 
 
+STAMP = PKG_DIR / "_C.so.stamp"
+
+
+def _tree_stamp() -> str:
+    """Hash of every source, header and flag that goes into ``_C.so``."""
+    h = hashlib.sha1(_deps_stamp().encode())
+    for src in _sources():
+        h.update(src.name.encode())
+        h.update(src.read_bytes())
+    return h.hexdigest()
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every source under csrc/ for sm_100a and link ``bagua_b200/_C.so`` (incremental)."""
+    """Compile every source under csrc/ for sm_100a and link ``bagua_b200/_C.so`` (incremental).
+
+    The object cache (``csrc/build``) does not travel with a snapshot of the tree, the library and its stamp do: when the
+    stamp matches the sources nothing is compiled, so a GPU box that received a current ``_C.so`` starts immediately."""
+    stamp = _tree_stamp()
+    if not force and TARGET.exists() and STAMP.exists() and STAMP.read_text().strip() == stamp:
+        return TARGET
     if not Path(NVCC).exists():
         raise RuntimeError(f"nvcc not found at {NVCC}; set CUDA_HOME")
     OBJ_DIR.mkdir(parents=True, exist_ok=True)
@@ -114,6 +132,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    STAMP.write_text(_tree_stamp() + "\n")
     return TARGET
 
 
