@@ -290,3 +290,26 @@ def test_redis_store_logic_with_a_fake_redis_module(monkeypatch):
     assert loader.num_keys() == 208 and [loader.get(i, lambda k: -1) for i in range(7)] == [i * 3 for i in range(7)]
     store.clear()
     assert store.num_keys() == 0
+
+
+def test_fused_op_entry_points_fall_back_on_cpu():
+    """ops.nhwc / ops.gemm front-ends on tensors the sm_100a kernels do not cover (CPU, fp32): plain torch results and gradients."""
+    from bagua_b200.ops.gemm import grouped_linear
+    from bagua_b200.ops.nhwc import bias_relu, bias_relu_maxpool2, conv_bias_relu
+
+    torch.manual_seed(0)
+    conv = torch.nn.Conv2d(3, 8, 3, padding=1)
+    x = torch.randn(2, 3, 8, 8)
+    torch.testing.assert_close(conv_bias_relu(x, conv), torch.relu(conv(x)))
+    torch.testing.assert_close(conv_bias_relu(x, conv, pool=True), torch.nn.functional.max_pool2d(torch.relu(conv(x)), 2))
+    y, b = torch.randn(2, 8, 4, 4), torch.randn(8)
+    torch.testing.assert_close(bias_relu(y.clone(), b), torch.relu(y + b.view(1, -1, 1, 1)))
+    torch.testing.assert_close(bias_relu_maxpool2(y.clone(), b), torch.nn.functional.max_pool2d(torch.relu(y + b.view(1, -1, 1, 1)), 2))
+    xg, w, bias = torch.randn(3, 16, 8, requires_grad=True), torch.randn(3, 4, 8, requires_grad=True), torch.randn(3, 4, requires_grad=True)
+    out = grouped_linear(xg, w, bias)
+    ref = torch.einsum("gmk,gnk->gmn", xg, w) + bias.unsqueeze(1)
+    torch.testing.assert_close(out, ref)
+    g1 = torch.autograd.grad(out.pow(2).sum(), (xg, w, bias))
+    g2 = torch.autograd.grad(ref.pow(2).sum(), (xg, w, bias))
+    for a, c in zip(g1, g2):
+        torch.testing.assert_close(a, c)
