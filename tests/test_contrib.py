@@ -313,3 +313,25 @@ def test_fused_op_entry_points_fall_back_on_cpu():
     g2 = torch.autograd.grad(ref.pow(2).sum(), (xg, w, bias))
     for a, c in zip(g1, g2):
         torch.testing.assert_close(a, c)
+
+
+def test_model_zoo_matches_the_published_architectures():
+    """Parameter counts of the BASELINE models (built on the meta device — no memory): VGG16 and ResNet-50 equal torchvision's,
+    BERT-large + QA head equals HuggingFace's ``BertForQuestionAnswering`` (no pooler)."""
+    from bagua_b200 import models
+
+    with torch.device("meta"):
+        counts = {
+            "vgg16": sum(p.numel() for p in models.vgg16().parameters()),
+            "resnet50": sum(p.numel() for p in models.resnet50().parameters()),
+            "bert_large_qa": sum(p.numel() for p in models.BertForQuestionAnswering(models.bert_large_config()).parameters()),
+        }
+        moe = models.GPT2MoE(models.gpt2_medium_moe8_config(), world_size=8)
+    assert counts == {"vgg16": 138_357_544, "resnet50": 25_557_032, "bert_large_qa": 334_094_338}
+    experts = [p for p in moe.parameters() if getattr(p, "expert", False)]
+    assert experts and all(p.expert for p in experts) and sum(p.numel() for p in moe.parameters()) > 300e6
+    tiny = models.GPT2MoE(models.GPT2MoEConfig(vocab_size=128, n_positions=16, n_embd=32, n_layer=2, n_head=2, num_experts=2), world_size=1)
+    idx = torch.randint(0, 128, (2, 16))
+    loss, _ = tiny(idx, idx)
+    loss.backward()
+    assert torch.isfinite(loss) and all(p.grad is not None for p in tiny.parameters() if p.requires_grad)
