@@ -126,6 +126,8 @@ class FusedGradientAllReduceAlgorithmImpl(GradientAllReduceAlgorithmImpl):
         return [BaguaBucket(b, flatten=True, name=str(i), alignment=max(1, 16 // es), group=self.process_group) for i, b in enumerate(tensors)]
 
     def init_operations(self, bagua_ddp, bucket):
+        import os
+
         import torch
 
         from ...core import dtype_code, native
@@ -167,6 +169,8 @@ class FusedGradientAllReduceAlgorithmImpl(GradientAllReduceAlgorithmImpl):
         momentum = torch.zeros(vpr * per, dtype=torch.float32, device=flat.device)
         # NVLS whenever the fabric offers it (the variant validated on 2 and 8 GPUs); peer ld/st two-shot otherwise
         use_mc = bool(wslice.has_multicast and bucket._slice.has_multicast and eng.has_multicast)
+        if os.environ.get("BAGUA_FUSED_MULTIMEM", "auto") == "0":   # experiment switch: peer ld/st flavour of the fused kernel
+            use_mc = False
         # 16 CTAs: the configuration measured at 56 994 img/s on 8 GPUs (profiles/bench8_fused.json); the kernel also streams
         # the fp32 optimizer shard, so it wants more CTAs than the bare multimem allreduce (8)
         cfg = eng.launch_cfg("multimem" if use_mc else "two_shot", nbytes, blocks=16 if use_mc else 32)
