@@ -173,7 +173,7 @@ class FusedGradientAllReduceAlgorithmImpl(GradientAllReduceAlgorithmImpl):
             use_mc = False
         # 16 CTAs: the configuration measured at 56 994 img/s on 8 GPUs (profiles/bench8_fused.json); the kernel also streams
         # the fp32 optimizer shard, so it wants more CTAs than the bare multimem allreduce (8)
-        cfg = eng.launch_cfg("multimem" if use_mc else "two_shot", nbytes, blocks=16 if use_mc else 32)
+        cfg = eng.launch_cfg("multimem" if use_mc else "two_shot", nbytes, blocks=int(os.environ.get("BAGUA_FUSED_BLOCKS", "0")) or (16 if use_mc else 32))
         scale = (1.0 / n) if self.average else 1.0
         if is_adam:
             second = torch.zeros(vpr * per, dtype=torch.float32, device=flat.device)
