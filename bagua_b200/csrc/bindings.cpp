@@ -286,6 +286,19 @@ PYBIND11_MODULE(_C, m) {
         launch_bias_relu_nhwc_bwd(reinterpret_cast<const void*>(g), reinterpret_cast<const void*>(y), reinterpret_cast<void*>(gout),
                                   reinterpret_cast<float*>(bias_grad), rows, C, dtype, S(stream));
     });
+    m.def("bias_relu_nhwc_bwd_fin",
+          [](uint64_t g, uint64_t y, uint64_t gout, uint64_t ws, uint64_t bias_grad_out, uint64_t ticket, size_t rows, int C, int dtype, uint64_t stream) {
+              launch_bias_relu_nhwc_bwd(reinterpret_cast<const void*>(g), reinterpret_cast<const void*>(y), reinterpret_cast<void*>(gout),
+                                        reinterpret_cast<float*>(ws), rows, C, dtype, S(stream), reinterpret_cast<void*>(bias_grad_out),
+                                        reinterpret_cast<unsigned int*>(ticket));
+          });
+    m.def("bias_relu_pool_nhwc_bwd_fin",
+          [](uint64_t g, uint64_t out, uint64_t idx, uint64_t gin, uint64_t ws, uint64_t bias_grad_out, uint64_t ticket, int N, int H, int W, int C, int dtype,
+             uint64_t stream) {
+              launch_bias_relu_pool_nhwc_bwd(reinterpret_cast<const void*>(g), reinterpret_cast<const void*>(out), reinterpret_cast<const uint8_t*>(idx),
+                                             reinterpret_cast<void*>(gin), reinterpret_cast<float*>(ws), N, H, W, C, dtype, S(stream),
+                                             reinterpret_cast<void*>(bias_grad_out), reinterpret_cast<unsigned int*>(ticket));
+          });
     m.def("bias_relu_pool_nhwc_fwd", [](uint64_t x, uint64_t bias, uint64_t out, uint64_t idx, int N, int H, int W, int C, int dtype, uint64_t stream) {
         launch_bias_relu_pool_nhwc_fwd(reinterpret_cast<const void*>(x), reinterpret_cast<const void*>(bias), reinterpret_cast<void*>(out),
                                        reinterpret_cast<uint8_t*>(idx), N, H, W, C, dtype, S(stream));

@@ -57,11 +57,14 @@ void launch_peer_barrier(const PeerCtx& ctx, cudaStream_t stream);
 
 // ---- fused NHWC conv-block epilogues (nhwc_fused.cu); tensors are [N,H,W,C] f16/bf16, rows = N*H*W --------------------
 void launch_bias_relu_nhwc_fwd(void* y, const void* bias, size_t rows, int C, int dtype, cudaStream_t stream);
-void launch_bias_relu_nhwc_bwd(const void* g, const void* y, void* gout, float* bias_grad, size_t rows, int C, int dtype, cudaStream_t stream);
+// bias_grad_out/ticket == nullptr: `bias_grad` (fp32, zeroed by the caller) receives the channel sums.  Otherwise `bias_grad` is a
+// zeroed fp32 workspace that the kernel leaves zeroed again, the sums land in `bias_grad_out` (tensor dtype), `ticket` is a zeroed counter.
+void launch_bias_relu_nhwc_bwd(const void* g, const void* y, void* gout, float* bias_grad, size_t rows, int C, int dtype, cudaStream_t stream,
+                               void* bias_grad_out = nullptr, unsigned int* ticket = nullptr);
 void launch_bias_relu_pool_nhwc_fwd(const void* x, const void* bias, void* out, uint8_t* idx, int N, int H, int W, int C, int dtype,
                                     cudaStream_t stream);
 void launch_bias_relu_pool_nhwc_bwd(const void* g, const void* out, const uint8_t* idx, void* gin, float* bias_grad, int N, int H, int W, int C,
-                                    int dtype, cudaStream_t stream);
+                                    int dtype, cudaStream_t stream, void* bias_grad_out = nullptr, unsigned int* ticket = nullptr);
 
 // ---- tcgen05 grouped GEMM (gemm_tcgen05.cu) ----------------------------------------------------------------------
 // C[g] = act(A[g]·B[g]^T + bias[g]); A [G,M,K], B [G,N,K], C [G,M,N] bf16 (K-contiguous operands), bias fp32 [G,N] or null; act: 0 none, 1 GELU(tanh)

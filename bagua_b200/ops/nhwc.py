@@ -2,6 +2,8 @@
 single-pass forward and backward (the backward also produces the bias gradient, so the convolution runs bias-free)."""
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -17,6 +19,27 @@ def fused_supported(x: torch.Tensor, channels: int) -> bool:
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+_MAX_C = 2048
+_workspaces = {}
+
+
+def _finish_in_kernel() -> bool:
+    """Opt-in (``BAGUA_NHWC_FINALIZE=1``): the backward kernels finish the bias-gradient reduction themselves (last CTA converts
+    the fp32 sums and re-zeroes the workspace) instead of a ``zeros`` fill before and a dtype cast after every launch."""
+    return os.environ.get("BAGUA_NHWC_FINALIZE", "0") == "1"
+
+
+def _workspace(device: torch.device, stream: int) -> torch.Tensor:
+    """Zeroed fp32[2048] sums + one uint32 ticket, per (device, stream): kernels on one stream run back to back and each one
+    hands the buffer back zeroed, so it is allocated and cleared exactly once."""
+    key = (device.index, stream)
+    ws = _workspaces.get(key)
+    if ws is None:
+        ws = torch.zeros(_MAX_C + 4, dtype=torch.float32, device=device)
+        _workspaces[key] = ws
+    return ws
 
 
 class _BiasReLU(torch.autograd.Function):
@@ -35,6 +58,13 @@ class _BiasReLU(torch.autograd.Function):
         N, C, H, W = y.shape
         g = g.contiguous(memory_format=torch.channels_last)
         gout = torch.empty_like(g, memory_format=torch.channels_last)
+        if _finish_in_kernel():
+            stream = _stream()
+            ws = _workspace(y.device, stream)
+            bias_grad = torch.empty(C, dtype=ctx.bias_dtype, device=y.device)
+            native().bias_relu_nhwc_bwd_fin(g.data_ptr(), y.data_ptr(), gout.data_ptr(), ws.data_ptr(), bias_grad.data_ptr(), ws.data_ptr() + 4 * _MAX_C,
+                                            N * H * W, C, dtype_code(y.dtype), stream)
+            return gout, bias_grad
         bg = torch.zeros(C, dtype=torch.float32, device=y.device)
         native().bias_relu_nhwc_bwd(g.data_ptr(), y.data_ptr(), gout.data_ptr(), bg.data_ptr(), N * H * W, C, dtype_code(y.dtype), _stream())
         return gout, bg.to(ctx.bias_dtype)
@@ -58,6 +88,13 @@ class _BiasReLUMaxPool2(torch.autograd.Function):
         N, C, H, W = ctx.in_shape
         g = g.contiguous(memory_format=torch.channels_last)
         gin = torch.empty((N, C, H, W), dtype=out.dtype, device=out.device, memory_format=torch.channels_last)
+        if _finish_in_kernel():
+            stream = _stream()
+            ws = _workspace(out.device, stream)
+            bias_grad = torch.empty(C, dtype=ctx.bias_dtype, device=out.device)
+            native().bias_relu_pool_nhwc_bwd_fin(g.data_ptr(), out.data_ptr(), idx.data_ptr(), gin.data_ptr(), ws.data_ptr(), bias_grad.data_ptr(),
+                                                 ws.data_ptr() + 4 * _MAX_C, N, H, W, C, dtype_code(out.dtype), stream)
+            return gin, bias_grad
         bg = torch.zeros(C, dtype=torch.float32, device=out.device)
         native().bias_relu_pool_nhwc_bwd(g.data_ptr(), out.data_ptr(), idx.data_ptr(), gin.data_ptr(), bg.data_ptr(), N, H, W, C, dtype_code(out.dtype),
                                          _stream())

@@ -58,3 +58,26 @@ print("2CTA_OK")
 ''' % repo
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, BAGUA_GEMM_2CTA="1"), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "2CTA_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.skipif(__import__("os").environ.get("BAGUA_EXPERIMENTAL") != "1", reason="in-kernel bias-gradient finish: opt-in until validated on hardware")
+def test_nhwc_backward_with_in_kernel_bias_grad_finish(dev, monkeypatch):
+    """BAGUA_NHWC_FINALIZE=1 (last CTA converts the fp32 sums, workspace handed back zeroed) must equal the fill + kernel + cast path,
+    repeatedly on the same stream (the workspace is reused without clearing)."""
+    from bagua_b200.ops.nhwc import bias_relu, bias_relu_maxpool2
+
+    torch.manual_seed(4)
+    for C, H in [(64, 56), (512, 14), (2048, 4)]:
+        x = torch.randn(8, C, H, H, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        b = torch.randn(C, device=dev).to(torch.bfloat16)
+        for fn in (bias_relu, bias_relu_maxpool2):
+            res = []
+            for fin in ("0", "1", "1"):
+                monkeypatch.setenv("BAGUA_NHWC_FINALIZE", fin)
+                xi, bi = x.clone().requires_grad_(True), b.clone().requires_grad_(True)
+                out = fn(xi * 1.0, bi)
+                out.float().pow(2).sum().backward()
+                res.append((out.detach().float(), xi.grad.float(), bi.grad.float()))
+            for other in res[1:]:
+                for a, c in zip(res[0], other):
+                    torch.testing.assert_close(a, c, rtol=2e-2, atol=2e-2 * max(1.0, a.abs().max().item()))
