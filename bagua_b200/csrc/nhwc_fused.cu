@@ -15,6 +15,7 @@
 
 #include "kernels.h"
 #include "peer.cuh"
+#include "quant.cuh"
 
 namespace bagua {
 using namespace dev;
