@@ -15,6 +15,9 @@ one)
   BAGUA_GEMM_2CTA=1 timeout 200 python benchmarks/gemm_bench.py --out gpurun_out/gemm_bench_2cta.json > gpurun_out/gemm_bench_2cta.log 2>&1; echo "gemm 2cta exit=$?" | tee -a gpurun_out/plan_one.txt
   timeout 120 python benchmarks/torch_ddp_baseline.py --steps 30 --warmup 5 > gpurun_out/torch_ddp_n1.json 2> gpurun_out/torch_ddp_n1.err; echo "torch ddp baseline exit=$?" | tee -a gpurun_out/plan_one.txt
   timeout 120 python bench.py --steps 30 --warmup 5 > gpurun_out/bench1.json 2> gpurun_out/bench1.err; echo "bench exit=$?" | tee -a gpurun_out/plan_one.txt
+  # A/B of the host-overhead experiment (only meaningful if the gated test above passed)
+  BAGUA_NHWC_FINALIZE=1 timeout 120 python bench.py --steps 30 --warmup 5 > gpurun_out/bench1_nhwc_finalize.json 2> gpurun_out/bench1_nhwc_finalize.err
+  echo "bench (nhwc finalize) exit=$?" | tee -a gpurun_out/plan_one.txt
   ;;
 two)
   # opt-in kernels written without hardware access in round 1: fused GEMM+combine, fused allreduce+Adam, mixed-precision Adam
