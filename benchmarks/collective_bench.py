@@ -20,6 +20,7 @@ p.add_argument("--dtype", default="bf16")
 p.add_argument("--iters", type=int, default=20)
 p.add_argument("--sizes", default="65536,1048576,16777216,134217728,268435456")
 p.add_argument("--blocks", default="4,8,16,32,64")
+p.add_argument("--rs-ag", action="store_true", help="also time the split reduce-scatter / all-gather kernels (hierarchical path, blocking API) vs NCCL")
 args = p.parse_args()
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -70,15 +71,29 @@ for nbytes in [int(x) for x in args.sizes.split(",")]:
             op, chosen = eng.make_allreduce_op(sl, sl, nbytes, dtype, True, v, blocks=nb)
             ms = timeit(lambda: C.run_op(op, stream, local), args.iters)
             results.append({"bytes": nbytes, "variant": chosen, "blocks": nb, "ms": ms})
+    if args.rs_ag and nbytes % (16 * world) == 0:
+        from bagua_b200.core import dtype_code
+
+        shard = torch.empty(numel // world, dtype=dtype, device=dev)
+        for name, fn in (("nccl_reduce_scatter", lambda: dist.reduce_scatter_tensor(shard, x)), ("nccl_all_gather", lambda: dist.all_gather_into_tensor(x, shard))):
+            results.append({"bytes": nbytes, "variant": name, "blocks": 0, "ms": timeit(fn, args.iters), "half": True})
+        use_mc = bool(sl.has_multicast and eng.has_multicast)
+        for nb in [int(b) for b in args.blocks.split(",")]:
+            cfg = eng.launch_cfg("multimem" if use_mc else "two_shot", nbytes, blocks=nb)
+            rs = C.ReduceScatterOp(eng.comm, sl.buf, sl.offset, nbytes, dtype_code(dtype), 1.0 / world, use_mc, cfg)
+            ag = C.AllGatherOp(eng.comm, sl.buf, sl.offset, nbytes, dtype_code(dtype), use_mc, cfg)
+            suffix = "_multimem" if use_mc else "_peer"
+            results.append({"bytes": nbytes, "variant": "reduce_scatter" + suffix, "blocks": nb, "ms": timeit(lambda: C.run_op(rs, stream, local), args.iters), "half": True})
+            results.append({"bytes": nbytes, "variant": "all_gather" + suffix, "blocks": nb, "ms": timeit(lambda: C.run_op(ag, stream, local), args.iters), "half": True})
     sl.free()
 
 if rank == 0:
     for r in results:
         r["algbw_GBs"] = r["bytes"] / r["ms"] / 1e6
-        r["busbw_GBs"] = r["algbw_GBs"] * 2 * (world - 1) / world
-    print(f"{'bytes':>12} {'variant':>10} {'blocks':>6} {'ms':>9} {'algbw GB/s':>11} {'busbw GB/s':>11}")
+        r["busbw_GBs"] = r["algbw_GBs"] * (1 if r.get("half") else 2) * (world - 1) / world
+    print(f"{'bytes':>12} {'variant':>24} {'blocks':>6} {'ms':>9} {'algbw GB/s':>11} {'busbw GB/s':>11}")
     for r in results:
-        print(f"{r['bytes']:>12} {r['variant']:>10} {r['blocks']:>6} {r['ms']:>9.4f} {r['algbw_GBs']:>11.1f} {r['busbw_GBs']:>11.1f}")
+        print(f"{r['bytes']:>12} {r['variant']:>24} {r['blocks']:>6} {r['ms']:>9.4f} {r['algbw_GBs']:>11.1f} {r['busbw_GBs']:>11.1f}")
     if args.out:
         os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
         with open(args.out, "w") as f:
