@@ -79,6 +79,74 @@ class BaguaBucketPy:
     def append_python_op(self, op):
         self.inner.append_python_op(op, "python")
 
+    # -- the reference's low-level op builders (bagua-core-py/src/lib.rs:431-520), composed from python ops here: users of
+    #    ``bagua_core`` work with loose tensors, not with the symmetric bucket arena the fused kernels need ----------------
+    def _flat_or_gather(self):
+        ts = [t.torch_tensor for t in self._tensors]
+        flat = torch.cat([t.reshape(-1) for t in ts])
+
+        def scatter_back():
+            off = 0
+            with torch.no_grad():
+                for t in ts:
+                    t.copy_(flat[off: off + t.numel()].view_as(t))
+                    off += t.numel()
+
+        return flat, scatter_back
+
+    def append_centralized_synchronous_op(self, communicator_internode=None, communicator_intranode=None, hierarchical: bool = False,
+                                          average: bool = True, scattergather: bool = False, compression: Optional[str] = None):
+        """All-reduce (optionally MinMaxUInt8-compressed) of the bucket's tensors over the default group."""
+        from bagua_b200 import communication as comm_mod
+        from bagua_b200.bucket import _torch_allreduce
+        from bagua_b200.ops import quant
+
+        pg = comm_mod._get_default_group()
+
+        def run(_name: str):
+            if compression is not None:
+                assert compression == "MinMaxUInt8", f"unknown compression {compression}"
+                quant.bytegrad_allreduce_fallback(self, pg, average)
+                return
+            flat, scatter_back = self._flat_or_gather()
+            _torch_allreduce(flat, pg, average, hierarchical)
+            scatter_back()
+
+        self.inner.append_python_op(run, "centralized_synchronous")
+
+    def append_decentralized_synchronous_op(self, communicator_internode=None, communicator_intranode=None, hierarchical: bool = True,
+                                            peer_selection_mode: str = "all", peer_weight: Optional["BaguaTensorPy"] = None):
+        """``peer_weight`` ← average of the bucket over all ranks (``all``) or with this step's partner (``shift_one``)."""
+        import torch.distributed as dist
+
+        from bagua_b200 import communication as comm_mod
+        from bagua_b200.core import native as _native
+
+        pg = comm_mod._get_default_group()
+        assert peer_weight is not None, "decentralized op needs a peer_weight tensor"
+        state = {"step": 0}
+
+        def run(_name: str):
+            flat, _ = self._flat_or_gather()
+            out = peer_weight.torch_tensor.view(-1)
+            n, r = pg.size(), pg.rank()
+            if peer_selection_mode == "all":
+                out.copy_(flat)
+                dist.all_reduce(out, group=pg.torch_group)
+                out.div_(n)
+            elif peer_selection_mode == "shift_one":
+                peer = _native().PeerAverageOp.shift_one_peer(r, n, state["step"])
+                recv = torch.empty_like(flat)
+                reqs = [dist.isend(flat, pg.ranks[peer], group=pg.torch_group), dist.irecv(recv, pg.ranks[peer], group=pg.torch_group)]
+                for q in reqs:
+                    q.wait()
+                out.copy_((flat + recv) / 2)
+                state["step"] += 1
+            else:
+                raise ValueError(f"unsupported peer_selection_mode {peer_selection_mode}")
+
+        self.inner.append_python_op(run, "decentralized_synchronous")
+
     def print_ops(self):
         print(self.inner.print_ops())
 

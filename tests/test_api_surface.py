@@ -194,3 +194,42 @@ def test_compat_helpers_behave():
     apply_flattened_call_all(ts, lambda flat: flat.mul_(3))
     assert torch.equal(ts[0], torch.full((3,), 3.0)) and torch.equal(ts[1], torch.full((2, 2), 6.0)) and torch.equal(ts[2], torch.full((4,), 3.0, dtype=torch.float64))
     assert CommMember.NON_COMM_MEMBER is not None
+
+
+def _core_shim_ops_worker(rank, world):
+    """Low-level ``bagua_core`` usage as in the reference's rust-level tests: loose tensors → BaguaTensorPy → BaguaBucketPy with a
+    centralized (plain and MinMaxUInt8) and a decentralized op → BaguaCommBackendPy."""
+    import bagua_b200 as bagua
+    import bagua_core as B
+
+    bagua.init_process_group()
+    a, b = torch.full((8,), float(rank + 1)), torch.full((4, 2), float(10 * (rank + 1)))
+    ta, tb = B.BaguaTensorPy("a", a), B.BaguaTensorPy("b", b)
+    bucket = B.BaguaBucketPy("bk", [ta, tb])
+    bucket.append_centralized_synchronous_op(None, None, hierarchical=False, average=True)
+    backend = B.BaguaCommBackendPy(10, -1)
+    backend.register_ordered_buckets([bucket])
+    backend.mark_communication_ready(ta, 0)
+    backend.mark_communication_ready(tb, 0)
+    assert backend.wait_pending_comm_ops() == 1
+    plain = (a.clone(), b.clone())
+    # compressed: values land within the 8-bit quantisation error of the mean
+    c = torch.linspace(-1, 1, 16) * (rank + 1)
+    tc = B.BaguaTensorPy("c", c)
+    peer = torch.zeros(16)
+    b2 = B.BaguaBucketPy("bk2", [tc])
+    b2.append_centralized_synchronous_op(None, None, hierarchical=False, average=True, scattergather=True, compression="MinMaxUInt8")
+    b2.append_decentralized_synchronous_op(None, None, hierarchical=False, peer_selection_mode="shift_one", peer_weight=B.BaguaTensorPy("pw", peer))
+    backend2 = B.BaguaCommBackendPy(10, -1)
+    backend2.register_ordered_buckets([b2])
+    backend2.mark_communication_ready(tc, 0)
+    backend2.wait_pending_comm_ops()
+    return plain, c.clone(), peer.clone()
+
+
+def test_bagua_core_shim_low_level_ops():
+    res = run_distributed(_core_shim_ops_worker, world=2)
+    for (a, b), c, peer in res:
+        assert torch.equal(a, torch.full((8,), 1.5)) and torch.equal(b, torch.full((4, 2), 15.0))
+        torch.testing.assert_close(c, torch.linspace(-1, 1, 16) * 1.5, rtol=0, atol=0.03)
+        torch.testing.assert_close(peer, c, rtol=0, atol=1e-6)      # both ranks hold the same compressed mean → pair average = itself
