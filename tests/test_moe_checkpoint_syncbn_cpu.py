@@ -175,3 +175,34 @@ def _syncbn_worker(rank, world):
 
 def test_sync_batchnorm_equals_global_batchnorm():
     assert all(run_distributed(_syncbn_worker, world=2))
+
+
+def _bf16_moe_worker(rank, world):
+    """Regression: a bf16 model whose MoE gate must stay fp32 trains under with_bagua (casting the gate inside ``forward`` used to
+    re-create the parameter and break the engine's 'backend tensor == parameter grad' contract)."""
+    import bagua_b200 as bagua
+    from bagua_b200 import models
+    from bagua_b200.parallel.algorithms import gradient_allreduce
+
+    bagua.init_process_group()
+    torch.manual_seed(0)
+    cfg = models.GPT2MoEConfig(vocab_size=128, n_positions=16, n_embd=32, n_layer=2, n_head=2, num_experts=2 * world)
+    model = models.GPT2MoE(cfg, world_size=world).to(torch.bfloat16)
+    gate_dtypes = {p.dtype for n, p in model.named_parameters() if n.endswith("wg.weight")}
+    assert gate_dtypes == {torch.float32}
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    model = model.with_bagua([opt], gradient_allreduce.GradientAllReduceAlgorithm())
+    idx = torch.randint(0, 128, (2, 16), generator=torch.Generator().manual_seed(rank))
+    for _ in range(3):
+        opt.zero_grad()
+        loss, _ = model(idx, idx)
+        loss.backward()
+        opt.step()
+    gate = [p for n, p in model.named_parameters() if n.endswith("wg.weight")][0]
+    return float(loss), gate.detach().clone()
+
+
+def test_bf16_model_with_fp32_gate_trains_under_with_bagua():
+    res = run_distributed(_bf16_moe_worker, world=2, timeout=240)
+    assert all(l == l for l, _ in res)                                  # finite
+    assert torch.equal(res[0][1], res[1][1])                            # the gate is data-parallel: identical on both ranks
