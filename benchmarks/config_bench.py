@@ -24,6 +24,7 @@ p.add_argument("--warmup", type=int, default=5)
 p.add_argument("--batch-size", type=int, default=0)
 p.add_argument("--tiny", action="store_true", help="shrunken models for CPU smoke tests")
 p.add_argument("--cpu", action="store_true")
+p.add_argument("--force-bf16", action="store_true", help="bf16 parameters even on the CPU smoke path (exercises the same python code as the GPU run)")
 p.add_argument("--comm-report", action="store_true", help="per-bucket device time / GB/s of the communication programs (adds 2 event records per bucket)")
 p.add_argument("--arm", choices=["peer", "nccl"], default="peer", help="nccl = same schedule on NCCL collectives / cuBLAS experts only (baseline arm)")
 args = p.parse_args()
@@ -46,7 +47,7 @@ if "MASTER_PORT" not in os.environ:
 bagua.init_process_group()
 rank, world = bagua.get_rank(), bagua.get_world_size()
 dev = torch.device("cuda", bagua.get_local_rank()) if cuda else torch.device("cpu")
-dtype = torch.bfloat16 if cuda else torch.float32
+dtype = torch.bfloat16 if (cuda or args.force_bf16) else torch.float32
 torch.manual_seed(1 + rank)
 torch.backends.cudnn.benchmark = True
 cfg = args.config

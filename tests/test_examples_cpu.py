@@ -31,3 +31,20 @@ def test_example_runs_under_the_static_launcher(name, tmp_path):
     cmd = [sys.executable, "-m", "bagua_b200.distributed.launch", "--nproc_per_node=2", f"--master_port={free_port()}", os.path.join(REPO, argv[0]), *argv[1:]]
     r = run_in_session(cmd, 240, env=ENV, cwd=str(tmp_path))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.parametrize("config", ["bert_bytegrad", "resnet50_decentralized", "resnet50_async", "gpt2_moe"])
+def test_baseline_config_benchmarks_run_tiny_in_bf16(config, tmp_path):
+    """benchmarks/config_bench.py for every BASELINE configuration: tiny models, two CPU ranks, bf16 parameters — the python
+    paths of the GPU runs (dtype handling, algorithm wiring, MoE gate) without spending GPU time on a typo."""
+    import json
+
+    from tests.mp_utils import free_port, run_in_session
+
+    cmd = [sys.executable, "-m", "bagua_b200.distributed.launch", "--nproc_per_node=2", f"--master_port={free_port()}",
+           os.path.join(REPO, "benchmarks/config_bench.py"), "--config", config, "--tiny", "--cpu", "--force-bf16", "--steps", "2", "--warmup", "3", "--batch-size", "2"]
+    r = run_in_session(cmd, 300, env=ENV, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+    out = json.loads(line)
+    assert out["config"] == config and out["n_gpus"] == 2 and out["loss_finite"] and out["value"] > 0
