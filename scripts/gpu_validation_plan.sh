@@ -24,6 +24,13 @@ two)
   BAGUA_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_peer_gpu.py -q -k "fused or abort or sync_batchnorm or peer_allgather" > gpurun_out/pytest_experimental_2.log 2>&1
   echo "experimental exit=$?" | tee gpurun_out/plan_two.txt
   timeout 400 python -m pytest tests/test_peer_gpu.py -x -q > gpurun_out/pytest_peer_2.log 2>&1; echo "peer exit=$?" | tee -a gpurun_out/plan_two.txt
+  # the shipped examples on real GPUs (each asserts its own results)
+  for ex in "communication_primitives/main.py" "mnist/main.py --algorithm bytegrad --epochs 1 --steps-per-epoch 20" "moe/mnist_main.py --steps 20" \
+            "squad/main.py --tiny --epochs 1 --num-synthetic 256 --max-seq-length 128 --algorithm qadam" \
+            "imagenet/main.py --arch vgg16 --synthetic --epochs 1 --steps-per-epoch 10 --fused-shard"; do
+    timeout 240 python -m bagua_b200.distributed.launch --nproc_per_node=2 --master_port=$((29640 + RANDOM % 50)) examples/$ex > gpurun_out/example_$(echo $ex | cut -d/ -f1).log 2>&1
+    echo "example $ex exit=$?" | tee -a gpurun_out/plan_two.txt
+  done
   for fused in 0 1; do
     BAGUA_MOE_FUSED_COMBINE=$fused timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $((29610 + fused)) \
       benchmarks/config_bench.py --config gpt2_moe --steps 10 --warmup 3 >> gpurun_out/config_bench_n2.jsonl 2>> gpurun_out/config_bench_n2.err
