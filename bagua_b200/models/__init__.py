@@ -11,4 +11,15 @@ _REGISTRY = {"vgg16": vgg16, "resnet50": resnet50, "mnist": MnistNet}
 
 
 def get_model(name: str, **kwargs):
-    return _REGISTRY[name](**kwargs)
+    """A model by name: the built-in zoo first, then any ``torchvision.models`` architecture (random init) when torchvision
+    is installed — what the reference's synthetic benchmark does with ``getattr(torchvision.models, name)()``."""
+    if name in _REGISTRY:
+        return _REGISTRY[name](**kwargs)
+    try:
+        import torchvision.models as tvm
+    except ImportError as e:
+        raise KeyError(f"unknown model {name!r}; built in: {sorted(_REGISTRY)} (torchvision is not installed)") from e
+    ctor = getattr(tvm, name, None)
+    if not callable(ctor):
+        raise KeyError(f"unknown model {name!r}; built in: {sorted(_REGISTRY)}, or any torchvision.models architecture")
+    return ctor(weights=None, **kwargs)
