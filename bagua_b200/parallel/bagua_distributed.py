@@ -478,7 +478,10 @@ class BaguaDistributedDataParallel:
                 if not ddp.require_backward_grad_sync:
                     return
                 bt = p._bagua_backend_tensor
-                if bt.data_ptr() != p.grad.data_ptr():
+                # pointer contract (the gradient is still the registered bucket view): verified on the first steps and then
+                # periodically — it only breaks when user code replaces .grad, which shows up immediately
+                step = ddp.bagua_train_step_counter
+                if (step < 4 or not step & 63) and bt.data_ptr() != p.grad.data_ptr():
                     raise AssertionError("bagua backend tensor data_ptr should match parameter grad")
                 mark(bt, ddp._stream_cache)
                 if not ddp._is_post_backward_callback_queued:
