@@ -94,7 +94,7 @@ def test_autotune_service_with_mock_workers():
 
 
 def test_system_autotune_measures_with_bagua_sys_perf():
-    """The offline tuner end to end on CPU: two real ``bagua_sys_perf`` launches (MNIST net, 2 ranks) scored from their
+    """The offline tuner end to end on CPU: a real ``bagua_sys_perf`` launch (MNIST net, 2 ranks) scored from their
     Horovod-style output (reference autotune_system.py:60-62,92-169)."""
     import os
 
@@ -106,10 +106,8 @@ def test_system_autotune_measures_with_bagua_sys_perf():
     os.environ.update(PYTHONPATH=repo + os.pathsep + os.environ.get("PYTHONPATH", ""), CUDA_VISIBLE_DEVICES="", BAGUA_FORCE_CPU="1")
     try:
         extra = ["--cpu", "--num-iters", "1", "--num-batches-per-iter", "2", "--num-warmup-batches", "1", "--batch-size", "8"]
-        score = autotune_system.sysperf("", 2, 22, {"BAGUA_COMM_BLOCKS": 4}, model="mnist", extra_args=extra, master_port=free_port())
-        assert score > 0
-        env, best = autotune_system.autotune_system_hyperparameters("", 2, 22, max_samples=2, model="mnist", extra_args=extra, port_fn=free_port)
-        assert best > 0 and isinstance(env, dict)
+        env, best = autotune_system.autotune_system_hyperparameters("", 2, 22, max_samples=1, model="mnist", extra_args=extra, port_fn=free_port)
+        assert best > 0 and isinstance(env, dict)      # one real launch, scored from the "Total img/sec" line
     finally:
         os.environ.clear()
         os.environ.update(old)
