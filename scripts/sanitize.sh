@@ -8,4 +8,8 @@ for tool in memcheck racecheck synccheck; do
       > gpurun_out/sanitizer_$tool.log 2>&1
   echo "$tool exit=$?" | tee -a gpurun_out/sanitizer_summary.txt
 done
+# kernels written after the last GPU session (memcheck only: racecheck does not model tcgen05 / mbarrier traffic)
+BAGUA_EXPERIMENTAL=1 compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_zz_new_kernels_gpu.py -q -x \
+    > gpurun_out/sanitizer_memcheck_new_kernels.log 2>&1
+echo "memcheck(new kernels) exit=$?" | tee -a gpurun_out/sanitizer_summary.txt
 # host side: the C++ scheduler under TSAN/ASAN runs in the CPU suite (tests/test_scheduler_tsan.py)
