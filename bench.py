@@ -248,11 +248,14 @@ def main():
 
     e2e = None
     if not args.no_e2e:
-        e2e_loop(3)
-        ms_e2e = timed(e2e_loop, args.steps, whole_loop=True)
-        h2d = x_host[0].numel() * x_host[0].element_size() + y_host[0].numel() * y_host[0].element_size()
-        e2e = {"value": bs * world * args.steps / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-               "ms_per_step": ms_e2e / args.steps}
+        try:
+            e2e_loop(3)
+            ms_e2e = timed(e2e_loop, args.steps, whole_loop=True)
+            h2d = x_host[0].numel() * x_host[0].element_size() + y_host[0].numel() * y_host[0].element_size()
+            e2e = {"value": bs * world * args.steps / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                   "ms_per_step": ms_e2e / args.steps}
+        except Exception as exc:  # noqa: BLE001 - the device-timed headline above must still be reported
+            e2e = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank == 0:
         variants = sorted({getattr(b, "allreduce_variant", "none") for b in model.bagua_buckets})
