@@ -155,6 +155,36 @@ def build_net_plugin(force: bool = False, verbose: bool = False) -> Path:
     return NET_TARGET
 
 
+HOOKS_SRC = CSRC / "torch_hooks" / "hooks.cpp"
+HOOKS_TARGET = PKG_DIR / "_C_torch.so"
+
+
+def build_torch_hooks(force: bool = False, verbose: bool = False) -> Path:
+    """Build the optional torch extension with the native autograd hooks (``bagua_b200/_C_torch.so``): host code only, the one
+    translation unit compiled against libtorch.  Uses the system ``g++`` (dynamic libstdc++, like torch itself)."""
+    import torch
+    from torch.utils import cpp_extension
+
+    stamp_file = PKG_DIR / "_C_torch.so.stamp"
+    stamp = hashlib.sha1(HOOKS_SRC.read_bytes() + torch.__version__.encode()).hexdigest()
+    if not force and HOOKS_TARGET.exists() and stamp_file.exists() and stamp_file.read_text().strip() == stamp:
+        return HOOKS_TARGET
+    cxx = shutil.which("g++") or CXX
+    lib_dir = str(Path(torch.__file__).parent / "lib")
+    incs = [f"-I{i}" for i in cpp_extension.include_paths()] + [f"-I{sysconfig.get_paths()['include']}"]
+    abi = int(getattr(torch._C, "_GLIBCXX_USE_CXX11_ABI", True))
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", f"-D_GLIBCXX_USE_CXX11_ABI={abi}", "-DTORCH_EXTENSION_NAME=_C_torch",
+           "-DTORCH_API_INCLUDE_EXTENSION_H", *incs, str(HOOKS_SRC), "-o", str(HOOKS_TARGET), f"-L{lib_dir}", "-ltorch", "-ltorch_cpu", "-lc10",
+           "-ltorch_python", f"-Wl,-rpath,{lib_dir}"]
+    if verbose:
+        print("[bagua_b200 build]", " ".join(cmd), flush=True)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"torch hooks extension build failed:\n{res.stdout[-2000:]}\n{res.stderr[-4000:]}")
+    stamp_file.write_text(stamp + "\n")
+    return HOOKS_TARGET
+
+
 def is_built() -> bool:
     return TARGET.exists()
 
@@ -163,3 +193,4 @@ if __name__ == "__main__":
     path = build(force="--force" in sys.argv, verbose=True)
     print(f"built {path}")
     print(f"built {build_net_plugin(force='--force' in sys.argv, verbose=True)}")
+    print(f"built {build_torch_hooks(force='--force' in sys.argv, verbose=True)}")

@@ -45,8 +45,19 @@ AdamParams make_adam(float lr, float b1, float b2, float eps, float wd, int step
 }
 }  // namespace
 
+// Entry point for the optional torch extension (csrc/torch_hooks): marks a tensor ready without going through Python.
+extern "C" __attribute__((visibility("default"))) void bagua_native_mark_ready(void* backend, void* tensor_handle, uint64_t stream) {
+    auto* b = static_cast<bagua::Backend*>(backend);
+    auto* t = static_cast<std::shared_ptr<bagua::Tensor>*>(tensor_handle);
+    b->mark_ready_on_stream(*t, reinterpret_cast<bagua::StreamHandle>(stream));
+}
+
 PYBIND11_MODULE(_C, m) {
     m.doc() = "bagua_b200 native core (sm_100a)";
+    m.def("native_mark_ready_fn", [] { return reinterpret_cast<uint64_t>(&bagua_native_mark_ready); });
+    m.def("backend_raw_ptr", [](Backend& b) { return reinterpret_cast<uint64_t>(&b); });
+    m.def("tensor_handle_new", [](std::shared_ptr<Tensor> t) { return reinterpret_cast<uint64_t>(new std::shared_ptr<Tensor>(std::move(t))); });
+    m.def("tensor_handle_free", [](uint64_t h) { delete reinterpret_cast<std::shared_ptr<Tensor>*>(h); });
     m.def("log_level", [] { return std::string(bagua::log::name(bagua::log::threshold())); });
     m.def("set_log_level", [](const std::string& lvl) { bagua::log::threshold() = bagua::log::parse_level(lvl.c_str()); });
     m.attr("MAX_PEERS") = kMaxPeers;

@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import collections
 import logging
+import os
 import time
 from types import MethodType
 from typing import Dict, List, Optional, Tuple
@@ -29,10 +30,26 @@ from .. import env
 from ..bucket import BaguaBucket, BucketArena, bucket_arena
 from ..core import to_bagua_datatype
 from ..define import BaguaHyperparameter, TensorDeclaration
+from ..core import native
 from ..tensor import dense_strides
 from ..utils import StatisticalAverage
 
 logger = logging.getLogger(__name__)
+
+_hooks_ext = [False]
+
+
+def _native_hooks_ext():
+    """The optional torch extension with the C++ autograd hooks, or ``None`` (not built / not loadable → Python hooks)."""
+    if _hooks_ext[0] is False:
+        try:
+            from .. import _C_torch  # noqa: F401  (built by bagua_b200/_build.py:build_torch_hooks)
+
+            _hooks_ext[0] = _C_torch
+        except Exception as e:  # noqa: BLE001
+            logger.warning("bagua_b200: native autograd hooks unavailable (%s); using Python hooks", e)
+            _hooks_ext[0] = None
+    return _hooks_ext[0]
 
 __all__ = ["BaguaDistributedDataParallel"]
 
@@ -94,6 +111,8 @@ class BaguaDistributedDataParallel:
         self._speed_metrics = StatisticalAverage()
         self._on_cuda = any(p.is_cuda for p in module.parameters())
         self._stream_cache = 0
+        self._native_state = None      # csrc/torch_hooks HookState when BAGUA_NATIVE_HOOKS=1
+        self._native_hooked = []
         self._bagua_autotune_client = None
         if env.get_autotune_level() >= 1:
             from ..service.autotune_service import AutotuneClient
@@ -119,6 +138,8 @@ class BaguaDistributedDataParallel:
                 if ddp._report_metrics:
                     ddp._log_metrics()
             ddp._is_post_backward_callback_queued = False
+            if ddp._native_state is not None:
+                ddp._native_state.new_pass(ddp.bagua_train_step_counter, ddp._stream_cache, ddp.require_backward_grad_sync)
 
         module._bagua_states._bagua_framework_hooks.append(module.register_forward_pre_hook(forward_pre_hook))
         self._bagua_init_algorithm()
@@ -330,6 +351,18 @@ class BaguaDistributedDataParallel:
         self._register_autograd_hooks()
         self._register_optimizer_hooks()
 
+    @property
+    def require_backward_grad_sync(self) -> bool:
+        """Cleared inside ``no_sync()``: gradients accumulate locally and nothing is marked ready."""
+        return self._require_backward_grad_sync
+
+    @require_backward_grad_sync.setter
+    def require_backward_grad_sync(self, value: bool):
+        self._require_backward_grad_sync = bool(value)
+        state = getattr(self, "_native_state", None)
+        if state is not None:
+            state.set_enabled(bool(value))
+
     def _bagua_cleanup_algorithm(self):
         # let in-flight work of the previous program drain before its buffers are recycled
         try:
@@ -364,6 +397,8 @@ class BaguaDistributedDataParallel:
         self._fwd_pre_hook = self.bagua_algorithm.init_forward_pre_hook(self)
         self._backward_hook = self.bagua_algorithm.init_backward_hook(self)
         self._post_backward_hook = self.bagua_algorithm.init_post_backward_hook(self)
+        if self._native_hooked:  # native hooks hold the scheduler records and gradient addresses of the OLD buckets
+            self._register_autograd_hooks()
 
     # ---------------------------------------------------------------------------------------------------------
     # per-bucket communication profile
@@ -438,6 +473,17 @@ class BaguaDistributedDataParallel:
         for h in st._bagua_autograd_hooks:
             h.remove()
         st._bagua_autograd_hooks.clear()
+        # native hook records live on the MODULE state like the Python handles: a later with_bagua() builds a new engine object
+        # and must be able to take down what its predecessor installed
+        native_hooked = getattr(st, "_bagua_native_hooked", [])
+        if native_hooked:
+            ext, C = _native_hooks_ext(), native()
+            for p, handle in native_hooked:
+                ext.HookState.remove(p)
+                C.tensor_handle_free(handle)
+        st._bagua_native_hooked = []
+        self._native_hooked = st._bagua_native_hooked
+        self._native_state = None
 
     def _register_autograd_hooks(self):
         self._cleanup_autograd_hooks()
@@ -446,8 +492,10 @@ class BaguaDistributedDataParallel:
 
         def queue_post_backward():
             if not ddp._is_post_backward_callback_queued:
-                torch.autograd.Variable._execution_engine.queue_callback(ddp._real_post_backward_hook)
                 ddp._is_post_backward_callback_queued = True
+                # parameters with native hooks share the "already queued" flag of this backward pass
+                if ddp._native_state is None or ddp._native_state.try_queue():
+                    torch.autograd.Variable._execution_engine.queue_callback(ddp._real_post_backward_hook)
 
         def factory(name: str):
             def hook(param):
@@ -489,9 +537,22 @@ class BaguaDistributedDataParallel:
 
             return hook
 
+        # Opt-in (BAGUA_NATIVE_HOOKS=1): the same fast path as a C++ hook object (csrc/torch_hooks) — no GIL, no Python frame per
+        # parameter; Python is entered once per backward pass to queue the post-backward callback.
+        ext = _native_hooks_ext() if (default_hook and os.environ.get("BAGUA_NATIVE_HOOKS", "0") == "1") else None
+        if ext is not None:
+            C = native()
+            self._native_state = ext.HookState(C.backend_raw_ptr(self._bagua_backend), C.native_mark_ready_fn(), self._real_post_backward_hook)
+            self._native_state.new_pass(self.bagua_train_step_counter, self._stream_cache, self.require_backward_grad_sync)
         for name, p in self.module.named_parameters():
             if p.requires_grad:
                 fast = default_hook and name in comm_names and hasattr(p, "_bagua_backend_tensor")
+                if fast and ext is not None and p.grad is not None:
+                    handle = C.tensor_handle_new(p._bagua_backend_tensor)
+                    if self._native_state.install(p, handle, p.grad.data_ptr(), name):
+                        self._native_hooked.append((p, handle))
+                        continue
+                    C.tensor_handle_free(handle)
                 st._bagua_autograd_hooks.append(p.register_post_accumulate_grad_hook(fast_factory(name, p) if fast else factory(name)))
 
     def _real_post_backward_hook(self):

@@ -18,6 +18,10 @@ one)
   # A/B of the host-overhead experiment (only meaningful if the gated test above passed)
   BAGUA_NHWC_FINALIZE=1 timeout 120 python bench.py --steps 30 --warmup 5 > gpurun_out/bench1_nhwc_finalize.json 2> gpurun_out/bench1_nhwc_finalize.err
   echo "bench (nhwc finalize) exit=$?" | tee -a gpurun_out/plan_one.txt
+  BAGUA_NATIVE_HOOKS=1 timeout 120 python bench.py --steps 30 --warmup 5 > gpurun_out/bench1_native_hooks.json 2> gpurun_out/bench1_native_hooks.err
+  echo "bench (native hooks) exit=$?" | tee -a gpurun_out/plan_one.txt
+  BAGUA_NATIVE_HOOKS=1 BAGUA_NHWC_FINALIZE=1 timeout 120 python bench.py --steps 30 --warmup 5 > gpurun_out/bench1_native_hooks_nhwc.json 2> gpurun_out/bench1_native_hooks_nhwc.err
+  echo "bench (native hooks + nhwc finalize) exit=$?" | tee -a gpurun_out/plan_one.txt
   ;;
 two)
   # opt-in kernels written without hardware access in round 1: fused GEMM+combine, fused allreduce+Adam, mixed-precision Adam

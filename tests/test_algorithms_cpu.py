@@ -1,6 +1,7 @@
 """Algorithms end to end on CPU/gloo with world_size 2 (the BASELINE 'plumbing' config) against python oracles —
 same strategy as the reference's tests: a torch re-implementation of each algorithm is the executable spec."""
 import copy
+import os
 
 import pytest
 import torch
@@ -327,3 +328,40 @@ def _fused_fallback_worker(rank, world, kind="sgd"):
 def test_fused_allreduce_sgd_cpu_fallback(kind):
     for mine, oracle in run_distributed(_fused_fallback_worker, world=2, args=(kind,)):
         torch.testing.assert_close(mine, oracle, rtol=1e-5, atol=1e-6)
+
+
+# ---- the same scenarios with the C++ autograd hooks (csrc/torch_hooks, BAGUA_NATIVE_HOOKS=1) ----------------------------------
+def _native_hooks_worker(rank, world):
+    import bagua_b200 as bagua
+    from bagua_b200.parallel.algorithms import bytegrad, gradient_allreduce
+
+    assert os.environ.get("BAGUA_NATIVE_HOOKS") == "1"
+    mine, oracle = _grad_allreduce_worker(rank, world)               # oracle equality + comm_report with native hooks
+    torch.manual_seed(rank)
+    model = _net()
+    opt = torch.optim.SGD(model.parameters(), lr=0.05)
+    model = model.with_bagua([opt], gradient_allreduce.GradientAllReduceAlgorithm())
+    n_native = len(model.bagua_ddp._native_hooked)
+    _train(model, opt, rank, 2)
+    model = model.with_bagua([opt], bytegrad.ByteGradAlgorithm())    # switching algorithms re-installs the hooks on new buckets
+    _train(model, opt, rank, 2)
+    model.bagua_ddp._reset_buckets()                                  # what the autotuner does: new buckets, same algorithm
+    _train(model, opt, rank, 2)
+    return mine, oracle, n_native, len(model.bagua_ddp._native_hooked), _flat(model)
+
+
+def test_native_autograd_hooks_match_python_hooks():
+    from bagua_b200 import _build
+
+    try:
+        _build.build_torch_hooks()
+    except Exception as e:  # noqa: BLE001
+        pytest.skip(f"torch hooks extension cannot be built here: {e}")
+    res = run_distributed(_native_hooks_worker, world=2, extra_env={"BAGUA_NATIVE_HOOKS": "1"}, timeout=300)
+    for mine, oracle, n0, n1, _ in res:
+        torch.testing.assert_close(mine, oracle, rtol=1e-5, atol=1e-6)
+        assert n0 == 4 and n1 == 4                                    # every parameter of the net got a native hook, also after re-bucketing
+    assert torch.equal(res[0][4], res[1][4])
+    r0, r1 = run_distributed(_ddp_wrapper_worker, world=2, extra_env={"BAGUA_NATIVE_HOOKS": "1"})
+    assert torch.equal(r0[0], r1[0]) and not torch.equal(r0[2], r1[2])   # no_sync() disables the native hooks too
+    torch.testing.assert_close(r0[3], r1[3])
