@@ -155,7 +155,7 @@ def build_net_plugin(force: bool = False, verbose: bool = False) -> Path:
     return NET_TARGET
 
 
-HOOKS_SRC = CSRC / "torch_hooks" / "hooks.cpp"
+HOOKS_DIR = CSRC / "torch_hooks"
 HOOKS_TARGET = PKG_DIR / "_C_torch.so"
 
 
@@ -166,16 +166,17 @@ def build_torch_hooks(force: bool = False, verbose: bool = False) -> Path:
     from torch.utils import cpp_extension
 
     stamp_file = PKG_DIR / "_C_torch.so.stamp"
-    stamp = hashlib.sha1(HOOKS_SRC.read_bytes() + torch.__version__.encode()).hexdigest()
+    srcs = sorted(HOOKS_DIR.glob("*.cpp"))
+    stamp = hashlib.sha1(b"".join(p.read_bytes() for p in srcs) + torch.__version__.encode()).hexdigest()
     if not force and HOOKS_TARGET.exists() and stamp_file.exists() and stamp_file.read_text().strip() == stamp:
         return HOOKS_TARGET
     cxx = shutil.which("g++") or CXX
     lib_dir = str(Path(torch.__file__).parent / "lib")
-    incs = [f"-I{i}" for i in cpp_extension.include_paths()] + [f"-I{sysconfig.get_paths()['include']}"]
+    incs = [f"-I{i}" for i in cpp_extension.include_paths()] + [f"-I{sysconfig.get_paths()['include']}", f"-I{Path(CUDA_HOME) / 'include'}"]
     abi = int(getattr(torch._C, "_GLIBCXX_USE_CXX11_ABI", True))
     cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", f"-D_GLIBCXX_USE_CXX11_ABI={abi}", "-DTORCH_EXTENSION_NAME=_C_torch",
-           "-DTORCH_API_INCLUDE_EXTENSION_H", *incs, str(HOOKS_SRC), "-o", str(HOOKS_TARGET), f"-L{lib_dir}", "-ltorch", "-ltorch_cpu", "-lc10",
-           "-ltorch_python", f"-Wl,-rpath,{lib_dir}"]
+           "-DTORCH_API_INCLUDE_EXTENSION_H", *incs, *map(str, srcs), "-o", str(HOOKS_TARGET), f"-L{lib_dir}", "-ltorch", "-ltorch_cpu", "-lc10",
+           "-lc10_cuda", "-ltorch_cuda", "-ltorch_python", f"-Wl,-rpath,{lib_dir}"]
     if verbose:
         print("[bagua_b200 build]", " ".join(cmd), flush=True)
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -54,6 +54,7 @@ extern "C" __attribute__((visibility("default"))) void bagua_native_mark_ready(v
 
 PYBIND11_MODULE(_C, m) {
     m.doc() = "bagua_b200 native core (sm_100a)";
+    m.def("nhwc_api_ptr", [] { return reinterpret_cast<uint64_t>(bagua_nhwc_api()); });
     m.def("native_mark_ready_fn", [] { return reinterpret_cast<uint64_t>(&bagua_native_mark_ready); });
     m.def("backend_raw_ptr", [](Backend& b) { return reinterpret_cast<uint64_t>(&b); });
     m.def("tensor_handle_new", [](std::shared_ptr<Tensor> t) { return reinterpret_cast<uint64_t>(new std::shared_ptr<Tensor>(std::move(t))); });

@@ -66,6 +66,21 @@ void launch_bias_relu_pool_nhwc_fwd(const void* x, const void* bias, void* out, 
 void launch_bias_relu_pool_nhwc_bwd(const void* g, const void* out, const uint8_t* idx, void* gin, float* bias_grad, int N, int H, int W, int C,
                                     int dtype, cudaStream_t stream, void* bias_grad_out = nullptr, unsigned int* ticket = nullptr);
 
+// C table of the four epilogue launchers for the optional torch extension (csrc/torch_hooks/nhwc_functions.cpp): C++ autograd
+// Functions call the kernels without a Python frame. Every entry returns 0 or non-zero with the message in last_error().
+extern "C" {
+struct BaguaNhwcApi {
+    int (*bias_relu_fwd)(void* y, const void* bias, size_t rows, int C, int dtype, void* stream);
+    int (*bias_relu_bwd)(const void* g, const void* y, void* gout, float* bias_grad, size_t rows, int C, int dtype, void* stream, void* bias_grad_out,
+                         unsigned int* ticket);
+    int (*pool_fwd)(const void* x, const void* bias, void* out, uint8_t* idx, int N, int H, int W, int C, int dtype, void* stream);
+    int (*pool_bwd)(const void* g, const void* out, const uint8_t* idx, void* gin, float* bias_grad, int N, int H, int W, int C, int dtype, void* stream,
+                    void* bias_grad_out, unsigned int* ticket);
+    const char* (*last_error)();
+};
+const BaguaNhwcApi* bagua_nhwc_api();
+}
+
 // ---- tcgen05 grouped GEMM (gemm_tcgen05.cu) ----------------------------------------------------------------------
 // C[g] = act(A[g]·B[g]^T + bias[g]); A [G,M,K], B [G,N,K], C [G,M,N] bf16 (K-contiguous operands), bias fp32 [G,N] or null; act: 0 none, 1 GELU(tanh)
 bool grouped_gemm_supported(int M, int N, int K);

@@ -284,3 +284,40 @@ void launch_bias_relu_pool_nhwc_bwd(const void* g, const void* out, const uint8_
 }
 
 }  // namespace bagua
+
+// ---- C table for the torch extension ----------------------------------------------------------------------------------------
+namespace bagua {
+namespace {
+thread_local std::string g_nhwc_error;
+template <typename F>
+int guarded(F&& f) {
+    try {
+        f();
+        return 0;
+    } catch (const std::exception& e) {
+        g_nhwc_error = e.what();
+        return 1;
+    }
+}
+int api_bias_relu_fwd(void* y, const void* bias, size_t rows, int C, int dtype, void* stream) {
+    return guarded([&] { launch_bias_relu_nhwc_fwd(y, bias, rows, C, dtype, static_cast<cudaStream_t>(stream)); });
+}
+int api_bias_relu_bwd(const void* g, const void* y, void* gout, float* bias_grad, size_t rows, int C, int dtype, void* stream, void* bias_grad_out,
+                      unsigned int* ticket) {
+    return guarded([&] { launch_bias_relu_nhwc_bwd(g, y, gout, bias_grad, rows, C, dtype, static_cast<cudaStream_t>(stream), bias_grad_out, ticket); });
+}
+int api_pool_fwd(const void* x, const void* bias, void* out, uint8_t* idx, int N, int H, int W, int C, int dtype, void* stream) {
+    return guarded([&] { launch_bias_relu_pool_nhwc_fwd(x, bias, out, idx, N, H, W, C, dtype, static_cast<cudaStream_t>(stream)); });
+}
+int api_pool_bwd(const void* g, const void* out, const uint8_t* idx, void* gin, float* bias_grad, int N, int H, int W, int C, int dtype, void* stream,
+                 void* bias_grad_out, unsigned int* ticket) {
+    return guarded(
+        [&] { launch_bias_relu_pool_nhwc_bwd(g, out, idx, gin, bias_grad, N, H, W, C, dtype, static_cast<cudaStream_t>(stream), bias_grad_out, ticket); });
+}
+const char* api_last_error() { return g_nhwc_error.c_str(); }
+const BaguaNhwcApi g_nhwc_api = {api_bias_relu_fwd, api_bias_relu_bwd, api_pool_fwd, api_pool_bwd, api_last_error};
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) const BaguaNhwcApi* bagua_nhwc_api() { return &g_nhwc_api; }
+}  // namespace bagua
+

@@ -96,8 +96,11 @@ private:
 
 }  // namespace
 
+void init_nhwc_bindings(py::module_& m);  // nhwc_functions.cpp
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
-    m.doc() = "bagua_b200 native autograd hooks";
+    m.doc() = "bagua_b200 native autograd hooks and C++ autograd Functions";
+    init_nhwc_bindings(m);
     py::class_<HookState>(m, "HookState")
         .def(py::init<uint64_t, uint64_t, py::object>(), py::arg("backend_ptr"), py::arg("mark_fn_ptr"), py::arg("post_backward"))
         .def("new_pass", &HookState::new_pass)

@@ -101,9 +101,30 @@ class _BiasReLUMaxPool2(torch.autograd.Function):
         return gin, bg.to(ctx.bias_dtype)
 
 
+_native_fns = [False]
+
+
+def _native_functions():
+    """C++ autograd Functions of the optional torch extension (opt-in ``BAGUA_NATIVE_NHWC=1``), or ``None``."""
+    if _native_fns[0] is False:
+        ext = None
+        if os.environ.get("BAGUA_NATIVE_NHWC", "0") == "1":
+            try:
+                from .. import _C_torch as ext  # built by bagua_b200/_build.py:build_torch_hooks
+
+                ext.nhwc_init(native().nhwc_api_ptr(), _finish_in_kernel())
+            except Exception:  # noqa: BLE001 - not built / not loadable: the Python Functions below do the same work
+                ext = None
+        _native_fns[0] = ext
+    return _native_fns[0]
+
+
 def bias_relu(y: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
     """``relu(y + bias[None, :, None, None])`` in place on a channels_last f16/bf16 CUDA tensor (torch ops otherwise)."""
     if fused_supported(y, y.shape[1]) and bias.dtype == y.dtype:
+        ext = _native_functions()
+        if ext is not None:
+            return ext.bias_relu(y, bias)
         return _BiasReLU.apply(y, bias)
     return F.relu(y + bias.view(1, -1, 1, 1))
 
@@ -111,6 +132,9 @@ def bias_relu(y: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
 def bias_relu_maxpool2(x: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
     """``max_pool2d(relu(x + bias), 2, 2)`` in one pass."""
     if fused_supported(x, x.shape[1]) and bias.dtype == x.dtype and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0:
+        ext = _native_functions()
+        if ext is not None:
+            return ext.bias_relu_maxpool2(x, bias)
         return _BiasReLUMaxPool2.apply(x, bias)
     return F.max_pool2d(F.relu(x + bias.view(1, -1, 1, 1)), 2, 2)
 

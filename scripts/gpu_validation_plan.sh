@@ -20,8 +20,10 @@ one)
   echo "bench (nhwc finalize) exit=$?" | tee -a gpurun_out/plan_one.txt
   BAGUA_NATIVE_HOOKS=1 timeout 120 python bench.py --steps 30 --warmup 5 > gpurun_out/bench1_native_hooks.json 2> gpurun_out/bench1_native_hooks.err
   echo "bench (native hooks) exit=$?" | tee -a gpurun_out/plan_one.txt
-  BAGUA_NATIVE_HOOKS=1 BAGUA_NHWC_FINALIZE=1 timeout 120 python bench.py --steps 30 --warmup 5 > gpurun_out/bench1_native_hooks_nhwc.json 2> gpurun_out/bench1_native_hooks_nhwc.err
-  echo "bench (native hooks + nhwc finalize) exit=$?" | tee -a gpurun_out/plan_one.txt
+  BAGUA_NATIVE_NHWC=1 timeout 120 python bench.py --steps 30 --warmup 5 > gpurun_out/bench1_native_nhwc.json 2> gpurun_out/bench1_native_nhwc.err
+  echo "bench (C++ nhwc functions) exit=$?" | tee -a gpurun_out/plan_one.txt
+  BAGUA_NATIVE_HOOKS=1 BAGUA_NATIVE_NHWC=1 BAGUA_NHWC_FINALIZE=1 timeout 120 python bench.py --steps 30 --warmup 5 > gpurun_out/bench1_all_host_opts.json 2> gpurun_out/bench1_all_host_opts.err
+  echo "bench (native hooks + C++ nhwc functions + in-kernel finish) exit=$?" | tee -a gpurun_out/plan_one.txt
   ;;
 two)
   # opt-in kernels written without hardware access in round 1: fused GEMM+combine, fused allreduce+Adam, mixed-precision Adam

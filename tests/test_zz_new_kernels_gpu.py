@@ -81,3 +81,31 @@ def test_nhwc_backward_with_in_kernel_bias_grad_finish(dev, monkeypatch):
             for other in res[1:]:
                 for a, c in zip(res[0], other):
                     torch.testing.assert_close(a, c, rtol=2e-2, atol=2e-2 * max(1.0, a.abs().max().item()))
+
+
+@pytest.mark.skipif(__import__("os").environ.get("BAGUA_EXPERIMENTAL") != "1", reason="C++ autograd Functions of the NHWC epilogues: opt-in until validated on hardware")
+def test_native_nhwc_functions_match_python_functions(dev, monkeypatch):
+    """BAGUA_NATIVE_NHWC=1 routes bias_relu / bias_relu_maxpool2 through the C++ autograd Functions of _C_torch.so (same kernels):
+    outputs, input gradients and bias gradients must be identical to the Python Functions, with and without the in-kernel finish."""
+    from bagua_b200 import _build
+    from bagua_b200.models import vgg16
+    from bagua_b200.ops import nhwc
+
+    _build.build_torch_hooks()
+    torch.manual_seed(6)
+    x = torch.randn(4, 3, 64, 64, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    model = vgg16(num_classes=10).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
+    results = []
+    for native, fin in (("0", "0"), ("1", "0"), ("1", "1")):
+        monkeypatch.setenv("BAGUA_NATIVE_NHWC", native)
+        monkeypatch.setenv("BAGUA_NHWC_FINALIZE", fin)
+        nhwc._native_fns[0] = False                      # re-read the switches
+        model.zero_grad(set_to_none=True)
+        out = model(x)
+        out.float().pow(2).sum().backward()
+        assert (nhwc._native_functions() is not None) == (native == "1")
+        results.append([out.detach().float()] + [p.grad.float().clone() for p in model.parameters()])
+    for other in results[1:]:
+        for a, b in zip(results[0], other):
+            torch.testing.assert_close(a, b, rtol=2e-2, atol=2e-2 * max(1.0, a.abs().max().item()))
+    nhwc._native_fns[0] = False
