@@ -335,3 +335,59 @@ def test_model_zoo_matches_the_published_architectures():
     loss, _ = tiny(idx, idx)
     loss.backward()
     assert torch.isfinite(loss) and all(p.grad is not None for p in tiny.parameters() if p.requires_grad)
+
+
+def test_cpp_nhwc_autograd_functions_with_a_host_kernel_table(tmp_path):
+    """The C++ autograd Functions of _C_torch.so (BAGUA_NATIVE_NHWC) driven on CPU through a host double of the kernel table
+    (tests/cpp/fake_nhwc_api.cpp): in-place output, saved tensors, gradient shapes / memory format / dtypes, the zero-fill + cast
+    path and the in-kernel-finish path (workspace handed back zeroed) — against plain PyTorch autograd."""
+    import ctypes
+    import os
+    import shutil
+    import subprocess
+
+    from bagua_b200 import _build
+
+    try:
+        _build.build_torch_hooks()
+        from bagua_b200 import _C_torch as E
+    except Exception as e:  # noqa: BLE001
+        pytest.skip(f"torch extension unavailable: {e}")
+    so = tmp_path / "libfake_nhwc.so"
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "fake_nhwc_api.cpp")
+    subprocess.run([shutil.which("g++"), "-O1", "-std=c++17", "-shared", "-fPIC", src, "-o", str(so)], check=True)
+    lib = ctypes.CDLL(str(so))
+    lib.fake_nhwc_api.restype = ctypes.c_void_p
+    torch.manual_seed(0)
+    x0 = (torch.randn(2, 8, 6, 6) * 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    b0 = (torch.randn(8) * 0.5).to(torch.bfloat16)
+    w = torch.randn(2, 8, 6, 6).to(torch.bfloat16)
+    wp = torch.randn(2, 8, 3, 3).to(torch.bfloat16)
+    try:
+        for fin in (False, True, True):                      # the workspace of the finish path is reused across calls
+            E.nhwc_init(lib.fake_nhwc_api(), fin)
+            x, b = x0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+            y_in = x * 1.0                                   # non-leaf input, like a convolution output
+            y = E.bias_relu(y_in, b)
+            assert y.data_ptr() == y_in.data_ptr()           # in place
+            (y.float() * w.float()).sum().backward()
+            xr, br = x0.clone().float().requires_grad_(True), b0.clone().float().requires_grad_(True)
+            (torch.relu(xr + br.view(1, -1, 1, 1)) * w.float()).sum().backward()
+            torch.testing.assert_close(y.detach().float(), torch.relu(x0.float() + b0.float().view(1, -1, 1, 1)), rtol=2e-2, atol=2e-2)
+            assert x.grad.dtype == torch.bfloat16 and b.grad.dtype == torch.bfloat16 and x.grad.is_contiguous(memory_format=torch.channels_last)
+            torch.testing.assert_close(x.grad.float(), xr.grad, rtol=2e-2, atol=2e-2)
+            torch.testing.assert_close(b.grad.float(), br.grad, rtol=3e-2, atol=0.15)
+            x, b = x0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+            p = E.bias_relu_maxpool2(x * 1.0, b)
+            assert p.shape == (2, 8, 3, 3) and p.is_contiguous(memory_format=torch.channels_last)
+            (p.float() * wp.float()).sum().backward()
+            xr, br = x0.clone().float().requires_grad_(True), b0.clone().float().requires_grad_(True)
+            ref = torch.nn.functional.max_pool2d(torch.relu(xr + br.view(1, -1, 1, 1)), 2)
+            (ref * wp.float()).sum().backward()
+            torch.testing.assert_close(p.detach().float(), ref.detach(), rtol=2e-2, atol=2e-2)
+            torch.testing.assert_close(x.grad.float(), xr.grad, rtol=2e-2, atol=2e-2)
+            torch.testing.assert_close(b.grad.float(), br.grad, rtol=3e-2, atol=0.15)
+        assert [lib.fake_nhwc_calls(i) for i in range(4)] == [3, 3, 3, 3]
+    finally:
+        E.nhwc_init(0, False)                                # detach the double: nhwc_ready() is False again
+    assert not E.nhwc_ready()
