@@ -391,3 +391,58 @@ def test_cpp_nhwc_autograd_functions_with_a_host_kernel_table(tmp_path):
     finally:
         E.nhwc_init(0, False)                                # detach the double: nhwc_ready() is False again
     assert not E.nhwc_ready()
+
+
+def test_python_nhwc_functions_finish_path_with_the_host_double(tmp_path, monkeypatch):
+    """ops/nhwc.py's Python autograd Functions, including the BAGUA_NHWC_FINALIZE workspace path, on CPU: ``native()`` is replaced by
+    an adapter over the same host kernel double, results are compared with plain PyTorch autograd."""
+    import ctypes as C
+    import os
+    import shutil
+    import subprocess
+    import types
+
+    from bagua_b200.ops import nhwc
+
+    so = tmp_path / "libfake_nhwc.so"
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "fake_nhwc_api.cpp")
+    subprocess.run([shutil.which("g++"), "-O1", "-std=c++17", "-shared", "-fPIC", src, "-o", str(so)], check=True)
+    lib = C.CDLL(str(so))
+    lib.fake_nhwc_api.restype = C.c_void_p
+    table = (C.c_void_p * 5).from_address(lib.fake_nhwc_api())
+    vp, sz, i32 = C.c_void_p, C.c_size_t, C.c_int
+    fwd = C.CFUNCTYPE(i32, vp, vp, sz, i32, i32, vp)(table[0])
+    bwd = C.CFUNCTYPE(i32, vp, vp, vp, vp, sz, i32, i32, vp, vp, vp)(table[1])
+    pfwd = C.CFUNCTYPE(i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp)(table[2])
+    pbwd = C.CFUNCTYPE(i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp)(table[3])
+    fake = types.SimpleNamespace(
+        bias_relu_nhwc_fwd=lambda y, b, rows, c, dt, s: fwd(y, b, rows, c, dt, None),
+        bias_relu_nhwc_bwd=lambda g, y, go, bg, rows, c, dt, s: bwd(g, y, go, bg, rows, c, dt, None, None, None),
+        bias_relu_nhwc_bwd_fin=lambda g, y, go, ws, out, tk, rows, c, dt, s: bwd(g, y, go, ws, rows, c, dt, None, out, tk),
+        bias_relu_pool_nhwc_fwd=lambda x, b, o, idx, n, h, w, c, dt, s: pfwd(x, b, o, idx, n, h, w, c, dt, None),
+        bias_relu_pool_nhwc_bwd=lambda g, o, idx, gi, bg, n, h, w, c, dt, s: pbwd(g, o, idx, gi, bg, n, h, w, c, dt, None, None, None),
+        bias_relu_pool_nhwc_bwd_fin=lambda g, o, idx, gi, ws, out, tk, n, h, w, c, dt, s: pbwd(g, o, idx, gi, ws, n, h, w, c, dt, None, out, tk),
+    )
+    monkeypatch.setattr(nhwc, "native", lambda: fake)
+    monkeypatch.setattr(nhwc, "_stream", lambda: 0)
+    monkeypatch.setattr(nhwc, "fused_supported", lambda x, channels: x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last))
+    monkeypatch.setattr(nhwc, "_native_fns", [None])
+    nhwc._workspaces.clear()
+    torch.manual_seed(1)
+    x0 = (torch.randn(2, 8, 4, 4) * 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    b0 = (torch.randn(8) * 0.5).to(torch.bfloat16)
+    for fin in ("0", "1", "1"):
+        monkeypatch.setenv("BAGUA_NHWC_FINALIZE", fin)
+        for pool in (False, True):
+            x, b = x0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+            out = (nhwc.bias_relu_maxpool2 if pool else nhwc.bias_relu)(x * 1.0, b)
+            out.float().pow(2).sum().backward()
+            xr, br = x0.clone().float().requires_grad_(True), b0.clone().float().requires_grad_(True)
+            ref = torch.relu(xr + br.view(1, -1, 1, 1))
+            ref = torch.nn.functional.max_pool2d(ref, 2) if pool else ref
+            ref.pow(2).sum().backward()
+            torch.testing.assert_close(out.detach().float(), ref.detach(), rtol=2e-2, atol=2e-2)
+            torch.testing.assert_close(x.grad.float(), xr.grad, rtol=3e-2, atol=3e-2)
+            torch.testing.assert_close(b.grad.float(), br.grad, rtol=3e-2, atol=0.2)
+            assert b.grad.dtype == torch.bfloat16
+    nhwc._workspaces.clear()
