@@ -23,6 +23,12 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _kernels_apply(params) -> bool:
+    """The sm_100a kernels handle CUDA tensors; everything else takes the plain torch update (also the hook the CPU tests use to
+    drive the kernel call sites with a host double)."""
+    return params[0].device.type == "cuda"
+
+
 def flat_sgd_(param, grad, momentum_buf, *, lr, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False, first_step=False,
               grad_scale=1.0, zero_grad=False, model: Optional[torch.Tensor] = None):
     """One fused SGD step over flat CUDA tensors (param: fp32 master or model dtype; optional low-precision ``model`` copy)."""
@@ -252,7 +258,7 @@ class FusedSGD(_FusedBase):
             params = [p for p in group["params"] if p.grad is not None]
             if not params:
                 continue
-            if params[0].device.type != "cuda":
+            if not _kernels_apply(params):
                 self._torch_step(params, group)
                 continue
             by_dtype: Dict[torch.dtype, List[torch.nn.Parameter]] = {}
@@ -328,7 +334,7 @@ class FusedAdam(_FusedBase):
             params = [p for p in group["params"] if p.grad is not None]
             if not params:
                 continue
-            if params[0].device.type != "cuda":
+            if not _kernels_apply(params):
                 self._torch_step(params, group)
                 continue
             by_dtype: Dict[torch.dtype, List[torch.nn.Parameter]] = {}

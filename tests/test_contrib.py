@@ -446,3 +446,87 @@ def test_python_nhwc_functions_finish_path_with_the_host_double(tmp_path, monkey
             torch.testing.assert_close(b.grad.float(), br.grad, rtol=3e-2, atol=0.2)
             assert b.grad.dtype == torch.bfloat16
     nhwc._workspaces.clear()
+
+
+def test_fused_adam_multi_tensor_call_sites_with_a_numpy_kernel_double(monkeypatch):
+    """FusedAdam's multi-tensor path (parameters outside the bucket arena) on CPU: the pointer tables built by ``_MultiPlan`` are
+    decoded by a numpy stand-in of ``multi_tensor_adam`` / ``multi_tensor_adam_mp`` that applies the Adam update in place — checks the
+    list order [param, grad, exp_avg, exp_avg_sq(, master)], the fp32 state of bf16 parameters and the chunk/block map against
+    ``torch.optim.AdamW``."""
+    import ctypes
+    import types
+
+    import numpy as np
+
+    from bagua_b200.ops import optim
+
+    def view(ptr, n, np_dtype):
+        return np.ctypeslib.as_array((ctypes.c_uint8 * (n * np.dtype(np_dtype).itemsize)).from_address(ptr)).view(np_dtype)
+
+    def bf16_to_f32(u16):
+        return (u16.astype(np.uint32) << 16).view(np.float32)
+
+    def f32_to_bf16(f):
+        u = f.astype(np.float32).view(np.uint32)
+        return ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)
+
+    calls = {"mp": 0, "plain": 0}
+
+    def adam(ptrs, sizes, b2t, b2c, n_t, n_blocks, chunk, dtype, lr, b1, b2, eps, wd, step, adamw, grad_scale, stream, mixed):
+        P = view(ptrs, (5 if mixed else 4) * n_t, np.int64)
+        S = view(sizes, n_t, np.int64)
+        T, Ck = view(b2t, n_blocks, np.int32), view(b2c, n_blocks, np.int32)
+        covered = np.zeros(n_t, dtype=np.int64)
+        for blk in range(n_blocks):                                   # one "CTA" per (tensor, chunk)
+            t, off = int(T[blk]), int(Ck[blk]) * chunk
+            n = min(int(S[t]) - off, chunk)
+            covered[t] += n
+            lowp = dtype in (1, 4)
+            raw = (lambda base, np_dt: view(int(base), int(S[t]), np_dt)[off:off + n])
+            g16 = raw(P[n_t + t], np.uint16) if lowp else None
+            g = bf16_to_f32(g16) if lowp else raw(P[n_t + t], np.float32).copy()
+            if mixed:
+                m1, m2, w = raw(P[2 * n_t + t], np.float32), raw(P[3 * n_t + t], np.float32), raw(P[4 * n_t + t], np.float32)
+            else:
+                assert not lowp
+                m1, m2, w = raw(P[2 * n_t + t], np.float32), raw(P[3 * n_t + t], np.float32), raw(P[t], np.float32)
+            g = g * grad_scale
+            if adamw:
+                w *= 1 - lr * wd
+            else:
+                g = g + wd * w
+            m1[:] = b1 * m1 + (1 - b1) * g
+            m2[:] = b2 * m2 + (1 - b2) * g * g
+            w -= (lr / (1 - b1 ** step)) * (m1 / (np.sqrt(m2) / np.sqrt(1 - b2 ** step) + eps))
+            if mixed:
+                raw(P[t], np.uint16)[:] = f32_to_bf16(w)
+        assert (covered == S).all()                                   # the block map covers every element exactly once
+        calls["mp" if mixed else "plain"] += 1
+
+    fake = types.SimpleNamespace(multi_tensor_adam_mp=lambda *a: adam(*a, mixed=True), multi_tensor_adam=lambda *a: adam(*a, mixed=False))
+    monkeypatch.setattr(optim, "native", lambda: fake)
+    monkeypatch.setattr(optim, "_kernels_apply", lambda params: True)
+    monkeypatch.setattr(optim, "_stream", lambda: 0)
+    monkeypatch.setattr(optim._MultiPlan, "CHUNK", 1000)                # several blocks per tensor
+    torch.manual_seed(9)
+    shapes = [(65, 33), (1000,), (7, 9, 11), (3,)]
+    for dtype in (torch.bfloat16, torch.float32):
+        ps = [torch.nn.Parameter((torch.randn(s) * 0.1).to(dtype)) for s in shapes]
+        rs = [torch.nn.Parameter(p.detach().float().clone()) for p in ps]
+        opt, ropt = optim.FusedAdam(ps, lr=1e-3, adamw=True, weight_decay=0.01), torch.optim.AdamW(rs, lr=1e-3, weight_decay=0.01)
+        for _ in range(6):
+            for p, r in zip(ps, rs):
+                g = torch.randn_like(r)
+                p.grad, r.grad = g.to(dtype), g.to(dtype).float()
+            opt.step()
+            ropt.step()
+        for p, r in zip(ps, rs):
+            st = opt.state[p]
+            assert st["exp_avg"].dtype == torch.float32 and st["step"] == 6
+            if dtype == torch.bfloat16:
+                torch.testing.assert_close(st["master"], r.data, rtol=1e-4, atol=1e-5)
+                torch.testing.assert_close(p.data.float(), r.data, rtol=0, atol=8e-3)
+            else:
+                assert "master" not in st
+                torch.testing.assert_close(p.data, r.data, rtol=1e-4, atol=1e-5)
+    assert calls == {"mp": 6, "plain": 6}
