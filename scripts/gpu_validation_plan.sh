@@ -2,7 +2,7 @@
 # The GPU work that is queued behind the CPU-only development of round 1, in the order it should be spent
 # (each block is one gpurun call; budgets in GPU-minutes = wall minutes x GPUs).
 #
-#   1 GPU  (~12 min):  gpurun --timeout 900  -- 'bash scripts/gpu_validation_plan.sh one'
+#   1 GPU  (~20 min):  gpurun --timeout 1500 -- 'bash scripts/gpu_validation_plan.sh one'
 #   2 GPUs (~2x10 min): gpurun --gpus 2 --timeout 900 -- 'bash scripts/gpu_validation_plan.sh two'
 #   8 GPUs (~8x6 min):  gpurun --gpus 8 --timeout 600 -- 'bash scripts/gpu_validation_plan.sh eight'
 set -uo pipefail
