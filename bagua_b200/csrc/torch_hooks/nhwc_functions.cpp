@@ -140,4 +140,12 @@ void init_nhwc_bindings(py::module_& m) {
         TORCH_CHECK(g_api != nullptr, "call nhwc_init first");
         return BiasReLUMaxPool2::apply(std::move(x), std::move(bias));
     });
+    // Whole conv block in one call from Python: bias-free convolution (cuDNN) + fused epilogue.
+    m.def("conv_bias_relu", [](const at::Tensor& x, const at::Tensor& weight, const at::Tensor& bias, std::vector<int64_t> stride,
+                               std::vector<int64_t> padding, std::vector<int64_t> dilation, int64_t groups, bool pool) {
+        TORCH_CHECK(g_api != nullptr, "call nhwc_init first");
+        at::Tensor y = at::conv2d(x, weight, c10::nullopt, stride, padding, dilation, groups);
+        if (pool) return BiasReLUMaxPool2::apply(std::move(y), bias);
+        return BiasReLU::apply(std::move(y), bias);
+    });
 }

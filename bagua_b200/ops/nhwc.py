@@ -139,9 +139,21 @@ def bias_relu_maxpool2(x: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
     return F.max_pool2d(F.relu(x + bias.view(1, -1, 1, 1)), 2, 2)
 
 
+def _out_hw(x: torch.Tensor, conv: torch.nn.Conv2d):
+    """Spatial size of ``conv(x)`` (integer padding only — the modules the fused path accepts)."""
+    out = []
+    for i in range(2):
+        k, s, p, d = conv.kernel_size[i], conv.stride[i], conv.padding[i], conv.dilation[i]
+        out.append((x.shape[2 + i] + 2 * p - d * (k - 1) - 1) // s + 1)
+    return out
+
+
 def conv_bias_relu(x: torch.Tensor, conv: torch.nn.Conv2d, pool: bool = False) -> torch.Tensor:
     """Conv2d (cuDNN, bias-free) followed by the fused epilogue; falls back to the plain module sequence when unsupported."""
     if conv.bias is not None and fused_supported(x, conv.out_channels) and conv.weight.dtype == x.dtype:
+        ext = _native_functions()
+        if ext is not None and conv.bias.dtype == x.dtype and (not pool or (_out_hw(x, conv)[0] % 2 == 0 and _out_hw(x, conv)[1] % 2 == 0)):
+            return ext.conv_bias_relu(x, conv.weight, conv.bias, list(conv.stride), list(conv.padding), list(conv.dilation), conv.groups, pool)
         y = F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
         return bias_relu_maxpool2(y, conv.bias) if pool else bias_relu(y, conv.bias)
     y = F.relu(conv(x))

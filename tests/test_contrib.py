@@ -388,6 +388,18 @@ def test_cpp_nhwc_autograd_functions_with_a_host_kernel_table(tmp_path):
             torch.testing.assert_close(x.grad.float(), xr.grad, rtol=2e-2, atol=2e-2)
             torch.testing.assert_close(b.grad.float(), br.grad, rtol=3e-2, atol=0.15)
         assert [lib.fake_nhwc_calls(i) for i in range(4)] == [3, 3, 3, 3]
+        # the whole block in one call: at::conv2d (bias-free) + epilogue, vs conv → relu → pool with plain modules
+        E.nhwc_init(lib.fake_nhwc_api(), False)
+        conv = torch.nn.Conv2d(8, 8, 3, padding=1).to(torch.bfloat16).to(memory_format=torch.channels_last)
+        for pool in (False, True):
+            xin = x0.clone().requires_grad_(True)
+            out = E.conv_bias_relu(xin, conv.weight, conv.bias, [1, 1], [1, 1], [1, 1], 1, pool)
+            ref = torch.relu(conv(x0))
+            ref = torch.nn.functional.max_pool2d(ref, 2) if pool else ref
+            torch.testing.assert_close(out.float(), ref.float(), rtol=5e-2, atol=5e-2)
+            conv.zero_grad()
+            out.float().sum().backward()
+            assert xin.grad is not None and conv.weight.grad is not None and conv.bias.grad.dtype == torch.bfloat16
     finally:
         E.nhwc_init(0, False)                                # detach the double: nhwc_ready() is False again
     assert not E.nhwc_ready()
