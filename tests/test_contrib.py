@@ -542,3 +542,49 @@ def test_fused_adam_multi_tensor_call_sites_with_a_numpy_kernel_double(monkeypat
                 assert "master" not in st
                 torch.testing.assert_close(p.data, r.data, rtol=1e-4, atol=1e-5)
     assert calls == {"mp": 6, "plain": 6}
+
+
+def test_vgg_fused_feature_path_on_cpu_through_the_native_extension(tmp_path, monkeypatch):
+    """VGG16's ``_features_fused`` (13 conv blocks, 5 with pooling) end to end on CPU: ops/nhwc.py routes every block through the
+    C++ extension (BAGUA_NATIVE_NHWC=1) whose kernel table is the host double — output and all gradients against the plain
+    ``features`` Sequential.  The only things this does not cover on the GPU path are the CUDA kernels and the stream lookup."""
+    import ctypes
+    import os
+    import shutil
+    import subprocess
+    import types
+
+    from bagua_b200 import _build
+    from bagua_b200.models import vgg16
+    from bagua_b200.ops import nhwc
+
+    try:
+        _build.build_torch_hooks()
+        from bagua_b200 import _C_torch as E
+    except Exception as e:  # noqa: BLE001
+        pytest.skip(f"torch extension unavailable: {e}")
+    so = tmp_path / "libfake_nhwc.so"
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "fake_nhwc_api.cpp")
+    subprocess.run([shutil.which("g++"), "-O2", "-std=c++17", "-shared", "-fPIC", src, "-o", str(so)], check=True)
+    lib = ctypes.CDLL(str(so))
+    lib.fake_nhwc_api.restype = ctypes.c_void_p
+    monkeypatch.setenv("BAGUA_NATIVE_NHWC", "1")
+    monkeypatch.setattr(nhwc, "native", lambda: types.SimpleNamespace(nhwc_api_ptr=lambda: lib.fake_nhwc_api()))
+    monkeypatch.setattr(nhwc, "fused_supported", lambda x, channels: x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last))
+    monkeypatch.setattr(nhwc, "_native_fns", [False])
+    try:
+        torch.manual_seed(2)
+        model = vgg16(num_classes=10).to(torch.bfloat16).to(memory_format=torch.channels_last)
+        x = torch.randn(2, 3, 32, 32).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        res = []
+        for fused in (True, False):
+            model.zero_grad(set_to_none=True)
+            feats = model._features_fused(x) if fused else model.features(x)
+            assert feats.shape == (2, 512, 1, 1)
+            feats.float().pow(2).sum().backward()
+            res.append([feats.detach().float()] + [p.grad.float().clone() for p in model.features.parameters()])
+        assert nhwc._native_functions() is E and lib.fake_nhwc_calls(0) == 8 and lib.fake_nhwc_calls(2) == 5     # 8 plain + 5 pooled blocks
+        for a, b in zip(*res):
+            torch.testing.assert_close(a, b, rtol=8e-2, atol=8e-2 * max(1.0, b.abs().max().item()))
+    finally:
+        E.nhwc_init(0, False)
