@@ -283,6 +283,7 @@ def main():
                 "optimizer": ("SGD fused into the bucket allreduce kernel (sharded fp32 master weights)" if args.fused_shard else f"FusedSGD(momentum={args.momentum}, fp32 master weights)"),
                 "allreduce_variants": variants,
                 "buckets": len(model.bagua_buckets),
+                "host_opts": {k: os.environ.get(k, "0") for k in ("BAGUA_NATIVE_HOOKS", "BAGUA_NATIVE_NHWC", "BAGUA_NHWC_FINALIZE")},
                 "l2_policy": "working set (276 MB bf16 weights + activations) far exceeds the 126 MB L2; no explicit flush",
                 "baseline_note": "vs_baseline = value / (126.5 img/s/GPU x N): Bagua+Bagua-Net VGG16 fp32 on 32x V100 (rust/bagua-net/README.md:52-67)",
             },
