@@ -661,7 +661,10 @@ def init_process_group(store=None, rank: int = -1, world_size: int = -1, local_w
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             os.environ.setdefault("MASTER_PORT", "29500")
             # rank / world size come from the environment: passing them explicitly makes torch rewrite the env:// URL, which
-            # breaks re-rendezvous of restarted gangs under the elastic launcher (stale store keys → connect refused)
+            # breaks re-rendezvous of restarted gangs under the elastic launcher (stale store keys → connect refused).
+            # A bare single-process run (no launcher) has neither variable: it is rank 0 of 1.
+            os.environ.setdefault("RANK", str(env.get_rank()))
+            os.environ.setdefault("WORLD_SIZE", str(env.get_world_size()))
             dist.init_process_group(backend=backend, **kwargs)
     _rank_mappings = None
     _patch_torch_process_group()

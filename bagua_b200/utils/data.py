@@ -18,7 +18,8 @@ class DevicePrefetcher:
         self.loader = loader
         self.device = device
         self.transform = transform
-        self.stream = torch.cuda.Stream(device=device)
+        self.on_cuda = torch.device(device).type == "cuda"
+        self.stream = torch.cuda.Stream(device=device) if self.on_cuda else None
 
     def _stage(self, batch):
         with torch.cuda.stream(self.stream):
@@ -31,6 +32,11 @@ class DevicePrefetcher:
 
     def __iter__(self) -> Iterator:
         it = iter(self.loader)
+        if not self.on_cuda:  # host-only run: nothing to overlap, same interface
+            for batch in it:
+                moved = tuple(t.to(self.device) for t in batch)
+                yield self.transform(*moved) if self.transform is not None else moved
+            return
         try:
             nxt = self._stage(next(it))
         except StopIteration:
@@ -56,8 +62,11 @@ class LossReader:
 
     def __init__(self, device: torch.device, slots: int = 8, lag: int = 2):
         assert 1 <= lag < slots
-        self.buf = torch.zeros(slots, dtype=torch.float32).pin_memory()
-        self.events = [torch.cuda.Event() for _ in range(slots)]
+        self.on_cuda = torch.device(device).type == "cuda"
+        self.buf = torch.zeros(slots, dtype=torch.float32)
+        if self.on_cuda:
+            self.buf = self.buf.pin_memory()
+        self.events = [torch.cuda.Event() if self.on_cuda else None for _ in range(slots)]
         self.n = 0          # losses pushed
         self.read = 0       # losses already read on the host
         self.slots = slots
@@ -67,14 +76,16 @@ class LossReader:
     def _read_until(self, count: int):
         while self.read < count:
             j = self.read % self.slots
-            self.events[j].synchronize()
+            if self.events[j] is not None:
+                self.events[j].synchronize()
             self.last = float(self.buf[j])
             self.read += 1
 
     def push(self, loss: torch.Tensor) -> Optional[float]:
         i = self.n % self.slots
         self.buf[i : i + 1].copy_(loss.detach().float().reshape(1), non_blocking=True)
-        self.events[i].record()
+        if self.events[i] is not None:
+            self.events[i].record()
         self.n += 1
         self._read_until(self.n - self.lag)
         return self.last

@@ -39,6 +39,10 @@ def parse():
     p.add_argument("--fused-shard", dest="fused_shard", action="store_true", default=None,
                    help="fold the SGD update into the allreduce kernel (sharded optimizer state); default: on for N > 1")
     p.add_argument("--no-fused-shard", dest="fused_shard", action="store_false")
+    # plumbing self-test used by tests/ (no GPU there): the same code path end to end on the host with a small image; its
+    # output is marked "selftest" and is not a benchmark result
+    p.add_argument("--selftest-cpu", action="store_true", help=argparse.SUPPRESS)
+    p.add_argument("--image-size", type=int, default=224, help=argparse.SUPPRESS)
     return p.parse_args()
 
 
@@ -134,8 +138,13 @@ def main():
         os.environ["MASTER_ADDR"] = "127.0.0.1"
         os.environ["MASTER_PORT"] = str(find_free_network_port())
     os.environ.setdefault("LOCAL_WORLD_SIZE", str(world))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    cpu = args.selftest_cpu
+    if cpu:
+        dev, dtype = torch.device("cpu"), torch.float32
+    else:
+        torch.cuda.set_device(local_rank)
+        dev, dtype = torch.device("cuda", local_rank), torch.bfloat16
+    img = args.image_size
 
     import bagua_b200 as bagua
     from bagua_b200.models import get_model
@@ -149,7 +158,7 @@ def main():
     if args.fused_shard is None:
         args.fused_shard = world > 1 and args.algorithm == "gradient_allreduce"
     bs = args.batch_size
-    model = get_model(args.model).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
+    model = get_model(args.model).to(dev).to(dtype).to(memory_format=torch.channels_last)
     if args.fused_shard:
         from bagua_b200.parallel.algorithms.gradient_allreduce import FusedGradientAllReduceAlgorithm, make_sharded_fused_sgd
 
@@ -161,11 +170,12 @@ def main():
     model = model.with_bagua([optimizer], algorithm)
 
     # synthetic ImageNet batch (reference: fixed random data + target, synthetic_benchmark.py)
-    x_dev = torch.randn(bs, 3, 224, 224, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    x_dev = torch.randn(bs, 3, img, img, device=dev).to(dtype).contiguous(memory_format=torch.channels_last)
     y_dev = torch.randint(0, 1000, (bs,), device=dev)
     n_host = 4
-    x_host = [torch.randn(bs, 3, 224, 224).pin_memory() for _ in range(n_host)]
-    y_host = [torch.randint(0, 1000, (bs,)).pin_memory() for _ in range(n_host)]
+    pin = (lambda t: t) if cpu else (lambda t: t.pin_memory())
+    x_host = [pin(torch.randn(bs, 3, img, img)) for _ in range(n_host)]
+    y_host = [pin(torch.randint(0, 1000, (bs,))) for _ in range(n_host)]
 
     def train_step(x, y):
         optimizer.zero_grad()
@@ -178,7 +188,7 @@ def main():
     from bagua_b200.utils.data import DevicePrefetcher, LossReader
 
     def to_model_format(x, y):
-        return x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last), y
+        return x.to(dtype).contiguous(memory_format=torch.channels_last), y
 
     def host_batches(n):
         for i in range(n):
@@ -198,9 +208,27 @@ def main():
     def sync_all():
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+        if not cpu:
+            torch.cuda.synchronize()
+
+    def timed_host(fn, steps, whole_loop):
+        import time
+
+        sync_all()
+        t0 = time.perf_counter()
+        if whole_loop:
+            fn(steps)
+        else:
+            for i in range(steps):
+                fn(i)
+        ms = torch.tensor([(time.perf_counter() - t0) * 1e3])
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
 
     def timed(fn, steps, whole_loop=False):
+        if cpu:
+            return timed_host(fn, steps, whole_loop)
         sync_all()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.nvtx.range_push("timed")
@@ -238,10 +266,10 @@ def main():
         return 0
     from bagua_b200.core import native
 
-    torch.cuda.synchronize()
+    sync_all()
     launches0 = native().launch_count()  # every kernel of this library counts itself (csrc/common.h: count_launch)
     ms = timed(lambda i: train_step(x_dev, y_dev), args.steps)
-    model.bagua_ddp._bagua_backend.wait_pending_comm_ops(torch.cuda.current_stream().cuda_stream, False)
+    model.bagua_ddp._bagua_backend.wait_pending_comm_ops(0 if cpu else torch.cuda.current_stream().cuda_stream, cpu)
     gpu_launches = native().launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     value = bs * world * args.steps / (ms / 1e3)
@@ -270,14 +298,14 @@ def main():
             "higher_is_better": True,
             "scaling": "weak",
             "vs_baseline": value / (PUBLISHED_PER_GPU * world),
-            "dtype": "bf16",
+            "dtype": "bf16" if not cpu else "fp32",
             "data": "synthetic (random ImageNet-shaped batch, random-init weights)",
             "impl": "ours",
             "config": {
                 "model": args.model,
                 "global_batch": bs * world,
                 "per_gpu_batch": bs,
-                "image": "3x224x224",
+                "image": f"3x{img}x{img}",
                 "parallelism": f"dp{world}",
                 "algorithm": args.algorithm,
                 "optimizer": ("SGD fused into the bucket allreduce kernel (sharded fp32 master weights)" if args.fused_shard else f"FusedSGD(momentum={args.momentum}, fp32 master weights)"),
@@ -291,6 +319,8 @@ def main():
             "e2e": e2e,
             "gpu_launches": int(gpu_launches),
         }
+        if cpu:
+            out["selftest"] = "host plumbing check, not a benchmark result"
         sys.stdout.flush()
         os.dup2(saved_stdout_fd, 1)
         print(json.dumps(out), flush=True)

@@ -48,3 +48,61 @@ def test_baseline_config_benchmarks_run_tiny_in_bf16(config, tmp_path):
     line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
     out = json.loads(line)
     assert out["config"] == config and out["n_gpus"] == 2 and out["loss_finite"] and out["value"] > 0
+
+
+_BARE = {k: v for k, v in ENV.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+_CONTRACT_KEYS = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+                  "config", "clocks", "e2e", "gpu_launches")
+
+
+@pytest.mark.parametrize("ranks", [1, 2])
+def test_bench_contract_on_the_host(ranks, tmp_path):
+    """bench.py end to end in its host self-test mode, started exactly like the driver starts it: a bare ``python bench.py``
+    (no launcher, no RANK/WORLD_SIZE in the environment) for one rank, ``torch.distributed.run`` for two.  One JSON line on
+    stdout with every key of the contract; the e2e arm ran through DevicePrefetcher/LossReader."""
+    import json
+
+    from tests.mp_utils import free_port, run_in_session
+
+    tail = ["--selftest-cpu", "--image-size", "32", "--batch-size", "2", "--steps", "2", "--warmup", "3", "--gpus", str(ranks)]
+    if ranks == 1:
+        cmd = [sys.executable, os.path.join(REPO, "bench.py"), *tail]
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={ranks}", "--master-addr", "127.0.0.1",
+               "--master-port", str(free_port()), os.path.join(REPO, "bench.py"), *tail]
+    r = run_in_session(cmd, 600, env=_BARE, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines  # only the result may reach stdout
+    out = json.loads(lines[0])
+    assert all(k in out for k in _CONTRACT_KEYS), sorted(out)
+    assert out["n_gpus"] == ranks and out["steps"] == 2 and out["value"] > 0 and out["selftest"]
+    assert out["e2e"]["value"] > 0 and out["e2e"]["h2d_bytes_per_step"] == 2 * 3 * 32 * 32 * 4 + 2 * 8 and out["e2e"]["d2h_bytes_per_step"] == 4
+    assert out["config"]["global_batch"] == 2 * ranks and out["config"]["parallelism"] == f"dp{ranks}"
+
+
+def test_bench_reference_arm_reports_itself_unavailable(tmp_path):
+    import json
+
+    from tests.mp_utils import run_in_session
+
+    r = run_in_session([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "2", "--warmup", "3"], 120, env=_BARE,
+                       cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["impl"] == "reference" and ("unavailable" in out or "value" in out)
+
+
+def test_smoke_steps_without_a_launcher_environment(tmp_path):
+    """``__graft_entry__.smoke()``'s training steps on the host, from a process with no RANK/WORLD_SIZE/MASTER_* (how the driver calls
+    it): the default process group must come up as rank 0 of 1."""
+    from tests.mp_utils import run_in_session
+
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import torch, __graft_entry__ as g\n"
+            "loss, opt = g._smoke_steps(torch.device('cpu'), torch.float32)\n"
+            "import bagua_b200 as b\n"
+            "assert b.get_rank() == 0 and b.get_world_size() == 1 and torch.isfinite(loss.detach()).item()\n"
+            "print('SMOKE_HOST_OK')\n") % REPO
+    r = run_in_session([sys.executable, "-c", code], 300, env=_BARE, cwd=str(tmp_path))
+    assert r.returncode == 0 and "SMOKE_HOST_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
