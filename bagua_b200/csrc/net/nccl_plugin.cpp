@@ -176,7 +176,9 @@ ncclResult_t net_test(void* request, int* done, int* sizes) {
     *done = 0;
     if (r->pending.load(std::memory_order_acquire) > 0) return ncclSuccess;
     const bool failed = r->error.load(std::memory_order_relaxed) != 0;
-    const uint64_t dt = now_ns() - r->t_post_ns;
+    const uint64_t t_done = now_ns();
+    const uint64_t dt = t_done - r->t_post_ns;
+    trace_span(r->is_send, r->t_post_ns, t_done, r->size, failed);
     if (r->is_send) {
         stats().bytes_sent.fetch_add(r->size, std::memory_order_relaxed);
         stats().isend_ns.fetch_add(dt, std::memory_order_relaxed);
@@ -232,6 +234,8 @@ BAGUA_EXPORT int bagua_net_stats_json(char* buf, int cap) {
     }
     return static_cast<int>(s.size());
 }
+
+BAGUA_EXPORT void bagua_net_trace_flush() { bagua_net::trace_flush(); }
 
 BAGUA_EXPORT int bagua_net_device_count() { return static_cast<int>(bagua_net::discover_devices().size()); }
 }

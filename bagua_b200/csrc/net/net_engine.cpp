@@ -565,6 +565,66 @@ static void push_once(const std::string& host, const std::string& port, int rank
     freeaddrinfo(res);
 }
 
+namespace {
+struct Tracer {
+    FILE* f = nullptr;
+    std::mutex mu;
+    bool first = true;
+    int rank = 0;
+    unsigned since_flush = 0;
+    Tracer() {
+        const char* prefix = getenv("BAGUA_NET_TRACE_FILE");
+        const char* jaeger = getenv("BAGUA_NET_JAEGER_ADDRESS");
+        rank = static_cast<int>(env_long("RANK", 0));
+        std::string path;
+        if (prefix && *prefix) {
+            path = std::string(prefix) + "." + std::to_string(rank) + ".json";
+        } else if (jaeger && *jaeger) {
+            if (rank >= 8) return;  // the reference traces the first eight ranks only
+            const char* tmp = getenv("TMPDIR");
+            path = std::string(tmp && *tmp ? tmp : "/tmp") + "/bagua_net_trace." + std::to_string(rank) + ".json";
+            fprintf(stderr, "bagua-net: BAGUA_NET_JAEGER_ADDRESS is set; spans are written as a trace-event file to %s\n", path.c_str());
+        } else {
+            return;
+        }
+        f = fopen(path.c_str(), "w");
+        if (f) fputs("[\n", f);
+    }
+    ~Tracer() {
+        if (f) {
+            fputs("\n]\n", f);
+            fclose(f);
+        }
+    }
+};
+Tracer& tracer() {
+    static Tracer t;
+    return t;
+}
+}  // namespace
+
+void trace_span(bool is_send, uint64_t start_ns, uint64_t end_ns, size_t bytes, bool failed) {
+    Tracer& t = tracer();
+    if (!t.f) return;
+    std::lock_guard<std::mutex> lk(t.mu);
+    fprintf(t.f, "%s{\"name\":\"%s\",\"cat\":\"bagua_net\",\"ph\":\"X\",\"ts\":%.3f,\"dur\":%.3f,\"pid\":%d,\"tid\":%d,\"args\":{\"bytes\":%zu,\"ok\":%s}}",
+            t.first ? "" : ",\n", is_send ? "isend" : "irecv", start_ns / 1e3, (end_ns - start_ns) / 1e3, t.rank, is_send ? 0 : 1, bytes,
+            failed ? "false" : "true");
+    t.first = false;
+    if (++t.since_flush >= 256) {
+        fflush(t.f);
+        t.since_flush = 0;
+    }
+}
+
+void trace_flush() {
+    Tracer& t = tracer();
+    if (!t.f) return;
+    std::lock_guard<std::mutex> lk(t.mu);
+    fflush(t.f);
+    t.since_flush = 0;
+}
+
 void start_metrics_push_if_configured() {
     static std::once_flag once;
     std::call_once(once, [] {

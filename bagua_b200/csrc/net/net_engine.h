@@ -67,6 +67,12 @@ struct Stats {
 Stats& stats();
 // Starts (once) a thread pushing stats().prometheus() to BAGUA_NET_PROMETHEUS_ADDRESS ("host:port") every 5 s.
 void start_metrics_push_if_configured();
+// Span tracing (the reference exports isend/irecv spans to Jaeger for ranks < 8, nthread_per_socket_backend.rs:113-137,226).
+// BAGUA_NET_TRACE_FILE=<prefix> writes one Chrome/Perfetto trace-event file per rank (<prefix>.<rank>.json, "ph":"X" spans
+// named isend/irecv with byte counts); BAGUA_NET_JAEGER_ADDRESS alone selects the same exporter with the file under
+// $TMPDIR (no thrift/UDP Jaeger client is built in).  Off by default: trace_span() is one branch.
+void trace_span(bool is_send, uint64_t start_ns, uint64_t end_ns, size_t bytes, bool failed);
+void trace_flush();
 
 struct Request {
     std::atomic<int> pending{0};   // outstanding pieces (control header + chunks)

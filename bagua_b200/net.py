@@ -181,6 +181,10 @@ class PluginHandle:
         self.lib.bagua_net_stats_json(buf, 1024)
         return json.loads(buf.value.decode())
 
+    def trace_flush(self):
+        """Write buffered isend/irecv spans to the trace file (``BAGUA_NET_TRACE_FILE`` / ``BAGUA_NET_JAEGER_ADDRESS``)."""
+        self.lib.bagua_net_trace_flush()
+
 
 def loopback_probe(nbytes: int = 256 << 20, iters: int = 8) -> dict:
     """Throughput of one connection over the first usable interface (both ends in this process)."""

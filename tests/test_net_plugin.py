@@ -135,3 +135,40 @@ def test_enable_sets_nccl_environment():
     assert env["NCCL_NET_PLUGIN"] == "bagua" and env["BAGUA_NET_NSTREAMS"] == "8" and env["BAGUA_NET_MIN_CHUNKSIZE"] == str(1 << 19)
     first = env["LD_LIBRARY_PATH"].split(":")[0]
     assert os.path.exists(os.path.join(first, "libnccl-net-bagua.so")) and env["LD_LIBRARY_PATH"].endswith("/x")
+
+
+def test_span_trace_file(tmp_path):
+    """BAGUA_NET_TRACE_FILE: every completed isend/irecv becomes one trace-event span with its byte count (the reference ships
+    spans to Jaeger, nthread_per_socket_backend.rs:113-137).  The tracer reads its environment once per process → subprocess."""
+    import json
+    import subprocess
+    import sys
+
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys
+sys.path.insert(0, %r)
+import numpy as np
+from bagua_b200 import net as bnet
+bnet.build_if_needed() if hasattr(bnet, "build_if_needed") else None
+h = bnet.PluginHandle()
+handle, lc = h.listen(0)
+sc = h.connect(handle)
+rc = h.accept(lc)
+for n in (64, 100000, 3 << 20):
+    src = np.arange(n, dtype=np.uint8)
+    dst = np.zeros(n, dtype=np.uint8)
+    r = h.irecv(rc, dst.ctypes.data, n)
+    s = h.isend(sc, src.ctypes.data, n)
+    h.wait(s); h.wait(r)
+    assert (src == dst).all()
+h.trace_flush()
+h.close_send(sc); h.close_recv(rc); h.close_listen(lc)
+print("TRACE_OK")
+''' % repo
+    env = dict(os.environ, BAGUA_NET_TRACE_FILE=str(tmp_path / "spans"), RANK="3", NCCL_SOCKET_IFNAME="lo", BAGUA_NET_NSTREAMS="3", BAGUA_NET_MIN_CHUNKSIZE="65536")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "TRACE_OK" in r.stdout, r.stdout + r.stderr
+    events = json.loads((tmp_path / "spans.3.json").read_text())
+    assert sorted((e["name"], e["args"]["bytes"]) for e in events) == sorted([(k, n) for n in (64, 100000, 3 << 20) for k in ("isend", "irecv")])
+    assert all(e["ph"] == "X" and e["pid"] == 3 and e["dur"] >= 0 and e["args"]["ok"] for e in events)
