@@ -16,6 +16,7 @@ stream with the group's own signal pads, in the same order on every rank.
 """
 from __future__ import annotations
 
+import logging
 import os
 from typing import Dict, Optional, Tuple
 
@@ -24,6 +25,7 @@ import torch.distributed as dist
 
 from ..core import dtype_code, native
 
+logger = logging.getLogger(__name__)
 _contexts: Dict[int, Optional["MoEPeerContext"]] = {}
 
 
@@ -204,7 +206,8 @@ def get_context(group, world: int) -> Optional[MoEPeerContext]:
         if eng is not None:
             ctx = MoEPeerContext(eng)
             ctx._pg = pg
-    except Exception:  # noqa: BLE001
+    except Exception as e:  # noqa: BLE001
+        logger.warning("bagua_b200: MoE peer dispatch/combine unavailable (%s); using all_to_all_single", e)
         ctx = None
     _contexts[key] = ctx
     return ctx

@@ -113,7 +113,10 @@ def _native_functions():
                 from .. import _C_torch as ext  # built by bagua_b200/_build.py:build_torch_hooks
 
                 ext.nhwc_init(native().nhwc_api_ptr(), _finish_in_kernel())
-            except Exception:  # noqa: BLE001 - not built / not loadable: the Python Functions below do the same work
+            except Exception as e:  # noqa: BLE001 - not built / not loadable: the Python Functions below do the same work
+                import logging
+
+                logging.getLogger(__name__).warning("bagua_b200: BAGUA_NATIVE_NHWC=1 but the torch extension is unavailable (%s); using the Python Functions", e)
                 ext = None
         _native_fns[0] = ext
     return _native_fns[0]

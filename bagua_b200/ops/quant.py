@@ -45,7 +45,9 @@ def torch_compress_chunk(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     upper = torch.round(mx * scale)
     lower = upper - LEVELS
     level = torch.minimum(torch.round(xf * scale), upper)
-    return torch.stack([mn, mx]).to(x.dtype), (level - lower).to(torch.uint8)
+    # round-half-even can put min·scale 256 levels below upper (both products end in .5): the GPU's float→uint8 conversion
+    # saturates that −1 to 0; torch's CPU cast would wrap it to 255, so clamp explicitly
+    return torch.stack([mn, mx]).to(x.dtype), (level - lower).clamp_(0, LEVELS).to(torch.uint8)
 
 
 def torch_decompress_chunk(minmax: torch.Tensor, q: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:

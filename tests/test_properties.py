@@ -1,0 +1,125 @@
+"""Property-based tests (hypothesis) of the host-side invariants the kernels and the scheduler rely on."""
+import math
+
+import pytest
+import torch
+
+hypothesis = pytest.importorskip("hypothesis")
+from hypothesis import given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+DTYPES = ["f32", "f16", "bf16"]
+UNIT = {"f32": 4, "f16": 2, "bf16": 2}
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.lists(st.tuples(st.integers(1, 5_000_000), st.sampled_from(DTYPES)), min_size=1, max_size=40), st.integers(10, 26))
+def test_bucket_split_is_a_dtype_homogeneous_ordered_partition(tensors, size_2p):
+    """every tensor lands in exactly one bucket, a bucket holds one dtype, registration order is kept inside
+    a dtype, and a bucket closes as soon as it reaches the size (so only the last bucket of a dtype may be smaller)."""
+    from bagua_b200.define import TensorDeclaration
+    from bagua_b200.service.autotune_task_manager import split_bucket_by_bucket_size
+
+    decls = [TensorDeclaration(name=f"t{i}", num_elements=n, dtype=d) for i, (n, d) in enumerate(tensors)]
+    bucket_size = 1 << size_2p
+    buckets = split_bucket_by_bucket_size(decls, bucket_size)
+    flat = [td["name"] for b in buckets for td in b]
+    assert sorted(flat) == sorted(d["name"] for d in decls) and len(set(flat)) == len(flat)
+    per_dtype = {}
+    for b in buckets:
+        kinds = {str(getattr(td["dtype"], "value", td["dtype"])) for td in b}
+        assert len(kinds) == 1
+        per_dtype.setdefault(kinds.pop(), []).append(b)
+    for kind, bs in per_dtype.items():
+        order = [int(td["name"][1:]) for b in bs for td in b]
+        assert order == sorted(order)
+        for b in bs[:-1]:
+            nbytes = sum(td["num_elements"] * UNIT[kind] for td in b)
+            assert nbytes >= bucket_size and nbytes - b[-1]["num_elements"] * UNIT[kind] < bucket_size
+
+
+@settings(max_examples=100, deadline=None)
+@given(st.integers(1, 8), st.integers(1, 4000), st.floats(1e-3, 1e3), st.floats(-1e3, 1e3), st.sampled_from([torch.float32, torch.float16]))
+def test_minmax_uint8_roundtrip_error_bound(n_chunks, chunk, spread, offset, dtype):
+    """MinMaxUInt8 (reference bagua_kernels.cu:456-501): every chunk decodes to within one quantisation step of its input, the
+    compressed size follows the 32-byte-aligned wire format, and constant chunks survive exactly."""
+    from bagua_b200.ops import quant
+
+    torch.manual_seed(chunk * 31 + n_chunks)
+    if dtype == torch.float16:
+        spread, offset = min(spread, 100.0), max(min(offset, 100.0), -100.0)
+    x = (torch.rand(n_chunks * chunk) * spread + offset).to(dtype)
+    buf = quant.torch_compress(x, n_chunks)
+    assert buf.dtype == torch.uint8 and buf.numel() == quant.compressed_size(x.numel(), n_chunks)
+    y = quant.torch_decompress(buf, x.numel(), n_chunks, dtype)
+    for c in range(n_chunks):
+        xs, ys = x[c * chunk:(c + 1) * chunk].float(), y[c * chunk:(c + 1) * chunk].float()
+        step = (xs.max() - xs.min()).item() / 255.0
+        tol = step * 1.01 + (abs(xs).max().item() + 1.0) * (2e-3 if dtype == torch.float16 else 2e-6) + 1e-6
+        assert (xs - ys).abs().max().item() <= tol
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.integers(2, 64), st.integers(0, 500))
+def test_shift_one_pairs_every_rank_with_exactly_one_partner(nranks, step):
+    """shift_one peer selection (reference decentralized_full_precision_synchronous.rs:83-96) is an involution without fixed
+    points for even world sizes: rank r's partner names r back, so the pairwise exchange cannot deadlock."""
+    from bagua_b200.core import native
+
+    if nranks % 2:
+        nranks += 1
+    f = native().PeerAverageOp.shift_one_peer
+    peers = [f(r, nranks, step) for r in range(nranks)]
+    assert sorted(peers) == list(range(nranks))
+    assert all(peers[p] == r and p != r for r, p in enumerate(peers))
+
+
+def _flatten_worker(rank, world):
+    """Runs inside a one-rank process group (buckets register with the default group's scheduler)."""
+    import random
+
+    import bagua_b200 as bagua
+    from bagua_b200.bucket import BaguaBucket
+
+    bagua.init_process_group()
+    rng = random.Random(7)
+    for case in range(60):
+        alignment = rng.choice([1, 4, 8, 64])
+        shapes = [[rng.randint(1, 7) for _ in range(rng.randint(0, 3))] for _ in range(rng.randint(1, 8))]
+        ts = [(torch.randn(*shp) if shp else torch.randn(())).ensure_bagua_tensor(f"c{case}p{i}", f"prop{case}") for i, shp in enumerate(shapes)]
+        before = [t.clone() for t in ts]
+        b = BaguaBucket(ts, f"b{case}", flatten=True, alignment=alignment)
+        assert b.check_flatten()
+        total = sum(t.numel() for t in ts)
+        flat = b.backend_tensor
+        assert flat.numel() >= total and flat.numel() % alignment == 0 and flat.numel() - total < alignment
+        off = 0
+        for t, ref in zip(ts, before):
+            assert torch.equal(t, ref)
+            assert t.data_ptr() == flat.data_ptr() + off * t.element_size()
+            off += t.numel()
+        flat.fill_(3.0)  # writes through the flat tensor are visible in every member
+        assert all(bool((t == 3.0).all()) for t in ts)
+    return True
+
+
+def test_flattened_bucket_aliases_every_tensor():
+    """BaguaBucket(flatten=True): tensors become views of one flat tensor (in order, without gaps), values are preserved, the
+    padded length is the next multiple of the alignment and ``check_flatten`` holds — 60 random shape lists."""
+    from tests.mp_utils import run_distributed
+
+    assert all(run_distributed(_flatten_worker, world=1))
+
+
+@settings(max_examples=6, deadline=None)
+@given(st.integers(0, 2 ** 31), st.integers(5, 16))
+def test_bayesian_optimizer_stays_inside_the_declared_space(seed, rounds):
+    from bagua_b200.service.bayesian_optimizer import BayesianOptimizer, BoolParam, FloatParam, IntParam
+
+    space = {"i": IntParam(val=3, space_dimension=(1, 9)), "f": FloatParam(val=0.5, space_dimension=(0.25, 4.0)), "b": BoolParam(False)}
+    opt = BayesianOptimizer(space, n_initial_points=4, seed=seed % 1000)
+    for _ in range(rounds):
+        p = opt.ask()
+        assert isinstance(p["i"], int) and 1 <= p["i"] <= 9
+        assert 0.25 <= p["f"] <= 4.0 and isinstance(p["b"], bool)
+        opt.tell(p, -((p["i"] - 6) ** 2) - (math.log2(p["f"])) ** 2 + (0.5 if p["b"] else 0.0))
