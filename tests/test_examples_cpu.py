@@ -70,7 +70,7 @@ def test_bench_contract_on_the_host(ranks, tmp_path):
     else:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={ranks}", "--master-addr", "127.0.0.1",
                "--master-port", str(free_port()), os.path.join(REPO, "bench.py"), *tail]
-    r = run_in_session(cmd, 600, env=_BARE, cwd=str(tmp_path))
+    r = run_in_session(cmd, 600, env=dict(_BARE, OMP_NUM_THREADS="4"), cwd=str(tmp_path))  # torchrun would pin 1 thread per rank
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, lines  # only the result may reach stdout
