@@ -1,6 +1,8 @@
 // Multi-stream TCP transport — see net_engine.h for the design.
 #include "net_engine.h"
 
+#include <strings.h>
+
 #include <arpa/inet.h>
 #include <cerrno>
 #include <climits>
@@ -43,6 +45,13 @@ Config Config::from_env() {
     long m = env_long("BAGUA_NET_MIN_CHUNKSIZE", static_cast<long>(c.min_chunk));
     c.min_chunk = static_cast<size_t>(m < 4096 ? 4096 : m);
     c.sock_buf = static_cast<int>(env_long("BAGUA_NET_SOCKBUF", c.sock_buf));
+    // The reference selects between two transports with BAGUA_NET_IMPLEMENT=BASIC|TOKIO (rust/bagua-net/src/lib.rs:19-33); this
+    // plugin has one (thread per socket, condition-variable driven), so both names are accepted and anything else is reported.
+    const char* impl = getenv("BAGUA_NET_IMPLEMENT");
+    if (impl && *impl && strcasecmp(impl, "BASIC") != 0 && strcasecmp(impl, "TOKIO") != 0) {
+        static std::once_flag warned;
+        std::call_once(warned, [impl] { fprintf(stderr, "bagua-net: unknown BAGUA_NET_IMPLEMENT=%s (BASIC and TOKIO select the same transport here)\n", impl); });
+    }
     return c;
 }
 
