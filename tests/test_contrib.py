@@ -588,3 +588,132 @@ def test_vgg_fused_feature_path_on_cpu_through_the_native_extension(tmp_path, mo
             torch.testing.assert_close(a, b, rtol=8e-2, atol=8e-2 * max(1.0, b.abs().max().item()))
     finally:
         E.nhwc_init(0, False)
+
+
+def test_fused_linear_combine_autograd_with_a_host_double_of_the_peer_kernels():
+    """``ops.moe_peer.linear_combine`` (fc2 GEMM whose epilogue does the MoE combine): its hand-written backward — scatter of
+    grad·gate to the owners, dgrad / wgrad GEMMs, bias and gate-weight gradients — against plain autograd over
+    ``Σ_k gate[s,k] · (x·wᵀ + b)[expert, slot]``.  The two peer kernels are replaced by single-rank torch implementations of
+    their contracts (csrc/moe_kernels.cu scatter, gemm_tcgen05.cu PEER epilogue + local-layout gather)."""
+    from bagua_b200.ops import moe_peer
+
+    class HostContext(moe_peer.MoEPeerContext):
+        def __init__(self):
+            self.world, self.rank = 1, 0
+
+        def scatter(self, rows, expert_idx, slot_idx, scale, E_local, C):
+            out = torch.zeros(1, E_local, C, rows.shape[1], dtype=rows.dtype)
+            for s in range(rows.shape[0]):
+                for k in range(expert_idx.shape[1]):
+                    if slot_idx[s, k] >= 0:
+                        out[0, expert_idx[s, k], slot_idx[s, k]] = rows[s] * (scale[s, k] if scale is not None else 1.0)
+            return out
+
+        def linear_push_gather(self, x, w, bias, expert_idx, slot_idx, weights, S, C):
+            y = torch.bmm(x, w.transpose(1, 2)) + (bias.unsqueeze(1) if bias is not None else 0.0)
+            picked = torch.zeros(S, expert_idx.shape[1], w.shape[1], dtype=x.dtype)
+            for s in range(S):
+                for k in range(expert_idx.shape[1]):
+                    if slot_idx[s, k] >= 0:
+                        picked[s, k] = y[expert_idx[s, k], slot_idx[s, k]]
+            return (picked * weights.unsqueeze(-1)).sum(1).to(x.dtype), picked
+
+    torch.manual_seed(3)
+    E, C, K, N, S, topk = 3, 4, 8, 6, 7, 2
+    expert_idx = torch.stack([torch.randperm(E)[:topk] for _ in range(S)])
+    slot_idx = torch.full((S, topk), -1, dtype=torch.int64)
+    fill = [0] * E
+    for s in range(S):
+        for k in range(topk):
+            e = int(expert_idx[s, k])
+            if fill[e] < C:             # tokens beyond the capacity are dropped (slot −1)
+                slot_idx[s, k] = fill[e]
+                fill[e] += 1
+    assert (slot_idx < 0).any() and (slot_idx >= 0).any()
+
+    def inputs():
+        torch.manual_seed(4)
+        return [torch.randn(E, C, K, requires_grad=True), torch.randn(E, N, K, requires_grad=True), torch.randn(E, N, requires_grad=True),
+                torch.rand(S, topk, requires_grad=True)]
+
+    x, w, b, gate = inputs()
+    out = moe_peer.linear_combine(x, w, b, gate, expert_idx, slot_idx, HostContext(), C)
+    g = torch.randn_like(out)
+    out.backward(g)
+
+    xr, wr, br, gr = inputs()
+    y = torch.bmm(xr, wr.transpose(1, 2)) + br.unsqueeze(1)
+    valid = (slot_idx >= 0)
+    rows = y[expert_idx.clamp(min=0), slot_idx.clamp(min=0)] * valid.unsqueeze(-1)
+    ref = (rows * gr.unsqueeze(-1)).sum(1)
+    ref.backward(g)
+    torch.testing.assert_close(out, ref)
+    for got, want, name in [(x.grad, xr.grad, "x"), (w.grad, wr.grad, "w"), (b.grad, br.grad, "bias"), (gate.grad, gr.grad, "gate")]:
+        torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5, msg=lambda m, name=name: f"grad of {name}: {m}")
+
+
+def test_experts_forward_combine_equals_experts_then_combine_on_the_host():
+    """``Experts.forward_combine`` (fc1 → GELU → fc2 with the combine in the GEMM epilogue) against the two-step path
+    ``combine(experts(x))`` — outputs and the gradients of every expert parameter, the dispatched tokens and the gate weights;
+    peer kernels replaced by single-rank host doubles (see the test above)."""
+    from bagua_b200.ops import moe_peer
+    from bagua_b200.parallel.moe.experts import Experts
+
+    class MLP(torch.nn.Module):
+        grouped_gemm_compatible = True
+
+        def __init__(self, m, h):
+            super().__init__()
+            self.fc1, self.fc2 = torch.nn.Linear(m, h), torch.nn.Linear(h, m)
+
+        def forward(self, x):
+            return self.fc2(torch.nn.functional.gelu(self.fc1(x), approximate="tanh"))
+
+    class HostContext(moe_peer.MoEPeerContext):
+        def __init__(self):
+            self.world, self.rank = 1, 0
+
+        def scatter(self, rows, expert_idx, slot_idx, scale, E_local, C):
+            out = torch.zeros(1, E_local, C, rows.shape[1], dtype=rows.dtype)
+            ok = slot_idx >= 0
+            s_idx, k_idx = ok.nonzero(as_tuple=True)
+            out[0, expert_idx[s_idx, k_idx], slot_idx[s_idx, k_idx]] = rows[s_idx] * (scale[s_idx, k_idx].unsqueeze(-1) if scale is not None else 1.0)
+            return out
+
+        def linear_push_gather(self, x, w, bias, expert_idx, slot_idx, weights, S, C):
+            y = torch.bmm(x, w.transpose(1, 2)) + (bias.unsqueeze(1) if bias is not None else 0.0)
+            ok = (slot_idx >= 0).unsqueeze(-1)
+            picked = y[expert_idx.clamp(min=0), slot_idx.clamp(min=0)] * ok
+            return (picked * weights.unsqueeze(-1)).sum(1).to(x.dtype), picked
+
+    torch.manual_seed(11)
+    E, C, M, H, S, topk = 2, 5, 6, 10, 8, 2
+    experts = Experts(MLP(M, H), E)
+    for p in experts.parameters():
+        torch.nn.init.normal_(p, std=0.3)
+    expert_idx = torch.stack([torch.randperm(E)[:topk] for _ in range(S)])
+    slot_idx = torch.full((S, topk), -1, dtype=torch.int64)
+    fill = [0] * E
+    for s in range(S):
+        for k in range(topk):
+            e = int(expert_idx[s, k])
+            if fill[e] < C:
+                slot_idx[s, k], fill[e] = fill[e], fill[e] + 1
+    g_out = torch.randn(S, M)
+
+    def run(fused: bool):
+        experts.zero_grad()
+        torch.manual_seed(12)
+        x = torch.randn(1, E, C, M, requires_grad=True)
+        gate = torch.rand(S, topk, requires_grad=True)
+        if fused:
+            out = experts.forward_combine(x, gate, expert_idx, slot_idx, HostContext())
+        else:
+            y = experts(x)[0]                                                   # [E, C, M]
+            ok = (slot_idx >= 0).unsqueeze(-1)
+            out = (y[expert_idx.clamp(min=0), slot_idx.clamp(min=0)] * ok * gate.unsqueeze(-1)).sum(1)
+        out.backward(g_out)
+        return [out.detach(), x.grad, gate.grad] + [p.grad.clone() for p in experts.parameters()]
+
+    for a, b in zip(run(True), run(False)):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
