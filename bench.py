@@ -39,6 +39,8 @@ def parse():
     p.add_argument("--fused-shard", dest="fused_shard", action="store_true", default=None,
                    help="fold the SGD update into the allreduce kernel (sharded optimizer state); default: on for N > 1")
     p.add_argument("--no-fused-shard", dest="fused_shard", action="store_false")
+    p.add_argument("--cuda-graph", action="store_true",
+                   help="experimental, one GPU only: replay the whole step from a CUDA graph (bagua_b200.utils.graph.GraphedTrainStep)")
     # plumbing self-test used by tests/ (no GPU there): the same code path end to end on the host with a small image; its
     # output is marked "selftest" and is not a benchmark result
     p.add_argument("--selftest-cpu", action="store_true", help=argparse.SUPPRESS)
@@ -195,13 +197,14 @@ def main():
             yield x_host[i % n_host], y_host[i % n_host]
 
     loss_reader = LossReader(dev)
+    e2e_step = [train_step]  # replaced by the graphed step with --cuda-graph
 
     def e2e_loop(steps):
         """The loop a user writes: pinned host batches → DevicePrefetcher (H2D of batch i+1 overlaps step i) → train step →
         asynchronous D2H read of every step's loss."""
         last = None
         for x, y in DevicePrefetcher(host_batches(steps), dev, to_model_format):
-            loss = train_step(x, y)
+            loss = e2e_step[0](x, y)
             last = loss_reader.push(loss)
         return loss_reader.flush()
 
@@ -267,15 +270,29 @@ def main():
     from bagua_b200.core import native
 
     sync_all()
+    step_fn = train_step
+    launches_per_replay = 0
+    if args.cuda_graph:
+        if world != 1 or cpu:
+            raise SystemExit("--cuda-graph captures a step without communication: one GPU only")
+        from bagua_b200.utils.graph import GraphedTrainStep
+
+        before = native().launch_count()
+        train_step(x_dev, y_dev)                      # kernels replayed from a graph do not pass the launch counter: count one eager step
+        launches_per_replay = native().launch_count() - before
+        step_fn = GraphedTrainStep(model, train_step, (x_dev, y_dev), optimizers=[optimizer])
+        step_fn(x_dev, y_dev)                         # capture happens on the first call, outside the timed region
+        sync_all()
     launches0 = native().launch_count()  # every kernel of this library counts itself (csrc/common.h: count_launch)
-    ms = timed(lambda i: train_step(x_dev, y_dev), args.steps)
+    ms = timed(lambda i: step_fn(x_dev, y_dev), args.steps)
     model.bagua_ddp._bagua_backend.wait_pending_comm_ops(0 if cpu else torch.cuda.current_stream().cuda_stream, cpu)
-    gpu_launches = native().launch_count() - launches0
+    gpu_launches = native().launch_count() - launches0 + launches_per_replay * args.steps
     clocks = sampler.stop() if rank == 0 else None
     value = bs * world * args.steps / (ms / 1e3)
 
     e2e = None
     if not args.no_e2e:
+        e2e_step[0] = step_fn
         try:
             e2e_loop(3)
             ms_e2e = timed(e2e_loop, args.steps, whole_loop=True)
@@ -311,7 +328,8 @@ def main():
                 "optimizer": ("SGD fused into the bucket allreduce kernel (sharded fp32 master weights)" if args.fused_shard else f"FusedSGD(momentum={args.momentum}, fp32 master weights)"),
                 "allreduce_variants": variants,
                 "buckets": len(model.bagua_buckets),
-                "host_opts": {k: os.environ.get(k, "0") for k in ("BAGUA_NATIVE_HOOKS", "BAGUA_NATIVE_NHWC", "BAGUA_NHWC_FINALIZE")},
+                "host_opts": dict({k: os.environ.get(k, "0") for k in ("BAGUA_NATIVE_HOOKS", "BAGUA_NATIVE_NHWC", "BAGUA_NHWC_FINALIZE")},
+                                  cuda_graph=bool(args.cuda_graph)),
                 "l2_policy": "working set (276 MB bf16 weights + activations) far exceeds the 126 MB L2; no explicit flush",
                 "baseline_note": "vs_baseline = value / (126.5 img/s/GPU x N): Bagua+Bagua-Net VGG16 fp32 on 32x V100 (rust/bagua-net/README.md:52-67)",
             },

@@ -24,6 +24,9 @@ one)
   echo "bench (C++ nhwc functions) exit=$?" | tee -a gpurun_out/plan_one.txt
   BAGUA_NATIVE_HOOKS=1 BAGUA_NATIVE_NHWC=1 BAGUA_NHWC_FINALIZE=1 timeout 120 python bench.py --steps 30 --warmup 5 > gpurun_out/bench1_all_host_opts.json 2> gpurun_out/bench1_all_host_opts.err
   echo "bench (native hooks + C++ nhwc functions + in-kernel finish) exit=$?" | tee -a gpurun_out/plan_one.txt
+  # whole step replayed from a CUDA graph (gated test test_graphed_train_step_matches_eager_steps must have passed above)
+  timeout 180 python bench.py --steps 30 --warmup 5 --cuda-graph > gpurun_out/bench1_cuda_graph.json 2> gpurun_out/bench1_cuda_graph.err
+  echo "bench (cuda graph) exit=$?" | tee -a gpurun_out/plan_one.txt
   ;;
 two)
   # opt-in kernels written without hardware access in round 1: fused GEMM+combine, fused allreduce+Adam, mixed-precision Adam

@@ -717,3 +717,32 @@ def test_experts_forward_combine_equals_experts_then_combine_on_the_host():
 
     for a, b in zip(run(True), run(False)):
         torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
+
+
+def test_graphed_train_step_refuses_what_it_cannot_capture():
+    """utils.graph.GraphedTrainStep: optimizers with per-step host state and replicas that communicate inside the step are
+    rejected up front (a silently dropped all-reduce or a frozen Adam bias correction would train the wrong model)."""
+    from bagua_b200.ops.optim import FusedAdam, FusedSGD
+    from bagua_b200.utils.graph import GraphedTrainStep, graph_safe_optimizer
+
+    lin = torch.nn.Linear(4, 4)
+    assert graph_safe_optimizer(FusedSGD(lin.parameters(), lr=0.1)) is None
+    assert graph_safe_optimizer(torch.optim.SGD(lin.parameters(), lr=0.1, momentum=0.9)) is None
+    assert "step count" in graph_safe_optimizer(FusedAdam(lin.parameters()))
+    assert "capturable" in graph_safe_optimizer(torch.optim.Adam(lin.parameters()))
+    with pytest.raises(ValueError):
+        GraphedTrainStep(lin, lambda x: lin(x).sum(), (torch.randn(2, 4),), optimizers=[FusedAdam(lin.parameters())])
+
+    class FakeGroup:
+        def size(self):
+            return 2
+
+    class FakeEngine:
+        process_group, require_backward_grad_sync = FakeGroup(), True
+
+    lin.bagua_ddp = FakeEngine()
+    with pytest.raises(NotImplementedError):
+        GraphedTrainStep(lin, lambda x: lin(x).sum(), (torch.randn(2, 4),), optimizers=[FusedSGD(lin.parameters(), lr=0.1)])
+    FakeEngine.require_backward_grad_sync = False          # inside no_sync(): nothing is communicated → only the device check is left
+    with pytest.raises(RuntimeError):
+        GraphedTrainStep(lin, lambda x: lin(x).sum(), (torch.randn(2, 4),), optimizers=[FusedSGD(lin.parameters(), lr=0.1)])

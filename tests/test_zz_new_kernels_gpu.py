@@ -109,3 +109,65 @@ def test_native_nhwc_functions_match_python_functions(dev, monkeypatch):
         for a, b in zip(results[0], other):
             torch.testing.assert_close(a, b, rtol=2e-2, atol=2e-2 * max(1.0, a.abs().max().item()))
     nhwc._native_fns[0] = False
+
+
+@pytest.mark.skipif(__import__("os").environ.get("BAGUA_EXPERIMENTAL") != "1", reason="CUDA-graph step capture: opt-in until validated on hardware")
+def test_graphed_train_step_matches_eager_steps():
+    """utils.graph.GraphedTrainStep (one-rank with_bagua model, FusedSGD with momentum, fused NHWC epilogues) — separate interpreter so
+    a capture failure cannot poison this process's CUDA context."""
+    import os
+    import subprocess
+    import sys
+
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import os, sys, copy, torch
+import torch.nn.functional as F
+sys.path.insert(0, %r)
+import bagua_b200 as bagua
+from bagua_b200.env import find_free_network_port
+from bagua_b200.models import vgg16
+from bagua_b200.ops.optim import FusedSGD
+from bagua_b200.parallel.algorithms import gradient_allreduce
+from bagua_b200.utils.graph import GraphedTrainStep
+os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", str(find_free_network_port()))
+torch.cuda.set_device(0); dev = torch.device("cuda", 0)
+bagua.init_process_group()
+torch.backends.cudnn.benchmark = False
+torch.manual_seed(0)
+base = vgg16(num_classes=10, dropout=0.0).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
+def make(tag):
+    m = copy.deepcopy(base)
+    opt = FusedSGD(m.parameters(), lr=0.01, momentum=0.9)
+    m = m.with_bagua([opt], gradient_allreduce.GradientAllReduceAlgorithm())
+    def step(x, y):
+        opt.zero_grad()
+        loss = F.cross_entropy(m(x).float(), y)
+        loss.backward()
+        opt.step()
+        return loss
+    return m, opt, step
+batches = [(torch.randn(4, 3, 64, 64, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last), torch.randint(0, 10, (4,), device=dev)) for _ in range(6)]
+m1, o1, eager = make("eager")
+m2, o2, step2 = make("graphed")
+g = GraphedTrainStep(m2, step2, batches[0], optimizers=[o2], warmup=3)
+for _ in range(3):                      # the capture warms up with three real steps on batch 0: mirror them
+    eager(*batches[0])
+losses = []
+for x, y in batches[:4]:
+    le = eager(x, y)
+    lg = g(x, y).clone()
+    losses.append((float(le), float(lg)))
+torch.cuda.synchronize()
+for le, lg in losses:
+    assert abs(le - lg) <= 2e-2 * max(1.0, abs(le)), losses
+for p, q in zip(m1.parameters(), m2.parameters()):
+    assert torch.allclose(p.float(), q.float(), rtol=2e-2, atol=2e-2)
+assert g.captures == 1 and g.replays == 4
+o2.param_groups[0]["lr"] = 0.005             # a schedule step → re-capture
+g(*batches[4]); torch.cuda.synchronize()
+assert g.captures == 2 and torch.isfinite(g.static_loss).item()
+print("GRAPH_OK", losses)
+''' % repo
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "GRAPH_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
