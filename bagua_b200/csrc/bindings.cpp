@@ -139,6 +139,10 @@ PYBIND11_MODULE(_C, m) {
         .def("watchdog_error", &Backend::watchdog_error)
         .def("set_record_spans", &Backend::set_record_spans)
         .def("set_profile", &Backend::set_profile)
+        .def("set_inline", &Backend::set_inline)
+        .def("inline_mode", &Backend::inline_mode)
+        .def("graph_capturable", &Backend::graph_capturable)
+        .def("inline_total", &Backend::inline_total)
         .def("bucket_stats",
              [](Backend& b, bool reset) {
                  py::list out;

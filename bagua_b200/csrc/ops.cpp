@@ -196,7 +196,11 @@ void LowPrecRingOp::run(Bucket&, StreamHandle stream, int) {
                       cfg_.nblocks, cfg_.nthreads, S(stream));
 }
 
-void CopyOp::run(Bucket&, StreamHandle stream, int) {
+void CopyOp::run(Bucket&, StreamHandle stream, int device) {
+    if (device < 0) {  // CPU backend: plain host copy
+        std::memcpy(reinterpret_cast<void*>(dst_), reinterpret_cast<const void*>(src_), bytes_);
+        return;
+    }
     BAGUA_CUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<void*>(dst_), reinterpret_cast<const void*>(src_), bytes_, cudaMemcpyDeviceToDevice,
                                      S(stream)));
 }

@@ -115,6 +115,7 @@ public:
           master_(master), momentum_(momentum), scale_(scale), zero_grads_(zero_grads), use_mc_(use_multimem), cfg_(cfg) {}
     const char* kind() const override { return "allreduce_sgd"; }
     void run(Bucket&, StreamHandle stream, int device) override;
+    bool step_invariant() const override { return steps_ > 0; }  // only the very first launch differs (momentum initialisation)
     void set_hyper(float lr, float momentum, float dampening, float weight_decay, bool nesterov) {
         std::lock_guard<std::mutex> lk(mu_);
         hp_.lr = lr, hp_.momentum = momentum, hp_.dampening = dampening, hp_.weight_decay = weight_decay, hp_.nesterov = nesterov;
@@ -184,6 +185,7 @@ public:
           master_(master), m1_(exp_avg), m2_(exp_avg_sq), scale_(scale), zero_grads_(zero_grads), use_mc_(use_multimem), cfg_(cfg) {}
     const char* kind() const override { return "allreduce_adam"; }
     void run(Bucket&, StreamHandle stream, int device) override;
+    bool step_invariant() const override { return false; }  // bias corrections are passed by value
     void set_hyper(float lr, float beta1, float beta2, float eps, float weight_decay, bool adamw) {
         std::lock_guard<std::mutex> lk(mu_);
         lr_ = lr, b1_ = beta1, b2_ = beta2, eps_ = eps, wd_ = weight_decay, adamw_ = adamw;
@@ -217,6 +219,7 @@ public:
         : comm_(std::move(comm)), weights_(weights), off_(off), out_(out), bytes_(bytes), dtype_(dtype), cfg_(cfg) {}
     const char* kind() const override { return "peer_average_shift_one"; }
     void run(Bucket&, StreamHandle stream, int device) override;
+    bool step_invariant() const override { return false; }  // the partner rotates with the step
     static int shift_one_peer(int rank, int nranks, int64_t step);
     int64_t step() const { return step_; }
 

@@ -295,6 +295,26 @@ void Backend::schedule_locked(std::unique_lock<std::mutex>& lk) {
         b->user_events_.clear();
         b->producer_stream_set_ = false;
         tk->t_sched = std::chrono::steady_clock::now();
+        bool issue_inline = inline_.load(std::memory_order_relaxed) && queue_.empty() && !in_flight_;
+        if (issue_inline)
+            for (auto& op : b->ops()) issue_inline = issue_inline && !op->host_blocking();
+        if (issue_inline) {
+            // the marking thread issues the bucket itself (asynchronous launches only), still under mu_: nothing can overtake it
+            BAGUA_LOG(DEBUG, "bucket %s ready: issued inline (%zu wait events)", b->name().c_str(), tk->wait_events.size());
+            not_waited_.push_back(tk);
+            scheduled_total_++;
+            inline_total_++;
+            if (b == ordered_.front()) iteration_++;
+            in_flight_ = tk;
+            int prev_dev = -1;
+            if (device_ >= 0 && cudaGetDevice(&prev_dev) == cudaSuccess && prev_dev != device_) cudaSetDevice(device_);
+            issue_ticket(tk);
+            if (device_ >= 0 && prev_dev >= 0 && prev_dev != device_) cudaSetDevice(prev_dev);
+            tk->issued = true;
+            in_flight_.reset();
+            cv_done_.notify_all();
+            continue;
+        }
         BAGUA_LOG(DEBUG, "bucket %s ready: scheduled (%zu in queue, %zu wait events)", b->name().c_str(), queue_.size() + 1, tk->wait_events.size());
         queue_.push_back(tk);
         not_waited_.push_back(tk);
@@ -302,6 +322,54 @@ void Backend::schedule_locked(std::unique_lock<std::mutex>& lk) {
         if (b == ordered_.front()) iteration_++;  // wrapped around the whole list (single bucket case)
         cv_worker_.notify_one();
     }
+}
+
+void Backend::issue_ticket(const std::shared_ptr<Ticket>& tk) {
+    try {
+        if (device_ >= 0)
+            for (auto e : tk->wait_events) BAGUA_CUDA_CHECK(cudaStreamWaitEvent(S(stream_), E(e), 0));
+        const bool prof = profile_.load(std::memory_order_relaxed);
+        ProfSample smp;
+        std::chrono::steady_clock::time_point t_issue;
+        if (prof) {
+            t_issue = std::chrono::steady_clock::now();
+            smp.name = tk->bucket->name();
+            smp.queue_ms = std::chrono::duration<double, std::milli>(t_issue - tk->t_sched).count();
+            if (device_ >= 0) {
+                smp.start = acquire_timing_event();
+                smp.stop = acquire_timing_event();
+                BAGUA_CUDA_CHECK(cudaEventRecord(E(smp.start), S(stream_)));
+            }
+        }
+        nvtxRangePushA(tk->bucket->name().c_str());
+        for (auto& op : tk->bucket->ops()) {
+            nvtxRangePushA(op->kind());
+            BAGUA_LOG(TRACE, "bucket %s: issuing op %s", tk->bucket->name().c_str(), op->kind());
+            op->run(*tk->bucket, stream_, device_);
+            nvtxRangePop();
+        }
+        nvtxRangePop();
+        if (prof) {
+            if (device_ >= 0)
+                BAGUA_CUDA_CHECK(cudaEventRecord(E(smp.stop), S(stream_)));
+            else
+                smp.host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_issue).count();
+            std::lock_guard<std::mutex> plk(prof_mu_);
+            prof_pending_.push_back(std::move(smp));
+        }
+        if (device_ >= 0) {
+            tk->done_event = acquire_event();
+            BAGUA_CUDA_CHECK(cudaEventRecord(E(tk->done_event), S(stream_)));
+        }
+    } catch (const std::exception& ex) {
+        tk->failed = true;
+        tk->error = ex.what();
+        BAGUA_LOG(ERROR, "communication of %s failed: %s", tk->bucket->describe_ops().c_str(), ex.what());
+    } catch (...) {
+        tk->failed = true;
+        tk->error = "unknown error in comm op";
+    }
+    for (auto e : tk->pooled_waits) release_event(e);
 }
 
 void Backend::worker_loop() {
@@ -317,56 +385,12 @@ void Backend::worker_loop() {
             in_flight_ = tk;
             cv_space_.notify_all();
         }
-        try {
-            if (device_ >= 0) {
-                if (!device_set) {
-                    BAGUA_CUDA_CHECK(cudaSetDevice(device_));
-                    device_set = true;
-                }
-                for (auto e : tk->wait_events) BAGUA_CUDA_CHECK(cudaStreamWaitEvent(S(stream_), E(e), 0));
-            }
-            const bool prof = profile_.load(std::memory_order_relaxed);
-            ProfSample smp;
-            std::chrono::steady_clock::time_point t_issue;
-            if (prof) {
-                t_issue = std::chrono::steady_clock::now();
-                smp.name = tk->bucket->name();
-                smp.queue_ms = std::chrono::duration<double, std::milli>(t_issue - tk->t_sched).count();
-                if (device_ >= 0) {
-                    smp.start = acquire_timing_event();
-                    smp.stop = acquire_timing_event();
-                    BAGUA_CUDA_CHECK(cudaEventRecord(E(smp.start), S(stream_)));
-                }
-            }
-            nvtxRangePushA(tk->bucket->name().c_str());
-            for (auto& op : tk->bucket->ops()) {
-                nvtxRangePushA(op->kind());
-                BAGUA_LOG(TRACE, "bucket %s: issuing op %s", tk->bucket->name().c_str(), op->kind());
-                op->run(*tk->bucket, stream_, device_);
-                nvtxRangePop();
-            }
-            nvtxRangePop();
-            if (prof) {
-                if (device_ >= 0)
-                    BAGUA_CUDA_CHECK(cudaEventRecord(E(smp.stop), S(stream_)));
-                else
-                    smp.host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_issue).count();
-                std::lock_guard<std::mutex> plk(prof_mu_);
-                prof_pending_.push_back(std::move(smp));
-            }
-            if (device_ >= 0) {
-                tk->done_event = acquire_event();
-                BAGUA_CUDA_CHECK(cudaEventRecord(E(tk->done_event), S(stream_)));
-            }
-        } catch (const std::exception& ex) {
-            tk->failed = true;
-            tk->error = ex.what();
-            BAGUA_LOG(ERROR, "communication of %s failed: %s", tk->bucket->describe_ops().c_str(), ex.what());
-        } catch (...) {
-            tk->failed = true;
-            tk->error = "unknown error in comm op";
+        if (device_ >= 0 && !device_set) {
+            cudaError_t de = cudaSetDevice(device_);
+            if (de != cudaSuccess) BAGUA_LOG(ERROR, "cudaSetDevice(%d) failed on the comm worker: %s", device_, cudaGetErrorString(de));
+            device_set = true;
         }
-        for (auto e : tk->pooled_waits) release_event(e);
+        issue_ticket(tk);
         {
             std::lock_guard<std::mutex> lk(mu_);
             tk->issued = true;
@@ -398,6 +422,14 @@ void Backend::watchdog_loop() {
             cv_done_.notify_all();
         }
     }
+}
+
+bool Backend::graph_capturable() {
+    std::lock_guard<std::mutex> lk(mu_);
+    for (auto& b : ordered_)
+        for (auto& op : b->ops())
+            if (op->host_blocking() || !op->step_invariant()) return false;
+    return true;
 }
 
 std::string Backend::watchdog_error() {

@@ -72,6 +72,11 @@ public:
     virtual const char* kind() const = 0;
     // Launch (never host-block on GPU work) on `stream`. device < 0 ⇒ CPU mode.
     virtual void run(Bucket& bucket, StreamHandle stream, int device) = 0;
+    // True for ops that may block the calling thread or need the GIL (python callbacks): never issued inline.
+    virtual bool host_blocking() const { return false; }
+    // False for ops whose launch arguments change from step to step (step counters, rotating peers): a CUDA graph would
+    // freeze them, so such a bucket program must not be captured.
+    virtual bool step_invariant() const { return true; }
 };
 
 class CallbackOp final : public CommOp {
@@ -80,6 +85,7 @@ public:
     explicit CallbackOp(Fn fn, std::string label = "python") : fn_(std::move(fn)), label_(std::move(label)) {}
     const char* kind() const override { return label_.c_str(); }
     void run(Bucket& bucket, StreamHandle, int) override;
+    bool host_blocking() const override { return true; }
 
 private:
     Fn fn_;
@@ -168,6 +174,15 @@ public:
     std::vector<ReadySpan> pop_ready_spans();
     void set_record_spans(bool on) { record_spans_ = on; }
     void set_profile(bool on) { profile_ = on; }
+    // Inline issue: a bucket whose program consists of native (asynchronously launching) ops only is issued by the thread
+    // that marks its last tensor ready instead of being handed to the worker thread — no thread hand-off on the critical
+    // path, and every CUDA call happens on the marking thread, which is what a stream capture (CUDA graph) needs. Order is
+    // preserved: a bucket is issued inline only while the worker has nothing queued or in flight.
+    void set_inline(bool on) { inline_ = on; }
+    bool inline_mode() const { return inline_.load(); }
+    // Every registered bucket consists of native ops with step-invariant launch arguments (or has no ops at all).
+    bool graph_capturable();
+    uint64_t inline_total() const { return inline_total_.load(); }
     // Folds every finished measurement into the table and returns it (non-blocking: kernels still running stay pending).
     std::vector<BucketStat> bucket_stats(bool reset = false);
     uint64_t scheduled_total() const { return scheduled_total_.load(); }
@@ -191,6 +206,7 @@ private:
     void schedule_locked(std::unique_lock<std::mutex>& lk);
     void on_tensor_ready_locked(const std::shared_ptr<Tensor>& t, std::unique_lock<std::mutex>& lk);
     void worker_loop();
+    void issue_ticket(const std::shared_ptr<Ticket>& tk);  // waits, ops, done event; never touches mu_
     void watchdog_loop();
     EventHandle acquire_event();
     void release_event(EventHandle e);
@@ -202,6 +218,8 @@ private:
     std::atomic<bool> watchdog_fatal_{true};
     std::atomic<bool> record_spans_{false};
     std::atomic<bool> profile_{false};
+    std::atomic<bool> inline_{false};
+    std::atomic<uint64_t> inline_total_{0};
     struct ProfSample {
         std::string name;
         EventHandle start = nullptr, stop = nullptr;  // GPU backend

@@ -104,6 +104,10 @@ class BaguaDistributedDataParallel:
         module._bagua_states._bagua_framework_hooks = []
 
         self._bagua_backend = comm_mod.get_backend(self.bagua_module_name)
+        if os.environ.get("BAGUA_INLINE_COMM", "0") == "1":
+            # native bucket programs are launched by the autograd thread that completes the bucket (no hand-off to the
+            # scheduler's worker thread); python ops keep using the worker. Required for CUDA-graph capture (utils/graph.py).
+            self._bagua_backend.set_inline(True)
         self._bagua_hyperparameters = BaguaHyperparameter()
         self._report_metrics = env.is_report_metrics_switch_on()   # BAGUA_REPORT_METRICS / --report_metrics
         self._report_every = 100

@@ -7,9 +7,13 @@ vgg16_n1_torch_profiler.txt), so any extra host work — data loading, logging, 
 
 Scope (deliberately narrow, see docs/kernels.md):
 
-* replicas that do not communicate inside the step — world size 1, or a gradient-accumulation micro-step under ``no_sync()``.
-  Bucket communication is issued by the scheduler's worker thread on the communication stream, which cannot take part in a
-  capture; with more than one rank the constructor refuses instead of silently dropping the all-reduce;
+* one rank (or a micro-step under ``no_sync()``): the gradient hooks are switched off for the step, nothing is communicated;
+* several ranks: the scheduler is put in *inline issue* mode (``Backend::set_inline``, csrc/scheduler.h) — the autograd thread
+  that marks a bucket's last gradient launches the bucket's kernels itself on the communication stream, so every CUDA call
+  of the step happens on capturing streams (fork: comm stream waits for the "gradients ready" event; join: the main stream
+  waits for the bucket's done event in the post-backward hook).  The peer kernels read their barrier epochs from device
+  memory, so a replay is indistinguishable from a fresh launch as long as every rank replays the same graph.  Bucket
+  programs that contain python ops (gloo / NCCL fallbacks, QAdam's momentum op) run on the worker thread and are refused;
 * optimizers whose kernel arguments do not change from step to step: :class:`bagua_b200.ops.optim.FusedSGD`,
   ``torch.optim.SGD`` and torch optimizers constructed with ``capturable=True``.  :class:`FusedAdam` passes the step count
   (bias correction) by value and is rejected.  A changed learning rate is detected on the next call and triggers a re-capture.
@@ -55,10 +59,9 @@ class GraphedTrainStep:
                 raise ValueError(f"optimizer cannot be captured in a CUDA graph: {why}")
         inner = getattr(model, "inner", None)  # DistributedDataParallel wrapper: .inner is the engine
         self.ddp = getattr(model, "bagua_ddp", None) or (inner if hasattr(inner, "require_backward_grad_sync") else None)
-        if self.ddp is not None and self.ddp.process_group.size() > 1 and self.ddp.require_backward_grad_sync:
-            raise NotImplementedError(
-                "GraphedTrainStep captures steps without bucket communication (world size 1 or inside no_sync()); with "
-                f"{self.ddp.process_group.size()} ranks the all-reduce runs on the scheduler's stream and cannot be captured")
+        self.communicates = bool(self.ddp is not None and self.ddp.process_group.size() > 1 and self.ddp.require_backward_grad_sync)
+        if self.communicates and getattr(self.ddp, "_speed_metrics_switch_on", False):
+            raise NotImplementedError("autotune / speed metrics record timing events every step and cannot be captured; switch them off")
         if not torch.cuda.is_available() or any(not t.is_cuda for t in example_inputs):
             raise RuntimeError("GraphedTrainStep needs a CUDA device and CUDA example inputs")
         self.static_inputs: List[torch.Tensor] = [t.detach().clone() for t in example_inputs]
@@ -76,7 +79,7 @@ class GraphedTrainStep:
     def _without_hooks(self):
         """Gradient hooks call into the scheduler (event records + a worker thread): switched off for the step — there is
         nothing to communicate in the supported configurations."""
-        ddp = self.ddp
+        ddp = self.ddp if not self.communicates else None   # communicating replicas keep their hooks: the buckets are captured too
 
         class _Ctx:
             def __enter__(self_inner):
@@ -93,14 +96,30 @@ class GraphedTrainStep:
     def capture(self):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
+        backend = self.ddp._bagua_backend if self.communicates else None
+        if backend is not None:
+            backend.set_inline(True)
+            backend.set_profile(False)      # the profile polls timing events (cudaEventQuery), which a capture forbids
+            issued_before, scheduled_before = backend.inline_total(), backend.scheduled_total()
         with self._without_hooks():
             with torch.cuda.stream(side):
                 for _ in range(self.warmup):
                     self.train_step(*self.static_inputs)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            if backend is not None:
+                inline, total = backend.inline_total() - issued_before, backend.scheduled_total() - scheduled_before
+                if total == 0 or inline != total:
+                    raise NotImplementedError(f"{total - inline} of {total} bucket launches went through the scheduler's worker thread "
+                                              "(python ops in the bucket program): this algorithm cannot be captured in a CUDA graph")
+                if not backend.graph_capturable():
+                    raise NotImplementedError("a bucket op passes step-dependent arguments (Adam step count, rotating shift_one partner): "
+                                              "a CUDA graph would freeze them")
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            # thread_local: torch's NCCL watchdog thread polls its events with cudaEventQuery, which a global-mode capture
+            # would take as a violation; the threads that launch into the capture (this one, autograd's device thread) only
+            # make capturable calls
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                 self.static_loss = self.train_step(*self.static_inputs)
         self._captured_hyper = self._hyper()
         self.captures += 1

@@ -30,7 +30,7 @@ one)
   ;;
 two)
   # opt-in kernels written without hardware access in round 1: fused GEMM+combine, fused allreduce+Adam, mixed-precision Adam
-  BAGUA_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_peer_gpu.py -q -k "fused or abort or sync_batchnorm or peer_allgather" > gpurun_out/pytest_experimental_2.log 2>&1
+  BAGUA_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_peer_gpu.py -q -k "fused or abort or sync_batchnorm or peer_allgather or graphed" > gpurun_out/pytest_experimental_2.log 2>&1
   echo "experimental exit=$?" | tee gpurun_out/plan_two.txt
   timeout 400 python -m pytest tests/test_peer_gpu.py -x -q > gpurun_out/pytest_peer_2.log 2>&1; echo "peer exit=$?" | tee -a gpurun_out/plan_two.txt
   # the shipped examples on real GPUs (each asserts its own results)
@@ -40,6 +40,15 @@ two)
     timeout 240 python -m bagua_b200.distributed.launch --nproc_per_node=2 --master_port=$((29640 + RANDOM % 50)) examples/$ex > gpurun_out/example_$(echo $ex | cut -d/ -f1).log 2>&1
     echo "example $ex exit=$?" | tee -a gpurun_out/plan_two.txt
   done
+  # inline issue of the bucket kernels (no worker-thread hand-off) — A/B on the 2-GPU point
+  for inl in 0 1; do
+    BAGUA_INLINE_COMM=$inl timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $((29630 + inl)) \
+      bench.py --gpus 2 --steps 30 --warmup 5 > gpurun_out/bench2_inline$inl.json 2> gpurun_out/bench2_inline$inl.err
+    echo "bench2 inline=$inl exit=$?" | tee -a gpurun_out/plan_two.txt
+  done
+  timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29637 \
+    bench.py --gpus 2 --steps 30 --warmup 5 --cuda-graph > gpurun_out/bench2_cuda_graph.json 2> gpurun_out/bench2_cuda_graph.err
+  echo "bench2 cuda graph exit=$?" | tee -a gpurun_out/plan_two.txt
   for fused in 0 1; do
     BAGUA_MOE_FUSED_COMBINE=$fused timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $((29610 + fused)) \
       benchmarks/config_bench.py --config gpt2_moe --steps 10 --warmup 3 >> gpurun_out/config_bench_n2.jsonl 2>> gpurun_out/config_bench_n2.err

@@ -11,6 +11,19 @@
 
 using namespace bagua;
 
+// a native (non-blocking) op: eligible for inline issue on the marking thread
+struct RecordOp final : CommOp {
+    std::vector<int>* order;
+    std::mutex* mu;
+    int b;
+    RecordOp(std::vector<int>* o, std::mutex* m, int bucket) : order(o), mu(m), b(bucket) {}
+    const char* kind() const override { return "record"; }
+    void run(Bucket&, StreamHandle, int) override {
+        std::lock_guard<std::mutex> lk(*mu);
+        order->push_back(b);
+    }
+};
+
 int main() {
     constexpr int kBuckets = 16, kTensorsPerBucket = 8, kIters = 200;
     Backend be(4, -1, nullptr, 30.0);
@@ -29,15 +42,19 @@ int main() {
             tensors.push_back(x);
         }
         auto bk = std::make_shared<Bucket>("bucket" + std::to_string(b), ts);
-        bk->append_op(std::make_shared<CallbackOp>([&order, &order_mu, b](const std::string&) {
-            std::lock_guard<std::mutex> lk(order_mu);
-            order.push_back(b);
-        }));
+        if (b % 3 == 0)  // "python" ops always go through the worker; the native ones are issued inline when the switch is on
+            bk->append_op(std::make_shared<CallbackOp>([&order, &order_mu, b](const std::string&) {
+                std::lock_guard<std::mutex> lk(order_mu);
+                order.push_back(b);
+            }));
+        else
+            bk->append_op(std::make_shared<RecordOp>(&order, &order_mu, b));
         buckets.push_back(bk);
     }
     be.register_ordered_buckets(buckets);
     int failures = 0;
     for (int it = 0; it < kIters; ++it) {
+        be.set_inline((it & 1) != 0);  // alternate worker-only and inline issue; the order contract is the same
         std::vector<std::thread> producers;
         constexpr int kProducers = 4;
         for (int p = 0; p < kProducers; ++p) {
@@ -67,6 +84,10 @@ int main() {
     for (auto& st : be.bucket_stats(false)) launches += st.count;
     if (launches != static_cast<uint64_t>(kIters) * kBuckets) {
         std::fprintf(stderr, "profile counted %llu launches, expected %d\n", static_cast<unsigned long long>(launches), kIters * kBuckets);
+        ++failures;
+    }
+    if (be.inline_total() == 0) {
+        std::fprintf(stderr, "inline issue never happened\n");
         ++failures;
     }
     be.shutdown();

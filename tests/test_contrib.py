@@ -738,11 +738,11 @@ def test_graphed_train_step_refuses_what_it_cannot_capture():
             return 2
 
     class FakeEngine:
-        process_group, require_backward_grad_sync = FakeGroup(), True
+        process_group, require_backward_grad_sync, _speed_metrics_switch_on = FakeGroup(), True, True
 
     lin.bagua_ddp = FakeEngine()
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError):     # autotune's per-step timing events cannot be captured
         GraphedTrainStep(lin, lambda x: lin(x).sum(), (torch.randn(2, 4),), optimizers=[FusedSGD(lin.parameters(), lr=0.1)])
-    FakeEngine.require_backward_grad_sync = False          # inside no_sync(): nothing is communicated → only the device check is left
+    FakeEngine._speed_metrics_switch_on = False   # communicating replicas are captured through inline issue → only the device check is left here
     with pytest.raises(RuntimeError):
         GraphedTrainStep(lin, lambda x: lin(x).sum(), (torch.randn(2, 4),), optimizers=[FusedSGD(lin.parameters(), lr=0.1)])

@@ -168,3 +168,75 @@ def test_log_level_is_settable():
     C.set_log_level("nonsense")
     assert C.log_level() == "WARN"
     C.set_log_level(before)
+
+
+def test_inline_issue_runs_native_ops_on_the_marking_thread_and_keeps_the_order():
+    """``Backend.set_inline(True)``: a bucket made of native ops only is issued by the thread that marks its last tensor (what
+    a CUDA-graph capture needs: no second thread touches the streams); buckets with a python op still go through the worker,
+    and a native bucket behind one of those follows it into the queue so the registered order is never violated."""
+    import numpy as np
+
+    C = native()
+    be = C.Backend(10, -1, 0, 30.0)
+    src = [np.full(16, float(i + 1), dtype=np.float32) for i in range(3)]
+    dst = [np.zeros(16, dtype=np.float32) for _ in range(3)]
+    ts = [C.Tensor(f"t{i}", src[i].ctypes.data, 16, 0, -1) for i in range(3)]
+    bs = [C.Bucket(f"b{i}", [ts[i]]) for i in range(3)]
+    order, gate = [], threading.Event()
+    bs[0].append_op(C.CopyOp(dst[0].ctypes.data, src[0].ctypes.data, 64))
+
+    def slow_python_op(name):
+        gate.wait(5)
+        order.append(("python", bool(dst[2][0] == 3.0)))      # bucket 2 must not have been issued before this op finished
+
+    bs[1].append_python_op(slow_python_op)
+    bs[2].append_op(C.CopyOp(dst[2].ctypes.data, src[2].ctypes.data, 64))
+    be.register_ordered_buckets(bs)
+    assert not be.inline_mode()
+    be.set_inline(True)
+    be.mark_communication_ready(ts[0], 0)
+    assert dst[0][0] == 1.0 and be.inline_total() == 1       # done before mark() returned: issued on this thread
+    be.mark_communication_ready(ts[1], 0)                      # python op → worker thread (blocked on the gate)
+    be.mark_communication_ready(ts[2], 0)                      # native, but the worker is busy → queued behind bucket 1
+    assert dst[2][0] == 0.0 and be.inline_total() == 1
+    gate.set()
+    assert be.wait_pending_comm_ops(0, True) == 3
+    assert order == [("python", False)] and dst[2][0] == 3.0
+    # next iteration with the switch off: everything through the worker again
+    be.set_inline(False)
+    dst[0][:] = 0
+    for t in ts:
+        be.mark_communication_ready(t, 0)
+    assert be.wait_pending_comm_ops(0, True) == 3 and dst[0][0] == 1.0 and be.inline_total() == 1
+    be.shutdown()
+
+
+def test_inline_issue_shares_the_profile_path_with_the_worker():
+    C = native()
+    be = C.Backend(10, -1, 0, 30.0)
+    t = C.Tensor("t", 0x1000, 4, 0, -1)
+    b = C.Bucket("b", [t])
+
+    b.append_op(C.CopyOp(0x10, 0x20, 0))      # zero-byte copy: a valid native op
+    be.register_ordered_buckets([b])
+    be.set_inline(True)
+    be.set_profile(True)                      # the profile path is shared with the worker
+    for _ in range(3):
+        be.mark_communication_ready(t, 0)
+        assert be.wait_pending_comm_ops(0, True) == 1
+    stats = be.bucket_stats(False)
+    assert stats[0]["count"] == 3 and be.inline_total() == 3
+    be.shutdown()
+
+
+def test_graph_capturable_only_with_native_step_invariant_ops():
+    C = native()
+    be = C.Backend(10, -1, 0, 30.0)
+    t0, t1 = C.Tensor("a", 0x1000, 4, 0, -1), C.Tensor("b", 0x2000, 4, 0, -1)
+    b0, b1 = C.Bucket("b0", [t0]), C.Bucket("b1", [t1])
+    b0.append_op(C.CopyOp(0x10, 0x20, 0))
+    be.register_ordered_buckets([b0, b1])
+    assert be.graph_capturable()                      # native op + an empty program
+    b1.append_python_op(lambda name: None)            # python ops run on the worker thread: not capturable
+    assert not be.graph_capturable()
+    be.shutdown()
