@@ -118,6 +118,18 @@ class FusedGradientAllReduceAlgorithmImpl(GradientAllReduceAlgorithmImpl):
         self.optimizer = optimizer
         self._weight_slices = []
 
+    def init_forward_pre_hook(self, bagua_ddp):
+        """The update of iteration *i* runs inside the bucket kernels of *i*'s backward pass, before ``optimizer.step()`` is
+        called — so the hyper-parameters are published at the start of every iteration (after any ``lr_scheduler.step()`` of
+        the previous one), not only from ``step()``."""
+        opt = self.optimizer
+
+        def hook(input):
+            if getattr(opt, "_comm_ops", None):
+                opt._sync_hyper()
+
+        return hook
+
     def tensors_to_buckets(self, tensors, do_flatten):
         from ...bucket import BaguaBucket
 

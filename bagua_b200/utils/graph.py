@@ -94,6 +94,9 @@ class GraphedTrainStep:
         return _Ctx()
 
     def capture(self):
+        """First call: warm up (real steps), verify that the bucket programs are capturable, capture.  Later calls (a
+        hyper-parameter changed): capture only — nothing executes during a capture, so no extra optimisation step is taken."""
+        first = self.graph is None
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         backend = self.ddp._bagua_backend if self.communicates else None
@@ -102,12 +105,13 @@ class GraphedTrainStep:
             backend.set_profile(False)      # the profile polls timing events (cudaEventQuery), which a capture forbids
             issued_before, scheduled_before = backend.inline_total(), backend.scheduled_total()
         with self._without_hooks():
-            with torch.cuda.stream(side):
-                for _ in range(self.warmup):
-                    self.train_step(*self.static_inputs)
-            torch.cuda.current_stream().wait_stream(side)
+            if first:
+                with torch.cuda.stream(side):
+                    for _ in range(self.warmup):
+                        self.train_step(*self.static_inputs)
+                torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            if backend is not None:
+            if backend is not None and first:
                 inline, total = backend.inline_total() - issued_before, backend.scheduled_total() - scheduled_before
                 if total == 0 or inline != total:
                     raise NotImplementedError(f"{total - inline} of {total} bucket launches went through the scheduler's worker thread "
