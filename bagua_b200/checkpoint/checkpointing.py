@@ -112,6 +112,9 @@ def save_checkpoint(iteration: int, checkpoints_path: str, model: torch.nn.Modul
     Collective: every rank must call it (expert ranks write their experts; rank 0 writes the shared part and the tracker)."""
     logger.info("saving checkpoint at iteration %7d to %s", iteration, checkpoints_path)
     has_moe, num_experts = _has_moe_layers(model)
+    # optimizers whose state is sharded across ranks (in-bucket fused SGD/Adam) consolidate it with a collective: every rank
+    # has to take part even though only rank 0 writes the result
+    collective_opt_sd = optimizer.state_dict() if (optimizer is not None and getattr(optimizer, "collective_state_dict", False)) else None
     if has_moe:
         ep_rank = _rank()
         num_local = num_experts // _world()
@@ -122,7 +125,7 @@ def save_checkpoint(iteration: int, checkpoints_path: str, model: torch.nn.Modul
             torch.save(sd, name)
         opt_name = _get_optimizer_ckpt_name(checkpoints_path, iteration, ep_rank)
         _ensure_directory_exists(opt_name)
-        torch.save({"optimizer": optimizer.state_dict() if optimizer else None}, opt_name)
+        torch.save({"optimizer": (collective_opt_sd if collective_opt_sd is not None else optimizer.state_dict()) if optimizer else None}, opt_name)
         if ep_rank == 0:
             state = {"iteration": iteration, "model": model_sd}
             if lr_scheduler is not None:
@@ -133,7 +136,7 @@ def save_checkpoint(iteration: int, checkpoints_path: str, model: torch.nn.Modul
     elif _rank() == 0:
         state = {"iteration": iteration, "model": model.state_dict()}
         if optimizer is not None:
-            state["optimizer"] = optimizer.state_dict()
+            state["optimizer"] = collective_opt_sd if collective_opt_sd is not None else optimizer.state_dict()
         if lr_scheduler is not None:
             state["lr_scheduler"] = lr_scheduler.state_dict()
         name = _get_model_ckpt_name(checkpoints_path, iteration)
@@ -175,6 +178,8 @@ def load_checkpoint(checkpoints_path: str, model: torch.nn.Module, optimizer: Op
     model.load_state_dict(ckpt["model"], strict=strict)
     if optimizer is not None and optim_ckpt.get("optimizer") is not None:
         optimizer.load_state_dict(optim_ckpt["optimizer"])
+    elif optimizer is not None and hasattr(optimizer, "refresh_master_weights"):
+        optimizer.refresh_master_weights()  # weights changed under an optimizer that keeps fp32 master copies
     if lr_scheduler is not None and "lr_scheduler" in ckpt:
         lr_scheduler.load_state_dict(ckpt["lr_scheduler"])
     _barrier()

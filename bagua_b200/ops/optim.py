@@ -214,6 +214,17 @@ class _FusedBase(torch.optim.Optimizer):
     def flat_segments(self) -> List[_Segment]:
         return [s for s in self._segments.values() if s]
 
+    @torch.no_grad()
+    def refresh_master_weights(self):
+        """Re-read the fp32 master copies from the (low-precision) parameters.  Needed after the weights were loaded or
+        edited behind the optimizer's back: the next step writes ``master − lr·update`` over the parameters."""
+        for seg in self.flat_segments():
+            if seg.master is not None:
+                seg.master.copy_(seg.param_flat.float())
+        for p, st in self.state.items():
+            if isinstance(st, dict) and "master" in st:
+                st["master"].copy_(p.data)
+
 
 class FusedSGD(_FusedBase):
     """SGD (momentum / nesterov / weight decay) with the update of a whole bucket-flattened model in one kernel.

@@ -43,6 +43,113 @@ class GradientAllReduceAlgorithm(Algorithm):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# Checkpointable state of the in-bucket optimizers
+# ---------------------------------------------------------------------------------------------------------------
+_STATE_KEYS = {"sgd": ("master", "momentum_buffer"), "adam": ("master", "exp_avg", "exp_avg_sq")}
+
+
+def consolidate_shards(shards, numel: int, layout):
+    """``shards``: the per-rank fp32 state vectors of one bucket in rank order (each ``ceil(vecs/N)·16/elem`` long, the last ones
+    padded); ``layout``: ``[(name, offset, numel, shape, strides)]`` of the bucket's tensors (offsets in elements of the flat
+    bucket, strides = the parameter's dense memory layout, e.g. channels_last).  Returns ``{name: contiguous tensor(shape)}`` —
+    the state as an unsharded optimizer would hold it, independent of world size, bucketing and memory format."""
+    import torch
+
+    full = torch.cat([s.reshape(-1) for s in shards])[:numel]
+    return {name: torch.as_strided(full, shape, strides, off).contiguous().clone() for name, off, n, shape, strides in layout}
+
+
+def shard_of(per_name, layout, numel: int, lo: int, hi: int, length: int, device=None):
+    """Inverse of :func:`consolidate_shards` for one rank: the ``[lo, hi)`` slice of the bucket-flat vector assembled from the
+    per-parameter tensors, zero-padded to the shard ``length``.  Parameters missing from ``per_name`` contribute zeros."""
+    import torch
+
+    out = torch.zeros(length, dtype=torch.float32, device=device)
+    for name, off, n, shape, strides in layout:
+        a, b = max(off, lo), min(off + n, hi)
+        if a < b and name in per_name:
+            mem = torch.empty_strided(shape, strides, dtype=torch.float32)       # the parameter's memory order
+            mem.copy_(per_name[name].to(torch.float32).reshape(shape))
+            flat = torch.as_strided(mem, (n,), (1,))
+            out[a - lo: b - lo].copy_(flat[a - off: b - off])
+    return out
+
+
+class _ShardedStateMixin:
+    """``state_dict()`` / ``load_state_dict()`` of the optimizers whose state lives in 1/N shards next to the buckets.
+
+    The saved form is *consolidated*: per parameter name, full-shape fp32 ``master`` weights and moments (all-gathered from the
+    shards — a collective, every rank must call ``state_dict()``; ``collective_state_dict`` tells the checkpoint module), so
+    a checkpoint does not depend on the world size or on the bucket boundaries (autotune may move them)."""
+
+    _kind = "sgd"
+
+    @property
+    def collective_state_dict(self) -> bool:
+        return bool(getattr(self, "_shards", None))
+
+    def _gather(self, t, group):
+        import torch
+        import torch.distributed as dist
+
+        out = [torch.empty_like(t) for _ in range(group.size())]
+        dist.all_gather(out, t.contiguous(), group=group.torch_group)
+        return out
+
+    def state_dict(self):
+        if not getattr(self, "_shards", None):
+            return super().state_dict()
+        state = {}
+        steps = 0
+        for rec in self._shards:
+            for key, t in zip(_STATE_KEYS[self._kind], rec["state"]):
+                for name, full in consolidate_shards(self._gather(t, rec["group"]), rec["numel"], rec["layout"]).items():
+                    state.setdefault(name, {})[key] = full.cpu()
+            steps = max(steps, int(rec["op"].steps()))
+        groups = [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]
+        return {"sharded_fused": self._kind, "steps": steps, "state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd):
+        if not isinstance(sd, dict) or "sharded_fused" not in sd:
+            return super().load_state_dict(sd)
+        if sd["sharded_fused"] != self._kind:
+            raise ValueError(f"checkpoint holds {sd['sharded_fused']} state, this optimizer is {self._kind}")
+        for g, saved in zip(self.param_groups, sd["param_groups"]):
+            g.update(saved)
+        if not getattr(self, "_shards", None):
+            self._pending_state = sd          # applied bucket by bucket when the algorithm builds the ops (with_bagua)
+            return
+        for rec in self._shards:
+            self._apply_to_shard(rec, sd)
+        self._sync_hyper()
+
+    def _apply_to_shard(self, rec, sd):
+        for key, t in zip(_STATE_KEYS[self._kind], rec["state"]):
+            per_name = {name: st[key] for name, st in sd["state"].items() if key in st}
+            t.copy_(shard_of(per_name, rec["layout"], rec["numel"], rec["lo"], rec["hi"], t.numel(), device=t.device))
+        rec["op"].set_steps(int(sd.get("steps", 0)))
+
+    def refresh_master_weights(self):
+        """Re-read the fp32 master shards from the model weights (call after loading or editing weights without optimizer
+        state: the next bucket kernel writes ``master − lr·update`` over the parameters)."""
+        if not getattr(self, "_shards", None):
+            return super().refresh_master_weights() if hasattr(super(), "refresh_master_weights") else None
+        for rec in self._shards:
+            lo, hi = rec["lo"], min(rec["hi"], rec["numel"])
+            if hi > lo:
+                rec["state"][0][: hi - lo].copy_(rec["weights"][lo:hi].float())
+
+    def _register_shard(self, rec):
+        if not hasattr(self, "_shards"):
+            self._shards = []
+        self._shards.append(rec)
+        pending = getattr(self, "_pending_state", None)
+        if pending is not None:
+            self._apply_to_shard(rec, pending)
+
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # Gradient allreduce with the optimizer folded into the communication kernel
 # ---------------------------------------------------------------------------------------------------------------
 class ShardedFusedSGD(object):
@@ -57,10 +164,13 @@ def make_sharded_fused_sgd(params, lr=1e-3, momentum=0.0, dampening=0.0, weight_
     without a peer engine) it behaves like :class:`bagua_b200.ops.optim.FusedSGD`."""
     from ...ops.optim import FusedSGD
 
-    class _ShardedFusedSGD(FusedSGD, ShardedFusedSGD):
+    class _ShardedFusedSGD(_ShardedStateMixin, FusedSGD, ShardedFusedSGD):
+        _kind = "sgd"
+
         def __init__(self, *a, **k):
             super().__init__(*a, **k)
             self._comm_ops = []   # AllReduceSgdOp per bucket once the algorithm has taken over
+            self._shards = []
 
         def _sync_hyper(self):
             g = self.param_groups[0]
@@ -90,10 +200,13 @@ def make_sharded_fused_adam(params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weigh
     process (or without a peer engine) it behaves like :class:`bagua_b200.ops.optim.FusedAdam`."""
     from ...ops.optim import FusedAdam
 
-    class _ShardedFusedAdam(FusedAdam, ShardedFusedAdam):
+    class _ShardedFusedAdam(_ShardedStateMixin, FusedAdam, ShardedFusedAdam):
+        _kind = "adam"
+
         def __init__(self, *a, **k):
             super().__init__(*a, **k)
             self._comm_ops = []
+            self._shards = []
 
         def _sync_hyper(self):
             g = self.param_groups[0]
@@ -200,6 +313,10 @@ class FusedGradientAllReduceAlgorithmImpl(GradientAllReduceAlgorithmImpl):
         bucket._ops_keepalive.append(op)
         bucket.allreduce_variant = ("fused_adam_" if is_adam else "fused_sgd_") + ("multimem" if use_mc else "two_shot")
         opt._comm_ops.append(op)
+        layout = [(t.bagua_tensor_name, (t.bagua_getter_closure().data_ptr() - base) // flat.element_size(), t.bagua_getter_closure().numel(),
+                   tuple(t.shape), tuple(dense_strides(t))) for t in bucket.tensors if not t.bagua_tensor_name.startswith("bagua_padding_tensor")]
+        opt._register_shard({"bucket": bucket.name, "group": self.process_group, "numel": flat.numel(), "lo": lo, "hi": hi, "layout": layout,
+                             "state": bucket._fused_state, "op": op, "weights": wflat})
         opt._sync_hyper()
 
 
@@ -213,4 +330,5 @@ class FusedGradientAllReduceAlgorithm(Algorithm):
 
     def reify(self, process_group):
         self.optimizer._comm_ops = []
+        self.optimizer._shards = []
         return FusedGradientAllReduceAlgorithmImpl(process_group, self.optimizer, average=self.average)

@@ -30,7 +30,7 @@ one)
   ;;
 two)
   # opt-in kernels written without hardware access in round 1: fused GEMM+combine, fused allreduce+Adam, mixed-precision Adam
-  BAGUA_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_peer_gpu.py -q -k "fused or abort or sync_batchnorm or peer_allgather or graphed" > gpurun_out/pytest_experimental_2.log 2>&1
+  BAGUA_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_peer_gpu.py -q -k "fused or abort or sync_batchnorm or peer_allgather or graphed or sharded" > gpurun_out/pytest_experimental_2.log 2>&1
   echo "experimental exit=$?" | tee gpurun_out/plan_two.txt
   timeout 400 python -m pytest tests/test_peer_gpu.py -x -q > gpurun_out/pytest_peer_2.log 2>&1; echo "peer exit=$?" | tee -a gpurun_out/plan_two.txt
   # the shipped examples on real GPUs (each asserts its own results)

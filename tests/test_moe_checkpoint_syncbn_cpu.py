@@ -206,3 +206,101 @@ def test_bf16_model_with_fp32_gate_trains_under_with_bagua():
     res = run_distributed(_bf16_moe_worker, world=2, timeout=240)
     assert all(l == l for l, _ in res)                                  # finite
     assert torch.equal(res[0][1], res[1][1])                            # the gate is data-parallel: identical on both ranks
+
+
+def test_sharded_fused_optimizer_state_is_world_size_independent():
+    """In-bucket fused SGD / Adam keep fp32 master weights and moments in 1/N shards next to the buckets.  ``state_dict()``
+    consolidates them per parameter name (all-gather), ``load_state_dict()`` re-shards for the current layout: saved from 2
+    ranks with one bucket, restored into 3 ranks with two buckets, every shard equals the slice of the same flat vectors.  The
+    collective is replaced by a local concatenation; channels_last parameters keep their logical order in the checkpoint."""
+    from bagua_b200.parallel.algorithms.gradient_allreduce import make_sharded_fused_adam, make_sharded_fused_sgd
+    from bagua_b200.tensor import dense_strides
+
+    torch.manual_seed(1)
+    params = {"conv.weight": torch.randn(4, 3, 2, 2).to(memory_format=torch.channels_last), "conv.bias": torch.randn(4), "fc.weight": torch.randn(6, 8)}
+    per = 4  # fp32 buckets: 16 bytes = 4 elements
+
+    class Op:
+        def __init__(self):
+            self.s = 0
+
+        def steps(self):
+            return self.s
+
+        def set_steps(self, s):
+            self.s = s
+
+        def set_hyper(self, *a):
+            self.hyper = a
+
+    def build(world, bucket_names, factory, n_state):
+        """``world`` optimizers (one per rank) with shard records for the given bucketing; state filled from per-name truth."""
+        ranks = [factory([torch.nn.Parameter(torch.zeros(1))], lr=0.1) for _ in range(world)]
+        truth, recs = {}, [[] for _ in range(world)]
+        for bi, names in enumerate(bucket_names):
+            layout, off = [], 0
+            for n in names:
+                t = params[n]
+                layout.append((n, off, t.numel(), tuple(t.shape), tuple(dense_strides(t))))
+                off += t.numel()
+            numel = (off + per - 1) // per * per
+            vpr = (numel // per + world - 1) // world
+            length = vpr * per
+            for r in range(world):
+                lo, hi = r * length, min((r + 1) * length, numel)
+                state = tuple(torch.zeros(length) for _ in range(n_state))
+                recs[r].append({"bucket": str(bi), "group": None, "numel": numel, "lo": lo, "hi": max(lo, hi), "layout": layout, "state": state,
+                                "op": Op(), "weights": torch.zeros(numel)})
+        for r, opt in enumerate(ranks):
+            opt._comm_ops = [rec["op"] for rec in recs[r]]
+            for rec in recs[r]:
+                opt._register_shard(rec)
+            # all-gather double: the same record of every rank, in rank order
+            opt._gather = lambda t, group, r=r: [other_rec["state"][idx] for other_rec, idx in _locate(t, recs)]
+        return ranks, recs
+
+    def _locate(t, recs):
+        for r, rr in enumerate(recs):
+            for bi, rec in enumerate(rr):
+                for idx, st in enumerate(rec["state"]):
+                    if st is t:
+                        return [(recs[q][bi], idx) for q in range(len(recs))]
+        raise AssertionError("tensor is not a registered shard")
+
+    for factory, keys in ((make_sharded_fused_sgd, ("master", "momentum_buffer")), (make_sharded_fused_adam, ("master", "exp_avg", "exp_avg_sq"))):
+        src, src_recs = build(2, [["conv.weight", "conv.bias", "fc.weight"]], factory, len(keys))
+        from bagua_b200.parallel.algorithms.gradient_allreduce import shard_of
+
+        truth = {k: {n: torch.randn_like(params[n].contiguous()) for n in params} for k in keys}
+        for r in range(2):
+            for rec in src_recs[r]:
+                for k, t in zip(keys, rec["state"]):
+                    t.copy_(shard_of(truth[k], rec["layout"], rec["numel"], rec["lo"], rec["hi"], t.numel()))
+                rec["op"].set_steps(17)
+        sds = [o.state_dict() for o in src]
+        assert src[0].collective_state_dict and sds[0]["steps"] == 17 and sds[0]["param_groups"][0]["lr"] == 0.1
+        for n in params:
+            for k in keys:
+                assert torch.equal(sds[0]["state"][n][k], truth[k][n]) and torch.equal(sds[1]["state"][n][k], truth[k][n])
+        dst, dst_recs = build(3, [["fc.weight"], ["conv.bias", "conv.weight"]], factory, len(keys))
+        sds[0]["param_groups"][0]["lr"] = 0.025
+        for r, o in enumerate(dst):
+            o.load_state_dict(sds[0])
+            assert o.param_groups[0]["lr"] == 0.025
+            for rec in dst_recs[r]:
+                assert rec["op"].steps() == 17
+                for k, t in zip(keys, rec["state"]):
+                    assert torch.equal(t, shard_of(truth[k], rec["layout"], rec["numel"], rec["lo"], rec["hi"], t.numel()))
+        again = dst[1].state_dict()
+        for n in params:
+            for k in keys:
+                assert torch.equal(again["state"][n][k], truth[k][n])
+        # a state loaded before with_bagua() is kept and applied bucket by bucket when the algorithm builds the ops
+        late = factory([torch.nn.Parameter(torch.zeros(1))], lr=0.1)
+        late.load_state_dict(sds[0])
+        assert not late.collective_state_dict and late.param_groups[0]["lr"] == 0.025
+        _, fresh = build(3, [["fc.weight"], ["conv.bias", "conv.weight"]], factory, len(keys))
+        for rec in fresh[2]:
+            late._register_shard(rec)
+            for k, t in zip(keys, rec["state"]):
+                assert torch.equal(t, shard_of(truth[k], rec["layout"], rec["numel"], rec["lo"], rec["hi"], t.numel())) and rec["op"].steps() == 17
