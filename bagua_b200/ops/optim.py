@@ -114,6 +114,7 @@ class _Segment:
             self.master = self.param_flat.float()
         self.state: Dict[str, torch.Tensor] = {}
         self.steps = 0
+        self.bound = False  # per-parameter optimizer state aliased to the flat buffers (see _FusedBase._bind_state)
 
     def state_flat(self, key: str) -> torch.Tensor:
         t = self.state.get(key)
@@ -139,7 +140,7 @@ def _can_flatten(group_params: List[torch.nn.Parameter], all_params: List[torch.
     if not group_params:
         return False
     g0 = group_params[0].grad
-    if g0 is None or g0.device.type != "cuda":
+    if g0 is None or not _kernels_apply([g0]):
         return False
     mine = set(id(p) for p in group_params)
     for p in group_params:
@@ -214,6 +215,42 @@ class _FusedBase(torch.optim.Optimizer):
     def flat_segments(self) -> List[_Segment]:
         return [s for s in self._segments.values() if s]
 
+    def _bind_state(self, seg: _Segment, key: str, flat: Optional[torch.Tensor] = None) -> bool:
+        """``self.state[p][key]`` of every parameter of the segment becomes its view of the segment's flat buffer.  Values
+        that are already there — a loaded checkpoint, the buffers of a segment that was rebuilt — are copied in first, so
+        ``state_dict()`` / ``load_state_dict()`` round-trip through the flat kernels.  Returns whether anything was adopted."""
+        flat = seg.state_flat(key) if flat is None else flat
+        adopted = False
+        for i, p in enumerate(seg.params):
+            view = seg.view_of(flat, i)
+            cur = self.state[p].get(key)
+            if isinstance(cur, torch.Tensor) and cur.data_ptr() != view.data_ptr() and cur.shape == view.shape:
+                view.copy_(cur)
+                adopted = True
+            self.state[p][key] = view
+        return adopted
+
+    def state_dict(self):
+        for seg in self.flat_segments():
+            step = self.state[seg.params[0]].get("step") if seg.params else None
+            if step is not None:
+                for p in seg.params[1:]:
+                    self.state[p]["step"] = step
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        """torch casts loaded state to the parameter dtype; moments and master weights of low-precision parameters are fp32
+        here, so tensors are re-read from ``state_dict`` unchanged, and the flat segments re-adopt them at the next step."""
+        super().load_state_dict(state_dict)
+        ids = [i for g in state_dict["param_groups"] for i in g["params"]]
+        params = [p for g in self.param_groups for p in g["params"]]
+        for pid, p in zip(ids, params):
+            for k, v in state_dict["state"].get(pid, {}).items():
+                if isinstance(v, torch.Tensor):
+                    self.state[p][k] = v.detach().clone().to(device=p.device)
+        for seg in self.flat_segments():
+            seg.bound = False
+
     @torch.no_grad()
     def refresh_master_weights(self):
         """Re-read the fp32 master copies from the (low-precision) parameters.  Needed after the weights were loaded or
@@ -251,11 +288,14 @@ class FusedSGD(_FusedBase):
             seg = self._segment_for(gi, group)
             lr, mom, damp, wd, nest = group["lr"], group["momentum"], group["dampening"], group["weight_decay"], group["nesterov"]
             if seg is not None:
+                if not seg.bound or (mom != 0 and "momentum_buffer" not in seg.state):
+                    if mom != 0 and self._bind_state(seg, "momentum_buffer"):
+                        seg.steps = max(seg.steps, 1)  # adopted momentum: this is not a first step
+                    if seg.master is not None:
+                        self._bind_state(seg, "master", seg.master)
+                    seg.bound = True
                 first = seg.steps == 0
                 mbuf = seg.state_flat("momentum_buffer") if mom != 0 else None
-                if first and mom != 0:
-                    for i, p in enumerate(seg.params):
-                        self.state[p]["momentum_buffer"] = seg.view_of(mbuf, i)
                 if seg.master is not None:
                     flat_sgd_(seg.master, seg.grad_flat, mbuf, lr=lr, momentum=mom, dampening=damp, weight_decay=wd, nesterov=nest,
                               first_step=first, grad_scale=self.grad_scale, zero_grad=self.zero_grad_in_step, model=seg.param_flat)
@@ -330,13 +370,17 @@ class FusedAdam(_FusedBase):
             seg = self._segment_for(gi, group)
             lr, betas, eps, wd, adamw = group["lr"], group["betas"], group["eps"], group["weight_decay"], group["adamw"]
             if seg is not None:
+                if not seg.bound:
+                    adopted = self._bind_state(seg, "exp_avg")
+                    self._bind_state(seg, "exp_avg_sq")
+                    if seg.master is not None:
+                        self._bind_state(seg, "master", seg.master)
+                    if adopted:  # loaded checkpoint / rebuilt segment: continue its step count (bias correction)
+                        seg.steps = max(seg.steps, int(self.state[seg.params[0]].get("step", 0)))
+                    seg.bound = True
                 seg.steps += 1
                 m1, m2 = seg.state_flat("exp_avg"), seg.state_flat("exp_avg_sq")
-                if seg.steps == 1:
-                    for i, p in enumerate(seg.params):
-                        self.state[p]["exp_avg"], self.state[p]["exp_avg_sq"] = seg.view_of(m1, i), seg.view_of(m2, i)
-                for p in seg.params[:1]:
-                    self.state[p]["step"] = seg.steps
+                self.state[seg.params[0]]["step"] = seg.steps  # the other parameters get it in state_dict() (hot path: one write)
                 target = seg.master if seg.master is not None else seg.param_flat
                 flat_adam_(target, seg.grad_flat, m1, m2, lr=lr, betas=betas, eps=eps, weight_decay=wd, step=seg.steps, adamw=adamw,
                            grad_scale=self.grad_scale, zero_grad=self.zero_grad_in_step, model=seg.param_flat if seg.master is not None else None)

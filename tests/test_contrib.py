@@ -746,3 +746,100 @@ def test_graphed_train_step_refuses_what_it_cannot_capture():
     FakeEngine._speed_metrics_switch_on = False   # communicating replicas are captured through inline issue → only the device check is left here
     with pytest.raises(RuntimeError):
         GraphedTrainStep(lin, lambda x: lin(x).sum(), (torch.randn(2, 4),), optimizers=[FusedSGD(lin.parameters(), lr=0.1)])
+
+
+def _flat_resume_worker(rank, world):
+    """FusedSGD / FusedAdam on the flat (bucket-arena) path with host doubles of the two flat kernels: checkpoint after 3 steps,
+    train 2 more, then a fresh model + optimizer restored from the checkpoint must reproduce those 2 steps exactly — momentum,
+    Adam moments + step count and the fp32 master weights of a bf16 model all travel through state_dict()."""
+    import copy
+
+    import bagua_b200 as bagua
+    from bagua_b200.ops import optim
+    from bagua_b200.parallel.algorithms import gradient_allreduce
+
+    def flat_sgd_double(param, grad, momentum_buf, *, lr, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False, first_step=False, grad_scale=1.0,
+                        zero_grad=False, model=None):
+        g = grad.float() * grad_scale
+        if weight_decay:
+            g = g + weight_decay * param.float()
+        if momentum:
+            if first_step:
+                momentum_buf.copy_(g)
+            else:
+                momentum_buf.mul_(momentum).add_(g, alpha=1 - dampening)
+            g = g + momentum * momentum_buf if nesterov else momentum_buf
+        param.add_(g.to(param.dtype), alpha=-lr)
+        if model is not None:
+            model.copy_(param)
+        if zero_grad:
+            grad.zero_()
+
+    def flat_adam_double(param, grad, exp_avg, exp_avg_sq, *, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, step=1, adamw=False, grad_scale=1.0,
+                         zero_grad=False, model=None):
+        g = grad.float() * grad_scale
+        if adamw:
+            param.mul_(1 - lr * weight_decay)
+        elif weight_decay:
+            g = g + weight_decay * param.float()
+        exp_avg.mul_(betas[0]).add_(g, alpha=1 - betas[0])
+        exp_avg_sq.mul_(betas[1]).addcmul_(g, g, value=1 - betas[1])
+        denom = exp_avg_sq.sqrt() / (1 - betas[1] ** step) ** 0.5 + eps
+        param.add_((exp_avg / denom).to(param.dtype), alpha=-lr / (1 - betas[0] ** step))
+        if model is not None:
+            model.copy_(param)
+        if zero_grad:
+            grad.zero_()
+
+    optim._kernels_apply = lambda params: True
+    optim.flat_sgd_, optim.flat_adam_ = flat_sgd_double, flat_adam_double
+    bagua.init_process_group()
+    torch.manual_seed(2)
+    base = torch.nn.Sequential(torch.nn.Linear(12, 16), torch.nn.Tanh(), torch.nn.Linear(16, 4))
+    batches = [torch.randn(8, 12) for _ in range(5)]
+    cases = [("sgd", torch.float32, lambda ps: optim.FusedSGD(ps, lr=0.05, momentum=0.9, weight_decay=1e-3)),
+             ("sgd-bf16-master", torch.bfloat16, lambda ps: optim.FusedSGD(ps, lr=0.05, momentum=0.9)),
+             ("adam", torch.float32, lambda ps: optim.FusedAdam(ps, lr=1e-2, adamw=True, weight_decay=0.01)),
+             ("adam-bf16-master", torch.bfloat16, lambda ps: optim.FusedAdam(ps, lr=1e-2))]
+    for tag, dtype, make in cases:
+        def fresh(state=None):
+            m = copy.deepcopy(base).to(dtype)
+            if state is not None:
+                m.load_state_dict(state)
+            o = make(m.parameters())
+            m = m.with_bagua([o], gradient_allreduce.GradientAllReduceAlgorithm())
+            return m, o
+
+        def run(m, o, xs):
+            for x in xs:
+                o.zero_grad()
+                m(x.to(dtype)).float().pow(2).mean().backward()
+                o.step()
+            return torch.cat([p.detach().float().reshape(-1) for p in m.parameters()])
+
+        m, o = fresh()
+        run(m, o, batches[:3])
+        assert o.flat_segments(), f"{tag}: the flat path was not taken"
+        sd, msd = copy.deepcopy(o.state_dict()), copy.deepcopy(m.state_dict())
+        if dtype == torch.bfloat16:
+            assert all(st["master"].dtype == torch.float32 for st in sd["state"].values())
+        want = run(m, o, batches[3:])
+        m2, o2 = fresh(msd)
+        o2.load_state_dict(sd)
+        got = run(m2, o2, batches[3:])
+        assert torch.equal(got, want), f"{tag}: resume diverged by {(got - want).abs().max().item()}"
+        if tag == "sgd":   # the host double itself against torch.optim.SGD
+            ref = copy.deepcopy(base)
+            ropt = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-3)
+            for x in batches:
+                ropt.zero_grad()
+                ref(x).pow(2).mean().backward()
+                ropt.step()
+            torch.testing.assert_close(want, torch.cat([p.detach().reshape(-1) for p in ref.parameters()]), rtol=1e-5, atol=1e-6)
+    return True
+
+
+def test_flat_fused_optimizers_resume_exactly_from_state_dict():
+    from tests.mp_utils import run_distributed
+
+    assert all(run_distributed(_flat_resume_worker, world=1))
