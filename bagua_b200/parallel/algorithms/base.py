@@ -75,7 +75,8 @@ class AlgorithmImpl:
                 # the gradient must still be the bucket view registered with the scheduler (zero_grad(set_to_none=True)
                 # or an optimizer that replaces .grad would silently break the aliasing)
                 if parameter._bagua_backend_tensor.data_ptr() != parameter.grad.data_ptr():
-                    raise AssertionError("bagua backend tensor data_ptr should match parameter grad")
+                    raise AssertionError("bagua backend tensor data_ptr should match parameter grad (the gradient must stay the bucket view: "
+                                         "use zero_grad(set_to_none=False) and do not assign a new tensor to .grad)")
                 bagua_ddp.mark_tensor_ready(parameter)
 
         return hook

@@ -534,7 +534,8 @@ class BaguaDistributedDataParallel:
                 # periodically — it only breaks when user code replaces .grad, which shows up immediately
                 step = ddp.bagua_train_step_counter
                 if (step < 4 or not step & 63) and bt.data_ptr() != p.grad.data_ptr():
-                    raise AssertionError("bagua backend tensor data_ptr should match parameter grad")
+                    raise AssertionError("bagua backend tensor data_ptr should match parameter grad (the gradient must stay the bucket view: "
+                                         "use zero_grad(set_to_none=False) and do not assign a new tensor to .grad)")
                 mark(bt, ddp._stream_cache)
                 if not ddp._is_post_backward_callback_queued:
                     queue_post_backward()
