@@ -59,6 +59,7 @@ setup(
         "console_scripts": [
             "baguarun = bagua_b200.script.baguarun:main",
             "bagua_sys_perf = bagua_b200.script.bagua_sys_perf:main",
+            "bagua_doctor = bagua_b200.script.bagua_doctor:main",
         ]
     },
     cmdclass={"build_ext": BuildNative, "build_py": BuildPyWithNative},

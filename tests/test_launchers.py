@@ -167,3 +167,19 @@ def test_baguarun_starts_one_launcher_per_host_and_propagates_failure(tmp_path):
                        env=env, capture_output=True, text=True)
     lines = d.stdout.strip().splitlines()
     assert len(lines) == 3 and "--nnodes=3" in lines[2] and "--node_rank=2" in lines[2] and "--master_addr=a" in lines[2] and lines[2].rstrip("'").endswith("train.py --lr 1")
+
+
+def test_bagua_doctor_reports_and_self_tests():
+    """``python -m bagua_b200.script.bagua_doctor --json``: library state, versions, environment deviations and a passing self-test."""
+    import json
+    import subprocess
+    import sys
+
+    env = dict(os.environ, NCCL_SOCKET_IFNAME="lo", BAGUA_DEFAULT_BUCKET_SIZE="1048576", CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, "-m", "bagua_b200.script.bagua_doctor", "--json"], capture_output=True, text=True, timeout=180, env=env,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    rep = json.loads(r.stdout[r.stdout.index("{"):])
+    assert rep["ok"] and all(t["ok"] for t in rep["self_test"]) and len(rep["self_test"]) >= 2
+    assert rep["libraries"]["_C.so (native core, sm_100a kernels)"]["current_with_sources"] is True
+    assert rep["environment"]["BAGUA_DEFAULT_BUCKET_SIZE"] == "1048576" and rep["gpus"]["count"] == 0
