@@ -595,6 +595,15 @@ class BaguaDistributedDataParallel:
             optimizer.step = MethodType(new_step, optimizer)
             optimizer._bagua_post_step_hook = hook  # fuse_step() triggers it too
             optimizer.zero_grad = MethodType(new_zero_grad, optimizer)
+        # same contract for ``model.zero_grad()`` (nn.Module defaults to set_to_none=True since torch 2.0)
+        module = self.module
+        if not hasattr(module, "_bagua_original_zero_grad"):
+            module._bagua_original_zero_grad = module.zero_grad
+
+            def module_zero_grad(self_mod, set_to_none: bool = False):
+                return self_mod._bagua_original_zero_grad(set_to_none=False)
+
+            module.zero_grad = MethodType(module_zero_grad, module)
 
     def _reset_algorithm_state(self):
         st = self.module._bagua_states

@@ -367,3 +367,30 @@ def test_report_metrics_switch_logs_per_bucket_profile(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in (r.stdout + r.stderr).splitlines() if "[bagua metrics]" in ln]
     assert len(lines) == 2 and "step=4" in lines[0] and "step=8" in lines[1] and "'launches': 4" in lines[1], lines
+
+
+def _zero_grad_worker(rank, world):
+    """``model.zero_grad()`` and ``optimizer.zero_grad()`` (both default to set_to_none=True in current torch) keep the gradients
+    allocated as bucket views, so training continues without tripping the pointer contract."""
+    import bagua_b200 as bagua
+    from bagua_b200.parallel.algorithms import gradient_allreduce
+
+    bagua.init_process_group()
+    torch.manual_seed(3)
+    model = torch.nn.Linear(6, 3)
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    model = model.with_bagua([opt], gradient_allreduce.GradientAllReduceAlgorithm())
+    ptrs = None
+    for i in range(4):
+        (model.zero_grad if i % 2 else opt.zero_grad)()
+        assert all(p.grad is not None and float(p.grad.abs().sum()) == 0.0 for p in model.parameters())
+        model(torch.randn(5, 6)).sum().backward()
+        opt.step()
+        now = [p.grad.data_ptr() for p in model.parameters()]
+        assert ptrs is None or now == ptrs
+        ptrs = now
+    return True
+
+
+def test_zero_grad_keeps_bucket_views():
+    assert all(run_distributed(_zero_grad_worker, world=2))
