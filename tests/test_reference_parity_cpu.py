@@ -389,6 +389,17 @@ def _zero_grad_worker(rank, world):
         now = [p.grad.data_ptr() for p in model.parameters()]
         assert ptrs is None or now == ptrs
         ptrs = now
+    # the DDP-compatible wrapper: its own nn.Module.zero_grad must not drop the views either
+    from bagua_b200.parallel.data_parallel import DistributedDataParallel
+
+    inner = torch.nn.Linear(6, 3)
+    opt2 = torch.optim.SGD(inner.parameters(), lr=0.1)
+    ddp = DistributedDataParallel(inner, optimizers=[opt2])
+    for _ in range(3):
+        ddp.zero_grad()
+        ddp(torch.randn(5, 6)).sum().backward()
+        opt2.step()
+        assert all(p.grad is not None for p in inner.parameters())
     return True
 
 
