@@ -107,6 +107,10 @@ class DistributedDataParallel_V1_9_0(DistributedDataParallel_V1_9_0_Interface):
     def forward(self, *inputs, **kwargs):
         return self.module(*inputs, **kwargs)
 
+    def zero_grad(self, set_to_none: bool = False):
+        """Gradients are views of the bucket arena and stay allocated (nn.Module's default would drop them)."""
+        return super().zero_grad(set_to_none=False)
+
     @contextmanager
     def no_sync(self):
         r"""Disable gradient synchronisation inside the context; gradients accumulate locally in the bucket views and are
