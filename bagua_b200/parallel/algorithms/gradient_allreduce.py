@@ -329,6 +329,11 @@ class FusedGradientAllReduceAlgorithm(Algorithm):
         self.average = average
 
     def reify(self, process_group):
-        self.optimizer._comm_ops = []
-        self.optimizer._shards = []
+        opt = self.optimizer
+        if getattr(opt, "_shards", None):
+            # the buckets are about to be rebuilt (with_bagua again, new bucketing): carry momentum / moments / master weights
+            # over in their consolidated form; they are re-sharded when the new bucket ops are created
+            opt._pending_state = opt.state_dict()
+        opt._comm_ops = []
+        opt._shards = []
         return FusedGradientAllReduceAlgorithmImpl(process_group, self.optimizer, average=self.average)

@@ -202,6 +202,8 @@ class BaguaDistributedDataParallel:
         if isinstance(optimizer, torch.optim.LBFGS):
             raise ValueError("cannot broadcast torch.optim.LBFGS state")
         comm = self.process_group.get_global_communicator()
+        if getattr(optimizer, "collective_state_dict", False):
+            return  # state sharded across ranks by construction (in-bucket optimizers): nothing to replicate
         sd = optimizer.state_dict()
         if len(sd["state"]) == 0:
             return
