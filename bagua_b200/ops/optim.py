@@ -278,14 +278,16 @@ class FusedSGD(_FusedBase):
         self.grad_scale = grad_scale
 
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, only: Optional[set] = None):
+        """``only``: restrict the update to these parameter ids (chunked multi-tensor kernels; used by the in-bucket optimizers
+        for parameters that are not part of any bucket — MoE experts, ignored parameters)."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
         C = native()
         for gi, group in enumerate(self.param_groups):
-            seg = self._segment_for(gi, group)
+            seg = self._segment_for(gi, group) if only is None else None
             lr, mom, damp, wd, nest = group["lr"], group["momentum"], group["dampening"], group["weight_decay"], group["nesterov"]
             if seg is not None:
                 if not seg.bound or (mom != 0 and "momentum_buffer" not in seg.state):
@@ -306,7 +308,7 @@ class FusedSGD(_FusedBase):
                 self.kernel_launches += 1
                 continue
             # multi-tensor path (per dtype)
-            params = [p for p in group["params"] if p.grad is not None]
+            params = [p for p in group["params"] if p.grad is not None and (only is None or id(p) in only)]
             if not params:
                 continue
             if not _kernels_apply(params):
@@ -332,7 +334,8 @@ class FusedSGD(_FusedBase):
                 C.multi_tensor_sgd(*plan.args(), dtype_code(dt), mom != 0, float(lr), float(mom), float(damp), float(wd), bool(nest), bool(first),
                                    float(self.grad_scale), _stream())
                 self.kernel_launches += 1
-        self._grads_zeroed = self.zero_grad_in_step and all(s is not None for s in self._segments.values()) and len(self._segments) == len(self.param_groups)
+        if only is None:
+            self._grads_zeroed = self.zero_grad_in_step and all(s is not None for s in self._segments.values()) and len(self._segments) == len(self.param_groups)
         return loss
 
     def _torch_step(self, params, group):
@@ -360,14 +363,15 @@ class FusedAdam(_FusedBase):
         self.grad_scale = grad_scale
 
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, only: Optional[set] = None):
+        """``only``: see :meth:`FusedSGD.step`."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
         C = native()
         for gi, group in enumerate(self.param_groups):
-            seg = self._segment_for(gi, group)
+            seg = self._segment_for(gi, group) if only is None else None
             lr, betas, eps, wd, adamw = group["lr"], group["betas"], group["eps"], group["weight_decay"], group["adamw"]
             if seg is not None:
                 if not seg.bound:
@@ -386,7 +390,7 @@ class FusedAdam(_FusedBase):
                            grad_scale=self.grad_scale, zero_grad=self.zero_grad_in_step, model=seg.param_flat if seg.master is not None else None)
                 self.kernel_launches += 1
                 continue
-            params = [p for p in group["params"] if p.grad is not None]
+            params = [p for p in group["params"] if p.grad is not None and (only is None or id(p) in only)]
             if not params:
                 continue
             if not _kernels_apply(params):
@@ -423,7 +427,8 @@ class FusedAdam(_FusedBase):
                 fn(*plan.args(), dtype_code(dt), float(lr), float(betas[0]), float(betas[1]), float(eps), float(wd), int(step), bool(adamw),
                    float(self.grad_scale), _stream())
                 self.kernel_launches += 1
-        self._grads_zeroed = self.zero_grad_in_step and all(s is not None for s in self._segments.values()) and len(self._segments) == len(self.param_groups)
+        if only is None:
+            self._grads_zeroed = self.zero_grad_in_step and all(s is not None for s in self._segments.values()) and len(self._segments) == len(self.param_groups)
         return loss
 
     def _torch_step(self, params, group):

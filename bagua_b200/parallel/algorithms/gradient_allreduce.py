@@ -139,9 +139,23 @@ class _ShardedStateMixin:
             if hi > lo:
                 rec["state"][0][: hi - lo].copy_(rec["weights"][lo:hi].float())
 
+    def _step_uncovered(self):
+        """Parameters that no bucket kernel updates — MoE experts (excluded from data parallelism), ignored parameters —
+        get the ordinary fused update here; their gradients are cleared like the bucketed ones."""
+        covered = getattr(self, "_covered", set())
+        left = [p for g in self.param_groups for p in g["params"] if id(p) not in covered and p.grad is not None]
+        if left:
+            super().step(only={id(p) for p in left})
+            import torch
+
+            torch._foreach_zero_([p.grad for p in left])
+
     def _register_shard(self, rec):
         if not hasattr(self, "_shards"):
             self._shards = []
+        if not hasattr(self, "_covered"):
+            self._covered = set()
+        self._covered.update(rec.get("param_ids", ()))
         self._shards.append(rec)
         pending = getattr(self, "_pending_state", None)
         if pending is not None:
@@ -182,6 +196,7 @@ def make_sharded_fused_sgd(params, lr=1e-3, momentum=0.0, dampening=0.0, weight_
                 return super().step(closure)
             # the update already happened in the bucket kernels of this iteration; publish hyper-parameters for the next
             self._sync_hyper()
+            self._step_uncovered()
             self._grads_zeroed = True
             self.kernel_launches += len(self._comm_ops)
             return None
@@ -217,6 +232,7 @@ def make_sharded_fused_adam(params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weigh
             if not self._comm_ops:
                 return super().step(closure)
             self._sync_hyper()
+            self._step_uncovered()
             self._grads_zeroed = True
             self.kernel_launches += len(self._comm_ops)
             return None
@@ -316,7 +332,7 @@ class FusedGradientAllReduceAlgorithmImpl(GradientAllReduceAlgorithmImpl):
         layout = [(t.bagua_tensor_name, (t.bagua_getter_closure().data_ptr() - base) // flat.element_size(), t.bagua_getter_closure().numel(),
                    tuple(t.shape), tuple(dense_strides(t))) for t in bucket.tensors if not t.bagua_tensor_name.startswith("bagua_padding_tensor")]
         opt._register_shard({"bucket": bucket.name, "group": self.process_group, "numel": flat.numel(), "lo": lo, "hi": hi, "layout": layout,
-                             "state": bucket._fused_state, "op": op, "weights": wflat})
+                             "state": bucket._fused_state, "op": op, "weights": wflat, "param_ids": [id(t) for t in bucket.tensors]})
         opt._sync_hyper()
 
 
@@ -336,4 +352,5 @@ class FusedGradientAllReduceAlgorithm(Algorithm):
             opt._pending_state = opt.state_dict()
         opt._comm_ops = []
         opt._shards = []
+        opt._covered = set()
         return FusedGradientAllReduceAlgorithmImpl(process_group, self.optimizer, average=self.average)

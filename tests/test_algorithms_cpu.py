@@ -365,3 +365,38 @@ def test_native_autograd_hooks_match_python_hooks():
     r0, r1 = run_distributed(_ddp_wrapper_worker, world=2, extra_env={"BAGUA_NATIVE_HOOKS": "1"})
     assert torch.equal(r0[0], r1[0]) and not torch.equal(r0[2], r1[2])   # no_sync() disables the native hooks too
     torch.testing.assert_close(r0[3], r1[3])
+
+
+def test_in_bucket_optimizers_also_update_parameters_outside_the_buckets():
+    """MoE experts and ignored parameters are not part of any bucket, so no bucket kernel updates them: the sharded optimizers'
+    ``step()`` applies the ordinary update to exactly those parameters (and clears their gradients), and leaves the
+    bucketed ones to the kernels."""
+    import torch
+
+    from bagua_b200.parallel.algorithms.gradient_allreduce import make_sharded_fused_adam, make_sharded_fused_sgd
+
+    class Op:
+        def set_hyper(self, *a):
+            self.hyper = a
+
+        def steps(self):
+            return 0
+
+    for make, ref_cls, kw in ((make_sharded_fused_sgd, torch.optim.SGD, dict(lr=0.1, momentum=0.9)),
+                              (lambda ps, **k: make_sharded_fused_adam(ps, adamw=True, **k), torch.optim.AdamW, dict(lr=0.01, weight_decay=0.01))):
+        torch.manual_seed(0)
+        bucketed, expert = torch.nn.Parameter(torch.randn(5)), torch.nn.Parameter(torch.randn(3, 4))
+        ref = torch.nn.Parameter(expert.detach().clone())
+        opt = make([bucketed, expert], **kw)
+        ropt = ref_cls([ref], **kw)
+        opt._comm_ops, opt._covered = [Op()], {id(bucketed)}     # what FusedGradientAllReduceAlgorithm sets up on a GPU box
+        before = bucketed.detach().clone()
+        for _ in range(3):
+            g = torch.randn(3, 4)
+            bucketed.grad, expert.grad, ref.grad = torch.ones(5), g.clone(), g.clone()
+            opt.step()
+            ropt.step()
+            assert float(expert.grad.abs().sum()) == 0.0          # cleared like the bucketed gradients
+            assert torch.equal(bucketed.grad, torch.ones(5))      # the kernel's business, not step()'s
+        torch.testing.assert_close(expert.detach(), ref.detach(), rtol=1e-5, atol=1e-6)
+        assert torch.equal(bucketed.detach(), before)
