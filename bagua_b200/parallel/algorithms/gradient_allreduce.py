@@ -107,13 +107,16 @@ class _ShardedStateMixin:
                     state.setdefault(name, {})[key] = full.cpu()
             steps = max(steps, int(rec["op"].steps()))
         groups = [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]
-        return {"sharded_fused": self._kind, "steps": steps, "state": state, "param_groups": groups}
+        # parameters outside the buckets (MoE experts, ignored ones) are stepped by the base class: their state in torch's format
+        return {"sharded_fused": self._kind, "steps": steps, "state": state, "param_groups": groups, "uncovered": super().state_dict()}
 
     def load_state_dict(self, sd):
         if not isinstance(sd, dict) or "sharded_fused" not in sd:
             return super().load_state_dict(sd)
         if sd["sharded_fused"] != self._kind:
             raise ValueError(f"checkpoint holds {sd['sharded_fused']} state, this optimizer is {self._kind}")
+        if sd.get("uncovered") is not None:
+            super().load_state_dict(sd["uncovered"])
         for g, saved in zip(self.param_groups, sd["param_groups"]):
             g.update(saved)
         if not getattr(self, "_shards", None):

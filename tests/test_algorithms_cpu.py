@@ -400,3 +400,11 @@ def test_in_bucket_optimizers_also_update_parameters_outside_the_buckets():
             assert torch.equal(bucketed.grad, torch.ones(5))      # the kernel's business, not step()'s
         torch.testing.assert_close(expert.detach(), ref.detach(), rtol=1e-5, atol=1e-6)
         assert torch.equal(bucketed.detach(), before)
+        # the expert's optimizer state is part of the (otherwise shard-derived) checkpoint
+        opt._shards = [{"state": (), "group": None, "numel": 0, "layout": [], "lo": 0, "hi": 0, "op": Op(), "weights": None}]
+        sd = opt.state_dict()
+        assert sd["sharded_fused"] and len(sd["uncovered"]["state"]) == 1
+        opt2 = make([torch.nn.Parameter(bucketed.detach().clone()), torch.nn.Parameter(expert.detach().clone())], **kw)
+        opt2.load_state_dict(sd)
+        loaded = list(opt2.state.values())
+        assert len(loaded) == 1 and all(torch.equal(v, list(opt.state.values())[0][k]) for k, v in loaded[0].items() if isinstance(v, torch.Tensor))
