@@ -145,8 +145,11 @@ class _ShardedStateMixin:
     def _step_uncovered(self):
         """Parameters that no bucket kernel updates — MoE experts (excluded from data parallelism), ignored parameters —
         get the ordinary fused update here; their gradients are cleared like the bucketed ones."""
-        covered = getattr(self, "_covered", set())
-        left = [p for g in self.param_groups for p in g["params"] if id(p) not in covered and p.grad is not None]
+        candidates = getattr(self, "_uncovered_cache", None)
+        if candidates is None:  # the parameter list is static between (re-)initialisations: looked up once, usually empty
+            covered = getattr(self, "_covered", set())
+            candidates = self._uncovered_cache = [p for g in self.param_groups for p in g["params"] if id(p) not in covered]
+        left = [p for p in candidates if p.grad is not None]
         if left:
             super().step(only={id(p) for p in left})
             import torch
@@ -159,6 +162,7 @@ class _ShardedStateMixin:
         if not hasattr(self, "_covered"):
             self._covered = set()
         self._covered.update(rec.get("param_ids", ()))
+        self._uncovered_cache = None
         self._shards.append(rec)
         pending = getattr(self, "_pending_state", None)
         if pending is not None:
@@ -356,4 +360,5 @@ class FusedGradientAllReduceAlgorithm(Algorithm):
         opt._comm_ops = []
         opt._shards = []
         opt._covered = set()
+        opt._uncovered_cache = None
         return FusedGradientAllReduceAlgorithmImpl(process_group, self.optimizer, average=self.average)
