@@ -154,6 +154,17 @@ def _can_flatten(group_params: List[torch.nn.Parameter], all_params: List[torch.
         # parameters that are themselves communicated in place (weight-averaging algorithms) must not be re-pointed
         if hasattr(p, "_bagua_backend_tensor") and getattr(p, "_bagua_getter_closure", None) is None:
             return False
+    # the flat kernels update (and clear) the whole span: every tensor of the buckets involved must belong to this group —
+    # a second optimizer's parameters interleaved in the same buckets would have their gradients cleared under its feet
+    seen_buckets = set()
+    for p in group_params:
+        b = getattr(p, "_bagua_bucket", None)
+        if b is None or id(b) in seen_buckets:
+            continue
+        seen_buckets.add(id(b))
+        for t in b.tensors:
+            if id(t) not in mine and not getattr(t, "bagua_tensor_name", "").startswith("bagua_padding_tensor"):
+                return False
     es = g0.element_size()
     lo = min(p.grad.data_ptr() for p in group_params)
     hi = max(p.grad.data_ptr() + p.grad.numel() * es for p in group_params)

@@ -843,3 +843,36 @@ def test_flat_fused_optimizers_resume_exactly_from_state_dict():
     from tests.mp_utils import run_distributed
 
     assert all(run_distributed(_flat_resume_worker, world=1))
+
+
+def _two_optimizers_worker(rank, world):
+    """Two fused optimizers over disjoint halves of one model whose gradients share a bucket: neither may take the flat path (its
+    kernel would clear the other optimizer's gradients inside the span); the chunked path trains exactly like two torch SGDs."""
+    import copy
+
+    import bagua_b200 as bagua
+    from bagua_b200.ops import optim
+    from bagua_b200.parallel.algorithms import gradient_allreduce
+
+    optim._kernels_apply = lambda params: True          # pretend the kernels apply: the decision under test is _can_flatten's
+
+    def no_kernel(*a, **k):
+        raise AssertionError("flat kernel must not be used when a bucket mixes two optimizers")
+
+    optim.flat_sgd_ = no_kernel
+    bagua.init_process_group()
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 8), torch.nn.Tanh(), torch.nn.Linear(8, 2))
+    a, b = optim.FusedSGD(model[0].parameters(), lr=0.1, momentum=0.9), optim.FusedSGD(model[2].parameters(), lr=0.05)
+    model = model.with_bagua([a, b], gradient_allreduce.GradientAllReduceAlgorithm())
+    assert len(model.bagua_buckets) == 1
+    group = a.param_groups[0]["params"]
+    model(torch.randn(4, 6)).sum().backward()
+    assert not optim._can_flatten(group, group) and not optim._can_flatten(b.param_groups[0]["params"], b.param_groups[0]["params"])
+    return True
+
+
+def test_flat_path_is_refused_when_a_bucket_mixes_optimizers():
+    from tests.mp_utils import run_distributed
+
+    assert all(run_distributed(_two_optimizers_worker, world=1))
