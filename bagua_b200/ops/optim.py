@@ -263,6 +263,33 @@ class _FusedBase(torch.optim.Optimizer):
             seg.bound = False
 
     @torch.no_grad()
+    def clip_grad_norm_(self, max_norm: float, norm_type: float = 2.0) -> torch.Tensor:
+        """Global gradient-norm clipping without a per-tensor pass: for parameter groups on the flat path the norm is one
+        reduction over the group's span of the bucket arena and the scaling one in-place multiply (the gaps of the span are
+        alignment padding that holds zeros); other parameters go through the usual per-tensor path.  No host synchronisation;
+        returns the total norm (a device tensor) like ``torch.nn.utils.clip_grad_norm_``.  Call it after the gradients are
+        complete (after ``backward()`` of the last micro-batch) and before ``step()``."""
+        flat_ids, norms, loose = set(), [], []
+        for gi, group in enumerate(self.param_groups):
+            seg = self._segment_for(gi, group)
+            if seg is not None:
+                norms.append(torch.linalg.vector_norm(seg.grad_flat, norm_type, dtype=torch.float32))
+                flat_ids.update(id(p) for p in seg.params)
+        for group in self.param_groups:
+            loose += [p for p in group["params"] if p.grad is not None and id(p) not in flat_ids]
+        norms += [torch.linalg.vector_norm(p.grad, norm_type, dtype=torch.float32) for p in loose]
+        if not norms:
+            return torch.zeros(())
+        dev = norms[0].device
+        total = torch.linalg.vector_norm(torch.stack([n.to(dev) for n in norms]), norm_type)
+        coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+        for seg in self.flat_segments():
+            seg.grad_flat.mul_(coef.to(seg.grad_flat.device, seg.grad_flat.dtype))
+        for p in loose:
+            p.grad.mul_(coef.to(p.grad.device, p.grad.dtype))
+        return total
+
+    @torch.no_grad()
     def refresh_master_weights(self):
         """Re-read the fp32 master copies from the (low-precision) parameters.  Needed after the weights were loaded or
         edited behind the optimizer's back: the next step writes ``master − lr·update`` over the parameters."""

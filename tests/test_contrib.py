@@ -836,6 +836,20 @@ def _flat_resume_worker(rank, world):
                 ref(x).pow(2).mean().backward()
                 ropt.step()
             torch.testing.assert_close(want, torch.cat([p.detach().reshape(-1) for p in ref.parameters()]), rtol=1e-5, atol=1e-6)
+    # clip_grad_norm_ on the flat path: one reduction + one multiply over the arena span, same result as the per-tensor utility
+    m = copy.deepcopy(base)
+    twin = copy.deepcopy(base)
+    o = optim.FusedSGD(m.parameters(), lr=0.05, momentum=0.9)
+    m = m.with_bagua([o], gradient_allreduce.GradientAllReduceAlgorithm())
+    o.zero_grad()
+    m(batches[0]).pow(2).mean().mul(50).backward()
+    twin(batches[0]).pow(2).mean().mul(50).backward()
+    total = o.clip_grad_norm_(0.1)
+    want_total = torch.nn.utils.clip_grad_norm_(twin.parameters(), 0.1)
+    assert o.flat_segments() and float(want_total) > 0.1
+    torch.testing.assert_close(total, want_total)
+    for p, q in zip(m.parameters(), twin.parameters()):
+        torch.testing.assert_close(p.grad, q.grad)
     return True
 
 
