@@ -194,8 +194,9 @@ def make_sharded_fused_sgd(params, lr=1e-3, momentum=0.0, dampening=0.0, weight_
             self._shards = []
 
         def _sync_hyper(self):
-            g = self.param_groups[0]
-            for op in self._comm_ops:
+            groups = getattr(self, "_comm_groups", ())
+            for i, op in enumerate(self._comm_ops):
+                g = self.param_groups[groups[i] if i < len(groups) else 0]   # every bucket op serves one parameter group
                 op.set_hyper(float(g["lr"]), float(g["momentum"]), float(g["dampening"]), float(g["weight_decay"]), bool(g["nesterov"]))
 
         def step(self, closure=None):
@@ -231,8 +232,9 @@ def make_sharded_fused_adam(params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weigh
             self._shards = []
 
         def _sync_hyper(self):
-            g = self.param_groups[0]
-            for op in self._comm_ops:
+            groups = getattr(self, "_comm_groups", ())
+            for i, op in enumerate(self._comm_ops):
+                g = self.param_groups[groups[i] if i < len(groups) else 0]
                 op.set_hyper(float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), bool(g["adamw"]))
 
         def step(self, closure=None):
@@ -254,6 +256,10 @@ class FusedGradientAllReduceAlgorithmImpl(GradientAllReduceAlgorithmImpl):
         self.optimizer = optimizer
         self._weight_slices = []
 
+    @property
+    def bucket_pieces(self) -> int:
+        return max(1, len(self.optimizer.param_groups))
+
     def init_forward_pre_hook(self, bagua_ddp):
         """The update of iteration *i* runs inside the bucket kernels of *i*'s backward pass, before ``optimizer.step()`` is
         called — so the hyper-parameters are published at the start of every iteration (after any ``lr_scheduler.step()`` of
@@ -271,7 +277,24 @@ class FusedGradientAllReduceAlgorithmImpl(GradientAllReduceAlgorithmImpl):
 
         assert do_flatten, "the fused optimizer needs flattened buckets"
         es = tensors[0][0].bagua_getter_closure().element_size()
-        return [BaguaBucket(b, flatten=True, name=str(i), alignment=max(1, 16 // es), group=self.process_group) for i, b in enumerate(tensors)]
+        # One bucket kernel applies ONE set of hyper-parameters: with several parameter groups (weight decay / no weight decay)
+        # every suggested bucket is split so that each piece holds tensors of a single group. The pieces keep their place in
+        # the bucket order, so they become ready at about the same point of the backward pass as the original bucket.
+        group_of = {id(p): gi for gi, g in enumerate(self.optimizer.param_groups) for p in g["params"]}
+        multi = len(self.optimizer.param_groups) > 1
+        buckets = []
+        for i, b in enumerate(tensors):
+            if not multi:
+                buckets.append(BaguaBucket(b, flatten=True, name=str(i), alignment=max(1, 16 // es), group=self.process_group))
+                continue
+            pieces = {}
+            for t in b:
+                pieces.setdefault(group_of.get(id(t), 0), []).append(t)
+            for gi in sorted(pieces):
+                bk = BaguaBucket(pieces[gi], flatten=True, name=f"{i}.g{gi}", alignment=max(1, 16 // es), group=self.process_group)
+                bk._fused_group = gi
+                buckets.append(bk)
+        return buckets
 
     def init_operations(self, bagua_ddp, bucket):
         import os
@@ -287,7 +310,7 @@ class FusedGradientAllReduceAlgorithmImpl(GradientAllReduceAlgorithmImpl):
         is_adam = isinstance(opt, ShardedFusedAdam)
         if eng is None or bucket._slice is None or not (isinstance(opt, ShardedFusedSGD) or is_adam):
             return super().init_operations(bagua_ddp, bucket)
-        assert len(opt.param_groups) == 1, "the in-kernel optimizer supports a single parameter group"
+        group_index = getattr(bucket, "_fused_group", 0)
         C = native()
         flat = bucket.backend_tensor
         n, rank = self.process_group.size(), self.process_group.rank()
@@ -336,6 +359,9 @@ class FusedGradientAllReduceAlgorithmImpl(GradientAllReduceAlgorithmImpl):
         bucket._ops_keepalive.append(op)
         bucket.allreduce_variant = ("fused_adam_" if is_adam else "fused_sgd_") + ("multimem" if use_mc else "two_shot")
         opt._comm_ops.append(op)
+        if not hasattr(opt, "_comm_groups"):
+            opt._comm_groups = []
+        opt._comm_groups.append(group_index)
         layout = [(t.bagua_tensor_name, (t.bagua_getter_closure().data_ptr() - base) // flat.element_size(), t.bagua_getter_closure().numel(),
                    tuple(t.shape), tuple(dense_strides(t))) for t in bucket.tensors if not t.bagua_tensor_name.startswith("bagua_padding_tensor")]
         opt._register_shard({"bucket": bucket.name, "group": self.process_group, "numel": flat.numel(), "lo": lo, "hi": hi, "layout": layout,
@@ -358,6 +384,7 @@ class FusedGradientAllReduceAlgorithm(Algorithm):
             # over in their consolidated form; they are re-sharded when the new bucket ops are created
             opt._pending_state = opt.state_dict()
         opt._comm_ops = []
+        opt._comm_groups = []
         opt._shards = []
         opt._covered = set()
         opt._uncovered_cache = None

@@ -389,7 +389,9 @@ class BaguaDistributedDataParallel:
         if self.gradient_as_bucket_view and raw:
             sizes = [sum(t.bagua_getter_closure().numel() * t.bagua_getter_closure().element_size() for t in b) for b in raw]
             dev = raw[0][0].bagua_getter_closure().device
-            self._arena = BucketArena(self.process_group, dev, BucketArena.required_bytes(sizes))
+            # an algorithm may cut every suggested bucket into several pieces (one per optimizer parameter group): room for their padding
+            pieces = max(1, int(getattr(self.bagua_algorithm, "bucket_pieces", 1)))
+            self._arena = BucketArena(self.process_group, dev, BucketArena.required_bytes(sizes, slack=2 * 1024 * pieces))
         with bucket_arena(self._arena):
             self.bagua_buckets = self.bagua_algorithm.tensors_to_buckets(raw, self.gradient_as_bucket_view)
         for bucket in self.bagua_buckets:

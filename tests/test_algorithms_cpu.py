@@ -408,3 +408,48 @@ def test_in_bucket_optimizers_also_update_parameters_outside_the_buckets():
         opt2.load_state_dict(sd)
         loaded = list(opt2.state.values())
         assert len(loaded) == 1 and all(torch.equal(v, list(opt.state.values())[0][k]) for k, v in loaded[0].items() if isinstance(v, torch.Tensor))
+
+
+def _fused_two_groups_worker(rank, world):
+    """Weight decay on the matrices, none on the biases — two parameter groups: the fused algorithm cuts every bucket into
+    single-group pieces (one bucket kernel applies one set of hyper-parameters) and training equals torch AdamW with the same
+    groups on averaged gradients."""
+    import torch.distributed as dist
+
+    import bagua_b200 as bagua
+    from bagua_b200.parallel.algorithms.gradient_allreduce import FusedGradientAllReduceAlgorithm, make_sharded_fused_adam
+
+    bagua.init_process_group()
+    torch.manual_seed(3)
+    model = _net()
+    oracle = copy.deepcopy(model)
+
+    def groups(m):
+        decay = [p for p in m.parameters() if p.dim() > 1]
+        rest = [p for p in m.parameters() if p.dim() <= 1]
+        return [{"params": decay, "weight_decay": 0.05}, {"params": rest, "weight_decay": 0.0, "lr": 5e-3}]
+
+    opt = make_sharded_fused_adam(groups(model), lr=1e-2, adamw=True)
+    oopt = torch.optim.AdamW(groups(oracle), lr=1e-2)
+    model = model.with_bagua([opt], FusedGradientAllReduceAlgorithm(opt))
+    group_of = {id(p): gi for gi, g in enumerate(opt.param_groups) for p in g["params"]}
+    names = []
+    for b in model.bagua_buckets:
+        kinds = {group_of[id(t)] for t in b.tensors if not t.bagua_tensor_name.startswith("bagua_padding_tensor")}
+        assert len(kinds) == 1 and b.name.endswith(f".g{kinds.pop()}")
+        names.append(b.name)
+
+    def avg(_it):
+        for p in oracle.parameters():
+            dist.all_reduce(p.grad)
+            p.grad /= world
+
+    _train(model, opt, rank, 4)
+    _train(oracle, oopt, rank, 4, post=avg)
+    return _flat(model), _flat(oracle), names
+
+
+def test_fused_algorithm_splits_buckets_by_parameter_group():
+    for mine, oracle, names in run_distributed(_fused_two_groups_worker, world=2):
+        torch.testing.assert_close(mine, oracle, rtol=1e-5, atol=1e-6)
+        assert len(names) >= 2 and any(n.endswith(".g0") for n in names) and any(n.endswith(".g1") for n in names)
