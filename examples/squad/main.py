@@ -98,7 +98,9 @@ if args.algorithm == "qadam":
     optimizer = q_adam.QAdamOptimizer(model.parameters(), lr=args.learning_rate, warmup_steps=100)
     algorithm = q_adam.QAdamAlgorithm(optimizer)
 elif args.fused_shard and cuda and world > 1:
-    optimizer = make_sharded_fused_adam(model.parameters(), lr=args.learning_rate, weight_decay=args.weight_decay, adamw=True)
+    # AdamW inside the bucket kernels; the algorithm cuts the buckets so that each kernel serves one of the two groups
+    optimizer = make_sharded_fused_adam([{"params": decay, "weight_decay": args.weight_decay}, {"params": no_decay, "weight_decay": 0.0}],
+                                        lr=args.learning_rate, adamw=True)
     algorithm = FusedGradientAllReduceAlgorithm(optimizer)
 else:
     groups = [{"params": decay, "weight_decay": args.weight_decay}, {"params": no_decay, "weight_decay": 0.0}]
