@@ -62,4 +62,5 @@ from .parallel import moe  # noqa: F401
 
 
 def version() -> str:
+    """Package version string."""
     return __version__

@@ -139,6 +139,9 @@ class _DecentralizedOpHandle:
 
 
 class BaguaBucket:
+    """A group of bagua tensors communicated together (reference bagua/torch_api/bucket.py:18-366): optionally flattened into one
+    contiguous slice of the model's bucket arena (NVSwitch symmetric memory on GPUs), carrying the ordered list of communication
+    ops the scheduler runs once every tensor of the bucket is ready."""
     def __init__(self, tensors: List[torch.Tensor], name: str, flatten: bool, alignment: int = 1, group=None):
         """
         Args:

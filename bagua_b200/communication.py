@@ -765,7 +765,7 @@ def broadcast_coalesced(tensors: Sequence[torch.Tensor], src: int = 0, comm: Opt
 
 
 def broadcast_object(obj: object, src: int = 0, comm: Optional[Communicator] = None) -> object:
-    """Broadcast a picklable python object; returns it on every rank (reference communication.py:683-741)."""
+    """Broadcast a picklable python object; returns it on every rank (reference communication.py:668-708)."""
     c = _comm(comm)
     dev = "cuda" if _use_cuda() else "cpu"
     if c.rank() == src:
@@ -793,6 +793,7 @@ def reduce(send_tensor, recv_tensor, dst: int, op: ReduceOp = ReduceOp.SUM, comm
 
 
 def reduce_inplace(tensor, dst: int, op: ReduceOp = ReduceOp.SUM, comm: Optional[Communicator] = None):
+    """In-place :func:`reduce`: ``tensor`` on ``dst`` becomes the reduction over all ranks (reference communication.py:792-813)."""
     c = _comm(comm)
     _check(c, tensor)
     with _on_comm_stream(c):
@@ -827,6 +828,7 @@ def allreduce(send_tensor, recv_tensor, op: ReduceOp = ReduceOp.SUM, comm: Optio
 
 
 def allreduce_inplace(tensor, op: ReduceOp = ReduceOp.SUM, comm: Optional[Communicator] = None):
+    """In-place all-reduce of ``tensor`` over the communicator (``AVG`` divides by its size); CUDA tensors on one NVSwitch node take the peer kernels (reference communication.py:922-943)."""
     c = _comm(comm)
     _check(c, tensor)
     with _on_comm_stream(c):
@@ -864,6 +866,7 @@ def _peer_engine_for(c: Communicator):
 
 
 def allgather(send_tensor, recv_tensor, comm: Optional[Communicator] = None):
+    """``recv_tensor`` (``nranks × send_tensor.numel()``) = concatenation of every rank's ``send_tensor`` in rank order (reference communication.py:946-982)."""
     c = _comm(comm)
     _check(c, send_tensor, recv_tensor)
     with _on_comm_stream(c):
@@ -873,6 +876,7 @@ def allgather(send_tensor, recv_tensor, comm: Optional[Communicator] = None):
 
 
 def allgather_inplace(tensor, comm: Optional[Communicator] = None):
+    """All-gather inside one buffer: chunk ``rank`` of ``tensor`` is this rank's contribution, all chunks are filled on return (reference communication.py:985-1005)."""
     c = _comm(comm)
     _check(c, tensor)
     with _on_comm_stream(c):
@@ -880,6 +884,7 @@ def allgather_inplace(tensor, comm: Optional[Communicator] = None):
 
 
 def gather(send_tensor, recv_tensor, dst: int, comm: Optional[Communicator] = None):
+    """``recv_tensor`` on ``dst`` = concatenation of every rank's ``send_tensor``; untouched elsewhere (reference communication.py:1008-1046)."""
     c = _comm(comm)
     _check(c, send_tensor, recv_tensor)
     with _on_comm_stream(c):
@@ -887,6 +892,7 @@ def gather(send_tensor, recv_tensor, dst: int, comm: Optional[Communicator] = No
 
 
 def gather_inplace(tensor, count: int, dst: int, comm: Optional[Communicator] = None):
+    """In-place gather: the first ``count`` elements of ``tensor`` are sent; on ``dst`` ``tensor`` holds all ranks' pieces afterwards (reference communication.py:1049-1081)."""
     c = _comm(comm)
     _check(c, tensor)
     with _on_comm_stream(c):
@@ -894,6 +900,7 @@ def gather_inplace(tensor, count: int, dst: int, comm: Optional[Communicator] = 
 
 
 def scatter(send_tensor, recv_tensor, src: int, comm: Optional[Communicator] = None):
+    """Rank ``src`` splits ``send_tensor`` into ``nranks`` equal chunks; every rank receives its chunk in ``recv_tensor`` (reference communication.py:1084-1123)."""
     c = _comm(comm)
     _check(c, send_tensor, recv_tensor)
     with _on_comm_stream(c):
@@ -901,6 +908,7 @@ def scatter(send_tensor, recv_tensor, src: int, comm: Optional[Communicator] = N
 
 
 def scatter_inplace(tensor, count: int, src: int, comm: Optional[Communicator] = None):
+    """In-place scatter: chunk ``rank`` (``count`` elements) of ``src``'s ``tensor`` lands in the first ``count`` elements of ``tensor`` (reference communication.py:1126-1160)."""
     c = _comm(comm)
     _check(c, tensor)
     with _on_comm_stream(c):
@@ -908,6 +916,7 @@ def scatter_inplace(tensor, count: int, src: int, comm: Optional[Communicator] =
 
 
 def reduce_scatter(send_tensor, recv_tensor, op: ReduceOp = ReduceOp.SUM, comm: Optional[Communicator] = None):
+    """Reduce ``send_tensor`` over all ranks and leave chunk ``rank`` of the result in ``recv_tensor`` (reference communication.py:1163-1202)."""
     c = _comm(comm)
     _check(c, send_tensor, recv_tensor)
     with _on_comm_stream(c):
@@ -917,6 +926,7 @@ def reduce_scatter(send_tensor, recv_tensor, op: ReduceOp = ReduceOp.SUM, comm: 
 
 
 def reduce_scatter_inplace(tensor, op: ReduceOp = ReduceOp.SUM, comm: Optional[Communicator] = None):
+    """In-place reduce-scatter: chunk ``rank`` of ``tensor`` holds the reduced chunk afterwards (reference communication.py:1205-1235)."""
     c = _comm(comm)
     _check(c, tensor)
     with _on_comm_stream(c):
@@ -924,6 +934,7 @@ def reduce_scatter_inplace(tensor, op: ReduceOp = ReduceOp.SUM, comm: Optional[C
 
 
 def alltoall(send_tensor, recv_tensor, comm: Optional[Communicator] = None):
+    """Chunk ``j`` of ``send_tensor`` goes to rank ``j``; chunk ``i`` of ``recv_tensor`` comes from rank ``i`` (equal chunks; reference communication.py:1238-1276)."""
     c = _comm(comm)
     _check(c, send_tensor, recv_tensor)
     with _on_comm_stream(c):
@@ -931,6 +942,7 @@ def alltoall(send_tensor, recv_tensor, comm: Optional[Communicator] = None):
 
 
 def alltoall_inplace(tensor, comm: Optional[Communicator] = None):
+    """In-place :func:`alltoall` (reference communication.py:1279-1298)."""
     c = _comm(comm)
     _check(c, tensor)
     with _on_comm_stream(c):
@@ -938,6 +950,7 @@ def alltoall_inplace(tensor, comm: Optional[Communicator] = None):
 
 
 def alltoall_v(send_tensor, send_counts, send_displs, recv_tensor, recv_counts, recv_displs, comm: Optional[Communicator] = None):
+    """All-to-all with per-peer element counts and displacements, MPI_Alltoallv style (reference communication.py:1301-1350)."""
     c = _comm(comm)
     _check(c, send_tensor, recv_tensor)
     with _on_comm_stream(c):
@@ -945,6 +958,7 @@ def alltoall_v(send_tensor, send_counts, send_displs, recv_tensor, recv_counts, 
 
 
 def alltoall_v_inplace(tensor, counts, displs, comm: Optional[Communicator] = None):
+    """In-place :func:`alltoall_v` with identical send and receive layout (reference communication.py:1353-1374)."""
     c = _comm(comm)
     _check(c, tensor)
     with _on_comm_stream(c):

@@ -32,6 +32,7 @@ _DTYPE_BYTES = {TensorDtype.F32: 4, TensorDtype.F16: 2, TensorDtype.BF16: 2, Ten
 
 
 def get_tensor_declaration_bytes(td: TensorDeclaration) -> int:
+    """Size in bytes of the tensor a declaration describes (reference bagua_define.py:24-35; bf16 added)."""
     dtype = td["dtype"]
     if not isinstance(dtype, TensorDtype):
         dtype = TensorDtype(dtype)

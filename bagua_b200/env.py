@@ -156,3 +156,24 @@ def find_free_network_port() -> int:
         s.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
         s.bind(("127.0.0.1", 0))
         return s.getsockname()[1]
+
+
+def _document_accessors():
+    """Every accessor that is a named view of one ``SETTINGS`` row gets that row as its docstring (``VAR``: meaning, default)."""
+    import inspect
+    import re
+
+    for name, fn in list(globals().items()):
+        if not inspect.isfunction(fn) or fn.__doc__ or fn.__module__ != __name__ or name.startswith("_"):
+            continue
+        try:
+            m = re.search(r'_read\("([A-Z_]+)"\)', inspect.getsource(fn))
+        except OSError:  # no source available (frozen / zipped install)
+            m = None
+        if m and m.group(1) in SETTINGS:
+            st = SETTINGS[m.group(1)]
+            fn.__doc__ = f"``{st.var}``: {st.help} (default {st.default!r})."
+
+
+get_autotune_server_addr.__doc__ = "``AUTO_TUNE_SERVER_ADDR`` (``host:port`` of the autotune service; set by the launcher when autotune is on), or ``None``."
+_document_accessors()

@@ -23,6 +23,7 @@ HANDLE_BYTES = 128
 
 
 def plugin_path(build: bool = True) -> Path:
+    """Path of ``libnccl-net-bagua.so`` (built on demand)."""
     if build and not _LIB.exists():
         from ._build import build_net_plugin
 

@@ -17,6 +17,7 @@ __all__ = ["grouped_linear", "grouped_gemm_tn", "tcgen05_supported"]
 
 
 def tcgen05_supported(x: torch.Tensor, M: int, N: int, K: int) -> bool:
+    """Whether the tcgen05 grouped GEMM handles this problem: bf16 CUDA operands, ``M % 128 == 0``, ``N % 128 == 0``, ``K % 64 == 0``."""
     return x.is_cuda and x.dtype == torch.bfloat16 and native().grouped_gemm_supported(M, N, K)
 
 

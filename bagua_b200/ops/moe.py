@@ -101,6 +101,8 @@ def _peer_ctx(tokens: torch.Tensor, group, world: int):
 
 
 def dispatch(tokens, expert_idx, slot_idx, num_experts: int, capacity: int, group, world: int, num_local_experts: int) -> torch.Tensor:
+    """Route token rows to their experts' capacity slots: ``tokens [S, M]`` → ``[world, E_local, C, M]`` on the expert owners (peer scatter
+    kernel on one NVSwitch node, dense one-hot + ``all_to_all_single`` otherwise).  Differentiable."""
     ctx = _peer_ctx(tokens, group, world)
     if ctx is not None:
         return ctx.dispatch(tokens, expert_idx, slot_idx, num_experts, capacity, num_local_experts)
@@ -111,6 +113,8 @@ def dispatch(tokens, expert_idx, slot_idx, num_experts: int, capacity: int, grou
 
 
 def combine(expert_out, expert_idx, slot_idx, weights, num_experts: int, capacity: int, group, world: int, num_local_experts: int) -> torch.Tensor:
+    """Inverse of :func:`dispatch`: fetch every token's expert outputs and sum them with the gate ``weights`` → ``[S, M]``.  Differentiable
+    in ``expert_out`` and ``weights``."""
     ctx = _peer_ctx(expert_out, group, world)
     if ctx is not None:
         return ctx.combine(expert_out, expert_idx, slot_idx, weights, num_experts, capacity, num_local_experts)

@@ -30,6 +30,7 @@ _contexts: Dict[int, Optional["MoEPeerContext"]] = {}
 
 
 class MoEPeerContext:
+    """Symmetric buffers + kernel wrappers of one process group's MoE exchange (scatter / gather / GEMM-push over peer memory)."""
     def __init__(self, engine):
         self.engine = engine
         self.comm = engine.comm

@@ -13,6 +13,8 @@ __all__ = ["bias_relu", "bias_relu_maxpool2", "conv_bias_relu", "fused_supported
 
 
 def fused_supported(x: torch.Tensor, channels: int) -> bool:
+    """Whether the fused NHWC epilogue kernels accept ``x``: channels_last f16/bf16 CUDA 4-D tensor, channels a multiple of 8 that
+    maps onto a 256-thread block (``256 % (channels / 8) == 0``), at most 2048."""
     return (x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and x.dim() == 4 and channels % 8 == 0 and channels <= 2048
             and 256 % (channels // 8) == 0 and x.is_contiguous(memory_format=torch.channels_last))
 

@@ -78,6 +78,7 @@ class _MultiPlan:
 
 
 def multi_tensor_plan(lists: List[List[torch.Tensor]]) -> _MultiPlan:
+    """Device pointer / size / block tables for the chunked multi-tensor kernels over ``lists`` (``[list][tensor]``, equal lengths)."""
     return _MultiPlan(lists)
 
 

@@ -23,6 +23,7 @@ def _align32(x: int) -> int:
 
 
 def chunk_bytes(chunk_elems: int) -> int:
+    """Wire size of one MinMaxUInt8 chunk: 32-byte header (min, max) + payload padded to 32 bytes."""
     return _align32(chunk_elems) + 32
 
 
@@ -51,6 +52,7 @@ def torch_compress_chunk(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 
 
 def torch_decompress_chunk(minmax: torch.Tensor, q: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """Inverse of :func:`torch_compress_chunk`: ``(q + lower) / scale`` in ``dtype``."""
     mn, mx = minmax[0].float(), minmax[1].float()
     scale = _scale(mn, mx)
     upper = torch.round(mx * scale)
@@ -73,6 +75,7 @@ def torch_compress(x: torch.Tensor, n_chunks: int) -> torch.Tensor:
 
 
 def torch_decompress(buf: torch.Tensor, numel: int, n_chunks: int, dtype: torch.dtype) -> torch.Tensor:
+    """Decode a whole wire buffer of ``n_chunks`` chunks back into ``numel`` elements of ``dtype`` (any device)."""
     c = numel // n_chunks
     cb = chunk_bytes(c)
     es = torch.empty(0, dtype=dtype).element_size()

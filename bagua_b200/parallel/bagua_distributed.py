@@ -63,6 +63,10 @@ class _States:
 
 
 class BaguaDistributedDataParallel:
+    """The data-parallel engine behind ``module.with_bagua`` / ``DistributedDataParallel`` (reference
+    bagua/torch_api/data_parallel/bagua_distributed.py:27-505): builds the tensor list and the buckets with the algorithm, installs
+    the forward-pre / gradient / post-backward / optimizer hooks, broadcasts parameters and optimizer state from rank 0, talks to
+    the autotune service, and hands ready gradients to the C++ scheduler."""
     def __init__(
         self,
         module: torch.nn.Module,

@@ -43,6 +43,8 @@ class _Encoder(json.JSONEncoder):
 
 
 class AutotuneServiceTaskManager:
+    """Per-model tuning session of the service: the task manager (search), the check board (which rank reported which iteration), the
+    sampling clock and the hyper-parameters currently in force (reference autotune_service.py:35-45)."""
     def __init__(self, task_name: str, world_size: int, is_output_autotune_log: bool) -> None:
         self.inner = AutotuneTaskManager(task_name, is_output_autotune_log)
         self.warmup_pass_count = 0
@@ -54,6 +56,8 @@ class AutotuneServiceTaskManager:
 
 
 class AutotuneService:
+    """The autotune HTTP service run by rank 0 (reference autotune_service.py:48-303): workers register their tensors, report speed and
+    tensor ready order, and ask for the next bucketing; a new sample is only issued when every rank has reached the same iteration."""
     MAX_TRACE_INFO = 1000
 
     def __init__(self, world_size, autotune_level=0, max_samples=60, sampling_confidence_time_s=5, warmup_time_s=30,
@@ -227,6 +231,7 @@ def run_autotune_server(port: int, world_size: int, **kwargs):
 
 
 def start_autotune_server_process(port: int, world_size: int, **kwargs) -> multiprocessing.Process:
+    """Start :class:`AutotuneService` on ``port`` in a daemon process and return it."""
     ctx = multiprocessing.get_context("spawn")
     p = ctx.Process(target=run_autotune_server, args=(port, world_size), kwargs=kwargs, daemon=True)
     p.start()

@@ -37,6 +37,9 @@ def sysperf(host_list: str, nproc_per_node: int, ssh_port: int, env: dict, model
 
 def autotune_system_hyperparameters(host_list: str, nproc_per_node: int, ssh_port: int, max_samples: int = 100, model: str = "vgg16", extra_args=(),
                                     port_fn=None):
+    """Offline tuner of the NCCL system knobs (``NCCL_MIN_NCHANNELS``, ``NCCL_SOCKET_NTHREADS``, ``NCCL_NSOCKS_PERTHREAD``,
+    ``NCCL_BUFFSIZE``): launches ``bagua_sys_perf --model <model>`` over ``baguarun`` for every sample, reads the throughput it
+    prints and returns the best setting (reference service/autotune_system.py:92-169)."""
     optim = BayesianOptimizer(
         {
             "NCCL_MIN_NCHANNELS": IntParam(0, (0, 12)),

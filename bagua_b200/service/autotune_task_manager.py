@@ -50,6 +50,8 @@ def split_bucket_by_bucket_size(tensor_list: List[TensorDeclaration], bucket_siz
 
 
 class AutotuneTaskManager:
+    """Search loop of one model (reference autotune_task_manager.py:21-185): records (hyper-parameters, score) samples, asks the Bayesian
+    optimizer for the next bucket size / hierarchical flag / kernel variant and turns it into buckets over the reported tensor order."""
     RECORD_MAX_NUM = 1000
 
     def __init__(self, task_name: str, need_to_log: bool) -> None:

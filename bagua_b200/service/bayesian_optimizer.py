@@ -13,18 +13,21 @@ __all__ = ["IntParam", "FloatParam", "BoolParam", "BayesianOptimizer"]
 
 
 class IntParam:
+    """Integer search dimension ``[lo, hi]`` with its current value."""
     def __init__(self, val: int, space_dimension: Tuple[int, int]):
         self.val = int(val)
         self.space_dimension = (int(space_dimension[0]), int(space_dimension[1]))
 
 
 class FloatParam:
+    """Real-valued search dimension ``[lo, hi]`` with its current value."""
     def __init__(self, val: float, space_dimension: Tuple[float, float]):
         self.val = float(val)
         self.space_dimension = (float(space_dimension[0]), float(space_dimension[1]))
 
 
 class BoolParam:
+    """Boolean search dimension with its current value."""
     def __init__(self, val: bool):
         self.val = bool(val)
         self.space_dimension = (0, 1)

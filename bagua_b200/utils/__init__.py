@@ -64,6 +64,7 @@ def get_flattened_tensor(tensors: List[torch.Tensor]) -> Optional[torch.Tensor]:
 
 
 def align_size(size: int, align: int) -> int:
+    """``size`` rounded up to a multiple of ``align``."""
     return int(math.ceil(size / align)) * align
 
 

@@ -159,3 +159,17 @@ def test_native_call_sites_match_the_bindings():
                     problems.append((os.path.relpath(p,REPO), node.lineno, nm, errs[0]))
     assert checked > 60, checked
     assert not problems, "\n".join(str(p) for p in sorted(set(problems)))
+
+
+def test_public_api_is_documented_and_the_index_is_current():
+    """Every public class / function of the package carries a docstring, and docs/api.md is what scripts/gen_api_docs.py
+    generates from them now (regenerate with ``python scripts/gen_api_docs.py > docs/api.md``)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("gen_api_docs", os.path.join(REPO, "scripts", "gen_api_docs.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    _, missing = gen.collect()
+    assert not missing, "public symbols without a docstring: " + ", ".join(missing)
+    with open(os.path.join(REPO, "docs", "api.md")) as f:
+        assert f.read() == gen.render(), "docs/api.md is stale: python scripts/gen_api_docs.py > docs/api.md"
