@@ -453,3 +453,122 @@ def test_fused_algorithm_splits_buckets_by_parameter_group():
     for mine, oracle, names in run_distributed(_fused_two_groups_worker, world=2):
         torch.testing.assert_close(mine, oracle, rtol=1e-5, atol=1e-6)
         assert len(names) >= 2 and any(n.endswith(".g0") for n in names) and any(n.endswith(".g1") for n in names)
+
+
+def _fused_init_operations_worker(rank, world):
+    """``FusedGradientAllReduceAlgorithmImpl.init_operations`` — the code that builds the in-bucket optimizer on a GPU box
+    (weights re-pointed into a symmetric slice, fp32 master shard, op construction, shard bookkeeping) — run on the host with
+    doubles of the peer engine and of the two native op classes: parameters keep their values, the recorded layout addresses
+    the right elements (consolidated ``master`` == the weights), ``state_dict`` / ``load_state_dict`` round-trip."""
+    import bagua_b200 as bagua
+    import bagua_b200.core as core
+    from bagua_b200.parallel.algorithms.gradient_allreduce import FusedGradientAllReduceAlgorithm, make_sharded_fused_adam, make_sharded_fused_sgd
+
+    class Slice:
+        has_multicast = False
+        buf, offset = object(), 0
+
+        def __init__(self, nbytes):
+            self.tensor = torch.zeros(nbytes, dtype=torch.uint8)
+
+        def view(self, dtype, numel):
+            return self.tensor.view(dtype)[:numel]
+
+        def free(self):
+            pass
+
+    class Engine:
+        has_multicast, comm = False, object()
+
+        def alloc(self, nbytes):
+            return Slice(nbytes)
+
+        def launch_cfg(self, variant, nbytes, blocks=0):
+            return ("cfg", variant, blocks)
+
+    class Op:
+        def __init__(self, *args):
+            self.args, self.hyper, self.s = args, None, 0
+
+        def set_hyper(self, *a):
+            self.hyper = a
+
+        def steps(self):
+            return self.s
+
+        def set_steps(self, s):
+            self.s = s
+
+    class SgdOp(Op):
+        pass
+
+    class AdamOp(Op):
+        pass
+
+    class BackendBucket:
+        def __init__(self):
+            self.ops = []
+
+        def append_op(self, op):
+            self.ops.append(op)
+
+        def clear_ops(self):
+            self.ops = []
+
+    real_native = core.native()
+
+    class FakeC:
+        AllReduceSgdOp, AllReduceAdamOp = SgdOp, AdamOp
+
+        def __getattr__(self, name):
+            return getattr(real_native, name)
+
+    bagua.init_process_group()
+    for make, op_cls, keys in ((lambda ps: make_sharded_fused_sgd(ps, lr=0.1, momentum=0.9), SgdOp, ("master", "momentum_buffer")),
+                               (lambda ps: make_sharded_fused_adam([{"params": [p for p in ps if p.dim() > 1], "weight_decay": 0.1},
+                                                                    {"params": [p for p in ps if p.dim() <= 1], "weight_decay": 0.0}], lr=0.01, adamw=True),
+                                AdamOp, ("master", "exp_avg", "exp_avg_sq"))):
+        torch.manual_seed(5)
+        model = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3), torch.nn.Flatten(), torch.nn.Linear(8 * 36, 5)).to(memory_format=torch.channels_last)
+        want = {n: p.detach().clone() for n, p in model.named_parameters()}
+        opt = make(list(model.parameters()))
+        model = model.with_bagua([opt], FusedGradientAllReduceAlgorithm(opt))
+        impl, ddp = model.bagua_ddp.bagua_algorithm, model.bagua_ddp
+        core_native = core.native
+        core.native = lambda: FakeC()
+        try:
+            for bucket in model.bagua_buckets:
+                nbytes = bucket.backend_tensor.numel() * bucket.backend_tensor.element_size()
+                bucket._engine = lambda group=None: Engine()
+                bucket._slice = Slice(nbytes)
+                bucket.backend_bucket = BackendBucket()
+                impl.init_operations(ddp, bucket)
+                assert isinstance(bucket.backend_bucket.ops[0], op_cls) and bucket.allreduce_variant.endswith("two_shot")
+        finally:
+            core.native = core_native
+        assert len(opt._comm_ops) == len(model.bagua_buckets) == len(opt._shards) and opt.collective_state_dict
+        assert all(op.hyper is not None for op in opt._comm_ops)
+        if op_cls is AdamOp:   # every bucket op follows the weight decay of ITS parameter group
+            decays = {opt._comm_groups[i]: op.hyper[4] for i, op in enumerate(opt._comm_ops)}
+            assert decays == {0: 0.1, 1: 0.0}, decays
+        for n, p in model.named_parameters():   # weights now live in the "symmetric" slices, values and memory format unchanged
+            assert torch.equal(p.detach(), want[n]) and p.stride() == want[n].stride()
+        opt._gather = lambda t, group: [t]      # world size 1: the all-gather is the identity
+        sd = opt.state_dict()
+        assert set(sd["state"]) == set(want)
+        for n in want:
+            torch.testing.assert_close(sd["state"][n]["master"], want[n].contiguous())
+            assert all(sd["state"][n][k].shape == want[n].shape for k in keys)
+        for rec in opt._shards:                  # perturb, restore, compare
+            for t in rec["state"]:
+                t.add_(1.0)
+        opt.load_state_dict(sd)
+        again = opt.state_dict()
+        for n in want:
+            for k in keys:
+                assert torch.equal(again["state"][n][k], sd["state"][n][k])
+    return True
+
+
+def test_fused_init_operations_with_host_doubles():
+    assert all(run_distributed(_fused_init_operations_worker, world=1))
