@@ -572,3 +572,117 @@ def _fused_init_operations_worker(rank, world):
 
 def test_fused_init_operations_with_host_doubles():
     assert all(run_distributed(_fused_init_operations_worker, world=1))
+
+
+def _hier_branch_worker(rank, world):
+    """The multi-node branch of ``append_centralized_synchronous_op`` (NVLink reduce-scatter kernel → rail all-reduce of this
+    rank's slice → NVLink all-gather kernel) with doubles of the intra-node engine and the two native ops that EXECUTE their
+    contract through gloo: 4 ranks posing as 2 nodes × 2 GPUs must end with the global average in every bucket."""
+    import torch.distributed as dist
+
+    import bagua_b200 as bagua
+    import bagua_b200.core as core
+    from bagua_b200.bucket import BaguaBucket
+
+    bagua.init_process_group()
+    pg = bagua.communication._get_default_group()
+    L, nodes = 2, world // 2
+    node, local = rank // L, rank % L
+    intra = [dist.new_group([n * L + i for i in range(L)]) for n in range(nodes)][node]
+    rail = [dist.new_group([n * L + i for n in range(nodes)]) for i in range(L)][local]
+    ran = []
+
+    class Slice:
+        has_multicast, buf, offset = False, object(), 0
+
+    class IntraEngine:
+        has_multicast, comm, rank = False, object(), local
+
+        def launch_cfg(self, variant, nbytes, blocks=0):
+            return None
+
+    flat_holder = {}
+
+    class RS:   # contract of reduce_scatter_kernel: my 1/L slice of the buffer becomes scale × sum over the node
+        def __init__(self, comm, buf, off, nbytes, dtype, scale, use_mc, cfg):
+            self.nbytes, self.scale = nbytes, scale
+
+        def run(self):
+            flat = flat_holder["flat"]
+            tmp = flat.clone()
+            dist.all_reduce(tmp, group=intra)
+            es = flat.element_size()
+            vpr = (self.nbytes // 16 + L - 1) // L
+            lo, hi = local * vpr * 16 // es, min((local + 1) * vpr * 16, self.nbytes) // es
+            flat[lo:hi] = tmp[lo:hi] * self.scale
+            ran.append("rs")
+
+    class AG:   # contract of all_gather_kernel: every rank of the node receives every slice
+        def __init__(self, comm, buf, off, nbytes, dtype, use_mc, cfg):
+            self.nbytes = nbytes
+
+        def run(self):
+            flat = flat_holder["flat"]
+            es = flat.element_size()
+            vpr = (self.nbytes // 16 + L - 1) // L
+            for src in range(L):
+                lo, hi = src * vpr * 16 // es, min((src + 1) * vpr * 16, self.nbytes) // es
+                if hi > lo:
+                    piece = flat[lo:hi].clone()
+                    dist.broadcast(piece, node * L + src, group=intra)
+                    flat[lo:hi] = piece
+            ran.append("ag")
+
+    class BackendBucket:
+        def __init__(self):
+            self.ops = []
+
+        def append_op(self, op):
+            self.ops.append(("native", op))
+
+        def append_python_op(self, fn, label="python"):
+            self.ops.append(("python", fn))
+
+        def clear_ops(self):
+            self.ops = []
+
+    real_native = core.native()
+
+    class FakeC:
+        ReduceScatterOp, AllGatherOp = RS, AG
+
+        def __getattr__(self, name):
+            return getattr(real_native, name)
+
+    torch.manual_seed(rank)
+    ts = [torch.randn(37).ensure_bagua_tensor("a", "hier"), torch.randn(3, 9).ensure_bagua_tensor("b", "hier")]
+    want = torch.cat([t.reshape(-1).clone() for t in ts])
+    dist.all_reduce(want)
+    want /= world
+    bucket = BaguaBucket(ts, "h", flatten=True, alignment=4)
+    flat_holder["flat"] = bucket.backend_tensor
+    bucket._slice = Slice()
+    bucket.backend_bucket = BackendBucket()
+    type(pg).nnodes = property(lambda self: nodes)
+    pg.hier_engine = lambda: (IntraEngine(), rail, L, nodes)
+    bucket._engine = lambda group=None: None
+    core_native, core.native = core.native, (lambda: FakeC())
+    import bagua_b200.bucket as bucket_mod
+
+    bucket_native, bucket_mod.native = bucket_mod.native, (lambda: FakeC())
+    try:
+        bucket.append_centralized_synchronous_op(hierarchical=True, average=True)
+    finally:
+        core.native, bucket_mod.native = core_native, bucket_native
+    kinds = [k for k, _ in bucket.backend_bucket.ops]
+    assert kinds == ["native", "python", "native"] and bucket.allreduce_variant.startswith("hier:"), (kinds, bucket.allreduce_variant)
+    for kind, op in bucket.backend_bucket.ops:
+        op.run() if kind == "native" else op("h")
+    got = torch.cat([t.reshape(-1) for t in ts])
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-6)
+    return ran
+
+
+def test_hierarchical_bucket_program_with_executing_doubles():
+    for ran in run_distributed(_hier_branch_worker, world=4):
+        assert ran == ["rs", "ag"]
