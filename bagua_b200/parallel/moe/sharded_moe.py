@@ -2,7 +2,7 @@
 (reference: bagua/torch_api/model_parallel/moe/sharded_moe.py:1-375).
 
 Semantics kept: fp32 gate, capacity = ceil(tokens/experts·factor) (≥ ``min_capacity`` for top-1), random token selection
-under overflow for top-1, Gumbel-max second expert for top-2, the auxiliary load-balancing loss, ``exp_counts`` on CPU.
+under overflow for top-1, Gumbel-max second expert for top-2, the auxiliary load-balancing loss, ``exp_counts`` (kept on the device unless ``BAGUA_MOE_EXP_COUNTS_ON_CPU=1``).
 
 B200-first formulation: gating produces *indices* — for every token and choice k: expert id, slot in that expert's
 capacity buffer (or dropped) and combine weight — instead of the reference's dense one-hot ``[S, E, C]`` tensors, whose
@@ -13,6 +13,7 @@ symmetric buffer on the peer GPU (``bagua_b200/ops/moe.py``), which *is* the all
 from __future__ import annotations
 
 import math
+import os
 from typing import Any, Optional, Tuple
 
 import torch
@@ -54,7 +55,7 @@ class GateOutput:
         self.weights = weights            # float32 [S, K] (0 for dropped); differentiable w.r.t. the gate
         self.capacity = capacity
         self.num_experts = num_experts
-        self.exp_counts = exp_counts      # CPU int tensor [E]
+        self.exp_counts = exp_counts      # int tensor [E] (device of the logits; CPU on request)
 
     def dense(self) -> Tuple[Tensor, Tensor]:
         """(combine_weights[S,E,C], dispatch_mask[S,E,C]) exactly as the reference returns them."""
@@ -65,6 +66,14 @@ class GateOutput:
             s = torch.nonzero(valid, as_tuple=True)[0]
             cw = cw.index_put((s, self.expert_idx[s, k], self.slot_idx[s, k]), self.weights[s, k], accumulate=True)
         return cw, cw.bool()
+
+
+def _exp_counts(mask1: Tensor) -> Tensor:
+    """Tokens routed to each expert (first choice).  The reference copies this to the CPU in every forward
+    (sharded_moe.py:126,202) — one host synchronisation per MoE layer that drains the launch queue; here it stays where it was
+    computed and is only a CPU tensor on request (``BAGUA_MOE_EXP_COUNTS_ON_CPU=1``, or ``.cpu()`` by whoever logs it)."""
+    counts = torch.sum(mask1, dim=0).detach()
+    return counts.to("cpu") if os.environ.get("BAGUA_MOE_EXP_COUNTS_ON_CPU", "0") == "1" else counts
 
 
 def top1gating_indices(logits: Tensor, capacity_factor: float, min_capacity: int, used_token: Optional[Tensor] = None,
@@ -78,7 +87,7 @@ def top1gating_indices(logits: Tensor, capacity_factor: float, min_capacity: int
     mask1 = F.one_hot(indices1_s, num_classes=E)
     if used_token is not None:
         mask1 = mask1 * used_token.to(mask1.dtype).unsqueeze(1)
-    exp_counts = torch.sum(mask1, dim=0).detach().to("cpu")
+    exp_counts = _exp_counts(mask1)
     me = torch.mean(gates, dim=0)
     ce = torch.mean(mask1.float(), dim=0)
     l_aux = torch.sum(me * ce) * E
@@ -107,7 +116,7 @@ def top2gating_indices(logits: Tensor, capacity_factor: float) -> GateOutput:
     mask2 = F.one_hot(indices2_s, num_classes=E)
     locations1 = torch.cumsum(mask1, dim=0) - 1
     locations2 = torch.cumsum(mask2, dim=0) - 1 + torch.sum(mask1, dim=0, keepdim=True)
-    exp_counts = torch.sum(mask1, dim=0).detach().to("cpu")
+    exp_counts = _exp_counts(mask1)
     me = torch.mean(gates, dim=0)
     ce = torch.mean(mask1.float(), dim=0)
     l_aux = torch.mean(me * ce) * E * E
