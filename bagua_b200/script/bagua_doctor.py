@@ -3,7 +3,8 @@
 Prints the build state of the three native libraries (and whether they are current with the sources), the toolchain and
 library versions, the GPUs / NVLink peer access / symmetric-memory multicast support that the peer kernels depend on, the
 ``BAGUA_*`` environment that deviates from the defaults, and runs a small self-test: the C++ scheduler on the host backend
-always, one fused optimizer step and (with ≥ 2 ranks under a launcher) one all-reduce per kernel variant when GPUs are present.
+always, one fused optimizer kernel when a GPU is present, and — when started under a launcher with several ranks — an
+all-reduce across the job (peer kernels on one NVSwitch node, NCCL / gloo otherwise).
 Exit code 0 = everything that could be checked passed."""
 from __future__ import annotations
 
@@ -129,6 +130,28 @@ def _self_test() -> List[dict]:
         return f"{len(h.devices())} usable interface(s)"
 
     check("NCCL net plugin loads", net_plugin)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:   # started under a launcher: exercise the communication path of this job
+        def collective():
+            import bagua_b200 as bagua
+
+            on_gpu = torch.cuda.is_available() and os.environ.get("BAGUA_FORCE_CPU", "0") != "1"
+            if on_gpu:
+                torch.cuda.set_device(bagua.get_local_rank())
+            if not bagua.is_initialized():
+                bagua.init_process_group()
+            n, r = bagua.get_world_size(), bagua.get_rank()
+            detail = []
+            for numel in (1024, 1 << 20):       # latency-bound (one-shot kernel) and bandwidth-bound message
+                t = torch.full((numel,), float(r + 1), device="cuda" if on_gpu else "cpu")
+                bagua.allreduce_inplace(t, op=bagua.ReduceOp.AVG)
+                assert torch.allclose(t, torch.full_like(t, (n + 1) / 2)), f"all-reduce of {numel} elements is wrong on rank {r}"
+            eng = bagua.communication._get_default_group().peer_engine() if on_gpu else None
+            detail.append(f"{n} ranks, backend {'nccl + peer kernels' if eng is not None else ('nccl' if on_gpu else 'gloo')}")
+            if eng is not None:
+                detail.append(f"NVLS multicast {'available' if eng.has_multicast else 'not available'}")
+            return ", ".join(detail)
+
+        check("all-reduce across the job", collective)
     if torch.cuda.is_available():
         def fused_step():
             from bagua_b200.ops.optim import flat_sgd_

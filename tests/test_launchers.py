@@ -187,3 +187,14 @@ def test_bagua_doctor_reports_and_self_tests():
     assert rep["ok"] and all(t["ok"] for t in rep["self_test"]) and len(rep["self_test"]) >= 2
     assert rep["libraries"]["_C.so (native core, sm_100a kernels)"]["current_with_sources"] is True
     assert rep["environment"]["BAGUA_DEFAULT_BUCKET_SIZE"] == "1048576" and rep["gpus"]["count"] == 0
+
+
+def test_bagua_doctor_under_the_launcher_checks_the_collective_path(tmp_path):
+    from tests.mp_utils import free_port, run_in_session
+
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, NCCL_SOCKET_IFNAME="lo", CUDA_VISIBLE_DEVICES="", BAGUA_FORCE_CPU="1", PYTHONPATH=repo + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = run_in_session([sys.executable, "-m", "bagua_b200.distributed.launch", "--nproc_per_node=2", f"--master_port={free_port()}", "-m",
+                        "bagua_b200.script.bagua_doctor"], 180, env=env, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("[ok] all-reduce across the job: 2 ranks, backend gloo") == 2 and "FAIL" not in r.stdout
