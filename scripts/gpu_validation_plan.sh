@@ -9,7 +9,8 @@ set -uo pipefail
 mkdir -p gpurun_out
 case "${1:-one}" in
 one)
-  timeout 600 python -m pytest tests -m "gpu and not multigpu" -x -q > gpurun_out/pytest_gpu_1.log 2>&1; echo "pytest1 exit=$?" | tee gpurun_out/plan_one.txt
+  timeout 120 python -m bagua_b200.script.bagua_doctor --json > gpurun_out/doctor_1.json 2> gpurun_out/doctor_1.err; echo "doctor exit=$?" | tee gpurun_out/plan_one.txt
+  timeout 600 python -m pytest tests -m "gpu and not multigpu" -x -q > gpurun_out/pytest_gpu_1.log 2>&1; echo "pytest1 exit=$?" | tee -a gpurun_out/plan_one.txt
   timeout 600 bash scripts/ncu_profile.sh; echo "ncu exit=$?" | tee -a gpurun_out/plan_one.txt
   BAGUA_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_zz_new_kernels_gpu.py -x -q > gpurun_out/pytest_new_kernels.log 2>&1; echo "new kernels exit=$?" | tee -a gpurun_out/plan_one.txt
   BAGUA_GEMM_2CTA=1 timeout 200 python benchmarks/gemm_bench.py --out gpurun_out/gemm_bench_2cta.json > gpurun_out/gemm_bench_2cta.log 2>&1; echo "gemm 2cta exit=$?" | tee -a gpurun_out/plan_one.txt
@@ -29,9 +30,11 @@ one)
   echo "bench (cuda graph) exit=$?" | tee -a gpurun_out/plan_one.txt
   ;;
 two)
+  timeout 180 python -m bagua_b200.distributed.launch --nproc_per_node=2 --master_port=29605 -m bagua_b200.script.bagua_doctor > gpurun_out/doctor_2.log 2>&1
+  echo "doctor(2) exit=$?" | tee gpurun_out/plan_two.txt
   # opt-in kernels written without hardware access in round 1: fused GEMM+combine, fused allreduce+Adam, mixed-precision Adam
   BAGUA_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_peer_gpu.py -q -k "fused or abort or sync_batchnorm or peer_allgather or graphed or sharded" > gpurun_out/pytest_experimental_2.log 2>&1
-  echo "experimental exit=$?" | tee gpurun_out/plan_two.txt
+  echo "experimental exit=$?" | tee -a gpurun_out/plan_two.txt
   timeout 400 python -m pytest tests/test_peer_gpu.py -x -q > gpurun_out/pytest_peer_2.log 2>&1; echo "peer exit=$?" | tee -a gpurun_out/plan_two.txt
   # the shipped examples on real GPUs (each asserts its own results)
   for ex in "communication_primitives/main.py" "mnist/main.py --algorithm bytegrad --epochs 1 --steps-per-epoch 20" "moe/mnist_main.py --steps 20" \
