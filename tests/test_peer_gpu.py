@@ -565,7 +565,7 @@ def _sharded_state_worker(rank, world):
         model.load_state_dict(snap_model)
         opt.load_state_dict(snap_opt)
         again = steps(3, 2)
-        torch.testing.assert_close(again, after, rtol=1e-6, atol=1e-7)
+        torch.testing.assert_close(again, after, rtol=1e-5, atol=1e-6)   # in-switch reduction order is not specified for > 2 ranks
         out.append(torch.cat([v["master"].reshape(-1) for _, v in sorted(snap_opt["state"].items())]))
     return torch.cat(out)
 
