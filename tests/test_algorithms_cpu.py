@@ -663,7 +663,7 @@ def _hier_branch_worker(rank, world):
     flat_holder["flat"] = bucket.backend_tensor
     bucket._slice = Slice()
     bucket.backend_bucket = BackendBucket()
-    type(pg).nnodes = property(lambda self: nodes)
+    pg.nnodes = nodes
     pg.hier_engine = lambda: (IntraEngine(), rail, L, nodes)
     bucket._engine = lambda group=None: None
     core_native, core.native = core.native, (lambda: FakeC())
