@@ -51,10 +51,10 @@ setup(
     version="0.1.0",
     description="Blackwell-native distributed training engine with the capabilities of BaguaSys/bagua",
     packages=find_packages(include=["bagua_b200*", "bagua", "bagua.*", "bagua_core*"]),
-    package_data={"bagua_b200": ["_C.so", "libnccl-net-bagua.so", "csrc/*", "csrc/net/*"]},
+    package_data={"bagua_b200": ["_C.so", "_C_torch.so", "libnccl-net-bagua.so", "*.stamp", "csrc/*", "csrc/net/*", "csrc/torch_hooks/*"]},
     python_requires=">=3.10",
     install_requires=["torch>=2.6", "numpy", "pydantic>=2", "scikit-learn", "requests", "pybind11"],
-    extras_require={"ssh": ["fabric", "paramiko"], "redis": ["redis"], "test": ["pytest", "pytest-timeout"]},
+    extras_require={"ssh": ["fabric", "paramiko"], "redis": ["redis"], "test": ["pytest", "pytest-timeout", "hypothesis"]},
     entry_points={
         "console_scripts": [
             "baguarun = bagua_b200.script.baguarun:main",
