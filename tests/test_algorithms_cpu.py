@@ -686,3 +686,19 @@ def _hier_branch_worker(rank, world):
 def test_hierarchical_bucket_program_with_executing_doubles():
     for ran in run_distributed(_hier_branch_worker, world=4):
         assert ran == ["rs", "ag"]
+
+
+def _inline_switch_worker(rank, world):
+    mine, oracle = _grad_allreduce_worker(rank, world)
+    import bagua_b200 as bagua  # noqa: F401
+    from bagua_b200 import communication as comm_mod
+
+    backends = list(comm_mod._backends.values())
+    # gloo bucket programs are python ops: the switch is on, yet everything still goes through the worker thread
+    return mine, oracle, [b.inline_mode() for b in backends], sum(b.inline_total() for b in backends)
+
+
+def test_inline_comm_switch_is_harmless_for_python_bucket_programs():
+    for mine, oracle, modes, inlined in run_distributed(_inline_switch_worker, world=2, extra_env={"BAGUA_INLINE_COMM": "1"}):
+        torch.testing.assert_close(mine, oracle, rtol=1e-5, atol=1e-6)
+        assert modes and all(modes) and inlined == 0
