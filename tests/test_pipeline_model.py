@@ -208,3 +208,96 @@ def test_model_detects_a_wrong_arrival_count():
         except AssertionError:
             failures += 1
     assert failures > 0
+
+
+# ---- symmetric-buffer reuse of the fused fc2+combine path (ops/moe_peer.py: linear_push_gather) ---------------------------------
+class EpochBarrier:
+    """peer_barrier(ctx, epoch) of csrc/peer.cuh: every rank publishes ``epoch`` to all peers and waits until all have."""
+
+    def __init__(self, world):
+        self.seen = [[0] * world for _ in range(world)]   # seen[r][p]: the epoch of rank p as visible on rank r
+
+    def arrive(self, rank, epoch):
+        for r in range(len(self.seen)):
+            self.seen[r][rank] = epoch
+
+    def passed(self, rank, epoch):
+        return all(e >= epoch for e in self.seen[rank])
+
+
+def _moe_rank(rank, world, layers, bar, buf, reading, rng):
+    """Kernel sequence of one rank for ``layers`` MoE layers sharing ONE symmetric buffer: the GEMM epilogue pushes this rank's expert
+    outputs into every peer's buffer (no entry barrier), then the local-layout gather kernel: barrier, read own buffer, barrier."""
+    epoch = 0
+    for layer in range(layers):
+        for dst in rng.sample(range(world), world):            # PEER epilogue: tiles leave in any order
+            assert reading[dst] == 0 or buf[dst][rank] == layer, f"layer {layer} overwrites rank {dst}'s buffer while it still reads layer {buf[dst][rank]}"
+            buf[dst][rank] = layer
+            yield None
+        bar.arrive(rank, epoch + 1)                              # gather kernel, entry barrier: all pushes of this layer have landed
+        while not bar.passed(rank, epoch + 1):
+            yield None
+        reading[rank] += 1
+        for src in range(world):
+            assert buf[rank][src] == layer, f"rank {rank} gathers layer {layer} but the slot of rank {src} holds layer {buf[rank][src]}"
+            yield None
+        reading[rank] -= 1
+        bar.arrive(rank, epoch + 2)                              # exit barrier: nobody may recycle the buffers before every reader is done
+        while not bar.passed(rank, epoch + 2):
+            yield None
+        epoch += 2
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_fused_combine_buffer_reuse_is_race_free(world):
+    for seed in range(60):
+        rng = random.Random(seed)
+        bar, buf, reading = EpochBarrier(world), [[-1] * world for _ in range(world)], [0] * world
+        ranks = [_moe_rank(r, world, 5, bar, buf, reading, rng) for r in range(world)]
+        live = list(ranks)
+        guard = 0
+        while live:
+            a = rng.choice(live)               # arbitrary relative speeds of the ranks
+            try:
+                next(a)
+            except StopIteration:
+                live.remove(a)
+            guard += 1
+            assert guard < 200000, "livelock"
+
+
+def test_the_buffer_model_needs_the_exit_barrier():
+    """Without the second barrier a fast rank's next push lands in a buffer that a slow rank is still gathering from."""
+    def no_exit_barrier(rank, world, layers, bar, buf, reading, rng):
+        epoch = 0
+        for layer in range(layers):
+            for dst in range(world):
+                assert reading[dst] == 0 or buf[dst][rank] == layer
+                buf[dst][rank] = layer
+                yield None
+            bar.arrive(rank, epoch + 1)
+            while not bar.passed(rank, epoch + 1):
+                yield None
+            reading[rank] += 1
+            for src in range(world):
+                assert buf[rank][src] == layer
+                yield None
+            reading[rank] -= 1
+            epoch += 1
+
+    failures = 0
+    for seed in range(40):
+        rng = random.Random(seed)
+        world = 4
+        bar, buf, reading = EpochBarrier(world), [[-1] * world for _ in range(world)], [0] * world
+        live = [no_exit_barrier(r, world, 4, bar, buf, reading, rng) for r in range(world)]
+        try:
+            while live:
+                a = rng.choice(live)
+                try:
+                    next(a)
+                except StopIteration:
+                    live.remove(a)
+        except AssertionError:
+            failures += 1
+    assert failures > 0
