@@ -7,6 +7,11 @@ the batch resident on the device — the reference's own synthetic benchmark sha
 bs 32/GPU, SGD, cross-entropy, fixed random batch); ``e2e`` repeats the measurement through the public API with a
 host→device copy of every step's inputs from pinned memory and a device→host read of the loss.
 
+Opt-in experiments (never part of the default measurement, recorded under ``config.host_opts``): ``--cuda-graph`` replays the
+whole step from a CUDA graph; ``BAGUA_NATIVE_HOOKS`` / ``BAGUA_NATIVE_NHWC`` / ``BAGUA_NHWC_FINALIZE`` / ``BAGUA_INLINE_COMM`` move host
+work into C++.  ``--selftest-cpu`` runs the same code path on the host with a small image for the test-suite; its output is
+marked ``selftest`` and is not a benchmark result.
+
 ``--impl reference`` runs the unmodified reference from ``baseline/_ref`` when it is installed there; it cannot be built
 offline in this image (needs cargo/rustc + setuptools_rust + MPI + a downloaded NCCL), in which case the
 arm reports itself unavailable.
