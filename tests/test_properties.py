@@ -123,3 +123,44 @@ def test_bayesian_optimizer_stays_inside_the_declared_space(seed, rounds):
         assert isinstance(p["i"], int) and 1 <= p["i"] <= 9
         assert 0.25 <= p["f"] <= 4.0 and isinstance(p["b"], bool)
         opt.tell(p, -((p["i"] - 6) ** 2) - (math.log2(p["f"])) ** 2 + (0.5 if p["b"] else 0.0))
+
+
+@settings(max_examples=120, deadline=None, derandomize=True)
+@given(st.lists(st.tuples(st.lists(st.integers(1, 5), min_size=1, max_size=4), st.booleans()), min_size=1, max_size=6), st.integers(1, 8), st.integers(1, 8),
+       st.sampled_from([4, 8]))
+def test_optimizer_shards_consolidate_and_reshard_for_any_world_size(tensors, world_save, world_load, per):
+    """Checkpoint format of the in-bucket optimizers: shards written by ``world_save`` ranks consolidate into per-parameter
+    tensors in logical order (also for channels_last parameters) and re-shard exactly for ``world_load`` ranks."""
+    from bagua_b200.parallel.algorithms.gradient_allreduce import consolidate_shards, shard_of
+    from bagua_b200.tensor import dense_strides
+
+    torch.manual_seed(len(tensors) * 17 + world_save)
+    params, layout, off = {}, [], 0
+    for i, (shape, channels_last) in enumerate(tensors):
+        t = torch.randn(*shape)
+        if channels_last and t.dim() == 4:
+            t = t.contiguous(memory_format=torch.channels_last)
+        params[f"p{i}"] = t
+        layout.append((f"p{i}", off, t.numel(), tuple(t.shape), tuple(dense_strides(t))))
+        off += t.numel()
+    numel = (off + per - 1) // per * per
+    flat = torch.zeros(numel)
+    for name, o, n, shape, strides in layout:
+        flat[o:o + n] = torch.as_strided(params[name], (n,), (1,))       # memory order, as the bucket holds it
+
+    def shards(world):
+        length = ((numel // per + world - 1) // world) * per
+        out = []
+        for r in range(world):
+            lo, hi = r * length, min((r + 1) * length, numel)
+            s = torch.zeros(length)
+            if hi > lo:
+                s[: hi - lo] = flat[lo:hi]
+            out.append((s, lo, max(lo, hi), length))
+        return out
+
+    cons = consolidate_shards([s for s, _, _, _ in shards(world_save)], numel, layout)
+    for name, t in params.items():
+        assert torch.equal(cons[name], t.contiguous()) and cons[name].is_contiguous()
+    for s, lo, hi, length in shards(world_load):
+        assert torch.equal(shard_of(cons, layout, numel, lo, hi, length), s)
