@@ -164,3 +164,33 @@ def test_optimizer_shards_consolidate_and_reshard_for_any_world_size(tensors, wo
         assert torch.equal(cons[name], t.contiguous()) and cons[name].is_contiguous()
     for s, lo, hi, length in shards(world_load):
         assert torch.equal(shard_of(cons, layout, numel, lo, hi, length), s)
+
+
+@settings(max_examples=300, deadline=None, derandomize=True)
+@given(st.integers(1, 1 << 30), st.integers(1, 16), st.integers(12, 24), st.integers(0, 1000))
+def test_net_plugin_chunk_plan_partitions_the_message(size, nstreams, min_chunk_2p, cursor):
+    """csrc/net plan_chunks (both ends of a connection derive it from the message size alone): contiguous cover of [0, size), at
+    most one chunk per stream, cuts on 16-byte boundaries, consecutive streams starting at the rotating cursor, and no more
+    chunks than ``size / min_chunk`` allows."""
+    __import__("os").environ.setdefault("NCCL_SOCKET_IFNAME", "lo")
+    h = _plugin_handle()
+    min_chunk = 1 << min_chunk_2p
+    plan = h.plan_chunks(size, nstreams, min_chunk, cursor)
+    assert 1 <= len(plan) <= nstreams and len(plan) <= max(1, size // min_chunk)
+    pos = 0
+    for i, (off, nbytes, stream) in enumerate(plan):
+        assert off == pos and nbytes > 0 and stream == (cursor + i) % nstreams
+        assert off % 16 == 0
+        pos += nbytes
+    assert pos == size
+
+
+_handle_cache = []
+
+
+def _plugin_handle():
+    if not _handle_cache:
+        from bagua_b200 import net
+
+        _handle_cache.append(net.PluginHandle())
+    return _handle_cache[0]
