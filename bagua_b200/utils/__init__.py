@@ -19,6 +19,7 @@ __all__ = [
     "StatisticalAverage",
     "average_by_removing_extreme_values",
     "align_size",
+    "GraphedTrainStep",
 ]
 
 
@@ -176,3 +177,12 @@ def apply_flattened_call_all(tensors: List[torch.Tensor], call):
         groups.setdefault(t.type(), []).append(t)
     for group in groups.values():
         apply_flattened_call(group, call)
+
+
+def __getattr__(name):  # lazy: utils.graph is only needed by scripts that capture CUDA graphs
+    if name == "GraphedTrainStep":
+        from .graph import GraphedTrainStep
+
+        return GraphedTrainStep
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
+
