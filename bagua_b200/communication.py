@@ -828,7 +828,8 @@ def allreduce(send_tensor, recv_tensor, op: ReduceOp = ReduceOp.SUM, comm: Optio
 
 
 def allreduce_inplace(tensor, op: ReduceOp = ReduceOp.SUM, comm: Optional[Communicator] = None):
-    """In-place all-reduce of ``tensor`` over the communicator (``AVG`` divides by its size); CUDA tensors on one NVSwitch node take the peer kernels (reference communication.py:922-943)."""
+    """In-place all-reduce of ``tensor`` over the communicator (``AVG`` divides by its size); CUDA tensors on one NVSwitch node
+    take the peer kernels (reference communication.py:922-943)."""
     c = _comm(comm)
     _check(c, tensor)
     with _on_comm_stream(c):
@@ -892,7 +893,8 @@ def gather(send_tensor, recv_tensor, dst: int, comm: Optional[Communicator] = No
 
 
 def gather_inplace(tensor, count: int, dst: int, comm: Optional[Communicator] = None):
-    """In-place gather: the first ``count`` elements of ``tensor`` are sent; on ``dst`` ``tensor`` holds all ranks' pieces afterwards (reference communication.py:1049-1081)."""
+    """In-place gather: the first ``count`` elements of ``tensor`` are sent; on ``dst`` ``tensor`` holds all ranks' pieces
+    afterwards (reference communication.py:1049-1081)."""
     c = _comm(comm)
     _check(c, tensor)
     with _on_comm_stream(c):
@@ -908,7 +910,8 @@ def scatter(send_tensor, recv_tensor, src: int, comm: Optional[Communicator] = N
 
 
 def scatter_inplace(tensor, count: int, src: int, comm: Optional[Communicator] = None):
-    """In-place scatter: chunk ``rank`` (``count`` elements) of ``src``'s ``tensor`` lands in the first ``count`` elements of ``tensor`` (reference communication.py:1126-1160)."""
+    """In-place scatter: chunk ``rank`` (``count`` elements) of ``src``'s ``tensor`` lands in the first ``count`` elements of
+    ``tensor`` (reference communication.py:1126-1160)."""
     c = _comm(comm)
     _check(c, tensor)
     with _on_comm_stream(c):
