@@ -334,12 +334,17 @@ class BaguaBucket:
         compression: Optional[str] = None,
         group=None,
         variant: str = "auto",
+        momentum_source=None,
     ) -> "BaguaBucket":
         """Allreduce (optionally MinMaxUInt8-compressed) of the bucket across the group
         (reference bucket.py:167-213; comm ops 1 and 2 of SURVEY §2.5).
 
         ``hierarchical`` is accepted for API parity; inside one NVSwitch domain the flat kernel is already optimal, and
-        across nodes the intra-node / inter-node legs are composed from the group's intra/inter communicators."""
+        across nodes the intra-node / inter-node legs are composed from the group's intra/inter communicators.
+
+        ``momentum_source=(grad_flat, beta1)`` (compressed ops only; QAdam): the bucket holds a first moment and
+        ``m = beta1*m + (1-beta1)*grad_flat`` is applied before the exchange — inside the fused kernel's first pass on NVSwitch
+        (the reference needs a python op on the comm thread for it, algorithms/q_adam.py:193-221)."""
         pg = self._process_group(group)
         eng = self._engine(group)
         n = pg.size()
@@ -353,14 +358,33 @@ class BaguaBucket:
                 self._aux_slices += [inbox, outbox]
                 op = C.ByteGradOp(eng.comm, self.backend_tensor.data_ptr(), total, dtype_code(self.backend_tensor.dtype), inbox.buf, inbox.offset,
                                   outbox.buf, outbox.offset, average, eng.launch_cfg("two_shot", total, 0 if n > 4 else 32))
+                if momentum_source is not None:
+                    gflat, beta1 = momentum_source
+                    assert gflat.dtype == self.backend_tensor.dtype and gflat.numel() == total and gflat.is_contiguous()
+                    op.set_momentum_source(gflat.data_ptr(), float(beta1))
+                    self._ops_keepalive.append(gflat)
                 self.backend_bucket.append_op(op)
                 self._ops_keepalive.append(op)
+                self.allreduce_variant = "bytegrad_fused" + ("+momentum" if momentum_source is not None else "")
                 return self
+            if momentum_source is not None:
+                gflat, beta1 = momentum_source
+
+                def momentum(_name: str):
+                    flat, scatter_back = self._flat_or_gather()
+                    with torch.no_grad():
+                        flat.mul_(beta1).add_(gflat.view(-1)[: flat.numel()], alpha=1 - beta1)
+                    if scatter_back is not None:
+                        scatter_back()
+
+                self.append_python_op(momentum, group=group)
+            self.allreduce_variant = "bytegrad_pipeline"
             self.append_python_op(lambda _name: quant.bytegrad_allreduce_fallback(self, pg, average), group=group)
             return self
-        if n == 1:
+        if n == 1 and eng is None:
             self.allreduce_variant = "none(world=1)"
             return self  # nothing to reduce; the scheduler still orders the bucket (events only)
+        # (n == 1 WITH an engine is the self-peer mode, BAGUA_SELF_PEER=1: the same kernels run with this GPU as the only peer)
         if eng is not None and self._slice is not None and self.backend_tensor.dtype in (torch.float32, torch.float16, torch.bfloat16):
             nbytes = self.backend_tensor.numel() * self.backend_tensor.element_size()
             v = "two_shot" if (scattergather and variant == "auto") else variant
@@ -494,11 +518,17 @@ class BaguaBucket:
     def append_asynchronous_model_average_op(self, peer_selection_mode: str = "all", group=None):
         """Background model averaging step (reference bucket.py:322-352; comm op 5).  Returns the op object with
         ``lock_weight() / unlock_weight() / abort() / reset()``."""
-        from .parallel.async_op import AsyncModelAverageOp
+        from .parallel.async_op import AsyncModelAverageOp, FusedAsyncModelAverageOp
 
         assert peer_selection_mode == "all", "only peer_selection_mode='all' is supported (as in the reference)"
-        op = AsyncModelAverageOp(self, self._process_group(group))
-        self.backend_bucket.append_python_op(op.run, "async_model_average")
+        pg = self._process_group(group)
+        op = FusedAsyncModelAverageOp.create(self, pg)   # one kernel per round over NVSwitch peer memory
+        if op is not None:
+            self.backend_bucket.append_op(op.native_op)
+            self._ops_keepalive.append(op)
+        else:
+            op = AsyncModelAverageOp(self, pg)             # CPU / multi-node: torch.distributed
+            self.backend_bucket.append_python_op(op.run, "async_model_average")
         self._async_op = op
         return op
 

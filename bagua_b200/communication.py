@@ -800,16 +800,21 @@ def reduce_inplace(tensor, dst: int, op: ReduceOp = ReduceOp.SUM, comm: Optional
         c.reduce_inplace(tensor, dst, op)
 
 
-def _peer_allreduce(c: Communicator, tensor: torch.Tensor, op) -> bool:
-    """Route eligible allreduces through the NVSwitch kernels; returns False when NCCL/gloo must do it."""
+def _peer_allreduce_eligible(c: Communicator, tensor: torch.Tensor, op):
     if not _use_cuda() or ReduceOp(int(op)) not in (ReduceOp.SUM, ReduceOp.AVG):
-        return False
+        return None
     if tensor.dtype not in (torch.float32, torch.float16, torch.bfloat16) or not tensor.is_contiguous():
-        return False
+        return None
     owner = c._owner() if c._owner else None
     if owner is None or c.scope != "global":
-        return False
-    eng = owner.peer_engine()
+        return None
+    return owner.peer_engine()
+
+
+def _peer_allreduce(c: Communicator, tensor: torch.Tensor, op) -> bool:
+    """Route eligible allreduces through the NVSwitch kernels; returns False when NCCL/gloo must do it.  Called from the
+    caller's own stream (NOT under ``_on_comm_stream``): the engine orders the kernel after it on its blocking stream."""
+    eng = _peer_allreduce_eligible(c, tensor, op)
     if eng is None:
         return False
     return eng.allreduce_tensor(tensor, average=ReduceOp(int(op)) == ReduceOp.AVG)
@@ -820,11 +825,16 @@ def allreduce(send_tensor, recv_tensor, op: ReduceOp = ReduceOp.SUM, comm: Optio
     c = _comm(comm)
     _check(c, send_tensor, recv_tensor)
     assert send_tensor.numel() == recv_tensor.numel(), "send and recv tensors must have the same size"
+    if _peer_allreduce_eligible(c, recv_tensor, op):
+        # peer kernels: own communicator, own stream, ordered after the caller's stream (PeerEngine.blocking_region)
+        if recv_tensor.data_ptr() != send_tensor.data_ptr():
+            recv_tensor.copy_(send_tensor)
+        if _peer_allreduce(c, recv_tensor, op):
+            return
     with _on_comm_stream(c):
         if recv_tensor.data_ptr() != send_tensor.data_ptr():
             recv_tensor.copy_(send_tensor)
-        if not _peer_allreduce(c, recv_tensor, op):
-            c.allreduce_inplace(recv_tensor, op)
+        c.allreduce_inplace(recv_tensor, op)
 
 
 def allreduce_inplace(tensor, op: ReduceOp = ReduceOp.SUM, comm: Optional[Communicator] = None):
@@ -832,27 +842,28 @@ def allreduce_inplace(tensor, op: ReduceOp = ReduceOp.SUM, comm: Optional[Commun
     take the peer kernels (reference communication.py:922-943)."""
     c = _comm(comm)
     _check(c, tensor)
+    if _peer_allreduce(c, tensor, op):
+        return
     with _on_comm_stream(c):
-        if not _peer_allreduce(c, tensor, op):
-            c.allreduce_inplace(tensor, op)
+        c.allreduce_inplace(tensor, op)
 
 
 def allreduce_coalesced_inplace(tensors: Sequence[torch.Tensor], op: ReduceOp = ReduceOp.SUM, comm: Optional[Communicator] = None):
     """All-reduce a list of tensors as flat messages (one per dtype)."""
     c = _comm(comm)
     _check(c, *tensors)
-    with _on_comm_stream(c):
-        by_dtype: Dict[torch.dtype, List[torch.Tensor]] = {}
-        for t in tensors:
-            by_dtype.setdefault(t.dtype, []).append(t)
-        for group in by_dtype.values():
-            flat = torch.cat([t.reshape(-1) for t in group])
-            if not _peer_allreduce(c, flat, op):
+    by_dtype: Dict[torch.dtype, List[torch.Tensor]] = {}
+    for t in tensors:
+        by_dtype.setdefault(t.dtype, []).append(t)
+    for group in by_dtype.values():
+        flat = torch.cat([t.reshape(-1) for t in group])
+        if not _peer_allreduce(c, flat, op):
+            with _on_comm_stream(c):
                 c.allreduce_inplace(flat, op)
-            off = 0
-            for t in group:
-                t.copy_(flat[off : off + t.numel()].view_as(t))
-                off += t.numel()
+        off = 0
+        for t in group:
+            t.copy_(flat[off : off + t.numel()].view_as(t))
+            off += t.numel()
 
 
 def _peer_engine_for(c: Communicator):
@@ -870,10 +881,11 @@ def allgather(send_tensor, recv_tensor, comm: Optional[Communicator] = None):
     """``recv_tensor`` (``nranks × send_tensor.numel()``) = concatenation of every rank's ``send_tensor`` in rank order (reference communication.py:946-982)."""
     c = _comm(comm)
     _check(c, send_tensor, recv_tensor)
+    eng = _peer_engine_for(c)
+    if eng is not None and eng.allgather_tensor(send_tensor, recv_tensor):
+        return
     with _on_comm_stream(c):
-        eng = _peer_engine_for(c)
-        if eng is None or not eng.allgather_tensor(send_tensor, recv_tensor):
-            c.allgather(send_tensor, recv_tensor)
+        c.allgather(send_tensor, recv_tensor)
 
 
 def allgather_inplace(tensor, comm: Optional[Communicator] = None):
@@ -922,10 +934,11 @@ def reduce_scatter(send_tensor, recv_tensor, op: ReduceOp = ReduceOp.SUM, comm: 
     """Reduce ``send_tensor`` over all ranks and leave chunk ``rank`` of the result in ``recv_tensor`` (reference communication.py:1163-1202)."""
     c = _comm(comm)
     _check(c, send_tensor, recv_tensor)
+    eng = _peer_engine_for(c) if ReduceOp(int(op)) in (ReduceOp.SUM, ReduceOp.AVG) else None
+    if eng is not None and eng.reduce_scatter_tensor(send_tensor, recv_tensor, ReduceOp(int(op)) == ReduceOp.AVG):
+        return
     with _on_comm_stream(c):
-        eng = _peer_engine_for(c) if ReduceOp(int(op)) in (ReduceOp.SUM, ReduceOp.AVG) else None
-        if eng is None or not eng.reduce_scatter_tensor(send_tensor, recv_tensor, ReduceOp(int(op)) == ReduceOp.AVG):
-            c.reduce_scatter(send_tensor, recv_tensor, op)
+        c.reduce_scatter(send_tensor, recv_tensor, op)
 
 
 def reduce_scatter_inplace(tensor, op: ReduceOp = ReduceOp.SUM, comm: Optional[Communicator] = None):

@@ -168,7 +168,7 @@ PYBIND11_MODULE(_C, m) {
 
     py::class_<PeerComm, std::shared_ptr<PeerComm>>(m, "PeerComm")
         .def(py::init<int, int, int, const std::vector<uint64_t>&, double>(), py::arg("rank"), py::arg("world"), py::arg("device"),
-             py::arg("flag_ptrs"), py::arg("timeout_s") = 60.0)
+             py::arg("flag_ptrs"), py::arg("timeout_s") = 300.0)
         .def("rank", &PeerComm::rank)
         .def("nranks", &PeerComm::world)
         .def("device_id", &PeerComm::device)
@@ -176,6 +176,8 @@ PYBIND11_MODULE(_C, m) {
         .def("reset_abort", &PeerComm::reset_abort)
         .def("check_abort", &PeerComm::aborted)
         .def("error_code", &PeerComm::error_code)
+        .def("host_error", &PeerComm::host_error)
+        .def("check_fatal", [](PeerComm& c, const std::string& what) { c.check_fatal(what.c_str()); }, py::arg("what") = "the next collective")
         .def("clear_error", &PeerComm::clear_error)
         .def("set_timeout", &PeerComm::set_timeout)
         .def("barrier", [](PeerComm& c, uint64_t stream) { launch_peer_barrier(c.ctx(), S(stream)); });
@@ -238,7 +240,21 @@ PYBIND11_MODULE(_C, m) {
         .def(py::init<std::shared_ptr<PeerComm>, uint64_t, size_t, int, SymmBuf, size_t, SymmBuf, size_t, bool, LaunchCfg>(), py::arg("comm"),
              py::arg("data_ptr"), py::arg("numel"), py::arg("dtype"), py::arg("inbox"), py::arg("inbox_off"), py::arg("outbox"),
              py::arg("outbox_off"), py::arg("average"), py::arg("cfg"))
+        .def("set_momentum_source", &ByteGradOp::set_momentum_source, py::arg("grad_ptr"), py::arg("beta1"))
         .def_static("box_bytes", &ByteGradOp::box_bytes);
+    py::class_<WeightGate, std::shared_ptr<WeightGate>>(m, "WeightGate")
+        .def(py::init<int>(), py::arg("device"))
+        .def("acquire", [](WeightGate& g, uint64_t stream, double timeout_s) { g.acquire(SH(stream), timeout_s); }, py::arg("stream"), py::arg("timeout_s") = 10.0)
+        .def("release", [](WeightGate& g, uint64_t stream) { g.release(SH(stream)); })
+        .def("state", &WeightGate::state);
+    py::class_<AsyncAverageOp, CommOp, std::shared_ptr<AsyncAverageOp>>(m, "AsyncAverageOp")
+        .def(py::init<std::shared_ptr<PeerComm>, uint64_t, SymmBuf, size_t, SymmBuf, size_t, size_t, int, std::shared_ptr<WeightGate>, double, bool, LaunchCfg>(),
+             py::arg("comm"), py::arg("weights_ptr"), py::arg("snap"), py::arg("snap_off"), py::arg("avg"), py::arg("avg_off"), py::arg("bytes"), py::arg("dtype"),
+             py::arg("gate"), py::arg("gate_timeout_s"), py::arg("use_multimem"), py::arg("cfg"))
+        .def("abort", &AsyncAverageOp::abort)
+        .def("reset", &AsyncAverageOp::reset)
+        .def("status", &AsyncAverageOp::status)
+        .def("rounds", &AsyncAverageOp::rounds);
     py::class_<LowPrecRingOp, CommOp, std::shared_ptr<LowPrecRingOp>>(m, "LowPrecRingOp")
         .def(py::init<std::shared_ptr<PeerComm>, uint64_t, uint64_t, uint64_t, uint64_t, size_t, int, SymmBuf, size_t, LaunchCfg>(),
              py::arg("comm"), py::arg("x_ptr"), py::arg("w_ptr"), py::arg("l_ptr"), py::arg("r_ptr"), py::arg("numel"), py::arg("dtype"),

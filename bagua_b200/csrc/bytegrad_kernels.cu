@@ -8,6 +8,7 @@
 // stored into every rank's outbox (that IS the all-gather), then dequantised into the gradient bucket.
 // Wire format, rounding and the reduce-in-T-then-requantise numerics are those of the reference so results are
 // interchangeable with its python oracle (tests/internal/compressor.py).
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
@@ -122,7 +123,8 @@ __device__ __forceinline__ uint32_t* mm_slot(const ByteGradScratch& s, int parit
 template <typename T, int P>
 __global__ void __launch_bounds__(512) bytegrad_kernel(PeerCtx ctx, T* data, size_t chunk, PeerBuf inbox, size_t inbox_off,
                                                        PeerBuf outbox, size_t outbox_off, ByteGradScratch scratch,
-                                                       unsigned long long seq, unsigned long long gb_base, int average) {
+                                                       unsigned long long seq, unsigned long long gb_base, int average,
+                                                       const T* grad, float beta1) {
     const int parity = static_cast<int>(seq & 1ULL);
     const int nb = gridDim.x;
     const int bpc = nb / P;  // blocks per chunk in the scatter phases (host guarantees nb % P == 0)
@@ -139,13 +141,25 @@ __global__ void __launch_bounds__(512) bytegrad_kernel(PeerCtx ctx, T* data, siz
     }
 
     // ---- A: per-chunk min/max of my data ------------------------------------------------------------------
+    // QAdam's compressed stage communicates the first moment: with `grad` given, the bucket IS the moment and the local update
+    // m = β1·m + (1−β1)·g (reference bagua/torch_api/algorithms/q_adam.py:193-221, a python op on the comm thread there) is
+    // applied in this same pass, rounded through T after each torch-level step (mul_, then add_ with alpha).
     const int cj = blockIdx.x / bpc, sb = blockIdx.x % bpc;
     {
-        const T* src = data + static_cast<size_t>(cj) * chunk;
+        T* src = data + static_cast<size_t>(cj) * chunk;
+        const T* gsrc = grad ? grad + static_cast<size_t>(cj) * chunk : nullptr;
+        const float omb = 1.0f - beta1;
         float mn = INFINITY, mx = -INFINITY;
         for (size_t g = static_cast<size_t>(sb) * blockDim.x + threadIdx.x; g < groups; g += static_cast<size_t>(bpc) * blockDim.x) {
             float f[16];
             load16<T>(src + g * 16, f);
+            if (gsrc) {
+                float gg[16];
+                load16<T>(gsrc + g * 16, gg);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) f[k] = round_through<T>(__fmaf_rn(omb, gg[k], round_through<T>(__fmul_rn(beta1, f[k]))));
+                store16<T>(src + g * 16, f);
+            }
 #pragma unroll
             for (int k = 0; k < 16; ++k) mn = fminf(mn, f[k]), mx = fmaxf(mx, f[k]);
         }
@@ -399,21 +413,60 @@ static void next_launch(const ByteGradScratch& s, int n_barriers, int nblocks, u
     s.host_state[1] += static_cast<unsigned long long>(n_barriers) * nblocks;
 }
 
+// Both kernels below synchronise their own CTAs with a counter barrier, i.e. every CTA of the grid must be resident at the same
+// time. A cooperative launch makes the driver guarantee exactly that (the launch waits until the whole grid fits, or fails if
+// it never can), instead of relying on the SMs happening to be free while cuDNN owns the GPU. BAGUA_COOPERATIVE_LAUNCH=0 → plain.
+static bool use_cooperative() {
+    static const bool on = [] {
+        const char* e = std::getenv("BAGUA_COOPERATIVE_LAUNCH");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+template <typename K>
+static int clamp_grid_to_residency(K kernel, int nblocks, int nthreads, int multiple_of) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nthreads, 0) != cudaSuccess || per_sm < 1 || sms < 1) return nblocks;
+    int cap = per_sm * sms;
+    if (nblocks > cap) nblocks = cap / multiple_of * multiple_of;
+    return nblocks < multiple_of ? multiple_of : nblocks;
+}
+template <typename K>
+static void launch_grid_synced(K kernel, int nblocks, int nthreads, cudaStream_t stream, void** args) {
+    if (use_cooperative()) {
+        cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(nblocks), dim3(nthreads), args, 0, stream);
+        if (e != cudaSuccess) throw std::runtime_error(std::string("bagua: cooperative launch failed: ") + cudaGetErrorString(e));
+    } else {
+        cudaError_t e = cudaLaunchKernel(reinterpret_cast<const void*>(kernel), dim3(nblocks), dim3(nthreads), args, 0, stream);
+        if (e != cudaSuccess) throw std::runtime_error(std::string("bagua: launch failed: ") + cudaGetErrorString(e));
+    }
+}
+
 void launch_bytegrad(const PeerCtx& ctx, void* data, size_t numel, int dtype, const PeerBuf& inbox, size_t inbox_off,
                      const PeerBuf& outbox, size_t outbox_off, const ByteGradScratch& scratch, bool average, int nblocks,
-                     int nthreads, cudaStream_t stream) {
+                     int nthreads, cudaStream_t stream, const void* grad, float beta1) {
     const int P = ctx.world;
     if (numel % (static_cast<size_t>(P) * 32)) throw std::runtime_error("bagua: bytegrad bucket must be a multiple of 32*nranks elements");
     if (nblocks % P || nblocks < P || nblocks > kMaxCommBlocks) throw std::runtime_error("bagua: bytegrad grid must be a multiple of nranks (≤ 256)");
-    const size_t chunk = numel / P;
-    unsigned long long seq, base;
-    next_launch(scratch, 4, nblocks, seq, base);
+    size_t chunk = numel / P;
     dispatch_float(dtype, [&](auto tag) {
         using T = decltype(tag);
         dispatch_world(P, [&](auto pw) {
             constexpr int PP = decltype(pw)::value;
-            bytegrad_kernel<T, PP><<<nblocks, nthreads, 0, stream>>>(ctx, static_cast<T*>(data), chunk, inbox, inbox_off, outbox,
-                                                                   outbox_off, scratch, seq, base, average ? 1 : 0);
+            auto kernel = bytegrad_kernel<T, PP>;
+            const int nb = clamp_grid_to_residency(kernel, nblocks, nthreads, P);
+            unsigned long long seq, base;
+            next_launch(scratch, 4, nb, seq, base);
+            PeerCtx c = ctx;
+            T* d = static_cast<T*>(data);
+            PeerBuf in = inbox, out = outbox;
+            ByteGradScratch sc = scratch;
+            int avg = average ? 1 : 0;
+            const T* g = static_cast<const T*>(grad);
+            void* args[] = {&c, &d, &chunk, &in, &inbox_off, &out, &outbox_off, &sc, &seq, &base, &avg, &g, &beta1};
+            launch_grid_synced(kernel, nb, nthreads, stream, args);
         });
     });
     check("bytegrad");
@@ -424,12 +477,18 @@ void launch_lpdec_ring(const PeerCtx& ctx, void* x, void* w, void* l, void* r, s
                        cudaStream_t stream) {
     if (numel % 32) throw std::runtime_error("bagua: low-precision ring bucket must be a multiple of 32 elements");
     if (nblocks < 1 || nblocks > kMaxCommBlocks) throw std::runtime_error("bagua: bad grid for lpdec ring");
-    unsigned long long seq, base;
-    next_launch(scratch, 2, nblocks, seq, base);
     dispatch_float(dtype, [&](auto tag) {
         using T = decltype(tag);
-        lpdec_ring_kernel<T><<<nblocks, nthreads, 0, stream>>>(ctx, static_cast<T*>(x), static_cast<T*>(w), static_cast<T*>(l),
-                                                               static_cast<T*>(r), numel, box, box_off, scratch, seq, base, left, right);
+        auto kernel = lpdec_ring_kernel<T>;
+        const int nb = clamp_grid_to_residency(kernel, nblocks, nthreads, 1);
+        unsigned long long seq, base;
+        next_launch(scratch, 2, nb, seq, base);
+        PeerCtx c = ctx;
+        T *xx = static_cast<T*>(x), *ww = static_cast<T*>(w), *ll = static_cast<T*>(l), *rr = static_cast<T*>(r);
+        PeerBuf bx = box;
+        ByteGradScratch sc = scratch;
+        void* args[] = {&c, &xx, &ww, &ll, &rr, &numel, &bx, &box_off, &sc, &seq, &base, &left, &right};
+        launch_grid_synced(kernel, nb, nthreads, stream, args);
     });
     check("lpdec_ring");
 }

@@ -33,6 +33,11 @@ enum RedOp : int { SUM = 0, PRODUCT = 1, MIN = 2, MAX = 3, BOR = 7, BAND = 8, BX
 constexpr int kMaxPeers = 8;        // one NVSwitch domain (HGX B200 = 8 GPUs)
 constexpr int kMaxCommBlocks = 256;  // upper bound on CTAs of any peer kernel (flag slots per block)
 constexpr int kFlagStride = kMaxPeers;
+// Behind the barrier flags every signal pad carries a small "vote" area: slot [s] is written by rank s (all of its CTAs write
+// the same word) just before a barrier and read by the owner just after it — an all-to-all of one word riding on the barrier
+// (used by async_average_kernel to agree on abort without a separate collective).
+constexpr int kVoteWordOffset = kMaxCommBlocks * kMaxPeers;  // in uint32 words from the start of the pad
+constexpr int kVoteWords = 64;
 
 // Everything a peer kernel needs to talk to the other GPUs of its group.
 // flags[p] points at rank p's signal pad: uint32 [kMaxCommBlocks][kMaxPeers]; slot [b][s] is written
@@ -42,6 +47,7 @@ struct PeerCtx {
     uint32_t* epochs;        // local, private: uint32 [kMaxCommBlocks] — last epoch used by block b
     volatile int* abort;     // host-mapped flag; non-zero → spinning kernels bail out
     int* error;              // local device int; set to non-zero by a kernel that timed out / aborted
+    volatile int* host_error;  // the same code mirrored into host-mapped memory: the host polls it without synchronising
     unsigned long long timeout_ns;
     int rank;
     int world;

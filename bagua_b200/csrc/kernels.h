@@ -37,7 +37,7 @@ struct AdamParams {
 void launch_allreduce(const PeerCtx& ctx, const PeerBuf& src, const PeerBuf& dst, size_t src_off, size_t dst_off, size_t bytes,
                       int dtype, float scale, int variant, int nblocks, int nthreads, cudaStream_t stream);
 void launch_allreduce_oneshot(const PeerCtx& ctx, const PeerBuf& staging, size_t staging_off, size_t slot_bytes, const void* in, void* out,
-                              size_t bytes, int dtype, float scale, int nblocks, int nthreads, cudaStream_t stream);
+                              size_t bytes, int dtype, float scale, int nblocks, int nthreads, cudaStream_t stream, uint32_t call_parity);
 void launch_allreduce_sgd(const PeerCtx& ctx, const PeerBuf& grads, const PeerBuf& weights, size_t g_off, size_t w_off,
                           size_t bytes, int dtype, float* master, float* momentum, const SgdParams& hp, float scale,
                           bool zero_grads, bool use_multimem, int nblocks, int nthreads, cudaStream_t stream);
@@ -54,6 +54,13 @@ void launch_allreduce_adam(const PeerCtx& ctx, const PeerBuf& grads, const PeerB
 void launch_peer_average(const PeerCtx& ctx, const PeerBuf& weights, size_t off, int peer, void* out, size_t bytes, int dtype,
                          int nblocks, int nthreads, cudaStream_t stream);
 void launch_peer_barrier(const PeerCtx& ctx, cudaStream_t stream);
+// One round of asynchronous model averaging in one launch (vote + snapshot → mean of the snapshots → w += mean − snapshot under the
+// device-side weight gate); `status` (host-mapped) receives 1 = averaged, 0 = some rank voted stop, -1 = barrier failure.
+void launch_async_average(const PeerCtx& ctx, void* w, const PeerBuf& snap, size_t snap_off, const PeerBuf& avg, size_t avg_off, size_t bytes, int dtype,
+                          uint32_t seq, bool go, uint32_t* gate, unsigned long long gate_timeout_ns, int* status, bool use_multimem, int nblocks, int nthreads,
+                          cudaStream_t stream);
+void launch_gate_acquire(uint32_t* gate, unsigned long long timeout_ns, cudaStream_t stream);
+void launch_gate_release(uint32_t* gate, cudaStream_t stream);
 
 // ---- fused NHWC conv-block epilogues (nhwc_fused.cu); tensors are [N,H,W,C] f16/bf16, rows = N*H*W --------------------
 void launch_bias_relu_nhwc_fwd(void* y, const void* bias, size_t rows, int C, int dtype, cudaStream_t stream);
@@ -118,7 +125,7 @@ struct ByteGradScratch {
 // chunks into the bucket. `inbox`/`outbox` are symmetric buffers of P * minmax_uint8_chunk_bytes(chunk) bytes.
 void launch_bytegrad(const PeerCtx& ctx, void* data, size_t numel, int dtype, const PeerBuf& inbox, size_t inbox_off,
                      const PeerBuf& outbox, size_t outbox_off, const ByteGradScratch& scratch, bool average, int nblocks,
-                     int nthreads, cudaStream_t stream);
+                     int nthreads, cudaStream_t stream, const void* grad = nullptr, float beta1 = 0.f);  // grad: QAdam m = β1·m + (1−β1)·g in phase A
 
 // Low-precision decentralized ring step (comm_ops/decentralized_low_precision_synchronous.rs:28-153) in one kernel.
 // x: weights (in/out), w: replica of own weights, l/r: replicas of the left/right neighbours.

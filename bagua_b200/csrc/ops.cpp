@@ -40,11 +40,12 @@ PeerComm::PeerComm(int rank, int world, int device, const std::vector<uint64_t>&
     BAGUA_CUDA_CHECK(cudaMemset(ctx_.epochs, 0, kMaxCommBlocks * sizeof(uint32_t)));
     BAGUA_CUDA_CHECK(cudaMalloc(&ctx_.error, sizeof(int)));
     BAGUA_CUDA_CHECK(cudaMemset(ctx_.error, 0, sizeof(int)));
-    BAGUA_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&abort_host_), sizeof(int), cudaHostAllocMapped));
-    *abort_host_ = 0;
+    BAGUA_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&host_words_), 2 * sizeof(int), cudaHostAllocMapped));
+    host_words_[0] = host_words_[1] = 0;
     int* dev_view = nullptr;
-    BAGUA_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dev_view), abort_host_, 0));
+    BAGUA_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dev_view), host_words_, 0));
     ctx_.abort = dev_view;
+    ctx_.host_error = dev_view + 1;
     ctx_.rank = rank;
     ctx_.world = world;
     set_timeout(timeout_s);
@@ -55,12 +56,20 @@ PeerComm::~PeerComm() {
     // Best effort: the context may already be gone at interpreter shutdown.
     if (ctx_.epochs) cudaFree(ctx_.epochs);
     if (ctx_.error) cudaFree(ctx_.error);
-    if (abort_host_) cudaFreeHost(abort_host_);
+    if (host_words_) cudaFreeHost(host_words_);
 }
 
-void PeerComm::abort() { __atomic_store_n(abort_host_, 1, __ATOMIC_RELEASE); }
-void PeerComm::reset_abort() { __atomic_store_n(abort_host_, 0, __ATOMIC_RELEASE); }
-bool PeerComm::aborted() const { return __atomic_load_n(abort_host_, __ATOMIC_ACQUIRE) != 0; }
+void PeerComm::abort() { __atomic_store_n(host_words_, 1, __ATOMIC_RELEASE); }
+void PeerComm::reset_abort() { __atomic_store_n(host_words_, 0, __ATOMIC_RELEASE); }
+bool PeerComm::aborted() const { return __atomic_load_n(host_words_, __ATOMIC_ACQUIRE) != 0; }
+
+void PeerComm::check_fatal(const char* what) const {
+    const int code = host_error();
+    if (code == 0) return;
+    static const char* names[] = {"", "timed out waiting for another rank", "was aborted", "timed out in its grid barrier", "saw a peer in a different round"};
+    throw std::runtime_error(std::string("bagua: an earlier peer kernel of this communicator ") + (code >= 1 && code <= 4 ? names[code] : "failed") +
+                             " (error " + std::to_string(code) + "); the collective was skipped on this rank, replicas may have diverged — refusing to run " + what);
+}
 void PeerComm::set_timeout(double seconds) { ctx_.timeout_ns = static_cast<unsigned long long>(seconds * 1e9); }
 
 int PeerComm::error_code() {
@@ -72,6 +81,7 @@ int PeerComm::error_code() {
 void PeerComm::clear_error() {
     DeviceGuard g(device_);
     BAGUA_CUDA_CHECK(cudaMemset(ctx_.error, 0, sizeof(int)));
+    __atomic_store_n(host_words_ + 1, 0, __ATOMIC_RELEASE);
 }
 
 SymmBuf::SymmBuf(const std::vector<uint64_t>& ptrs, uint64_t mc, size_t nbytes) : bytes(nbytes) {
@@ -102,16 +112,19 @@ QuantScratch::~QuantScratch() {
 }
 
 void AllReduceOp::run(Bucket&, StreamHandle stream, int) {
+    comm_->check_fatal("allreduce");
     launch_allreduce(comm_->ctx(), src_.buf, dst_.buf, src_off_, dst_off_, bytes_, dtype_, scale_, variant_, cfg_.nblocks, cfg_.nthreads,
                      S(stream));
 }
 
 void AllReduceOneShotOp::run(Bucket&, StreamHandle stream, int) {
+    comm_->check_fatal("allreduce_oneshot");
     launch_allreduce_oneshot(comm_->ctx(), staging_.buf, staging_off_, slot_bytes_, reinterpret_cast<const void*>(in_), reinterpret_cast<void*>(out_),
-                             bytes_, dtype_, scale_, cfg_.nblocks, cfg_.nthreads, S(stream));
+                             bytes_, dtype_, scale_, cfg_.nblocks, cfg_.nthreads, S(stream), comm_->next_oneshot_parity());
 }
 
 void AllReduceSgdOp::run(Bucket&, StreamHandle stream, int) {
+    comm_->check_fatal("allreduce_sgd");
     SgdParams hp;
     float scale;
     {
@@ -126,14 +139,17 @@ void AllReduceSgdOp::run(Bucket&, StreamHandle stream, int) {
 }
 
 void ReduceScatterOp::run(Bucket&, StreamHandle stream, int) {
+    comm_->check_fatal("reduce_scatter");
     launch_reduce_scatter(comm_->ctx(), buf_.buf, off_, bytes_, dtype_, scale_, use_mc_, cfg_.nblocks, cfg_.nthreads, S(stream));
 }
 
 void AllGatherOp::run(Bucket&, StreamHandle stream, int) {
+    comm_->check_fatal("all_gather");
     launch_all_gather(comm_->ctx(), buf_.buf, off_, bytes_, dtype_, use_mc_, cfg_.nblocks, cfg_.nthreads, S(stream));
 }
 
 void AllReduceAdamOp::run(Bucket&, StreamHandle stream, int) {
+    comm_->check_fatal("allreduce_adam");
     AdamParams hp{};
     float scale;
     {
@@ -159,9 +175,10 @@ int PeerAverageOp::shift_one_peer(int rank, int nranks, int64_t step) {
 }
 
 void PeerAverageOp::run(Bucket&, StreamHandle stream, int) {
+    comm_->check_fatal("peer_average");
     const int n = comm_->world();
-    if (n % 2) throw std::runtime_error("bagua: decentralized shift_one needs an even number of ranks, got " + std::to_string(n));
-    const int peer = shift_one_peer(comm_->rank(), n, step_);
+    if (n % 2 && n != 1) throw std::runtime_error("bagua: decentralized shift_one needs an even number of ranks, got " + std::to_string(n));
+    const int peer = n == 1 ? 0 : shift_one_peer(comm_->rank(), n, step_);  // n == 1: self-peer mode, the partner is this GPU
     launch_peer_average(comm_->ctx(), weights_.buf, off_, peer, reinterpret_cast<void*>(out_), bytes_, dtype_, cfg_.nblocks, cfg_.nthreads,
                         S(stream));
     step_++;
@@ -178,8 +195,9 @@ ByteGradOp::ByteGradOp(std::shared_ptr<PeerComm> comm, uint64_t data, size_t num
 }
 
 void ByteGradOp::run(Bucket&, StreamHandle stream, int) {
+    comm_->check_fatal("bytegrad");
     launch_bytegrad(comm_->ctx(), reinterpret_cast<void*>(data_), numel_, dtype_, inbox_.buf, inbox_off_, outbox_.buf, outbox_off_,
-                    scratch_->get(), average_, cfg_.nblocks, cfg_.nthreads, S(stream));
+                    scratch_->get(), average_, cfg_.nblocks, cfg_.nthreads, S(stream), reinterpret_cast<const void*>(grad_), beta1_);
 }
 
 LowPrecRingOp::LowPrecRingOp(std::shared_ptr<PeerComm> comm, uint64_t x, uint64_t w, uint64_t l, uint64_t r, size_t numel, int dtype,
@@ -190,10 +208,55 @@ LowPrecRingOp::LowPrecRingOp(std::shared_ptr<PeerComm> comm, uint64_t x, uint64_
 }
 
 void LowPrecRingOp::run(Bucket&, StreamHandle stream, int) {
+    comm_->check_fatal("lpdec_ring");
     const int n = comm_->world(), r = comm_->rank();
     launch_lpdec_ring(comm_->ctx(), reinterpret_cast<void*>(x_), reinterpret_cast<void*>(w_), reinterpret_cast<void*>(l_),
                       reinterpret_cast<void*>(r_), numel_, dtype_, box_.buf, box_off_, scratch_->get(), (r + n - 1) % n, (r + 1) % n,
                       cfg_.nblocks, cfg_.nthreads, S(stream));
+}
+
+WeightGate::WeightGate(int device) : device_(device) {
+    DeviceGuard g(device);
+    BAGUA_CUDA_CHECK(cudaMalloc(&words_, 8 * sizeof(uint32_t)));
+    BAGUA_CUDA_CHECK(cudaMemset(words_, 0, 8 * sizeof(uint32_t)));
+    BAGUA_CUDA_CHECK(cudaDeviceSynchronize());
+}
+WeightGate::~WeightGate() {
+    if (words_) cudaFree(words_);
+}
+void WeightGate::acquire(StreamHandle stream, double timeout_s) {
+    DeviceGuard g(device_);
+    launch_gate_acquire(words_, static_cast<unsigned long long>(timeout_s * 1e9), S(stream));
+}
+void WeightGate::release(StreamHandle stream) {
+    DeviceGuard g(device_);
+    launch_gate_release(words_, S(stream));
+}
+uint32_t WeightGate::state() {
+    DeviceGuard g(device_);
+    uint32_t v = 0;
+    BAGUA_CUDA_CHECK(cudaMemcpy(&v, words_, sizeof(v), cudaMemcpyDeviceToHost));
+    return v;
+}
+
+AsyncAverageOp::AsyncAverageOp(std::shared_ptr<PeerComm> comm, uint64_t weights, SymmBuf snap, size_t snap_off, SymmBuf avg, size_t avg_off, size_t bytes,
+                               int dtype, std::shared_ptr<WeightGate> gate, double gate_timeout_s, bool use_multimem, LaunchCfg cfg)
+    : comm_(std::move(comm)), w_(weights), snap_(snap), avg_(avg), snap_off_(snap_off), avg_off_(avg_off), bytes_(bytes), dtype_(dtype),
+      gate_(std::move(gate)), gate_timeout_s_(gate_timeout_s), use_mc_(use_multimem), cfg_(cfg) {
+    DeviceGuard g(comm_->device());
+    BAGUA_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&status_host_), sizeof(int), cudaHostAllocMapped));
+    *status_host_ = 1;
+    BAGUA_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&status_dev_), status_host_, 0));
+}
+AsyncAverageOp::~AsyncAverageOp() {
+    if (status_host_) cudaFreeHost(status_host_);
+}
+void AsyncAverageOp::run(Bucket&, StreamHandle stream, int) {
+    comm_->check_fatal("async_model_average");
+    launch_async_average(comm_->ctx(), reinterpret_cast<void*>(w_), snap_.buf, snap_off_, avg_.buf, avg_off_, bytes_, dtype_, seq_ & 0x7fffffffu, go_.load(),
+                         gate_ ? gate_->words() : nullptr, static_cast<unsigned long long>(gate_timeout_s_ * 1e9), status_dev_, use_mc_, cfg_.nblocks,
+                         cfg_.nthreads, S(stream));
+    seq_++;
 }
 
 void CopyOp::run(Bucket&, StreamHandle stream, int device) {

@@ -4,6 +4,7 @@
 // (comm_ops/*.rs). Here a "communicator" is nothing but symmetric signal pads + an abort/timeout flag: the
 // collectives themselves are kernels (peer_kernels.cu, bytegrad_kernels.cu) that load/store peer memory.
 #pragma once
+#include <atomic>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -27,15 +28,22 @@ public:
     void abort();            // make every spinning kernel of this comm give up (ncclCommAbort analogue)
     void reset_abort();
     bool aborted() const;
-    int error_code();        // synchronising read of the device error word (0 ok, 1 timeout, 2 aborted, 3 grid timeout)
+    int error_code();        // synchronising read of the device error word (0 ok, 1 timeout, 2 aborted, 3 grid timeout, 4 protocol)
+    // Non-synchronising read of the host-mapped mirror of the error word: what a failed kernel left behind (0 = healthy).
+    int host_error() const { return __atomic_load_n(host_words_ + 1, __ATOMIC_ACQUIRE); }
+    // Throws when a kernel of this communicator has failed: a collective that was skipped on some rank means diverged replicas,
+    // so the failure is fatal for every later op (the reference's NCCL path blocks and then panics via its watchdog instead).
+    void check_fatal(const char* what) const;
     void clear_error();
     void set_timeout(double seconds);
-    static size_t signal_pad_bytes() { return static_cast<size_t>(kMaxCommBlocks) * kMaxPeers * sizeof(uint32_t); }
+    uint32_t next_oneshot_parity() { return oneshot_calls_++ & 1u; }
+    static size_t signal_pad_bytes() { return (static_cast<size_t>(kMaxCommBlocks) * kMaxPeers + kVoteWords) * sizeof(uint32_t); }
 
 private:
     PeerCtx ctx_{};
     int device_;
-    int* abort_host_ = nullptr;
+    int* host_words_ = nullptr;  // host-mapped: [0] abort flag, [1] error mirror
+    uint32_t oneshot_calls_ = 0;
 };
 
 struct SymmBuf {
@@ -93,6 +101,7 @@ public:
           scale_(scale), cfg_(cfg) {}
     const char* kind() const override { return "allreduce_oneshot"; }
     void run(Bucket&, StreamHandle stream, int device) override;
+    bool step_invariant() const override { return false; }  // the staging half alternates with the communicator's call counter
 
 private:
     std::shared_ptr<PeerComm> comm_;
@@ -238,8 +247,11 @@ class ByteGradOp final : public CommOp {
 public:
     ByteGradOp(std::shared_ptr<PeerComm> comm, uint64_t data, size_t numel, int dtype, SymmBuf inbox, size_t inbox_off, SymmBuf outbox,
                size_t outbox_off, bool average, LaunchCfg cfg);
-    const char* kind() const override { return "bytegrad_fused"; }
+    const char* kind() const override { return grad_ ? "qadam_momentum_bytegrad_fused" : "bytegrad_fused"; }
     void run(Bucket&, StreamHandle stream, int device) override;
+    // QAdam compressed stage: the bucket holds the first moment; `grad` (same layout, same dtype) is folded in as
+    // m = beta1*m + (1-beta1)*grad inside the kernel's first pass (0 switches it off).
+    void set_momentum_source(uint64_t grad, float beta1) { grad_ = grad, beta1_ = beta1; }
     static size_t box_bytes(size_t numel, int nranks) { return static_cast<size_t>(nranks) * minmax_uint8_chunk_bytes(numel / nranks); }
 
 private:
@@ -252,6 +264,8 @@ private:
     bool average_;
     LaunchCfg cfg_;
     std::unique_ptr<QuantScratch> scratch_;
+    uint64_t grad_ = 0;
+    float beta1_ = 0.f;
 };
 
 class LowPrecRingOp final : public CommOp {
@@ -271,6 +285,59 @@ private:
     size_t box_off_;
     LaunchCfg cfg_;
     std::unique_ptr<QuantScratch> scratch_;
+};
+
+// The device-side weight gate of asynchronous model averaging (see async_average_kernel): a few words in device memory that the
+// trainer's stream acquires before a forward pass and releases after the optimizer step, and that the averaging kernel takes for
+// its apply phase. Replaces the reference's host mutex + two host synchronisations per iteration.
+class WeightGate {
+public:
+    explicit WeightGate(int device);
+    ~WeightGate();
+    WeightGate(const WeightGate&) = delete;
+    uint32_t* words() const { return words_; }
+    void acquire(StreamHandle stream, double timeout_s);  // enqueue on the trainer's stream
+    void release(StreamHandle stream);
+    uint32_t state();                                      // synchronising read (tests / diagnostics)
+
+private:
+    uint32_t* words_ = nullptr;
+    int device_;
+};
+
+// One round of asynchronous model averaging = one kernel (comm op 5; reference decentralized_full_precision_asynchronous.rs:97-162).
+class AsyncAverageOp final : public CommOp {
+public:
+    AsyncAverageOp(std::shared_ptr<PeerComm> comm, uint64_t weights, SymmBuf snap, size_t snap_off, SymmBuf avg, size_t avg_off, size_t bytes, int dtype,
+                   std::shared_ptr<WeightGate> gate, double gate_timeout_s, bool use_multimem, LaunchCfg cfg);
+    ~AsyncAverageOp() override;
+    const char* kind() const override { return "async_model_average_fused"; }
+    void run(Bucket&, StreamHandle stream, int device) override;
+    bool step_invariant() const override { return false; }
+    void abort() { go_.store(false); }   // this rank votes "stop" from the next round on
+    void reset() {
+        go_.store(true);
+        *status_host_ = 1;
+    }
+    // Outcome of the last completed round (host-mapped word written by the kernel): 1 averaged, 0 a rank voted stop (all ranks see
+    // the same), -1 failed. Valid once the round's ticket has completed.
+    int status() const { return __atomic_load_n(status_host_, __ATOMIC_ACQUIRE); }
+    uint64_t rounds() const { return seq_; }
+
+private:
+    std::shared_ptr<PeerComm> comm_;
+    uint64_t w_;
+    SymmBuf snap_, avg_;
+    size_t snap_off_, avg_off_, bytes_;
+    int dtype_;
+    std::shared_ptr<WeightGate> gate_;
+    double gate_timeout_s_;
+    bool use_mc_;
+    LaunchCfg cfg_;
+    std::atomic<bool> go_{true};
+    uint32_t seq_ = 0;
+    int* status_host_ = nullptr;
+    int* status_dev_ = nullptr;
 };
 
 // Plain device-to-device copy on the comm stream (snapshots / copy-back).

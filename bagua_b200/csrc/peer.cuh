@@ -154,6 +154,15 @@ struct Vec16<__half> {
     }
 };
 
+// A kernel that gives up (barrier time-out, abort, grid-barrier time-out, protocol violation) leaves a non-zero code in the
+// device error word AND in its host-mapped mirror, which the host checks before every further peer op and in
+// wait_pending_comm_ops: a failed collective is fatal for the job (replicas would silently diverge otherwise).
+__device__ __forceinline__ void raise_error(const PeerCtx& ctx, int code) {
+    atomicExch(ctx.error, code);
+    *ctx.host_error = code;
+    __threadfence_system();
+}
+
 // ---- cross-GPU barrier ----------------------------------------------------------------------------------
 // Every CTA b of every rank owns flag row b. Thread p (< world) publishes `epoch` into rank p's slot
 // [b][my_rank] with a system-scope release and spins with acquire loads on its own slot [b][p].
@@ -175,7 +184,7 @@ __device__ __forceinline__ bool peer_barrier(const PeerCtx& ctx, uint32_t epoch)
                 unsigned long long now = globaltimer_ns();
                 if (t0 == 0) t0 = now;
                 if (*ctx.abort != 0 || now - t0 > ctx.timeout_ns) {
-                    atomicExch(ctx.error, *ctx.abort != 0 ? 2 : 1);
+                    raise_error(ctx, *ctx.abort != 0 ? 2 : 1);
                     s_ok = 0;
                     break;
                 }
@@ -184,6 +193,41 @@ __device__ __forceinline__ bool peer_barrier(const PeerCtx& ctx, uint32_t epoch)
     }
     __syncthreads();
     return s_ok != 0;
+}
+
+// The same barrier carrying one word per rank (an all-to-all of a uint32 riding on the flags): every CTA of rank r deposits
+// `my_word` in slot [r] of every peer's vote area right before the releasing flag store, and after the acquire reads the P
+// words deposited in its own pad into s_votes[0..world). All CTAs of a rank must pass the same word. A rank can only be one
+// launch ahead of a peer's slowest CTA after that CTA has read its votes (stream order + the kernel's closing barrier), so
+// the single vote area needs no double-buffering.
+__device__ __forceinline__ bool peer_barrier_vote(const PeerCtx& ctx, uint32_t epoch, uint32_t my_word, uint32_t* s_votes) {
+    __shared__ int s_ok_v;
+    if (threadIdx.x == 0) s_ok_v = 1;
+    __syncthreads();
+    if (threadIdx.x < ctx.world) {
+        const int p = threadIdx.x;
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(ctx.flags[p] + kVoteWordOffset + ctx.rank), "r"(my_word) : "memory");
+        st_release_sys(ctx.flags[p] + blockIdx.x * kFlagStride + ctx.rank, epoch);
+        const uint32_t* mine = ctx.flags[ctx.rank] + blockIdx.x * kFlagStride + p;
+        unsigned long long t0 = 0;
+        uint32_t spins = 0;
+        bool ok = true;
+        while (static_cast<int32_t>(ld_acquire_sys(mine) - epoch) < 0) {
+            if ((++spins & 0x3ff) == 0) {
+                unsigned long long now = globaltimer_ns();
+                if (t0 == 0) t0 = now;
+                if (*ctx.abort != 0 || now - t0 > ctx.timeout_ns) {
+                    raise_error(ctx, *ctx.abort != 0 ? 2 : 1);
+                    s_ok_v = 0;
+                    ok = false;
+                    break;
+                }
+            }
+        }
+        if (ok) s_votes[p] = ld_relaxed_sys(ctx.flags[ctx.rank] + kVoteWordOffset + p);
+    }
+    __syncthreads();
+    return s_ok_v != 0;
 }
 
 // Epoch bookkeeping: each CTA keeps its own counter so launches with different grid sizes compose.

@@ -205,9 +205,12 @@ __global__ void __launch_bounds__(512) all_gather_kernel(PeerCtx ctx, PeerBuf bu
 template <typename T, int P>
 __global__ void __launch_bounds__(512) allreduce_oneshot_kernel(PeerCtx ctx, PeerBuf staging, size_t staging_off,
                                                                 size_t slot_bytes, const char* in, char* out, size_t total_vecs,
-                                                                float scale) {
+                                                                float scale, uint32_t call_parity) {
     const uint32_t e0 = load_epoch(ctx);
-    const size_t parity = (e0 & 1u);
+    // Which half of the double-buffered staging area: a per-communicator CALL counter kept by the host (every rank issues the same
+    // one-shot calls in the same order). It must not be derived from the per-CTA epochs: launches with different grids (and the
+    // other kernel families, which advance epochs by 1 or 2) would put the CTAs of one rank out of step with each other.
+    const size_t parity = (call_parity & 1u);
     const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
     const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     for (size_t v = tid; v < total_vecs; v += stride) {
@@ -469,6 +472,212 @@ __global__ void __launch_bounds__(512)
     store_epoch(ctx, e0 + 2);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Asynchronous model averaging: ONE launch per round (the reference runs clone + a 1-byte MIN allreduce + host sync +
+// allreduce + apply kernel + two more host syncs, comm_ops/decentralized_full_precision_asynchronous.rs:97-162).
+//
+//   1. vote + snapshot   every CTA deposits "go / stop" in every peer's vote area and copies its columns of the weights
+//                        into the symmetric `snap` buffer; the opening barrier carries the votes: if ANY rank wants to
+//                        stop, every rank skips the round and reports it (that is the abort negotiation — no NCCL, no
+//                        .item()).
+//   2. mean              rank r averages slice r of the P snapshots (peer loads or multimem.ld_reduce) and publishes it
+//                        into every rank's `avg` buffer (peer stores or multimem.st); barrier.
+//   3. apply             w += mean − snapshot, but only while holding the device-side WEIGHT GATE: a word the trainer's
+//                        stream acquires before a forward pass and releases after the optimizer step (gate kernels below).
+//                        So the delta lands between two iterations — never under a forward/backward (what the reference's
+//                        host mutex guarantees) and never interleaved with the optimizer's read-modify-write (which the
+//                        reference does not guarantee) — without any host synchronisation, and a straggling peer only
+//                        delays this background kernel, never the trainer.
+//
+// Column striping: CTA b touches vectors {s·vpr + j : j ≡ (b, thread) mod grid} of every slice s in all three phases, so the
+// per-CTA barriers (CTA b of every rank) are all the synchronisation needed; there is no grid-wide barrier.
+// gate words: [0] state (0 free, 1 trainer, 2 averaging), [1] "averaging is waiting" (fairness), [2] CTAs finished,
+// [3] CTAs past the last cross-rank barrier, [4] decision of the acquiring CTA (1 apply, 2 skip).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <typename T, int P, bool USE_MC>
+__global__ void __launch_bounds__(512)
+    async_average_kernel(PeerCtx ctx, char* w, PeerBuf snap, size_t snap_off, PeerBuf avg, size_t avg_off, size_t total_vecs, uint32_t seq,
+                         int go, uint32_t* gate, unsigned long long gate_timeout_ns, volatile int* status) {
+    __shared__ uint32_t s_votes[kMaxPeers];
+    __shared__ int s_gate;
+    constexpr int N = Vec16<T>::N;
+    const uint32_t e0 = load_epoch(ctx);
+    const size_t vpr = (total_vecs + P - 1) / P;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    char* my_snap = snap.ptr[ctx.rank] + snap_off;
+    // 1: snapshot (weights may be mid-update by the optimizer on another stream: every 16-byte vector is still a value the
+    //    weight had at some instant, which is all the element-wise averaging algebra needs)
+    for (size_t j = tid; j < vpr; j += stride) {
+#pragma unroll
+        for (int s = 0; s < P; ++s) {
+            const size_t v = static_cast<size_t>(s) * vpr + j;
+            if (v < total_vecs) st_stream16(my_snap + v * 16, ld_peer16(w + v * 16));
+        }
+    }
+    bool ok = peer_barrier_vote(ctx, e0 + 1, (seq << 1) | (go ? 1u : 0u), s_votes);
+    bool all_go = true;
+    if (ok) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            if ((s_votes[p] >> 1) != (seq & 0x7fffffffu)) ok = false;  // a peer is in a different round: protocol violation
+            all_go = all_go && (s_votes[p] & 1u);
+        }
+        if (!ok && threadIdx.x == 0) raise_error(ctx, 4);
+    }
+    if (ok && all_go) {
+        // 2: mean of my slice → everybody's avg buffer
+        constexpr int U = USE_MC ? 8 : (P <= 2 ? 8 : (P <= 4 ? 4 : 2));
+        const size_t base = static_cast<size_t>(ctx.rank) * vpr;
+        const size_t limit = (base + vpr < total_vecs ? base + vpr : total_vecs);
+        const float inv = 1.0f / P;
+        for (size_t j0 = base + tid; j0 < limit; j0 += stride * U) {
+            uint4 raw[U][USE_MC ? 1 : P];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const size_t v = j0 + u * stride;
+                if (v < limit) {
+                    if (USE_MC) {
+                        raw[u][0] = multimem_ld_reduce_add<T>(snap.mc + snap_off + v * 16);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < (USE_MC ? 1 : P); ++i) raw[u][i] = ld_peer16(snap.ptr[(ctx.rank + i) % P] + snap_off + v * 16);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const size_t v = j0 + u * stride;
+                if (v >= limit) continue;
+                float acc[N];
+                Vec16<T>::unpack(raw[u][0], acc);
+                if (!USE_MC) {
+#pragma unroll
+                    for (int i = 1; i < (USE_MC ? 1 : P); ++i) {
+                        float f[N];
+                        Vec16<T>::unpack(raw[u][i], f);
+#pragma unroll
+                        for (int k = 0; k < N; ++k) acc[k] += f[k];
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < N; ++k) acc[k] *= inv;
+                const uint4 out = Vec16<T>::pack(acc);
+                if (USE_MC) {
+                    multimem_st16(avg.mc + avg_off + v * 16, out);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < P; ++i) st_peer16(avg.ptr[(ctx.rank + i) % P] + avg_off + v * 16, out);
+                }
+            }
+        }
+        ok = peer_barrier(ctx, e0 + 2);
+        if (ok) {
+            // 3: take the weight gate — by the LAST CTA to get here, i.e. once everything that is left is local work, so the
+            //    trainer (who lets a waiting averaging kernel go first) never waits on another rank. Bounded: if the trainer keeps
+            //    the gate (e.g. an evaluation loop that never steps the optimizer) the whole kernel skips this round's apply.
+            if (threadIdx.x == 0) {
+                int got = 0;
+                if (gate == nullptr) {
+                    got = 1;
+                } else if (atomicAdd(&gate[3], 1u) + 1u == gridDim.x) {
+                    atomicExch(&gate[1], 1u);
+                    const unsigned long long t0 = globaltimer_ns();
+                    uint32_t spins = 0;
+                    for (;;) {
+                        if (atomicCAS(&gate[0], 0u, 2u) == 0u) {
+                            got = 1;
+                            break;
+                        }
+                        if ((++spins & 0xff) == 0 && (*ctx.abort != 0 || globaltimer_ns() - t0 > gate_timeout_ns)) break;
+                        __nanosleep(200);
+                    }
+                    __threadfence();
+                    atomicExch(&gate[4], got ? 1u : 2u);  // decision for the sibling CTAs
+                } else {
+                    const unsigned long long t0 = globaltimer_ns();
+                    uint32_t d = 0, spins = 0;
+                    while ((d = ld_acquire_gpu_u32(&gate[4])) == 0u) {
+                        if ((++spins & 0xff) == 0 && globaltimer_ns() - t0 > 2 * gate_timeout_ns + ctx.timeout_ns) break;
+                        __nanosleep(200);
+                    }
+                    got = d == 1u;
+                }
+                s_gate = got;
+            }
+            __syncthreads();
+            if (s_gate) {
+                const char* my_avg = avg.ptr[ctx.rank] + avg_off;
+                for (size_t j = tid; j < vpr; j += stride) {
+#pragma unroll
+                    for (int s = 0; s < P; ++s) {
+                        const size_t v = static_cast<size_t>(s) * vpr + j;
+                        if (v >= total_vecs) continue;
+                        float a[N], sn[N], cur[N];
+                        Vec16<T>::unpack(ld_peer16(my_avg + v * 16), a);       // written by rank s during this kernel
+                        Vec16<T>::unpack(ld_stream16(my_snap + v * 16), sn);  // written by this very thread in phase 1
+                        Vec16<T>::unpack(ld_peer16(w + v * 16), cur);         // the weights as they are NOW
+#pragma unroll
+                        for (int k = 0; k < N; ++k) cur[k] += a[k] - sn[k];
+                        st_stream16(w + v * 16, Vec16<T>::pack(cur));
+                    }
+                }
+            }
+            if (gate != nullptr) {
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    __threadfence();
+                    if (atomicAdd(&gate[2], 1u) == gridDim.x - 1) {  // last CTA out hands the weights back and re-arms the words
+                        gate[2] = 0u, gate[3] = 0u, gate[4] = 0u;
+                        __threadfence();
+                        atomicCAS(&gate[0], 2u, 0u);
+                        atomicExch(&gate[1], 0u);
+                    }
+                }
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *status = !ok ? -1 : (all_go ? 1 : 0);
+        __threadfence_system();
+    }
+    if (ok) store_epoch(ctx, e0 + 2);
+}
+
+// The trainer's side of the weight gate, enqueued on the compute stream. acquire: let a waiting averaging kernel go first
+// (fairness word), then CAS free→trainer; bounded so that a wedged averaging kernel cannot hang training. release: plain store.
+__global__ void gate_acquire_kernel(uint32_t* gate, unsigned long long timeout_ns) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const unsigned long long t0 = globaltimer_ns();
+    uint32_t spins = 0;
+    while (ld_acquire_gpu_u32(&gate[1]) != 0u && ld_acquire_gpu_u32(&gate[0]) != 1u) {
+        if ((++spins & 0xff) == 0 && globaltimer_ns() - t0 > timeout_ns) break;
+        __nanosleep(100);
+    }
+    for (;;) {
+        const uint32_t prev = atomicCAS(&gate[0], 0u, 1u);
+        if (prev == 0u || prev == 1u) break;
+        if ((++spins & 0xff) == 0 && globaltimer_ns() - t0 > timeout_ns) {
+            atomicExch(&gate[0], 1u);  // give up waiting: training goes on (the averaging kernel sees its CAS fail and skips)
+            break;
+        }
+        __nanosleep(100);
+    }
+    __threadfence();
+}
+__global__ void gate_release_kernel(uint32_t* gate) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    __threadfence();
+    atomicCAS(&gate[0], 1u, 0u);
+}
+
 // A bare cross-GPU barrier (1 CTA) — used for arena hand-over and by tests.
 __global__ void peer_barrier_kernel(PeerCtx ctx) {
     const uint32_t e0 = load_epoch(ctx);
@@ -535,7 +744,7 @@ void launch_allreduce(const PeerCtx& ctx, const PeerBuf& src, const PeerBuf& dst
 }
 
 void launch_allreduce_oneshot(const PeerCtx& ctx, const PeerBuf& staging, size_t staging_off, size_t slot_bytes, const void* in, void* out,
-                              size_t bytes, int dtype, float scale, int nblocks, int nthreads, cudaStream_t stream) {
+                              size_t bytes, int dtype, float scale, int nblocks, int nthreads, cudaStream_t stream, uint32_t call_parity) {
     if (bytes % 16) throw std::runtime_error("bagua: one-shot allreduce needs a 16-byte multiple");
     if (bytes > slot_bytes) throw std::runtime_error("bagua: one-shot allreduce message larger than its staging slot");
     check_blocks(nblocks);
@@ -546,7 +755,7 @@ void launch_allreduce_oneshot(const PeerCtx& ctx, const PeerBuf& staging, size_t
         dispatch_world(ctx.world, [&](auto pw) {
             constexpr int P = decltype(pw)::value;
             allreduce_oneshot_kernel<T, P><<<nblocks, nthreads, 0, stream>>>(
-                ctx, staging, staging_off, slot_bytes, static_cast<const char*>(in), static_cast<char*>(out), vecs, scale);
+                ctx, staging, staging_off, slot_bytes, static_cast<const char*>(in), static_cast<char*>(out), vecs, scale, call_parity);
         });
     });
     check_launch("allreduce_oneshot");
@@ -646,6 +855,38 @@ void launch_peer_average(const PeerCtx& ctx, const PeerBuf& weights, size_t off,
         peer_average_kernel<T><<<nblocks, nthreads, 0, stream>>>(ctx, weights, off, peer, static_cast<char*>(out), vecs);
     });
     check_launch("peer_average");
+}
+
+void launch_async_average(const PeerCtx& ctx, void* w, const PeerBuf& snap, size_t snap_off, const PeerBuf& avg, size_t avg_off, size_t bytes, int dtype,
+                          uint32_t seq, bool go, uint32_t* gate, unsigned long long gate_timeout_ns, int* status, bool use_multimem, int nblocks, int nthreads,
+                          cudaStream_t stream) {
+    if (bytes % 16 || snap_off % 16 || avg_off % 16) throw std::runtime_error("bagua: async_average needs 16-byte aligned size/offsets");
+    check_blocks(nblocks);
+    const size_t vecs = bytes / 16;
+    if (vecs == 0) return;
+    if (use_multimem && (!snap.mc || !avg.mc)) throw std::runtime_error("bagua: multimem async_average requested but no multicast mapping");
+    dispatch_float(dtype, [&](auto tag) {
+        using T = decltype(tag);
+        dispatch_world(ctx.world, [&](auto pw) {
+            constexpr int P = decltype(pw)::value;
+            if (use_multimem)
+                async_average_kernel<T, P, true><<<nblocks, nthreads, 0, stream>>>(ctx, static_cast<char*>(w), snap, snap_off, avg, avg_off, vecs, seq, go ? 1 : 0,
+                                                                                 gate, gate_timeout_ns, status);
+            else
+                async_average_kernel<T, P, false><<<nblocks, nthreads, 0, stream>>>(ctx, static_cast<char*>(w), snap, snap_off, avg, avg_off, vecs, seq, go ? 1 : 0,
+                                                                                  gate, gate_timeout_ns, status);
+        });
+    });
+    check_launch("async_average");
+}
+
+void launch_gate_acquire(uint32_t* gate, unsigned long long timeout_ns, cudaStream_t stream) {
+    gate_acquire_kernel<<<1, 32, 0, stream>>>(gate, timeout_ns);
+    check_launch("gate_acquire");
+}
+void launch_gate_release(uint32_t* gate, cudaStream_t stream) {
+    gate_release_kernel<<<1, 32, 0, stream>>>(gate);
+    check_launch("gate_release");
 }
 
 void launch_peer_barrier(const PeerCtx& ctx, cudaStream_t stream) {

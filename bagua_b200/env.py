@@ -40,7 +40,7 @@ SETTINGS: Dict[str, _Setting] = {s.var: s for s in (
     _Setting("BAGUA_AUTOTUNE_SERVER_WAIT_TIME", int, 300, "seconds to wait for the autotune service to come up"),
     _Setting("BAGUA_REPORT_METRICS", _flag, False, "report training metrics"),
     _Setting("BAGUA_COMM_TIMEOUT_S", float, 300.0, "scheduler watchdog: limit for one bucket's communication"),
-    _Setting("BAGUA_PEER_TIMEOUT_S", float, 60.0, "bound on in-kernel cross-GPU spins"),
+    _Setting("BAGUA_PEER_TIMEOUT_S", float, 300.0, "bound on in-kernel cross-GPU spins (same as the watchdog: a peer kernel that gives up is fatal)"),
     _Setting("BAGUA_ALLREDUCE_VARIANT", str.lower, "auto", "auto | one_shot | two_shot | multimem | nccl"),
 )}
 

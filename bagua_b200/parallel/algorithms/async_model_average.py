@@ -73,10 +73,6 @@ class AsyncModelAverageAlgorithmImpl(AlgorithmImpl):
                     name, bagua_ddp.bagua_module_name, getter_closure=lambda p: p.grad, setter_closure=lambda p, t: setattr(p, "grad", t)
                 )
             else:
-                if param.is_bagua_tensor():
-                    # switching from the warm-up registration (grad) to the weight itself
-                    param._bagua_getter_closure = None
-                    param._bagua_setter_closure = None
                 t = param.ensure_bagua_tensor(name, bagua_ddp.bagua_module_name)
             tensors.append(t)
         self._communication_tensor_names = set(name for name, _ in parameters)
@@ -108,7 +104,7 @@ class AsyncModelAverageAlgorithmImpl(AlgorithmImpl):
         def hook():
             if self.step_id <= self.warmup_steps:
                 bagua_ddp.wait_pending_comm_ops()
-            else:
+            elif not getattr(self, "_release_after_step", False):
                 self._unlock_model(bagua_ddp)
 
         return hook
@@ -126,22 +122,50 @@ class AsyncModelAverageAlgorithmImpl(AlgorithmImpl):
             bucket.append_centralized_synchronous_op(hierarchical=False, average=True, group=self.thread_group)
         else:
             bucket._async_op = bucket.append_asynchronous_model_average_op(peer_selection_mode=self.peer_selection_mode, group=self.thread_group)
+            self._install_step_hooks(bagua_ddp)
 
     def _sync_compute_stream(self):
         if torch.cuda.is_available() and comm_mod._use_cuda():
             torch.cuda.current_stream().synchronize()
 
+    @staticmethod
+    def _gated(bagua_ddp) -> bool:
+        """True when every bucket runs the fused kernel: the weight lock is then a device-side gate (stream-ordered, no host
+        sync); otherwise it is the host mutex of the reference and the compute stream is drained around it."""
+        from ..async_op import FusedAsyncModelAverageOp
+
+        ops = [getattr(b, "_async_op", None) for b in bagua_ddp.bagua_buckets]
+        return bool(ops) and all(isinstance(o, FusedAsyncModelAverageOp) for o in ops)
+
     def _lock_model(self, bagua_ddp):
-        self._sync_compute_stream()
+        if not self._gated(bagua_ddp):
+            self._sync_compute_stream()
         for bucket in bagua_ddp.bagua_buckets:
             if hasattr(bucket, "_async_op"):
                 bucket._async_op.lock_weight()
 
     def _unlock_model(self, bagua_ddp):
-        self._sync_compute_stream()
+        if not self._gated(bagua_ddp):
+            self._sync_compute_stream()
         for bucket in bagua_ddp.bagua_buckets:
             if hasattr(bucket, "_async_op"):
                 bucket._async_op.unlock_weight()
+
+    def _install_step_hooks(self, bagua_ddp):
+        """With the device-side gate the trainer keeps the weights until the optimizer has stepped (so the averaging delta never
+        interleaves with the optimizer's read-modify-write): the release moves from post-backward into a step post-hook of the
+        optimizers handed to ``with_bagua``.  Without optimizers (or on the host-mutex path) the reference's post-backward unlock stays."""
+        self._release_after_step = False
+        if not self._gated(bagua_ddp):
+            return
+        opts = [o for o in getattr(bagua_ddp, "bagua_optimizers", []) if hasattr(o, "register_step_post_hook")]
+        if not opts:
+            return
+        for o in opts:
+            if getattr(o, "_bagua_async_gate_hook", None) is not None:
+                o._bagua_async_gate_hook.remove()
+            o._bagua_async_gate_hook = o.register_step_post_hook(lambda *_a, **_k: self._unlock_model(bagua_ddp))
+        self._release_after_step = True
 
     def _check_op_status(self, bagua_ddp) -> bool:
         b = bagua_ddp.bagua_buckets[0]

@@ -270,12 +270,30 @@ class FusedGradientAllReduceAlgorithmImpl(GradientAllReduceAlgorithmImpl):
             if getattr(opt, "_comm_ops", None):
                 opt._sync_hyper()
 
+        # _reset_buckets builds this hook after the last init_operations: every new shard has consumed the carried-over state
+        # (checkpoint loaded before with_bagua, or the snapshot taken in tensors_to_buckets) — it must not be applied again
+        opt._pending_state = None
         return hook
+
+    def _carry_state_over(self):
+        """Called at the start of every (re-)bucketing — with_bagua, the autotune service moving bucket boundaries every 100 steps,
+        the find_unused_parameters rebuild: snapshot the sharded master weights / moments / step count in their consolidated
+        (world-size and bucketing independent) form and forget the old shards; ``init_operations`` re-shards from the snapshot.
+        Collective (an all-gather per state tensor), like re-bucketing itself."""
+        opt = self.optimizer
+        if getattr(opt, "_shards", None):
+            opt._pending_state = opt.state_dict()
+        opt._comm_ops = []
+        opt._comm_groups = []
+        opt._shards = []
+        opt._covered = set()
+        opt._uncovered_cache = None
 
     def tensors_to_buckets(self, tensors, do_flatten):
         from ...bucket import BaguaBucket
 
         assert do_flatten, "the fused optimizer needs flattened buckets"
+        self._carry_state_over()
         es = tensors[0][0].bagua_getter_closure().element_size()
         # One bucket kernel applies ONE set of hyper-parameters: with several parameter groups (weight decay / no weight decay)
         # every suggested bucket is split so that each piece holds tensors of a single group. The pieces keep their place in
@@ -340,7 +358,11 @@ class FusedGradientAllReduceAlgorithmImpl(GradientAllReduceAlgorithmImpl):
         momentum = torch.zeros(vpr * per, dtype=torch.float32, device=flat.device)
         # NVLS whenever the fabric offers it (the variant validated on 2 and 8 GPUs); peer ld/st two-shot otherwise
         use_mc = bool(wslice.has_multicast and bucket._slice.has_multicast and eng.has_multicast)
-        if os.environ.get("BAGUA_FUSED_MULTIMEM", "auto") == "0":   # experiment switch: peer ld/st flavour of the fused kernel
+        # with 2 ranks the in-switch reduction buys nothing (each GPU pulls half the bucket either way) and the peer ld/st kernel
+        # is the faster one on the plain allreduce (profiles/allreduce_n2.json: two-shot 654 vs multimem 402 GB/s): same policy
+        # as PeerEngine.choose_variant. BAGUA_FUSED_MULTIMEM=0/1 forces either flavour.
+        force = os.environ.get("BAGUA_FUSED_MULTIMEM", "auto")
+        if force == "0" or (force != "1" and n <= 2):
             use_mc = False
         # 16 CTAs: the configuration measured at 56 994 img/s on 8 GPUs (profiles/bench8_fused.json); the kernel also streams
         # the fp32 optimizer shard, so it wants more CTAs than the bare multimem allreduce (8)
@@ -378,14 +400,5 @@ class FusedGradientAllReduceAlgorithm(Algorithm):
         self.average = average
 
     def reify(self, process_group):
-        opt = self.optimizer
-        if getattr(opt, "_shards", None):
-            # the buckets are about to be rebuilt (with_bagua again, new bucketing): carry momentum / moments / master weights
-            # over in their consolidated form; they are re-sharded when the new bucket ops are created
-            opt._pending_state = opt.state_dict()
-        opt._comm_ops = []
-        opt._comm_groups = []
-        opt._shards = []
-        opt._covered = set()
-        opt._uncovered_cache = None
+        # optimizer state is carried across (re-)bucketing by the impl (tensors_to_buckets → _carry_state_over)
         return FusedGradientAllReduceAlgorithmImpl(process_group, self.optimizer, average=self.average)

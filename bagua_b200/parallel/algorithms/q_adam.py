@@ -150,8 +150,29 @@ class QAdamAlgorithmImpl(AlgorithmImpl):
             bucket.append_centralized_synchronous_op(hierarchical=False, average=True, group=self.process_group)
             return
 
+        beta1, _b2 = self.optimizer.param_groups[0]["betas"]
+        flat = bucket.backend_tensor
+        if flat is not None and flat.is_cuda and bucket._engine(self.process_group) is not None:
+            # NVSwitch path: the momentum update m = β1·m + (1−β1)·g runs INSIDE the fused ByteGrad kernel's first pass (the
+            # reference needs a python op on the comm thread here, q_adam.py:193-221). For that the gradients get the same flat
+            # layout as the momentum bucket: every p.grad becomes a view of one mirror buffer (zero_grad keeps the views).
+            from ...tensor import dense_strides
+
+            gflat = torch.zeros_like(flat)
+            base, es = flat.data_ptr(), flat.element_size()
+            with torch.no_grad():
+                for t in bucket.tensors:
+                    m = t.bagua_getter_closure()
+                    view = torch.as_strided(gflat, t.shape, dense_strides(m), (m.data_ptr() - base) // es)
+                    if t.grad is not None:
+                        view.copy_(t.grad)
+                    t.grad = view
+            bucket._qadam_grad_flat = gflat
+            bucket.append_centralized_synchronous_op(hierarchical=self.hierarchical, average=True, scattergather=True, compression="MinMaxUInt8",
+                                                     group=self.process_group, momentum_source=(gflat, beta1))
+            return
+
         def calculate_momentum(*_):
-            beta1, _b2 = self.optimizer.param_groups[0]["betas"]
             moms = [t.bagua_getter_closure() for t in bucket.tensors]
             grads = [t.grad for t in bucket.tensors]
             with torch.no_grad():

@@ -109,3 +109,75 @@ class AsyncModelAverageOp:
                     dist.all_reduce(self.red, group=pg.torch_group)
                 with self.lock:
                     self.flat.add_(self.red / n - self.snap)
+
+
+class FusedAsyncModelAverageOp:
+    """GPU flavour of the op: one ``async_average_kernel`` launch per round (vote + snapshot → mean of the snapshots over peer
+    memory → ``w += mean − snapshot``), issued by the scheduler's worker as a native op — no python on the worker, no NCCL,
+    no ``.item()``, no stream synchronisation.
+
+    The reference's host mutex (held by the trainer from forward-pre to post-backward, with a host sync at both ends,
+    algorithms/async_model_average.py:212-225) becomes a *device-side weight gate* (``csrc``: ``WeightGate``): the trainer's
+    stream acquires it before a forward pass and releases it after the optimizer step; the averaging kernel takes it only for
+    its final, purely local apply phase.  ``lock_weight`` / ``unlock_weight`` keep their names; they enqueue the gate kernels on
+    the caller's current stream and return immediately."""
+
+    def __init__(self, bucket, group, eng, snap_slice, avg_slice):
+        C = native()
+        flat = bucket.backend_tensor
+        self.bucket, self.group, self.flat = bucket, group, flat
+        self.snap, self.red = snap_slice, avg_slice
+        nbytes = flat.numel() * flat.element_size()
+        self.gate = C.WeightGate(flat.device.index)
+        use_mc = bool(eng.has_multicast and snap_slice.has_multicast and avg_slice.has_multicast and eng.world > 2)
+        import os
+
+        self.gate_timeout_s = float(os.environ.get("BAGUA_ASYNC_GATE_TIMEOUT_S", "2.0"))
+        blocks = int(os.environ.get("BAGUA_ASYNC_BLOCKS", "0")) or 16
+        self.native_op = C.AsyncAverageOp(eng.comm, flat.data_ptr(), snap_slice.buf, snap_slice.offset, avg_slice.buf, avg_slice.offset, nbytes,
+                                          dtype_code(flat.dtype), self.gate, self.gate_timeout_s, use_mc, eng.launch_cfg("two_shot", nbytes * 4, blocks))
+        self.variant = "async_fused_" + ("multimem" if use_mc else "peer")
+        self._trainer_holds = False
+        self._stopped = False
+
+    @classmethod
+    def create(cls, bucket, group):
+        flat = bucket.backend_tensor
+        assert flat is not None, "Async algorithm supports `do_flatten=True` only"
+        eng = bucket._engine(group)
+        if eng is None or not flat.is_cuda or flat.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+            return None
+        nbytes = flat.numel() * flat.element_size()
+        if nbytes % 16:
+            return None
+        snap, avg = eng.alloc(nbytes), eng.alloc(nbytes)
+        bucket._companion_slices += [snap, avg]
+        return cls(bucket, group, eng, snap, avg)
+
+    # trainer side (training thread, its current stream) ---------------------------------------------------------------
+    def lock_weight(self):
+        if not self._trainer_holds:
+            self.gate.acquire(torch.cuda.current_stream().cuda_stream, max(self.gate_timeout_s * 5, 10.0))
+            self._trainer_holds = True
+
+    def unlock_weight(self):
+        if self._trainer_holds:
+            self.gate.release(torch.cuda.current_stream().cuda_stream)
+            self._trainer_holds = False
+
+    # control ------------------------------------------------------------------------------------------------------------
+    def abort(self):
+        self.native_op.abort()
+
+    def reset(self):
+        self.native_op.reset()
+        self._stopped = False
+
+    def get_status(self) -> bool:
+        """False once a completed round reported that some rank voted to stop (every rank sees the same round outcome)."""
+        st = self.native_op.status()
+        if st < 0:
+            raise RuntimeError("bagua: asynchronous model averaging failed (peer barrier time-out or protocol violation)")
+        if st == 0:
+            self._stopped = True
+        return not self._stopped

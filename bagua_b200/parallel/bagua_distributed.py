@@ -626,5 +626,12 @@ class BaguaDistributedDataParallel:
         self._bagua_backend.mark_ready_on_stream(tensor._bagua_backend_tensor, self._consumer_stream())
 
     def wait_pending_comm_ops(self) -> int:
-        """Order the current stream after every scheduled bucket (device-side wait on GPU, host wait on CPU)."""
-        return self._bagua_backend.wait_pending_comm_ops(self._consumer_stream(), not self._on_cuda)
+        """Order the current stream after every scheduled bucket (device-side wait on GPU, host wait on CPU).  Also the point where
+        a peer kernel that gave up (barrier time-out / abort) in an earlier iteration becomes a Python exception: its error word is
+        mirrored in host-mapped memory, so the check costs a load, not a synchronisation."""
+        n = self._bagua_backend.wait_pending_comm_ops(self._consumer_stream(), not self._on_cuda)
+        if self._on_cuda:
+            eng = getattr(self.process_group, "_peer_engine", None)
+            if eng is not None:
+                eng.check_error()
+        return n

@@ -36,19 +36,31 @@ def _round_up(x: int, a: int) -> int:
 
 class _Slab:
     def __init__(self, engine: "PeerEngine", nbytes: int):
-        import torch.distributed._symmetric_memory as symm_mem
-
         self.nbytes = nbytes
-        self.tensor = symm_mem.empty(nbytes, dtype=torch.uint8, device=engine.device)
-        self.tensor.zero_()
-        self.handle = symm_mem.rendezvous(self.tensor, engine.torch_pg)
-        ptrs = [int(p) for p in self.handle.buffer_ptrs]
-        mc = 0
-        if engine.use_multicast:
+        ptrs, mc = None, 0
+        if engine.world > 1 or engine.self_peer_symm:
             try:
-                mc = int(self.handle.multicast_ptr or 0)
+                import torch.distributed._symmetric_memory as symm_mem
+
+                self.tensor = symm_mem.empty(nbytes, dtype=torch.uint8, device=engine.device)
+                self.tensor.zero_()
+                self.handle = symm_mem.rendezvous(self.tensor, engine.torch_pg)
+                ptrs = [int(p) for p in self.handle.buffer_ptrs]
+                if engine.use_multicast:
+                    try:
+                        mc = int(self.handle.multicast_ptr or 0)
+                    except Exception:  # noqa: BLE001
+                        mc = 0
             except Exception:  # noqa: BLE001
-                mc = 0
+                if engine.world > 1:
+                    raise
+                engine.self_peer_symm = False  # a 1-rank group that torch's allocator will not rendezvous: plain memory below
+                ptrs = None
+        if ptrs is None:
+            # self-peer mode (world == 1): "every peer" is this GPU, ordinary device memory is symmetric by definition
+            self.tensor = torch.zeros(nbytes, dtype=torch.uint8, device=engine.device)
+            self.handle = None
+            ptrs = [self.tensor.data_ptr()]
         self.ptrs = ptrs
         self.mc = mc
         self.buf = native().SymmBuf(ptrs, mc, nbytes)
@@ -113,7 +125,12 @@ class PeerEngine:
         if env.get_allreduce_variant() == "nccl":
             return None
         n = len(group.ranks)
-        if n < 2 or n > native().MAX_PEERS or group.nnodes != 1:
+        # n == 1: nothing to exchange — but BAGUA_SELF_PEER=1 still builds the engine with this GPU as its only peer, so the very
+        # same kernels / ops / bucket programs run (slices, barriers, optimizer epilogue) on a single-GPU box: used by smoke(),
+        # the 1-GPU tests and `ncu` captures of the peer kernels (ncu cannot wrap a multi-rank job).
+        if n == 1 and os.environ.get("BAGUA_SELF_PEER", "0") != "1":
+            return None
+        if n > native().MAX_PEERS or group.nnodes != 1:
             return None
         if dist.get_rank() not in group.ranks:
             return None
@@ -127,13 +144,23 @@ class PeerEngine:
         self.rank = group.ranks.index(dist.get_rank())
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.use_multicast = os.environ.get("BAGUA_DISABLE_MULTICAST", "0") != "1"
+        self.self_peer_symm = self.world == 1 and os.environ.get("BAGUA_SELF_PEER_SYMM", "1") == "1"  # try torch symm_mem (→ multicast) even alone
         self._slabs: List[_Slab] = []
         # signal pads first: their own tiny symmetric allocation, zeroed before anybody can signal
         pad = self._new_slab(_round_up(C.signal_pad_bytes(), 4096), track=False)
         self._pad_slab = pad
         self.comm = C.PeerComm(self.rank, self.world, self.device.index, pad.ptrs, env.get_peer_kernel_timeout_s())
+        # The blocking API (bagua.allreduce_inplace & co, SyncBatchNorm) is driven by the TRAINING thread while the scheduler's worker
+        # issues bucket kernels: two issue orders that are not the same on every rank. They therefore get their own signal pad
+        # (barriers pair only with their own kind), their own staging / workspace and their own stream (one kind can never queue
+        # behind a spinning kernel of the other kind).
+        pad2 = self._new_slab(_round_up(C.signal_pad_bytes(), 4096), track=False)
+        self._pad_slab2 = pad2
+        self.comm_blocking = C.PeerComm(self.rank, self.world, self.device.index, pad2.ptrs, env.get_peer_kernel_timeout_s())
+        self.blocking_stream = torch.cuda.Stream(device=self.device, priority=-1)
         torch.cuda.synchronize()
-        dist.barrier(group=self.torch_pg)
+        if self.world > 1:
+            dist.barrier(group=self.torch_pg)
         self.has_multicast = pad.mc != 0
         self._staging: Optional[SymmSlice] = None
         self._workspace: Optional[SymmSlice] = None
@@ -246,56 +273,89 @@ class PeerEngine:
                 blocks = max(1, min(32, vecs // (self.world * 2048)))
         return C.LaunchCfg(int(min(blocks, C.MAX_COMM_BLOCKS)), 512)
 
-    def staging(self) -> SymmSlice:
+    def staging(self, blocking: bool = False) -> SymmSlice:
+        """One-shot staging area (double-buffered by call parity); the blocking communicator has its own."""
+        if blocking:
+            if getattr(self, "_staging_blocking", None) is None:
+                self._staging_blocking = self.alloc(2 * self.world * ONE_SHOT_SLOT)
+            return self._staging_blocking
         if self._staging is None:
             self._staging = self.alloc(2 * self.world * ONE_SHOT_SLOT)
         return self._staging
 
     # -- op factories ----------------------------------------------------------------------------------------------
     def make_allreduce_op(self, src: SymmSlice, dst: SymmSlice, nbytes: int, dtype: torch.dtype, average: bool, variant: str = "auto",
-                          src_off: int = 0, dst_off: int = 0, blocks: int = 0):
+                          src_off: int = 0, dst_off: int = 0, blocks: int = 0, comm=None):
         """Native op reducing ``nbytes`` at ``src``(+off) over all ranks into ``dst``(+off) on all ranks."""
         C = native()
+        comm = comm if comm is not None else self.comm
+        blocking = comm is not self.comm
         v = self.choose_variant(nbytes, variant)
         scale = 1.0 / self.world if average else 1.0
         nbytes16 = _round_up(nbytes, 16)
         if v == "one_shot" and nbytes16 <= ONE_SHOT_SLOT:
-            st = self.staging()
-            return C.AllReduceOneShotOp(self.comm, st.buf, st.offset, ONE_SHOT_SLOT, src.tensor.data_ptr() + src_off, dst.tensor.data_ptr() + dst_off,
+            st = self.staging(blocking)
+            return C.AllReduceOneShotOp(comm, st.buf, st.offset, ONE_SHOT_SLOT, src.tensor.data_ptr() + src_off, dst.tensor.data_ptr() + dst_off,
                                         nbytes16, dtype_code(dtype), scale, self.launch_cfg("one_shot", nbytes16, blocks)), "one_shot"
         if v == "one_shot":
             v = "multimem" if self.has_multicast else "two_shot"
         if v == "multimem" and not (src.has_multicast and dst.has_multicast):
             v = "two_shot"
         code = C.AR_MULTIMEM if v == "multimem" else C.AR_TWO_SHOT
-        op = C.AllReduceOp(self.comm, src.buf, dst.buf, src.offset + src_off, dst.offset + dst_off, nbytes16, dtype_code(dtype), scale, code,
+        op = C.AllReduceOp(comm, src.buf, dst.buf, src.offset + src_off, dst.offset + dst_off, nbytes16, dtype_code(dtype), scale, code,
                            self.launch_cfg(v, nbytes16, blocks))
         return op, v
 
     # -- blocking-API fast path --------------------------------------------------------------------------------------
+    class _BlockingRegion:
+        """Work of the blocking API: ordered after the caller's current stream, executed on the engine's own blocking stream with
+        the blocking communicator, and finished (host wait) on exit — never queued behind a bucket kernel of the comm stream."""
+
+        def __init__(self, eng: "PeerEngine"):
+            self.eng = eng
+
+        def __enter__(self):
+            self.eng.comm_blocking.check_fatal("a blocking collective")
+            bs = self.eng.blocking_stream
+            bs.wait_stream(torch.cuda.current_stream())
+            self.ctx = torch.cuda.stream(bs)
+            self.ctx.__enter__()
+            return bs
+
+        def __exit__(self, *exc):
+            self.ctx.__exit__(*exc)
+            self.eng.blocking_stream.synchronize()
+            if exc[0] is None:
+                self.eng.comm_blocking.check_fatal("this blocking collective")
+            return False
+
+    def blocking_region(self):
+        return PeerEngine._BlockingRegion(self)
+
     def allreduce_tensor(self, tensor: torch.Tensor, average: bool) -> bool:
-        """All-reduce an arbitrary contiguous CUDA tensor on the *current* stream through the peer kernels."""
+        """Blocking all-reduce of an arbitrary contiguous CUDA tensor through the peer kernels (see :meth:`blocking_region`)."""
         C = native()
         nbytes = tensor.numel() * tensor.element_size()
         if nbytes == 0:
             return True
-        stream = torch.cuda.current_stream().cuda_stream
         scale = 1.0 / self.world if average else 1.0
-        if nbytes % 16 == 0 and tensor.data_ptr() % 16 == 0 and nbytes <= ONE_SHOT_SLOT:
-            st = self.staging()
-            op = C.AllReduceOneShotOp(self.comm, st.buf, st.offset, ONE_SHOT_SLOT, tensor.data_ptr(), tensor.data_ptr(), nbytes, dtype_code(tensor.dtype),
-                                      scale, self.launch_cfg("one_shot", nbytes))
+        with self.blocking_region() as bs:
+            stream = bs.cuda_stream
+            if nbytes % 16 == 0 and tensor.data_ptr() % 16 == 0 and nbytes <= ONE_SHOT_SLOT:
+                st = self.staging(blocking=True)
+                op = C.AllReduceOneShotOp(self.comm_blocking, st.buf, st.offset, ONE_SHOT_SLOT, tensor.data_ptr(), tensor.data_ptr(), nbytes,
+                                          dtype_code(tensor.dtype), scale, self.launch_cfg("one_shot", nbytes))
+                C.run_op(op, stream, self.device.index)
+                return True
+            padded = _round_up(nbytes, 16 * self.world)
+            ws = self._ensure_workspace(padded)
+            flat = ws.tensor[:nbytes].view(tensor.dtype)
+            flat.copy_(tensor.reshape(-1))
+            if padded > nbytes:
+                ws.tensor[nbytes:padded].zero_()
+            op, _ = self.make_allreduce_op(ws, ws, padded, tensor.dtype, average, "auto", comm=self.comm_blocking)
             C.run_op(op, stream, self.device.index)
-            return True
-        padded = _round_up(nbytes, 16 * self.world)
-        ws = self._ensure_workspace(padded)
-        flat = ws.tensor[:nbytes].view(tensor.dtype)
-        flat.copy_(tensor.reshape(-1))
-        if padded > nbytes:
-            ws.tensor[nbytes:padded].zero_()
-        op, _ = self.make_allreduce_op(ws, ws, padded, tensor.dtype, average, "auto")
-        C.run_op(op, stream, self.device.index)
-        tensor.reshape(-1).copy_(flat)
+            tensor.reshape(-1).copy_(flat)
         return True
 
     def _ensure_workspace(self, nbytes: int) -> "SymmSlice":
@@ -311,12 +371,14 @@ class PeerEngine:
         if sb == 0 or sb % 16 or recv.numel() * recv.element_size() != sb * self.world or not (send.is_contiguous() and recv.is_contiguous()):
             return False
         total = sb * self.world
-        ws = self._ensure_workspace(total)
-        ws.tensor[self.rank * sb: (self.rank + 1) * sb].copy_(send.reshape(-1).view(torch.uint8))
-        use_mc = bool(ws.has_multicast and self.has_multicast)
-        op = C.AllGatherOp(self.comm, ws.buf, ws.offset, total, dtype_code(torch.float32), use_mc, self.launch_cfg("multimem" if use_mc else "two_shot", total))
-        C.run_op(op, torch.cuda.current_stream().cuda_stream, self.device.index)
-        recv.reshape(-1).view(torch.uint8).copy_(ws.tensor[:total])
+        with self.blocking_region() as bs:
+            ws = self._ensure_workspace(total)
+            ws.tensor[self.rank * sb: (self.rank + 1) * sb].copy_(send.reshape(-1).view(torch.uint8))
+            use_mc = bool(ws.has_multicast and self.has_multicast)
+            op = C.AllGatherOp(self.comm_blocking, ws.buf, ws.offset, total, dtype_code(torch.float32), use_mc,
+                               self.launch_cfg("multimem" if use_mc else "two_shot", total))
+            C.run_op(op, bs.cuda_stream, self.device.index)
+            recv.reshape(-1).view(torch.uint8).copy_(ws.tensor[:total])
         return True
 
     def reduce_scatter_tensor(self, send: torch.Tensor, recv: torch.Tensor, average: bool) -> bool:
@@ -328,13 +390,14 @@ class PeerEngine:
                 or send.dtype not in (torch.float32, torch.float16, torch.bfloat16) or not (send.is_contiguous() and recv.is_contiguous())):
             return False
         total = rb * self.world
-        ws = self._ensure_workspace(total)
-        ws.tensor[:total].view(send.dtype).copy_(send.reshape(-1))
-        use_mc = bool(ws.has_multicast and self.has_multicast)
-        op = C.ReduceScatterOp(self.comm, ws.buf, ws.offset, total, dtype_code(send.dtype), (1.0 / self.world) if average else 1.0, use_mc,
-                               self.launch_cfg("multimem" if use_mc else "two_shot", total))
-        C.run_op(op, torch.cuda.current_stream().cuda_stream, self.device.index)
-        recv.reshape(-1).copy_(ws.tensor[self.rank * rb: (self.rank + 1) * rb].view(recv.dtype))
+        with self.blocking_region() as bs:
+            ws = self._ensure_workspace(total)
+            ws.tensor[:total].view(send.dtype).copy_(send.reshape(-1))
+            use_mc = bool(ws.has_multicast and self.has_multicast)
+            op = C.ReduceScatterOp(self.comm_blocking, ws.buf, ws.offset, total, dtype_code(send.dtype), (1.0 / self.world) if average else 1.0, use_mc,
+                                   self.launch_cfg("multimem" if use_mc else "two_shot", total))
+            C.run_op(op, bs.cuda_stream, self.device.index)
+            recv.reshape(-1).copy_(ws.tensor[self.rank * rb: (self.rank + 1) * rb].view(recv.dtype))
         return True
 
     def barrier(self, stream: Optional[torch.cuda.Stream] = None):
@@ -342,6 +405,6 @@ class PeerEngine:
         self.comm.barrier(s)
 
     def check_error(self):
-        code = self.comm.error_code()
-        if code:
-            raise RuntimeError({1: "peer kernel timed out waiting for another rank", 2: "peer kernel aborted", 3: "grid barrier timed out"}.get(code, f"peer kernel error {code}"))
+        """Raise if a kernel of this engine has failed (non-synchronising: reads the host-mapped error mirrors)."""
+        self.comm.check_fatal("further communication")
+        self.comm_blocking.check_fatal("further communication")

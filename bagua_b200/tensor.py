@@ -62,8 +62,11 @@ class BaguaTensor:
                 assert self.bagua_tensor_name == name, "assigning a different name to an existing bagua tensor is forbidden"
             if module_name is not None:
                 self.bagua_module_name = module_name
-            self._bagua_getter_closure = getter_closure if getter_closure is not None else getattr(self, "_bagua_getter_closure", None)
-            self._bagua_setter_closure = setter_closure if setter_closure is not None else getattr(self, "_bagua_setter_closure", None)
+            # re-registration REPLACES the closures, ``None`` meaning "the tensor itself" exactly as on first registration
+            # (reference tensor.py:60-88): a module switched from a gradient algorithm (getter = p.grad) to a weight algorithm
+            # (decentralized, async averaging: no closures) must communicate its weights from then on, not stale gradients
+            self._bagua_getter_closure = getter_closure
+            self._bagua_setter_closure = setter_closure
             self._bagua_refresh_backend_tensor()
             return self
         self.bagua_tensor_name = name if name is not None else ""

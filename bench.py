@@ -1,20 +1,27 @@
 #!/usr/bin/env python
-"""Headline benchmark: VGG16 synthetic-ImageNet training throughput (images/s), GradientAllReduce, bf16.
+"""Headline benchmark (BASELINE.json): VGG16 images/s (GradientAllReduce) AND BERT-large samples/s (ByteGrad), bf16, synthetic
+data of the named shapes, random-init weights, device-timed (CUDA events), max over ranks.
 
-Contract (see the task statement): ``python bench.py --gpus N --steps K --warmup W`` (launched through torchrun for
-N > 1) prints ONE JSON line from rank 0.  ``value`` is device-timed (CUDA events, max over ranks) whole-job images/s with
-the batch resident on the device — the reference's own synthetic benchmark shape (examples/benchmark/synthetic_benchmark.py:
-bs 32/GPU, SGD, cross-entropy, fixed random batch); ``e2e`` repeats the measurement through the public API with a
-host→device copy of every step's inputs from pinned memory and a device→host read of the loss.
+Contract (task statement): ``python bench.py --gpus N --steps K --warmup W`` (launched through torchrun for N > 1) prints ONE
+JSON line from rank 0.  The top-level ``metric`` / ``value`` / ``e2e`` / … describe the VGG16 workload — the reference's own
+synthetic benchmark shape (examples/benchmark/synthetic_benchmark.py: bs 32/GPU, SGD, cross-entropy, fixed random batch) — and
+the ``bert_large_bytegrad`` block carries the same fields for the second half of the metric: BERT-large question answering on
+SQuAD-shaped batches (seq 384, bs 6/GPU as examples/squad/README.md:19-28) with the ByteGrad algorithm and AdamW.
 
-Opt-in experiments (never part of the default measurement, recorded under ``config.host_opts``): ``--cuda-graph`` replays the
-whole step from a CUDA graph; ``BAGUA_NATIVE_HOOKS`` / ``BAGUA_NATIVE_NHWC`` / ``BAGUA_NHWC_FINALIZE`` / ``BAGUA_INLINE_COMM`` move host
-work into C++.  ``--selftest-cpu`` runs the same code path on the host with a small image for the test-suite; its output is
-marked ``selftest`` and is not a benchmark result.
+Arms (``--impl``):
+  ours           the framework as a user gets it: fused NVSwitch bucket kernels, fused optimizers.
+  nccl_baseline  SAME models / optimizers / bucketing / scheduler with ``BAGUA_ALLREDUCE_VARIANT=nccl``: one NCCL all-reduce per
+                 bucket, ByteGrad as the reference's 7-step compress → alltoall → … pipeline on torch.distributed — the re-expression
+                 of the reference's schedule that SURVEY §6 prescribes as the same-box baseline.  Context, never the driver's arm.
+  ddp            stock PyTorch: ``DistributedDataParallel`` + ``torch.optim`` + eager modules (no bagua_b200 kernel). Context.
+  reference      the unmodified reference from ``baseline/_ref``; it cannot be installed offline in this image (Rust core: cargo,
+                 setuptools_rust, mpicxx and a downloaded NCCL are all missing), so the arm reports itself unavailable.
 
-``--impl reference`` runs the unmodified reference from ``baseline/_ref`` when it is installed there; it cannot be built
-offline in this image (needs cargo/rustc + setuptools_rust + MPI + a downloaded NCCL), in which case the
-arm reports itself unavailable.
+Every N runs the SAME program: at N = 1 the engine is built in self-peer mode (``BAGUA_SELF_PEER=1``: this GPU is its own and
+only peer), so the bucket kernels (reduce-scatter → optimizer → all-gather, fused ByteGrad) do at N = 1 exactly the per-GPU work
+they do at N = 8 — the scaling base is not flattered by a cheaper single-GPU code path.
+
+``--selftest-cpu`` runs the same code end to end on the host with tiny shapes for the test-suite (marked ``selftest``).
 """
 from __future__ import annotations
 
@@ -26,28 +33,30 @@ import subprocess
 import sys
 
 REPO = os.path.dirname(os.path.abspath(__file__))
-PUBLISHED_PER_GPU = 126.5  # VGG16 img/s per GPU, Bagua + Bagua-Net, 32x V100 (rust/bagua-net/README.md:52-67)
+# context only: VGG16 fp32, Bagua + Bagua-Net, 32 x V100 over 100 Gb TCP (rust/bagua-net/README.md:52-67); BASELINE.json publishes
+# no number for this hardware / dtype, so `vs_baseline` is null
+PUBLISHED_CONTEXT = {"vgg16_img_s_per_gpu": 126.5, "hardware": "32x V100, fp32, 100 Gb TCP", "source": "rust/bagua-net/README.md:52-67"}
 
 
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=30)
+    p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=5)
-    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--model", default="vgg16", choices=["vgg16", "resnet50"])
-    p.add_argument("--batch-size", type=int, default=32, help="per GPU")
-    p.add_argument("--algorithm", default="gradient_allreduce")
+    p.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl_baseline", "ddp"])
+    p.add_argument("--workloads", default="vgg16,bert", help="comma list out of vgg16, resnet50, bert")
+    p.add_argument("--batch-size", type=int, default=32, help="images per GPU (vgg16 / resnet50)")
+    p.add_argument("--bert-batch-size", type=int, default=6, help="sequences per GPU (reference: examples/squad/README.md)")
+    p.add_argument("--seq-len", type=int, default=384)
     p.add_argument("--momentum", type=float, default=0.0)
     p.add_argument("--no-e2e", action="store_true")
-    p.add_argument("--profile", default="", help="write a torch.profiler kernel table of 3 steps to this file (not a benchmark run)")
+    p.add_argument("--no-verify", action="store_true", help="skip the fused-vs-unfused weight check that precedes the timed region")
+    p.add_argument("--no-self-peer", action="store_true", help="N = 1: plain single-GPU path (flat fused optimizer, no bucket kernels)")
+    p.add_argument("--profile", default="", help="write a torch.profiler kernel table of 3 steps per workload to this file prefix (not a benchmark run)")
     p.add_argument("--fused-shard", dest="fused_shard", action="store_true", default=None,
-                   help="fold the SGD update into the allreduce kernel (sharded optimizer state); default: on for N > 1")
+                   help="fold the SGD update into the allreduce kernel (sharded optimizer state); default: on whenever the group has a peer engine")
     p.add_argument("--no-fused-shard", dest="fused_shard", action="store_false")
-    p.add_argument("--cuda-graph", action="store_true",
-                   help="experimental: replay the whole step, bucket kernels included, from a CUDA graph (bagua_b200.utils.graph.GraphedTrainStep)")
-    # plumbing self-test used by tests/ (no GPU there): the same code path end to end on the host with a small image; its
-    # output is marked "selftest" and is not a benchmark result
+    p.add_argument("--cuda-graph", action="store_true", help="experimental: replay the whole VGG16 step from a CUDA graph (utils.graph.GraphedTrainStep)")
     p.add_argument("--selftest-cpu", action="store_true", help=argparse.SUPPRESS)
     p.add_argument("--image-size", type=int, default=224, help=argparse.SUPPRESS)
     return p.parse_args()
@@ -57,7 +66,8 @@ def reference_arm(args):
     ref = os.path.join(REPO, "baseline", "_ref")
     why = None
     if not os.path.isdir(os.path.join(ref, "bagua")):
-        why = "reference not installed: its Rust core (bagua-core) needs cargo/rustc, setuptools_rust, mpicxx and a downloaded NCCL tarball — none available offline in this image"
+        why = ("reference not installed: `pip install --no-index --no-build-isolation --find-links /opt/wheelhouse --target baseline/_ref /root/reference` fails at "
+               "metadata generation (No module named 'setuptools_rust'); its Rust core also needs cargo/rustc, mpicxx and a downloaded NCCL tarball — none available offline")
     else:
         sys.path.insert(0, ref)
         try:
@@ -72,9 +82,10 @@ def reference_arm(args):
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason sampler running for the duration of the timed region."""
+    """nvidia-smi clock / throttle-reason sampler running for the duration of a timed region."""
 
-    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.proc = None
@@ -87,6 +98,7 @@ class ClockSampler:
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:  # noqa: BLE001
             self.proc = None
+        return self
 
     def stop(self):
         if self.proc is None:
@@ -97,7 +109,7 @@ class ClockSampler:
         except Exception:  # noqa: BLE001
             self.proc.kill()
             out = ""
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.strip().splitlines():
             parts = [x.strip() for x in line.split(",")]
@@ -106,16 +118,364 @@ class ClockSampler:
             try:
                 sm.append(float(parts[0]))
                 mx.append(float(parts[1]))
+                pw.append(float(parts[2]))
             except ValueError:
                 continue
             for n, v in zip(names, parts[3:7]):
                 if v == "Active":
                     reasons.add(n)
-        # keep the samples taken under load (upper half) for the median
         sm_sorted = sorted(sm)
-        under_load = sm_sorted[len(sm_sorted) // 2:] if len(sm_sorted) > 3 else sm_sorted
+        under_load = sm_sorted[len(sm_sorted) // 2:] if len(sm_sorted) > 3 else sm_sorted  # samples taken under load: upper half
         return {"sm_mhz": statistics.median(under_load) if under_load else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class Ctx:
+    """Everything a workload needs from the launch environment."""
+
+
+def make_ctx(args):
+    import torch
+    import torch.distributed as dist
+
+    c = Ctx()
+    c.args = args
+    c.world = int(os.environ.get("WORLD_SIZE", "1"))
+    c.rank = int(os.environ.get("RANK", "0"))
+    c.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    c.cpu = args.selftest_cpu
+    if c.cpu:
+        c.dev, c.dtype = torch.device("cpu"), torch.float32
+    else:
+        torch.cuda.set_device(c.local_rank)
+        c.dev, c.dtype = torch.device("cuda", c.local_rank), torch.bfloat16
+    c.torch, c.dist = torch, dist
+
+    def sync_all():
+        if c.world > 1:
+            dist.barrier()
+        if not c.cpu:
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, whole_loop=False):
+        """Exactly ``steps`` calls (or one ``fn(steps)`` loop) between barrier + synchronize pairs; CUDA events on the launching
+        stream; MAX over ranks."""
+        sync_all()
+        if c.cpu:
+            import time
+
+            t0 = time.perf_counter()
+            fn(steps) if whole_loop else [fn(i) for i in range(steps)]
+            ms = torch.tensor([(time.perf_counter() - t0) * 1e3])
+            if c.world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            return float(ms.item())
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.nvtx.range_push("timed")
+        start.record()
+        if whole_loop:
+            fn(steps)
+        else:
+            for i in range(steps):
+                fn(i)
+        end.record()
+        torch.cuda.nvtx.range_pop()
+        torch.cuda.synchronize()
+        ms = torch.tensor([start.elapsed_time(end)], device=c.dev)
+        if c.world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return float(ms.item())
+
+    c.sync_all, c.timed = sync_all, timed
+    return c
+
+
+def launch_counter(c):
+    if c.args.impl == "ddp":
+        return lambda: 0
+    from bagua_b200.core import native
+
+    return native().launch_count  # every kernel of this library counts itself (csrc/common.h: count_launch)
+
+
+def measure(c, name, train_step, dev_batch, host_batches, to_model_format, per_step_items, unit, finish=None):
+    """Warm-up, device-timed region, e2e region (pinned host batches → prefetcher → step → loss read-back)."""
+    torch = c.torch
+    args = c.args
+    from bagua_b200.utils.data import DevicePrefetcher, LossReader
+
+    sampler = ClockSampler(c.local_rank).start() if (c.rank == 0 and not c.cpu) else None
+    warm = max(args.warmup, 3)
+    loss = None
+    for _ in range(warm):
+        loss = train_step(*dev_batch)
+    if args.profile and not c.cpu:
+        from torch.profiler import ProfilerActivity, profile
+
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for _ in range(3):
+                train_step(*dev_batch)
+            torch.cuda.synchronize()
+        if c.rank == 0:
+            with open(f"{args.profile}.{name}.txt", "w") as f:
+                f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
+    count = launch_counter(c)
+    c.sync_all()
+    n0 = count()
+    holder = {"loss": loss}
+
+    def one(_i):
+        holder["loss"] = train_step(*dev_batch)
+
+    ms = c.timed(one, args.steps)
+    if finish is not None:
+        finish()
+    launches = count() - n0
+    clocks = sampler.stop() if sampler is not None else None
+    loss_val = float(holder["loss"].detach().float().item())     # the loss of the last timed step, read after the timed region
+    if loss_val != loss_val or loss_val in (float("inf"), float("-inf")):
+        raise SystemExit(f"{name}: non-finite loss {loss_val} after the timed region — the number would be a throughput of nothing")
+    value = per_step_items * c.world * args.steps / (ms / 1e3)
+    e2e = None
+    if not args.no_e2e:
+        reader = LossReader(c.dev)
+
+        def loop(steps):
+            for batch in DevicePrefetcher(host_batches(steps), c.dev, to_model_format):
+                reader.push(train_step(*batch))
+            return reader.flush()
+
+        try:
+            loop(3)
+            ms_e2e = c.timed(loop, args.steps, whole_loop=True)
+            if finish is not None:
+                finish()
+            first = next(iter(host_batches(1)))
+            h2d = sum(t.numel() * t.element_size() for t in first)
+            e2e = {"value": per_step_items * c.world * args.steps / (ms_e2e / 1e3), "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                   "ms_per_step": ms_e2e / args.steps, "last_loss": reader.last}
+        except Exception as exc:  # noqa: BLE001 - the device-timed number above must still be reported
+            e2e = {"error": f"{type(exc).__name__}: {exc}"}
+    return {"value": value, "unit": unit, "ms_per_step": ms / args.steps, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "final_loss": loss_val}
+
+
+def verify_fused_update(c, build_model, fused_model, optimizer, batch, loss_fn, lr, steps=2):
+    """Outside every timed region: the update rule of the fused bucket kernels (reduce-scatter → SGD on fp32 master shards →
+    all-gather) against a plain twin — same architecture and initial weights, gradients all-reduced in fp32 by torch.distributed,
+    fp32 master weights updated by hand.  Same RNG seed before each twin's step so dropout masks coincide."""
+    torch, dist = c.torch, c.dist
+    twin = build_model()
+    twin.load_state_dict({k: v.clone() for k, v in fused_model.state_dict().items()})
+    masters = [p.detach().float().clone() for p in twin.parameters()]
+    for s in range(steps):
+        torch.manual_seed(4242 + s)
+        optimizer.zero_grad()
+        loss_fn(fused_model, *batch).backward()
+        optimizer.step()
+        torch.manual_seed(4242 + s)
+        for p in twin.parameters():
+            p.grad = None
+        loss_fn(twin, *batch).backward()
+        with torch.no_grad():
+            for p, m in zip(twin.parameters(), masters):
+                g = p.grad.float()
+                if c.world > 1:
+                    dist.all_reduce(g)
+                    g /= c.world
+                m.add_(g, alpha=-lr)
+                p.copy_(m)
+    if not c.cpu:
+        fused_model.bagua_ddp.wait_pending_comm_ops()
+        torch.cuda.synchronize()
+    worst_ulps, mism, total, worst_abs = 0.0, 0, 0, 0.0
+    eps = 2.0 ** -7 if c.dtype == torch.bfloat16 else 2.0 ** -20
+    for a, b in zip(fused_model.parameters(), twin.parameters()):
+        a32, b32 = a.detach().float(), b.detach().float()
+        d = (a32 - b32).abs()
+        scale = torch.maximum(a32.abs(), b32.abs()).clamp_min(1e-3) * eps
+        worst_ulps = max(worst_ulps, float((d / scale).max().item()))
+        worst_abs = max(worst_abs, float(d.max().item()))
+        mism += int((d > scale).sum().item())
+        total += d.numel()
+    del twin, masters
+    ok = worst_ulps <= 8.0 and mism <= 1e-3 * total
+    out = {"what": f"{steps} steps of the fused bucket kernels vs fp32-allreduce + hand-written SGD on a twin model", "max_diff_in_ulps_of_the_weight_dtype": worst_ulps,
+           "max_abs_diff": worst_abs, "fraction_beyond_1_ulp": mism / max(total, 1), "ok": bool(ok)}
+    if not ok:
+        raise SystemExit(f"fused bucket update disagrees with the unfused oracle: {out}")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------------------------------
+def run_cnn(c, model_name):
+    torch, args = c.torch, c.args
+    import torch.nn.functional as F
+
+    from bagua_b200.models import get_model
+
+    world, dev, dtype, cpu = c.world, c.dev, c.dtype, c.cpu
+    bs, img = args.batch_size, args.image_size
+    lr = 0.01 * world
+    torch.manual_seed(1234)
+
+    def build():
+        m = get_model(model_name)
+        if args.impl == "ddp" and hasattr(m, "fuse_epilogues"):
+            m.fuse_epilogues = False  # stock eager Conv2d → ReLU → MaxPool2d modules on this arm
+        m = m.to(dev).to(dtype)
+        return m.to(memory_format=torch.channels_last) if not cpu else m
+
+    def loss_fn(m, x, y):
+        return F.cross_entropy(m(x).float(), y)
+
+    model = build()
+    verify = None
+    finish = None
+    cfg = {}
+    if args.impl == "ddp":
+        if world > 1:
+            model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[c.local_rank], gradient_as_bucket_view=True)
+        optimizer = torch.optim.SGD(model.parameters(), lr=lr, momentum=args.momentum)
+        cfg["optimizer"] = f"torch.optim.SGD(momentum={args.momentum}) on bf16 parameters"
+        cfg["allreduce_variants"] = ["torch DDP (NCCL)"]
+    else:
+        import bagua_b200 as bagua
+        from bagua_b200.ops.optim import FusedSGD
+        from bagua_b200.parallel.algorithms import Algorithm
+
+        eng = bagua.communication._get_default_group().peer_engine() if not cpu else None
+        fused = args.fused_shard if args.fused_shard is not None else (eng is not None)
+        if fused:
+            from bagua_b200.parallel.algorithms.gradient_allreduce import FusedGradientAllReduceAlgorithm, make_sharded_fused_sgd
+
+            optimizer = make_sharded_fused_sgd(model.parameters(), lr=lr, momentum=args.momentum)
+            algorithm = FusedGradientAllReduceAlgorithm(optimizer)
+            cfg["optimizer"] = "SGD fused into the bucket reduce-scatter→all-gather kernel (fp32 master weights, state sharded N ways)"
+        else:
+            optimizer = FusedSGD(model.parameters(), lr=lr, momentum=args.momentum, master_weights=True, zero_grad_in_step=True)
+            algorithm = Algorithm.init("gradient_allreduce")
+            cfg["optimizer"] = f"FusedSGD(momentum={args.momentum}, fp32 master weights), one flat kernel per step"
+        model = model.with_bagua([optimizer], algorithm)
+        cfg["allreduce_variants"] = sorted({getattr(b, "allreduce_variant", "none") for b in model.bagua_buckets})
+        cfg["buckets"] = len(model.bagua_buckets)
+        finish = model.bagua_ddp.wait_pending_comm_ops
+        if fused and not args.no_verify and model_name == "vgg16" and args.momentum == 0.0:
+            xv = torch.randn(bs, 3, img, img, device=dev).to(dtype)
+            xv = xv.contiguous(memory_format=torch.channels_last) if not cpu else xv
+            yv = torch.randint(0, 1000, (bs,), device=dev)
+            verify = verify_fused_update(c, build, model, optimizer, (xv, yv), loss_fn, lr)
+
+    torch.manual_seed(1234 + c.rank)
+    x_dev = torch.randn(bs, 3, img, img, device=dev).to(dtype)
+    x_dev = x_dev.contiguous(memory_format=torch.channels_last) if not cpu else x_dev
+    y_dev = torch.randint(0, 1000, (bs,), device=dev)
+    n_host = 4
+    pin = (lambda t: t) if cpu else (lambda t: t.pin_memory())
+    x_host = [pin(torch.randn(bs, 3, img, img)) for _ in range(n_host)]
+    y_host = [pin(torch.randint(0, 1000, (bs,))) for _ in range(n_host)]
+
+    def train_step(x, y):
+        optimizer.zero_grad()
+        loss = loss_fn(model, x, y)
+        loss.backward()
+        optimizer.step()
+        return loss
+
+    step_fn = train_step
+    if args.cuda_graph and args.impl == "ours" and not cpu:
+        from bagua_b200.utils.graph import GraphedTrainStep
+
+        step_fn = GraphedTrainStep(model, train_step, (x_dev, y_dev), optimizers=[optimizer])
+        step_fn(x_dev, y_dev)
+
+    def to_model_format(x, y):
+        x = x.to(dtype)
+        return (x.contiguous(memory_format=torch.channels_last) if not cpu else x), y
+
+    def host_batches(n):
+        for i in range(n):
+            yield x_host[i % n_host], y_host[i % n_host]
+
+    res = measure(c, model_name, step_fn, (x_dev, y_dev), host_batches, to_model_format, bs, "images/s", finish)
+    algo = "GradientAllReduce"
+    res["metric"] = f"{model_name} synthetic-ImageNet training throughput ({algo})"
+    res["config"] = dict(cfg, model=model_name, global_batch=bs * world, per_gpu_batch=bs, image=f"3x{img}x{img}", parallelism=f"dp{world}",
+                         algorithm=algo, lr=lr, momentum=args.momentum, cuda_graph=bool(args.cuda_graph),
+                         l2_policy="working set (276 MB bf16 weights + activations) far exceeds the 126 MB L2; no explicit flush")
+    if verify is not None:
+        res["verify"] = verify
+    del model, optimizer
+    return res
+
+
+def run_bert(c):
+    torch, args = c.torch, c.args
+    from bagua_b200 import models
+
+    world, dev, dtype, cpu = c.world, c.dev, c.dtype, c.cpu
+    bs, seq = args.bert_batch_size, args.seq_len
+    cfgm = models.bert_large_config() if not cpu else models.BertConfig(vocab_size=500, hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128)
+    if cpu:
+        seq = min(seq, 32)
+    torch.manual_seed(4321)
+    model = models.BertForQuestionAnswering(cfgm).to(dev).to(dtype)
+    cfg = {}
+    finish = None
+    if args.impl == "ddp":
+        if world > 1:
+            model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[c.local_rank], gradient_as_bucket_view=True)
+        optimizer = torch.optim.AdamW(model.parameters(), lr=3e-5, weight_decay=0.01)
+        cfg["optimizer"] = "torch.optim.AdamW on bf16 parameters"
+        cfg["allreduce_variants"] = ["torch DDP (NCCL, uncompressed bf16)"]
+        algo = "none (plain DDP all-reduce; stock PyTorch has no ByteGrad)"
+    else:
+        from bagua_b200.ops.optim import FusedAdam
+        from bagua_b200.parallel.algorithms import bytegrad
+
+        optimizer = FusedAdam(model.parameters(), lr=3e-5, adamw=True, weight_decay=0.01) if not cpu else torch.optim.AdamW(model.parameters(), lr=3e-5)
+        model = model.with_bagua([optimizer], bytegrad.ByteGradAlgorithm())
+        cfg["optimizer"] = "FusedAdam(adamw, fp32 master weights + moments), one flat kernel per step"
+        cfg["allreduce_variants"] = sorted({getattr(b, "allreduce_variant", "none") for b in model.bagua_buckets})
+        cfg["buckets"] = len(model.bagua_buckets)
+        finish = model.bagua_ddp.wait_pending_comm_ops
+        algo = "ByteGrad (MinMaxUInt8)"
+
+    torch.manual_seed(99 + c.rank)
+
+    def make(device, pinned=False):
+        t = (torch.randint(0, cfgm.vocab_size, (bs, seq)), torch.randint(0, 2, (bs, seq)), torch.ones(bs, seq, dtype=torch.int64),
+             torch.randint(0, seq, (bs,)), torch.randint(0, seq, (bs,)))
+        if pinned and not cpu:
+            return tuple(x.pin_memory() for x in t)
+        return tuple(x.to(device) for x in t)
+
+    dev_batch = make(dev)
+    n_host = 4
+    host = [make("cpu", pinned=True) for _ in range(n_host)]
+
+    def train_step(ids, tt, mask, sp, ep):
+        optimizer.zero_grad()
+        loss = model(ids, token_type_ids=tt, attention_mask=mask, start_positions=sp, end_positions=ep)[0]
+        loss.backward()
+        optimizer.step()
+        return loss
+
+    def host_batches(n):
+        for i in range(n):
+            yield host[i % n_host]
+
+    res = measure(c, "bert", train_step, dev_batch, host_batches, None, bs, "samples/s", finish)
+    res["metric"] = f"BERT-large SQuAD-shaped fine-tuning throughput ({algo})"
+    res["config"] = dict(cfg, model="bert-large (24 layers, hidden 1024, 16 heads, 335 M parameters) + QA head" if not cpu else "tiny bert (selftest)",
+                         global_batch=bs * world, per_gpu_batch=bs, seq_len=seq, parallelism=f"dp{world}", algorithm=algo,
+                         reference_config="examples/squad/README.md:19-28 (seq 384, bs 6/GPU, lr 3e-5)",
+                         l2_policy="670 MB of bf16 weights + 4 GB of optimizer state per step far exceed the 126 MB L2; no explicit flush")
+    del model, optimizer
+    return res
 
 
 def main():
@@ -129,227 +489,73 @@ def main():
     saved_stdout_fd = os.dup(1)
     os.dup2(2, 1)
 
-    import torch
-    import torch.distributed as dist
-    import torch.nn.functional as F
-
-    sys.path.insert(0, REPO)
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world == 1 and args.gpus > 1:
         raise SystemExit(f"--gpus {args.gpus} needs a torchrun launch with {args.gpus} ranks")
+    if args.impl == "nccl_baseline":
+        os.environ["BAGUA_ALLREDUCE_VARIANT"] = "nccl"      # no peer engine: every bucket op is torch.distributed on the comm stream
+    elif args.impl == "ours" and world == 1 and not args.no_self_peer and not args.selftest_cpu:
+        os.environ.setdefault("BAGUA_SELF_PEER", "1")       # N = 1 runs the same bucket kernels with this GPU as the only peer
+    sys.path.insert(0, REPO)
     if "MASTER_PORT" not in os.environ:
         from bagua_b200.env import find_free_network_port
 
         os.environ["MASTER_ADDR"] = "127.0.0.1"
         os.environ["MASTER_PORT"] = str(find_free_network_port())
     os.environ.setdefault("LOCAL_WORLD_SIZE", str(world))
-    cpu = args.selftest_cpu
-    if cpu:
-        dev, dtype = torch.device("cpu"), torch.float32
+
+    c = make_ctx(args)
+    torch = c.torch
+    if args.impl == "ddp":
+        if world > 1:
+            c.dist.init_process_group("nccl" if not c.cpu else "gloo")
     else:
-        torch.cuda.set_device(local_rank)
-        dev, dtype = torch.device("cuda", local_rank), torch.bfloat16
-    img = args.image_size
+        import bagua_b200 as bagua
 
-    import bagua_b200 as bagua
-    from bagua_b200.models import get_model
-    from bagua_b200.ops.optim import FusedSGD
-    from bagua_b200.parallel.algorithms import Algorithm
-
-    bagua.init_process_group()
+        bagua.init_process_group()
     torch.backends.cudnn.benchmark = True
-    torch.manual_seed(1234 + rank)
 
-    if args.fused_shard is None:
-        args.fused_shard = world > 1 and args.algorithm == "gradient_allreduce"
-    bs = args.batch_size
-    model = get_model(args.model).to(dev).to(dtype).to(memory_format=torch.channels_last)
-    if args.fused_shard:
-        from bagua_b200.parallel.algorithms.gradient_allreduce import FusedGradientAllReduceAlgorithm, make_sharded_fused_sgd
-
-        optimizer = make_sharded_fused_sgd(model.parameters(), lr=0.01 * world, momentum=args.momentum)
-        algorithm = FusedGradientAllReduceAlgorithm(optimizer)
-    else:
-        optimizer = FusedSGD(model.parameters(), lr=0.01 * world, momentum=args.momentum, master_weights=True, zero_grad_in_step=True)
-        algorithm = Algorithm.init(args.algorithm)
-    model = model.with_bagua([optimizer], algorithm)
-
-    # synthetic ImageNet batch (reference: fixed random data + target, synthetic_benchmark.py)
-    x_dev = torch.randn(bs, 3, img, img, device=dev).to(dtype).contiguous(memory_format=torch.channels_last)
-    y_dev = torch.randint(0, 1000, (bs,), device=dev)
-    n_host = 4
-    pin = (lambda t: t) if cpu else (lambda t: t.pin_memory())
-    x_host = [pin(torch.randn(bs, 3, img, img)) for _ in range(n_host)]
-    y_host = [pin(torch.randint(0, 1000, (bs,))) for _ in range(n_host)]
-
-    def train_step(x, y):
-        optimizer.zero_grad()
-        out = model(x)
-        loss = F.cross_entropy(out.float(), y)
-        loss.backward()
-        optimizer.step()
-        return loss
-
-    from bagua_b200.utils.data import DevicePrefetcher, LossReader
-
-    def to_model_format(x, y):
-        return x.to(dtype).contiguous(memory_format=torch.channels_last), y
-
-    def host_batches(n):
-        for i in range(n):
-            yield x_host[i % n_host], y_host[i % n_host]
-
-    loss_reader = LossReader(dev)
-    e2e_step = [train_step]  # replaced by the graphed step with --cuda-graph
-
-    def e2e_loop(steps):
-        """The loop a user writes: pinned host batches → DevicePrefetcher (H2D of batch i+1 overlaps step i) → train step →
-        asynchronous D2H read of every step's loss."""
-        last = None
-        for x, y in DevicePrefetcher(host_batches(steps), dev, to_model_format):
-            loss = e2e_step[0](x, y)
-            last = loss_reader.push(loss)
-        return loss_reader.flush()
-
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        if not cpu:
-            torch.cuda.synchronize()
-
-    def timed_host(fn, steps, whole_loop):
-        import time
-
-        sync_all()
-        t0 = time.perf_counter()
-        if whole_loop:
-            fn(steps)
+    results = {}
+    for wl in [w.strip() for w in args.workloads.split(",") if w.strip()]:
+        if wl in ("vgg16", "resnet50"):
+            results[wl] = run_cnn(c, wl)
+        elif wl == "bert":
+            results["bert"] = run_bert(c)
         else:
-            for i in range(steps):
-                fn(i)
-        ms = torch.tensor([(time.perf_counter() - t0) * 1e3])
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
-
-    def timed(fn, steps, whole_loop=False):
-        if cpu:
-            return timed_host(fn, steps, whole_loop)
-        sync_all()
-        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.nvtx.range_push("timed")
-        start.record()
-        if whole_loop:
-            fn(steps)
-        else:
-            for i in range(steps):
-                fn(i)
-        end.record()
-        torch.cuda.nvtx.range_pop()
-        torch.cuda.synchronize()
-        ms = torch.tensor([start.elapsed_time(end)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-            dist.barrier()
-        return float(ms.item())
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()  # started before the warm-up so that the (short) timed region is covered by several samples
-    for i in range(max(args.warmup, 3)):
-        train_step(x_dev, y_dev)
-    if args.profile:
-        from torch.profiler import ProfilerActivity, profile
-
-        torch.cuda.synchronize()
-        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-            for _ in range(3):
-                train_step(x_dev, y_dev)
+            raise SystemExit(f"unknown workload {wl}")
+        if not c.cpu:
             torch.cuda.synchronize()
-        if rank == 0:
-            with open(args.profile, "w") as f:
-                f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
-        return 0
-    from bagua_b200.core import native
+            torch.cuda.empty_cache()
+        c.sync_all()
 
-    sync_all()
-    step_fn = train_step
-    launches_per_replay = 0
-    if args.cuda_graph:
-        if cpu:
-            raise SystemExit("--cuda-graph needs a GPU")
-        from bagua_b200.utils.graph import GraphedTrainStep
-
-        before = native().launch_count()
-        train_step(x_dev, y_dev)                      # kernels replayed from a graph do not pass the launch counter: count one eager step
-        launches_per_replay = native().launch_count() - before
-        step_fn = GraphedTrainStep(model, train_step, (x_dev, y_dev), optimizers=[optimizer])
-        step_fn(x_dev, y_dev)                         # capture happens on the first call, outside the timed region
-        sync_all()
-    launches0 = native().launch_count()  # every kernel of this library counts itself (csrc/common.h: count_launch)
-    ms = timed(lambda i: step_fn(x_dev, y_dev), args.steps)
-    model.bagua_ddp._bagua_backend.wait_pending_comm_ops(0 if cpu else torch.cuda.current_stream().cuda_stream, cpu)
-    gpu_launches = native().launch_count() - launches0 + launches_per_replay * args.steps
-    clocks = sampler.stop() if rank == 0 else None
-    value = bs * world * args.steps / (ms / 1e3)
-
-    e2e = None
-    if not args.no_e2e:
-        e2e_step[0] = step_fn
-        try:
-            e2e_loop(3)
-            ms_e2e = timed(e2e_loop, args.steps, whole_loop=True)
-            h2d = x_host[0].numel() * x_host[0].element_size() + y_host[0].numel() * y_host[0].element_size()
-            e2e = {"value": bs * world * args.steps / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                   "ms_per_step": ms_e2e / args.steps}
-        except Exception as exc:  # noqa: BLE001 - the device-timed headline above must still be reported
-            e2e = {"error": f"{type(exc).__name__}: {exc}"}
-
-    if rank == 0:
-        variants = sorted({getattr(b, "allreduce_variant", "none") for b in model.bagua_buckets})
+    if c.rank == 0:
+        first = next(iter(results))
+        head = results.get("vgg16", results[first])
         out = {
-            "metric": f"{args.model} synthetic-ImageNet training throughput ({args.algorithm})",
-            "value": value,
-            "unit": "images/s",
-            "n_gpus": world,
-            "steps": args.steps,
-            "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps,
-            "higher_is_better": True,
-            "scaling": "weak",
-            "vs_baseline": value / (PUBLISHED_PER_GPU * world),
-            "dtype": "bf16" if not cpu else "fp32",
-            "data": "synthetic (random ImageNet-shaped batch, random-init weights)",
-            "impl": "ours",
-            "config": {
-                "model": args.model,
-                "global_batch": bs * world,
-                "per_gpu_batch": bs,
-                "image": f"3x{img}x{img}",
-                "parallelism": f"dp{world}",
-                "algorithm": args.algorithm,
-                "optimizer": ("SGD fused into the bucket allreduce kernel (sharded fp32 master weights)" if args.fused_shard else f"FusedSGD(momentum={args.momentum}, fp32 master weights)"),
-                "allreduce_variants": variants,
-                "buckets": len(model.bagua_buckets),
-                "host_opts": dict({k: os.environ.get(k, "0") for k in ("BAGUA_NATIVE_HOOKS", "BAGUA_NATIVE_NHWC", "BAGUA_NHWC_FINALIZE", "BAGUA_INLINE_COMM")},
-                                  cuda_graph=bool(args.cuda_graph)),
-                "l2_policy": "working set (276 MB bf16 weights + activations) far exceeds the 126 MB L2; no explicit flush",
-                "baseline_note": "vs_baseline = value / (126.5 img/s/GPU x N): Bagua+Bagua-Net VGG16 fp32 on 32x V100 (rust/bagua-net/README.md:52-67)",
-            },
-            "clocks": clocks,
-            "e2e": e2e,
-            "gpu_launches": int(gpu_launches),
+            "metric": head["metric"], "value": head["value"], "unit": head["unit"], "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if not c.cpu else "fp32", "data": "synthetic (random batches of the named shapes, random-init weights)", "impl": args.impl,
+            "config": head["config"], "clocks": head["clocks"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
+            "published_context": PUBLISHED_CONTEXT,
         }
-        if cpu:
+        if "verify" in head:
+            out["verify"] = head["verify"]
+        if "bert" in results and head is not results["bert"]:
+            b = results["bert"]
+            out["bert_large_bytegrad"] = {k: b[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "clocks", "e2e", "gpu_launches", "final_loss")}
+            out["bert_large_bytegrad"].update(n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), higher_is_better=True, scaling="weak", dtype=out["dtype"])
+        for k, v in results.items():
+            if v is not head and k != "bert":
+                out[k] = v
+        out["config"]["self_peer_n1"] = os.environ.get("BAGUA_SELF_PEER", "0") == "1"
+        if c.cpu:
             out["selftest"] = "host plumbing check, not a benchmark result"
         sys.stdout.flush()
         os.dup2(saved_stdout_fd, 1)
         print(json.dumps(out), flush=True)
         os.dup2(2, 1)
     if world > 1:
-        dist.barrier()
+        c.dist.barrier()
     return 0
 
 

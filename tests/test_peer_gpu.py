@@ -247,7 +247,6 @@ def _fused_combine_worker(rank, world):
     return True
 
 
-@pytest.mark.skipif(__import__("os").environ.get("BAGUA_EXPERIMENTAL") != "1", reason="fused GEMM+combine kernel is opt-in until validated on hardware")
 def test_moe_fused_gemm_combine_matches_two_step():
     run_distributed(_fused_combine_worker, world=_ngpu(), use_cuda=True)
 
@@ -288,7 +287,6 @@ def _fused_adam_worker(rank, world):
     return mine
 
 
-@pytest.mark.skipif(__import__("os").environ.get("BAGUA_EXPERIMENTAL") != "1", reason="fused allreduce+Adam kernel is opt-in until validated on hardware")
 def test_fused_allreduce_adam_matches_adamw():
     res = run_distributed(_fused_adam_worker, world=_ngpu(), use_cuda=True)
     for r in res[1:]:
@@ -338,8 +336,7 @@ def _hier_worker(rank, world):
     return mine
 
 
-@pytest.mark.skipif(__import__("os").environ.get("BAGUA_EXPERIMENTAL") != "1" or torch.cuda.device_count() < 4,
-                    reason="hierarchical (virtual multi-node) path: opt-in until validated on hardware; needs >= 4 GPUs")
+@pytest.mark.skipif(torch.cuda.device_count() < 4, reason="hierarchical (virtual multi-node) path needs >= 4 GPUs posing as 2 nodes")
 def test_hierarchical_allreduce_on_virtual_nodes():
     n = 4 if _ngpu() < 8 else 8
     res = run_distributed(_hier_worker, world=n, use_cuda=True)
@@ -384,16 +381,22 @@ def _abort_worker(rank, world):
         torch.cuda.synchronize()
         out["timeout_latency_s"] = time.time() - t0
         out["code_after_timeout"] = eng.comm.error_code()
+        try:
+            C.run_op(op, stream.cuda_stream, rank)
+            out["fatal_after_timeout"] = False
+        except RuntimeError as e:
+            out["fatal_after_timeout"] = "timed out waiting for another rank" in str(e)
+        eng.comm.clear_error()
     dist.barrier()
     return out
 
 
-@pytest.mark.skipif(__import__("os").environ.get("BAGUA_EXPERIMENTAL") != "1", reason="fault-injection test: opt-in until validated on hardware")
 def test_abort_and_timeout_unblock_a_lonely_allreduce():
     res = run_distributed(_abort_worker, world=2, use_cuda=True)
     r0 = res[0]
     assert r0["spinning"] and r0["abort_latency_s"] < 1.0 and r0["code_after_abort"] == 2
     assert 1.5 < r0["timeout_latency_s"] < 6.0 and r0["code_after_timeout"] in (1, 3)
+    assert r0["fatal_after_timeout"], "a timed-out collective must make every later op of the communicator raise"
 
 
 def _syncbn_worker(rank, world):
@@ -427,7 +430,6 @@ def _syncbn_worker(rank, world):
     return True
 
 
-@pytest.mark.skipif(__import__("os").environ.get("BAGUA_EXPERIMENTAL") != "1", reason="SyncBatchNorm CUDA path: opt-in until validated on hardware")
 def test_sync_batchnorm_cuda_matches_torch():
     run_distributed(_syncbn_worker, world=min(_ngpu(), 4), use_cuda=True)
 
@@ -468,7 +470,6 @@ def _peer_collectives_worker(rank, world):
     return True
 
 
-@pytest.mark.skipif(__import__("os").environ.get("BAGUA_EXPERIMENTAL") != "1", reason="peer all-gather / reduce-scatter: opt-in until validated on hardware")
 def test_peer_allgather_and_reduce_scatter_match_torch():
     run_distributed(_peer_collectives_worker, world=_ngpu(), use_cuda=True)
 
@@ -526,7 +527,6 @@ def _graphed_step_worker(rank, world):
     return out
 
 
-@pytest.mark.skipif(__import__("os").environ.get("BAGUA_EXPERIMENTAL") != "1", reason="multi-rank CUDA-graph capture (inline issue): opt-in until validated on hardware")
 def test_graphed_step_with_bucket_communication_matches_eager():
     res = run_distributed(_graphed_step_worker, world=_ngpu(), use_cuda=True)
     assert len(res) == _ngpu()
@@ -570,8 +570,221 @@ def _sharded_state_worker(rank, world):
     return torch.cat(out)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("BAGUA_EXPERIMENTAL") != "1", reason="sharded optimizer checkpointing: opt-in until validated on hardware")
 def test_fused_sharded_optimizer_state_dict_roundtrip():
     res = run_distributed(_sharded_state_worker, world=_ngpu(), use_cuda=True)
     for r in res[1:]:
         assert torch.equal(res[0], r)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Decentralized algorithms against python re-implementations on real GPUs, with a bucket large enough (>= 8 MiB) to leave the
+# one-shot / padding paths (reference: tests/torch_api/test_decentralized.py:169-259,326-399 and
+# tests/torch_api/test_low_precision_decentralized.py:157-255).
+# ---------------------------------------------------------------------------------------------------------------------
+def _big_mlp(dev):
+    torch.manual_seed(77)
+    return torch.nn.Sequential(torch.nn.Linear(1024, 1024), torch.nn.ReLU(), torch.nn.Linear(1024, 1024), torch.nn.ReLU(), torch.nn.Linear(1024, 64)).to(dev)
+
+
+def _exchange(t, peer):
+    import torch.distributed as dist
+
+    got = torch.empty_like(t)
+    for r in dist.batch_isend_irecv([dist.P2POp(dist.isend, t, peer), dist.P2POp(dist.irecv, got, peer)]):
+        r.wait()
+    return got
+
+
+def _decentralized_oracle_worker(rank, world, mode):
+    import copy
+
+    import torch.distributed as dist
+
+    import bagua_b200 as bagua
+    from bagua_b200.core import native
+    from bagua_b200.parallel.algorithms import decentralized
+
+    bagua.init_process_group()
+    dev = torch.device("cuda", rank)
+    model = _big_mlp(dev)
+    oracle = copy.deepcopy(model)
+    opt = torch.optim.SGD(model.parameters(), lr=0.05)
+    oopt = torch.optim.SGD(oracle.parameters(), lr=0.05)
+    model = model.with_bagua([opt], decentralized.DecentralizedAlgorithm(hierarchical=False, peer_selection_mode=mode))
+    bucket = model.bagua_buckets[0]
+    assert bucket.bytes() >= 8 * 1024 * 1024
+    assert "python" not in bucket.backend_bucket.print_ops(), bucket.backend_bucket.print_ops()
+    oparams = list(reversed(list(oracle.parameters())))      # bucket order
+    for step in range(4):
+        x = torch.randn(16, 1024, device=dev, generator=torch.Generator(device=dev).manual_seed(100 * step + rank))
+        # --- oracle: average the weights as they are at forward time, swap them in before the optimizer step
+        flat = torch.cat([p.data.reshape(-1) for p in oparams])
+        if mode == "all":
+            pw = flat.clone()
+            dist.all_reduce(pw)
+            pw /= world
+        else:
+            peer = native().PeerAverageOp.shift_one_peer(rank, world, step)
+            pw = (flat + _exchange(flat, peer)) / 2
+        oopt.zero_grad()
+        oracle(x).pow(2).mean().backward()
+        off = 0
+        with torch.no_grad():
+            for p in oparams:
+                p.copy_(pw[off: off + p.numel()].view_as(p))
+                off += p.numel()
+        oopt.step()
+        # --- bagua
+        opt.zero_grad()
+        model(x).pow(2).mean().backward()
+        torch.cuda.synchronize()
+        got_pw = bucket._peer_weight.view(-1)[: pw.numel()]
+        torch.testing.assert_close(got_pw, pw, rtol=1e-6, atol=1e-6)           # the peer_weight replica itself
+        opt.step()
+    torch.cuda.synchronize()
+    mine = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    want = torch.cat([p.detach().reshape(-1) for p in oracle.parameters()])
+    torch.testing.assert_close(mine, want, rtol=1e-5, atol=1e-6)
+    assert bagua.communication._get_default_group().peer_engine().comm.error_code() == 0
+    return True
+
+
+@pytest.mark.parametrize("mode", ["all", "shift_one"])
+def test_decentralized_matches_python_oracle_on_gpus(mode):
+    world = _ngpu() if _ngpu() % 2 == 0 else _ngpu() - 1
+    run_distributed(_decentralized_oracle_worker, world=world, args=(mode,), use_cuda=True)
+
+
+def _lp_decentralized_oracle_worker(rank, world):
+    import copy
+
+    import bagua_b200 as bagua
+    from bagua_b200.ops import quant
+    from bagua_b200.parallel.algorithms import decentralized
+
+    bagua.init_process_group()
+    dev = torch.device("cuda", rank)
+    model = _big_mlp(dev)
+    oracle = copy.deepcopy(model)
+    opt = torch.optim.SGD(model.parameters(), lr=0.05)
+    oopt = torch.optim.SGD(oracle.parameters(), lr=0.05)
+    model = model.with_bagua([opt], decentralized.LowPrecisionDecentralizedAlgorithm(hierarchical=False))
+    assert all("low_precision_ring_fused" in b.backend_bucket.print_ops() for b in model.bagua_buckets)
+    assert sum(b.bytes() for b in model.bagua_buckets) >= 8 * 1024 * 1024
+    # the oracle keeps weight / left / right replicas per bucket, in bucket layout
+    names = {id(p): n for n, p in model.named_parameters()}
+    oparam = dict(oracle.named_parameters())
+    state = []
+    for b in model.bagua_buckets:
+        ps = [oparam[names[id(t)]] for t in b.tensors]
+        w = torch.cat([p.data.reshape(-1) for p in ps])
+        state.append({"params": ps, "w": w.clone(), "l": w.clone(), "r": w.clone()})
+    left, right = (rank + world - 1) % world, (rank + 1) % world
+    for step in range(4):
+        x = torch.randn(16, 1024, device=dev, generator=torch.Generator(device=dev).manual_seed(100 * step + rank))
+        oopt.zero_grad()
+        oracle(x).pow(2).mean().backward()
+        oopt.step()
+        for st in state:
+            xx = torch.cat([p.data.reshape(-1) for p in st["params"]])
+            xx.add_(st["l"], alpha=1.0 / 3.0).add_(st["r"], alpha=1.0 / 3.0).sub_(st["w"], alpha=5.0 / 3.0)
+            mm, q = quant.torch_compress_chunk(xx)
+            lmm, lq = _exchange(mm, left), _exchange(q, left)
+            if world > 2:
+                rmm, rq = _exchange(mm, right), _exchange(q, right)
+            else:
+                rmm, rq = lmm, lq
+            st["l"] += quant.torch_decompress_chunk(lmm, lq, xx.dtype)
+            st["r"] += quant.torch_decompress_chunk(rmm, rq, xx.dtype)
+            xx = st["w"] + quant.torch_decompress_chunk(mm, q, xx.dtype)
+            st["w"].copy_(xx)
+            off = 0
+            with torch.no_grad():
+                for p in st["params"]:
+                    p.copy_(xx[off: off + p.numel()].view_as(p))
+                    off += p.numel()
+        opt.zero_grad()
+        model(x).pow(2).mean().backward()
+        opt.step()
+    torch.cuda.synchronize()
+    for b, st in zip(model.bagua_buckets, state):
+        n = st["w"].numel()
+        for got, want, what in ((b._weight.view(-1)[:n], st["w"], "weight"), (b._left_peer_weight.view(-1)[:n], st["l"], "left"),
+                                (b._right_peer_weight.view(-1)[:n], st["r"], "right")):
+            level = (want.max() - want.min()).item() / 255
+            d = (got - want).abs()
+            assert d.max().item() <= 4 * level + 1e-5, (what, d.max().item(), level)       # rare one-level flips compound over 4 steps
+            assert (d > 1e-4).float().mean().item() < 1e-2, what
+    assert bagua.communication._get_default_group().peer_engine().comm.error_code() == 0
+    return True
+
+
+def test_low_precision_decentralized_replicas_match_python_oracle_on_gpus():
+    run_distributed(_lp_decentralized_oracle_worker, world=_ngpu(), use_cuda=True)
+
+
+def _fused_sgd_oracle_worker(rank, world, variant):
+    """The kernel behind the N > 1 headline: reduce-scatter → SGD(momentum, nesterov, wd) → all-gather vs torch.optim.SGD on
+    all-reduced gradients, bf16 and fp32, two-shot (peer ld/st) and multimem (NVLS) flavours, buckets from 64 KiB to 256 MiB."""
+    import torch.distributed as dist
+
+    import bagua_b200 as bagua
+    from bagua_b200.core import dtype_code, native
+
+    bagua.init_process_group()
+    eng = bagua.communication._get_default_group().peer_engine()
+    C = native()
+    dev = torch.device("cuda", rank)
+    use_mc = variant == "multimem"
+    if use_mc and not eng.has_multicast:
+        return "no multicast"
+    stream = torch.cuda.current_stream().cuda_stream
+    for dtype in (torch.float32, torch.bfloat16):
+        es = torch.empty(0, dtype=dtype).element_size()
+        for nbytes in (64 * 1024, 8 * 1024 ** 2 + 48, 256 * 1024 ** 2):
+            nbytes = nbytes // 16 * 16
+            numel = nbytes // es
+            gs, ws = eng.alloc(nbytes), eng.alloc(nbytes)
+            per = 16 // es
+            vpr = (nbytes // 16 + world - 1) // world
+            lo, hi = rank * vpr * per, min((rank + 1) * vpr * per, numel)
+            torch.manual_seed(1)
+            w0 = torch.randn(numel, device=dev).to(dtype)
+            ws.view(dtype, numel).copy_(w0)
+            master = torch.zeros(vpr * per, device=dev)
+            if hi > lo:
+                master[: hi - lo].copy_(w0[lo:hi].float())
+            mom = torch.zeros(vpr * per, device=dev)
+            op = C.AllReduceSgdOp(eng.comm, gs.buf, ws.buf, gs.offset, ws.offset, nbytes, dtype_code(dtype), master.data_ptr(), mom.data_ptr(), 1.0 / world, True,
+                                  use_mc, eng.launch_cfg("multimem" if use_mc else "two_shot", nbytes, 16 if use_mc else 32))
+            op.set_hyper(0.1, 0.9, 0.0, 1e-4, True)
+            ref = torch.nn.Parameter(w0.float().clone())
+            ropt = torch.optim.SGD([ref], lr=0.1, momentum=0.9, nesterov=True, weight_decay=1e-4)
+            for step in range(3):
+                torch.manual_seed(10 * step + rank)
+                g = torch.randn(numel, device=dev).to(dtype)
+                gs.view(dtype, numel).copy_(g)
+                gsum = g.float()
+                dist.all_reduce(gsum)
+                ref.grad = gsum / world
+                ropt.step()
+                torch.cuda.synchronize()
+                dist.barrier()
+                C.run_op(op, stream, rank)
+                torch.cuda.synchronize()
+                assert gs.view(dtype, numel).abs().max().item() == 0.0
+            if hi > lo:
+                tol = 1e-4 if dtype == torch.float32 else 2e-2      # bf16: the in-switch sum is rounded to bf16 once
+                torch.testing.assert_close(master[: hi - lo], ref.data[lo:hi], rtol=tol, atol=tol)
+            got = ws.view(dtype, numel).float()
+            torch.testing.assert_close(got, ref.data.to(dtype).float(), rtol=0, atol=4e-2 if dtype == torch.bfloat16 else 1e-4)
+            gs.free()
+            ws.free()
+    assert eng.comm.error_code() == 0
+    return "ok"
+
+
+@pytest.mark.parametrize("variant", ["two_shot", "multimem"])
+def test_fused_allreduce_sgd_kernel_matches_torch_sgd(variant):
+    res = run_distributed(_fused_sgd_oracle_worker, world=_ngpu(), args=(variant,), use_cuda=True, timeout=600)
+    assert all(r in ("ok", "no multicast") for r in res)
