@@ -59,6 +59,7 @@ void launch_peer_barrier(const PeerCtx& ctx, cudaStream_t stream);
 void launch_async_average(const PeerCtx& ctx, void* w, const PeerBuf& snap, size_t snap_off, const PeerBuf& avg, size_t avg_off, size_t bytes, int dtype,
                           uint32_t seq, bool go, uint32_t* gate, unsigned long long gate_timeout_ns, int* status, bool use_multimem, int nblocks, int nthreads,
                           cudaStream_t stream);
+void preload_gate_kernels();
 void launch_gate_acquire(uint32_t* gate, unsigned long long timeout_ns, cudaStream_t stream);
 void launch_gate_release(uint32_t* gate, cudaStream_t stream);
 

@@ -219,6 +219,7 @@ WeightGate::WeightGate(int device) : device_(device) {
     DeviceGuard g(device);
     BAGUA_CUDA_CHECK(cudaMalloc(&words_, 8 * sizeof(uint32_t)));
     BAGUA_CUDA_CHECK(cudaMemset(words_, 0, 8 * sizeof(uint32_t)));
+    preload_gate_kernels();
     BAGUA_CUDA_CHECK(cudaDeviceSynchronize());
 }
 WeightGate::~WeightGate() {

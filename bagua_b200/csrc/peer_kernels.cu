@@ -880,6 +880,16 @@ void launch_async_average(const PeerCtx& ctx, void* w, const PeerBuf& snap, size
     check_launch("async_average");
 }
 
+// CUDA loads kernels lazily, and loading one while another kernel is RUNNING can wait for that kernel to finish (programming guide,
+// "Lazy Loading": concurrent execution is not guaranteed while a kernel still has to be loaded). The trainer-side gate kernels are
+// launched precisely while an averaging kernel may be parked in front of the gate waiting for them — so they are loaded up front.
+void preload_gate_kernels() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, gate_acquire_kernel);
+    cudaFuncGetAttributes(&a, gate_release_kernel);
+    cudaGetLastError();
+}
+
 void launch_gate_acquire(uint32_t* gate, unsigned long long timeout_ns, cudaStream_t stream) {
     gate_acquire_kernel<<<1, 32, 0, stream>>>(gate, timeout_ns);
     check_launch("gate_acquire");

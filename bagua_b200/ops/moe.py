@@ -8,6 +8,8 @@ Paths: (1) NVSwitch peer kernels (``csrc/moe_kernels.cu``): rows are stored/load
 The reference does dense one-hot einsums + ``all_to_all_single`` (sharded_moe.py:352-374)."""
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -93,7 +95,7 @@ class _GatherRows(torch.autograd.Function):
 
 def _peer_ctx(tokens: torch.Tensor, group, world: int):
     """The NVSwitch MoE context for this group, or None."""
-    if not tokens.is_cuda or world < 2:
+    if not tokens.is_cuda or (world < 2 and os.environ.get("BAGUA_SELF_PEER", "0") != "1"):   # world 1 only in self-peer mode
         return None
     from . import moe_peer
 

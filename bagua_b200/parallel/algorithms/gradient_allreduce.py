@@ -345,7 +345,10 @@ class FusedGradientAllReduceAlgorithmImpl(GradientAllReduceAlgorithmImpl):
                 g = t.bagua_getter_closure()
                 assert t.dtype == flat.dtype, "weights and gradients must share a dtype for the fused kernel"
                 off = (g.data_ptr() - base) // flat.element_size()
-                view = torch.as_strided(wflat, t.shape, dense_strides(t), off)
+                # as_strided's offset is ABSOLUTE in the storage (the symmetric slab), not relative to wflat: without the slice's own
+                # offset the parameter would alias whatever sits at the start of the slab — the gradient arena the kernel zeroes
+                view = torch.as_strided(wflat, t.shape, dense_strides(t), wflat.storage_offset() + off)
+                assert view.data_ptr() == wflat.data_ptr() + off * flat.element_size()
                 view.copy_(t.data)
                 t.data = view
         vecs = nbytes // 16

