@@ -367,9 +367,9 @@ class FusedGradientAllReduceAlgorithmImpl(GradientAllReduceAlgorithmImpl):
         force = os.environ.get("BAGUA_FUSED_MULTIMEM", "auto")
         if force == "0" or (force != "1" and n <= 2):
             use_mc = False
-        # 16 CTAs: the configuration measured at 56 994 img/s on 8 GPUs (profiles/bench8_fused.json); the kernel also streams
-        # the fp32 optimizer shard, so it wants more CTAs than the bare multimem allreduce (8)
-        cfg = eng.launch_cfg("multimem" if use_mc else "two_shot", nbytes, blocks=int(os.environ.get("BAGUA_FUSED_BLOCKS", "0")) or (16 if use_mc else 32))
+        # multimem flavour: 16 CTAs (measured on 8 GPUs, round 1); the peer ld/st flavour (1-2 ranks) also streams a large optimizer
+        # shard per rank and wants 64 (VGG16 N=1 self-peer: 8 CTAs 5.43 ms/step, 32: 4.34, 64: 4.23 = the flat-optimizer path)
+        cfg = eng.launch_cfg("multimem" if use_mc else "two_shot", nbytes, blocks=int(os.environ.get("BAGUA_FUSED_BLOCKS", "0")) or (16 if use_mc else 64))
         scale = (1.0 / n) if self.average else 1.0
         if is_adam:
             second = torch.zeros(vpr * per, dtype=torch.float32, device=flat.device)

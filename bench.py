@@ -240,7 +240,7 @@ def measure(c, name, train_step, dev_batch, host_batches, to_model_format, per_s
     value = per_step_items * c.world * args.steps / (ms / 1e3)
     e2e = None
     if not args.no_e2e:
-        reader = LossReader(c.dev)
+        reader = LossReader(c.dev, lag=int(os.environ.get("BAGUA_BENCH_LOSS_LAG", "2")))
 
         def loop(steps):
             for batch in DevicePrefetcher(host_batches(steps), c.dev, to_model_format):
@@ -248,7 +248,7 @@ def measure(c, name, train_step, dev_batch, host_batches, to_model_format, per_s
             return reader.flush()
 
         try:
-            loop(3)
+            loop(max(args.warmup, 3))   # the prefetcher's side-stream buffers and the cast kernels warm up too
             ms_e2e = c.timed(loop, args.steps, whole_loop=True)
             if finish is not None:
                 finish()

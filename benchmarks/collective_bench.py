@@ -33,6 +33,10 @@ pg = bagua.communication._get_default_group()
 eng = pg.peer_engine()
 assert eng is not None
 C = native()
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import ClockSampler  # noqa: E402
+
+sampler = ClockSampler(local).start() if rank == 0 else None
 dtype = {"bf16": torch.bfloat16, "f32": torch.float32}[args.dtype]
 dev = torch.device("cuda", local)
 stream = torch.cuda.current_stream().cuda_stream
@@ -97,6 +101,8 @@ if rank == 0:
     if args.out:
         os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
         with open(args.out, "w") as f:
-            json.dump({"world": world, "dtype": args.dtype, "multicast": eng.has_multicast, "results": results}, f, indent=1)
+            json.dump({"world": world, "dtype": args.dtype, "multicast": eng.has_multicast, "clocks": sampler.stop(),
+                       "roofline_note": "an all-reduce moves ~bytes in and ~bytes out of every GPU: the NVLink bound is ALGBW <= 900 GB/s nominal per direction (770 GB/s measured peer copy); busbw is reported for comparison with nccl-tests only",
+                       "results": results}, f, indent=1)
 assert eng.comm.error_code() == 0
 dist.barrier()

@@ -28,6 +28,8 @@ p.add_argument("--force-bf16", action="store_true", help="bf16 parameters even o
 p.add_argument("--comm-report", action="store_true", help="per-bucket device time / GB/s of the communication programs (adds 2 event records per bucket)")
 p.add_argument("--arm", choices=["peer", "nccl"], default="peer", help="nccl = same schedule on NCCL collectives / cuBLAS experts only (baseline arm)")
 args = p.parse_args()
+if os.environ.get("WORLD_SIZE", "1") == "1" and args.arm == "peer" and not args.cpu:
+    os.environ.setdefault("BAGUA_SELF_PEER", "1")   # one GPU: same kernels with this GPU as the only peer (see bench.py)
 if args.arm == "nccl":
     os.environ["BAGUA_ALLREDUCE_VARIANT"] = "nccl"
     os.environ["BAGUA_MOE_PEER"] = "0"
@@ -119,6 +121,10 @@ def sync():
         torch.cuda.synchronize()
 
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import ClockSampler  # noqa: E402
+
+sampler = ClockSampler(bagua.get_local_rank()).start() if (cuda and rank == 0) else None
 for _ in range(max(args.warmup, 3)):
     loss = step()
 sync()
@@ -154,7 +160,9 @@ if rank == 0:
         "config": cfg, "arm": args.arm, "moe_fused_combine": os.environ.get("BAGUA_MOE_FUSED_COMBINE", "0"), "n_gpus": world, "value": per_step * world * args.steps / (ms.item() / 1e3), "unit": unit, "ms_per_step": ms.item() / args.steps,
         "per_gpu_batch": bs, "dtype": str(dtype), "loss_finite": finite,
         "arm": "nccl-only" if os.environ.get("BAGUA_ALLREDUCE_VARIANT") == "nccl" else "peer-kernels",
-        "moe_peer": os.environ.get("BAGUA_MOE_PEER", "1"),
+        "moe_peer": os.environ.get("BAGUA_MOE_PEER", "1"), "steps": args.steps, "warmup": max(args.warmup, 3),
+        "clocks": sampler.stop() if sampler is not None else None, "final_loss": float(loss.detach().float().item()),
+        "timing": "CUDA events around the K steps on the launching stream, max over ranks; synthetic data, random-init weights",
     }))
 if world > 1:
     dist.barrier()

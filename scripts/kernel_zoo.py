@@ -34,9 +34,15 @@ flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
 rows = []
 
 
+UNDER_NCU = os.environ.get("ZOO_NCU", "0") == "1"   # one launch per kernel, no warm-up: every launch is replayed ~40x by ncu
+
+
 def timed(name, fn, nbytes_alg, iters=5, flops=0.0):
     """``nbytes_alg``: algorithmic HBM bytes of one launch (what an ideal implementation must move)."""
-    fn()
+    if UNDER_NCU:
+        iters = 1
+    else:
+        fn()
     ts = []
     for _ in range(iters):
         flush.zero_()
