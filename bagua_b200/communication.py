@@ -570,6 +570,14 @@ def get_autotune_service_port() -> Optional[int]:
     return _autotune_service_port
 
 
+_autotune_service_host: List[Optional[str]] = [None]
+
+
+def get_autotune_service_host() -> str:
+    """Host under which this process reaches the autotune service (decided by the health check in ``init_process_group``)."""
+    return _autotune_service_host[0] or env.get_master_addr()
+
+
 def _start_autotune_server(world_size: int):
     """Rank 0 hosts the autotune HTTP service in a daemon process (reference communication.py:384-443)."""
     global _autotune_server, _autotune_service_port
@@ -583,18 +591,23 @@ def _start_autotune_server(world_size: int):
         _autotune_server = start_autotune_server_process(port, world_size)
         store.set("bagua_autotune_service_port", str(port))
     _autotune_service_port = int(store.get("bagua_autotune_service_port"))
-    os.environ.setdefault("AUTO_TUNE_SERVER_ADDR", f"{env.get_master_addr()}:{_autotune_service_port}")
     from .service.autotune_service import AutotuneClient
-
-    client = AutotuneClient(env.get_master_addr(), _autotune_service_port)
     import time
 
+    # Where rank 0 is reachable: MASTER_ADDR normally — but the elastic launcher exports the node's *hostname* there, which
+    # need not resolve inside a container; processes of rank 0's own node then reach the service through loopback.
+    hosts = [env.get_master_addr()]
+    if env.get_node_rank() == 0 and "127.0.0.1" not in hosts:
+        hosts.append("127.0.0.1")
     deadline = time.time() + max(30, env.get_autotune_server_wait_time())
     while time.time() < deadline:
-        if client.health_check():
-            return
+        for h in hosts:
+            if AutotuneClient(h, _autotune_service_port, timeout=2.0).health_check():
+                _autotune_service_host[0] = h
+                os.environ["AUTO_TUNE_SERVER_ADDR"] = f"{h}:{_autotune_service_port}"
+                return
         time.sleep(0.2)
-    raise RuntimeError("autotune service did not come up in time")
+    raise RuntimeError(f"autotune service did not come up in time (tried {hosts}, port {_autotune_service_port})")
 
 
 def start_autotune_server(service_port: int = -1):
@@ -611,7 +624,7 @@ def get_hyperparameters_service_client():
     from .service.autotune_service import AutotuneClient
 
     port = _autotune_service_port if _autotune_service_port else env.get_bagua_service_port()
-    return AutotuneClient(env.get_master_addr(), port)
+    return AutotuneClient(get_autotune_service_host(), port)
 
 
 class CommMember(object):

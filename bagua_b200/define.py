@@ -63,6 +63,10 @@ class BaguaHyperparameter(BaseModel):
     is_hierarchical_reduce: bool = False
     allreduce_variant: str = "auto"
     comm_blocks: int = 0
+    # Per bucket (same order as ``buckets``): the kernel variant / CTA count the service looked up, for that bucket's message
+    # size, in the bus-bandwidth table the workers MEASURED on their fabric at start-up (PeerEngine.calibrate). Empty = none measured.
+    bucket_variants: List[str] = []
+    bucket_blocks: List[int] = []
 
     def update(self, param_dict: dict) -> "BaguaHyperparameter":
         tmp = self.model_dump()

@@ -23,6 +23,14 @@ class GradientAllReduceAlgorithmImpl(AlgorithmImpl):
         variant = self.variant
         if variant == "auto" and hp is not None and getattr(hp, "allreduce_variant", "auto") != "auto":
             variant = hp.allreduce_variant
+        if variant == "auto" and hp is not None and getattr(hp, "bucket_variants", None):
+            # autotune service: variant per bucket, looked up by message size in the bus-bandwidth table measured at start-up
+            try:
+                i = [b.name for b in bagua_ddp.bagua_buckets].index(bucket.name)
+                if i < len(hp.bucket_variants):
+                    variant = hp.bucket_variants[i]
+            except ValueError:
+                pass
         bucket.append_centralized_synchronous_op(hierarchical=self.hierarchical, average=self.average, group=self.process_group, variant=variant)
 
 

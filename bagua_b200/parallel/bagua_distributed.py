@@ -127,7 +127,7 @@ class BaguaDistributedDataParallel:
 
             port = comm_mod.get_autotune_service_port()
             assert port is not None, "autotune level > 0 but the autotune service was not started by init_process_group"
-            self._bagua_autotune_client = AutotuneClient(env.get_master_addr(), port)
+            self._bagua_autotune_client = AutotuneClient(comm_mod.get_autotune_service_host(), port)
             self._bagua_backend.set_record_spans(True)
 
         ddp = self
@@ -267,7 +267,14 @@ class BaguaDistributedDataParallel:
     def _bagua_autotune_register_tensors(self):
         if self._bagua_autotune_client is None:
             return
-        rsp = self._bagua_autotune_client.register_tensors(model_name=self.bagua_module_name, tensor_list=self._tensor_declarations())
+        # the allreduce variants are measured once on this fabric (every rank derives the same table: MAX-reduced event times) and
+        # handed to the service, which then picks the kernel variant per bucket from the bucket's message size
+        table = None
+        if self._on_cuda:
+            eng = self.process_group.peer_engine()
+            if eng is not None and eng.world > 1:
+                table = eng.variant_table or eng.calibrate()
+        rsp = self._bagua_autotune_client.register_tensors(model_name=self.bagua_module_name, tensor_list=self._tensor_declarations(), variant_table=table)
         assert rsp.status_code == 200, f"Unexpected rsp={rsp}"
 
     def _bagua_autotune_get_buckets(self) -> List[List[torch.Tensor]]:

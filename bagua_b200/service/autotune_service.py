@@ -53,6 +53,7 @@ class AutotuneServiceTaskManager:
         self.check_board = [-1] * world_size
         self.time_hp_last_granted = time.time()
         self.hyperparameter = BaguaHyperparameter()
+        self.variant_table: List[dict] = []   # measured by the workers: [{"bytes", "variant", "blocks", "ms", "busbw_GBs"}, ...]
 
 
 class AutotuneService:
@@ -94,8 +95,33 @@ class AutotuneService:
             hp_manager.hyperparameter = recommended
         else:
             hp_manager.hyperparameter = hp_manager.inner.best_hyperparameter()
+        self.apply_variant_table(hp_manager, hp_manager.hyperparameter)
         hp_manager.sampling_count += 1
         hp_manager.time_hp_last_granted = time.time()
+
+    # -- kernel variant per message size, from measured bus bandwidth ---------------------------------------------------
+    @staticmethod
+    def _bucket_bytes(bucket) -> int:
+        unit = {"f32": 4, "f16": 2, "bf16": 2, "u8": 1, "i64": 8}
+        return sum(int(td["num_elements"]) * unit.get(str(getattr(td["dtype"], "value", td["dtype"])), 4) for td in bucket)
+
+    def apply_variant_table(self, mgr: AutotuneServiceTaskManager, hp: BaguaHyperparameter) -> BaguaHyperparameter:
+        """Every bucket gets the allreduce kernel variant (and CTA count) that was fastest, at the calibrated message size nearest
+        to the bucket's own (log scale), in the table the workers measured on their fabric — unless the search itself is trying
+        a global variant (``allreduce_variant != "auto"``)."""
+        import math
+
+        if not mgr.variant_table or hp.allreduce_variant != "auto":
+            hp.bucket_variants, hp.bucket_blocks = [], []
+            return hp
+        vs, bs = [], []
+        for b in hp.buckets:
+            n = max(self._bucket_bytes(b), 1)
+            row = min(mgr.variant_table, key=lambda r: abs(math.log2(n) - math.log2(max(int(r["bytes"]), 1))))
+            vs.append(str(row["variant"]))
+            bs.append(int(row.get("blocks", 0)))
+        hp.bucket_variants, hp.bucket_blocks = vs, bs
+        return hp
 
     # -- endpoints -----------------------------------------------------------------------------------------------
     def register_tensors(self, req: dict):
@@ -108,7 +134,10 @@ class AutotuneService:
         mgr = self.model_dict[model_name]
         bucket_size = self.default_bucket_size if whether_to_bucket else 10 * 1024 ** 5
         with mgr.lock:
+            if req.get("variant_table"):
+                mgr.variant_table = list(req["variant_table"])
             hp = BaguaHyperparameter(buckets=split_bucket_by_bucket_size(tensor_list, bucket_size), bucket_size=bucket_size)
+            self.apply_variant_table(mgr, hp)
             mgr.time_hp_last_granted = time.time()
             mgr.hyperparameter = hp
             return 200, {"recommended_hyperparameters": hp.dict()}
@@ -230,11 +259,48 @@ def run_autotune_server(port: int, world_size: int, **kwargs):
     server.serve_forever()
 
 
-def start_autotune_server_process(port: int, world_size: int, **kwargs) -> multiprocessing.Process:
-    """Start :class:`AutotuneService` on ``port`` in a daemon process and return it."""
-    ctx = multiprocessing.get_context("spawn")
-    p = ctx.Process(target=run_autotune_server, args=(port, world_size), kwargs=kwargs, daemon=True)
-    p.start()
+class _ServerProcess:
+    """Handle of the service process with the small part of ``multiprocessing.Process`` its users need."""
+
+    def __init__(self, popen):
+        self._p = popen
+        self.pid = popen.pid
+
+    def is_alive(self) -> bool:
+        return self._p.poll() is None
+
+    def terminate(self):
+        if self.is_alive():
+            self._p.terminate()
+
+    def kill(self):
+        if self.is_alive():
+            self._p.kill()
+
+    def join(self, timeout=None):
+        try:
+            self._p.wait(timeout=timeout)
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def start_autotune_server_process(port: int, world_size: int, **kwargs) -> "_ServerProcess":
+    """Start :class:`AutotuneService` on ``port`` in its own interpreter (``python -m bagua_b200.service.autotune_service``) and
+    return a handle.  Deliberately NOT ``multiprocessing`` with the spawn start method: that re-imports the parent's ``__main__``
+    — the user's training script, which has no reason to carry an ``if __name__ == "__main__"`` guard — and the child would call
+    ``init_process_group`` as a second rank 0 and hang the job; fork is not an option once CUDA / NCCL are initialised."""
+    import atexit
+    import os
+    import subprocess
+    import sys
+
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "CUDA_VISIBLE_DEVICES")}
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
+    cmd = [sys.executable, "-m", "bagua_b200.service.autotune_service", "--port", str(port), "--world-size", str(world_size), "--kwargs", json.dumps(kwargs)]
+    p = _ServerProcess(subprocess.Popen(cmd, env=env, stdin=subprocess.DEVNULL))
+    atexit.register(p.terminate)
     return p
 
 
@@ -262,8 +328,9 @@ def reset_error_retry(request_func, max_retries: int = 3, delay_s: float = 1.0):
 class AutotuneClient:
     """REST client with keep-alive and retries (reference autotune_service.py:306-435)."""
 
-    def __init__(self, service_addr: str, service_port: int, proxies: Optional[dict] = None):
+    def __init__(self, service_addr: str, service_port: int, proxies: Optional[dict] = None, timeout: float = 5.0):
         self.base = f"http://{service_addr}:{service_port}"
+        self.health_timeout = timeout
         self.session = requests.Session()
         self.session.trust_env = False
         self.proxies = proxies or {"http": None, "https": None}
@@ -283,8 +350,11 @@ class AutotuneClient:
     def report_metrics(self, model_name: str, rank: int, train_iter: int, hyperparameters: dict, speed: float):
         return self._post("/api/v1/report_metrics", {"model_name": model_name, "rank": rank, "train_iter": train_iter, "hyperparameters": hyperparameters, "speed": speed})
 
-    def register_tensors(self, model_name: str, tensor_list: List[TensorDeclaration], whether_to_bucket: bool = True):
-        return self._post("/api/v1/register_tensors", {"model_name": model_name, "tensor_list": tensor_list, "whether_to_bucket": whether_to_bucket})
+    def register_tensors(self, model_name: str, tensor_list: List[TensorDeclaration], whether_to_bucket: bool = True, variant_table: Optional[list] = None):
+        payload = {"model_name": model_name, "tensor_list": tensor_list, "whether_to_bucket": whether_to_bucket}
+        if variant_table:
+            payload["variant_table"] = variant_table   # measured allreduce bus bandwidth per size class (PeerEngine.calibrate)
+        return self._post("/api/v1/register_tensors", payload)
 
     def ask_hyperparameters(self, model_name: str, rank: int, train_iter: int):
         return self._post("/api/v1/ask_hyperparameters", {"model_name": model_name, "rank": rank, "train_iter": train_iter})
@@ -294,7 +364,22 @@ class AutotuneClient:
 
     def health_check(self) -> bool:
         try:
-            r = self.session.get(self.base + "/api/v1/health_check", proxies=self.proxies, timeout=5)
+            r = self.session.get(self.base + "/api/v1/health_check", proxies=self.proxies, timeout=self.health_timeout)
             return r.status_code == 200
         except Exception:  # noqa: BLE001
             return False
+
+
+def _main():
+    import argparse
+
+    ap = argparse.ArgumentParser(description="bagua_b200 autotune service")
+    ap.add_argument("--port", type=int, required=True)
+    ap.add_argument("--world-size", type=int, required=True)
+    ap.add_argument("--kwargs", default="{}")
+    a = ap.parse_args()
+    run_autotune_server(a.port, a.world_size, **json.loads(a.kwargs))
+
+
+if __name__ == "__main__":
+    _main()

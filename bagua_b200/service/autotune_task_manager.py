@@ -59,9 +59,15 @@ class AutotuneTaskManager:
         self.record_deque = collections.deque([(-1, BaguaHyperparameter(), float("-inf"))])
         self.autotune_logfile_path = None
         if need_to_log:
-            f = tempfile.NamedTemporaryFile(prefix="bagua_autotune_", mode="w", suffix=".log", delete=False)
-            self.autotune_logfile_path = f.name
-            f.close()
+            import os
+
+            fixed = os.environ.get("BAGUA_AUTOTUNE_LOG_FILE")   # CSV of (hyper-parameters tried, score); default: a temp file
+            if fixed:
+                self.autotune_logfile_path = fixed
+            else:
+                f = tempfile.NamedTemporaryFile(prefix="bagua_autotune_", mode="w", suffix=".log", delete=False)
+                self.autotune_logfile_path = f.name
+                f.close()
         self.bayesian_optimizer = BayesianOptimizer(
             {
                 "bucket_size_2p": IntParam(val=13, space_dimension=(10, 31)),  # 1 KiB … 2 GiB

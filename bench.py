@@ -82,52 +82,88 @@ def reference_arm(args):
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason sampler running for the duration of a timed region."""
+    """nvidia-smi clock / throttle-reason sampler.  ONE sampler runs for the whole process (nvidia-smi takes a moment to deliver
+    its first line, so a sampler started right before a 90 ms timed region can come back empty); every sample carries
+    nvidia-smi's own timestamp and ``region()`` / ``stop(begin, end)`` select the samples taken DURING a timed region."""
 
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.proc = None
         self.index = index
+        self._buf = []
+        self._thread = None
 
     def start(self):
+        import threading
+
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:  # noqa: BLE001
             self.proc = None
+            return self
+
+        def pump():
+            for line in self.proc.stdout:
+                self._buf.append(line)
+
+        self._thread = threading.Thread(target=pump, daemon=True)
+        self._thread.start()
         return self
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except Exception:  # noqa: BLE001
-            self.proc.kill()
-            out = ""
-        sm, mx, pw, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.strip().splitlines():
+    @staticmethod
+    def now() -> float:
+        import time
+
+        return time.time()
+
+    def _parse(self):
+        import datetime
+
+        rows = []
+        for line in list(self._buf):
             parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-                pw.append(float(parts[2]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[1]), float(parts[2]), float(parts[3]), parts[4:8]))
             except ValueError:
                 continue
-            for n, v in zip(names, parts[3:7]):
-                if v == "Active":
-                    reasons.add(n)
-        sm_sorted = sorted(sm)
-        under_load = sm_sorted[len(sm_sorted) // 2:] if len(sm_sorted) > 3 else sm_sorted  # samples taken under load: upper half
-        return {"sm_mhz": statistics.median(under_load) if under_load else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return rows
+
+    def summary(self, begin: float = None, end: float = None):
+        """Clock record of the samples with ``begin <= t <= end`` (host wall clock; all samples when omitted)."""
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        rows = self._parse()
+        sel = [r for r in rows if (begin is None or r[0] >= begin - 0.02) and (end is None or r[0] <= end + 0.02)]
+        note = None
+        if not sel and rows and begin is not None:   # region shorter than the sampling period: take the two nearest samples
+            sel = sorted(rows, key=lambda r: min(abs(r[0] - begin), abs(r[0] - end)))[:2]
+            note = "timed region shorter than the 20 ms sampling period: nearest samples"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in sel for n, v in zip(names, r[4]) if v == "Active"})
+        sm = sorted(r[1] for r in sel)
+        under_load = sm[len(sm) // 2:] if len(sm) > 3 else sm    # upper half: the samples under load
+        out = {"sm_mhz": statistics.median(under_load) if under_load else None, "sm_max_mhz": max((r[2] for r in sel), default=None),
+               "power_w_max": max((r[3] for r in sel), default=None), "reasons": reasons, "samples": len(sel)}
+        if note:
+            out["note"] = note
+        return out
+
+    def stop(self, begin: float = None, end: float = None):
+        out = self.summary(begin, end)
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
+        return out
 
 
 class Ctx:
@@ -205,7 +241,7 @@ def measure(c, name, train_step, dev_batch, host_batches, to_model_format, per_s
     args = c.args
     from bagua_b200.utils.data import DevicePrefetcher, LossReader
 
-    sampler = ClockSampler(c.local_rank).start() if (c.rank == 0 and not c.cpu) else None
+    sampler = getattr(c, "sampler", None)
     warm = max(args.warmup, 3)
     loss = None
     for _ in range(warm):
@@ -229,11 +265,13 @@ def measure(c, name, train_step, dev_batch, host_batches, to_model_format, per_s
     def one(_i):
         holder["loss"] = train_step(*dev_batch)
 
+    t_begin = ClockSampler.now()
     ms = c.timed(one, args.steps)
+    t_end = ClockSampler.now()
     if finish is not None:
         finish()
     launches = count() - n0
-    clocks = sampler.stop() if sampler is not None else None
+    clocks = sampler.summary(t_begin, t_end) if sampler is not None else None
     loss_val = float(holder["loss"].detach().float().item())     # the loss of the last timed step, read after the timed region
     if loss_val != loss_val or loss_val in (float("inf"), float("-inf")):
         raise SystemExit(f"{name}: non-finite loss {loss_val} after the timed region — the number would be a throughput of nothing")
@@ -506,6 +544,7 @@ def main():
 
     c = make_ctx(args)
     torch = c.torch
+    c.sampler = ClockSampler(c.local_rank).start() if (c.rank == 0 and not c.cpu) else None
     if args.impl == "ddp":
         if world > 1:
             c.dist.init_process_group("nccl" if not c.cpu else "gloo")
@@ -550,6 +589,8 @@ def main():
         out["config"]["self_peer_n1"] = os.environ.get("BAGUA_SELF_PEER", "0") == "1"
         if c.cpu:
             out["selftest"] = "host plumbing check, not a benchmark result"
+        if c.sampler is not None:
+            c.sampler.stop()
         sys.stdout.flush()
         os.dup2(saved_stdout_fd, 1)
         print(json.dumps(out), flush=True)

@@ -130,6 +130,7 @@ for _ in range(max(args.warmup, 3)):
 sync()
 if args.comm_report:
     model.bagua_ddp.comm_profile(True)
+t_begin = ClockSampler.now()
 if cuda:
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
@@ -145,6 +146,7 @@ else:
     for _ in range(args.steps):
         loss = step()
     ms = torch.tensor([(time.time() - t0) * 1e3])
+t_end = ClockSampler.now()
 if world > 1:
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 if cfg == "resnet50_async":
@@ -161,7 +163,7 @@ if rank == 0:
         "per_gpu_batch": bs, "dtype": str(dtype), "loss_finite": finite,
         "arm": "nccl-only" if os.environ.get("BAGUA_ALLREDUCE_VARIANT") == "nccl" else "peer-kernels",
         "moe_peer": os.environ.get("BAGUA_MOE_PEER", "1"), "steps": args.steps, "warmup": max(args.warmup, 3),
-        "clocks": sampler.stop() if sampler is not None else None, "final_loss": float(loss.detach().float().item()),
+        "clocks": sampler.stop(t_begin, t_end) if sampler is not None else None, "final_loss": float(loss.detach().float().item()),
         "timing": "CUDA events around the K steps on the launching stream, max over ranks; synthetic data, random-init weights",
     }))
 if world > 1:

@@ -198,3 +198,39 @@ def test_bagua_doctor_under_the_launcher_checks_the_collective_path(tmp_path):
                         "bagua_b200.script.bagua_doctor"], 180, env=env, cwd=str(tmp_path))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("[ok] all-reduce across the job: 2 ranks, backend gloo") == 2 and "FAIL" not in r.stdout
+
+
+def test_elastic_launcher_with_autotune_and_an_unguarded_script(tmp_path):
+    """``bagua_b200.distributed.run --standalone --autotune_level 1`` around a training script WITHOUT an ``if __name__ == "__main__"``
+    guard (the reference's CI line, .buildkite/scripts/benchmark.sh:14-37): the autotune service must run in its own interpreter
+    (a spawn-started multiprocessing child would re-import the script and hang in a second init_process_group) and be reachable
+    although the elastic launcher exports the node's hostname — not a routable address in a container — as MASTER_ADDR."""
+    from tests.mp_utils import run_in_session
+
+    script = tmp_path / "train.py"
+    script.write_text(textwrap.dedent(f"""
+        import sys
+        sys.path.insert(0, {REPO!r})
+        import torch, bagua_b200 as bagua
+        from bagua_b200.parallel.algorithms import gradient_allreduce
+        bagua.init_process_group()
+        assert bagua.communication.get_autotune_service_port() is not None
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(torch.nn.Linear(64, 256), torch.nn.ReLU(), torch.nn.Linear(256, 256), torch.nn.ReLU(), torch.nn.Linear(256, 8))
+        opt = torch.optim.SGD(model.parameters(), lr=0.01)
+        model = model.with_bagua([opt], gradient_allreduce.GradientAllReduceAlgorithm())
+        sizes = set()
+        for it in range(320):
+            opt.zero_grad(); model(torch.randn(4, 64)).pow(2).mean().backward(); opt.step()
+            sizes.add(model.bagua_ddp._bagua_hyperparameters.bucket_size)
+        sys.stdout.write(f"DONE {{bagua.get_rank()}} bucket sizes tried: {{len(sizes)}}" + chr(10)); sys.stdout.flush()
+    """))
+    env = dict(ENV)
+    for k in ("MASTER_ADDR", "MASTER_PORT", "RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    r = run_in_session([sys.executable, "-m", "bagua_b200.distributed.run", "--standalone", "--nnodes=1", "--nproc_per_node=2", f"--rdzv_endpoint=127.0.0.1:{_port()}",
+                        "--autotune_level", "1", "--autotune_warmup_time", "0", "--autotune_sampling_confidence_time", "0", "--autotune_max_samples", "2",
+                        f"--bagua_service_port={_port()}", str(script)], 240, env=env)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
+    done = [ln for ln in r.stdout.splitlines() if ln.startswith("DONE")]
+    assert len(done) == 2 and all(int(ln.rsplit(" ", 1)[1]) >= 2 for ln in done), done   # the service handed out new bucketings

@@ -595,6 +595,21 @@ def _exchange(t, peer):
     return got
 
 
+def _ring_exchange(t, left, right):
+    """Send ``t`` to both ring neighbours and receive theirs, as ONE batch (a send-to-left paired with a receive-from-left only
+    matches up on every rank when the world is 2)."""
+    import torch.distributed as dist
+
+    from_left, from_right = torch.empty_like(t), torch.empty_like(t)
+    if left == right:
+        ops = [dist.P2POp(dist.isend, t, left), dist.P2POp(dist.irecv, from_left, left)]
+    else:
+        ops = [dist.P2POp(dist.isend, t, left), dist.P2POp(dist.isend, t, right), dist.P2POp(dist.irecv, from_left, left), dist.P2POp(dist.irecv, from_right, right)]
+    for r in dist.batch_isend_irecv(ops):
+        r.wait()
+    return from_left, (from_left if left == right else from_right)
+
+
 def _decentralized_oracle_worker(rank, world, mode):
     import copy
 
@@ -689,11 +704,7 @@ def _lp_decentralized_oracle_worker(rank, world):
             xx = torch.cat([p.data.reshape(-1) for p in st["params"]])
             xx.add_(st["l"], alpha=1.0 / 3.0).add_(st["r"], alpha=1.0 / 3.0).sub_(st["w"], alpha=5.0 / 3.0)
             mm, q = quant.torch_compress_chunk(xx)
-            lmm, lq = _exchange(mm, left), _exchange(q, left)
-            if world > 2:
-                rmm, rq = _exchange(mm, right), _exchange(q, right)
-            else:
-                rmm, rq = lmm, lq
+            (lmm, rmm), (lq, rq) = _ring_exchange(mm, left, right), _ring_exchange(q, left, right)
             st["l"] += quant.torch_decompress_chunk(lmm, lq, xx.dtype)
             st["r"] += quant.torch_decompress_chunk(rmm, rq, xx.dtype)
             xx = st["w"] + quant.torch_decompress_chunk(mm, q, xx.dtype)

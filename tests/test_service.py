@@ -111,3 +111,34 @@ def test_system_autotune_measures_with_bagua_sys_perf():
     finally:
         os.environ.clear()
         os.environ.update(old)
+
+
+def test_service_picks_the_kernel_variant_per_bucket_from_the_measured_table():
+    """The workers hand the service the allreduce table they measured on their fabric; every bucket of every recommendation then
+    carries the variant / CTA count that was fastest at the calibrated size nearest (log scale) to the bucket's own bytes."""
+    world = 1
+    service = AutotuneService(world_size=world, autotune_level=1, max_samples=4, sampling_confidence_time_s=0.0, warmup_time_s=0.0, default_bucket_size=1 << 20)
+    port = find_free_network_port()
+    server = service.make_server("127.0.0.1", port)
+    threading.Thread(target=server.serve_forever, daemon=True).start()
+    client = AutotuneClient("127.0.0.1", port)
+    table = [{"bytes": 64 * 1024, "variant": "one_shot", "blocks": 4, "ms": 0.01, "busbw_GBs": 10.0},
+             {"bytes": 1 << 20, "variant": "multimem", "blocks": 8, "ms": 0.02, "busbw_GBs": 90.0},
+             {"bytes": 128 << 20, "variant": "two_shot", "blocks": 32, "ms": 0.3, "busbw_GBs": 700.0}]
+    tensors = [TensorDeclaration(name="small", num_elements=8 * 1024, dtype=TensorDtype.BF16),          # 16 KiB  -> one_shot
+               TensorDeclaration(name="mid", num_elements=1 << 20, dtype=TensorDtype.F32),              # 4 MiB   -> multimem
+               TensorDeclaration(name="big", num_elements=40 << 20, dtype=TensorDtype.F32)]             # 160 MiB -> two_shot
+    rsp = client.register_tensors("m", tensors, variant_table=table)
+    hp = rsp.json()["recommended_hyperparameters"]
+    by_first = {b[0]["name"]: (v, n) for b, v, n in zip(hp["buckets"], hp["bucket_variants"], hp["bucket_blocks"])}
+    assert by_first["small"] == ("one_shot", 4) and by_first["mid"] == ("multimem", 8) and by_first["big"] == ("two_shot", 32), by_first
+    # later recommendations (new bucket sizes from the optimiser) are annotated the same way
+    for it in (100, 200, 300):
+        client.report_metrics("m", 0, it, hp, speed=1.0)
+        hp = client.ask_hyperparameters("m", 0, it).json()["recommended_hyperparameters"]
+        assert len(hp["bucket_variants"]) == len(hp["buckets"]) or hp["allreduce_variant"] != "auto"
+    # a global variant chosen by the search wins over the table
+    mgr = service.model_dict["m"]
+    forced = BaguaHyperparameter().update(dict(hp, allreduce_variant="two_shot"))
+    assert service.apply_variant_table(mgr, forced).bucket_variants == []
+    server.shutdown()
