@@ -9,6 +9,7 @@ by every peer GPU, so a bucket's op is a single fused kernel (no staging copy, n
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, List, Optional
 
 import torch
@@ -357,7 +358,8 @@ class BaguaBucket:
                 inbox, outbox = eng.alloc(box), eng.alloc(box)
                 self._aux_slices += [inbox, outbox]
                 op = C.ByteGradOp(eng.comm, self.backend_tensor.data_ptr(), total, dtype_code(self.backend_tensor.dtype), inbox.buf, inbox.offset,
-                                  outbox.buf, outbox.offset, average, eng.launch_cfg("two_shot", total, 0 if n > 4 else 32))
+                                  outbox.buf, outbox.offset, average,
+                                  eng.launch_cfg("two_shot", total, int(os.environ.get("BAGUA_BYTEGRAD_BLOCKS", "0")) or (0 if n > 4 else 32)))
                 if momentum_source is not None:
                     gflat, beta1 = momentum_source
                     assert gflat.dtype == self.backend_tensor.dtype and gflat.numel() == total and gflat.is_contiguous()

@@ -150,7 +150,19 @@ __global__ void __launch_bounds__(512) bytegrad_kernel(PeerCtx ctx, T* data, siz
         const T* gsrc = grad ? grad + static_cast<size_t>(cj) * chunk : nullptr;
         const float omb = 1.0f - beta1;
         float mn = INFINITY, mx = -INFINITY;
-        for (size_t g = static_cast<size_t>(sb) * blockDim.x + threadIdx.x; g < groups; g += static_cast<size_t>(bpc) * blockDim.x) {
+        const size_t step = static_cast<size_t>(bpc) * blockDim.x;
+        size_t g = static_cast<size_t>(sb) * blockDim.x + threadIdx.x;
+        if (!gsrc) {
+            // read-only pass: two independent 32/64-byte groups in flight per thread (the loop is latency-bound, not bandwidth-bound)
+            for (; g + step < groups; g += 2 * step) {
+                float f0[16], f1[16];
+                load16<T>(src + g * 16, f0);
+                load16<T>(src + (g + step) * 16, f1);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) mn = fminf(mn, fminf(f0[k], f1[k])), mx = fmaxf(mx, fmaxf(f0[k], f1[k]));
+            }
+        }
+        for (; g < groups; g += step) {
             float f[16];
             load16<T>(src + g * 16, f);
             if (gsrc) {
@@ -179,7 +191,16 @@ __global__ void __launch_bounds__(512) bytegrad_kernel(PeerCtx ctx, T* data, siz
         const QuantParams q = make_quant(mn, mx);
         const T* src = data + static_cast<size_t>(cj) * chunk;
         char* dst = inbox.ptr[cj] + inbox_off + static_cast<size_t>(ctx.rank) * chunk_bytes;
-        for (size_t g = static_cast<size_t>(sb) * blockDim.x + threadIdx.x; g < groups; g += static_cast<size_t>(bpc) * blockDim.x) {
+        const size_t step = static_cast<size_t>(bpc) * blockDim.x;
+        size_t g = static_cast<size_t>(sb) * blockDim.x + threadIdx.x;
+        for (; g + step < groups; g += 2 * step) {
+            float f0[16], f1[16];
+            load16<T>(src + g * 16, f0);
+            load16<T>(src + (g + step) * 16, f1);
+            st_peer16(dst + 32 + g * 16, quantize16(f0, q));
+            st_peer16(dst + 32 + (g + step) * 16, quantize16(f1, q));
+        }
+        for (; g < groups; g += step) {
             float f[16];
             load16<T>(src + g * 16, f);
             st_peer16(dst + 32 + g * 16, quantize16(f, q));
@@ -260,9 +281,25 @@ __global__ void __launch_bounds__(512) bytegrad_kernel(PeerCtx ctx, T* data, siz
         for (int s = 0; s < P; ++s) {
             const QuantParams q = header_params<T>(mybox + static_cast<size_t>(s) * chunk_bytes);
             T* dst = data + static_cast<size_t>(s) * chunk;
-            for (size_t g = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < groups; g += static_cast<size_t>(nb) * blockDim.x) {
+            const size_t step = static_cast<size_t>(nb) * blockDim.x;
+            const char* payload = mybox + static_cast<size_t>(s) * chunk_bytes + 32;
+            size_t g = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+            for (; g + 3 * step < groups; g += 4 * step) {   // four independent 16-byte loads in flight per thread
+                uint4 r0 = ld_peer16(payload + g * 16), r1 = ld_peer16(payload + (g + step) * 16), r2 = ld_peer16(payload + (g + 2 * step) * 16),
+                      r3 = ld_peer16(payload + (g + 3 * step) * 16);
                 float f[16];
-                dequantize16(ld_peer16(mybox + static_cast<size_t>(s) * chunk_bytes + 32 + g * 16), q, f);
+                dequantize16(r0, q, f);
+                store16<T>(dst + g * 16, f);
+                dequantize16(r1, q, f);
+                store16<T>(dst + (g + step) * 16, f);
+                dequantize16(r2, q, f);
+                store16<T>(dst + (g + 2 * step) * 16, f);
+                dequantize16(r3, q, f);
+                store16<T>(dst + (g + 3 * step) * 16, f);
+            }
+            for (; g < groups; g += step) {
+                float f[16];
+                dequantize16(ld_peer16(payload + g * 16), q, f);
                 store16<T>(dst + g * 16, f);
             }
         }

@@ -47,16 +47,27 @@ __global__ void __launch_bounds__(kMoeThreads)
             char* d = dst.ptr[owner] + dst_off + drow * row_bytes;
             const char* src = reinterpret_cast<const char*>(rows_in) + static_cast<size_t>(s) * row_bytes;
             const float sc = scale ? scale[item] : 1.0f;
-            for (size_t v = lane; v < vec_per_row; v += 32) {
-                uint4 raw = ld_stream16(src + v * 16);
-                if (scale) {
-                    float f[Vec16<T>::N];
-                    Vec16<T>::unpack(raw, f);
+            // 4 independent 16-byte loads per lane before the first (NVLink) store: a row moves as 2 KB bursts, not 512 B round trips
+            for (size_t v0 = lane; v0 < vec_per_row; v0 += 32 * 4) {
+                uint4 raw[4];
 #pragma unroll
-                    for (int k = 0; k < Vec16<T>::N; ++k) f[k] *= sc;
-                    raw = Vec16<T>::pack(f);
+                for (int j = 0; j < 4; ++j) {
+                    const size_t v = v0 + static_cast<size_t>(j) * 32;
+                    if (v < vec_per_row) raw[j] = ld_stream16(src + v * 16);
                 }
-                st_peer16(d + v * 16, raw);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const size_t v = v0 + static_cast<size_t>(j) * 32;
+                    if (v >= vec_per_row) continue;
+                    if (scale) {
+                        float f[Vec16<T>::N];
+                        Vec16<T>::unpack(raw[j], f);
+#pragma unroll
+                        for (int k = 0; k < Vec16<T>::N; ++k) f[k] *= sc;
+                        raw[j] = Vec16<T>::pack(f);
+                    }
+                    st_peer16(d + v * 16, raw[j]);
+                }
             }
         }
         peer_barrier(ctx, e0 + 2);
@@ -81,14 +92,19 @@ __global__ void __launch_bounds__(kMoeThreads)
         const int nwarps = (gridDim.x * blockDim.x) >> 5;
         for (int s = warp; s < S; s += nwarps) {
             char* o = reinterpret_cast<char*>(out) + static_cast<size_t>(s) * row_bytes;
-            for (size_t v = lane; v < vec_per_row; v += 32) {
-                float acc[Vec16<T>::N];
+            for (size_t v0 = lane; v0 < vec_per_row; v0 += 32 * 4) {
+                float acc[4][Vec16<T>::N];
 #pragma unroll
-                for (int k = 0; k < Vec16<T>::N; ++k) acc[k] = 0.f;
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int q = 0; q < Vec16<T>::N; ++q) acc[j][q] = 0.f;
                 for (int k = 0; k < K; ++k) {
                     const int item = s * K + k;
                     const int64_t slot = slot_idx[item];
-                    uint4 raw = make_uint4(0, 0, 0, 0);
+                    uint4 raw[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) raw[j] = make_uint4(0, 0, 0, 0);
+                    float w = 0.f;
                     if (slot >= 0) {
                         const int64_t e = expert_idx[item];
                         const int owner = static_cast<int>(e / E_local);
@@ -98,16 +114,32 @@ __global__ void __launch_bounds__(kMoeThreads)
                         const int from = local_layout ? ctx.rank : owner;
                         const int major = local_layout ? owner : ctx.rank;
                         const size_t srow = (static_cast<size_t>(major) * E_local + el) * C + static_cast<size_t>(slot);
-                        raw = ld_peer16(src.ptr[from] + src_off + srow * row_bytes + v * 16);
-                        const float w = weights ? weights[item] : 1.0f;
-                        float f[Vec16<T>::N];
-                        Vec16<T>::unpack(raw, f);
+                        const char* rp = src.ptr[from] + src_off + srow * row_bytes;
+                        w = weights ? weights[item] : 1.0f;
 #pragma unroll
-                        for (int q = 0; q < Vec16<T>::N; ++q) acc[q] += w * f[q];
+                        for (int j = 0; j < 4; ++j) {   // four NVLink loads in flight per lane
+                            const size_t v = v0 + static_cast<size_t>(j) * 32;
+                            if (v < vec_per_row) raw[j] = ld_peer16(rp + v * 16);
+                        }
                     }
-                    if (picked) st_stream16(reinterpret_cast<char*>(picked) + static_cast<size_t>(item) * row_bytes + v * 16, raw);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const size_t v = v0 + static_cast<size_t>(j) * 32;
+                        if (v >= vec_per_row) continue;
+                        if (slot >= 0) {
+                            float f[Vec16<T>::N];
+                            Vec16<T>::unpack(raw[j], f);
+#pragma unroll
+                            for (int q = 0; q < Vec16<T>::N; ++q) acc[j][q] += w * f[q];
+                        }
+                        if (picked) st_stream16(reinterpret_cast<char*>(picked) + static_cast<size_t>(item) * row_bytes + v * 16, raw[j]);
+                    }
                 }
-                st_stream16(o + v * 16, Vec16<T>::pack(acc));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const size_t v = v0 + static_cast<size_t>(j) * 32;
+                    if (v < vec_per_row) st_stream16(o + v * 16, Vec16<T>::pack(acc[j]));
+                }
             }
         }
         peer_barrier(ctx, e0 + 2);  // owners may recycle their buffers only after every reader is done

@@ -102,24 +102,25 @@ def _peer_ctx(tokens: torch.Tensor, group, world: int):
     return moe_peer.get_context(group, world)
 
 
-def dispatch(tokens, expert_idx, slot_idx, num_experts: int, capacity: int, group, world: int, num_local_experts: int) -> torch.Tensor:
+def dispatch(tokens, expert_idx, slot_idx, num_experts: int, capacity: int, group, world: int, num_local_experts: int, key=None) -> torch.Tensor:
     """Route token rows to their experts' capacity slots: ``tokens [S, M]`` → ``[world, E_local, C, M]`` on the expert owners (peer scatter
     kernel on one NVSwitch node, dense one-hot + ``all_to_all_single`` otherwise).  Differentiable."""
     ctx = _peer_ctx(tokens, group, world)
     if ctx is not None:
-        return ctx.dispatch(tokens, expert_idx, slot_idx, num_experts, capacity, num_local_experts)
+        # key (one per MoE layer): the layer owns its receive buffer and uses the rows in place — no staging copy (ops/moe_peer.py)
+        return ctx.dispatch(tokens, expert_idx, slot_idx, num_experts, capacity, num_local_experts, key=key)
     flat = _flat_slots(expert_idx, slot_idx, capacity)
     rows = _ScatterRows.apply(tokens, flat, num_experts * capacity)            # [E_total*C, M]
     rows = _AllToAll.apply(rows.view(num_experts, capacity, -1), group, world)  # chunks of E_local experts per rank
     return rows.reshape(world, num_local_experts, capacity, -1)
 
 
-def combine(expert_out, expert_idx, slot_idx, weights, num_experts: int, capacity: int, group, world: int, num_local_experts: int) -> torch.Tensor:
+def combine(expert_out, expert_idx, slot_idx, weights, num_experts: int, capacity: int, group, world: int, num_local_experts: int, key=None) -> torch.Tensor:
     """Inverse of :func:`dispatch`: fetch every token's expert outputs and sum them with the gate ``weights`` → ``[S, M]``.  Differentiable
     in ``expert_out`` and ``weights``."""
     ctx = _peer_ctx(expert_out, group, world)
     if ctx is not None:
-        return ctx.combine(expert_out, expert_idx, slot_idx, weights, num_experts, capacity, num_local_experts)
+        return ctx.combine(expert_out, expert_idx, slot_idx, weights, num_experts, capacity, num_local_experts, key=key)
     rows = _AllToAll.apply(expert_out.reshape(num_experts, capacity, -1), group, world)
     flat = _flat_slots(expert_idx, slot_idx, capacity)
     return _GatherRows.apply(rows.reshape(num_experts * capacity, -1), flat, weights)

@@ -39,25 +39,35 @@ class MoEPeerContext:
         self._buffers: Dict[int, tuple] = {}
         self.blocks = int(os.environ.get("BAGUA_MOE_BLOCKS", "64"))
 
-    def _buf(self, nbytes: int, which: int):
-        pair = self._buffers.get(nbytes)
+    def _buf(self, nbytes: int, which: int, key=None):
+        """Symmetric buffer for an exchange.  ``key is None``: the pair shared by every call site of this size (results must be
+        copied out before the next exchange).  With a ``key`` (one per MoE layer and direction) the call site OWNS its buffer —
+        16 MiB per layer for GPT-2-medium MoE-8, nothing next to 180 GB — so the received rows are used in place: no ``clone``
+        behind the scatter.  Reuse is safe across iterations: a layer's next scatter opens with a cross-GPU barrier that every rank
+        reaches only after (stream order) it has finished the previous iteration's backward, the last reader of the buffer."""
+        pair = self._buffers.get((nbytes, key))
         if pair is None:
-            pair = (self.engine.alloc(nbytes), self.engine.alloc(nbytes))  # collective: identical call sequence on all ranks
-            self._buffers[nbytes] = pair
+            if key is None:
+                pair = (self.engine.alloc(nbytes), self.engine.alloc(nbytes))  # collective: identical call sequence on all ranks
+            else:
+                one = self.engine.alloc(nbytes)
+                pair = (one, one)
+            self._buffers[(nbytes, key)] = pair
         return pair[which]
 
     # -- raw kernels ------------------------------------------------------------------------------------------------------
-    def scatter(self, rows: torch.Tensor, expert_idx, slot_idx, scale: Optional[torch.Tensor], E_local: int, C: int) -> torch.Tensor:
-        """rows[S, M] → local view [world, E_local, C, M] of what every rank sent to my experts."""
+    def scatter(self, rows: torch.Tensor, expert_idx, slot_idx, scale: Optional[torch.Tensor], E_local: int, C: int, key=None) -> torch.Tensor:
+        """rows[S, M] → local view [world, E_local, C, M] of what every rank sent to my experts (``key``: see :meth:`_buf`)."""
         S, M = rows.shape
         K = expert_idx.shape[1]
         nbytes = self.world * E_local * C * M * rows.element_size()
-        buf = self._buf(nbytes, 0)
+        buf = self._buf(nbytes, 0, key)
         rows = rows.contiguous()
         native().moe_scatter(self.comm, buf.buf, buf.offset, rows.data_ptr(), expert_idx.data_ptr(), slot_idx.data_ptr(),
                              scale.data_ptr() if scale is not None else 0, S, K, M, E_local, C, dtype_code(rows.dtype), self.blocks,
                              torch.cuda.current_stream().cuda_stream)
-        return buf.view(rows.dtype, self.world * E_local * C * M).view(self.world, E_local, C, M).clone()
+        out = buf.view(rows.dtype, self.world * E_local * C * M).view(self.world, E_local, C, M)
+        return out if key is not None else out.clone()
 
     def gather(self, owner_rows: torch.Tensor, expert_idx, slot_idx, weights: Optional[torch.Tensor], S: int, keep_rows: bool,
                E_local: int, C: int) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
@@ -101,34 +111,35 @@ class MoEPeerContext:
                 and os.environ.get("BAGUA_MOE_FUSED_COMBINE", "0") == "1")
 
     # -- autograd ------------------------------------------------------------------------------------------------------
-    def dispatch(self, tokens, expert_idx, slot_idx, num_experts: int, capacity: int, num_local_experts: int):
-        return _Dispatch.apply(tokens, expert_idx.contiguous(), slot_idx.contiguous(), self, num_local_experts, capacity)
+    def dispatch(self, tokens, expert_idx, slot_idx, num_experts: int, capacity: int, num_local_experts: int, key=None):
+        return _Dispatch.apply(tokens, expert_idx.contiguous(), slot_idx.contiguous(), self, num_local_experts, capacity, key)
 
-    def combine(self, expert_out, expert_idx, slot_idx, weights, num_experts: int, capacity: int, num_local_experts: int):
-        return _Combine.apply(expert_out, weights, expert_idx.contiguous(), slot_idx.contiguous(), self, num_local_experts, capacity)
+    def combine(self, expert_out, expert_idx, slot_idx, weights, num_experts: int, capacity: int, num_local_experts: int, key=None):
+        return _Combine.apply(expert_out, weights, expert_idx.contiguous(), slot_idx.contiguous(), self, num_local_experts, capacity, key)
 
 
 class _Dispatch(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, tokens, expert_idx, slot_idx, pctx: MoEPeerContext, E_local: int, C: int):
+    def forward(ctx, tokens, expert_idx, slot_idx, pctx: MoEPeerContext, E_local: int, C: int, key=None):
         ctx.pctx, ctx.E_local, ctx.C, ctx.S = pctx, E_local, C, tokens.shape[0]
         ctx.save_for_backward(expert_idx, slot_idx)
-        return pctx.scatter(tokens, expert_idx, slot_idx, None, E_local, C)
+        return pctx.scatter(tokens, expert_idx, slot_idx, None, E_local, C, key=(key, "dispatch") if key is not None else None)
 
     @staticmethod
     def backward(ctx, grad_dispatched):
         expert_idx, slot_idx = ctx.saved_tensors
         g, _ = ctx.pctx.gather(grad_dispatched.contiguous(), expert_idx, slot_idx, None, ctx.S, False, ctx.E_local, ctx.C)
-        return g, None, None, None, None, None
+        return g, None, None, None, None, None, None
 
 
 class _Combine(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, expert_out, weights, expert_idx, slot_idx, pctx: MoEPeerContext, E_local: int, C: int):
+    def forward(ctx, expert_out, weights, expert_idx, slot_idx, pctx: MoEPeerContext, E_local: int, C: int, key=None):
         S = expert_idx.shape[0]
         w32 = weights.float().contiguous()
         out, picked = pctx.gather(expert_out.contiguous(), expert_idx, slot_idx, w32, S, True, E_local, C)
         ctx.pctx, ctx.E_local, ctx.C = pctx, E_local, C
+        ctx.key = key
         ctx.wdtype = weights.dtype
         ctx.save_for_backward(expert_idx, slot_idx, w32, picked)
         return out
@@ -139,8 +150,9 @@ class _Combine(torch.autograd.Function):
         grad_out = grad_out.contiguous()
         valid = (slot_idx >= 0).to(torch.float32)
         grad_w = (picked.float() * grad_out.float().unsqueeze(1)).sum(-1) * valid
-        grad_rows = ctx.pctx.scatter(grad_out, expert_idx, slot_idx, (w32 * valid).contiguous(), ctx.E_local, ctx.C)
-        return grad_rows, grad_w.to(ctx.wdtype), None, None, None, None, None
+        grad_rows = ctx.pctx.scatter(grad_out, expert_idx, slot_idx, (w32 * valid).contiguous(), ctx.E_local, ctx.C,
+                                     key=(ctx.key, "combine_bwd") if ctx.key is not None else None)
+        return grad_rows, grad_w.to(ctx.wdtype), None, None, None, None, None, None
 
 
 class _LinearCombine(torch.autograd.Function):

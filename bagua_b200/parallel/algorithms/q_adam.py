@@ -142,6 +142,10 @@ class QAdamAlgorithmImpl(AlgorithmImpl):
 
     def tensors_to_buckets(self, tensors: List[List[torch.Tensor]], do_flatten: bool) -> List[BaguaBucket]:
         n = self.process_group.size()
+        if self._compressing():
+            from .bytegrad import bytegrad_min_bucket_bytes, merge_small_buckets
+
+            tensors = merge_small_buckets(tensors, bytegrad_min_bucket_bytes(tensors))   # fixed cost per quantised exchange: see bytegrad.py
         return [BaguaBucket(b, flatten=do_flatten, name=str(i), alignment=32 * n, group=self.process_group) for i, b in enumerate(tensors)]
 
     def init_operations(self, bagua_ddp, bucket: BaguaBucket):

@@ -203,6 +203,15 @@ class MOELayer(torch.nn.Module):
         self.l_aux = None
         self.exp_counts = None
 
+    def _recv_key(self):
+        """Identity of this layer's private receive buffers (NVSwitch path): the dispatched rows are used in place, so ONE forward of
+        this layer may be outstanding per backward — true of ordinary training loops, activation recomputation and gradient
+        accumulation.  ``BAGUA_MOE_INPLACE_RECV=0`` restores the shared buffer + copy for exotic schedules (two forwards, then
+        two backwards)."""
+        import os
+
+        return id(self) if os.environ.get("BAGUA_MOE_INPLACE_RECV", "1") == "1" else None
+
     def forward(self, *input: Tensor, **kwargs: Any) -> Tensor:
         x = input[0]
         used_token = input[1] if len(input) > 1 else None
@@ -212,12 +221,12 @@ class MOELayer(torch.nn.Module):
         self.l_aux, self.exp_counts = g.l_aux, g.exp_counts
         # [E_total, C, M] rows land on the rank owning the expert: [world(src), E_local, C, M]
         dispatched = moe_ops.dispatch(tokens, g.expert_idx, g.slot_idx, g.num_experts, g.capacity, self.group, self.world_size,
-                                      self.num_local_experts)
+                                      self.num_local_experts, key=self._recv_key())
         fused = self.experts.fused_combine_context(dispatched, self.group, self.world_size) if hasattr(self.experts, "fused_combine_context") else None
         if fused is not None:
             combined = self.experts.forward_combine(dispatched, g.weights.to(x.dtype), g.expert_idx, g.slot_idx, fused)
             return combined.reshape(x.shape)
         expert_out = self.experts(dispatched)
         combined = moe_ops.combine(expert_out, g.expert_idx, g.slot_idx, g.weights.to(x.dtype), g.num_experts, g.capacity, self.group,
-                                   self.world_size, self.num_local_experts)
+                                   self.world_size, self.num_local_experts, key=self._recv_key())
         return combined.reshape(x.shape)

@@ -20,13 +20,16 @@ class DevicePrefetcher:
         self.transform = transform
         self.on_cuda = torch.device(device).type == "cuda"
         self.stream = torch.cuda.Stream(device=device) if self.on_cuda else None
+        self._events = [torch.cuda.Event() for _ in range(4)] if self.on_cuda else []   # recycled: at most two batches are in flight
+        self._n = 0
 
     def _stage(self, batch):
         with torch.cuda.stream(self.stream):
             moved = tuple(t.to(self.device, non_blocking=True) for t in batch)
             if self.transform is not None:
                 moved = self.transform(*moved)
-            ev = torch.cuda.Event()
+            ev = self._events[self._n % len(self._events)]
+            self._n += 1
             ev.record(self.stream)
         return moved, ev
 

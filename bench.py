@@ -431,8 +431,11 @@ def run_cnn(c, model_name):
         step_fn(x_dev, y_dev)
 
     def to_model_format(x, y):
-        x = x.to(dtype)
-        return (x.contiguous(memory_format=torch.channels_last) if not cpu else x), y
+        if cpu:
+            return x.to(dtype), y
+        out = torch.empty(x.shape, dtype=dtype, device=x.device, memory_format=torch.channels_last)
+        out.copy_(x)                      # fp32 NCHW → bf16 NHWC in ONE kernel on the prefetch stream
+        return out, y
 
     def host_batches(n):
         for i in range(n):
