@@ -66,8 +66,14 @@ class MoEPeerContext:
         native().moe_scatter(self.comm, buf.buf, buf.offset, rows.data_ptr(), expert_idx.data_ptr(), slot_idx.data_ptr(),
                              scale.data_ptr() if scale is not None else 0, S, K, M, E_local, C, dtype_code(rows.dtype), self.blocks,
                              torch.cuda.current_stream().cuda_stream)
-        out = buf.view(rows.dtype, self.world * E_local * C * M).view(self.world, E_local, C, M)
-        return out if key is not None else out.clone()
+        if key is None:
+            return buf.view(rows.dtype, self.world * E_local * C * M).view(self.world, E_local, C, M).clone()
+        # in-place use of the layer's own receive buffer: a tensor over the same bytes with its OWN autograd version counter (every
+        # slice of a slab is a view of one base tensor, so an in-place torch op on any other slice would otherwise mark these rows,
+        # which autograd saves for the expert GEMMs' backward, as "modified")
+        raw = buf.tensor
+        es = rows.element_size()
+        return torch.empty(0, dtype=rows.dtype, device=rows.device).set_(raw.untyped_storage(), raw.storage_offset() // es, (self.world, E_local, C, M))
 
     def gather(self, owner_rows: torch.Tensor, expert_idx, slot_idx, weights: Optional[torch.Tensor], S: int, keep_rows: bool,
                E_local: int, C: int) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
