@@ -12,6 +12,7 @@
 #include <stdexcept>
 #include <string>
 
+#include "bulk_pipe.cuh"
 #include "kernels.h"
 #include "peer.cuh"
 #include "quant.cuh"
@@ -120,11 +121,20 @@ __device__ __forceinline__ uint32_t* mm_slot(const ByteGradScratch& s, int parit
     return reinterpret_cast<uint32_t*>(s.minmax) + (static_cast<size_t>(parity) * (kMaxPeers + 1) + idx) * 2;
 }
 
+constexpr int kBgStages = 4;
+constexpr int kBgTile = 16384;
+
 template <typename T, int P>
 __global__ void __launch_bounds__(512) bytegrad_kernel(PeerCtx ctx, T* data, size_t chunk, PeerBuf inbox, size_t inbox_off,
                                                        PeerBuf outbox, size_t outbox_off, ByteGradScratch scratch,
                                                        unsigned long long seq, unsigned long long gb_base, int average,
                                                        const T* grad, float beta1) {
+    // The three passes over the whole bucket (A: min/max, B: quantise + send, E: dequantise) stream their input through the TMA
+    // bulk-copy engine into shared memory (bulk_pipe.cuh): 48 KB in flight per CTA without spending registers on it.
+    extern __shared__ __align__(128) unsigned char bg_smem[];
+    using Reader = BulkReader<kBgStages, kBgTile>;
+    Reader rd;
+    rd.init(bg_smem, ctx);
     const int parity = static_cast<int>(seq & 1ULL);
     const int nb = gridDim.x;
     const int bpc = nb / P;  // blocks per chunk in the scatter phases (host guarantees nb % P == 0)
@@ -153,14 +163,21 @@ __global__ void __launch_bounds__(512) bytegrad_kernel(PeerCtx ctx, T* data, siz
         const size_t step = static_cast<size_t>(bpc) * blockDim.x;
         size_t g = static_cast<size_t>(sb) * blockDim.x + threadIdx.x;
         if (!gsrc) {
-            // read-only pass: two independent 32/64-byte groups in flight per thread (the loop is latency-bound, not bandwidth-bound)
-            for (; g + step < groups; g += 2 * step) {
-                float f0[16], f1[16];
-                load16<T>(src + g * 16, f0);
-                load16<T>(src + (g + step) * 16, f1);
+            // read-only pass over my share of chunk cj (tiles sb, sb + bpc, ...), fed by the bulk-copy pipeline
+            rd.start(src, chunk * sizeof(T), static_cast<size_t>(sb), static_cast<size_t>(bpc));
+            const unsigned char* tile;
+            uint32_t n;
+            size_t off;
+            while (rd.next(tile, n, off)) {
+                for (uint32_t v = threadIdx.x * 16u; v < n; v += blockDim.x * 16u) {
+                    float f[Vec16<T>::N];
+                    Vec16<T>::unpack(lds16(tile + v), f);
 #pragma unroll
-                for (int k = 0; k < 16; ++k) mn = fminf(mn, fminf(f0[k], f1[k])), mx = fmaxf(mx, fmaxf(f0[k], f1[k]));
+                    for (int k = 0; k < Vec16<T>::N; ++k) mn = fminf(mn, f[k]), mx = fmaxf(mx, f[k]);
+                }
+                rd.release();
             }
+            g = groups;   // nothing left for the per-thread loop below
         }
         for (; g < groups; g += step) {
             float f[16];
@@ -191,19 +208,21 @@ __global__ void __launch_bounds__(512) bytegrad_kernel(PeerCtx ctx, T* data, siz
         const QuantParams q = make_quant(mn, mx);
         const T* src = data + static_cast<size_t>(cj) * chunk;
         char* dst = inbox.ptr[cj] + inbox_off + static_cast<size_t>(ctx.rank) * chunk_bytes;
-        const size_t step = static_cast<size_t>(bpc) * blockDim.x;
-        size_t g = static_cast<size_t>(sb) * blockDim.x + threadIdx.x;
-        for (; g + step < groups; g += 2 * step) {
-            float f0[16], f1[16];
-            load16<T>(src + g * 16, f0);
-            load16<T>(src + (g + step) * 16, f1);
-            st_peer16(dst + 32 + g * 16, quantize16(f0, q));
-            st_peer16(dst + 32 + (g + step) * 16, quantize16(f1, q));
-        }
-        for (; g < groups; g += step) {
-            float f[16];
-            load16<T>(src + g * 16, f);
-            st_peer16(dst + 32 + g * 16, quantize16(f, q));
+        constexpr uint32_t GB = 16 * sizeof(T);   // bytes of one 16-element group in the tile
+        // (with a momentum source phase A rewrote the bucket with generic stores from other CTAs: cross-proxy fence before the bulk reads)
+        rd.start(src, chunk * sizeof(T), static_cast<size_t>(sb), static_cast<size_t>(bpc), grad != nullptr);
+        const unsigned char* tile;
+        uint32_t n;
+        size_t off;
+        while (rd.next(tile, n, off)) {
+            const size_t e0 = off / sizeof(T);   // first element of this tile within the chunk
+            for (uint32_t gi = threadIdx.x; gi * GB < n; gi += blockDim.x) {
+                float f[16];
+#pragma unroll
+                for (uint32_t w = 0; w < GB / 16; ++w) Vec16<T>::unpack(lds16(tile + gi * GB + w * 16), f + w * Vec16<T>::N);
+                st_peer16(dst + 32 + e0 + static_cast<size_t>(gi) * 16, quantize16(f, q));
+            }
+            rd.release();
         }
         if (sb == 0 && threadIdx.x == 0) write_header<T>(dst, mn, mx);
     }
@@ -281,26 +300,18 @@ __global__ void __launch_bounds__(512) bytegrad_kernel(PeerCtx ctx, T* data, siz
         for (int s = 0; s < P; ++s) {
             const QuantParams q = header_params<T>(mybox + static_cast<size_t>(s) * chunk_bytes);
             T* dst = data + static_cast<size_t>(s) * chunk;
-            const size_t step = static_cast<size_t>(nb) * blockDim.x;
-            const char* payload = mybox + static_cast<size_t>(s) * chunk_bytes + 32;
-            size_t g = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-            for (; g + 3 * step < groups; g += 4 * step) {   // four independent 16-byte loads in flight per thread
-                uint4 r0 = ld_peer16(payload + g * 16), r1 = ld_peer16(payload + (g + step) * 16), r2 = ld_peer16(payload + (g + 2 * step) * 16),
-                      r3 = ld_peer16(payload + (g + 3 * step) * 16);
-                float f[16];
-                dequantize16(r0, q, f);
-                store16<T>(dst + g * 16, f);
-                dequantize16(r1, q, f);
-                store16<T>(dst + (g + step) * 16, f);
-                dequantize16(r2, q, f);
-                store16<T>(dst + (g + 2 * step) * 16, f);
-                dequantize16(r3, q, f);
-                store16<T>(dst + (g + 3 * step) * 16, f);
-            }
-            for (; g < groups; g += step) {
-                float f[16];
-                dequantize16(ld_peer16(payload + g * 16), q, f);
-                store16<T>(dst + g * 16, f);
+            // the payload was written by peer GPUs during this kernel (ordered by the barriers above): async-proxy reads need the fence
+            rd.start(mybox + static_cast<size_t>(s) * chunk_bytes + 32, chunk, static_cast<size_t>(blockIdx.x), static_cast<size_t>(nb), true);
+            const unsigned char* tile;
+            uint32_t n;
+            size_t off;
+            while (rd.next(tile, n, off)) {
+                for (uint32_t v = threadIdx.x * 16u; v < n; v += blockDim.x * 16u) {
+                    float f[16];
+                    dequantize16(lds16(tile + v), q, f);
+                    store16<T>(dst + off + v, f);
+                }
+                rd.release();
             }
         }
     }
@@ -461,22 +472,22 @@ static bool use_cooperative() {
     return on;
 }
 template <typename K>
-static int clamp_grid_to_residency(K kernel, int nblocks, int nthreads, int multiple_of) {
+static int clamp_grid_to_residency(K kernel, int nblocks, int nthreads, int multiple_of, size_t smem = 0) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nthreads, 0) != cudaSuccess || per_sm < 1 || sms < 1) return nblocks;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nthreads, smem) != cudaSuccess || per_sm < 1 || sms < 1) return nblocks;
     int cap = per_sm * sms;
     if (nblocks > cap) nblocks = cap / multiple_of * multiple_of;
     return nblocks < multiple_of ? multiple_of : nblocks;
 }
 template <typename K>
-static void launch_grid_synced(K kernel, int nblocks, int nthreads, cudaStream_t stream, void** args) {
+static void launch_grid_synced(K kernel, int nblocks, int nthreads, cudaStream_t stream, void** args, size_t smem = 0) {
     if (use_cooperative()) {
-        cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(nblocks), dim3(nthreads), args, 0, stream);
+        cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(nblocks), dim3(nthreads), args, smem, stream);
         if (e != cudaSuccess) throw std::runtime_error(std::string("bagua: cooperative launch failed: ") + cudaGetErrorString(e));
     } else {
-        cudaError_t e = cudaLaunchKernel(reinterpret_cast<const void*>(kernel), dim3(nblocks), dim3(nthreads), args, 0, stream);
+        cudaError_t e = cudaLaunchKernel(reinterpret_cast<const void*>(kernel), dim3(nblocks), dim3(nthreads), args, smem, stream);
         if (e != cudaSuccess) throw std::runtime_error(std::string("bagua: launch failed: ") + cudaGetErrorString(e));
     }
 }
@@ -493,7 +504,14 @@ void launch_bytegrad(const PeerCtx& ctx, void* data, size_t numel, int dtype, co
         dispatch_world(P, [&](auto pw) {
             constexpr int PP = decltype(pw)::value;
             auto kernel = bytegrad_kernel<T, PP>;
-            const int nb = clamp_grid_to_residency(kernel, nblocks, nthreads, P);
+            constexpr size_t smem = BulkReader<kBgStages, kBgTile>::smem_bytes();
+            static bool attr_set = false;   // per instantiation (this lambda body is instantiated per <T, PP>)
+            if (!attr_set) {
+                cudaError_t ae = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+                if (ae != cudaSuccess) throw std::runtime_error(std::string("bagua: bytegrad shared-memory opt-in failed: ") + cudaGetErrorString(ae));
+                attr_set = true;
+            }
+            const int nb = clamp_grid_to_residency(kernel, nblocks, nthreads, P, smem);
             unsigned long long seq, base;
             next_launch(scratch, 4, nb, seq, base);
             PeerCtx c = ctx;
@@ -503,7 +521,7 @@ void launch_bytegrad(const PeerCtx& ctx, void* data, size_t numel, int dtype, co
             int avg = average ? 1 : 0;
             const T* g = static_cast<const T*>(grad);
             void* args[] = {&c, &d, &chunk, &in, &inbox_off, &out, &outbox_off, &sc, &seq, &base, &avg, &g, &beta1};
-            launch_grid_synced(kernel, nb, nthreads, stream, args);
+            launch_grid_synced(kernel, nb, nthreads, stream, args, smem);
         });
     });
     check("bytegrad");

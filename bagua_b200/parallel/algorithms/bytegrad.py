@@ -12,10 +12,11 @@ __all__ = ["ByteGradAlgorithm", "ByteGradAlgorithmImpl"]
 
 
 def bytegrad_min_bucket_bytes(tensors) -> int:
-    """Lower bound on a ByteGrad bucket on GPUs (``BAGUA_BYTEGRAD_MIN_BUCKET_BYTES``, default 64 MiB; 0 on the host).  Every quantised
+    """Lower bound on a ByteGrad bucket on GPUs (``BAGUA_BYTEGRAD_MIN_BUCKET_BYTES``, default 32 MiB; 0 on the host).  Every quantised
     exchange — the fused kernel as well as the 7-step torch.distributed pipeline — has a fixed cost per bucket (four grid-wide and two
-    cross-GPU rendezvous in the kernel; 2·P+7 launches and two collectives in the pipeline) that dwarfs the transfer of a 10 MiB
-    bucket on NVSwitch: measured on BERT-large, 64 buckets of 10 MiB cost 12 ms of kernel time per step, 6 buckets of 64 MiB a third."""
+    cross-GPU rendezvous in the kernel; 2·P+7 launches and two collectives in the pipeline) that does not shrink with the bucket, while
+    NVSwitch moves 10 MiB in microseconds.  Measured on BERT-large, 1 GPU (profiles/r2/bytegrad_tuning_n1.md): 48 buckets of 10 MiB and
+    17 of 32 MiB train at the same speed with 64 CTAs (304 samples/s); the merge pays where the rendezvous cross GPUs."""
     import os
 
     try:
@@ -23,7 +24,7 @@ def bytegrad_min_bucket_bytes(tensors) -> int:
         on_gpu = first.is_cuda
     except Exception:  # noqa: BLE001
         on_gpu = False
-    return int(os.environ.get("BAGUA_BYTEGRAD_MIN_BUCKET_BYTES", str(64 * 1024 ** 2 if on_gpu else 0)))
+    return int(os.environ.get("BAGUA_BYTEGRAD_MIN_BUCKET_BYTES", str(32 * 1024 ** 2 if on_gpu else 0)))
 
 
 def merge_small_buckets(tensors: List[List[torch.Tensor]], min_bytes: int) -> List[List[torch.Tensor]]:

@@ -206,8 +206,11 @@ def make_ctx(args):
             if c.world > 1:
                 dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             return float(ms.item())
+        import time
+
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.nvtx.range_push("timed")
+        h0 = time.perf_counter()
         start.record()
         if whole_loop:
             fn(steps)
@@ -215,6 +218,7 @@ def make_ctx(args):
             for i in range(steps):
                 fn(i)
         end.record()
+        c.last_host_ms = (time.perf_counter() - h0) * 1e3   # time the host needed to ISSUE the steps (diagnostic: ~= the device time when launch-bound)
         torch.cuda.nvtx.range_pop()
         torch.cuda.synchronize()
         ms = torch.tensor([start.elapsed_time(end)], device=c.dev)
@@ -271,6 +275,8 @@ def measure(c, name, train_step, dev_batch, host_batches, to_model_format, per_s
     if finish is not None:
         finish()
     launches = count() - n0
+    host_ms = getattr(c, "last_host_ms", None)
+    host_ms = host_ms / args.steps if host_ms is not None else None
     clocks = sampler.summary(t_begin, t_end) if sampler is not None else None
     loss_val = float(holder["loss"].detach().float().item())     # the loss of the last timed step, read after the timed region
     if loss_val != loss_val or loss_val in (float("inf"), float("-inf")):
@@ -296,7 +302,8 @@ def measure(c, name, train_step, dev_batch, host_batches, to_model_format, per_s
                    "ms_per_step": ms_e2e / args.steps, "last_loss": reader.last}
         except Exception as exc:  # noqa: BLE001 - the device-timed number above must still be reported
             e2e = {"error": f"{type(exc).__name__}: {exc}"}
-    return {"value": value, "unit": unit, "ms_per_step": ms / args.steps, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "final_loss": loss_val}
+    return {"value": value, "unit": unit, "ms_per_step": ms / args.steps, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "final_loss": loss_val,
+            "host_issue_ms_per_step": host_ms}
 
 
 def verify_fused_update(c, build_model, fused_model, optimizer, batch, loss_fn, lr, steps=2):
@@ -578,13 +585,14 @@ def main():
             "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if not c.cpu else "fp32", "data": "synthetic (random batches of the named shapes, random-init weights)", "impl": args.impl,
             "config": head["config"], "clocks": head["clocks"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
+            "host_issue_ms_per_step": head.get("host_issue_ms_per_step"),
             "published_context": PUBLISHED_CONTEXT,
         }
         if "verify" in head:
             out["verify"] = head["verify"]
         if "bert" in results and head is not results["bert"]:
             b = results["bert"]
-            out["bert_large_bytegrad"] = {k: b[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "clocks", "e2e", "gpu_launches", "final_loss")}
+            out["bert_large_bytegrad"] = {k: b[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "clocks", "e2e", "gpu_launches", "final_loss", "host_issue_ms_per_step")}
             out["bert_large_bytegrad"].update(n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), higher_is_better=True, scaling="weak", dtype=out["dtype"])
         for k, v in results.items():
             if v is not head and k != "bert":
