@@ -48,64 +48,53 @@ class LoadBalancingDistributedSampler(Sampler):
             if not dist.is_available() or not dist.is_initialized():
                 raise RuntimeError("Requires distributed package to be available")
             rank = dist.get_rank()
-        if rank >= num_replicas or rank < 0:
+        if not 0 <= rank < num_replicas:
             raise ValueError(f"Invalid rank {rank}, rank should be in the interval [0, {num_replicas - 1}]")
-        if random_level < 0.0 or random_level > 1.0:
-            raise ValueError(f"Invalid random level {random_level}, shoule be in the range [0.0, 1.0]")
+        if not 0.0 <= random_level <= 1.0:
+            raise ValueError(f"random_level must lie in [0.0, 1.0], got {random_level}")
         self.dataset = dataset
         self.num_replicas = num_replicas
         self.rank = rank
         self.epoch = 0
         self.drop_last = drop_last
-        n = len(dataset)  # type: ignore[arg-type]
-        if self.drop_last and n % num_replicas != 0:
-            self.num_samples = math.ceil((n - num_replicas) / num_replicas)
-        else:
-            self.num_samples = math.ceil(n / num_replicas)
-        self.total_size = self.num_samples * num_replicas
         self.shuffle = shuffle
         self.seed = seed
-        self.complexities = np.asarray([complexity_fn(dataset[i]) for i in range(n)], dtype=np.int64)
-        self.item_complexity_map = {i: int(c) for i, c in enumerate(self.complexities)}
-        self._sorted_indices = np.argsort(self.complexities, kind="stable")
-        span = int(self.complexities.max() - self.complexities.min()) if n else 0
-        self.random_number = int(span * random_level + 1)
+        n = len(dataset)  # type: ignore[arg-type]
+        rows = (n - num_replicas) / num_replicas if (drop_last and n % num_replicas) else n / num_replicas
+        self.num_samples = math.ceil(rows)                 # steps per epoch = rows of the epoch plan
+        self.total_size = self.num_samples * num_replicas
+        # complexities are evaluated once; an epoch only re-sorts (jittered) keys
+        self.complexities = np.fromiter((complexity_fn(dataset[i]) for i in range(n)), dtype=np.int64, count=n)
+        self.item_complexity_map = dict(enumerate(self.complexities.tolist()))
+        self._by_cost = np.argsort(self.complexities, kind="stable")
+        spread = int(np.ptp(self.complexities)) if n else 0
+        self.random_number = int(spread * random_level + 1)    # exclusive upper bound of the per-epoch jitter
 
-    def _chunks(self, ordered: np.ndarray) -> np.ndarray:
-        """[num_chunks, num_replicas] index matrix, wrapping around the ordered list when it is too short."""
-        num_chunks = max(1, self.num_samples)
-        need = num_chunks * self.num_replicas
-        reps = math.ceil(need / len(ordered))
-        return np.tile(ordered, reps)[:need].reshape(num_chunks, self.num_replicas)
-
-    def shuffle_chunks(self):
+    # -- the epoch plan ----------------------------------------------------------------------------------------------------
+    def epoch_plan(self, epoch: Optional[int] = None) -> np.ndarray:
+        """``[num_samples, num_replicas]`` matrix of dataset indices for ``epoch`` (default: the current one): row *t* is what the
+        replicas load at step *t* — ``num_replicas`` neighbours in (jittered) cost order — and replica *r* reads column *r*.
+        Deterministic in ``(seed, epoch)``, so every replica derives the same matrix without communicating."""
+        epoch = self.epoch if epoch is None else epoch
+        rows, width = max(1, self.num_samples), self.num_replicas
+        order = self._by_cost
+        row_order = np.arange(rows)
         if self.shuffle:
             g = torch.Generator()
-            g.manual_seed(self.seed + self.epoch)
+            g.manual_seed(self.seed + epoch)
             if self.random_number > 0:
                 jitter = torch.randint(self.random_number, (len(self.complexities),), generator=g).numpy()
-                ordered = np.argsort(self.complexities + jitter, kind="stable")
-            else:
-                ordered = self._sorted_indices
-            index_chunks = self._chunks(ordered)
-            chunk_indices = torch.randperm(len(index_chunks), generator=g).tolist()
-        else:
-            index_chunks = self._chunks(self._sorted_indices)
-            chunk_indices = list(range(len(index_chunks)))
-        if not self.drop_last:
-            pad = self.num_samples - len(chunk_indices)
-            if pad > 0:
-                chunk_indices += (chunk_indices * math.ceil(pad / len(chunk_indices)))[:pad]
-        else:
-            chunk_indices = chunk_indices[: self.num_samples]
-        assert len(chunk_indices) == self.num_samples
-        return index_chunks.tolist(), chunk_indices
+                order = np.argsort(self.complexities + jitter, kind="stable")
+            row_order = torch.randperm(rows, generator=g).numpy()
+        # cost-ordered indices laid out row by row; a short list wraps around so that the last row is full
+        grid = np.resize(order, rows * width).reshape(rows, width)
+        plan = grid[row_order]
+        if len(plan) < self.num_samples:                    # only when the dataset is smaller than one row per step
+            plan = np.resize(plan, (self.num_samples, width))
+        return plan[: self.num_samples]
 
     def __iter__(self) -> Iterator:
-        index_chunks, chunk_indices = self.shuffle_chunks()
-        indices = [index_chunks[i][self.rank] for i in chunk_indices]
-        assert len(indices) == self.num_samples
-        return iter(indices)
+        return iter(self.epoch_plan()[:, self.rank].tolist())
 
     def __len__(self) -> int:
         return self.num_samples
@@ -131,14 +120,16 @@ class LoadBalancingDistributedBatchSampler(Sampler):
         self.drop_last = drop_last
         self.num_replicas = sampler.num_replicas
         self.rank = sampler.rank
-        self.generate_batches()
+        self._rebuild()
 
-    def generate_batches(self):
-        index_chunks, chunk_indices = self.sampler.shuffle_chunks()
-        batches = [self.batch_fn([index_chunks[i][r] for i in chunk_indices]) for r in range(self.num_replicas)]
-        lens = [len(b) for b in batches]
-        self.total_batch = min(lens) if self.drop_last else max(lens)
-        self.padded_batches = [(b + b[: self.total_batch - len(b)])[: self.total_batch] for b in batches]
+    def _rebuild(self):
+        """Batch every replica's column of the epoch plan, then give all replicas the same number of batches: the shortest list's
+        length when ``drop_last``, otherwise the longest (shorter lists repeat their first batches)."""
+        plan = self.sampler.epoch_plan()
+        per_replica = [self.batch_fn(plan[:, r].tolist()) for r in range(self.num_replicas)]
+        counts = [len(b) for b in per_replica]
+        self.total_batch = min(counts) if self.drop_last else max(counts)
+        self.padded_batches = [(b + b[: self.total_batch - len(b)])[: self.total_batch] for b in per_replica]
 
     def __iter__(self):
         return iter(self.padded_batches[self.rank])
@@ -148,4 +139,4 @@ class LoadBalancingDistributedBatchSampler(Sampler):
 
     def set_epoch(self, epoch: int) -> None:
         self.sampler.set_epoch(epoch)
-        self.generate_batches()
+        self._rebuild()
