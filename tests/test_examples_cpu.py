@@ -11,7 +11,9 @@ ENV = dict(os.environ, PYTHONPATH=REPO + os.pathsep + os.environ.get("PYTHONPATH
 CASES = {
     "mnist": ["examples/mnist/main.py", "--cpu", "--epochs", "1", "--steps-per-epoch", "5", "--algorithm", "bytegrad"],
     "mnist_fused": ["examples/mnist/main.py", "--cpu", "--epochs", "1", "--steps-per-epoch", "5", "--fuse-optimizer"],
-    "moe_mnist": ["examples/moe/mnist_main.py", "--cpu", "--steps", "5"],
+    "moe_mnist": ["examples/moe/mnist_main.py", "--cpu", "--epochs", "2", "--steps-per-epoch", "3", "--num-local-experts", "2", "--set-deterministic", "--save-model",
+                  "--log-interval", "1"],
+    "moe_mnist_dense_async": ["examples/moe/mnist_main.py", "--cpu", "--epochs", "1", "--steps-per-epoch", "3", "--algorithm", "async", "--async-sync-interval", "5"],
     "primitives": ["examples/communication_primitives/main.py"],
     "elastic": ["examples/elastic_training/main.py", "--cpu", "--steps", "5", "--ckpt", "{tmp}/ckpt.pt"],
     "imagenet": ["examples/imagenet/main.py", "--cpu", "--synthetic", "--epochs", "1", "--steps-per-epoch", "2", "--batch-size", "2", "--num-classes", "10",
