@@ -678,7 +678,19 @@ def init_process_group(store=None, rank: int = -1, world_size: int = -1, local_w
             # A bare single-process run (no launcher) has neither variable: it is rank 0 of 1.
             os.environ.setdefault("RANK", str(env.get_rank()))
             os.environ.setdefault("WORLD_SIZE", str(env.get_world_size()))
-            dist.init_process_group(backend=backend, **kwargs)
+            if os.environ.get("TORCHELASTIC_USE_AGENT_STORE", "") == "True":
+                # Elastic launcher: every attempt of the gang talks to the SAME agent-hosted TCPStore (MASTER_PORT does not change across
+                # restarts), and torch's env:// handler adds no per-attempt prefix — a restarted rank then reads its peer's address of
+                # the PREVIOUS attempt ("Gloo connectFullMesh failed … Connection refused", about every second restart on loopback).
+                # The keys of each attempt are isolated here.
+                from datetime import timedelta
+
+                attempt = os.environ.get("TORCHELASTIC_RESTART_COUNT", "0")
+                tcp = dist.TCPStore(env.get_master_addr(), env.get_master_port(), env.get_world_size(), False, timedelta(seconds=env.get_comm_timeout_s() + 600))
+                dist.init_process_group(backend=backend, store=dist.PrefixStore(f"/bagua_b200/attempt_{attempt}", tcp), rank=env.get_rank(),
+                                        world_size=env.get_world_size(), **kwargs)
+            else:
+                dist.init_process_group(backend=backend, **kwargs)
     _rank_mappings = None
     _patch_torch_process_group()
     _default_pg = new_group(stream=_make_stream())
