@@ -678,11 +678,11 @@ def init_process_group(store=None, rank: int = -1, world_size: int = -1, local_w
             # A bare single-process run (no launcher) has neither variable: it is rank 0 of 1.
             os.environ.setdefault("RANK", str(env.get_rank()))
             os.environ.setdefault("WORLD_SIZE", str(env.get_world_size()))
-            if os.environ.get("TORCHELASTIC_USE_AGENT_STORE", "") == "True":
+            if os.environ.get("TORCHELASTIC_USE_AGENT_STORE", "") == "True" and int(os.environ.get("TORCHELASTIC_RESTART_COUNT", "0") or 0) > 0:
                 # Elastic launcher: every attempt of the gang talks to the SAME agent-hosted TCPStore (MASTER_PORT does not change across
                 # restarts), and torch's env:// handler adds no per-attempt prefix — a restarted rank then reads its peer's address of
                 # the PREVIOUS attempt ("Gloo connectFullMesh failed … Connection refused", about every second restart on loopback).
-                # The keys of each attempt are isolated here.
+                # The keys of every RESTARTED attempt are isolated here (attempt 0 finds a fresh store and takes the stock env:// path).
                 from datetime import timedelta
 
                 attempt = os.environ.get("TORCHELASTIC_RESTART_COUNT", "0")
