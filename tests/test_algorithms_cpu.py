@@ -92,6 +92,14 @@ def _all_algorithms_worker(rank, world):
             opt = torch.optim.SGD(model.parameters(), lr=0.01)
             algo = Algorithm.init(name, **({"sync_interval_ms": 10} if name == "async" else {}))
         model = model.with_bagua([opt], algo)  # re-invoking with_bagua switches the algorithm
+        # what is communicated must follow the algorithm: gradients (or QAdam's first moment) for the centralized families, the WEIGHTS
+        # for decentralized / async — a re-registration replaces the getter closures, None meaning "the tensor itself"
+        for p in model.parameters():
+            eff = p.bagua_getter_closure()
+            if name in ("decentralized", "low_precision_decentralized", "async"):
+                assert eff.data_ptr() == p.data_ptr(), (name, "weight algorithms must communicate the weights, not stale gradient views")
+            elif name != "qadam":
+                assert p.grad is not None and eff.data_ptr() == p.grad.data_ptr(), name
         _train(model, opt, rank, 5)
         if name == "async":
             model.bagua_algorithm.abort(model)
@@ -104,6 +112,9 @@ def _all_algorithms_worker(rank, world):
 def test_all_algorithms_and_switching():
     res = run_distributed(_all_algorithms_worker, world=2, timeout=400)
     assert torch.equal(res[0]["gradient_allreduce"], res[1]["gradient_allreduce"])
+    # decentralized averaging must actually have mixed the replicas' weights (it would not if it exchanged gradient buffers): after the
+    # average of the last step the replicas are one local SGD update apart
+    assert (res[0]["decentralized"] - res[1]["decentralized"]).abs().max().item() < 0.05
 
 
 # ---- decentralized: oracle as in the reference's tests/torch_api/test_decentralized.py ------------------------------
