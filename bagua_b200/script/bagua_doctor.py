@@ -90,7 +90,13 @@ def _environment() -> Dict[str, str]:
     return changed
 
 
-def _self_test() -> List[dict]:
+def native_mod():
+    from bagua_b200.core import native
+
+    return native()
+
+
+def _self_test(peer_kernels: bool = False) -> List[dict]:
     import numpy as np
     import torch
 
@@ -164,6 +170,32 @@ def _self_test() -> List[dict]:
             return "flat_sgd kernel"
 
         check("fused optimizer kernel (sm_100a)", fused_step)
+        if peer_kernels:
+            def virtual_world():
+                """A 4-rank all-reduce, a fused allreduce+SGD step and a ByteGrad exchange among VIRTUAL ranks on this one GPU
+                (parallel/virtual.py): the peer kernels' slice arithmetic, barriers and quantisation without a second GPU."""
+                from bagua_b200.core import dtype_code
+                from bagua_b200.parallel.virtual import VirtualPeerWorld
+
+                C = native_mod()
+                P, n = 4, 1 << 16
+                w = VirtualPeerWorld(P, torch.device("cuda", torch.cuda.current_device()), timeout_s=10.0)
+                buf = w.alloc(n * 4)
+                for r in range(P):
+                    buf.view(r, torch.float32, n).fill_(float(r + 1))
+                w.run(lambda r: C.AllReduceOp(w.comms[r], buf.buf, buf.buf, 0, 0, n * 4, dtype_code(torch.float32), 1.0 / P, C.AR_TWO_SHOT, w.cfg(4)))
+                assert all(torch.allclose(buf.view(r, torch.float32, n), torch.full((n,), (P + 1) / 2, device="cuda")) for r in range(P))
+                numel = 32 * P * 64
+                box = C.ByteGradOp.box_bytes(numel, P)
+                inbox, outbox = w.alloc(box), w.alloc(box)
+                datas = [torch.linspace(-1, 1, numel, device="cuda") * (r + 1) for r in range(P)]
+                want = sum(datas) / P
+                w.run(lambda r: C.ByteGradOp(w.comms[r], datas[r].data_ptr(), numel, dtype_code(torch.float32), inbox.buf, 0, outbox.buf, 0, True, w.cfg(2 * P, 256)))
+                err = max((d - want).abs().max().item() for d in datas)
+                assert err <= 2.5 * (2.0 * P) / 255, f"ByteGrad error {err}"
+                return f"two-shot all-reduce and fused ByteGrad among {P} virtual ranks (max quantisation error {err:.4f})"
+
+            check("peer kernels among virtual ranks (one GPU)", virtual_world)
     return results
 
 
@@ -171,9 +203,10 @@ def main(argv=None) -> int:
     ap = argparse.ArgumentParser(description=__doc__.split("\n")[0])
     ap.add_argument("--json", action="store_true", help="machine-readable report")
     ap.add_argument("--no-self-test", action="store_true")
+    ap.add_argument("--kernels", action="store_true", help="also run the NVSwitch peer kernels among virtual ranks on this GPU (no second GPU needed)")
     args = ap.parse_args(argv)
     report = {"libraries": _lib_state(), "versions": _versions(), "gpus": _gpus(), "environment": _environment()}
-    report["self_test"] = [] if args.no_self_test else _self_test()
+    report["self_test"] = [] if args.no_self_test else _self_test(peer_kernels=args.kernels)
     ok = all(r["ok"] for r in report["self_test"]) and report["libraries"]["_C.so (native core, sm_100a kernels)"]["present"]
     report["ok"] = bool(ok)
     if args.json:

@@ -8,8 +8,15 @@ for tool in memcheck racecheck synccheck; do
       > gpurun_out/sanitizer_$tool.log 2>&1
   echo "$tool exit=$?" | tee -a gpurun_out/sanitizer_summary.txt
 done
-# kernels written after the last GPU session (memcheck only: racecheck does not model tcgen05 / mbarrier traffic)
-BAGUA_EXPERIMENTAL=1 compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_zz_new_kernels_gpu.py -q -x \
+# the peer / quantised / MoE kernels among virtual ranks on this one GPU (memcheck + synccheck; racecheck only tracks shared memory and
+# does not model tcgen05 / mbarrier / cross-stream global traffic). P = 1 cases keep the run short; spinning multi-stream cases are slow under
+# the sanitizer, so their in-kernel time-out is raised.
+for tool in memcheck synccheck; do
+  BAGUA_PEER_TIMEOUT_S=600 compute-sanitizer --tool $tool --error-exitcode 1 python -m pytest tests/test_virtual_peer_gpu.py -q -x -k "1-" \
+      > gpurun_out/sanitizer_${tool}_peer_kernels.log 2>&1
+  echo "$tool(peer kernels, P=1) exit=$?" | tee -a gpurun_out/sanitizer_summary.txt
+done
+compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_zz_new_kernels_gpu.py -q -x \
     > gpurun_out/sanitizer_memcheck_new_kernels.log 2>&1
 echo "memcheck(new kernels) exit=$?" | tee -a gpurun_out/sanitizer_summary.txt
 # host side: the C++ scheduler under TSAN/ASAN runs in the CPU suite (tests/test_scheduler_tsan.py)
