@@ -130,6 +130,7 @@ class Communicator:
         owner = self._owner() if self._owner else None
         if owner is not None and owner._peer_engine is not None:
             owner._peer_engine.comm.abort()
+            owner._peer_engine.comm_blocking.abort()   # the blocking API's own communicator spins on its own flags
 
     def check_abort(self) -> bool:
         return self._aborted
