@@ -100,7 +100,7 @@ class ClockSampler:
 
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:  # noqa: BLE001
             self.proc = None
@@ -140,11 +140,11 @@ class ClockSampler:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         rows = self._parse()
-        sel = [r for r in rows if (begin is None or r[0] >= begin - 0.02) and (end is None or r[0] <= end + 0.02)]
+        sel = [r for r in rows if (begin is None or r[0] >= begin - 0.05) and (end is None or r[0] <= end + 0.05)]
         note = None
         if not sel and rows and begin is not None:   # region shorter than the sampling period: take the two nearest samples
             sel = sorted(rows, key=lambda r: min(abs(r[0] - begin), abs(r[0] - end)))[:2]
-            note = "timed region shorter than the 20 ms sampling period: nearest samples"
+            note = "no sample inside the timed region (50 ms sampling period): nearest samples"
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in sel for n, v in zip(names, r[4]) if v == "Active"})
         sm = sorted(r[1] for r in sel)
