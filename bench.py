@@ -306,6 +306,16 @@ def measure(c, name, train_step, dev_batch, host_batches, to_model_format, per_s
             "host_issue_ms_per_step": host_ms}
 
 
+def _bucket_programs(model):
+    """The op list the scheduler runs per bucket, as the native core reports it (kinds such as ``allreduce_sgd``, ``bytegrad_fused``,
+    ``allreduce_multimem``; a ``python`` entry would be a torch.distributed fallback) with how many buckets carry each program."""
+    import collections
+    import re
+
+    progs = collections.Counter(re.sub(r"^bucket \S+ ", "", b.backend_bucket.print_ops()) for b in model.bagua_buckets)
+    return {k: v for k, v in sorted(progs.items())}
+
+
 def verify_fused_update(c, build_model, fused_model, optimizer, batch, loss_fn, lr, steps=2):
     """Outside every timed region: the update rule of the fused bucket kernels (reduce-scatter → SGD on fp32 master shards →
     all-gather) against a plain twin — same architecture and initial weights, gradients all-reduced in FP32 by torch.distributed,
@@ -419,6 +429,7 @@ def run_cnn(c, model_name):
         model = model.with_bagua([optimizer], algorithm)
         cfg["allreduce_variants"] = sorted({getattr(b, "allreduce_variant", "none") for b in model.bagua_buckets})
         cfg["buckets"] = len(model.bagua_buckets)
+        cfg["bucket_programs"] = _bucket_programs(model)
         finish = model.bagua_ddp.wait_pending_comm_ops
         if fused and not args.no_verify and model_name == "vgg16" and args.momentum == 0.0:
             xv = torch.randn(bs, 3, img, img, device=dev).to(dtype)
@@ -501,6 +512,7 @@ def run_bert(c):
         cfg["optimizer"] = "FusedAdam(adamw, fp32 master weights + moments), one flat kernel per step"
         cfg["allreduce_variants"] = sorted({getattr(b, "allreduce_variant", "none") for b in model.bagua_buckets})
         cfg["buckets"] = len(model.bagua_buckets)
+        cfg["bucket_programs"] = _bucket_programs(model)
         finish = model.bagua_ddp.wait_pending_comm_ops
         algo = "ByteGrad (MinMaxUInt8)"
 
