@@ -968,7 +968,9 @@ def reduce_scatter(send_tensor, recv_tensor, op: ReduceOp = ReduceOp.SUM, comm: 
 
 
 def reduce_scatter_inplace(tensor, op: ReduceOp = ReduceOp.SUM, comm: Optional[Communicator] = None):
-    """In-place reduce-scatter: chunk ``rank`` of ``tensor`` holds the reduced chunk afterwards (reference communication.py:1205-1235)."""
+    """In-place reduce-scatter: the FIRST ``numel / nranks`` elements of ``tensor`` hold this rank's chunk of the reduction
+    afterwards (MPI_IN_PLACE placement, which is what the reference's Aluminum call does — rust/…/communicators/mod.rs:1026-1058 —
+    not NCCL's chunk-``rank`` placement; reference communication.py:1205-1235)."""
     c = _comm(comm)
     _check(c, tensor)
     with _on_comm_stream(c):

@@ -192,6 +192,9 @@ __global__ void __launch_bounds__(512) bytegrad_kernel(PeerCtx ctx, T* data, siz
 #pragma unroll
             for (int k = 0; k < 16; ++k) mn = fminf(mn, f[k]), mx = fmaxf(mx, f[k]);
         }
+        // phase B reads what was just stored through the bulk-copy engine (async proxy): writer-side cross-proxy fence, the reader
+        // issues its own before the first bulk copy (bulk_pipe.cuh) — the grid barrier in between carries the ordering across CTAs
+        if (gsrc) asm volatile("fence.proxy.async;" ::: "memory");
         block_minmax(mn, mx);
         if (threadIdx.x == 0) {
             uint32_t* s = mm_slot(scratch, parity, cj);

@@ -15,7 +15,8 @@ CASES = {
                   "--log-interval", "1"],
     "moe_mnist_dense_async": ["examples/moe/mnist_main.py", "--cpu", "--epochs", "1", "--steps-per-epoch", "3", "--algorithm", "async", "--async-sync-interval", "5"],
     "primitives": ["examples/communication_primitives/main.py"],
-    "elastic": ["examples/elastic_training/main.py", "--cpu", "--steps", "5", "--ckpt", "{tmp}/ckpt.pt"],
+    "elastic": ["examples/elastic_training/main.py", "--cpu", "--epochs", "1", "--steps-per-epoch", "3", "--checkpoint_path", "{tmp}/ckpt.pt", "--log-interval", "1",
+                "--algorithm", "bytegrad"],
     "imagenet": ["examples/imagenet/main.py", "--cpu", "--synthetic", "--epochs", "1", "--steps-per-epoch", "2", "--batch-size", "2", "--num-classes", "10",
                  "--image-size", "32", "--print-freq", "1"],
     "synthetic_benchmark": ["examples/benchmark/synthetic_benchmark.py", "--cpu", "--model", "mnist", "--deterministic", "--num-warmup-batches", "1",
@@ -33,6 +34,27 @@ def test_example_runs_under_the_static_launcher(name, tmp_path):
     cmd = [sys.executable, "-m", "bagua_b200.distributed.launch", "--nproc_per_node=2", f"--master_port={free_port()}", os.path.join(REPO, argv[0]), *argv[1:]]
     r = run_in_session(cmd, 240, env=ENV, cwd=str(tmp_path))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_elastic_example_resumes_from_its_checkpoint(tmp_path):
+    """examples/elastic_training/main.py: a second gang (here: a second launch, with a different world size) finds the first one's
+    checkpoint, resumes with the following epoch and finishes; a third launch has nothing left to train."""
+    from tests.mp_utils import free_port, run_in_session
+
+    def launch(nproc, epochs):
+        cmd = [sys.executable, "-m", "bagua_b200.distributed.launch", f"--nproc_per_node={nproc}", f"--master_port={free_port()}",
+               os.path.join(REPO, "examples/elastic_training/main.py"), "--cpu", "--epochs", str(epochs), "--steps-per-epoch", "2", "--batch-size", "8",
+               "--test-batch-size", "50", "--checkpoint_path", str(tmp_path / "ckpt.pt"), "--log-interval", "1"]
+        r = run_in_session(cmd, 240, env=ENV, cwd=str(tmp_path))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+        return r.stdout
+
+    first = launch(2, 1)
+    assert "resumed from" not in first and "Train Epoch: 1" in first
+    second = launch(1, 2)
+    assert "next epoch 2" in second and "Train Epoch: 2" in second and "Train Epoch: 1 " not in second
+    third = launch(2, 2)
+    assert "next epoch 3" in third and "nothing left to train" in third
 
 
 @pytest.mark.parametrize("config", ["bert_bytegrad", "resnet50_decentralized", "resnet50_async", "gpt2_moe"])
