@@ -4,7 +4,7 @@ examples run without torchvision / transformers."""
 from .mnist import MnistNet  # noqa: F401
 from .vgg import vgg16, VGG  # noqa: F401
 from .resnet import resnet50, ResNet  # noqa: F401
-from .bert import BertConfig, BertForQuestionAnswering, bert_large_config  # noqa: F401
+from .bert import BertConfig, BertForQuestionAnswering, bert_large_config, bert_qa_from_pretrained, convert_hf_state_dict, save_pretrained, to_hf_state_dict  # noqa: F401
 from .gpt2_moe import GPT2MoEConfig, GPT2MoE, gpt2_medium_moe8_config  # noqa: F401
 
 _REGISTRY = {"vgg16": vgg16, "resnet50": resnet50, "mnist": MnistNet}

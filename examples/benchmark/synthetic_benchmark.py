@@ -29,7 +29,10 @@ p.add_argument("--async-warmup-steps", type=int, default=100)
 p.add_argument("--deterministic", action="store_true", help="fixed seeds + deterministic kernels; prints the final loss (the reference's CI "
                "compares it against a recorded value, .buildkite/scripts/benchmark_master.sh:84)")
 p.add_argument("--image-size", type=int, default=224)
-p.add_argument("--cpu", action="store_true", help="gloo + CPU tensors (smoke tests)")
+p.add_argument("--cpu", "--no-cuda", dest="cpu", action="store_true", help="gloo + CPU tensors (smoke tests)")
+p.add_argument("--amp", action="store_true", help="fp32 parameters, forward under torch.autocast (fp16 + GradScaler on GPUs, bf16 on CPUs); the reference's "
+               "flag of the same name crashes on an undefined args.scaler (synthetic_benchmark.py:181-186)")
+p.add_argument("--log-interval", type=int, default=0, help="also print the loss every N batches")
 args = p.parse_args()
 
 cuda = torch.cuda.is_available() and not args.cpu
@@ -64,11 +67,29 @@ if args.bf16:
 target = torch.randint(0, num_classes, (args.batch_size,), device=dev)
 
 
+amp_dtype = torch.float16 if cuda else torch.bfloat16
+scaler = torch.amp.GradScaler("cuda") if (args.amp and cuda) else None
+batches_done = 0
+
+
 def step():
+    global batches_done
     optimizer.zero_grad()
-    loss = F.cross_entropy(model(data).float(), target)
-    loss.backward()
-    optimizer.fuse_step() if args.fuse_optimizer else optimizer.step()
+    if args.amp:
+        with torch.autocast(dev.type, dtype=amp_dtype):
+            loss = F.cross_entropy(model(data).float(), target)
+    else:
+        loss = F.cross_entropy(model(data).float(), target)
+    if scaler is not None:   # gradients are communicated scaled; unscale + inf check happen in scaler.step after the all-reduce
+        scaler.scale(loss).backward()
+        scaler.step(optimizer)
+        scaler.update()
+    else:
+        loss.backward()
+        optimizer.fuse_step() if args.fuse_optimizer else optimizer.step()
+    batches_done += 1
+    if args.log_interval and batches_done % args.log_interval == 0 and bagua.get_rank() == 0:
+        print(f"batch {batches_done}: loss {loss.item():.6f}")
     return loss
 
 
