@@ -21,8 +21,9 @@ CASES = {
                  "--image-size", "32", "--print-freq", "1"],
     "synthetic_benchmark": ["examples/benchmark/synthetic_benchmark.py", "--cpu", "--model", "mnist", "--deterministic", "--num-warmup-batches", "1",
                             "--num-batches-per-iter", "2", "--num-iters", "2", "--batch-size", "4", "--algorithm", "low_precision_decentralized"],
-    "squad": ["examples/squad/main.py", "--cpu", "--tiny", "--epochs", "1", "--num-synthetic", "48", "--batch-size", "4", "--max-seq-length", "64",
-              "--print-freq", "2", "--algorithm", "decentralized"],
+    "squad": ["examples/squad/main.py", "--cpu", "--tiny", "--epochs", "1", "--num-synthetic", "24", "--batch-size", "4", "--max-seq-length", "64", "--doc_stride", "32",
+              "--print-freq", "2", "--algorithm", "decentralized", "--output_dir", "{tmp}/out", "--do_lower_case", "--save_steps", "2", "--eval_all_checkpoints",
+              "--gradient_accumulation_steps", "2", "--version_2_with_negative", "--evaluate_during_training"],
 }
 
 
