@@ -43,7 +43,7 @@ def parse():
     p = argparse.ArgumentParser(description="bagua_b200 ImageNet training")
     p.add_argument("data_pos", metavar="DIR", nargs="?", default="", help="dataset directory (train/ and val/)")
     p.add_argument("--data", default="", help="same as DIR")
-    p.add_argument("-a", "--arch", default="resnet50", choices=["resnet50", "vgg16"])
+    p.add_argument("-a", "--arch", default="resnet50", help="resnet50 / vgg16 (built in, fused NHWC epilogues) or any torchvision.models name")
     p.add_argument("-j", "--workers", type=int, default=4, metavar="N", help="data loading workers per rank")
     p.add_argument("--epochs", type=int, default=90, metavar="N")
     p.add_argument("--start-epoch", type=int, default=0, metavar="N", help="manual epoch number (useful on restarts)")
