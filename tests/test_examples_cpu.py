@@ -58,6 +58,25 @@ def test_elastic_example_resumes_from_its_checkpoint(tmp_path):
     assert "next epoch 3" in third and "nothing left to train" in third
 
 
+def test_moe_example_final_loss_is_unchanged_by_a_checkpoint_round_trip(tmp_path):
+    """The reference's CI runs examples/moe/mnist_main.py with and without --save-model under --set-deterministic and requires the
+    same final loss (.buildkite/scripts/benchmark_master.sh:137-151): saving and re-loading model, experts and optimizer after
+    every epoch must not change training."""
+    import re
+
+    from tests.mp_utils import free_port, run_in_session
+
+    def final_loss(extra):
+        cmd = [sys.executable, "-m", "bagua_b200.distributed.launch", "--nproc_per_node=2", f"--master_port={free_port()}",
+               os.path.join(REPO, "examples/moe/mnist_main.py"), "--cpu", "--epochs", "2", "--steps-per-epoch", "3", "--num-local-experts", "2", "--set-deterministic",
+               "--log-interval", "1", *extra]
+        r = run_in_session(cmd, 240, env=ENV, cwd=str(tmp_path))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+        return re.findall(r"Final Loss: ([0-9.]+)", r.stdout)[-1]
+
+    assert final_loss([]) == final_loss(["--save-model", "--save-dir", str(tmp_path / "ckpt")])
+
+
 @pytest.mark.parametrize("config", ["bert_bytegrad", "resnet50_decentralized", "resnet50_async", "gpt2_moe"])
 def test_baseline_config_benchmarks_run_tiny_in_bf16(config, tmp_path):
     """benchmarks/config_bench.py for every BASELINE configuration: tiny models, two CPU ranks, bf16 parameters — the python
