@@ -9,4 +9,4 @@ command -v nvcc >/dev/null || { echo "install.sh: nvcc not found (CUDA >= 12.8 t
 "$PY" -c "import __graft_entry__ as g; g.build()"
 "$PY" -m pip install --no-index --no-build-isolation --no-deps -e . 2>/dev/null || \
   echo "install.sh: editable install skipped (pip could not run offline); use PYTHONPATH=$(pwd) instead"
-"$PY" -c "import bagua_b200 as b; print('bagua_b200', getattr(b, '__version__', ''), 'native core:', b._C.build_info() if hasattr(b._C, 'build_info') else 'loaded')"
+"$PY" -c "from bagua_b200 import _C; print('bagua_b200 native core:', _C.show_version())"
