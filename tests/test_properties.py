@@ -194,3 +194,53 @@ def _plugin_handle():
 
         _handle_cache.append(net.PluginHandle())
     return _handle_cache[0]
+
+
+def test_bytegrad_bucket_merging_keeps_order_dtype_boundaries_and_the_size_floor():
+    """``merge_small_buckets`` (bytegrad.py): consecutive suggested buckets are concatenated until each holds ``min_bytes``; tensor order
+    is preserved (a merged bucket becomes ready when its last member would have), dtypes never mix, a small remainder joins its predecessor."""
+    import random
+
+    import torch
+
+    from bagua_b200.parallel.algorithms.bytegrad import merge_small_buckets
+
+    class T:   # what the function touches of a bagua tensor
+        def __init__(self, numel, dtype, tag):
+            self._t, self.tag = torch.empty(numel, dtype=dtype), tag
+
+        def bagua_getter_closure(self):
+            return self._t
+
+    def nbytes(bucket):
+        return sum(t._t.numel() * t._t.element_size() for t in bucket)
+
+    rng = random.Random(5)
+    for trial in range(200):
+        dtypes = [torch.float32] * rng.randint(1, 6) + [torch.bfloat16] * rng.randint(0, 6) + [torch.float32] * rng.randint(0, 3)
+        buckets, tag = [], 0
+        for dt in dtypes:
+            b = []
+            for _ in range(rng.randint(1, 4)):
+                b.append(T(rng.randint(1, 400), dt, tag))
+                tag += 1
+            buckets.append(b)
+        floor = rng.choice([0, 64, 1000, 4000, 10 ** 6])
+        merged = merge_small_buckets(buckets, floor)
+        assert [t.tag for b in merged for t in b] == list(range(tag)), "order / completeness"
+        assert all(len({t._t.dtype for t in b}) == 1 for b in merged), "mixed dtypes in one bucket"
+        if floor == 0:
+            assert merged == buckets
+            continue
+        # within one run of equal dtype only the LAST bucket may be under the floor
+        runs, cur = [], [merged[0]]
+        for b in merged[1:]:
+            if b[0]._t.dtype == cur[-1][0]._t.dtype:   # runs are adjacent buckets of one dtype
+                cur.append(b)
+            else:
+                runs.append(cur)
+                cur = [b]
+        runs.append(cur)
+        for run in runs:
+            assert all(nbytes(b) >= floor for b in run[:-1]), (trial, [nbytes(b) for b in run], floor)
+        assert len(merged) <= len(buckets)
