@@ -37,8 +37,8 @@ two)
   echo "experimental exit=$?" | tee -a gpurun_out/plan_two.txt
   timeout 400 python -m pytest tests/test_peer_gpu.py -x -q > gpurun_out/pytest_peer_2.log 2>&1; echo "peer exit=$?" | tee -a gpurun_out/plan_two.txt
   # the shipped examples on real GPUs (each asserts its own results)
-  for ex in "communication_primitives/main.py" "mnist/main.py --algorithm bytegrad --epochs 1 --steps-per-epoch 20" "moe/mnist_main.py --steps 20" \
-            "squad/main.py --tiny --epochs 1 --num-synthetic 256 --max-seq-length 128 --algorithm qadam" \
+  for ex in "communication_primitives/main.py" "mnist/main.py --algorithm bytegrad --epochs 1 --steps-per-epoch 20" "moe/mnist_main.py --epochs 1 --steps-per-epoch 20 --num-local-experts 2" \
+            "squad/main.py --tiny --epochs 1 --num-synthetic 64 --max_seq_length 128 --doc_stride 64 --algorithm qadam --output_dir /tmp/squad_plan --overwrite_output_dir" \
             "imagenet/main.py --arch vgg16 --synthetic --epochs 1 --steps-per-epoch 10 --fused-shard"; do
     timeout 240 python -m bagua_b200.distributed.launch --nproc_per_node=2 --master_port=$((29640 + RANDOM % 50)) examples/$ex > gpurun_out/example_$(echo $ex | cut -d/ -f1).log 2>&1
     echo "example $ex exit=$?" | tee -a gpurun_out/plan_two.txt
