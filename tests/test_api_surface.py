@@ -233,3 +233,34 @@ def test_bagua_core_shim_low_level_ops():
         assert torch.equal(a, torch.full((8,), 1.5)) and torch.equal(b, torch.full((4, 2), 15.0))
         torch.testing.assert_close(c, torch.linspace(-1, 1, 16) * 1.5, rtol=0, atol=0.03)
         torch.testing.assert_close(peer, c, rtol=0, atol=1e-6)      # both ranks hold the same compressed mean → pair average = itself
+
+
+REFERENCE_MODULES = [
+    "bagua", "bagua.bagua_define", "bagua.distributed", "bagua.distributed.launch", "bagua.distributed.run", "bagua.script", "bagua.script.baguarun",
+    "bagua.service", "bagua.service.autotune_service", "bagua.service.autotune_system", "bagua.service.autotune_task_manager",
+    "bagua.service.bayesian_optimizer", "bagua.torch_api", "bagua.torch_api.algorithms", "bagua.torch_api.algorithms.async_model_average",
+    "bagua.torch_api.algorithms.base", "bagua.torch_api.algorithms.bytegrad", "bagua.torch_api.algorithms.decentralized",
+    "bagua.torch_api.algorithms.gradient_allreduce", "bagua.torch_api.algorithms.q_adam", "bagua.torch_api.bucket", "bagua.torch_api.checkpoint",
+    "bagua.torch_api.checkpoint.checkpointing", "bagua.torch_api.communication", "bagua.torch_api.contrib", "bagua.torch_api.contrib.cache_loader",
+    "bagua.torch_api.contrib.cached_dataset", "bagua.torch_api.contrib.fuse", "bagua.torch_api.contrib.fuse.optimizer",
+    "bagua.torch_api.contrib.load_balancing_data_loader", "bagua.torch_api.contrib.sync_batchnorm", "bagua.torch_api.contrib.utils",
+    "bagua.torch_api.contrib.utils.redis_store", "bagua.torch_api.contrib.utils.store", "bagua.torch_api.data_parallel",
+    "bagua.torch_api.data_parallel.bagua_distributed", "bagua.torch_api.data_parallel.distributed", "bagua.torch_api.data_parallel.functional",
+    "bagua.torch_api.distributed", "bagua.torch_api.env", "bagua.torch_api.model_parallel", "bagua.torch_api.model_parallel.moe",
+    "bagua.torch_api.model_parallel.moe.experts", "bagua.torch_api.model_parallel.moe.layer", "bagua.torch_api.model_parallel.moe.sharded_moe",
+    "bagua.torch_api.model_parallel.moe.utils", "bagua.torch_api.tensor", "bagua.torch_api.utils", "bagua.version",
+]
+
+
+def test_every_module_path_of_the_reference_package_imports():
+    """All 49 python modules of the reference's ``bagua`` package (the list is /root/reference/bagua/**/*.py) exist under the same
+    dotted path in the alias package, so ``import bagua.torch_api.contrib.cache_loader`` style imports in user code keep working."""
+    import importlib
+
+    missing = []
+    for name in REFERENCE_MODULES:
+        try:
+            importlib.import_module(name)
+        except Exception as e:  # noqa: BLE001
+            missing.append(f"{name}: {type(e).__name__}: {e}")
+    assert not missing, missing
