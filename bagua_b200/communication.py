@@ -526,21 +526,49 @@ def from_torch_group(group: dist.ProcessGroup, stream=None) -> BaguaProcessGroup
     return pg
 
 
-def _patch_torch_process_group():
-    """``ProcessGroup.bagua_patch / bagua_pg / bagua_get_*_communicator`` (reference communication.py:78-105)."""
+class BaguaProcessGroupPatch:
+    """Methods grafted onto ``torch.distributed.ProcessGroup`` (reference communication.py:78-105): ``pg.bagua_patch(stream)`` registers
+    the torch group with the engine, ``pg.bagua_pg`` is its :class:`BaguaProcessGroup`, ``pg.bagua_get_*_communicator()`` its
+    communicators.  The cache is weakly keyed on the torch group."""
 
     def bagua_patch(self, stream=None):
         from_torch_group(self, stream)
         return self
 
+    @property
     def bagua_pg(self):
         return from_torch_group(self)
 
-    dist.ProcessGroup.bagua_patch = bagua_patch
-    dist.ProcessGroup.bagua_pg = property(bagua_pg)
-    dist.ProcessGroup.bagua_get_global_communicator = lambda self: from_torch_group(self).get_global_communicator()
-    dist.ProcessGroup.bagua_get_inter_node_communicator = lambda self: from_torch_group(self).get_inter_node_communicator()
-    dist.ProcessGroup.bagua_get_intra_node_communicator = lambda self: from_torch_group(self).get_intra_node_communicator()
+    def bagua_get_global_communicator(self):
+        return from_torch_group(self).get_global_communicator()
+
+    def bagua_get_inter_node_communicator(self):
+        return from_torch_group(self).get_inter_node_communicator()
+
+    def bagua_get_intra_node_communicator(self):
+        return from_torch_group(self).get_intra_node_communicator()
+
+
+def _patch_torch_process_group():
+    """Install :class:`BaguaProcessGroupPatch` on ``torch.distributed.ProcessGroup``."""
+    for name in ("bagua_patch", "bagua_pg", "bagua_get_global_communicator", "bagua_get_inter_node_communicator", "bagua_get_intra_node_communicator"):
+        setattr(dist.ProcessGroup, name, BaguaProcessGroupPatch.__dict__[name])
+
+
+def broadcast_nccl_unique_id(comm_key: str, root: int) -> str:
+    """Publish a fresh NCCL unique id (base64 text) from ``root`` under ``comm_key`` in the default group's c10d store and return it on
+    every rank (reference communication.py:551-560).  The engine itself never needs one — torch.distributed creates the NCCL
+    communicators here — but code that brings its own ``ncclCommInitRank`` can keep using the helper."""
+    from torch.distributed.distributed_c10d import _get_default_store
+
+    store = _get_default_store()
+    if dist.get_rank() == root:
+        from bagua_core import BaguaSingleCommunicatorPy
+
+        idstr = BaguaSingleCommunicatorPy.generate_nccl_unique_id_str()
+        store.set(comm_key, idstr)
+        return idstr
+    return store.get(comm_key).decode("utf-8")
 
 
 def get_backend(model_name: str):
@@ -628,10 +656,17 @@ def get_hyperparameters_service_client():
     return AutotuneClient(get_autotune_service_host(), port)
 
 
+class comm(object):
+    """``comm.WORLD``: "the default group's global communicator" (reference communication.py:563-565; ``None`` here, which every
+    collective already treats that way)."""
+
+    WORLD = None
+
+
 class CommMember(object):
     """Sentinels of the reference API (communication.py:567-570)."""
 
-    WORLD = None  # "use the default group's global communicator"
+    WORLD = comm.WORLD  # "use the default group's global communicator"
     NON_COMM_MEMBER = object()
 
 

@@ -12,7 +12,7 @@ import pickle
 import weakref
 from typing import Any, Callable, Dict, Optional
 
-__all__ = ["CacheLoader"]
+__all__ = ["CacheLoader", "BatchFetcher"]
 
 logger = logging.getLogger(__name__)
 _MISSING = object()
@@ -77,6 +77,41 @@ class _WriteBehind:
             return False
         self.entries = {}
         return True
+
+
+class BatchFetcher:
+    """The reference's buffered store accessor (cache_loader.py:97-140: ``BatchFetcher(store, read_buffer_size, writer_buffer_size)``
+    with ``read`` / ``write`` / ``write_post_read`` / ``flush_write_map``) on top of :class:`_WriteBehind`.  Values are python objects;
+    a key that is still in the write buffer is served from there.  ``read_buffer_size`` is accepted for signature compatibility (reads
+    go to the store one key at a time here: the stores answer a ``get`` in one round trip)."""
+
+    def __init__(self, store, read_buffer_size: int = 1, writer_buffer_size: int = 1):
+        self.store = store
+        self.read_buffer_size = max(int(read_buffer_size), 1)
+        self._pending = _WriteBehind(store, writer_buffer_size)
+
+    @property
+    def write_map(self) -> Dict[str, bytes]:
+        return self._pending.entries
+
+    def read(self, key: str):
+        """The cached object, or ``None``."""
+        value = self._pending.peek(key)
+        if value is not _MISSING:
+            return value
+        blob = self.store.get(key)
+        return None if blob is None else deserialize(blob)
+
+    def write(self, key: str, value: Any):
+        self._pending.add(key, value)
+
+    def write_post_read(self):
+        """Flush when the buffer has reached its size (``write`` already does; kept for call-site compatibility)."""
+        if len(self._pending.entries) >= self._pending.limit:
+            self._pending.drain()
+
+    def flush_write_map(self):
+        self._pending.drain()
 
 
 class CacheLoader:

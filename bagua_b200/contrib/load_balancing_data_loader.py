@@ -71,11 +71,9 @@ class LoadBalancingDistributedSampler(Sampler):
         self.random_number = int(spread * random_level + 1)    # exclusive upper bound of the per-epoch jitter
 
     # -- the epoch plan ----------------------------------------------------------------------------------------------------
-    def epoch_plan(self, epoch: Optional[int] = None) -> np.ndarray:
-        """``[num_samples, num_replicas]`` matrix of dataset indices for ``epoch`` (default: the current one): row *t* is what the
-        replicas load at step *t* — ``num_replicas`` neighbours in (jittered) cost order — and replica *r* reads column *r*.
-        Deterministic in ``(seed, epoch)``, so every replica derives the same matrix without communicating."""
-        epoch = self.epoch if epoch is None else epoch
+    def _chunks(self, epoch: int):
+        """``(grid, row_order)``: the cost-ordered indices laid out row by row (``num_replicas`` neighbours per row; a short list wraps
+        around so that the last row is full) and the order in which the rows are visited in ``epoch``."""
         rows, width = max(1, self.num_samples), self.num_replicas
         order = self._by_cost
         row_order = np.arange(rows)
@@ -86,12 +84,23 @@ class LoadBalancingDistributedSampler(Sampler):
                 jitter = torch.randint(self.random_number, (len(self.complexities),), generator=g).numpy()
                 order = np.argsort(self.complexities + jitter, kind="stable")
             row_order = torch.randperm(rows, generator=g).numpy()
-        # cost-ordered indices laid out row by row; a short list wraps around so that the last row is full
-        grid = np.resize(order, rows * width).reshape(rows, width)
+        return np.resize(order, rows * width).reshape(rows, width), row_order
+
+    def epoch_plan(self, epoch: Optional[int] = None) -> np.ndarray:
+        """``[num_samples, num_replicas]`` matrix of dataset indices for ``epoch`` (default: the current one): row *t* is what the
+        replicas load at step *t* — ``num_replicas`` neighbours in (jittered) cost order — and replica *r* reads column *r*.
+        Deterministic in ``(seed, epoch)``, so every replica derives the same matrix without communicating."""
+        grid, row_order = self._chunks(self.epoch if epoch is None else epoch)
         plan = grid[row_order]
         if len(plan) < self.num_samples:                    # only when the dataset is smaller than one row per step
-            plan = np.resize(plan, (self.num_samples, width))
+            plan = np.resize(plan, (self.num_samples, self.num_replicas))
         return plan[: self.num_samples]
+
+    def shuffle_chunks(self):
+        """``(index_chunks, chunk_indices)`` in the reference's shape (load_balancing_data_loader.py:148-190): the chunks of
+        ``num_replicas`` similar-cost samples and the order in which this epoch visits them."""
+        grid, row_order = self._chunks(self.epoch)
+        return grid.tolist(), row_order.tolist()
 
     def __iter__(self) -> Iterator:
         return iter(self.epoch_plan()[:, self.rank].tolist())
@@ -130,6 +139,10 @@ class LoadBalancingDistributedBatchSampler(Sampler):
         counts = [len(b) for b in per_replica]
         self.total_batch = min(counts) if self.drop_last else max(counts)
         self.padded_batches = [(b + b[: self.total_batch - len(b)])[: self.total_batch] for b in per_replica]
+
+    def generate_batches(self):
+        """Rebuild the batches of the current epoch (name of the reference's method, load_balancing_data_loader.py:285-306)."""
+        self._rebuild()
 
     def __iter__(self):
         return iter(self.padded_batches[self.rank])

@@ -16,6 +16,9 @@ from argparse import ArgumentParser
 
 from .launch import add_bagua_arguments, set_bagua_env
 
+# helpers of torch's launcher that the reference's run.py re-implements (bagua/distributed/run.py:436-585); same objects here
+from torch.distributed.run import config_from_args, determine_local_world_size, get_rdzv_endpoint, parse_min_max_nnodes, run_script_path  # noqa: E402,F401
+
 
 def get_args_parser() -> ArgumentParser:
     from torch.distributed.run import get_args_parser as torch_parser

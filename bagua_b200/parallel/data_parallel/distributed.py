@@ -9,7 +9,7 @@ from __future__ import annotations
 import warnings
 from contextlib import contextmanager
 from dataclasses import dataclass
-from typing import Any, List, Optional, Sequence
+from typing import Callable, Any, List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
@@ -73,12 +73,35 @@ class _DDPOptions:
 
 
 class DistributedDataParallel_V1_9_0_Interface(torch.nn.Module):
-    r"""What a PyTorch-1.9-style DDP wrapper offers: ``forward`` and ``no_sync`` (overridden by the concrete class)."""
+    r"""The method set of a PyTorch-1.9 ``DistributedDataParallel`` (reference data_parallel/distributed.py:24-60); everything is
+    abstract here, the concrete class below fills in what the engine supports."""
 
     def no_sync(self):
         raise NotImplementedError
 
     def forward(self, *inputs, **kwargs):
+        raise NotImplementedError
+
+    def scatter(self, inputs, kwargs, device_ids):
+        raise NotImplementedError
+
+    def to_kwargs(self, inputs, kwargs, device_id):
+        raise NotImplementedError
+
+    def gather(self, outputs, output_device):
+        raise NotImplementedError
+
+    def train(self, mode=True):
+        super().train(mode)
+        return self
+
+    def join(self, divide_by_initial_world_size=True, enable=True, throw_on_early_termination=False):
+        raise NotImplementedError
+
+    def register_comm_hook(self, state: object, hook: Callable):
+        raise NotImplementedError
+
+    def will_sync_module_buffers(self):
         raise NotImplementedError
 
 
@@ -110,6 +133,35 @@ class DistributedDataParallel_V1_9_0(DistributedDataParallel_V1_9_0_Interface):
     def zero_grad(self, set_to_none: bool = False):
         """Gradients are views of the bucket arena and stay allocated (nn.Module's default would drop them)."""
         return super().zero_grad(set_to_none=False)
+
+    def scatter(self, inputs, kwargs, device_ids):
+        """Move positional and keyword inputs to the module's (single) device, as torch's DDP does before ``forward``."""
+        from torch.nn.parallel.scatter_gather import scatter_kwargs
+
+        return scatter_kwargs(inputs, kwargs, device_ids, dim=self.dim)
+
+    def to_kwargs(self, inputs, kwargs, device_id):
+        moved_inputs, moved_kwargs = self.scatter(inputs, kwargs, [device_id])
+        return moved_inputs, moved_kwargs
+
+    def gather(self, outputs, output_device):
+        from torch.nn.parallel.scatter_gather import gather
+
+        return gather(outputs, output_device, dim=self.dim)
+
+    def join(self, divide_by_initial_world_size=True, enable=True, throw_on_early_termination=False):
+        """Uneven inputs across ranks are not supported by the bucket scheduler (every rank must mark every bucket every step) — the
+        reference leaves this method abstract as well (data_parallel/distributed.py:47-54)."""
+        raise NotImplementedError("join() (uneven inputs) is not supported; pad or drop the last incomplete batch instead")
+
+    def register_comm_hook(self, state: object, hook: Callable):
+        """Gradient communication is defined by the ``algorithm`` (``AlgorithmImpl.init_operations`` / ``append_python_op``), not by a
+        torch comm hook — abstract in the reference too (:56-57)."""
+        raise NotImplementedError("use a bagua Algorithm (e.g. a custom AlgorithmImpl with bucket.append_python_op) instead of a comm hook")
+
+    def will_sync_module_buffers(self) -> bool:
+        """Whether the next forward broadcasts the module's buffers from rank 0 (the engine does so whenever buffers exist)."""
+        return self.broadcast_buffers and any(True for _ in self.module.buffers())
 
     @contextmanager
     def no_sync(self):

@@ -187,7 +187,20 @@ class BaguaSingleCommunicatorPy:
 
     @staticmethod
     def generate_nccl_unique_id_str() -> str:
-        return "bagua_b200-symmetric-memory"  # no NCCL id is exchanged: groups rendezvous through torch.distributed
+        """A fresh ``ncclUniqueId`` (128 bytes, base64) as the reference returns (communicators/mod.rs:244-258).  The engine does not
+        consume it — groups rendezvous through torch.distributed and symmetric memory — but user code that creates its own NCCL
+        communicator can.  Without an NCCL-enabled torch build: 128 random bytes (still unique per call)."""
+        import base64
+
+        try:
+            import torch.cuda.nccl as nccl
+
+            raw = nccl.unique_id()
+        except Exception:  # noqa: BLE001
+            import os
+
+            raw = os.urandom(128)
+        return base64.b64encode(raw).decode("ascii")
 
     def __getattr__(self, name):
         return getattr(self._comm, name)

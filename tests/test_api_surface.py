@@ -135,8 +135,7 @@ def test_multiple_models_in_one_process():
 # names of the reference that are implementation details of ITS design (NCCL unique-id plumbing, Flask glue, the internals of
 # its alias-based fused optimizer) and have no counterpart by construction
 _NOT_APPLICABLE = {
-    "bagua.torch_api.contrib.cache_loader": {"BatchFetcher"},   # internal helper of the reference's loader; ours is _WriteBehind
-    "bagua.torch_api.communication": {"BaguaProcessGroupPatch", "run_flask_app", "broadcast_nccl_unique_id", "comm"},
+    "bagua.torch_api.communication": {"run_flask_app"},
     "bagua.torch_api.contrib.fuse.optimizer": {"flatten_tensors_with_closure", "flatten_params_and_states", "group_tensors", "infer_state_tensors",
                                                "make_optimizer_instance", "fuse_step", "do_fuse", "check_optimizer", "sync_param_group_scalars",
                                                "sync_optimizer_state", "get_tensor_state", "get_optimizer_param_states"},
@@ -264,3 +263,88 @@ def test_every_module_path_of_the_reference_package_imports():
         except Exception as e:  # noqa: BLE001
             missing.append(f"{name}: {type(e).__name__}: {e}")
     assert not missing, missing
+
+
+def _compat_symbols_worker(rank, world):
+    """Helpers of the reference that user code may touch: comm.WORLD, the ProcessGroup patch class, NCCL-id broadcast through the
+    store, the abstract DDP interface and what the concrete wrapper fills in."""
+    import base64
+
+    import torch
+    import torch.distributed as dist
+
+    import bagua.torch_api as bagua
+    from bagua.torch_api import communication as C
+    from bagua.torch_api.data_parallel.distributed import DistributedDataParallel_V1_9_0_Interface
+
+    bagua.init_process_group()
+    assert C.comm.WORLD is C.CommMember.WORLD
+    t = torch.ones(3) * (rank + 1)
+    bagua.allreduce_inplace(t, comm=C.comm.WORLD)
+    assert t.tolist() == [3.0, 3.0, 3.0]
+    pg = dist.group.WORLD
+    assert pg.bagua_patch() is pg and isinstance(pg.bagua_pg, C.BaguaProcessGroup) and pg.bagua_get_global_communicator().nranks() == world
+    assert dist.ProcessGroup.bagua_patch is C.BaguaProcessGroupPatch.bagua_patch
+    ident = C.broadcast_nccl_unique_id("test_comm_key", root=1)
+    assert len(base64.b64decode(ident)) == 128
+    gathered = [None] * world
+    dist.all_gather_object(gathered, ident)
+    assert gathered[0] == gathered[1], "every rank must hold the id that rank 1 generated"
+
+    iface = DistributedDataParallel_V1_9_0_Interface()
+    for call in (lambda: iface.scatter((), {}, [0]), lambda: iface.gather([], 0), lambda: iface.register_comm_hook(None, None), iface.will_sync_module_buffers):
+        try:
+            call()
+            raise AssertionError("the interface must stay abstract")
+        except NotImplementedError:
+            pass
+    net = torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.BatchNorm1d(4))
+    ddp = bagua.data_parallel.DistributedDataParallel(net, optimizers=[torch.optim.SGD(net.parameters(), lr=0.1)])
+    assert ddp.will_sync_module_buffers() is True and ddp.train(False) is ddp and not ddp.training and ddp.train() is ddp
+    assert all(callable(getattr(ddp, m)) for m in ("scatter", "to_kwargs", "gather"))   # device movers: exercised on GPUs only
+    for call in (lambda: ddp.join(), lambda: ddp.register_comm_hook(None, None)):
+        try:
+            call()
+            raise AssertionError("unsupported DDP features must say so")
+        except NotImplementedError as e:
+            assert str(e)
+    return True
+
+
+def test_compat_symbols_of_the_reference_modules():
+    from tests.mp_utils import run_distributed
+
+    assert all(run_distributed(_compat_symbols_worker, world=2))
+
+
+def test_sampler_and_cache_compat_methods():
+    import torch
+
+    from bagua.torch_api.contrib.cache_loader import BatchFetcher
+    from bagua.torch_api.contrib.load_balancing_data_loader import LoadBalancingDistributedBatchSampler, LoadBalancingDistributedSampler
+    from bagua_b200.contrib.utils.store import MemoryStore
+
+    data = [torch.zeros(n) for n in (5, 1, 9, 3, 7, 2, 8, 4)]
+    s = LoadBalancingDistributedSampler(data, complexity_fn=len, num_replicas=2, rank=1, shuffle=True, seed=3)
+    s.set_epoch(2)
+    chunks, order = s.shuffle_chunks()
+    assert sorted(i for c in chunks for i in c) == list(range(8)) and sorted(order) == list(range(4)) and all(len(c) == 2 for c in chunks)
+    assert list(s) == [chunks[i][1] for i in order]                      # replica 1 reads column 1 of the chunks in this epoch's order
+    assert all(abs(len(data[a]) - len(data[b])) <= 2 for a, b in chunks)   # neighbours in cost (jitter of at most 1 here)
+    bs = LoadBalancingDistributedBatchSampler(LoadBalancingDistributedSampler(data, complexity_fn=len, num_replicas=2, rank=0), batch_fn=lambda idx: [idx[i:i + 3] for i in range(0, len(idx), 3)])
+    before = list(bs)
+    bs.generate_batches()
+    assert list(bs) == before and len(bs) == 2
+
+    store = MemoryStore()
+    f = BatchFetcher(store, read_buffer_size=4, writer_buffer_size=2)
+    assert f.read("a") is None
+    f.write("a", {"x": 1})
+    assert f.read("a") == {"x": 1} and store.get("a") is None and list(f.write_map) == ["a"]     # still buffered
+    f.write("b", [2])
+    assert store.get("a") is not None and not f.write_map                                        # the buffer reached its size
+    f.write("c", 3)
+    f.write_post_read()
+    assert store.get("c") is None
+    f.flush_write_map()
+    assert f.read("c") == 3 and store.get("c") is not None
