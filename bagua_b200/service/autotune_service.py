@@ -242,6 +242,37 @@ class AutotuneService:
         return server
 
 
+    def setup_app(self, app):
+        """Register the same five routes on a Flask application (``app.route(rule, methods=[...])``) — how the reference builds its
+        server (autotune_service.py:278-410, ``AutotuneService.setup_app``).  The built-in server of :meth:`make_server` does not
+        need Flask; this is for embedding the service into an existing Flask / WSGI deployment.  Returns ``app``."""
+        service = self
+
+        def bind(rule: str, fn, methods):
+            def view():
+                try:
+                    req = None
+                    if "POST" in methods:
+                        from flask import request   # only a Flask deployment gets here
+
+                        req = json.loads(request.get_data(as_text=True) or "{}")
+                    code, body = fn(req)
+                except Exception as e:  # noqa: BLE001
+                    logger.exception("autotune service error")
+                    code, body = 500, str(e)
+                return (body if isinstance(body, str) else json.dumps(body, cls=_Encoder)), code, {"Content-Type": "application/json"}
+
+            view.__name__ = "bagua_autotune_" + rule.rsplit("/", 1)[-1]
+            app.route(rule, methods=list(methods))(view)
+
+        bind("/api/v1/register_tensors", service.register_tensors, ("POST",))
+        bind("/api/v1/report_metrics", service.report_metrics, ("POST",))
+        bind("/api/v1/ask_hyperparameters", service.ask_hyperparameters, ("POST",))
+        bind("/api/v1/report_tensor_execution_order", service.report_tensor_execution_order, ("POST",))
+        bind("/api/v1/health_check", service.health_check, ("GET",))
+        return app
+
+
 def run_autotune_server(port: int, world_size: int, **kwargs):
     """Serve forever (entry point of the daemon process on rank 0)."""
     from .. import env

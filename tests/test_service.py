@@ -142,3 +142,41 @@ def test_service_picks_the_kernel_variant_per_bucket_from_the_measured_table():
     forced = BaguaHyperparameter().update(dict(hp, allreduce_variant="two_shot"))
     assert service.apply_variant_table(mgr, forced).bucket_variants == []
     server.shutdown()
+
+
+def test_setup_app_registers_the_rest_routes_on_a_flask_like_application(monkeypatch):
+    """``AutotuneService.setup_app(app)`` (reference autotune_service.py:278-410): the five routes, served through Flask's calling
+    convention — checked with a stand-in ``flask`` module (Flask is not installed here) against the same service object."""
+    import json
+    import sys
+    import types
+
+    from bagua_b200.service.autotune_service import AutotuneService
+
+    class FakeApp:
+        def __init__(self):
+            self.views = {}
+
+        def route(self, rule, methods):
+            def deco(fn):
+                self.views[(rule, tuple(methods))] = fn
+                return fn
+            return deco
+
+    fake = types.ModuleType("flask")
+    fake.request = types.SimpleNamespace(get_data=lambda as_text=True: fake.body)
+    monkeypatch.setitem(sys.modules, "flask", fake)
+    service = AutotuneService(world_size=1, autotune_level=0)
+    app = service.setup_app(FakeApp())
+    assert sorted(r for r, _ in app.views) == ["/api/v1/ask_hyperparameters", "/api/v1/health_check", "/api/v1/register_tensors", "/api/v1/report_metrics",
+                                               "/api/v1/report_tensor_execution_order"]
+    body, code, headers = app.views[("/api/v1/health_check", ("GET",))]()
+    assert code == 200 and json.loads(body) == {"status": "ok"} and headers["Content-Type"] == "application/json"
+    fake.body = json.dumps({"model_name": "m", "whether_to_bucket": True,
+                            "tensor_list": [{"name": "a", "num_elements": 10, "dtype": "f32"}, {"name": "b", "num_elements": 20, "dtype": "f32"}]})
+    body, code, _ = app.views[("/api/v1/register_tensors", ("POST",))]()
+    reply = json.loads(body)
+    assert code == 200 and [t["name"] for b in reply["recommended_hyperparameters"]["buckets"] for t in b] == ["a", "b"]
+    fake.body = "{not json"
+    _, code, _ = app.views[("/api/v1/report_metrics", ("POST",))]()
+    assert code == 500
