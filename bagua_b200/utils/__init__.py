@@ -1,6 +1,7 @@
 """Small host-side helpers (reference: bagua/torch_api/utils.py:1-244)."""
 from __future__ import annotations
 
+import logging
 import math
 import time
 from collections import OrderedDict
@@ -21,6 +22,8 @@ __all__ = [
     "align_size",
     "GraphedTrainStep",
 ]
+
+LOGGER = logging.getLogger(__name__)   # reference utils.py:10
 
 
 def flatten(tensors: List[torch.Tensor]) -> torch.Tensor:
