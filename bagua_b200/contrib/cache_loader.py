@@ -18,13 +18,13 @@ logger = logging.getLogger(__name__)
 _MISSING = object()
 
 
-def serialize(obj: Any) -> bytes:
+def serialize(input: Any) -> bytes:  # noqa: A002 - parameter name of the reference (cache_loader.py:9-14)
     """Wire format of cached values (pickle, highest protocol)."""
-    return pickle.dumps(obj, protocol=pickle.HIGHEST_PROTOCOL)
+    return pickle.dumps(input, protocol=pickle.HIGHEST_PROTOCOL)
 
 
-def deserialize(blob: bytes) -> Any:
-    return pickle.loads(blob)
+def deserialize(input: bytes) -> Any:  # noqa: A002
+    return pickle.loads(input)
 
 
 def _make_store(backend: str, options: dict):

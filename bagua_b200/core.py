@@ -84,12 +84,12 @@ def dtype_code(dtype: torch.dtype) -> int:
         raise ValueError(f"unsupported tensor dtype {dtype} (supported: {list(DTYPE_CODE)})") from None
 
 
-def to_bagua_datatype(dtype: torch.dtype) -> TensorDtype:
+def to_bagua_datatype(datatype: torch.dtype) -> TensorDtype:
     """torch dtype → :class:`TensorDtype` (reference: bagua/torch_api/utils.py:81-92, plus bf16)."""
     try:
-        return _DTYPE_ENUM[dtype]
+        return _DTYPE_ENUM[datatype]
     except KeyError:
-        raise ValueError(f"unsupported data type {dtype}.") from None
+        raise ValueError(f"unsupported data type {datatype}.") from None
 
 
 def stream_ptr(stream: "torch.cuda.Stream | None" = None) -> int:

@@ -55,22 +55,22 @@ def parse_args(argv=None):
     return parser.parse_args(argv)
 
 
-def set_bagua_env(args, env: dict):
+def set_bagua_env(args, current_env: dict):
     """CLI flags → ``BAGUA_*`` environment (reference launch.py:157-179)."""
-    env["BAGUA_SERVICE_PORT"] = str(args.bagua_service_port)
-    env["BAGUA_DEFAULT_BUCKET_SIZE"] = str(args.default_bucket_size)
-    env["BAGUA_AUTOTUNE"] = str(args.autotune_level)
-    env["BAGUA_IS_OUTPUT_AUTOTUNE_LOG"] = str(int(args.is_output_autotune_log))
-    env["BAGUA_REPORT_METRICS"] = str(int(args.report_metrics))
-    env["BAGUA_AUTOTUNE_MAX_SAMPLES"] = str(args.autotune_max_samples)
-    env["BAGUA_AUTOTUNE_SAMPLING_CONFIDENCE_TIME_S"] = str(args.autotune_sampling_confidence_time)
-    env["BAGUA_AUTOTUNE_WARMUP_TIME_S"] = str(args.autotune_warmup_time)
+    current_env["BAGUA_SERVICE_PORT"] = str(args.bagua_service_port)
+    current_env["BAGUA_DEFAULT_BUCKET_SIZE"] = str(args.default_bucket_size)
+    current_env["BAGUA_AUTOTUNE"] = str(args.autotune_level)
+    current_env["BAGUA_IS_OUTPUT_AUTOTUNE_LOG"] = str(int(args.is_output_autotune_log))
+    current_env["BAGUA_REPORT_METRICS"] = str(int(args.report_metrics))
+    current_env["BAGUA_AUTOTUNE_MAX_SAMPLES"] = str(args.autotune_max_samples)
+    current_env["BAGUA_AUTOTUNE_SAMPLING_CONFIDENCE_TIME_S"] = str(args.autotune_sampling_confidence_time)
+    current_env["BAGUA_AUTOTUNE_WARMUP_TIME_S"] = str(args.autotune_warmup_time)
     if args.autotune_level > 0:
-        env["AUTO_TUNE_SERVER_ADDR"] = f"{args.master_addr}:{args.bagua_service_port}"
+        current_env["AUTO_TUNE_SERVER_ADDR"] = f"{args.master_addr}:{args.bagua_service_port}"
     if getattr(args, "enable_bagua_net", False):
         from ..net import enable as enable_net_plugin
 
-        enable_net_plugin(env)  # NCCL_NET_PLUGIN=bagua + LD_LIBRARY_PATH (reference launch.py:102-107 does the same for libnccl-net.so)
+        enable_net_plugin(current_env)  # NCCL_NET_PLUGIN=bagua + LD_LIBRARY_PATH (reference launch.py:102-107 does the same for libnccl-net.so)
 
 
 def _die_with_parent():

@@ -28,8 +28,8 @@ def get_args_parser() -> ArgumentParser:
     return parser
 
 
-def parse_args(argv=None):
-    return get_args_parser().parse_args(argv)
+def parse_args(args=None):
+    return get_args_parser().parse_args(args)
 
 
 def run(args):
@@ -49,8 +49,8 @@ def run(args):
     torch_run(args)
 
 
-def main(argv=None):
-    args = parse_args(argv)
+def main(args=None):
+    args = parse_args(args)
     run(args)
 
 

@@ -80,10 +80,10 @@ class AutotuneTaskManager:
     split_bucket_by_bucket_size = staticmethod(split_bucket_by_bucket_size)
 
     @staticmethod
-    def record_autotune_log(path: str, autotune_hp: dict, train_iter: int, score: float):
+    def record_autotune_log(autotune_logfile_path: str, autotune_hp: dict, train_iter: int, score: float):
         cols = dict(autotune_hp)
         cols.update({"train_iter": train_iter, "score": score})
-        with open(path, "a", newline="") as f:
+        with open(autotune_logfile_path, "a", newline="") as f:
             w = csv.DictWriter(f, fieldnames=sorted(cols.keys()))
             if f.tell() == 0:
                 w.writeheader()

@@ -5,7 +5,7 @@ the initial design (the reference also starts from 20 Halton points)."""
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Tuple, Union
+from typing import Optional, Dict, List, Tuple, Union
 
 import numpy as np
 
@@ -51,7 +51,14 @@ _PRIMES = [2, 3, 5, 7, 11, 13, 17, 19, 23, 29]
 class BayesianOptimizer:
     """Maximises a black-box score.  ``tell(params, score)`` feeds an observation, ``ask()`` proposes the next point."""
 
-    def __init__(self, param_declaration: Dict[str, Param], n_initial_points: int = 20, seed: int = 0):
+    def __init__(self, param_declaration: Dict[str, Param], n_initial_points: int = 20, initial_point_generator: str = "halton",
+                 random_state: Optional[int] = 0, seed: Optional[int] = None):
+        """Signature of the reference (bayesian_optimizer.py:39-57, a thin wrapper of ``skopt.Optimizer``); ``seed`` is an alias of
+        ``random_state``.  ``initial_point_generator``: ``"halton"`` (default) or ``"random"``."""
+        if initial_point_generator not in ("halton", "random"):
+            raise ValueError("initial_point_generator must be 'halton' or 'random'")
+        self.initial_point_generator = initial_point_generator
+        seed = seed if seed is not None else (random_state if random_state is not None else 0)
         self.param_declaration = dict(sorted(param_declaration.items()))
         self.names = list(self.param_declaration.keys())
         self.n_initial_points = n_initial_points
@@ -89,6 +96,8 @@ class BayesianOptimizer:
         self._y.append(float(score))
 
     def _initial_point(self) -> List[float]:
+        if self.initial_point_generator == "random":
+            return self._rng.rand(len(self.names)).tolist()
         i = self._asked + 1
         return [_halton(i, _PRIMES[d % len(_PRIMES)]) for d in range(len(self.names))]
 

@@ -348,3 +348,58 @@ def test_sampler_and_cache_compat_methods():
     assert store.get("c") is None
     f.flush_write_map()
     assert f.read("c") == 3 and store.get("c") is not None
+
+
+def test_public_signatures_accept_the_reference_parameter_names():
+    """Every public function / method of the reference's python package (when the tree is mounted) can be called here with the
+    reference's parameter NAMES in the reference's ORDER — keyword call sites in user code keep working."""
+    import ast
+    import importlib
+    import inspect
+    import os
+
+    root = "/root/reference/bagua"
+    if not os.path.isdir(root):
+        pytest.skip("reference tree not mounted")
+    allowed = {("bagua.torch_api.algorithms.gradient_allreduce", "GradientAllReduceAlgorithmImpl.init_operations")}   # the reference names it "_"
+    problems, checked = [], 0
+    for d, _, files in os.walk(root):
+        for f in files:
+            if not f.endswith(".py"):
+                continue
+            path = os.path.join(d, f)
+            mod = os.path.relpath(path, "/root/reference")[:-3].replace("/", ".")
+            mod = mod[: -len(".__init__")] if mod.endswith(".__init__") else mod
+            try:
+                m = importlib.import_module(mod)
+                tree = ast.parse(open(path).read())
+            except Exception:  # noqa: BLE001 - import gaps are the business of the tests above
+                continue
+            items = []
+            for n in tree.body:
+                if isinstance(n, ast.FunctionDef) and not n.name.startswith("_"):
+                    items.append((n.name, n))
+                elif isinstance(n, ast.ClassDef) and not n.name.startswith("_"):
+                    items += [(f"{n.name}.{k.name}", k) for k in n.body if isinstance(k, ast.FunctionDef) and (k.name == "__init__" or not k.name.startswith("_"))]
+            for name, node in items:
+                obj = m
+                for part in name.split("."):
+                    obj = getattr(obj, part, None)
+                    if obj is None:
+                        break
+                if obj is None or (mod, name) in allowed:
+                    continue
+                try:
+                    params = list(inspect.signature(obj).parameters.values())
+                except (TypeError, ValueError):
+                    continue
+                ref = [a.arg for a in node.args.posonlyargs + node.args.args if a.arg not in ("self", "cls")]
+                ours = [p.name for p in params if p.name not in ("self", "cls")]
+                takes_kwargs = any(p.kind == p.VAR_KEYWORD for p in params)
+                missing = [a for a in ref if a not in ours and not takes_kwargs]
+                positional = [p.name for p in params if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD) and p.name not in ("self", "cls")]
+                if missing or [a for a in ref if a in positional] != [a for a in positional if a in ref]:
+                    problems.append(f"{mod}.{name}: reference {ref}, here {ours}")
+                checked += 1
+    assert not problems, problems
+    assert checked > 150
