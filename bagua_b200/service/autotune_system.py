@@ -14,7 +14,7 @@ import sys
 from .bayesian_optimizer import BayesianOptimizer, IntParam
 
 
-def sysperf(host_list: str, nproc_per_node: int, ssh_port: int, env: dict, model: str = "vgg16", extra_args=(), master_port: int = 0) -> float:
+def sysperf(host_list: str, nproc_per_node: int, ssh_port: int, env: dict = {}, model: str = "vgg16", extra_args=(), master_port: int = 0) -> float:
     """One measurement: total img/s printed by ``bagua_sys_perf`` under ``env`` (0.0 when the run failed)."""
     full_env = dict(os.environ)
     full_env.update({k: str(v) for k, v in env.items()})
