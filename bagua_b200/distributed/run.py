@@ -25,6 +25,9 @@ def get_args_parser() -> ArgumentParser:
 
     parser = torch_parser()
     add_bagua_arguments(parser)
+    if not any("--use_env" in a.option_strings or "--use-env" in a.option_strings for a in parser._actions):
+        # torch ≥ 1.10 always passes LOCAL_RANK through the environment; the reference's launcher still takes the switch (run.py:424-430)
+        parser.add_argument("--use_env", "--use-env", default=True, action="store_true", help="accepted for compatibility: LOCAL_RANK is always set in the environment")
     return parser
 
 

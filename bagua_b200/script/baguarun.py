@@ -18,27 +18,65 @@ from typing import List
 
 def parse_args(argv=None):
     p = argparse.ArgumentParser(description="launch a bagua_b200 job on several hosts over ssh")
-    p.add_argument("--host_list", type=str, default=os.environ.get("BAGUA_NODE_DOMAIN_NAMES", ""), help="comma separated hosts (first = master)")
-    p.add_argument("--ssh_port", type=int, default=int(os.environ.get("BAGUA_SSH_PORT", 22)))
+    p.add_argument("--host_list", type=str, default=None,
+                   help="comma separated hosts, first = master; either plain (`a,b`, ssh port from --ssh_port / $BAGUA_SSH_PORT) or with the ssh port inline "
+                        "(`a:22,b:8022`). Default: $BAGUA_NODE_DOMAIN_NAMES")
+    p.add_argument("--ssh_port", type=int, default=None)
     p.add_argument("--nproc_per_node", type=int, default=1)
     p.add_argument("--master_port", type=int, default=29500)
-    p.add_argument("-x", dest="export_env", action="append", default=[], help="environment variable to forward to every host")
+    p.add_argument("--bagua_service_port", type=int, default=None, help="forwarded to the launcher on every host")
+    p.add_argument("--no_python", action="store_true", default=False, help="forwarded to the launcher: the script is an executable, not a python file")
+    p.add_argument("--enable_bagua_net", action="store_true", default=False, help="forwarded to the launcher: NCCL loads the Bagua-Net plugin")
+    p.add_argument("-x", dest="export_env", action="append", default=[], help="environment variable to forward to every host: NAME (current value) or NAME=VALUE")
     p.add_argument("--dry_run", action="store_true", help="print the per-host commands instead of running them")
     p.add_argument("launch_args", nargs=argparse.REMAINDER, help="[launcher flags] script [script args]")
-    return p.parse_args(argv)
+    args = p.parse_args(argv)
+    if args.host_list is None:
+        args.host_list = os.environ.get("BAGUA_NODE_DOMAIN_NAMES", "")
+    if args.ssh_port is None:
+        args.ssh_port = int(os.environ.get("BAGUA_SSH_PORT", 22))
+    return args
+
+
+def host_pairs(args) -> List[tuple]:
+    """``[(host, ssh_port)]`` from either form of ``--host_list`` (reference baguarun.py:176-190)."""
+    pairs = []
+    for item in (h.strip() for h in args.host_list.split(",")):
+        if not item:
+            continue
+        host, sep, port = item.rpartition(":")
+        if sep and port.isdigit() and host and "]" not in port:
+            pairs.append((host, int(port)))
+        else:
+            pairs.append((item, args.ssh_port))
+    return pairs
 
 
 def build_commands(args) -> List[List[str]]:
-    hosts = [h.strip() for h in args.host_list.split(",") if h.strip()]
+    hosts = host_pairs(args)
     if not hosts:
         raise SystemExit("baguarun: --host_list (or BAGUA_NODE_DOMAIN_NAMES) is required")
-    exports = " ".join(f"{k}={shlex.quote(os.environ[k])}" for k in args.export_env if k in os.environ)
+    exported = {}
+    for item in args.export_env:
+        name, sep, value = item.partition("=")
+        if sep:
+            exported[name] = value
+        elif name in os.environ:
+            exported[name] = os.environ[name]
+    exports = " ".join(f"{k}={shlex.quote(v)}" for k, v in exported.items())
+    passthrough = []
+    if args.bagua_service_port:
+        passthrough.append(f"--bagua_service_port={args.bagua_service_port}")
+    if args.no_python:
+        passthrough.append("--no_python")
+    if args.enable_bagua_net:
+        passthrough.append("--enable_bagua_net")
     cmds = []
-    for i, host in enumerate(hosts):
+    for i, (host, port) in enumerate(hosts):
         remote = (f"cd {shlex.quote(os.getcwd())} && {exports} {shlex.quote(sys.executable)} -m bagua_b200.distributed.launch "
-                  f"--nnodes={len(hosts)} --node_rank={i} --nproc_per_node={args.nproc_per_node} --master_addr={hosts[0]} --master_port={args.master_port} "
-                  + " ".join(shlex.quote(a) for a in args.launch_args))
-        cmds.append(["ssh", "-o", "StrictHostKeyChecking=no", "-p", str(args.ssh_port), host, remote])
+                  f"--nnodes={len(hosts)} --node_rank={i} --nproc_per_node={args.nproc_per_node} --master_addr={hosts[0][0]} --master_port={args.master_port} "
+                  + " ".join(passthrough + [shlex.quote(a) for a in args.launch_args]))
+        cmds.append(["ssh", "-o", "StrictHostKeyChecking=no", "-p", str(port), host, remote])
     return cmds
 
 

@@ -159,6 +159,14 @@ def test_baguarun_starts_one_launcher_per_host_and_propagates_failure(tmp_path):
                        env=env, capture_output=True, text=True)
     lines = d.stdout.strip().splitlines()
     assert len(lines) == 3 and "--nnodes=3" in lines[2] and "--node_rank=2" in lines[2] and "--master_addr=a" in lines[2] and lines[2].rstrip("'").endswith("train.py --lr 1")
+    # both --host_list forms, NAME=VALUE exports and the flags that are handed on to the per-host launcher (reference baguarun.py:61-71,176-203)
+    d = subprocess.run([sys.executable, "-m", "bagua_b200.script.baguarun", "--host_list", "a:2201,b", "--ssh_port", "2022", "--nproc_per_node", "4", "--dry_run",
+                        "--bagua_service_port", "29600", "--no_python", "--enable_bagua_net", "-x", "FOO=bar baz", "-x", "BAGUA_TEST_MARK", "./train.sh", "--lr", "1"],
+                       env=env, capture_output=True, text=True)
+    lines = d.stdout.strip().splitlines()
+    assert len(lines) == 2 and " -p 2201 a " in lines[0] and " -p 2022 b " in lines[1], d.stdout + d.stderr
+    for flag in ("--bagua_service_port=29600", "--no_python", "--enable_bagua_net", "--master_addr=a", "FOO=", "bar baz", "BAGUA_TEST_MARK=forwarded"):
+        assert flag in lines[1], (flag, lines[1])
 
 
 def test_bagua_doctor_reports_and_self_tests():
