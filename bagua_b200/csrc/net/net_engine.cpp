@@ -199,6 +199,17 @@ IfFilter parse_ifname_filter() {
     return f;
 }
 
+// NCCL_SOCKET_FAMILY restricts the address family of the interfaces considered: NCCL's own spelling (AF_INET / AF_INET6), the
+// reference's numeric sa_family value (rust/bagua-net/src/utils.rs:33-36,101: 2 / 10) or plain 4 / 6; anything else = no restriction.
+int parse_socket_family() {
+    const char* v = getenv("NCCL_SOCKET_FAMILY");
+    if (!v || !*v) return -1;
+    std::string s(v);
+    if (s == "AF_INET" || s == "4" || s == std::to_string(AF_INET)) return AF_INET;
+    if (s == "AF_INET6" || s == "6" || s == std::to_string(AF_INET6)) return AF_INET6;
+    return -1;
+}
+
 int read_speed(const std::string& ifn) {
     FILE* fp = fopen(("/sys/class/net/" + ifn + "/speed").c_str(), "r");
     int sp = -1;
@@ -219,12 +230,14 @@ std::string read_pci_path(const std::string& ifn) {
 std::vector<NetDevice> discover_devices() {
     std::vector<NetDevice> devs, fallback;
     IfFilter filt = parse_ifname_filter();
+    const int want_family = parse_socket_family();
     ifaddrs* list = nullptr;
     if (getifaddrs(&list) != 0) return devs;
     for (ifaddrs* it = list; it; it = it->ifa_next) {
         if (!it->ifa_addr || !(it->ifa_flags & IFF_UP) || !(it->ifa_flags & IFF_RUNNING)) continue;
         const int fam = it->ifa_addr->sa_family;
         if (fam != AF_INET && fam != AF_INET6) continue;
+        if (want_family != -1 && fam != want_family) continue;
         if (fam == AF_INET6) {
             auto* a6 = reinterpret_cast<sockaddr_in6*>(it->ifa_addr);
             if (IN6_IS_ADDR_LINKLOCAL(&a6->sin6_addr)) continue;

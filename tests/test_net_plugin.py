@@ -172,3 +172,45 @@ print("TRACE_OK")
     events = json.loads((tmp_path / "spans.3.json").read_text())
     assert sorted((e["name"], e["args"]["bytes"]) for e in events) == sorted([(k, n) for n in (64, 100000, 3 << 20) for k in ("isend", "irecv")])
     assert all(e["ph"] == "X" and e["pid"] == 3 and e["dur"] >= 0 and e["args"]["ok"] for e in events)
+
+
+@pytest.mark.parametrize("family", ["AF_INET", "2", "4", "AF_INET6", "nonsense"])
+def test_socket_family_filter(family):
+    """NCCL_SOCKET_FAMILY (reference rust/bagua-net/src/utils.rs:33-36,101): NCCL's spelling, the numeric sa_family and 4 / 6 select
+    the address family of the candidate interfaces; an unknown value means no restriction.  IPv4 loopback always exists here; IPv6
+    may not, in which case the filtered list is empty and the plugin says so instead of picking an IPv4 address."""
+    import subprocess
+    import sys
+
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys
+sys.path.insert(0, %r)
+import numpy as np
+from bagua_b200 import net as bnet
+try:
+    h = bnet.PluginHandle()
+    devs = h.devices()
+except Exception as e:
+    print("NO_DEVICE", type(e).__name__)
+    raise SystemExit(0)
+if not devs:
+    print("NO_DEVICE empty")
+    raise SystemExit(0)
+handle, lc = h.listen(0)
+sc = h.connect(handle)
+rc = h.accept(lc)
+src = np.arange(100000, dtype=np.uint8); dst = np.zeros(100000, dtype=np.uint8)
+r = h.irecv(rc, dst.ctypes.data, src.size); s = h.isend(sc, src.ctypes.data, src.size)
+h.wait(s); h.wait(r)
+assert (src == dst).all()
+h.close_send(sc); h.close_recv(rc); h.close_listen(lc)
+print("ROUNDTRIP_OK", devs[0]["name"])
+''' % repo
+    env = dict(os.environ, NCCL_SOCKET_IFNAME="lo", NCCL_SOCKET_FAMILY=family)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    if family in ("AF_INET", "2", "4", "nonsense"):
+        assert "ROUNDTRIP_OK lo" in r.stdout, r.stdout + r.stderr
+    else:
+        assert "ROUNDTRIP_OK lo" in r.stdout or "NO_DEVICE" in r.stdout, r.stdout + r.stderr
