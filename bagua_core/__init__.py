@@ -147,6 +147,30 @@ class BaguaBucketPy:
 
         self.inner.append_python_op(run, "decentralized_synchronous")
 
+    def append_low_precision_decentralized_synchronous_op(self, communicator_internode=None, communicator_intranode=None, hierarchical: bool = True,
+                                                           peer_selection_mode: str = "ring", compression: str = "MinMaxUInt8", weight: Optional["BaguaTensorPy"] = None,
+                                                           left_peer_weight: Optional["BaguaTensorPy"] = None, right_peer_weight: Optional["BaguaTensorPy"] = None):
+        """Ring exchange of MinMaxUInt8-compressed weight differences with the left and right neighbour (bagua-core-py/src/lib.rs:479-502;
+        comm_ops/decentralized_low_precision_synchronous.rs): the bucket holds the freshly stepped weights, ``weight`` / ``left_peer_weight`` /
+        ``right_peer_weight`` are the replicas the algorithm keeps between steps."""
+        from bagua_b200 import communication as comm_mod
+        from bagua_b200.ops import quant
+
+        assert compression == "MinMaxUInt8", f"unknown compression {compression}"
+        assert weight is not None and left_peer_weight is not None and right_peer_weight is not None
+        pg = comm_mod._get_default_group()
+        self.inner.append_python_op(lambda _name: quant.low_precision_ring_fallback(self, pg, weight.torch_tensor, left_peer_weight.torch_tensor,
+                                                                                    right_peer_weight.torch_tensor), "low_precision_decentralized_synchronous")
+
+    def append_decentralized_asynchronous_op(self, communicator_internode=None, communicator_intranode=None, peer_selection_mode: str = "all", torch_stream: int = 0):
+        """Model averaging that runs beside training (bagua-core-py/src/lib.rs:504-519): every execution snapshots the bucket, averages the
+        snapshot over all ranks and adds ``average − snapshot`` to the live tensors under the weight lock.  Returns the op object with the
+        reference's ``lock_weight / unlock_weight / abort / reset / get_status``."""
+        assert peer_selection_mode == "all", "only peer_selection_mode='all' is supported (as in the reference)"
+        op = DecentralizedFullPrecisionAsynchronousPy(self)
+        self.inner.append_python_op(op.run, "decentralized_asynchronous")
+        return op
+
     def print_ops(self):
         print(self.inner.print_ops())
 
@@ -158,6 +182,57 @@ class BaguaBucketPy:
 
     def reset_comm_ready(self):
         self.inner.reset_comm_ready()
+
+
+class DecentralizedFullPrecisionAsynchronousPy:
+    """Handle of an asynchronous model-average op on loose tensors (reference: bagua-core-py/src/lib.rs:394-428 over
+    comm_ops/decentralized_full_precision_asynchronous.rs)."""
+
+    def __init__(self, bucket: "BaguaBucketPy"):
+        import threading
+
+        self._bucket = bucket
+        self._lock = threading.Lock()
+        self._aborted = False
+
+    def lock_weight(self):
+        self._lock.acquire()
+
+    def unlock_weight(self):
+        if self._lock.locked():
+            self._lock.release()
+
+    def abort(self):
+        self._aborted = True
+
+    def reset(self):
+        self._aborted = False
+
+    def get_status(self) -> bool:
+        """True while the op takes part in averaging rounds."""
+        return not self._aborted
+
+    def run(self, _name: str = ""):
+        import torch.distributed as dist
+
+        from bagua_b200 import communication as comm_mod
+
+        pg = comm_mod._get_default_group()
+        # every rank must agree on whether this round happens: MIN over "I am still running" (the reference negotiates the same way)
+        go = torch.tensor([0 if self._aborted else 1], dtype=torch.int32)
+        dist.all_reduce(go, op=dist.ReduceOp.MIN, group=pg.torch_group)
+        if int(go.item()) == 0:
+            return
+        snapshot, _ = self._bucket._flat_or_gather()
+        avg = snapshot.clone()
+        dist.all_reduce(avg, group=pg.torch_group)
+        avg.div_(pg.size())
+        with self._lock, torch.no_grad():
+            off = 0
+            for t in (bt.torch_tensor for bt in self._bucket._tensors):
+                n = t.numel()
+                t.add_((avg[off: off + n] - snapshot[off: off + n]).view_as(t))
+                off += n
 
 
 class BaguaCommBackendPy:

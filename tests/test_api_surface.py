@@ -223,15 +223,57 @@ def _core_shim_ops_worker(rank, world):
     backend2.register_ordered_buckets([b2])
     backend2.mark_communication_ready(tc, 0)
     backend2.wait_pending_comm_ops()
-    return plain, c.clone(), peer.clone()
+    # low-precision decentralized ring + asynchronous average on loose tensors (bagua-core-py/src/lib.rs:479-519)
+    w0 = torch.linspace(0, 1, 32)
+    x = w0 + 0.1 * (rank + 1)                         # "weights after the local step"
+    tx = B.BaguaTensorPy("x", x)
+    weight, left, right = w0.clone(), w0.clone(), w0.clone()
+    b3 = B.BaguaBucketPy("bk3", [tx])
+    b3.append_low_precision_decentralized_synchronous_op(None, None, hierarchical=False, peer_selection_mode="ring", compression="MinMaxUInt8",
+                                                          weight=B.BaguaTensorPy("w", weight), left_peer_weight=B.BaguaTensorPy("l", left),
+                                                          right_peer_weight=B.BaguaTensorPy("r", right))
+    y = torch.full((6,), float(rank))
+    ty = B.BaguaTensorPy("y", y)
+    b4 = B.BaguaBucketPy("bk4", [ty])
+    op = b4.append_decentralized_asynchronous_op(None, None, peer_selection_mode="all", torch_stream=0)
+    backend3 = B.BaguaCommBackendPy(10, -1)
+    backend3.register_ordered_buckets([b3, b4])
+    assert op.get_status() is True
+    op.lock_weight()
+    y.add_(10.0)                                      # the trainer's update, made while it holds the weights
+    op.unlock_weight()
+    backend3.mark_communication_ready(tx, 0)
+    backend3.mark_communication_ready(ty, 0)
+    backend3.wait_pending_comm_ops()
+    first = y.clone()
+    ring = (x.clone(), weight.clone(), left.clone(), right.clone(), w0)
+    op.abort()
+    assert op.get_status() is False
+    backend3.mark_communication_ready(tx, 0)
+    backend3.mark_communication_ready(ty, 0)
+    backend3.wait_pending_comm_ops()
+    aborted = y.clone()
+    op.reset()
+    assert op.get_status() is True
+    return plain, c.clone(), peer.clone(), ring, (first, aborted)
 
 
 def test_bagua_core_shim_low_level_ops():
     res = run_distributed(_core_shim_ops_worker, world=2)
-    for (a, b), c, peer in res:
+    for rank, ((a, b), c, peer, lp, (first, aborted)) in enumerate(res):
         assert torch.equal(a, torch.full((8,), 1.5)) and torch.equal(b, torch.full((4, 2), 15.0))
         torch.testing.assert_close(c, torch.linspace(-1, 1, 16) * 1.5, rtol=0, atol=0.03)
         torch.testing.assert_close(peer, c, rtol=0, atol=1e-6)      # both ranks hold the same compressed mean → pair average = itself
+        # ring step: with all replicas equal to w0 the difference x + (l + r)/3 - 5w/3 = (x - w0) is what travels (8-bit); every rank's
+        # own replica moves by its own difference, the neighbour replicas by the neighbour's (2 ranks: left = right = the other rank)
+        x, weight, left, right, w0 = lp
+        mine, other = 0.1 * (rank + 1), 0.1 * (2 - rank)
+        torch.testing.assert_close(weight - w0, torch.full((32,), mine), rtol=0, atol=2e-3)
+        torch.testing.assert_close(left - w0, torch.full((32,), other), rtol=0, atol=2e-3)
+        torch.testing.assert_close(right - w0, torch.full((32,), other), rtol=0, atol=2e-3)
+        assert torch.equal(x, weight)
+        # asynchronous average: y = rank + 10 on both ranks → mean 10.5; an aborted op leaves the tensors alone
+        assert torch.equal(first, torch.full((6,), 10.5)) and torch.equal(aborted, first)
 
 
 REFERENCE_MODULES = [
