@@ -29,36 +29,19 @@ class LoadBalancingDistributedSampler(Sampler):
         random_level: 0.0 = strict complexity order … 1.0 = complexities jittered over their whole range.
     """
 
-    def __init__(
-        self,
-        dataset: Dataset,
-        complexity_fn: Callable[..., int],
-        num_replicas: Optional[int] = None,
-        rank: Optional[int] = None,
-        shuffle: bool = True,
-        seed: int = 0,
-        drop_last: bool = False,
-        random_level: float = 0,
-    ) -> None:
-        if num_replicas is None:
-            if not dist.is_available() or not dist.is_initialized():
-                raise RuntimeError("Requires distributed package to be available")
-            num_replicas = dist.get_world_size()
-        if rank is None:
-            if not dist.is_available() or not dist.is_initialized():
-                raise RuntimeError("Requires distributed package to be available")
-            rank = dist.get_rank()
+    def __init__(self, dataset: Dataset, complexity_fn: Callable[..., int], num_replicas: Optional[int] = None, rank: Optional[int] = None,
+                 shuffle: bool = True, seed: int = 0, drop_last: bool = False, random_level: float = 0) -> None:
+        if num_replicas is None or rank is None:
+            if not (dist.is_available() and dist.is_initialized()):
+                raise RuntimeError("num_replicas / rank were not given and there is no initialised process group to take them from")
+            num_replicas = dist.get_world_size() if num_replicas is None else num_replicas
+            rank = dist.get_rank() if rank is None else rank
         if not 0 <= rank < num_replicas:
             raise ValueError(f"Invalid rank {rank}, rank should be in the interval [0, {num_replicas - 1}]")
         if not 0.0 <= random_level <= 1.0:
             raise ValueError(f"random_level must lie in [0.0, 1.0], got {random_level}")
-        self.dataset = dataset
-        self.num_replicas = num_replicas
-        self.rank = rank
-        self.epoch = 0
-        self.drop_last = drop_last
-        self.shuffle = shuffle
-        self.seed = seed
+        self.dataset, self.num_replicas, self.rank = dataset, num_replicas, rank
+        self.shuffle, self.seed, self.drop_last, self.epoch = shuffle, seed, drop_last, 0
         n = len(dataset)  # type: ignore[arg-type]
         rows = (n - num_replicas) / num_replicas if (drop_last and n % num_replicas) else n / num_replicas
         self.num_samples = math.ceil(rows)                 # steps per epoch = rows of the epoch plan
