@@ -29,41 +29,24 @@ class BaguaModule:
             process_group: :class:`BaguaProcessGroup` (default group when ``None``).
             do_flatten: fuse each bucket's tensors into one flat storage (symmetric memory on NVSwitch).
         """
-        if process_group is None:
-            process_group = comm_mod._get_default_group()
-        if not hasattr(self, "_bagua_module_name"):
-            self._bagua_module_name = f"{self.__class__.__name__}_{next(_name_counter)}"
-        self.bagua_ddp = BaguaDistributedDataParallel(
-            self,
-            optimizers=optimizers,
-            algorithm=algorithm,
-            process_group=process_group,
-            bagua_module_name=self.bagua_module_name,
-            gradient_as_bucket_view=do_flatten,
-        )
+        group = process_group if process_group is not None else comm_mod._get_default_group()
+        if getattr(self, "_bagua_module_name", None) is None:
+            self._bagua_module_name = f"{type(self).__name__}_{next(_name_counter)}"
+        # the engine object owns hooks, buckets and the per-name native scheduler; calling with_bagua again replaces it
+        self.bagua_ddp = BaguaDistributedDataParallel(self, optimizers=optimizers, algorithm=algorithm, process_group=group,
+                                                      bagua_module_name=self._bagua_module_name, gradient_as_bucket_view=do_flatten)
         return self
 
-    @property
-    def bagua_module_name(self):
-        """Unique name of the module inside this process (one native scheduler per name)."""
+    def _get_name(self) -> str:
         return self._bagua_module_name
 
-    @bagua_module_name.setter
-    def bagua_module_name(self, name: str):
+    def _set_name(self, name: str) -> None:
         self._bagua_module_name = name
 
-    @property
-    def bagua_algorithm(self):
-        """The reified algorithm (an :class:`AlgorithmImpl`)."""
-        return self.bagua_ddp.bagua_algorithm
-
-    @property
-    def bagua_optimizers(self):
-        return self.bagua_ddp.bagua_optimizers
-
-    @property
-    def bagua_buckets(self):
-        return self.bagua_ddp.bagua_buckets
+    bagua_module_name = property(_get_name, _set_name, doc="Unique name of the module inside this process (one native scheduler per name); settable.")
+    bagua_algorithm = property(lambda self: self.bagua_ddp.bagua_algorithm, doc="The reified algorithm (an :class:`AlgorithmImpl`).")
+    bagua_optimizers = property(lambda self: self.bagua_ddp.bagua_optimizers, doc="Optimizers registered with :meth:`with_bagua`.")
+    bagua_buckets = property(lambda self: self.bagua_ddp.bagua_buckets, doc="The communication buckets of the current algorithm.")
 
 
 def _install():
