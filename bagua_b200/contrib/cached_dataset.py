@@ -19,10 +19,17 @@ class CachedDataset(Dataset):
 
     def __init__(self, dataset: Dataset, backend: str = "redis", dataset_name: str = "", writer_buffer_size: int = 20, **kwargs):
         self.dataset = dataset
+        #: the :class:`CacheLoader` behind this dataset (its ``hits`` / ``misses`` / ``store_errors`` counters tell whether the cache works)
         self.cache_loader = CacheLoader(backend, dataset_name, writer_buffer_size, **kwargs)
 
-    def __getitem__(self, item):
-        return self.cache_loader.get(item, lambda x: self.dataset[x])
-
-    def __len__(self):
+    def __len__(self) -> int:
         return len(self.dataset)
+
+    def __getitem__(self, index):
+        # the sample's position is its cache key; a miss falls through to the wrapped dataset and queues the result for writing
+        return self.cache_loader.get(index, self.dataset.__getitem__)
+
+    def cache_stats(self) -> dict:
+        """``{"hits", "misses", "store_errors"}`` of the underlying loader since construction."""
+        c = self.cache_loader
+        return {"hits": c.hits, "misses": c.misses, "store_errors": c.store_errors}
