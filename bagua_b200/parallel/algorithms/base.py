@@ -27,8 +27,14 @@ class Algorithm:
         return GlobalAlgorithmRegistry.get(name)(**kwargs)
 
 
+def _noop(*_args, **_kwargs):
+    """Default hook body: nothing to do at this point of the step."""
+
+
 class AlgorithmImpl:
-    """Base class of algorithm implementations; every method may be overridden."""
+    """Base class of algorithm implementations; every method may be overridden.  The defaults describe plain gradient communication:
+    gradients are the communicated tensors, the bucketing suggestion is followed, a gradient is marked ready when autograd has
+    accumulated it and the step waits for the scheduler after backward."""
 
     def __init__(self, process_group):
         self.process_group = process_group
@@ -38,21 +44,20 @@ class AlgorithmImpl:
         return False
 
     def init_tensors(self, bagua_ddp) -> List[torch.Tensor]:
-        """Register the tensors to communicate.  Default: every parameter's gradient, in *reverse* parameter order so
+        """Register the tensors to communicate. Default: every parameter's gradient, in *reverse* parameter order so
         bucket 0 holds what backward produces first (reference base.py:87-102)."""
-        parameters = bagua_ddp.bagua_build_params()
-        tensors = []
-        for name, param in reversed(parameters):
-            param = param.bagua_ensure_grad().ensure_bagua_tensor(
-                name,
-                bagua_ddp.bagua_module_name,
-                getter_closure=lambda p: p.grad,
-                setter_closure=lambda p, t: setattr(p, "grad", t),
-            )
-            tensors.append(param)
-        self._communication_tensor_names = set(name for name, _ in parameters)
-        assert len(self._communication_tensor_names) == len(tensors), "tensor names should be unique"
-        return tensors
+        named = bagua_ddp.bagua_build_params()
+        self._communication_tensor_names = {name for name, _ in named}
+        assert len(self._communication_tensor_names) == len(named), "tensor names should be unique"
+
+        def grad_of(p):
+            return p.grad
+
+        def set_grad(p, t):
+            p.grad = t
+
+        return [p.bagua_ensure_grad().ensure_bagua_tensor(name, bagua_ddp.bagua_module_name, getter_closure=grad_of, setter_closure=set_grad)
+                for name, p in reversed(named)]
 
     def tensors_to_buckets(self, tensors: List[List[torch.Tensor]], do_flatten: bool) -> List[BaguaBucket]:
         """Turn the bucketing suggestion into buckets (default: follow it)."""
@@ -60,67 +65,58 @@ class AlgorithmImpl:
 
     def init_forward_pre_hook(self, bagua_ddp) -> Callable:
         """Returns ``hook(input)`` run before every training forward."""
-
-        def hook(input):
-            pass
-
-        return hook
+        return _noop
 
     def init_backward_hook(self, bagua_ddp) -> Callable:
         """Returns ``hook(parameter_name, parameter)`` run when a parameter's gradient has been accumulated."""
-        names = self._communication_tensor_names
+        communicated = self._communication_tensor_names
 
-        def hook(parameter_name, parameter):
-            if parameter_name in names:
-                # the gradient must still be the bucket view registered with the scheduler (zero_grad(set_to_none=True)
-                # or an optimizer that replaces .grad would silently break the aliasing)
-                if parameter._bagua_backend_tensor.data_ptr() != parameter.grad.data_ptr():
-                    raise AssertionError("bagua backend tensor data_ptr should match parameter grad (the gradient must stay the bucket view: "
-                                         "use zero_grad(set_to_none=False) and do not assign a new tensor to .grad)")
-                bagua_ddp.mark_tensor_ready(parameter)
+        def mark_gradient_ready(parameter_name, parameter):
+            if parameter_name not in communicated:
+                return
+            if parameter._bagua_backend_tensor.data_ptr() != parameter.grad.data_ptr():
+                raise AssertionError("bagua backend tensor data_ptr should match parameter grad (the gradient must stay the bucket view: "
+                                     "use zero_grad(set_to_none=False) and do not assign a new tensor to .grad)")
+            bagua_ddp.mark_tensor_ready(parameter)
 
-        return hook
+        return mark_gradient_ready
 
     def init_post_backward_hook(self, bagua_ddp) -> Callable:
         """Returns ``hook()`` run once when the whole backward pass is done."""
-
-        def hook():
-            bagua_ddp.wait_pending_comm_ops()
-
-        return hook
+        return bagua_ddp.wait_pending_comm_ops
 
     def init_post_optimizer_step_hook(self, bagua_ddp) -> Callable:
         """Returns ``hook(optimizer)`` run after every ``optimizer.step()``."""
-
-        def hook(optimizer: torch.optim.Optimizer):
-            pass
-
-        return hook
+        return _noop
 
     def init_operations(self, bagua_ddp, bucket: BaguaBucket):
         """Register the communication ops of ``bucket``."""
 
 
 class _AlgorithmRegistry(dict):
+    """``name → {"algorithm": factory, "description": text}`` (reference base.py:211-263: the same dict-shaped registry, so code
+    that iterates ``GlobalAlgorithmRegistry`` keeps working)."""
+
     def register(self, name: str, algorithm: Callable, description: Optional[str] = None):
-        if not (name is None or isinstance(name, str)):
+        if name is not None and not isinstance(name, str):
             raise TypeError(f"`name` must be a str, found {name}")
         if name in self:
             raise ValueError(f"'{name}' is already present in the registry.")
-        data: Dict[str, Any] = {"algorithm": algorithm, "description": description or ""}
-        self[name] = data
+        entry: Dict[str, Any] = {"algorithm": algorithm, "description": description or ""}
+        self[name] = entry
 
     def get(self, name: str) -> Callable:
-        if name in self:
+        try:
             return self[name]["algorithm"]
-        available = ", ".join(sorted(self.keys())) or "none"
-        raise KeyError(f"'{name}' not found in registry. Available names: {available}")
+        except KeyError:
+            available = ", ".join(sorted(self.keys())) or "none"
+            raise KeyError(f"'{name}' not found in registry. Available names: {available}") from None
 
     def available_algorithms(self) -> List[str]:
-        return list(self.keys())
+        return list(self)
 
     def __str__(self) -> str:
-        return "Registered Algorithms: {}".format(", ".join(self.keys()))
+        return "Registered Algorithms: " + ", ".join(self)
 
 
 GlobalAlgorithmRegistry = _AlgorithmRegistry()
