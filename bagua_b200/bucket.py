@@ -161,6 +161,9 @@ class BaguaBucket:
         self._group = group
         self.padding_tensor = None
         eff0 = self.tensors[0].bagua_getter_closure()
+        kinds = {(t.bagua_getter_closure().dtype, t.bagua_getter_closure().device) for t in self.tensors}
+        if len(kinds) > 1:   # the reference's backend rejects such a bucket as well (bagua-core-internal/src/datatypes/mod.rs:1135-1147)
+            raise ValueError(f"bucket {name!r}: all tensors of a bucket must share one dtype and one device, got {sorted(str(k) for k in kinds)}")
         if alignment > 1:
             padding = sum(t.bagua_getter_closure().numel() for t in self.tensors) % alignment
             if padding > 0:

@@ -445,3 +445,22 @@ def test_public_signatures_accept_the_reference_parameter_names():
                 checked += 1
     assert not problems, problems
     assert checked > 150
+
+
+def _mixed_bucket_worker(rank, world):
+    import bagua_b200 as bagua
+    from bagua_b200.bucket import BaguaBucket
+
+    bagua.init_process_group()
+    a = torch.zeros(4).ensure_bagua_tensor("a", "m")
+    b = torch.zeros(4, dtype=torch.float16).ensure_bagua_tensor("b", "m")
+    try:
+        BaguaBucket([a, b], flatten=True, name="mixed")
+    except ValueError as e:
+        return "share one dtype" in str(e)
+    return False
+
+
+def test_a_bucket_rejects_mixed_dtypes_with_a_clear_message():
+    """a bucket mixes tensors of one dtype only (the reference's backend rejects mixed dtype / device)."""
+    assert all(run_distributed(_mixed_bucket_worker, world=1))
