@@ -155,6 +155,24 @@ PYBIND11_MODULE(_C, m) {
                  return out;
              },
              py::arg("reset") = false)
+        .def("set_timeline", &Backend::set_timeline)
+        .def("timeline_ms_of_event", &Backend::timeline_ms_of_event)
+        .def("timeline_ref_ns", &Backend::timeline_ref_ns)
+        .def("pop_bucket_timeline",
+             [](Backend& b) {
+                 py::list out;
+                 for (auto& s : b.pop_bucket_timeline()) {
+                     py::dict d;
+                     d["bucket"] = s.name;
+                     d["iteration"] = s.iteration;
+                     d["issue_ns"] = s.issue_ns;
+                     d["start_ms"] = s.start_ms;
+                     d["device_ms"] = s.device_ms;
+                     d["queue_ms"] = s.queue_ms;
+                     out.append(d);
+                 }
+                 return out;
+             })
         .def("pop_ready_spans",
              [](Backend& b) {
                  py::list out;

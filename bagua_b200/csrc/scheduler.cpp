@@ -98,6 +98,8 @@ void Backend::shutdown() {
         std::lock_guard<std::mutex> plk(prof_mu_);
         for (auto e : timing_pool_) cudaEventDestroy(E(e));
         timing_pool_.clear();
+        if (timeline_ref_) cudaEventDestroy(E(timeline_ref_));
+        timeline_ref_ = nullptr;
         for (auto& smp : prof_pending_) {
             if (smp.start) cudaEventDestroy(E(smp.start));
             if (smp.stop) cudaEventDestroy(E(smp.stop));
@@ -150,8 +152,18 @@ std::vector<BucketStat> Backend::bucket_stats(bool reset) {
                 f = 0.f;
             }
             ms = f;
+            if (timeline_.load(std::memory_order_relaxed) && timeline_ref_ && timeline_samples_.size() < kTimelineCap) {
+                float off = 0.f;
+                if (cudaEventElapsedTime(&off, E(timeline_ref_), E(smp.start)) != cudaSuccess) {
+                    (void)cudaGetLastError();   // the reference event belongs to a later set_timeline(true): sample predates it
+                    off = -1.f;
+                }
+                if (off >= 0.f) timeline_samples_.push_back(BucketSample{smp.name, smp.iteration, smp.issue_ns, off, ms, smp.queue_ms});
+            }
             timing_pool_.push_back(smp.start);
             timing_pool_.push_back(smp.stop);
+        } else if (timeline_.load(std::memory_order_relaxed) && timeline_samples_.size() < kTimelineCap && smp.issue_ns >= timeline_ref_ns_) {
+            timeline_samples_.push_back(BucketSample{smp.name, smp.iteration, smp.issue_ns, (smp.issue_ns - timeline_ref_ns_) / 1e6, ms, smp.queue_ms});
         }
         auto it = prof_stats_.find(smp.name);
         if (it != prof_stats_.end()) {
@@ -209,6 +221,7 @@ void Backend::register_ordered_buckets(std::vector<std::shared_ptr<Bucket>> buck
     cv_done_.wait(lk, [this] { return (queue_.empty() && !in_flight_) || stop_; });
     ordered_.clear();
     owner_.clear();
+    first_bucket_ = buckets.empty() ? nullptr : buckets.front().get();
     for (auto& b : buckets) {
         b->pending_ = 0;
         b->producer_stream_set_ = false;
@@ -295,6 +308,7 @@ void Backend::schedule_locked(std::unique_lock<std::mutex>& lk) {
         b->user_events_.clear();
         b->producer_stream_set_ = false;
         tk->t_sched = std::chrono::steady_clock::now();
+        tk->iteration = iteration_;
         bool issue_inline = inline_.load(std::memory_order_relaxed) && queue_.empty() && !in_flight_;
         if (issue_inline)
             for (auto& op : b->ops()) issue_inline = issue_inline && !op->host_blocking();
@@ -304,7 +318,7 @@ void Backend::schedule_locked(std::unique_lock<std::mutex>& lk) {
             not_waited_.push_back(tk);
             scheduled_total_++;
             inline_total_++;
-            if (b == ordered_.front()) iteration_++;
+            if (ordered_.front().get() == first_bucket_) iteration_++;  // the last bucket of the registered order: the step's program is complete
             in_flight_ = tk;
             int prev_dev = -1;
             if (device_ >= 0 && cudaGetDevice(&prev_dev) == cudaSuccess && prev_dev != device_) cudaSetDevice(device_);
@@ -319,7 +333,7 @@ void Backend::schedule_locked(std::unique_lock<std::mutex>& lk) {
         queue_.push_back(tk);
         not_waited_.push_back(tk);
         scheduled_total_++;
-        if (b == ordered_.front()) iteration_++;  // wrapped around the whole list (single bucket case)
+        if (ordered_.front().get() == first_bucket_) iteration_++;  // wrapped around the whole registered order (also the single-bucket case)
         cv_worker_.notify_one();
     }
 }
@@ -333,6 +347,8 @@ void Backend::issue_ticket(const std::shared_ptr<Ticket>& tk) {
         std::chrono::steady_clock::time_point t_issue;
         if (prof) {
             t_issue = std::chrono::steady_clock::now();
+            smp.issue_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(t_issue.time_since_epoch()).count();
+            smp.iteration = tk->iteration;
             smp.name = tk->bucket->name();
             smp.queue_ms = std::chrono::duration<double, std::milli>(t_issue - tk->t_sched).count();
             if (device_ >= 0) {
@@ -473,6 +489,43 @@ size_t Backend::wait_pending_comm_ops(StreamHandle consumer, bool host_sync) {
     }
     if (!err.empty()) throw std::runtime_error(err);
     return n;
+}
+
+void Backend::set_timeline(bool on) {
+    if (on) {
+        std::lock_guard<std::mutex> lk(prof_mu_);
+        timeline_samples_.clear();
+        timeline_ref_ns_ = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+        if (device_ >= 0) {
+            if (!timeline_ref_) {
+                cudaEvent_t e;
+                BAGUA_CUDA_CHECK(cudaEventCreate(&e));
+                timeline_ref_ = reinterpret_cast<EventHandle>(e);
+            }
+            BAGUA_CUDA_CHECK(cudaEventRecord(E(timeline_ref_), S(stream_)));
+        }
+    }
+    if (on && !timeline_.load()) profile_before_timeline_ = profile_.load();
+    timeline_ = on;
+    profile_ = on ? true : profile_before_timeline_;   // switching the timeline off leaves a comm_profile() the user had on untouched
+}
+
+std::vector<BucketSample> Backend::pop_bucket_timeline() {
+    (void)bucket_stats(false);   // resolves the samples whose kernels have finished
+    std::lock_guard<std::mutex> lk(prof_mu_);
+    std::vector<BucketSample> out;
+    out.swap(timeline_samples_);
+    return out;
+}
+
+double Backend::timeline_ms_of_event(uint64_t cuda_event_ptr) {
+    if (device_ < 0 || !timeline_.load() || !timeline_ref_ || cuda_event_ptr == 0) return -1.0;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, E(timeline_ref_), reinterpret_cast<cudaEvent_t>(cuda_event_ptr)) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return -1.0;
+    }
+    return ms;
 }
 
 std::vector<ReadySpan> Backend::pop_ready_spans() {

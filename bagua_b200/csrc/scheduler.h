@@ -145,6 +145,19 @@ struct BucketStat {
     double queue_ms = 0.0;  // sum of (issue time − schedule time) on the host
 };
 
+// One execution of one bucket's op list on the communication stream (opt-in, Backend::set_timeline): when the host issued it
+// (steady clock), when it began on the device relative to the moment the timeline was switched on, how long it ran there and
+// how long it had waited in the host queue. This is the per-bucket timeline that says which bucket's communication is exposed
+// after backward has ended (bagua_b200.utils.trace.export_chrome_trace puts it next to the tensor-ready marks).
+struct BucketSample {
+    std::string name;
+    uint64_t iteration = 0;
+    int64_t issue_ns = 0;      // steady clock, ns
+    double start_ms = 0.0;     // device timeline (GPU backend) or host timeline (CPU backend), 0 = set_timeline(true)
+    double device_ms = 0.0;
+    double queue_ms = 0.0;
+};
+
 struct ReadySpan {
     std::string tensor_name;
     int64_t t_ns;     // steady clock, ns
@@ -174,6 +187,14 @@ public:
     std::vector<ReadySpan> pop_ready_spans();
     void set_record_spans(bool on) { record_spans_ = on; }
     void set_profile(bool on) { profile_ = on; }
+    // Keep every resolved profile sample (bounded) for pop_bucket_timeline(); implies set_profile(on). On the GPU backend a
+    // reference event is recorded on the comm stream so that every sample gets a device-time offset.
+    void set_timeline(bool on);
+    std::vector<BucketSample> pop_bucket_timeline();
+    // Device time (ms) between the timeline's reference event and a caller's CUDA event (e.g. "backward ended" recorded on the
+    // compute stream); -1 when the timeline is off, the event has not completed yet or this is the CPU backend.
+    double timeline_ms_of_event(uint64_t cuda_event_ptr);
+    int64_t timeline_ref_ns() const { return timeline_ref_ns_; }
     // Inline issue: a bucket whose program consists of native (asynchronously launching) ops only is issued by the thread
     // that marks its last tensor ready instead of being handed to the worker thread — no thread hand-off on the critical
     // path, and every CUDA call happens on the marking thread, which is what a stream capture (CUDA graph) needs. Order is
@@ -201,6 +222,7 @@ private:
         bool failed = false;
         std::string error;
         std::chrono::steady_clock::time_point t_sched;
+        uint64_t iteration = 0;                 // training iteration the bucket belongs to (copied under mu_)
     };
 
     void schedule_locked(std::unique_lock<std::mutex>& lk);
@@ -225,7 +247,15 @@ private:
         EventHandle start = nullptr, stop = nullptr;  // GPU backend
         double host_ms = -1.0;                        // CPU backend
         double queue_ms = 0.0;
+        int64_t issue_ns = 0;
+        uint64_t iteration = 0;
     };
+    std::atomic<bool> timeline_{false};
+    bool profile_before_timeline_ = false;
+    EventHandle timeline_ref_ = nullptr;              // GPU backend: recorded on the comm stream by set_timeline(true)
+    int64_t timeline_ref_ns_ = 0;
+    std::vector<BucketSample> timeline_samples_;      // guarded by prof_mu_, capped at kTimelineCap entries
+    static constexpr size_t kTimelineCap = 1 << 16;
     std::mutex prof_mu_;
     std::deque<ProfSample> prof_pending_;
     std::vector<EventHandle> timing_pool_;
@@ -248,7 +278,8 @@ private:
     std::vector<ReadySpan> spans_;
     std::string watchdog_error_;
     std::atomic<uint64_t> scheduled_total_{0};
-    uint64_t iteration_ = 0;
+    uint64_t iteration_ = 0;            // complete passes over the registered bucket order (tags ready spans and timeline samples)
+    const Bucket* first_bucket_ = nullptr;  // head of the registered order: the deque is back at it when a pass is complete
     bool stop_ = false;
     std::thread worker_;
     std::thread watchdog_;

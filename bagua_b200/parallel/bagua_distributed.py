@@ -62,6 +62,26 @@ class _States:
     """Bookkeeping object stored on the wrapped module (so a second ``with_bagua`` can undo the first)."""
 
 
+def summarize_timeline(buckets: List[dict], step_begin: List[dict], backward_end: List[dict]) -> List[dict]:
+    """Per training step: when backward ended, when the last bucket's communication ended, the part of it that was NOT hidden behind
+    backward (``exposed_ms``) and the bucket that finished last.  A step is the window from its begin mark (forward-pre hook) to the
+    next step's; bucket executions and the backward-end mark are assigned to the window they start in.  Steps without a backward
+    (evaluation forward in train mode) or without communication (``no_sync``) are skipped."""
+    begins = sorted(step_begin, key=lambda m: m["ms"])
+    out = []
+    for i, b in enumerate(begins):
+        lo, hi = b["ms"], (begins[i + 1]["ms"] if i + 1 < len(begins) else float("inf"))
+        mine = [x for x in buckets if lo <= x["start_ms"] < hi]
+        ends = [m for m in backward_end if lo <= m["ms"] < hi]
+        if not mine or not ends:
+            continue
+        last = max(mine, key=lambda x: x["start_ms"] + x["device_ms"])
+        comm_end, bwd_end = last["start_ms"] + last["device_ms"], ends[-1]["ms"]
+        out.append({"step": b["step"], "begin_ms": lo, "backward_end_ms": bwd_end, "comm_end_ms": comm_end, "exposed_ms": max(0.0, comm_end - bwd_end),
+                    "last_bucket": last["bucket"], "buckets": len(mine), "comm_busy_ms": sum(x["device_ms"] for x in mine)})
+    return out
+
+
 class BaguaDistributedDataParallel:
     """The data-parallel engine behind ``module.with_bagua`` / ``DistributedDataParallel`` (reference
     bagua/torch_api/data_parallel/bagua_distributed.py:27-505): builds the tensor list and the buckets with the algorithm, installs
@@ -137,6 +157,8 @@ class BaguaDistributedDataParallel:
             ddp.autograd_graph_params.clear()
             if mod.training:
                 ddp.bagua_train_step_counter += 1
+                if getattr(ddp, "_timeline_on", False):
+                    ddp._timeline_mark("begin")
                 if ddp.bagua_algorithm.need_reset():
                     ddp._bagua_init_algorithm()
                 ddp._fwd_pre_hook(inputs)
@@ -443,6 +465,56 @@ class BaguaDistributedDataParallel:
         if enable:
             self._bagua_backend.bucket_stats(True)
 
+    def comm_timeline(self, enable: bool = True):
+        """Start / stop recording the per-bucket timeline: every execution of every bucket's op list with its start on the
+        communication stream's device timeline and its duration (``Backend::set_timeline``), the moment backward ended on the compute
+        stream in the same timebase, and the tensor-ready marks.  Off by default; costs two event records per bucket launch and one
+        per step.  Read it with :meth:`comm_timeline_collect` or ``bagua_b200.utils.trace.export_chrome_trace``."""
+        self._timeline_marks = []
+        self._timeline_on = bool(enable)
+        self._bagua_backend.set_record_spans(bool(enable) or self._bagua_autotune_client is not None)
+        self._bagua_backend.set_timeline(bool(enable))
+
+    def _timeline_mark(self, kind: str):
+        """``kind`` = "begin" (forward-pre hook of a training step) or "backward_end" (post-backward hook, BEFORE the algorithm waits for
+        communication).  No synchronisation: an event on the compute stream, or a host time stamp on the CPU backend."""
+        marks = self._timeline_marks
+        if len(marks) >= 16384:
+            return
+        if self._on_cuda:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream())
+            marks.append((self.bagua_train_step_counter, kind, ev, None))
+        else:
+            marks.append((self.bagua_train_step_counter, kind, None, time.monotonic_ns()))
+
+    def comm_timeline_collect(self) -> dict:
+        """Everything recorded since :meth:`comm_timeline` was switched on (and not collected yet):
+        ``{"buckets": [{bucket, iteration, issue_ns, start_ms, device_ms, queue_ms}], "backward_end": [{step, ms}],
+        "ready": [{tensor, iteration, ms}], "steps": [{step, backward_end_ms, comm_end_ms, exposed_ms, last_bucket}]}`` — ``ms`` values
+        share one timebase (device time of the comm stream's reference event on GPUs, the host's monotonic clock on CPUs; tensor-ready
+        marks are host times shifted to the same zero).  ``exposed_ms`` is how long communication ran on after backward had ended.
+        Call after a ``torch.cuda.synchronize()`` — kernels still in flight are reported by the next call."""
+        be = self._bagua_backend
+        buckets = list(be.pop_bucket_timeline())
+        ref_ns = be.timeline_ref_ns()
+        resolved, keep = {"begin": [], "backward_end": []}, []
+        for step, kind, ev, host_ns in getattr(self, "_timeline_marks", []):
+            if ev is None:
+                if host_ns >= ref_ns:
+                    resolved[kind].append({"step": step, "ms": (host_ns - ref_ns) / 1e6})
+            elif not ev.query():
+                keep.append((step, kind, ev, host_ns))      # still in flight: reported by the next call
+            else:
+                ms = be.timeline_ms_of_event(ev.cuda_event)
+                if ms >= 0:
+                    resolved[kind].append({"step": step, "ms": ms})
+        self._timeline_marks = keep
+        ready = [{"tensor": name, "iteration": int(it), "ms": (t - ref_ns) / 1e6} for name, t, it in be.pop_ready_spans() if t >= ref_ns] \
+            if self._bagua_autotune_client is None else []
+        return {"buckets": buckets, "step_begin": resolved["begin"], "backward_end": resolved["backward_end"], "ready": ready,
+                "steps": summarize_timeline(buckets, resolved["begin"], resolved["backward_end"])}
+
     def comm_report(self, reset: bool = False) -> List[dict]:
         """Per bucket: launches, mean / max device time of its op list, achieved GB/s over the bucket bytes (algorithmic
         bandwidth), mean host-side queueing delay and the kernel variant in use."""
@@ -576,6 +648,8 @@ class BaguaDistributedDataParallel:
                 st._bagua_autograd_hooks.append(p.register_post_accumulate_grad_hook(fast_factory(name, p) if fast else factory(name)))
 
     def _real_post_backward_hook(self):
+        if getattr(self, "_timeline_on", False):
+            self._timeline_mark("backward_end")
         self._post_backward_hook()
         if self._speed_metrics_switch_on:
             if self._on_cuda:

@@ -21,6 +21,7 @@ __all__ = [
     "average_by_removing_extreme_values",
     "align_size",
     "GraphedTrainStep",
+    "export_chrome_trace",
 ]
 
 LOGGER = logging.getLogger(__name__)   # reference utils.py:10
@@ -187,5 +188,9 @@ def __getattr__(name):  # lazy: utils.graph is only needed by scripts that captu
         from .graph import GraphedTrainStep
 
         return GraphedTrainStep
+    if name == "export_chrome_trace":
+        from .trace import export_chrome_trace
+
+        return export_chrome_trace
     raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
 

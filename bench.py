@@ -306,6 +306,43 @@ def measure(c, name, train_step, dev_batch, host_batches, to_model_format, per_s
             "host_issue_ms_per_step": host_ms}
 
 
+def timeline_probe(c, model, step_fn, dev_batch, finish, steps=6):
+    """AFTER the timed regions: a few more steps with the scheduler's per-bucket timeline on (engine.comm_timeline): when each bucket's
+    communication ran on the comm stream, when backward ended on the compute stream, and how many milliseconds of communication were NOT
+    hidden behind backward in each step — the attribution of the gap between N = 1 and N > 1.  Never fails the benchmark."""
+    try:
+        eng = model.bagua_ddp
+        torch = c.torch
+        eng.comm_timeline(True)
+        for _ in range(steps):
+            step_fn(*dev_batch)
+        if finish is not None:
+            finish()
+        if not c.cpu:
+            torch.cuda.synchronize()
+        tl = eng.comm_timeline_collect()
+        eng.comm_timeline(False)
+        rows = tl["steps"][1:] or tl["steps"]          # the first step after the switch pays for event creation
+        if not rows:
+            return {"steps": 0}
+        exposed = sorted(r["exposed_ms"] for r in rows)
+        last = {}
+        for r in rows:
+            last[r["last_bucket"]] = last.get(r["last_bucket"], 0) + 1
+        per_bucket = {}
+        for b in tl["buckets"]:
+            per_bucket.setdefault(b["bucket"], []).append(b["device_ms"])
+        return {"steps": len(rows), "exposed_ms_median": exposed[len(exposed) // 2], "exposed_ms_max": exposed[-1],
+                "comm_busy_ms_median": sorted(r["comm_busy_ms"] for r in rows)[len(rows) // 2],
+                "backward_end_to_step_begin_ms_median": sorted(r["backward_end_ms"] - r["begin_ms"] for r in rows)[len(rows) // 2],
+                "bucket_finishing_last": max(last, key=last.get), "buckets_per_step": rows[0]["buckets"],
+                "device_ms_per_bucket_median": {k: sorted(v)[len(v) // 2] for k, v in sorted(per_bucket.items())[:64]},
+                "what": "engine.comm_timeline: per-bucket device timeline of the comm stream vs the end of backward on the compute stream, "
+                        f"{len(rows)} untimed steps after the measurement"}
+    except Exception as e:  # noqa: BLE001 - diagnostics only
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
 def _bucket_programs(model):
     """The op list the scheduler runs per bucket, as the native core reports it (kinds such as ``allreduce_sgd``, ``bytegrad_fused``,
     ``allreduce_multimem``; a ``python`` entry would be a torch.distributed fallback) with how many buckets carry each program."""
@@ -472,6 +509,8 @@ def run_cnn(c, model_name):
             yield x_host[i % n_host], y_host[i % n_host]
 
     res = measure(c, model_name, step_fn, (x_dev, y_dev), host_batches, to_model_format, bs, "images/s", finish)
+    if args.impl != "ddp" and not args.cuda_graph:
+        res["comm_timeline"] = timeline_probe(c, model, step_fn, (x_dev, y_dev), finish)
     algo = "GradientAllReduce"
     res["metric"] = f"{model_name} synthetic-ImageNet training throughput ({algo})"
     res["config"] = dict(cfg, model=model_name, global_batch=bs * world, per_gpu_batch=bs, image=f"3x{img}x{img}", parallelism=f"dp{world}",
@@ -541,6 +580,8 @@ def run_bert(c):
             yield host[i % n_host]
 
     res = measure(c, "bert", train_step, dev_batch, host_batches, None, bs, "samples/s", finish)
+    if args.impl != "ddp":
+        res["comm_timeline"] = timeline_probe(c, model, train_step, dev_batch, finish)
     res["metric"] = f"BERT-large SQuAD-shaped fine-tuning throughput ({algo})"
     res["config"] = dict(cfg, model="bert-large (24 layers, hidden 1024, 16 heads, 335 M parameters) + QA head" if not cpu else "tiny bert (selftest)",
                          global_batch=bs * world, per_gpu_batch=bs, seq_len=seq, parallelism=f"dp{world}", algorithm=algo,
@@ -625,11 +666,13 @@ def main():
         }
         if "verify" in head:
             out["verify"] = head["verify"]
+        if "comm_timeline" in head:
+            out["comm_timeline"] = head["comm_timeline"]
         if "bert" in results and "error" in results["bert"]:
             out["bert_large_bytegrad"] = {"value": None, "error": results["bert"]["error"]}
         elif "bert" in results and head is not results["bert"]:
             b = results["bert"]
-            out["bert_large_bytegrad"] = {k: b[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "clocks", "e2e", "gpu_launches", "final_loss", "host_issue_ms_per_step")}
+            out["bert_large_bytegrad"] = {k: b[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "clocks", "e2e", "gpu_launches", "final_loss", "host_issue_ms_per_step", "comm_timeline") if k in b}
             out["bert_large_bytegrad"].update(n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), higher_is_better=True, scaling="weak", dtype=out["dtype"])
         for k, v in results.items():
             if v is not head and k != "bert":

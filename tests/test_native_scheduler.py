@@ -240,3 +240,85 @@ def test_graph_capturable_only_with_native_step_invariant_ops():
     b1.append_python_op(lambda name: None)            # python ops run on the worker thread: not capturable
     assert not be.graph_capturable()
     be.shutdown()
+
+
+def _timeline_worker(rank, world):
+    """comm_timeline on the CPU backend (host timebase): every bucket execution is a sample, backward-end marks line up with the steps,
+    the summary attributes the time communication ran on after backward, and the Chrome trace file carries all of it."""
+    import json
+    import os
+    import tempfile
+    import time
+
+    import torch
+    import torch.nn.functional as F
+
+    import bagua_b200 as bagua
+    from bagua_b200.parallel.algorithms import gradient_allreduce
+    from bagua_b200.utils import export_chrome_trace
+
+    bagua.init_process_group()
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.ReLU(), torch.nn.Linear(32, 32), torch.nn.ReLU(), torch.nn.Linear(32, 4))
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    os.environ["BAGUA_DEFAULT_BUCKET_SIZE"] = "2048"     # several buckets
+    net = net.with_bagua([opt], gradient_allreduce.GradientAllReduceAlgorithm())
+    eng = net.bagua_ddp
+    nb = len(net.bagua_buckets)
+    for _ in range(2):                                      # before the switch: must not show up
+        opt.zero_grad()
+        F.mse_loss(net(torch.randn(8, 16)), torch.zeros(8, 4)).backward()
+        opt.step()
+    eng.comm_timeline(True)
+    steps = 4
+    for _ in range(steps):
+        opt.zero_grad()
+        F.mse_loss(net(torch.randn(8, 16)), torch.zeros(8, 4)).backward()
+        opt.step()
+    time.sleep(0.05)
+    path = os.path.join(tempfile.mkdtemp(), f"trace{rank}.json")
+    tl = export_chrome_trace(net, path)
+    eng.comm_timeline(False)
+    again = eng.comm_timeline_collect()
+    with open(path) as f:
+        trace = json.load(f)
+    return nb, steps, tl, again, trace
+
+
+def test_comm_timeline_and_chrome_trace_on_the_cpu_backend():
+    from tests.mp_utils import run_distributed
+
+    for nb, steps, tl, again, trace in run_distributed(_timeline_worker, world=2):
+        assert nb >= 2
+        assert len(tl["buckets"]) == nb * steps and len(tl["backward_end"]) == steps and len(tl["steps"]) == steps
+        assert all(b["start_ms"] >= 0 and b["device_ms"] >= 0 and b["queue_ms"] >= 0 for b in tl["buckets"])
+        per_iter = {}
+        for b in tl["buckets"]:
+            per_iter.setdefault(b["iteration"], []).append(b["bucket"])
+        assert all(sorted(v) == sorted(per_iter[min(per_iter)]) and len(v) == nb for v in per_iter.values())
+        marks = [m["ms"] for m in tl["backward_end"]]
+        assert marks == sorted(marks) and [m["step"] for m in tl["backward_end"]] == list(range(3, 3 + steps))
+        for s in tl["steps"]:
+            assert s["buckets"] == nb and s["exposed_ms"] >= 0 and s["comm_end_ms"] >= 0 and abs(s["exposed_ms"] - max(0.0, s["comm_end_ms"] - s["backward_end_ms"])) < 1e-9
+            assert s["comm_busy_ms"] >= 0 and s["last_bucket"] in per_iter[min(per_iter)]
+        assert tl["ready"] and all(r["ms"] >= 0 for r in tl["ready"])
+        assert len(tl["step_begin"]) == steps and again["buckets"] == [] and again["backward_end"] == [] and again["step_begin"] == []          # collected once, and nothing is recorded after the switch-off
+        ev = trace["traceEvents"]
+        assert sum(e["ph"] == "X" and e["tid"] == 1 for e in ev) == nb * steps and sum(e["ph"] == "i" and e["tid"] == 2 for e in ev) == 2 * steps
+        assert any(e["ph"] == "M" and e["args"]["name"] == "comm stream" for e in ev) and len(trace["otherData"]["steps"]) == steps
+        slices = [e for e in ev if e["ph"] == "X" and e["tid"] == 1]
+        assert all("ops" in e["args"] and e["args"]["bytes"] > 0 for e in slices)
+
+
+def test_summarize_timeline_attributes_exposed_time_to_the_right_step():
+    from bagua_b200.parallel.bagua_distributed import summarize_timeline
+
+    buckets = [  # two steps, two buckets each; step 1 hides its communication, step 2 leaves 3 ms exposed in bucket "1"
+        {"bucket": "0", "iteration": 7, "start_ms": 1.0, "device_ms": 2.0}, {"bucket": "1", "iteration": 7, "start_ms": 4.0, "device_ms": 1.0},
+        {"bucket": "0", "iteration": 8, "start_ms": 21.0, "device_ms": 2.0}, {"bucket": "1", "iteration": 8, "start_ms": 29.0, "device_ms": 4.0},
+    ]
+    begins = [{"step": 11, "ms": 20.0}, {"step": 10, "ms": 0.0}, {"step": 12, "ms": 40.0}]     # step 12: a forward without backward
+    marks = [{"step": 11, "ms": 30.0}, {"step": 10, "ms": 10.0}]
+    out = summarize_timeline(buckets, begins, marks)
+    assert [(s["step"], s["exposed_ms"], s["last_bucket"], s["comm_busy_ms"]) for s in out] == [(10, 0.0, "1", 3.0), (11, 3.0, "1", 6.0)]
+    assert summarize_timeline(buckets, begins, []) == [] and summarize_timeline(buckets, [], marks) == []
