@@ -1,5 +1,6 @@
 // ThreadSanitizer stress of the C++ CommScheduler on the CPU backend: several producer threads mark tensors of many
 // buckets ready in random order while the worker executes callback ops and a consumer waits; checks ordering and counts.
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <memory>
@@ -30,6 +31,7 @@ int main() {
     be.set_watchdog_fatal(false);
     be.set_record_spans(true);
     be.set_profile(true);  // per-bucket statistics are read concurrently with the worker below
+    be.set_timeline(true); // ... and so is the per-bucket timeline (samples appended while the worker issues)
     std::vector<std::shared_ptr<Bucket>> buckets;
     std::vector<std::shared_ptr<Tensor>> tensors;
     std::vector<int> order;
@@ -80,6 +82,23 @@ int main() {
     }
     auto spans = be.pop_ready_spans();
     if (spans.empty()) ++failures;
+    // ready spans and timeline samples are tagged with the pass over the registered order they belong to
+    uint64_t max_iter = 0;
+    for (auto& sp : spans) max_iter = std::max<uint64_t>(max_iter, sp.iteration);
+    auto samples = be.pop_bucket_timeline();
+    std::vector<int> per_iter(kIters, 0);
+    for (auto& smp : samples) {
+        if (smp.iteration >= static_cast<uint64_t>(kIters) || smp.start_ms < 0 || smp.device_ms < 0) ++failures;
+        else per_iter[smp.iteration]++;
+    }
+    for (int it = 0; it < kIters; ++it)
+        if (per_iter[it] != kBuckets) ++failures;
+    if (samples.size() != static_cast<size_t>(kIters) * kBuckets || max_iter != static_cast<uint64_t>(kIters) - 1) {
+        std::fprintf(stderr, "timeline: %zu samples (expected %d), last span iteration %llu (expected %d)\n", samples.size(), kIters * kBuckets,
+                     static_cast<unsigned long long>(max_iter), kIters - 1);
+        ++failures;
+    }
+    be.set_timeline(false);
     uint64_t launches = 0;
     for (auto& st : be.bucket_stats(false)) launches += st.count;
     if (launches != static_cast<uint64_t>(kIters) * kBuckets) {
