@@ -334,7 +334,7 @@ def timeline_probe(c, model, step_fn, dev_batch, finish, steps=6):
             per_bucket.setdefault(b["bucket"], []).append(b["device_ms"])
         return {"steps": len(rows), "exposed_ms_median": exposed[len(exposed) // 2], "exposed_ms_max": exposed[-1],
                 "comm_busy_ms_median": sorted(r["comm_busy_ms"] for r in rows)[len(rows) // 2],
-                "backward_end_to_step_begin_ms_median": sorted(r["backward_end_ms"] - r["begin_ms"] for r in rows)[len(rows) // 2],
+                "step_begin_to_backward_end_ms_median": sorted(r["backward_end_ms"] - r["begin_ms"] for r in rows)[len(rows) // 2],
                 "bucket_finishing_last": max(last, key=last.get), "buckets_per_step": rows[0]["buckets"],
                 "device_ms_per_bucket_median": {k: sorted(v)[len(v) // 2] for k, v in sorted(per_bucket.items())[:64]},
                 "what": "engine.comm_timeline: per-bucket device timeline of the comm stream vs the end of backward on the compute stream, "
