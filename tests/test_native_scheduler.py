@@ -322,3 +322,62 @@ def test_summarize_timeline_attributes_exposed_time_to_the_right_step():
     out = summarize_timeline(buckets, begins, marks)
     assert [(s["step"], s["exposed_ms"], s["last_bucket"], s["comm_busy_ms"]) for s in out] == [(10, 0.0, "1", 3.0), (11, 3.0, "1", 6.0)]
     assert summarize_timeline(buckets, begins, []) == [] and summarize_timeline(buckets, [], marks) == []
+
+
+def test_timeline_gpu_branches_with_host_doubles(monkeypatch):
+    """The CUDA-side bookkeeping of the timeline (events recorded in the hooks, resolved against the scheduler's reference event, events
+    still in flight kept for the next collection) driven with stand-ins for ``torch.cuda.Event`` and the native backend."""
+    import types
+
+    import torch
+
+    from bagua_b200.parallel.bagua_distributed import BaguaDistributedDataParallel as Engine
+
+    class FakeEvent:
+        made = []
+
+        def __init__(self, enable_timing=False):
+            assert enable_timing
+            self.cuda_event, self.done, self.stream = 1000 + len(FakeEvent.made), True, None
+            FakeEvent.made.append(self)
+
+        def record(self, stream):
+            self.stream = stream
+
+        def query(self):
+            return self.done
+
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda: "compute-stream")
+
+    class FakeBackend:
+        def __init__(self):
+            self.calls = []
+
+        def pop_bucket_timeline(self):
+            return [{"bucket": "0", "iteration": 0, "issue_ns": 5, "start_ms": 2.0, "device_ms": 1.0, "queue_ms": 0.1},
+                    {"bucket": "1", "iteration": 0, "issue_ns": 6, "start_ms": 4.0, "device_ms": 3.0, "queue_ms": 0.1}]
+
+        def timeline_ref_ns(self):
+            return 100
+
+        def timeline_ms_of_event(self, ptr):
+            self.calls.append(ptr)
+            return {1000: 1.0, 1001: 5.0}.get(ptr, -1.0)     # begin at 1 ms, backward end at 5 ms; anything else unresolved
+
+        def pop_ready_spans(self):
+            return [("w", 50, 0), ("w", 2_000_100, 0)]       # the first one predates the reference
+
+    eng = types.SimpleNamespace(_bagua_backend=FakeBackend(), _timeline_marks=[], _on_cuda=True, bagua_train_step_counter=7, _bagua_autotune_client=None)
+    Engine._timeline_mark(eng, "begin")
+    Engine._timeline_mark(eng, "backward_end")
+    Engine._timeline_mark(eng, "begin")                      # next step has begun, its event is still in flight
+    FakeEvent.made[2].done = False
+    assert all(e.stream == "compute-stream" for e in FakeEvent.made) and [m[1] for m in eng._timeline_marks] == ["begin", "backward_end", "begin"]
+    tl = Engine.comm_timeline_collect(eng)
+    assert tl["step_begin"] == [{"step": 7, "ms": 1.0}] and tl["backward_end"] == [{"step": 7, "ms": 5.0}]
+    assert tl["ready"] == [{"tensor": "w", "iteration": 0, "ms": 2.0}]
+    assert len(eng._timeline_marks) == 1 and eng._timeline_marks[0][2] is FakeEvent.made[2]          # kept for the next collection
+    (step,) = tl["steps"]
+    assert step["step"] == 7 and step["exposed_ms"] == 2.0 and step["last_bucket"] == "1" and step["comm_busy_ms"] == 4.0 and step["buckets"] == 2
+    assert eng._bagua_backend.calls == [1000, 1001]
