@@ -21,6 +21,10 @@ Every N runs the SAME program: at N = 1 the engine is built in self-peer mode (`
 only peer), so the bucket kernels (reduce-scatter → optimizer → all-gather, fused ByteGrad) do at N = 1 exactly the per-GPU work
 they do at N = 8 — the scaling base is not flattered by a cheaper single-GPU code path.
 
+After each workload's timed regions six more steps run with the scheduler's per-bucket timeline on; the summary (``comm_timeline``:
+communication left exposed after backward, the bucket that finishes last, device time per bucket) explains the step time, it is
+not part of any timed region.  A failure of the second workload is reported in its block and does not take the first one's line with it.
+
 ``--selftest-cpu`` runs the same code end to end on the host with tiny shapes for the test-suite (marked ``selftest``).
 """
 from __future__ import annotations
