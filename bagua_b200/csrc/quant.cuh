@@ -45,6 +45,7 @@ struct QuantParams {
     float scale;
     float lower;
     float upper;
+    float inv_scale;   // correctly rounded 1/scale, computed once per chunk
 };
 
 __device__ __forceinline__ QuantParams make_quant(float mn, float mx) {
@@ -52,14 +53,24 @@ __device__ __forceinline__ QuantParams make_quant(float mn, float mx) {
     q.scale = __fdiv_rn(255.0f, __fadd_rn(__fsub_rn(mx, mn), 1e-7f));
     q.upper = rintf(__fmul_rn(mx, q.scale));
     q.lower = __fsub_rn(q.upper, 255.0f);
+    q.inv_scale = __frcp_rn(q.scale);
     return q;
 }
 __device__ __forceinline__ uint8_t quantize(float x, const QuantParams& q) {
     float level = fminf(rintf(__fmul_rn(x, q.scale)), q.upper);
     return static_cast<uint8_t>(__fsub_rn(level, q.lower));
 }
+// x' = (q + lower) / scale, evaluated as a multiplication by the chunk's reciprocal: an IEEE fp32 division is ~10 issue slots per
+// ELEMENT (MUFU.RCP + Newton steps + FCHK + slow-path call) and made up 39 % of the SASS of bytegrad_kernel<bf16, 8>, a kernel that ncu
+// shows to be instruction-issue bound (profiles/ncu_summary.md); the product differs from the quotient by at most one fp32 ulp, far below
+// a quantisation level, and every rank decodes with the same code, so replicas stay bit-identical. -DBAGUA_DEQUANT_IEEE_DIV restores the
+// division (bit-exact with the reference's formula, bagua_kernels.cu:456-501).
 __device__ __forceinline__ float dequantize(uint8_t v, const QuantParams& q) {
+#ifdef BAGUA_DEQUANT_IEEE_DIV
     return __fdiv_rn(__fadd_rn(static_cast<float>(v), q.lower), q.scale);
+#else
+    return __fmul_rn(__fadd_rn(static_cast<float>(v), q.lower), q.inv_scale);
+#endif
 }
 
 // Block-wide min/max of per-thread partials; result valid in thread 0.
