@@ -144,11 +144,20 @@ class ClockSampler:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         rows = self._parse()
-        sel = [r for r in rows if (begin is None or r[0] >= begin - 0.05) and (end is None or r[0] <= end + 0.05)]
         note = None
+        if not rows:   # the looping sampler delivered nothing (died, or an nvidia-smi that rejects the interval): ask once, now
+            try:
+                one = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=20).stdout
+                self._buf.extend(ln + "\n" for ln in one.splitlines() if ln.strip())
+                rows = self._parse()
+                note = "the looping sampler delivered no line; one query right after the timed region"
+            except Exception:  # noqa: BLE001
+                rows = []
+        sel = [r for r in rows if (begin is None or r[0] >= begin - 0.05) and (end is None or r[0] <= end + 0.05)]
         if not sel and rows and begin is not None:   # region shorter than the sampling period: take the two nearest samples
             sel = sorted(rows, key=lambda r: min(abs(r[0] - begin), abs(r[0] - end)))[:2]
-            note = "no sample inside the timed region (50 ms sampling period): nearest samples"
+            note = note or "no sample inside the timed region (50 ms sampling period): nearest samples"
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in sel for n, v in zip(names, r[4]) if v == "Active"})
         sm = sorted(r[1] for r in sel)

@@ -204,3 +204,46 @@ def test_bench_verify_accepts_the_right_update_and_rejects_a_wrong_one():
     model = build()
     with pytest.raises(SystemExit):
         bench.verify_fused_update(c, build, model, MasterSGD(model, 0.25), (x, y), loss_fn, 0.5)
+
+
+def test_clock_sampler_regions_nearest_samples_and_one_shot_fallback(tmp_path, monkeypatch):
+    """bench.py's nvidia-smi sampler against a stand-in ``nvidia-smi``: samples are selected by their own timestamps, a region shorter than
+    the sampling period takes the nearest samples, throttle reasons are collected, and a looping sampler that delivers nothing (an
+    nvidia-smi that rejects the interval) falls back to one query after the region."""
+    import datetime
+    import importlib.util
+    import time
+
+    spec = importlib.util.spec_from_file_location("bench_for_sampler_test", os.path.join(REPO, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    fake = tmp_path / "bin"
+    fake.mkdir()
+    smi = fake / "nvidia-smi"
+    # looping mode (-lms): print nothing and exit (as if the interval were rejected); one-shot mode: one line stamped "now"
+    smi.write_text("#!/bin/bash\nfor a in \"$@\"; do if [ \"$a\" = \"-lms\" ]; then exit 3; fi; done\n"
+                   "echo \"$(date '+%Y/%m/%d %H:%M:%S.%3N'), 1965, 1965, 612.5, Not Active, Not Active, Not Active, Active\"\n")
+    smi.chmod(0o755)
+    monkeypatch.setenv("PATH", str(fake) + os.pathsep + os.environ["PATH"])
+    s = bench.ClockSampler(0).start()
+    time.sleep(0.3)
+    t0 = time.time()
+    rec = s.stop(t0 - 0.01, t0)
+    assert rec["sm_mhz"] == 1965 and rec["sm_max_mhz"] == 1965 and rec["reasons"] == ["sw_power_cap"] and "one query" in rec["note"], rec
+
+    # timestamp selection and the upper-half rule on injected samples
+    s2 = bench.ClockSampler(0)
+    s2.proc = object()
+    base = time.time()
+
+    def line(dt, mhz, thermal="Not Active"):
+        ts = datetime.datetime.fromtimestamp(base + dt).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+        return f"{ts}, {mhz}, 1965, 500.0, Not Active, {thermal}, Not Active, Not Active\n"
+
+    s2._buf = [line(-5.0, 300), line(0.1, 1900), line(0.2, 1965), line(0.3, 1965), line(0.4, 1950), line(9.0, 210, "Active")]
+    inside = s2.summary(base, base + 0.5)
+    assert inside["samples"] == 4 and inside["sm_mhz"] == 1965 and inside["reasons"] == [] and "note" not in inside
+    short = s2.summary(base + 2.0, base + 2.01)
+    assert short["samples"] == 2 and "nearest samples" in short["note"]
+    hot = s2.summary(base + 8.9, base + 9.1)
+    assert hot["reasons"] == ["hw_thermal_slowdown"] and hot["sm_mhz"] == 210
