@@ -3,9 +3,11 @@
 // oracle tests/internal/compressor.py:4-33): scale = 255/(max-min+1e-7), upper = rint(max*scale),
 // lower = upper-255, q = min(rint(x*scale), upper) - lower, x' = (q + lower)/scale.
 #pragma once
+#ifndef BAGUA_QUANT_HOST_EMULATION
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#endif
 
 #include <cstdint>
 
@@ -56,9 +58,18 @@ __device__ __forceinline__ QuantParams make_quant(float mn, float mx) {
     q.inv_scale = __frcp_rn(q.scale);
     return q;
 }
+// float → uint8: on the device this is one saturating convert (an out-of-range value — the −1 that round-half-even can produce
+// at the lower end — becomes 0); the host emulation has to spell the saturation out because the C++ cast is undefined there.
+__device__ __forceinline__ uint8_t f32_to_u8_sat(float v) {
+#ifdef BAGUA_QUANT_HOST_EMULATION
+    return static_cast<uint8_t>(v < 0.f ? 0.f : (v > 255.f ? 255.f : v));
+#else
+    return static_cast<uint8_t>(v);
+#endif
+}
 __device__ __forceinline__ uint8_t quantize(float x, const QuantParams& q) {
     float level = fminf(rintf(__fmul_rn(x, q.scale)), q.upper);
-    return static_cast<uint8_t>(__fsub_rn(level, q.lower));
+    return f32_to_u8_sat(__fsub_rn(level, q.lower));
 }
 // x' = (q + lower) / scale, evaluated as a multiplication by the chunk's reciprocal: an IEEE fp32 division is ~10 issue slots per
 // ELEMENT (MUFU.RCP + Newton steps + FCHK + slow-path call) and made up 39 % of the SASS of bytegrad_kernel<bf16, 8>, a kernel that ncu
@@ -73,6 +84,7 @@ __device__ __forceinline__ float dequantize(uint8_t v, const QuantParams& q) {
 #endif
 }
 
+#ifndef BAGUA_QUANT_HOST_EMULATION   // tests/cpp/quant_emulation.cpp compiles the scalar math above for the host
 // Block-wide min/max of per-thread partials; result valid in thread 0.
 __device__ __forceinline__ void block_minmax(float& mn, float& mx) {
     __shared__ float s_mn[32], s_mx[32];
@@ -96,6 +108,8 @@ __device__ __forceinline__ void block_minmax(float& mn, float& mx) {
         }
     }
 }
+
+#endif  // BAGUA_QUANT_HOST_EMULATION
 
 }  // namespace dev
 }  // namespace bagua
