@@ -15,7 +15,10 @@ def main(argv=None):
     p.add_argument("--num-batches-per-iter", type=int, default=10)
     p.add_argument("--num-warmup-batches", type=int, default=10)
     p.add_argument("--algorithm", default="gradient_allreduce")
-    p.add_argument("--cpu", action="store_true")
+    p.add_argument("--cpu", "--no-cuda", dest="cpu", action="store_true", help="gloo + CPU tensors")
+    p.add_argument("--fp16-allreduce", action="store_true", default=False,
+                   help="communicate 16-bit gradients: the model runs in bf16 (GPU only), so the all-reduce moves half the bytes (the reference's flag, a Horovod leftover, has no effect there)")
+    p.add_argument("--use-adasum", action="store_true", default=False, help="accepted for command-line compatibility (Horovod leftover, no effect — as in the reference)")
     args = p.parse_args(argv)
 
     import torch
@@ -31,16 +34,21 @@ def main(argv=None):
     bagua.init_process_group()
     dev = torch.device("cuda", bagua.get_local_rank()) if cuda else torch.device("cpu")
     model = get_model(args.model).to(dev)
+    half = args.fp16_allreduce and cuda
+    if half:
+        model = model.to(torch.bfloat16)
     opt = torch.optim.SGD(model.parameters(), lr=0.01 * bagua.get_world_size())
     model = model.with_bagua([opt], Algorithm.init(args.algorithm))
     shape = (args.batch_size, 1, 28, 28) if args.model == "mnist" else (args.batch_size, 3, 224, 224)
     classes = 10 if args.model == "mnist" else 1000
     data, target = torch.randn(*shape, device=dev), torch.randint(0, classes, (args.batch_size,), device=dev)
+    if half:
+        data = data.to(torch.bfloat16)
 
     def step():
         opt.zero_grad()
         out = model(data)
-        loss = F.nll_loss(out, target) if args.model == "mnist" else F.cross_entropy(out, target)
+        loss = F.nll_loss(out.float(), target) if args.model == "mnist" else F.cross_entropy(out.float(), target)
         loss.backward()
         opt.step()
 
