@@ -123,6 +123,10 @@ def test_bench_contract_on_the_host(ranks, tmp_path):
     assert out["n_gpus"] == ranks and out["steps"] == 2 and out["value"] > 0 and out["selftest"]
     assert out["e2e"]["value"] > 0 and out["e2e"]["h2d_bytes_per_step"] == 2 * 3 * 32 * 32 * 4 + 2 * 8 and out["e2e"]["d2h_bytes_per_step"] == 4
     assert out["config"]["global_batch"] == 2 * ranks and out["config"]["parallelism"] == f"dp{ranks}"
+    # the post-measurement timeline probe (six untimed steps) reports how much communication stayed exposed after backward
+    for block in (out, out["bert_large_bytegrad"]):
+        tl = block["comm_timeline"]
+        assert "error" not in tl and tl["steps"] >= 3 and tl["exposed_ms_median"] >= 0 and tl["buckets_per_step"] >= 1 and tl["bucket_finishing_last"] in tl["device_ms_per_bucket_median"]
 
 
 def test_bench_reference_arm_reports_itself_unavailable(tmp_path):
