@@ -97,3 +97,81 @@ def test_the_grid_rendezvous_after_the_peer_barrier_is_load_bearing():
     for seed in range(300):
         found = found or run(2, 2, launches=2, rng=random.Random(seed), grid_after_peer=False)
     assert found is not None
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# lpdec_ring_kernel: ONE peer barrier per launch, the three-slot box double-buffered by launch parity
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ring(nranks, nb, launches, rng, double_buffered=True):
+    """Launch c: every CTA quantises its stripe of the difference and stores it into the LEFT neighbour's "from-right" slot, the RIGHT
+    neighbour's "from-left" slot and the own slot of box[parity(c)]; per-row peer barrier + grid rendezvous; every CTA reads its stripe
+    of the three slots of its own box.  There is no closing barrier: a fast rank enters launch c+1 while a neighbour still reads
+    launch c's slots — which is why the box has two halves."""
+    halves = 2 if double_buffered else 1
+    box = [[[[None] * nb for _ in range(3)] for _ in range(halves)] for _ in range(nranks)]     # [owner][half][slot][stripe]
+    flags = [[[0] * nranks for _ in range(nb)] for _ in range(nranks)]
+    grid_count, launch = [0] * nranks, [0] * nranks
+    program = ["send", "peer_arrive", "peer_wait", "grid", "receive"]
+
+    def fresh():
+        return [{"ip": 0, "waiting": None} for _ in range(nb)]
+
+    ctas = [fresh() for _ in range(nranks)]
+    steps = 0
+    while any(x < launches for x in launch):
+        steps += 1
+        assert steps < 300_000
+        runnable = []
+        for r in range(nranks):
+            if launch[r] >= launches:
+                continue
+            for b, cta in enumerate(ctas[r]):
+                if cta["ip"] >= len(program):
+                    continue
+                op = program[cta["ip"]]
+                if op == "grid" and cta["waiting"] is not None and grid_count[r] < cta["waiting"]:
+                    continue
+                if op == "peer_wait" and not all(flags[r][b][p] >= launch[r] + 1 for p in range(nranks)):
+                    continue
+                runnable.append((r, b))
+        r, b = rng.choice(runnable)
+        cta, c = ctas[r][b], launch[r]
+        op = program[cta["ip"]]
+        half = (c & 1) if double_buffered else 0
+        left, right = (r - 1) % nranks, (r + 1) % nranks
+        if op == "send":
+            box[left][half][1][b] = (r, c)       # the left neighbour's "from-right" slot
+            box[right][half][0][b] = (r, c)      # the right neighbour's "from-left" slot
+            box[r][half][2][b] = (r, c)
+        elif op == "peer_arrive":
+            for p in range(nranks):
+                flags[p][b][r] = c + 1
+        elif op == "grid":
+            if cta["waiting"] is None:
+                grid_count[r] += 1
+                cta["waiting"] = (c + 1) * nb
+                continue
+            cta["waiting"] = None
+        elif op == "receive":
+            want = ((left, c), (right, c), (r, c))
+            got = tuple(box[r][half][s][b] for s in range(3))
+            if got != want:
+                return f"rank {r} launch {c} row {b} received {got}, expected {want}"
+        cta["ip"] += 1
+        if all(x["ip"] >= len(program) for x in ctas[r]):
+            launch[r] += 1
+            ctas[r] = fresh()
+    return None
+
+
+@pytest.mark.parametrize("nranks,nb", [(2, 1), (2, 3), (3, 2), (4, 2)])
+def test_ring_box_halves_make_the_single_barrier_sufficient(nranks, nb):
+    for seed in range(120):
+        assert run_ring(nranks, nb, launches=4, rng=random.Random(seed)) is None
+
+
+def test_a_single_buffered_ring_box_is_caught():
+    found = None
+    for seed in range(300):
+        found = found or run_ring(3, 2, launches=3, rng=random.Random(seed), double_buffered=False)
+    assert found is not None
